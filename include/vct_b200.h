@@ -1,0 +1,183 @@
+/* vct_b200.h — C ABI of the B200-native per-frame GI pipeline (drop-in for the GL dispatch blocks of
+ * sfreed141/vct's Application::render, reference src/Application.cpp:196-1085).
+ *
+ * The reference has no plugin/FFI interface; the seam is the set of GL pass blocks inside render().  Each
+ * export below replaces exactly one of those blocks (file:line cited per function) and takes the same
+ * "uniforms" the block uploads, as one POD struct.  Conventions kept from the reference:
+ *   - matrices are column-major float[16] exactly as GLM stores them and glUniformMatrix4fv uploads them;
+ *   - the host computes every matrix uniform (projection, view, ls, inverse(ls), mvp_x/y/z, pv), as the
+ *     reference does on the CPU (src/Application.cpp:200-210, 689-692, 804);
+ *   - vertices are the reference's 56-byte `Vertex` (src/Graphics/Mesh.h:72-76), indices are uint32 in draw
+ *     order (per-material lists concatenated, src/Graphics/Mesh.cpp:340-371);
+ *   - lights are the 80-byte std140 records of src/Scene.cpp:64-76;
+ *   - never throws, never aborts: every call returns 0 on success, non-zero on error, and
+ *     vct_last_error() returns the message (reference logs and carries on, src/log.h:29-47);
+ *   - a context is NOT thread-safe: one host thread, in-order, like the single GL context.
+ * All device work is enqueued on the context's CUDA stream; calls that return data to the host synchronise.
+ * There is no CPU fallback: without a CUDA device vct_create fails.
+ */
+#ifndef VCT_B200_H
+#define VCT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCT_WARP_DIM 32            /* reference src/Application.h:178, shaders/generateWarpmap.geom:6 */
+#define VCT_MAX_LEVELS 12
+
+typedef struct vct_ctx vct_ctx;    /* opaque */
+
+/* Resources created once — reference `VCT` ctor + Application::init (src/Application.h:107-156,
+ * src/Application.cpp:37-70). */
+typedef struct {
+    int dim;            /* voxelDim (default 256)                          Application.h:133 */
+    int levels;         /* voxelLevels (default 6), clamped to [1, log2(dim)+1] like VCT::remake */
+    int shadow_size;    /* SHADOWMAP_WIDTH/HEIGHT (4096)                   Application.cpp:30-31 */
+    int width, height;  /* frame size                                      common.h:9-10 */
+    int device;         /* CUDA device ordinal */
+    /* z-slab sharding of the voxel volume across ranks; single GPU: rank 0 of 1. */
+    int rank, world_size;
+    int max_fragments;  /* capacity of the voxel-fragment buffer (0 = default 8 Mi) */
+} vct_config;
+
+/* 80-byte std140 light record — reference src/Scene.cpp:64-76, shaders/voxelize.frag:31-45. */
+typedef struct {
+    float position[3];  float _pad0;
+    float direction[3]; float _pad1;
+    float color[3];
+    float range;
+    float intensity;
+    int   enabled, selected, shadow_caster;
+    unsigned type;      /* 0 = point, 1 = directional */
+    float _pad2[3];
+} vct_light;
+
+/* Material as Mesh::draw binds it — reference src/Graphics/Mesh.cpp:326-360, Mesh.h:45-57.
+ * Texture ids are the ones given to vct_upload_texture; -1 = no map (GL handle 0). */
+typedef struct {
+    int   diffuse_tex, specular_tex, normal_tex, roughness_tex, metallic_tex, alpha_tex;
+    float shininess;
+    float diffuse[3];   /* always (0,0,0) in the reference (self-assignment bug, Mesh.h:34-43) */
+} vct_material;
+
+/* VoxelizeInfo SSBO — reference src/Application.h:195-198. */
+typedef struct { unsigned total_fragments, unique_voxels, max_fragments_per_voxel; } vct_voxelize_info;
+
+/* Cone settings — reference `VCTSettings`, src/Application.h:28-34, defaults :96-97. */
+typedef struct { int steps; float cone_angle, bias, cone_initial_height, lod_offset; } vct_cone_settings;
+
+/* Everything Application::render uploads as uniforms in one frame: `Settings` (src/Application.h:36-103),
+ * `VCT{min,max,center}` (:139-140) and the per-frame matrices. */
+typedef struct {
+    /* matrices (column-major) */
+    float projection[16];   /* perspective(fov, aspect, near, far)        Application.cpp:200 */
+    float view[16];         /* camera.lookAt()                            :201 */
+    float pv[16];           /* perspective(fov, aspect, 1, 20) * view     :202 */
+    float lp[16], lv[16];   /* light ortho / lookAt                       :208-209 */
+    float ls[16];           /* lp * lv                                    :210 */
+    float ls_inverse[16];   /* inverse(ls)                                :804 */
+    float mvp_x[16], mvp_y[16], mvp_z[16];   /* voxelisation views       :689-692 */
+    float eye[3];           /* camera.position */
+    float voxel_min[3], voxel_max[3], voxel_center[3];   /* vct.min/max/center (symmetric cube) */
+    float clear_color[3];   /* glClearColor                               :41 */
+    /* voxelisation — Settings */
+    int   voxelize_lighting;      /* true  */
+    int   voxelize_atomic_max;    /* reference default true; parity mode false */
+    int   axis_override;          /* -1 */
+    int   deterministic;          /* this build: 1 = apply running average in canonical draw order
+                                     (bit-reproducible), 0 = free-running CAS like the GLSL */
+    float voxel_set_opacity;      /* 0.5 */
+    int   temporal_filter_radiance; float temporal_decay;   /* false, 0.8 */
+    int   radiance_lighting;      /* false */
+    int   radiance_dilate;        /* false (malformed in the reference; rejected if set) */
+    int   voxel_fill_holes;       /* false */
+    int   mip_color_chain;        /* 1 = also filter voxelColor like the reference (:903-917) */
+    /* warp modes — common.glsl:44-60 */
+    int   warp_voxels, warp_texture, warp_texture_linear, warp_texture_axes[3];
+    int   use_warpmap_weights_texture;   /* true */
+    float warp_texture_high_resolution, warp_texture_low_resolution;   /* 2.0, 0.5 */
+    /* shading — phong.frag uniforms */
+    int   draw_radiance, draw_occlusion, cooktorrance, enable_postprocess, enable_normal_map;
+    int   enable_indirect, enable_diffuse, enable_specular, enable_reflections;
+    float ambient_scale, reflect_scale;
+    vct_cone_settings diffuse_cone, specular_cone;
+    int   specular_cone_angle_from_roughness;
+} vct_frame_params;
+
+/* GLBufferedTimer results in ns, same names as reference src/Application.h:192 (+ producers). */
+typedef struct {
+    double voxelize_ns, shadowmap_ns, radiance_ns, mipmap_ns, render_ns, total_ns;
+    double transfer_ns, gbuffer_ns, warpmap_ns, clear_ns, exchange_ns;
+} vct_timings;
+
+enum { VCT_VOL_COLOR = 0, VCT_VOL_NORMAL = 1, VCT_VOL_RADIANCE = 2, VCT_VOL_OCCUPANCY = 3, VCT_VOL_WARPMAP = 4,
+       VCT_VOL_WARP_WEIGHTS_LOW = 5, VCT_VOL_WARP_WEIGHTS_HIGH = 6 };
+
+/* ---- lifetime: VCT ctor/dtor/remake, Application::init --------------------------- Application.h:109-156 */
+int  vct_create(const vct_config* cfg, vct_ctx** out);
+int  vct_destroy(vct_ctx* ctx);
+int  vct_remake(vct_ctx* ctx, int dim, int levels);
+const char* vct_last_error(const vct_ctx* ctx);          /* ctx may be NULL: error of the last failed create */
+
+/* ---- scene upload: Mesh VAO/EBO/texture creation ------------------ Mesh.cpp:208-266, GLHelper.cpp:165-211 */
+int  vct_upload_mesh(vct_ctx*, int actor, const void* vertices, size_t n_vertices, size_t stride /*56*/,
+                     const uint32_t* indices, size_t n_indices, const int32_t* material_of_triangle);
+/* all mip levels packed back to back, level 0 first (the host generates them, like the DDS path
+ * ResourceLoader.h:94-103; glGenerateTextureMipmap's filter is implementation-defined) */
+int  vct_upload_texture(vct_ctx*, int tex, int width, int height, int channels, int levels, const void* pixels);
+int  vct_set_material(vct_ctx*, int material, const vct_material*);
+int  vct_set_actor_transform(vct_ctx*, int actor, const float model[16]);   /* Scene::draw "model" uniform, Scene.cpp:31-36 */
+int  vct_set_lights(vct_ctx*, const vct_light* lights, int n);              /* Scene::bindLightSSBO, Scene.cpp:58-62 */
+
+/* ---- one export per GL pass block of Application::render, same order ------------------------------------ */
+int  vct_shadowmap(vct_ctx*, const vct_frame_params*);     /* Application.cpp:212-233 */
+int  vct_occupancy(vct_ctx*, const vct_frame_params*);     /* :235-301  (32^3, imageAtomicOr) */
+int  vct_warpmap(vct_ctx*, const vct_frame_params*);       /* :303-577  (prefix sums + weights + warpmap, on device) */
+int  vct_voxelize(vct_ctx*, const vct_frame_params*);      /* :581-755  (clear + raster path) */
+int  vct_transfer(vct_ctx*, const vct_frame_params*);      /* :757-785 */
+int  vct_inject(vct_ctx*, const vct_frame_params*);        /* :787-837 */
+int  vct_fill_holes(vct_ctx*, const vct_frame_params*);    /* :839-875 */
+int  vct_mip(vct_ctx*, int which_volume);                  /* :877-921  (VCT_VOL_RADIANCE or VCT_VOL_COLOR) */
+int  vct_exchange(vct_ctx*);                               /* multi-GPU only: publish slab pyramid to the 3D texture
+                                                              after the caller's all-gather */
+int  vct_gbuffer(vct_ctx*, const vct_frame_params*);       /* :936-965  depth prepass -> visibility buffer */
+int  vct_cone_trace(vct_ctx*, const vct_frame_params*);    /* :967-1067 phong + cone tracing */
+int  vct_frame(vct_ctx*, const vct_frame_params*);         /* the whole graph, in reference order */
+int  vct_gi_passes(vct_ctx*, const vct_frame_params*);     /* the BASELINE metric's passes only:
+                                                              voxelize+transfer+inject(+fill)+mip+cone trace */
+
+/* ---- dead-shader equivalents (kernel parity only; the reference host never dispatches them) ------------- */
+int  vct_set_voxel_opacity(vct_ctx*, float opacity);       /* shaders/setVoxelOpacity.comp:18-35 */
+int  vct_temporal_radiance_filter(vct_ctx*, float decay);  /* shaders/temporalRadianceFilter.comp:9-19 */
+int  vct_filter3d(vct_ctx*, int which_volume, int src_level);  /* shaders/filter3d.comp:16-47 */
+int  vct_normalize_voxels_f16(vct_ctx*, void* color_rgba16f, void* normal_rgba16f, float opacity);
+                                                           /* shaders/normalizeVoxels.comp:19-42 on caller-provided
+                                                              DEVICE buffers of dim^3 half4 (USE_RGBA16F build) */
+
+/* ---- outputs ------------------------------------------------------------------------------------------- */
+int  vct_read_image(vct_ctx*, void* rgba8 /* width*height*4, row 0 = bottom like glReadPixels */);
+int  vct_read_volume(vct_ctx*, int which, int level, void* out);   /* RGBA8 words / u32 occupancy / u16x4 warpmap / f16x4 */
+int  vct_write_volume(vct_ctx*, int which, int level, const void* in);   /* test hook: seed a volume */
+int  vct_read_shadowmap(vct_ctx*, float* depth /* S*S */);
+int  vct_write_shadowmap(vct_ctx*, const float* depth);
+int  vct_read_visibility(vct_ctx*, uint64_t* vis /* W*H: depth bits << 32 | ~draw index */);
+int  vct_get_counters(vct_ctx*, vct_voxelize_info*);               /* Overlay.cpp:104-110 */
+int  vct_get_timings(vct_ctx*, vct_timings*);                      /* GLTimer.h:49-87 */
+int  vct_get_cone_steps(vct_ctx*, unsigned long long* steps);      /* texture fetches of the last cone trace */
+int  vct_sync(vct_ctx*);
+
+/* device pointers for zero-copy plumbing (torch.distributed all-gather of the pyramid, CUDA-GL interop) */
+void*  vct_device_ptr(vct_ctx*, int which, int level);
+size_t vct_level_bytes(vct_ctx*, int which, int level);
+void*  vct_stream(vct_ctx*);                                        /* cudaStream_t */
+/* kernels of this library launched since the last reset (bench.py's gpu_launches) */
+unsigned long long vct_launch_count(vct_ctx*, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCT_B200_H */

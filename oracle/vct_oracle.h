@@ -1,0 +1,82 @@
+/* vct_oracle.h — CPU ORACLE for the per-frame GI pipeline.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library; the product (vct_b200/) never links, imports or calls it.
+ *
+ * PARITY UNPINNED: the reference (sfreed141/vct @ c5c763d) has no tests, no golden vectors and cannot run in the
+ * build container or on the GPU box (no GL stack), so this oracle is a line-by-line restatement of the GLSL
+ * with OpenGL's semantics made explicit (DESIGN.md §"Canonical GL semantics").  It is pinned only by the
+ * known-answer values derived by hand from the reference's `#if 0` warp rig (src/main.cpp:20-127) and shader
+ * arithmetic, checked in tests/test_oracle_kat.py.
+ *
+ * POD parameter structs are shared with the product's public header (the boundary spec); no code is.
+ */
+#ifndef VCT_ORACLE_H
+#define VCT_ORACLE_H
+#include "../include/vct_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { int width, height, channels, levels; long long offset[16]; } orc_texture;
+
+typedef struct {
+    const float* vertices;            /* n_vertices x 14 (pos3 nrm3 uv2 tan3 bitan3) — Mesh.h:72-76 */
+    const int* vertex_actor;          /* n_vertices */
+    int n_vertices;
+    const unsigned* indices;          /* 3 x n_tris, global vertex ids, DRAW ORDER */
+    const int* tri_material;          /* n_tris */
+    int n_tris;
+    const float* actor_model;         /* n_actors x 16, column-major */
+    int n_actors;
+    const vct_material* materials; int n_materials;
+    const orc_texture* textures; int n_textures;
+    const unsigned char* texels;      /* blob the texture offsets index */
+    const vct_light* lights; int n_lights;
+} orc_scene;
+
+/* a0  shadow map — Application.cpp:212-233, simple.vert, reflectiveShadowMap.frag:34-38 */
+void orc_shadowmap(const orc_scene*, const vct_frame_params*, int S, float* depth);
+/* a1+a2 voxelise (raster path) — voxelize.vert/geom/frag.  warpmap = 32^3 x 4 u16 or NULL. */
+void orc_voxelize(const orc_scene*, const vct_frame_params*, int D, const float* shadow, int S,
+                  const unsigned short* warpmap, unsigned* color, unsigned* normal, vct_voxelize_info* info);
+/* a9(1) occupancy voxelise at 32^3 — voxelize.frag:187-193 */
+void orc_occupancy(const orc_scene*, const vct_frame_params*, unsigned* occ);
+/* a9(2-4) warpmap — Application.cpp:303-370 + generateWarpmap{Weights}.frag.  outputs 32^3 x 4 */
+void orc_warpmap(const unsigned* occ, const vct_frame_params*, unsigned short* warpmap,
+                 unsigned short* weights_low_f16, unsigned short* weights_high_f16);
+/* a3  transferVoxels.comp:29-70 (+ the radiance clear of Application.cpp:762-764) */
+void orc_transfer(const vct_frame_params*, int D, unsigned* color, unsigned* radiance, vct_voxelize_info* info);
+/* a5  injectRadiance.comp:40-103 */
+void orc_inject(const vct_frame_params*, int D, const unsigned* color, const unsigned* normal, const float* shadow,
+                int S, const unsigned short* warpmap, const float light_pos[3], const float light_int[3],
+                unsigned* radiance);
+/* a4  voxelFillHoles.comp:8-36 + copy back (Application.cpp:867-872) */
+void orc_fill_holes(int D, unsigned* radiance);
+/* a6  filterRadiance.comp:14-65; mode 0 BOX2, 1 BOX3, 2 CUBE.  src is Ds^3, dst is (Ds/2)^3 */
+void orc_mip(int Ds, const unsigned* src, unsigned* dst, int mode);
+/* dead variants */
+void orc_set_voxel_opacity(int D, float opacity, unsigned* color, unsigned* radiance, vct_voxelize_info* info);
+void orc_temporal_radiance_filter(int D, float decay, unsigned* vol);
+void orc_filter3d(int Ds, const unsigned* src, unsigned* dst);
+void orc_normalize_voxels_f16(int D, float opacity, unsigned short* color_f16, unsigned short* normal_f16,
+                              unsigned* radiance, vct_voxelize_info* info);
+/* a0' visibility — depth prepass + GL_EQUAL, Application.cpp:936-977, dither.frag */
+void orc_visibility(const orc_scene*, const vct_frame_params*, int W, int H, unsigned long long* vis);
+/* a7  phong.vert/frag incl. traceCone.  pyramids: levels packed back to back (level 0 first). */
+void orc_shade(const orc_scene*, const vct_frame_params*, int W, int H, const unsigned long long* vis,
+               int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
+               const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps);
+
+/* KAT helpers */
+unsigned orc_rgba8_avg(unsigned stored, float r, float g, float b);     /* voxelize.frag:111-139, one insertion */
+unsigned orc_pack_unorm4x8(float r, float g, float b, float a);
+void orc_warp_weight_table(int dim, float high, float low, float* low_out, float* high_out); /* Application.cpp:346-370 */
+float orc_cone_trace_const(int D, int L, unsigned voxel_word, const vct_cone_settings* cs, int* steps_out);
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
