@@ -1,0 +1,175 @@
+"""GPU parity: every pass of the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Gates (BASELINE.json north_star): occupancy mask bit-exact; RGBA8 volumes max|delta| <= 2/255 (this build's
+deterministic mode is expected to be bit-exact and the tests report the actual figure); final image PSNR >= 45 dB.
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import Oracle
+from vct_b200 import params as P
+from vct_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+D, L, SS, W, H = 64, 5, 512, 320, 240
+
+
+def max_byte_delta(a, b):
+    return int(np.abs(a.view(np.uint8).astype(np.int16) - b.view(np.uint8).astype(np.int16)).max()) if a.size else 0
+
+
+def psnr(a, b):
+    a = a.view(np.uint8).reshape(-1, 4)[:, :3].astype(np.float64); b = b.view(np.uint8).reshape(-1, 4)[:, :3].astype(np.float64)
+    mse = ((a - b) ** 2).mean()
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+@pytest.fixture(scope="module")
+def room():
+    from vct_b200.pipeline import Pipeline
+    sc = S.room_scene()
+    p = S.room_params(W, H)
+    o = Oracle(sc, D, L, SS, W, H)
+    g = Pipeline(sc, D, L, SS, W, H)
+    yield sc, p, o, g
+    g.close()
+
+
+def test_shadowmap_bit_exact(room):
+    sc, p, o, g = room
+    o.shadowmap(p); g.shadowmap(p)
+    got = g.read_shadowmap()
+    assert (o.shadow < 1).mean() > 0.05
+    assert np.array_equal(got.view(np.uint32), o.shadow.view(np.uint32)), f"{(got != o.shadow).sum()} texels differ"
+
+
+def test_voxelize_deterministic_bit_exact(room):
+    sc, p, o, g = room
+    o.voxelize(p); g.voxelize(p)
+    col, nrm = g.read_volume(P.VOL_COLOR), g.read_volume(P.VOL_NORMAL)
+    occ_o, occ_g = (o.color[0] >> 24) != 0, (col >> 24) != 0
+    assert occ_o.sum() > 1000
+    assert np.array_equal(occ_o, occ_g), "occupancy mask must be bit-exact"
+    assert g.counters().total_fragments == o.info.total_fragments
+    assert max_byte_delta(col, o.color[0]) <= 2 and max_byte_delta(nrm, o.normal) <= 2
+    assert np.array_equal(col, o.color[0]) and np.array_equal(nrm, o.normal), "deterministic mode is expected to be bit-exact"
+
+
+def test_transfer_inject_mip_bit_exact(room):
+    sc, p, o, g = room
+    o.transfer(p); g.transfer(p)
+    info = g.counters()
+    assert (info.unique_voxels, info.max_fragments_per_voxel) == (o.info.unique_voxels, o.info.max_fragments_per_voxel)
+    assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0])
+    assert np.array_equal(g.read_volume(P.VOL_RADIANCE), o.radiance[0])
+    o.inject(p); g.inject(p)
+    rad = g.read_volume(P.VOL_RADIANCE)
+    assert ((o.radiance[0] & 0xFFFFFF) != 0).sum() > 500
+    assert np.array_equal(rad, o.radiance[0])
+    o.mip("radiance"); o.mip("color"); g.mip(P.VOL_RADIANCE); g.mip(P.VOL_COLOR)
+    for l in range(1, L):
+        assert np.array_equal(g.read_volume(P.VOL_RADIANCE, l), o.radiance[l]), f"radiance level {l}"
+        assert np.array_equal(g.read_volume(P.VOL_COLOR, l), o.color[l]), f"colour level {l}"
+
+
+def test_visibility_bit_exact(room):
+    sc, p, o, g = room
+    o.visibility(p); g.gbuffer(p)
+    vis = g.read_visibility()
+    assert (o.vis != np.uint64(0xFFFFFFFFFFFFFFFF)).mean() > 0.5
+    assert np.array_equal(vis, o.vis), f"{(vis != o.vis).sum()} pixels differ"
+
+
+def test_final_image_psnr(room):
+    sc, p, o, g = room
+    o.shade(p); g.cone_trace(p)
+    img = g.read_image()
+    q = psnr(img, o.image)
+    steps = g.cone_steps()
+    print(f"PSNR {q:.2f} dB, max byte delta {max_byte_delta(img, o.image)}, cone steps gpu {steps} oracle {o.cone_steps}")
+    assert q >= 45.0
+    assert abs(steps - o.cone_steps) <= 0.01 * o.cone_steps
+
+
+def test_whole_frame_matches_pass_by_pass(room):
+    sc, p, o, g = room
+    before = g.read_image().copy()
+    g.frame(p)
+    assert np.array_equal(g.read_image(), before)
+    t = g.timings()
+    assert t["total_ns"] > 0
+
+
+def test_free_running_cas_mode_within_tolerance(room):
+    sc, p, o, g = room
+    q = type(p).from_buffer_copy(p); q.deterministic = 0
+    g.voxelize(q)
+    col = g.read_volume(P.VOL_COLOR)
+    o.voxelize(p)
+    assert np.array_equal((col >> 24), (o.color[0] >> 24)), "fragment counts per voxel are order independent"
+    d = np.abs(col.view(np.uint8).astype(np.int16) - o.color[0].view(np.uint8).astype(np.int16)).reshape(-1, 4)[:, :3]
+    frac = (d.max(1) <= 2).mean()
+    print(f"free-running CAS: {100 * frac:.3f}% of voxels within 2/255, max {d.max()}")
+    assert frac > 0.99
+    g.voxelize(p)
+
+
+def test_atomic_max_mode_bit_exact(room):
+    sc, p, o, g = room
+    q = type(p).from_buffer_copy(p); q.voxelize_atomic_max = 1
+    o.voxelize(q); g.voxelize(q)
+    assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0]) and np.array_equal(g.read_volume(P.VOL_NORMAL), o.normal)
+    o.voxelize(p); g.voxelize(p)
+
+
+def test_occupancy_and_warpmap_bit_exact(room):
+    sc, p, o, g = room
+    q = type(p).from_buffer_copy(p); q.warp_texture = 1
+    o.occupancy(q); g.occupancy(q)
+    assert o.occ.sum() > 50
+    assert np.array_equal(g.read_volume(P.VOL_OCCUPANCY), o.occ)
+    o.warpmap_pass(q); g.warpmap(q)
+    assert np.array_equal(g.read_volume(P.VOL_WARP_WEIGHTS_LOW), o.wlo) and np.array_equal(g.read_volume(P.VOL_WARP_WEIGHTS_HIGH), o.whi)
+    assert np.array_equal(g.read_volume(P.VOL_WARPMAP), o.warpmap)
+
+
+def test_warped_frame(room):
+    sc, p, o, g = room
+    q = type(p).from_buffer_copy(p); q.warp_texture = 1; q.temporal_filter_radiance = 1
+    for _ in range(2):                       # temporal filter: two frames of history
+        o.frame(q); g.frame(q)
+    assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0])
+    assert np.array_equal(g.read_volume(P.VOL_RADIANCE), o.radiance[0])
+    assert psnr(g.read_image(), o.image) >= 45.0
+    o.frame(p); g.frame(p)
+
+
+def test_fill_holes_and_dead_variants(room):
+    sc, p, o, g = room
+    o.frame(p); g.frame(p)
+    o.fill_holes(); g.fill_holes(p)
+    assert np.array_equal(g.read_volume(P.VOL_RADIANCE), o.radiance[0])
+    from tests.oracle_lib import lib, ptr
+    import ctypes as C
+    lib().orc_temporal_radiance_filter(D, 0.8, ptr(o.radiance[0])); g._ck(g.lib.vct_temporal_radiance_filter(g.h, 0.8))
+    assert np.array_equal(g.read_volume(P.VOL_RADIANCE), o.radiance[0])
+    info = P.VoxelizeInfo()
+    lib().orc_set_voxel_opacity(D, 0.25, ptr(o.color[0]), ptr(o.radiance[0]), C.byref(info)); g._ck(g.lib.vct_set_voxel_opacity(g.h, 0.25))
+    assert np.array_equal(g.read_volume(P.VOL_RADIANCE), o.radiance[0]) and np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0])
+    assert g.counters().unique_voxels == info.unique_voxels
+    dst = np.zeros((D // 2) ** 3, np.uint32)
+    lib().orc_filter3d(D, ptr(o.radiance[0]), ptr(dst)); g._ck(g.lib.vct_filter3d(g.h, P.VOL_RADIANCE, 0))
+    assert np.array_equal(g.read_volume(P.VOL_RADIANCE, 1), dst)
+    for mode in (1, 2):                      # BOX3 / CUBE kernel modes exist behind a uniform the host never sets
+        pass
+
+
+def test_error_paths(room):
+    sc, p, o, g = room
+    from vct_b200.lib import VctError
+    with pytest.raises(VctError):
+        g.read_volume(P.VOL_RADIANCE, 99)
+    q = type(p).from_buffer_copy(p); q.radiance_dilate = 1
+    with pytest.raises(VctError):
+        g.inject(q)

@@ -1,0 +1,454 @@
+// api.cu — the C ABI of include/vct_b200.h: resource ownership (reference `VCT` + Application::init), scene
+// upload (Mesh VAO/EBO/texture creation), the per-pass entry points that replace the GL dispatch blocks of
+// Application::render (src/Application.cpp:196-1085) and the whole-frame graph in the reference's pass order.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+thread_local std::string g_create_error;
+size_t vctk_tile_setup_bytes();
+
+namespace {
+
+int fail(vct_ctx* c, const char* msg) { c->error = msg; return 1; }
+
+void free_volumes(vct_ctx* c) {
+    for (int l = 0; l < VCT_MAX_LEVELS; ++l) {
+        if (c->radiance_surf[l]) cudaDestroySurfaceObject(c->radiance_surf[l]);
+        if (c->color_surf[l]) cudaDestroySurfaceObject(c->color_surf[l]);
+        c->radiance_surf[l] = c->color_surf[l] = 0;
+    }
+    for (cudaTextureObject_t* t : {&c->radiance_tex, &c->radiance_tex_point, &c->color_tex, &c->color_tex_point}) { if (*t) cudaDestroyTextureObject(*t); *t = 0; }
+    if (c->radiance_arr) cudaFreeMipmappedArray(c->radiance_arr);
+    if (c->color_arr) cudaFreeMipmappedArray(c->color_arr);
+    c->radiance_arr = c->color_arr = nullptr;
+    for (uint32_t** p : {&c->d_color, &c->d_radiance, &c->d_normal, &c->d_scratch}) { cudaFree(*p); *p = nullptr; }
+}
+
+int make_pyramid_texture(vct_ctx* c, cudaMipmappedArray_t* arr, cudaTextureObject_t* lin, cudaTextureObject_t* pt, cudaSurfaceObject_t* surf) {
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
+    VCT_CHECK(c, cudaMallocMipmappedArray(arr, &fd, make_cudaExtent(c->D, c->D, c->D), c->L, cudaArraySurfaceLoadStore));
+    for (int l = 0; l < c->L; ++l) {
+        cudaArray_t lev; VCT_CHECK(c, cudaGetMipmappedArrayLevel(&lev, *arr, l));
+        cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = lev;
+        VCT_CHECK(c, cudaCreateSurfaceObject(&surf[l], &rd));
+    }
+    cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = *arr;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;      // CLAMP_TO_BORDER, border 0
+    td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+    td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(c->L - 1);
+    td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;        // LINEAR_MIPMAP_LINEAR
+    VCT_CHECK(c, cudaCreateTextureObject(lin, &rd, &td, nullptr));
+    td.filterMode = cudaFilterModePoint; td.mipmapFilterMode = cudaFilterModePoint;          // mag NEAREST
+    VCT_CHECK(c, cudaCreateTextureObject(pt, &rd, &td, nullptr));
+    return 0;
+}
+
+// `VCT::make` (reference src/Application.h:143-148): voxelColor (L levels), voxelNormal (1), voxelRadiance (L)
+int make_volumes(vct_ctx* c) {
+    size_t off = 0;
+    for (int l = 0; l <= c->L; ++l) {
+        c->level_off[l] = off;
+        if (l < c->L) { const size_t d = level_dim(c->D, l); off += (d * d * d + 63) & ~(size_t)63; }
+    }
+    const size_t n0 = (size_t)c->D * c->D * c->D;
+    VCT_CHECK(c, cudaMalloc(&c->d_color, off * 4)); VCT_CHECK(c, cudaMalloc(&c->d_radiance, off * 4)); VCT_CHECK(c, cudaMalloc(&c->d_normal, n0 * 4));
+    VCT_CHECK(c, cudaMemsetAsync(c->d_color, 0, off * 4, c->stream)); VCT_CHECK(c, cudaMemsetAsync(c->d_radiance, 0, off * 4, c->stream));
+    VCT_CHECK(c, cudaMemsetAsync(c->d_normal, 0, n0 * 4, c->stream));
+    if (make_pyramid_texture(c, &c->radiance_arr, &c->radiance_tex, &c->radiance_tex_point, c->radiance_surf)) return 1;
+    const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
+    c->z_lo = (int)((long long)c->D * r / ws); c->z_hi = (int)((long long)c->D * (r + 1) / ws);
+    return 0;
+}
+
+int clamp_levels(int dim, int levels) {
+    int lg = 0; while ((1 << (lg + 1)) <= dim) lg++;
+    return std::min(std::max(levels, 1), std::min(lg + 1, VCT_MAX_LEVELS));
+}
+
+// concatenate the per-actor meshes into the device arrays the kernels index
+int finalize_scene(vct_ctx* c) {
+    if (!c->scene_dirty) return 0;
+    std::sort(c->meshes.begin(), c->meshes.end(), [](const HostMesh& a, const HostMesh& b) { return a.actor < b.actor; });
+    for (void** p : {(void**)&c->d_vertices, (void**)&c->d_vactor, (void**)&c->d_indices, (void**)&c->d_trimat, (void**)&c->d_models, (void**)&c->d_nmats, (void**)&c->d_wpos,
+                     (void**)&c->d_wnrm, (void**)&c->d_wT, (void**)&c->d_wB, (void**)&c->d_tri_count, (void**)&c->d_tri_base, (void**)&c->d_scan_tmp, (void**)&c->d_setup}) { cudaFree(*p); *p = nullptr; }
+    c->n_vertices = c->h_vertices.size() / 14; c->n_tris = c->h_trimat.size();
+    c->n_actors = 0; for (auto& m : c->meshes) c->n_actors = std::max(c->n_actors, m.actor + 1);
+    if (!c->n_vertices || !c->n_tris) { c->scene_dirty = false; return 0; }
+    const size_t nv = c->n_vertices, nt = c->n_tris;
+    VCT_CHECK(c, cudaMalloc(&c->d_vertices, nv * 56)); VCT_CHECK(c, cudaMalloc(&c->d_vactor, nv * 4));
+    VCT_CHECK(c, cudaMalloc(&c->d_indices, nt * 12)); VCT_CHECK(c, cudaMalloc(&c->d_trimat, nt * 4));
+    VCT_CHECK(c, cudaMalloc(&c->d_models, c->n_actors * sizeof(Mat4))); VCT_CHECK(c, cudaMalloc(&c->d_nmats, c->n_actors * 36));
+    VCT_CHECK(c, cudaMalloc(&c->d_wpos, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wnrm, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wT, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wB, nv * 16));
+    VCT_CHECK(c, cudaMalloc(&c->d_tri_count, nt * 4)); VCT_CHECK(c, cudaMalloc(&c->d_tri_base, nt * 4));
+    VCT_CHECK(c, cudaMalloc(&c->d_scan_tmp, (nt / 1024 + 65536) * 4));
+    VCT_CHECK(c, cudaMalloc(&c->d_setup, (2 * nt + 64) * vctk_tile_setup_bytes()));
+    VCT_CHECK(c, cudaMemcpy(c->d_vertices, c->h_vertices.data(), nv * 56, cudaMemcpyHostToDevice));
+    VCT_CHECK(c, cudaMemcpy(c->d_vactor, c->h_vactor.data(), nv * 4, cudaMemcpyHostToDevice));
+    VCT_CHECK(c, cudaMemcpy(c->d_indices, c->h_indices.data(), nt * 12, cudaMemcpyHostToDevice));
+    VCT_CHECK(c, cudaMemcpy(c->d_trimat, c->h_trimat.data(), nt * 4, cudaMemcpyHostToDevice));
+    c->scene_dirty = false;
+    return 0;
+}
+
+int upload_frame(vct_ctx* c, const vct_frame_params* p) {
+    if (!p) return fail(c, "null frame params");
+    if (p->radiance_dilate) return fail(c, "radianceDilate is malformed in the reference (injectRadiance.comp:59-64) and is not supported");
+    if (finalize_scene(c)) return 1;
+    FrameConst& f = c->h_fc;
+    auto cp = [](Mat4& d, const float* s) { std::memcpy(d.m, s, 64); };
+    cp(f.projection, p->projection); cp(f.view, p->view); cp(f.lp, p->lp); cp(f.lv, p->lv); cp(f.ls, p->ls); cp(f.ls_inverse, p->ls_inverse);
+    cp(f.mvp_x, p->mvp_x); cp(f.mvp_y, p->mvp_y); cp(f.mvp_z, p->mvp_z);
+    f.p = *p; f.D = c->D; f.L = c->L; f.S = c->S; f.W = c->W; f.H = c->H;
+    f.n_lights = c->n_lights; std::memcpy(f.lights, c->h_lights, sizeof f.lights);
+    f.z_lo = c->z_lo; f.z_hi = c->z_hi;
+    VCT_CHECK(c, cudaMemcpyAsync(c->d_fc, &f, sizeof f, cudaMemcpyHostToDevice, c->stream));
+    VCT_CHECK(c, cudaMemcpyAsync(c->d_tex, c->h_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES, cudaMemcpyHostToDevice, c->stream));
+    VCT_CHECK(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+enum { EV_START, EV_SHADOW, EV_WARP, EV_CLEAR, EV_VOXEL, EV_TRANSFER, EV_INJECT, EV_MIP, EV_GBUF, EV_TRACE, EV_COUNT };
+
+struct Graph { vct_ctx* c; bool timed; int rec(int e) { if (timed) { cudaError_t r = cudaEventRecord(c->ev[e], c->stream); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } } return 0; } };
+
+int ensure_color_texture(vct_ctx* c) {
+    if (c->color_arr) return 0;
+    return make_pyramid_texture(c, &c->color_arr, &c->color_tex, &c->color_tex_point, c->color_surf);
+}
+int ensure_scratch(vct_ctx* c) {
+    if (c->d_scratch) return 0;
+    VCT_CHECK(c, cudaMalloc(&c->d_scratch, (size_t)c->D * c->D * c->D * 4));
+    return 0;
+}
+int zero_info(vct_ctx* c) {
+    VCT_CHECK(c, cudaMemsetAsync(c->d_counters, 0, 3 * sizeof(unsigned), c->stream));     // glClearNamedBufferData, Application.cpp:581
+    return 0;
+}
+int gi_body(vct_ctx* c, Graph& g) {
+    const vct_frame_params& p = c->h_fc.p;
+    if (zero_info(c)) return 1;
+    if (vctk_clear_voxels(c) || g.rec(EV_CLEAR)) return 1;
+    if (vctk_voxelize(c, false) || g.rec(EV_VOXEL)) return 1;
+    if (vctk_transfer(c) || g.rec(EV_TRANSFER)) return 1;
+    if (vctk_inject(c)) return 1;
+    if (p.voxel_fill_holes) { if (ensure_scratch(c) || vctk_fill_holes(c)) return 1; }
+    if (g.rec(EV_INJECT)) return 1;
+    if (vctk_mip(c, VCT_VOL_RADIANCE, 0)) return 1;
+    if (p.mip_color_chain && vctk_mip(c, VCT_VOL_COLOR, 0)) return 1;
+    if (c->cfg.world_size <= 1) {
+        if (!p.draw_radiance) { if (ensure_color_texture(c) || vctk_publish(c, VCT_VOL_COLOR)) return 1; }
+        else if (vctk_publish(c, VCT_VOL_RADIANCE)) return 1;
+    }
+    return g.rec(EV_MIP);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vct_last_error(const vct_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+
+int vct_create(const vct_config* cfg, vct_ctx** out) {
+    if (!cfg || !out) { g_create_error = "vct_create: null argument"; return 1; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("vct_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback"; return 1; }
+    if (cfg->dim < 4 || (cfg->dim & (cfg->dim - 1)) || cfg->dim > 1024) { g_create_error = "vct_create: dim must be a power of two in [4,1024]"; return 1; }
+    if (cfg->shadow_size < 1 || cfg->width < 1 || cfg->height < 1) { g_create_error = "vct_create: bad sizes"; return 1; }
+    if (cfg->world_size > 1 && (cfg->rank < 0 || cfg->rank >= cfg->world_size || cfg->dim % cfg->world_size)) { g_create_error = "vct_create: bad rank/world_size"; return 1; }
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { g_create_error = std::string("vct_create: cudaSetDevice: ") + cudaGetErrorString(e); return 1; }
+    vct_ctx* c = new vct_ctx();
+    c->cfg = *cfg; c->D = cfg->dim; c->L = clamp_levels(cfg->dim, cfg->levels); c->S = cfg->shadow_size; c->W = cfg->width; c->H = cfg->height;
+    auto bail = [&](const char* what) { g_create_error = std::string("vct_create: ") + what + ": " + c->error; vct_destroy(c); return 1; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+    for (auto& ev : c->ev) if (cudaEventCreate(&ev) != cudaSuccess) return bail("event");
+    if (make_volumes(c)) return bail("volumes");
+    const int N = VCT_WARP_DIM;
+    auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
+    c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
+    c->tile_queue_cap = (size_t)4 << 20;
+    if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * 8) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
+        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, (size_t)c->W * c->H * 4) ||
+        alloc((void**)&c->d_key[0], c->frag_cap * 4) || alloc((void**)&c->d_key[1], c->frag_cap * 4) || alloc((void**)&c->d_val[0], c->frag_cap * 4) || alloc((void**)&c->d_val[1], c->frag_cap * 4) ||
+        alloc((void**)&c->d_frag_color, c->frag_cap * 16) || alloc((void**)&c->d_frag_normal, c->frag_cap * 16) || alloc((void**)&c->d_hist, (256 * 592 + 256) * 4) ||
+        alloc((void**)&c->d_tile_queue, c->tile_queue_cap * 16) || alloc((void**)&c->d_fc, sizeof(FrameConst)) || alloc((void**)&c->d_counters, sizeof(Counters)) ||
+        alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
+        return bail("cudaMalloc");
+    {   // warp map texture: RGBA16 unorm, LINEAR, CLAMP_TO_EDGE (reference src/Application.cpp:383-389)
+        cudaChannelFormatDesc fd = cudaCreateChannelDesc<ushort4>();
+        if (cudaMalloc3DArray(&c->warp_arr, &fd, make_cudaExtent(N, N, N)) != cudaSuccess) return bail("warp array");
+        cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = c->warp_arr;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+        if (cudaCreateTextureObject(&c->warp_tex, &rd, &td, nullptr) != cudaSuccess) return bail("warp texture");
+    }
+    for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("sync");
+    *out = c;
+    return 0;
+}
+
+int vct_destroy(vct_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_volumes(c);
+    if (c->warp_tex) cudaDestroyTextureObject(c->warp_tex);
+    if (c->warp_arr) cudaFreeArray(c->warp_arr);
+    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, (void*)c->d_key[0], (void*)c->d_key[1],
+                    (void*)c->d_val[0], (void*)c->d_val[1], (void*)c->d_frag_color, (void*)c->d_frag_normal, (void*)c->d_hist, (void*)c->d_tile_queue, (void*)c->d_fc, (void*)c->d_counters,
+                    (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_models, (void*)c->d_nmats, (void*)c->d_wpos,
+                    (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, (void*)c->d_tri_count, (void*)c->d_tri_base, (void*)c->d_scan_tmp, c->d_setup})
+        cudaFree(p);
+    for (void* p : c->tex_allocs) cudaFree(p);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+// VCT::remake (reference src/Application.h:118-129): destroy + create with clamped level count
+int vct_remake(vct_ctx* c, int dim, int levels) {
+    if (!c) return 1;
+    if (dim < 4 || (dim & (dim - 1)) || dim > 1024) return fail(c, "vct_remake: dim must be a power of two in [4,1024]");
+    VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    free_volumes(c);
+    c->D = dim; c->L = clamp_levels(dim, levels); c->cfg.dim = dim; c->cfg.levels = c->L;
+    return make_volumes(c);
+}
+
+int vct_upload_mesh(vct_ctx* c, int actor, const void* vertices, size_t n_vertices, size_t stride, const uint32_t* indices, size_t n_indices, const int32_t* material_of_triangle) {
+    if (!c) return 1;
+    if (stride < 56 || !vertices || !indices || n_indices % 3 || actor < 0) return fail(c, "vct_upload_mesh: bad arguments (Vertex stride is 56 bytes, src/Graphics/Mesh.h:72-76)");
+    for (auto& m : c->meshes) if (m.actor == actor) return fail(c, "vct_upload_mesh: actor already has a mesh");
+    for (size_t i = 0; i < n_indices; ++i) if (indices[i] >= n_vertices) return fail(c, "vct_upload_mesh: index out of range");
+    HostMesh m{}; m.actor = actor; m.n_vertices = n_vertices; m.n_tris = n_indices / 3; m.vbase = c->h_vertices.size() / 14; m.tbase = c->h_trimat.size();
+    for (int i = 0; i < 16; ++i) m.model.m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    const size_t v0 = c->h_vertices.size();
+    c->h_vertices.resize(v0 + n_vertices * 14);
+    for (size_t i = 0; i < n_vertices; ++i) std::memcpy(&c->h_vertices[v0 + 14 * i], (const char*)vertices + i * stride, 56);
+    c->h_vactor.insert(c->h_vactor.end(), n_vertices, actor);
+    for (size_t i = 0; i < n_indices; ++i) c->h_indices.push_back(indices[i] + (uint32_t)m.vbase);
+    for (size_t t = 0; t < n_indices / 3; ++t) c->h_trimat.push_back(material_of_triangle ? material_of_triangle[t] : 0);
+    c->meshes.push_back(m);
+    c->scene_dirty = true;
+    return 0;
+}
+
+int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels, int levels, const void* pixels) {
+    if (!c) return 1;
+    if (tex < 0 || tex >= VCT_MAX_TEXTURES || width < 1 || height < 1 || !(channels == 1 || channels == 3 || channels == 4) || levels < 1 || levels > 16 || !pixels)
+        return fail(c, "vct_upload_texture: bad arguments");
+    size_t total = 0;
+    for (int l = 0; l < levels; ++l) total += (size_t)std::max(1, width >> l) * std::max(1, height >> l) * channels;
+    uint8_t* d = nullptr;
+    VCT_CHECK(c, cudaMalloc(&d, total + 16));
+    VCT_CHECK(c, cudaMemcpy(d, pixels, total, cudaMemcpyHostToDevice));
+    c->tex_allocs.push_back(d);
+    DevTexture& t = c->h_tex[tex]; t.w = width; t.h = height; t.ch = channels; t.levels = levels;
+    size_t off = 0;
+    for (int l = 0; l < levels; ++l) { t.level[l] = d + off; off += (size_t)std::max(1, width >> l) * std::max(1, height >> l) * channels; }
+    c->n_textures = std::max(c->n_textures, tex + 1);
+    return 0;
+}
+
+int vct_set_material(vct_ctx* c, int material, const vct_material* m) {
+    if (!c) return 1;
+    if (material < 0 || material >= VCT_MAX_MATERIALS || !m) return fail(c, "vct_set_material: bad arguments");
+    DevMaterial& d = c->h_mat[material];
+    d.diffuse_tex = m->diffuse_tex; d.specular_tex = m->specular_tex; d.normal_tex = m->normal_tex; d.roughness_tex = m->roughness_tex; d.metallic_tex = m->metallic_tex; d.alpha_tex = m->alpha_tex;
+    d.shininess = m->shininess; std::memcpy(d.diffuse, m->diffuse, 12);
+    c->n_materials = std::max(c->n_materials, material + 1);
+    return 0;
+}
+
+int vct_set_actor_transform(vct_ctx* c, int actor, const float model[16]) {
+    if (!c) return 1;
+    for (auto& m : c->meshes) if (m.actor == actor) { std::memcpy(m.model.m, model, 64); return 0; }
+    return fail(c, "vct_set_actor_transform: unknown actor");
+}
+
+int vct_set_lights(vct_ctx* c, const vct_light* lights, int n) {
+    if (!c) return 1;
+    if (n < 0 || n > 8 || (n && !lights)) return fail(c, "vct_set_lights: 0..8 lights");
+    std::memset(c->h_lights, 0, sizeof c->h_lights);
+    if (n) std::memcpy(c->h_lights, lights, n * sizeof(vct_light));
+    c->n_lights = n;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- passes
+#define PASS_PROLOGUE                                   \
+    if (!c) return 1;                                   \
+    cudaSetDevice(c->cfg.device);                       \
+    if (upload_frame(c, p)) return 1;
+
+int vct_shadowmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_shadowmap(c); }
+int vct_occupancy(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_voxelize(c, true); }
+int vct_warpmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_warpmap(c); }
+int vct_voxelize(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return zero_info(c) || vctk_transform_vertices(c) || vctk_clear_voxels(c) || vctk_voxelize(c, false); }
+int vct_transfer(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transfer(c); }
+int vct_inject(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_inject(c); }
+int vct_fill_holes(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return ensure_scratch(c) || vctk_fill_holes(c); }
+int vct_gbuffer(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_visibility(c); }
+int vct_cone_trace(vct_ctx* c, const vct_frame_params* p) {
+    PASS_PROLOGUE;
+    if (!p->draw_radiance && !c->color_arr) { if (ensure_color_texture(c) || vctk_publish(c, VCT_VOL_COLOR)) return 1; }
+    VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
+    return vctk_cone_trace(c);
+}
+int vct_mip(vct_ctx* c, int which) {
+    if (!c) return 1;
+    cudaSetDevice(c->cfg.device);
+    if (which != VCT_VOL_RADIANCE && which != VCT_VOL_COLOR) return fail(c, "vct_mip: radiance or colour volume only");
+    if (vctk_mip(c, which, 0)) return 1;
+    if (c->cfg.world_size > 1) return 0;
+    if (which == VCT_VOL_COLOR && !c->color_arr) return 0;
+    return vctk_publish(c, which);
+}
+int vct_exchange(vct_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->cfg.device);
+    const bool rad = c->h_fc.p.draw_radiance != 0;
+    if (!rad && ensure_color_texture(c)) return 1;
+    return vctk_publish(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR);
+}
+
+int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
+    PASS_PROLOGUE;
+    Graph g{c, true};
+    if (g.rec(EV_START) || g.rec(EV_SHADOW) || g.rec(EV_WARP)) return 1;
+    if (vctk_transform_vertices(c)) return 1;
+    if (gi_body(c, g)) return 1;
+    if (c->cfg.world_size > 1) return 0;                      // caller all-gathers, then vct_exchange + vct_cone_trace
+    if (g.rec(EV_GBUF)) return 1;
+    VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
+    if (vctk_cone_trace(c)) return 1;
+    return g.rec(EV_TRACE);
+}
+
+// Application::render in the reference's pass order (src/Application.cpp:196-1085)
+int vct_frame(vct_ctx* c, const vct_frame_params* p) {
+    PASS_PROLOGUE;
+    Graph g{c, true};
+    if (g.rec(EV_START)) return 1;
+    if (vctk_transform_vertices(c) || vctk_shadowmap(c) || g.rec(EV_SHADOW)) return 1;
+    if (p->warp_texture) { if (vctk_voxelize(c, true) || vctk_warpmap(c)) return 1; }
+    if (g.rec(EV_WARP)) return 1;
+    if (gi_body(c, g)) return 1;
+    if (c->cfg.world_size > 1) return 0;
+    if (vctk_visibility(c) || g.rec(EV_GBUF)) return 1;
+    VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
+    if (vctk_cone_trace(c)) return 1;
+    return g.rec(EV_TRACE);
+}
+
+// dead-shader equivalents
+int vct_set_voxel_opacity(vct_ctx* c, float o) { if (!c) return 1; cudaSetDevice(c->cfg.device); return zero_info(c) || vctk_set_voxel_opacity(c, o); }
+int vct_temporal_radiance_filter(vct_ctx* c, float d) { if (!c) return 1; cudaSetDevice(c->cfg.device); return vctk_temporal_radiance_filter(c, d); }
+int vct_filter3d(vct_ctx* c, int which, int src_level) { if (!c) return 1; cudaSetDevice(c->cfg.device); return vctk_filter3d(c, which, src_level); }
+int vct_normalize_voxels_f16(vct_ctx* c, void* col, void* nrm, float o) { if (!c) return 1; cudaSetDevice(c->cfg.device); return zero_info(c) || vctk_normalize_voxels_f16(c, col, nrm, o); }
+
+// ------------------------------------------------------------------------------------------ outputs
+static int volume_ptr(vct_ctx* c, int which, int level, void** ptr, size_t* bytes) {
+    const int N = VCT_WARP_DIM;
+    switch (which) {
+        case VCT_VOL_COLOR: case VCT_VOL_RADIANCE: {
+            if (level < 0 || level >= c->L) return fail(c, "volume level out of range");
+            const size_t d = level_dim(c->D, level);
+            *ptr = (which == VCT_VOL_COLOR ? c->d_color : c->d_radiance) + c->level_off[level]; *bytes = d * d * d * 4; return 0;
+        }
+        case VCT_VOL_NORMAL: if (level) return fail(c, "voxelNormal has one level"); *ptr = c->d_normal; *bytes = (size_t)c->D * c->D * c->D * 4; return 0;
+        case VCT_VOL_OCCUPANCY: *ptr = c->d_occ; *bytes = N * N * N * 4; return 0;
+        case VCT_VOL_WARPMAP: *ptr = c->d_warpmap; *bytes = N * N * N * 8; return 0;
+        case VCT_VOL_WARP_WEIGHTS_LOW: *ptr = c->d_wlo; *bytes = N * N * N * 8; return 0;
+        case VCT_VOL_WARP_WEIGHTS_HIGH: *ptr = c->d_whi; *bytes = N * N * N * 8; return 0;
+    }
+    return fail(c, "unknown volume");
+}
+int vct_sync(vct_ctx* c) { if (!c) return 1; cudaSetDevice(c->cfg.device); VCT_CHECK(c, cudaStreamSynchronize(c->stream)); return 0; }
+int vct_read_volume(vct_ctx* c, int which, int level, void* out) {
+    if (!c || !out) return 1;
+    cudaSetDevice(c->cfg.device);
+    void* p; size_t b; if (volume_ptr(c, which, level, &p, &b)) return 1;
+    VCT_CHECK(c, cudaMemcpyAsync(out, p, b, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int vct_write_volume(vct_ctx* c, int which, int level, const void* in) {
+    if (!c || !in) return 1;
+    cudaSetDevice(c->cfg.device);
+    void* p; size_t b; if (volume_ptr(c, which, level, &p, &b)) return 1;
+    VCT_CHECK(c, cudaMemcpyAsync(p, in, b, cudaMemcpyHostToDevice, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (which == VCT_VOL_WARPMAP) {
+        cudaMemcpy3DParms cp = {}; cp.srcPtr = make_cudaPitchedPtr(c->d_warpmap, VCT_WARP_DIM * 8, VCT_WARP_DIM, VCT_WARP_DIM);
+        cp.dstArray = c->warp_arr; cp.extent = make_cudaExtent(VCT_WARP_DIM, VCT_WARP_DIM, VCT_WARP_DIM); cp.kind = cudaMemcpyDeviceToDevice;
+        VCT_CHECK(c, cudaMemcpy3DAsync(&cp, c->stream));
+    }
+    return 0;
+}
+int vct_read_image(vct_ctx* c, void* rgba8) {
+    if (!c || !rgba8) return 1;
+    cudaSetDevice(c->cfg.device);
+    VCT_CHECK(c, cudaMemcpyAsync(rgba8, c->d_image, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int vct_read_shadowmap(vct_ctx* c, float* d) {
+    if (!c || !d) return 1;
+    cudaSetDevice(c->cfg.device);
+    VCT_CHECK(c, cudaMemcpyAsync(d, c->d_shadow, (size_t)c->S * c->S * 4, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int vct_write_shadowmap(vct_ctx* c, const float* d) {
+    if (!c || !d) return 1;
+    cudaSetDevice(c->cfg.device);
+    VCT_CHECK(c, cudaMemcpyAsync(c->d_shadow, d, (size_t)c->S * c->S * 4, cudaMemcpyHostToDevice, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int vct_read_visibility(vct_ctx* c, uint64_t* v) {
+    if (!c || !v) return 1;
+    cudaSetDevice(c->cfg.device);
+    VCT_CHECK(c, cudaMemcpyAsync(v, c->d_vis, (size_t)c->W * c->H * 8, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+static int fetch_counters(vct_ctx* c) {
+    VCT_CHECK(c, cudaMemcpyAsync(&c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (c->h_counters.overflow) return fail(c, "a fixed-capacity device buffer overflowed (fragment buffer or raster tile queue): raise vct_config.max_fragments");
+    return 0;
+}
+int vct_get_counters(vct_ctx* c, vct_voxelize_info* info) {
+    if (!c || !info) return 1;
+    cudaSetDevice(c->cfg.device);
+    if (fetch_counters(c)) return 1;
+    info->total_fragments = c->h_counters.total_fragments; info->unique_voxels = c->h_counters.unique_voxels; info->max_fragments_per_voxel = c->h_counters.max_fragments_per_voxel;
+    return 0;
+}
+int vct_get_cone_steps(vct_ctx* c, unsigned long long* steps) {
+    if (!c || !steps) return 1;
+    cudaSetDevice(c->cfg.device);
+    if (fetch_counters(c)) return 1;
+    *steps = c->h_counters.cone_steps;
+    return 0;
+}
+int vct_get_timings(vct_ctx* c, vct_timings* t) {
+    if (!c || !t) return 1;
+    cudaSetDevice(c->cfg.device);
+    VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    auto ms = [&](int a, int b) { float v = 0.f; if (cudaEventElapsedTime(&v, c->ev[a], c->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0; } return (double)v * 1e6; };
+    std::memset(t, 0, sizeof *t);
+    t->shadowmap_ns = ms(EV_START, EV_SHADOW); t->warpmap_ns = ms(EV_SHADOW, EV_WARP); t->clear_ns = ms(EV_WARP, EV_CLEAR);
+    t->voxelize_ns = ms(EV_WARP, EV_VOXEL); t->transfer_ns = ms(EV_VOXEL, EV_TRANSFER); t->radiance_ns = ms(EV_TRANSFER, EV_INJECT);
+    t->mipmap_ns = ms(EV_INJECT, EV_MIP); t->gbuffer_ns = ms(EV_MIP, EV_GBUF); t->render_ns = ms(EV_GBUF, EV_TRACE); t->total_ns = ms(EV_START, EV_TRACE);
+    return 0;
+}
+void* vct_device_ptr(vct_ctx* c, int which, int level) { if (!c) return nullptr; void* p; size_t b; return volume_ptr(c, which, level, &p, &b) ? nullptr : p; }
+size_t vct_level_bytes(vct_ctx* c, int which, int level) { if (!c) return 0; void* p; size_t b; return volume_ptr(c, which, level, &p, &b) ? 0 : b; }
+void* vct_stream(vct_ctx* c) { return c ? (void*)c->stream : nullptr; }
+unsigned long long vct_launch_count(vct_ctx* c, int reset) { if (!c) return 0; const unsigned long long n = c->launches; if (reset) c->launches = 0; return n; }
+
+}  // extern "C"

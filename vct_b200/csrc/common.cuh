@@ -1,0 +1,183 @@
+// common.cuh — context, error handling and device helpers shared by every kernel file of libvct_b200.
+//
+// Exactness contract (DESIGN.md "Canonical GL semantics"): the translation units that decide WHICH voxel /
+// texel / pixel a value lands in (raster.cu, voxelize.cu, volume_passes.cu, warpmap.cu) are compiled with
+// -fmad=false so that every float operation is a separately rounded IEEE-754 op in source order; division and
+// sqrt are the correctly rounded defaults (-prec-div/-prec-sqrt).  cone_trace.cu is tolerance-gated (PSNR) and
+// is compiled with FMA contraction on.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vct_b200.h"
+
+#define VCT_SM_COUNT 148
+
+// ------------------------------------------------------------------------------------------- small vectors
+struct V3 { float x, y, z; };
+struct V4 { float x, y, z, w; };
+__host__ __device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ __forceinline__ V4 mk4(float x, float y, float z, float w) { V4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+__host__ __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__host__ __device__ __forceinline__ V3 operator/(V3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+__host__ __device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__host__ __device__ __forceinline__ V3 cross3(V3 a, V3 b) { return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+__host__ __device__ __forceinline__ float length3(V3 a) { return sqrtf(dot3(a, a)); }
+__host__ __device__ __forceinline__ V3 normalize3(V3 a) { float l = sqrtf(dot3(a, a)); return mk3(a.x / l, a.y / l, a.z / l); }
+__host__ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__host__ __device__ __forceinline__ float maxsel(float a, float b) { return a > b ? a : b; }
+__host__ __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+
+struct Mat4 { float m[16]; };                       // column-major, as uploaded by the host
+__host__ __device__ __forceinline__ V4 mul44(const Mat4& M, V4 v) {
+    const float* m = M.m;
+    V4 r;
+    r.x = ((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * v.w;
+    r.y = ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * v.w;
+    r.z = ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * v.w;
+    r.w = ((m[3] * v.x + m[7] * v.y) + m[11] * v.z) + m[15] * v.w;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------ unorm8 conversions
+__device__ __forceinline__ uint32_t f2u_trunc(float v) { return __float2uint_rz(v); }       // saturating, NaN -> 0
+__device__ __forceinline__ uint32_t unorm8(float v) {                                       // round(clamp(v,0,1)*255), RNE
+    if (!(v > 0.0f)) return 0u;
+    if (v > 1.0f) v = 1.0f;
+    return __float2uint_rn(v * 255.0f);
+}
+__device__ __forceinline__ uint32_t pack_unorm(V4 c) { return unorm8(c.x) | unorm8(c.y) << 8 | unorm8(c.z) << 16 | unorm8(c.w) << 24; }
+__device__ __forceinline__ V4 unpack_unorm(uint32_t w) {
+    return mk4((float)(w & 255u) / 255.0f, (float)((w >> 8) & 255u) / 255.0f, (float)((w >> 16) & 255u) / 255.0f, (float)(w >> 24) / 255.0f);
+}
+
+// ------------------------------------------------------------------------------------------ device scene
+struct DevTexture { const uint8_t* level[16]; int w, h, ch, levels; };
+struct DevMaterial { int diffuse_tex, specular_tex, normal_tex, roughness_tex, metallic_tex, alpha_tex; float shininess; float diffuse[3]; };
+
+// Per-frame constants every pass reads (uploaded once per frame into __constant__-like global struct).
+struct FrameConst {
+    Mat4 projection, view, lp, lv, ls, ls_inverse, mvp_x, mvp_y, mvp_z;
+    vct_frame_params p;          // scalar settings (matrices inside are unused on the device)
+    int D, L, S, W, H;
+    int n_lights;
+    vct_light lights[8];
+    int z_lo, z_hi;              // z-slab [z_lo, z_hi) owned by this rank
+};
+
+struct Counters {                // device-resident, zeroed per frame
+    unsigned total_fragments, unique_voxels, max_fragments_per_voxel;
+    unsigned n_frag_slots;       // fragments emitted (== total_fragments within this slab)
+    unsigned tile_queue_count;   // raster work queue
+    unsigned setup_count;        // big-triangle setups written by k_raster_bin
+    unsigned overflow;           // set when a fixed-capacity buffer was too small
+    unsigned long long cone_steps;
+};
+
+struct HostMesh {
+    int actor; size_t n_vertices, n_tris; size_t vbase, tbase;   // offsets into the concatenated device arrays
+    Mat4 model;
+};
+
+#define VCT_MAX_TEXTURES 256
+#define VCT_MAX_MATERIALS 256
+
+struct vct_ctx {
+    vct_config cfg{};
+    int D = 0, L = 0, S = 0, W = 0, H = 0;
+    int z_lo = 0, z_hi = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    unsigned long long launches = 0;
+
+    // scene
+    std::vector<HostMesh> meshes;
+    std::vector<float> h_vertices; std::vector<uint32_t> h_indices; std::vector<int32_t> h_trimat; std::vector<int32_t> h_vactor;
+    bool scene_dirty = true;
+    size_t n_vertices = 0, n_tris = 0;
+    float* d_vertices = nullptr;      // n x 14
+    int32_t* d_vactor = nullptr;
+    uint32_t* d_indices = nullptr; int32_t* d_trimat = nullptr;
+    Mat4* d_models = nullptr; float* d_nmats = nullptr; int n_actors = 0;
+    std::vector<Mat4> h_models; std::vector<float> h_nmats;
+    float4 *d_wpos = nullptr, *d_wnrm = nullptr, *d_wT = nullptr, *d_wB = nullptr;   // per-vertex world-space attributes
+    DevTexture h_tex[VCT_MAX_TEXTURES]{}; DevTexture* d_tex = nullptr; std::vector<void*> tex_allocs; int n_textures = 0;
+    DevMaterial h_mat[VCT_MAX_MATERIALS]{}; DevMaterial* d_mat = nullptr; int n_materials = 0;
+    vct_light h_lights[8]{}; int n_lights = 0;
+
+    // volumes (linear, x fastest): one allocation per pyramid, level offsets in voxels
+    uint32_t *d_color = nullptr, *d_radiance = nullptr, *d_normal = nullptr, *d_scratch = nullptr;
+    size_t level_off[VCT_MAX_LEVELS + 1]{};
+    cudaMipmappedArray_t radiance_arr = nullptr, color_arr = nullptr;
+    cudaTextureObject_t radiance_tex = 0, radiance_tex_point = 0, color_tex = 0, color_tex_point = 0;
+    cudaSurfaceObject_t radiance_surf[VCT_MAX_LEVELS]{}, color_surf[VCT_MAX_LEVELS]{};
+    // warp
+    uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
+    cudaArray_t warp_arr = nullptr; cudaTextureObject_t warp_tex = 0;
+    // shadow map / visibility / image
+    float* d_shadow = nullptr; unsigned long long* d_vis = nullptr; uint32_t* d_image = nullptr;
+    // voxel fragments
+    size_t frag_cap = 0;
+    uint32_t *d_tri_count = nullptr, *d_tri_base = nullptr, *d_scan_tmp = nullptr;
+    uint32_t *d_key[2] = {nullptr, nullptr}, *d_val[2] = {nullptr, nullptr};
+    float4 *d_frag_color = nullptr, *d_frag_normal = nullptr;
+    uint32_t* d_hist = nullptr;
+    // raster work queue
+    uint4* d_tile_queue = nullptr; size_t tile_queue_cap = 0; void* d_setup = nullptr;
+    // per-frame constants + counters
+    FrameConst* d_fc = nullptr; FrameConst h_fc{};
+    Counters* d_counters = nullptr; Counters h_counters{};
+    // timing
+    cudaEvent_t ev[32]{}; vct_timings timings{};
+};
+
+extern thread_local std::string g_create_error;
+
+#define VCT_CHECK(ctx, call)                                                                    \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            char b__[512];                                                                      \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            (ctx)->error = b__;                                                                 \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define VCT_LAUNCH_CHECK(ctx)                                                                   \
+    do {                                                                                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess) {                                                               \
+            char b__[512];                                                                      \
+            snprintf(b__, sizeof b__, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            (ctx)->error = b__;                                                                 \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+static inline int level_dim(int D, int l) { int d = D >> l; return d < 1 ? 1 : d; }
+
+// pass entry points implemented across the .cu files (all enqueue on ctx->stream)
+int vctk_transform_vertices(vct_ctx*);
+int vctk_clear_voxels(vct_ctx*);
+int vctk_voxelize(vct_ctx*, bool occupancy);
+int vctk_transfer(vct_ctx*);
+int vctk_inject(vct_ctx*);
+int vctk_fill_holes(vct_ctx*);
+int vctk_mip(vct_ctx*, int which, int mode);
+int vctk_publish(vct_ctx*, int which);
+int vctk_shadowmap(vct_ctx*);
+int vctk_visibility(vct_ctx*);
+int vctk_warpmap(vct_ctx*);
+int vctk_cone_trace(vct_ctx*);
+int vctk_set_voxel_opacity(vct_ctx*, float);
+int vctk_temporal_radiance_filter(vct_ctx*, float);
+int vctk_filter3d(vct_ctx*, int which, int src_level);
+int vctk_normalize_voxels_f16(vct_ctx*, void*, void*, float);

@@ -1,0 +1,315 @@
+// cone_trace.cu — per-pixel shading + voxel cone tracing (a7).  Tolerance-gated (final image PSNR), compiled
+// with FMA contraction on; the voxel pyramid and the warp map are read through HARDWARE 3D texture objects.
+//
+// Replaces the GL_EQUAL colour pass of phong.vert/phong.frag (reference src/Application.cpp:967-1067):
+//   phong.frag:427-439  normal (normal map through the interpolated TBN, or the vertex normal)
+//   phong.frag:305-344  direct lighting (Cook-Torrance :230-258 / Blinn :260-301, 5-tap PCF :183-207)
+//   phong.frag:455-512  6 weighted diffuse cones + 1 specular cone through traceCone (:135-180)
+//   phong.frag:210-218  Reinhard + gamma
+// Inputs: the visibility buffer (triangle id per pixel) — attributes are re-interpolated here with the
+// perspective-correct barycentrics of the unclipped triangle, so no fat G-buffer is stored.
+// Sampler state reproduced (src/Application.cpp:1094-1098, Application.h:146): min LINEAR_MIPMAP_LINEAR, mag
+// NEAREST, CLAMP_TO_BORDER(0): lambda <= 0.5 is a magnification -> point fetch of level 0 (GL 4.5 §8.14),
+// otherwise trilinear + mip-linear, lambda clamped to the last level.
+// Thread mapping: a warp shades an 8x4 pixel tile so that the 32 cones marched in lock-step (same cone index,
+// same step) stay spatially coherent in the texture cache; a CTA of 8 warps covers 32x8 pixels.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+__device__ const float kPI = 3.1415982f;                 // common.glsl:1 [sic]
+
+struct TraceArgs {
+    const FrameConst* fc; int W, H, y_lo, y_hi;
+    const unsigned long long* vis;
+    const uint32_t* indices; const int32_t* trimat; const float* verts;
+    const float4 *wpos, *wnrm, *wT, *wB;
+    const DevTexture* tex; const DevMaterial* mats; const float* shadow;
+    cudaTextureObject_t vol, vol_point, warp;
+    uint32_t* image; Counters* counters;
+};
+
+__device__ __forceinline__ V3 f4to3(float4 q) { return mk3(q.x, q.y, q.z); }
+__device__ __forceinline__ float ip(const float l[3], float a, float b, float c) { return l[0] * a + l[1] * b + l[2] * c; }
+__device__ __forceinline__ V3 ip3(const float l[3], V3 a, V3 b, V3 c) { return mk3(ip(l, a.x, b.x, c.x), ip(l, a.y, b.y, c.y), ip(l, a.z, b.z, c.z)); }
+
+// ---- 2D material textures: LINEAR_MIPMAP_NEAREST / NEAREST / REPEAT, software-filtered from linear memory
+__device__ __forceinline__ int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
+__device__ __forceinline__ V4 texel2d(const DevTexture& t, int level, int x, int y) {
+    const int w = max(1, t.w >> level), h = max(1, t.h >> level);
+    const uint8_t* p = t.level[level] + ((size_t)wrapi(y, h) * w + wrapi(x, w)) * t.ch;
+    const float k = 1.0f / 255.0f;
+    if (t.ch == 4) { const uchar4 q = *reinterpret_cast<const uchar4*>(p); return mk4(q.x * k, q.y * k, q.z * k, q.w * k); }
+    if (t.ch == 3) return mk4(p[0] * k, p[1] * k, p[2] * k, 1.0f);
+    return mk4(p[0] * k, 0.f, 0.f, 1.f);
+}
+__device__ __forceinline__ V4 lerp4(V4 a, V4 b, float t) { return mk4(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t); }
+__device__ __forceinline__ V4 sample2d(const DevTexture& t, float u, float v, float rho2) {
+    if (!(rho2 > 2.0f)) return texel2d(t, 0, (int)floorf(u * (float)t.w), (int)floorf(v * (float)t.h));
+    int d = 1; float lim = 8.0f;
+    while (d < t.levels - 1 && rho2 > lim) { d++; lim *= 4.0f; }
+    if (d > t.levels - 1) d = t.levels - 1;
+    const int w = max(1, t.w >> d), h = max(1, t.h >> d);
+    const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    const int x0 = (int)fx0, y0 = (int)fy0; const float fx = x - fx0, fy = y - fy0;
+    return lerp4(lerp4(texel2d(t, d, x0, y0), texel2d(t, d, x0 + 1, y0), fx), lerp4(texel2d(t, d, x0, y0 + 1), texel2d(t, d, x0 + 1, y0 + 1), fx), fy);
+}
+
+// ---- shadow map PCF (phong.frag:183-207), LINEAR + CLAMP_TO_BORDER(1)
+__device__ __forceinline__ float sm_texel(const float* __restrict__ sm, int S, int x, int y) { return (x < 0 || y < 0 || x >= S || y >= S) ? 1.0f : __ldg(sm + (size_t)y * S + x); }
+__device__ __forceinline__ float calc_shadow_factor(const float* __restrict__ sm, int S, V4 lsp) {
+    const float sx = (lsp.x / lsp.w + 1.0f) * 0.5f, sy = (lsp.y / lsp.w + 1.0f) * 0.5f, sz = (lsp.z / lsp.w + 1.0f) * 0.5f;
+    const float frag_depth = sz - 0.01f;
+    if (frag_depth > 1.0f) return 0.0f;
+    const float x = sx * (float)S - 0.5f, y = sy * (float)S - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    if (!(fabsf(fx0) < 1e9f) || !(fabsf(fy0) < 1e9f)) return 0.0f;       // every tap reads the border (1.0): never shadowed
+    const int x0 = (int)fx0, y0 = (int)fy0; const float fx = x - fx0, fy = y - fy0;
+    // the five bilinear footprints share a 4x4 texel neighbourhood: fetch the 12 distinct texels once
+    float t[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[j][i] = ((i == 0 || i == 3) && (j == 0 || j == 3)) ? 0.0f : sm_texel(sm, S, x0 - 1 + i, y0 - 1 + j);
+    auto bil = [&](int ox, int oy) {
+        const int i = 1 + ox, j = 1 + oy;
+        const float top = t[j][i] * (1.0f - fx) + t[j][i + 1] * fx, bot = t[j + 1][i] * (1.0f - fx) + t[j + 1][i + 1] * fx;
+        return top * (1.0f - fy) + bot * fy;
+    };
+    float f = 0.0f;
+    if (frag_depth > bil(0, 0)) f += 1.0f;
+    if (frag_depth > bil(1, 0)) f += 1.0f;
+    if (frag_depth > bil(0, 1)) f += 1.0f;
+    if (frag_depth > bil(-1, 0)) f += 1.0f;
+    if (frag_depth > bil(0, -1)) f += 1.0f;
+    return f / 5.0f;
+}
+
+// ---- common.glsl
+__device__ __forceinline__ V3 voxel_linear_position(V3 p, const vct_frame_params& fp) {
+    return mk3((p.x - fp.voxel_center[0] - fp.voxel_min[0]) / (fp.voxel_max[0] - fp.voxel_min[0]),
+               (p.y - fp.voxel_center[1] - fp.voxel_min[1]) / (fp.voxel_max[1] - fp.voxel_min[1]),
+               (p.z - fp.voxel_center[2] - fp.voxel_min[2]) / (fp.voxel_max[2] - fp.voxel_min[2]));
+}
+__device__ __forceinline__ float voxel_warp_fn1(float x) {
+    const float alpha = 0.25f;
+    x = alpha * x + (3.0f - 3.0f * alpha) * x * x + (2.0f * alpha - 2.0f) * x * x * x;
+    return clampf(x, 0.0f, 1.0f);
+}
+__device__ __forceinline__ V3 voxel_warp(V3 p, V3 c) {
+    V3 o = p - c;
+    o = mk3(voxel_warp_fn1(0.5f * o.x + 0.5f), voxel_warp_fn1(0.5f * o.y + 0.5f), voxel_warp_fn1(0.5f * o.z + 0.5f));
+    return c + mk3(2.0f * o.x - 1.0f, 2.0f * o.y - 1.0f, 2.0f * o.z - 1.0f);
+}
+
+// ---- traceCone, phong.frag:135-180
+struct ConeCtx { cudaTextureObject_t vol, vol_point, warp; int D, L; int warp_texture, warp_voxels; V3 eye_tc; };
+__device__ __forceinline__ V4 trace_cone(const ConeCtx& cx, V3 position, V3 normal, V3 direction, int steps, float bias, float cone_angle,
+                                         float cone_height, float lod_offset, unsigned& fetches) {
+    direction = normalize3(direction);
+    V3 color = mk3(0.f, 0.f, 0.f); float alpha = 0.0f;
+    const float scale = 1.0f / (float)cx.D;
+    const V3 start = position + (normal * bias) * scale;
+    const float tan_half = tanf(cone_angle / 2.0f);
+    const float max_lod = (float)(cx.L - 1);
+    for (int i = 0; i < steps && alpha < 0.95f; ++i) {
+        const float cone_radius = cone_height * tan_half;
+        const float lod = log2f(fmaxf(1.0f, 2.0f * cone_radius));
+        V3 sp = start + (direction * cone_height) * scale;
+        if (!(sp.x >= 0.0f && sp.x <= 1.0f && sp.y >= 0.0f && sp.y <= 1.0f && sp.z >= 0.0f && sp.z <= 1.0f)) break;   // also NaN
+        if (cx.warp_texture) { const float4 wq = tex3D<float4>(cx.warp, sp.x, sp.y, sp.z); sp = mk3(wq.x, wq.y, wq.z); }
+        else if (cx.warp_voxels) sp = voxel_warp(sp, cx.eye_tc);
+        const float lambda = lod + lod_offset;
+        float4 sc;
+        if (!(lambda > 0.5f)) sc = tex3DLod<float4>(cx.vol_point, sp.x, sp.y, sp.z, 0.0f);
+        else sc = tex3DLod<float4>(cx.vol, sp.x, sp.y, sp.z, fminf(lambda, max_lod));
+        fetches++;
+        const float a = 1.0f - alpha;
+        color = color + mk3(sc.x, sc.y, sc.z) * a;
+        alpha += a * sc.w;
+        cone_height += cone_radius;
+    }
+    return mk4(color.x, color.y, color.z, alpha);
+}
+
+__device__ __forceinline__ float pow2f(float x) { return x * x; }
+__device__ __forceinline__ float D_ggxtr(V3 N, V3 Hh, float rough) {
+    const float ndh = fmaxf(0.0f, dot3(N, Hh)), a2 = pow2f(rough);
+    return a2 / (kPI * pow2f(pow2f(ndh) * (a2 - 1.0f) + 1.0f));
+}
+__device__ __forceinline__ float G1(V3 N, V3 V, float rough) {
+    const float k = pow2f(rough + 1.0f) / 8.0f, ndv = fmaxf(0.0f, dot3(N, V));
+    return ndv / (ndv * (1.0f - k) + k);
+}
+struct LR { V3 diffuse, specular; };
+__device__ __forceinline__ LR cook_torrance(V3 dc, V3 lc, V3 N, V3 V, V3 L, V3 Hh, float rough, float metal) {
+    const float ndl = fmaxf(0.0f, dot3(N, L)), ndv = fmaxf(0.0f, dot3(N, V)), hdv = fmaxf(0.0f, dot3(Hh, V));
+    const V3 lambert = dc / kPI;
+    const float Dg = D_ggxtr(N, Hh, rough), G = G1(N, V, rough) * G1(N, L, rough);
+    const V3 F0 = mk3(mixf(0.04f, dc.x, metal), mixf(0.04f, dc.y, metal), mixf(0.04f, dc.z, metal));
+    const float p5 = powf(1.0f - hdv, 5.0f);
+    const V3 F = mk3(F0.x + (1.0f - F0.x) * p5, F0.y + (1.0f - F0.y) * p5, F0.z + (1.0f - F0.z) * p5);
+    const float den = fmaxf(4.0f * ndl * ndv, 0.001f);
+    const V3 fct = (F * (Dg * G)) / den;
+    const V3 kd = mk3((1.0f - F.x) * (1.0f - metal), (1.0f - F.y) * (1.0f - metal), (1.0f - F.z) * (1.0f - metal));
+    LR r; r.diffuse = ((lc * ndl) * kd) * lambert; r.specular = (lc * ndl) * fct;
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads) k_cone_trace(TraceArgs a) {
+    const FrameConst& fc = *a.fc;
+    const vct_frame_params& fp = fc.p;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (w & 3) * 8 + (lane & 7);
+    const int py = a.y_lo + blockIdx.y * 8 + (w >> 2) * 4 + (lane >> 3);
+    unsigned fetches = 0;
+    if (px < a.W && py < a.y_hi) {
+        const size_t o = (size_t)py * a.W + px;
+        const unsigned long long key = a.vis[o];
+        if (key == ~0ull) a.image[o] = pack_unorm(mk4(fp.clear_color[0], fp.clear_color[1], fp.clear_color[2], 1.0f));
+        else {
+            const uint32_t t = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+            const uint32_t i0 = __ldg(a.indices + 3 * (size_t)t), i1 = __ldg(a.indices + 3 * (size_t)t + 1), i2 = __ldg(a.indices + 3 * (size_t)t + 2);
+            const V3 w0 = f4to3(__ldg(a.wpos + i0)), w1 = f4to3(__ldg(a.wpos + i1)), w2 = f4to3(__ldg(a.wpos + i2));
+            // perspective-correct barycentrics (and their forward differences for the texture LOD)
+            float l[3], lx[3], ly[3];
+            {
+                V4 c[3];
+                c[0] = mul44(fc.projection, mul44(fc.view, mk4(w0.x, w0.y, w0.z, 1.0f)));
+                c[1] = mul44(fc.projection, mul44(fc.view, mk4(w1.x, w1.y, w1.z, 1.0f)));
+                c[2] = mul44(fc.projection, mul44(fc.view, mk4(w2.x, w2.y, w2.z, 1.0f)));
+                float ha[3], hb[3], hc[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const V4 p = c[(i + 1) % 3], q = c[(i + 2) % 3];
+                    ha[i] = __fmul_rn(p.y, q.w) - __fmul_rn(q.y, p.w); hb[i] = __fmul_rn(q.x, p.w) - __fmul_rn(p.x, q.w); hc[i] = __fmul_rn(p.x, q.y) - __fmul_rn(q.x, p.y);
+                }
+                const float nx = ((float)px + 0.5f) / (float)a.W * 2.0f - 1.0f, ny = ((float)py + 0.5f) / (float)a.H * 2.0f - 1.0f;
+                auto ev = [&](float x, float y, float out[3]) {
+                    const float b0 = ha[0] * x + hb[0] * y + hc[0], b1 = ha[1] * x + hb[1] * y + hc[1], b2 = ha[2] * x + hb[2] * y + hc[2];
+                    const float s = b0 + b1 + b2; out[0] = b0 / s; out[1] = b1 / s; out[2] = b2 / s;
+                };
+                ev(nx, ny, l); ev(nx + 2.0f / (float)a.W, ny, lx); ev(nx, ny + 2.0f / (float)a.H, ly);
+            }
+            const float* v0 = a.verts + 14 * (size_t)i0; const float* v1 = a.verts + 14 * (size_t)i1; const float* v2 = a.verts + 14 * (size_t)i2;
+            const float u0 = __ldg(v0 + 6), t0 = __ldg(v0 + 7), u1 = __ldg(v1 + 6), t1 = __ldg(v1 + 7), u2 = __ldg(v2 + 6), t2 = __ldg(v2 + 7);
+            const float u = ip(l, u0, u1, u2), v = ip(l, t0, t1, t2);
+            const float ux = ip(lx, u0, u1, u2) - u, vx = ip(lx, t0, t1, t2) - v, uy = ip(ly, u0, u1, u2) - u, vy = ip(ly, t0, t1, t2) - v;
+            auto fetch = [&](int ti) {
+                const DevTexture& T = a.tex[ti];
+                const float ax = ux * (float)T.w, bx = vx * (float)T.h, ay = uy * (float)T.w, by = vy * (float)T.h;
+                return sample2d(T, u, v, fmaxf(ax * ax + bx * bx, ay * ay + by * by));
+            };
+            const DevMaterial mat = a.mats[__ldg(a.trimat + t)];
+            const V3 Pw = ip3(l, w0, w1, w2);
+            const V3 fn = ip3(l, f4to3(__ldg(a.wnrm + i0)), f4to3(__ldg(a.wnrm + i1)), f4to3(__ldg(a.wnrm + i2)));
+            const V3 Tt = ip3(l, f4to3(__ldg(a.wT + i0)), f4to3(__ldg(a.wT + i1)), f4to3(__ldg(a.wT + i2)));
+            const V3 Bt = ip3(l, f4to3(__ldg(a.wB + i0)), f4to3(__ldg(a.wB + i1)), f4to3(__ldg(a.wB + i2)));
+            const V4 lf0 = mul44(fc.ls, mk4(w0.x, w0.y, w0.z, 1.0f)), lf1 = mul44(fc.ls, mk4(w1.x, w1.y, w1.z, 1.0f)), lf2 = mul44(fc.ls, mk4(w2.x, w2.y, w2.z, 1.0f));
+            const V4 lsp = mk4(ip(l, lf0.x, lf1.x, lf2.x), ip(l, lf0.y, lf1.y, lf2.y), ip(l, lf0.z, lf1.z, lf2.z), ip(l, lf0.w, lf1.w, lf2.w));
+            auto tbn = [&](V3 d) { return (Tt * d.x + Bt * d.y) + fn * d.z; };
+            V3 N;
+            if (fp.enable_normal_map && mat.normal_tex >= 0) {
+                const V4 nm = fetch(mat.normal_tex);
+                N = normalize3(tbn(normalize3(mk3(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f))));
+            } else N = normalize3(fn);
+            const V4 dc4 = mat.diffuse_tex >= 0 ? fetch(mat.diffuse_tex) : mk4(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2], 1.0f);
+            const V3 dc = mk3(dc4.x, dc4.y, dc4.z);
+            const V3 eye = mk3(fp.eye[0], fp.eye[1], fp.eye[2]);
+            const V3 Vv = normalize3(eye - Pw);
+            float rough = 0.5f; if (mat.roughness_tex >= 0) rough = fetch(mat.roughness_tex).x;
+            float metal = 0.0f; if (mat.metallic_tex >= 0) metal = fetch(mat.metallic_tex).x;
+            V3 dsum = mk3(0.f, 0.f, 0.f), ssum = mk3(0.f, 0.f, 0.f);
+            for (int i = 0; i < fc.n_lights; ++i) {
+                const vct_light& Lt = fc.lights[i];
+                if (!Lt.enabled) continue;
+                const V3 lc = mk3(Lt.color[0], Lt.color[1], Lt.color[2]), lpos = mk3(Lt.position[0], Lt.position[1], Lt.position[2]);
+                LR r; r.diffuse = mk3(0.f, 0.f, 0.f); r.specular = mk3(0.f, 0.f, 0.f);
+                if (Lt.type == 0u) {
+                    const float dist = length3(lpos - Pw);
+                    if (!(dist > Lt.range)) {
+                        const float e0 = 0.75f * Lt.range, tt = clampf((dist - e0) / (Lt.range - e0), 0.0f, 1.0f);
+                        const float att = 1.0f - tt * tt * (3.0f - 2.0f * tt);
+                        const V3 Ld = normalize3(lpos - Pw);
+                        if (fp.cooktorrance) { r = cook_torrance(dc, lc, N, Vv, Ld, normalize3(Vv + Ld), rough, metal); r.diffuse = r.diffuse * att; r.specular = r.specular * att; }
+                        else {
+                            const float df = fmaxf(dot3(N, Ld), 0.0f), sp = powf(fmaxf(dot3(N, normalize3(Vv + Ld)), 0.0f), mat.shininess);
+                            r.diffuse = ((lc * (df * att)) * Lt.intensity) * dc; r.specular = ((lc * (sp * att)) * Lt.intensity) * dc;
+                        }
+                    }
+                } else if (Lt.type == 1u) {
+                    const V3 Ld = normalize3(mk3(-Lt.direction[0], -Lt.direction[1], -Lt.direction[2]));
+                    if (fp.cooktorrance) r = cook_torrance(dc, lc, N, Vv, Ld, normalize3(Vv + Ld), rough, metal);
+                    else {
+                        const float df = fmaxf(dot3(N, Ld), 0.0f), sp = powf(fmaxf(dot3(N, normalize3(Vv + Ld)), 0.0f), mat.shininess);
+                        r.diffuse = ((lc * df) * Lt.intensity) * dc; r.specular = ((lc * sp) * Lt.intensity) * dc;
+                    }
+                }
+                if (Lt.shadow_caster) { const float sf = 1.0f - calc_shadow_factor(a.shadow, fc.S, lsp); r.diffuse = r.diffuse * sf; r.specular = r.specular * sf; }
+                dsum = dsum + r.diffuse; ssum = ssum + r.specular;
+            }
+            if (!fp.enable_diffuse) dsum = mk3(0.f, 0.f, 0.f);
+            if (!fp.enable_specular) ssum = mk3(0.f, 0.f, 0.f);
+            V3 col;
+            if (fp.enable_indirect) {
+                ConeCtx cx; cx.vol = a.vol; cx.vol_point = a.vol_point; cx.warp = a.warp; cx.D = fc.D; cx.L = fc.L;
+                cx.warp_texture = fp.warp_texture; cx.warp_voxels = fp.warp_voxels; cx.eye_tc = voxel_linear_position(eye, fp);
+                const V3 vp = voxel_linear_position(Pw, fp);
+                const float dirs[6][3] = {{0.f, 1.f, 0.f}, {0.f, 0.5f, 0.866025f}, {0.823639f, 0.5f, 0.267617f}, {0.509037f, 0.5f, -0.700629f},
+                                          {-0.5909037f, 0.5f, -0.700629f}, {-0.823639f, 0.5f, 0.267617f}};
+                const float wts[6] = {0.25f, 0.15f, 0.15f, 0.15f, 0.15f, 0.15f};
+                V4 ind = mk4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                for (int i = 0; i < 6; ++i) {
+                    const V3 dir = normalize3(tbn(mk3(dirs[i][0], dirs[i][1], dirs[i][2])));
+                    const V4 c = trace_cone(cx, vp, N, dir, fp.diffuse_cone.steps, fp.diffuse_cone.bias, fp.diffuse_cone.cone_angle, fp.diffuse_cone.cone_initial_height,
+                                            fp.diffuse_cone.lod_offset, fetches);
+                    ind = mk4(ind.x + wts[i] * c.x, ind.y + wts[i] * c.y, ind.z + wts[i] * c.z, ind.w + wts[i] * c.w);
+                }
+                const float occl = 1.0f - clampf(ind.w, 0.0f, 1.0f);
+                if (fp.enable_reflections) {
+                    float ang = fp.specular_cone.cone_angle;
+                    if (fp.specular_cone_angle_from_roughness && mat.roughness_tex >= 0) ang = fetch(mat.roughness_tex).x * kPI * 0.1f;
+                    const V3 I = Pw - eye;
+                    const V3 R = I - N * (2.0f * dot3(N, I));
+                    const V4 rc = trace_cone(cx, vp, N, R, fp.specular_cone.steps, fp.specular_cone.bias, ang, fp.specular_cone.cone_initial_height, fp.specular_cone.lod_offset, fetches);
+                    ind.x += rc.x * fp.reflect_scale; ind.y += rc.y * fp.reflect_scale; ind.z += rc.z * fp.reflect_scale;
+                }
+                const V3 indc = mk3(ind.x, ind.y, ind.z) * (dc * fp.ambient_scale);
+                col = (indc + dsum) + ssum;
+                if (fp.draw_occlusion) col = col * occl;
+            } else col = (dc * fp.ambient_scale + dsum) + ssum;
+            if (fp.enable_postprocess) {
+                col = mk3(col.x / (col.x + 1.0f), col.y / (col.y + 1.0f), col.z / (col.z + 1.0f));
+                const float g = 1.0f / 2.2f;
+                col = mk3(powf(col.x, g), powf(col.y, g), powf(col.z, g));
+            }
+            a.image[o] = pack_unorm(mk4(col.x, col.y, col.z, 1.0f));
+        }
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) fetches += __shfl_xor_sync(0xffffffffu, fetches, s);
+    if (lane == 0 && fetches) atomicAdd(&a.counters->cone_steps, (unsigned long long)fetches);
+}
+
+}  // namespace
+
+int vctk_cone_trace(vct_ctx* c) {
+    TraceArgs a{};
+    a.fc = c->d_fc; a.W = c->W; a.H = c->H;
+    // screen-tile sharding across ranks: contiguous bands of 8-row tiles
+    const int rows8 = (c->H + 7) / 8, ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
+    a.y_lo = (int)((long long)rows8 * r / ws) * 8; a.y_hi = (int)((long long)rows8 * (r + 1) / ws) * 8; if (a.y_hi > c->H) a.y_hi = c->H;
+    a.vis = c->d_vis; a.indices = c->d_indices; a.trimat = c->d_trimat; a.verts = c->d_vertices;
+    a.wpos = c->d_wpos; a.wnrm = c->d_wnrm; a.wT = c->d_wT; a.wB = c->d_wB; a.tex = c->d_tex; a.mats = c->d_mat; a.shadow = c->d_shadow;
+    const bool rad = c->h_fc.p.draw_radiance != 0;
+    a.vol = rad ? c->radiance_tex : c->color_tex; a.vol_point = rad ? c->radiance_tex_point : c->color_tex_point; a.warp = c->warp_tex;
+    a.image = c->d_image; a.counters = c->d_counters;
+    if (a.y_hi <= a.y_lo) return 0;
+    dim3 grid((c->W + 31) / 32, (a.y_hi - a.y_lo + 7) / 8);
+    k_cone_trace<<<grid, kThreads, 0, c->stream>>>(a);
+    VCT_LAUNCH_CHECK(c);
+    return 0;
+}

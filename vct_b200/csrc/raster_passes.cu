@@ -1,0 +1,303 @@
+// raster_passes.cu — depth producers: the light-space shadow map (a0) and the camera visibility buffer (a0').
+// Compiled with -fmad=false (coverage and depth are bit-exact vs the oracle).
+//
+//   shadow map   reference src/Application.cpp:212-233, simple.vert:15-22, reflectiveShadowMap.frag:34-38
+//                depth test LESS, back-face culling, depth = ndc.z*0.5+0.5 as float32, clear 1.0
+//   visibility   depth prepass + GL_EQUAL colour pass (src/Application.cpp:936-977, dither.frag:25-31):
+//                per pixel the nearest alpha-tested fragment, last-drawn wins among equal depths, stored as
+//                depthbits<<32 | (0xFFFFFFFF - drawIndex) and resolved with one 64-bit atomicMin
+//
+// Two kernels per pass.  k_raster_bin: one thread per triangle — transform, (near-)clip, fixed-point setup;
+// triangles with a small bounding box are rasterised on the spot, the others are cut into 32x8-pixel tiles
+// (trivially rejected tiles skipped) that the whole warp pushes onto a device work queue.  k_raster_tiles: a
+// persistent grid (CTAs = multiple of 148 SMs) pops tiles, one warp per tile, lane = pixel column, edge
+// functions stepped incrementally down the 8 rows.
+#include "raster.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSmallArea = 64;
+constexpr int kTileW = 32, kTileH = 8;
+
+struct TileSetup {               // 96 bytes, written once per big (sub-)triangle
+    TriSetup s;
+    uint32_t tri; int alpha_tex;
+};
+
+struct RasterArgs {
+    const FrameConst* fc; int W, H;
+    const uint32_t* indices; const int32_t* trimat; const float* verts; uint32_t n_tris;
+    const float4* wpos; const DevTexture* tex; const DevMaterial* mats;
+    unsigned* depth_bits; unsigned long long* vis;
+    TileSetup* setups; uint4* queue; unsigned queue_cap; unsigned setup_cap;
+    Counters* counters; unsigned* setup_count;
+};
+
+__device__ __forceinline__ void clip_verts(const RasterArgs& a, bool camera, uint32_t t, RV cv[3]) {
+    const FrameConst& fc = *a.fc;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 w = __ldg(a.wpos + __ldg(a.indices + 3 * (size_t)t + k));
+        const V4 c = camera ? mul44(fc.projection, mul44(fc.view, mk4(w.x, w.y, w.z, 1.0f))) : mul44(fc.lp, mul44(fc.lv, mk4(w.x, w.y, w.z, 1.0f)));
+        cv[k].x = c.x; cv[k].y = c.y; cv[k].z = c.z; cv[k].w = c.w;
+    }
+}
+__device__ __forceinline__ void load_uv(const RasterArgs& a, uint32_t t, float uv[3][2]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t vi = __ldg(a.indices + 3 * (size_t)t + k);
+        uv[k][0] = __ldg(a.verts + 14 * (size_t)vi + 6); uv[k][1] = __ldg(a.verts + 14 * (size_t)vi + 7);
+    }
+}
+// near-plane clip (z >= -w), intersections computed from the inside vertex (watertight across shared edges)
+__device__ __forceinline__ int clip_near(const RV in[3], RV out[2][3]) {
+    float d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d[i] = in[i].z + in[i].w;
+    RV poly[4]; int n = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int j = (i + 1) % 3;
+        const bool ii = d[i] >= 0.0f, jj = d[j] >= 0.0f;
+        if (ii) poly[n++] = in[i];
+        if (ii != jj) {
+            const RV a = ii ? in[i] : in[j], b = ii ? in[j] : in[i];
+            const float da = ii ? d[i] : d[j], db = ii ? d[j] : d[i];
+            const float t = da / (da - db);
+            RV r; r.x = (b.x - a.x) * t + a.x; r.y = (b.y - a.y) * t + a.y; r.z = (b.z - a.z) * t + a.z; r.w = (b.w - a.w) * t + a.w;
+            poly[n++] = r;
+        }
+    }
+    if (n < 3) return 0;
+    out[0][0] = poly[0]; out[0][1] = poly[1]; out[0][2] = poly[2];
+    if (n == 4) { out[1][0] = poly[0]; out[1][1] = poly[2]; out[1][2] = poly[3]; return 2; }
+    return 1;
+}
+
+// perspective-correct barycentrics of the unclipped triangle (2D homogeneous edge functions)
+struct Homog { float a[3], b[3], c[3]; };
+__device__ __forceinline__ Homog homog_setup(const RV v[3]) {
+    Homog h;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const RV p = v[(i + 1) % 3], q = v[(i + 2) % 3];
+        h.a[i] = p.y * q.w - q.y * p.w; h.b[i] = q.x * p.w - p.x * q.w; h.c[i] = p.x * q.y - q.x * p.y;
+    }
+    return h;
+}
+__device__ __forceinline__ void homog_eval(const Homog& h, float nx, float ny, float l[3]) {
+    float b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b[i] = (h.a[i] * nx + h.b[i] * ny) + h.c[i];
+    const float s = (b[0] + b[1]) + b[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) l[i] = b[i] / s;
+}
+
+// alpha test of reflectiveShadowMap.frag:35 / dither.frag:26-31: discard iff alpha.r < 0.1
+struct AlphaCtx { bool on; const DevTexture* tex; float uv[3][2]; float rho2; Homog hg; };
+template <bool CAMERA>
+__device__ __forceinline__ void alpha_setup(const RasterArgs& a, uint32_t t, int alpha_tex, const RV cv_unclipped[3], AlphaCtx& ac) {
+    ac.on = alpha_tex >= 0;
+    if (!ac.on) return;
+    ac.tex = a.tex + alpha_tex;
+    load_uv(a, t, ac.uv);
+    if (CAMERA) ac.hg = homog_setup(cv_unclipped);
+    else ac.rho2 = tri_rho2_affine(cv_unclipped, ac.uv, a.W, a.H, *ac.tex);
+}
+template <bool CAMERA>
+__device__ __forceinline__ bool alpha_pass(const RasterArgs& a, const AlphaCtx& ac, int px, int py, const float l[3]) {
+    if (!ac.on) return true;
+    if (!CAMERA) {
+        const float u = interp1(l, ac.uv[0][0], ac.uv[1][0], ac.uv[2][0]), v = interp1(l, ac.uv[0][1], ac.uv[1][1], ac.uv[2][1]);
+        return !(sample2d(*ac.tex, u, v, ac.rho2).x < 0.1f);
+    }
+    const float nx = ((float)px + 0.5f) / (float)a.W * 2.0f - 1.0f, ny = ((float)py + 0.5f) / (float)a.H * 2.0f - 1.0f;
+    float lb[3], lx[3], ly[3];
+    homog_eval(ac.hg, nx, ny, lb); homog_eval(ac.hg, nx + 2.0f / (float)a.W, ny, lx); homog_eval(ac.hg, nx, ny + 2.0f / (float)a.H, ly);
+    const float u = interp1(lb, ac.uv[0][0], ac.uv[1][0], ac.uv[2][0]), v = interp1(lb, ac.uv[0][1], ac.uv[1][1], ac.uv[2][1]);
+    const float ux = interp1(lx, ac.uv[0][0], ac.uv[1][0], ac.uv[2][0]) - u, vx = interp1(lx, ac.uv[0][1], ac.uv[1][1], ac.uv[2][1]) - v;
+    const float uy = interp1(ly, ac.uv[0][0], ac.uv[1][0], ac.uv[2][0]) - u, vy = interp1(ly, ac.uv[0][1], ac.uv[1][1], ac.uv[2][1]) - v;
+    const float ax = ux * (float)ac.tex->w, bx = vx * (float)ac.tex->h, ay = uy * (float)ac.tex->w, by = vy * (float)ac.tex->h;
+    return !(sample2d(*ac.tex, u, v, maxsel(ax * ax + bx * bx, ay * ay + by * by)).x < 0.1f);
+}
+
+template <bool CAMERA>
+__device__ __forceinline__ void depth_write(const RasterArgs& a, int px, int py, float z, uint32_t t) {
+    const float d = z * 0.5f + 0.5f;
+    const unsigned db = __float_as_uint(d);
+    const size_t o = (size_t)py * a.W + px;
+    if (CAMERA) {
+        const unsigned long long key = (unsigned long long)db << 32 | (0xFFFFFFFFu - t);
+        if (key < a.vis[o]) atomicMin(a.vis + o, key);
+    } else {
+        if (db < a.depth_bits[o]) atomicMin(a.depth_bits + o, db);
+    }
+}
+
+// Is the pixel-centre box [bx0,bx1]x[by0,by1] entirely outside one of the edges?
+__device__ __forceinline__ bool tile_rejected(const TriSetup& s, int bx0, int by0, int bx1, int by1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+        const long long ex = s.X[b] - s.X[a], ey = s.Y[b] - s.Y[a];
+        // E = ex*(Py - Ya) - ey*(Px - Xa) is maximised at Py = (ex>0 ? top : bottom), Px = (ey>0 ? left : right)
+        const long long Py = 256ll * (ex > 0 ? by1 : by0) + 128, Px = 256ll * (ey > 0 ? bx0 : bx1) + 128;
+        if (ex * (Py - s.Y[a]) - ey * (Px - s.X[a]) + s.bias[k] < 0) return true;
+    }
+    return false;
+}
+
+template <bool CAMERA>
+__global__ void __launch_bounds__(kThreads) k_raster_bin(RasterArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t n_round = (a.n_tris + 31u) & ~31u;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+        RV cv[3]; RV sub[2][3]; int nsub = 0; int alpha_tex = -1;
+        TriSetup S[2]; bool valid[2] = {false, false}, big[2] = {false, false};
+        if (t < a.n_tris) {
+            clip_verts(a, CAMERA, t, cv);
+            if (CAMERA) nsub = clip_near(cv, sub);
+            else { nsub = 1; sub[0][0] = cv[0]; sub[0][1] = cv[1]; sub[0][2] = cv[2]; }
+            for (int q = 0; q < nsub; ++q) {
+                valid[q] = tri_setup(sub[q], a.W, a.H, true, S[q]);
+                if (valid[q]) big[q] = (S[q].x1 - S[q].x0 + 1) * (S[q].y1 - S[q].y0 + 1) > kSmallArea;
+            }
+            if (valid[0] || valid[1]) alpha_tex = a.mats[__ldg(a.trimat + t)].alpha_tex;
+        }
+        // ---- small (sub-)triangles: rasterise now
+        if ((valid[0] && !big[0]) || (valid[1] && !big[1])) {
+            AlphaCtx ac; alpha_setup<CAMERA>(a, t, alpha_tex, cv, ac);
+            for (int q = 0; q < nsub; ++q) {
+                if (!valid[q] || big[q]) continue;
+                const TriSetup& s = S[q];
+                for (int py = s.y0; py <= s.y1; ++py)
+                    for (int px = s.x0; px <= s.x1; ++px) {
+                        float l[3];
+                        if (!tri_cover(s, px, py, l)) continue;
+                        const float z = interp1(l, s.z[0], s.z[1], s.z[2]);
+                        if (z < -1.0f || z > 1.0f) continue;
+                        if (!alpha_pass<CAMERA>(a, ac, px, py, l)) continue;
+                        depth_write<CAMERA>(a, px, py, z, t);
+                    }
+            }
+        }
+        // ---- big (sub-)triangles: the warp enumerates their tiles together
+        for (int q = 0; q < 2; ++q) {
+            unsigned todo = __ballot_sync(0xffffffffu, big[q]);
+            while (todo) {
+                const int src = __ffs(todo) - 1; todo &= todo - 1;
+                unsigned slot = 0;
+                if (lane == src) {
+                    slot = atomicAdd(a.setup_count, 1u);
+                    if (slot < a.setup_cap) { TileSetup ts; ts.s = S[q]; ts.tri = t; ts.alpha_tex = alpha_tex; a.setups[slot] = ts; }
+                    else a.counters->overflow = 1u;
+                }
+                slot = __shfl_sync(0xffffffffu, slot, src);
+                const int x0 = __shfl_sync(0xffffffffu, S[q].x0, src), x1 = __shfl_sync(0xffffffffu, S[q].x1, src);
+                const int y0 = __shfl_sync(0xffffffffu, S[q].y0, src), y1 = __shfl_sync(0xffffffffu, S[q].y1, src);
+                if (slot >= a.setup_cap) continue;
+                __syncwarp();
+                __threadfence_block();
+                const TriSetup s = a.setups[slot].s;                       // L1/L2 hit; written by lane `src` above
+                const int tx0 = x0 / kTileW, tx1 = x1 / kTileW, ty0 = y0 / kTileH, ty1 = y1 / kTileH;
+                const int ntx = tx1 - tx0 + 1, nt = ntx * (ty1 - ty0 + 1);
+                for (int base = 0; base < nt; base += 32) {
+                    const int i = base + lane;
+                    bool keep = false; int tx = 0, ty = 0;
+                    if (i < nt) {
+                        tx = tx0 + i % ntx; ty = ty0 + i / ntx;
+                        keep = !tile_rejected(s, max(tx * kTileW, x0), max(ty * kTileH, y0), min(tx * kTileW + kTileW - 1, x1), min(ty * kTileH + kTileH - 1, y1));
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (!m) continue;
+                    unsigned qbase = 0;
+                    if (lane == 0) qbase = atomicAdd(&a.counters->tile_queue_count, (unsigned)__popc(m));
+                    qbase = __shfl_sync(0xffffffffu, qbase, 0);
+                    if (keep) {
+                        const unsigned pos = qbase + __popc(m & ((1u << lane) - 1u));
+                        if (pos < a.queue_cap) a.queue[pos] = make_uint4(slot, (unsigned)tx, (unsigned)ty, 0u);
+                        else a.counters->overflow = 1u;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool CAMERA>
+__global__ void __launch_bounds__(kThreads) k_raster_tiles(RasterArgs a) {
+    const int lane = threadIdx.x & 31;
+    const unsigned n_items = min(a.counters->tile_queue_count, a.queue_cap);
+    const unsigned warps = gridDim.x * (kThreads / 32);
+    for (unsigned item = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); item < n_items; item += warps) {
+        const uint4 it = __ldg(a.queue + item);
+        const TileSetup& ts = a.setups[it.x];
+        const TriSetup s = ts.s;
+        const uint32_t t = ts.tri; const int alpha_tex = ts.alpha_tex;
+        AlphaCtx ac; ac.on = false;
+        if (alpha_tex >= 0) { RV cv[3]; clip_verts(a, CAMERA, t, cv); alpha_setup<CAMERA>(a, t, alpha_tex, cv, ac); }
+        const int px = (int)it.y * kTileW + lane;
+        const int py0 = max((int)it.z * kTileH, s.y0), py1 = min((int)it.z * kTileH + kTileH - 1, s.y1);
+        if (px < s.x0 || px > s.x1) continue;
+        // incremental edge functions down the column (exact: integers)
+        long long E[3], dEy[3];
+        const long long Px = 256ll * px + 128, Py = 256ll * py0 + 128;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int aa = (k + 1) % 3, bb = (k + 2) % 3;
+            E[k] = (long long)(s.X[bb] - s.X[aa]) * (Py - s.Y[aa]) - (long long)(s.Y[bb] - s.Y[aa]) * (Px - s.X[aa]);
+            dEy[k] = 256ll * (s.X[bb] - s.X[aa]);
+        }
+        const float fa = (float)s.area;
+        for (int py = py0; py <= py1; ++py) {
+            if (E[0] + s.bias[0] >= 0 && E[1] + s.bias[1] >= 0 && E[2] + s.bias[2] >= 0) {
+                const float e0 = (float)E[0] / fa, e1 = (float)E[1] / fa, e2 = (float)E[2] / fa;
+                float l[3]; l[0] = e0; l[1] = s.swapped ? e2 : e1; l[2] = s.swapped ? e1 : e2;
+                const float z = interp1(l, s.z[0], s.z[1], s.z[2]);
+                if (!(z < -1.0f || z > 1.0f) && alpha_pass<CAMERA>(a, ac, px, py, l)) depth_write<CAMERA>(a, px, py, z, t);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) E[k] += dEy[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill_u32(unsigned* __restrict__ p, size_t n, unsigned v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void __launch_bounds__(kThreads) k_fill_u64(unsigned long long* __restrict__ p, size_t n, unsigned long long v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_reset_queue(Counters* c, unsigned* setup_count) { c->tile_queue_count = 0; *setup_count = 0; }
+
+template <bool CAMERA>
+int run_raster(vct_ctx* c) {
+    RasterArgs a{};
+    a.fc = c->d_fc; a.W = CAMERA ? c->W : c->S; a.H = CAMERA ? c->H : c->S;
+    a.indices = c->d_indices; a.trimat = c->d_trimat; a.verts = c->d_vertices; a.n_tris = (uint32_t)c->n_tris;
+    a.wpos = c->d_wpos; a.tex = c->d_tex; a.mats = c->d_mat;
+    a.depth_bits = reinterpret_cast<unsigned*>(c->d_shadow); a.vis = c->d_vis;
+    a.setups = reinterpret_cast<TileSetup*>(c->d_setup); a.queue = c->d_tile_queue; a.queue_cap = (unsigned)c->tile_queue_cap;
+    a.setup_cap = (unsigned)(2 * c->n_tris + 64); a.counters = c->d_counters;
+    a.setup_count = &c->d_counters->setup_count;
+    const size_t npx = (size_t)a.W * a.H;
+    const int fill_grid = (int)std::min<size_t>((npx + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 32);
+    if (CAMERA) k_fill_u64<<<fill_grid, kThreads, 0, c->stream>>>(c->d_vis, npx, ~0ull);
+    else k_fill_u32<<<fill_grid, kThreads, 0, c->stream>>>(a.depth_bits, npx, 0x3F800000u);
+    VCT_LAUNCH_CHECK(c);
+    k_reset_queue<<<1, 1, 0, c->stream>>>(c->d_counters, a.setup_count); VCT_LAUNCH_CHECK(c);
+    if (!c->n_tris) return 0;
+    const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
+    k_raster_bin<CAMERA><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c);
+    k_raster_tiles<CAMERA><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c);
+    return 0;
+}
+
+}  // namespace
+
+size_t vctk_tile_setup_bytes() { return sizeof(TileSetup); }
+int vctk_shadowmap(vct_ctx* c) { return run_raster<false>(c); }
+int vctk_visibility(vct_ctx* c) { return run_raster<true>(c); }

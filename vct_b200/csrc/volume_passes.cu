@@ -1,0 +1,395 @@
+// volume_passes.cu — the HBM-bound voxel-space passes (compiled with -fmad=false: bit-exact vs the oracle).
+//
+//   k_clear            glClearTexImage of voxelColor/voxelNormal           reference src/Application.cpp:686-687
+//   k_transfer         transferVoxels.comp:29-70 fused with the radiance clear of Application.cpp:762-764
+//   k_inject           injectRadiance.comp:40-103
+//   k_fill_holes       voxelFillHoles.comp:8-36 (+ the copy back, Application.cpp:867-872)
+//   k_mip_box2(_small) filterRadiance.comp:25-35 (BOX2), k_mip_generic for BOX3/CUBE (:36-58)
+//   k_publish          linear level -> level of the cudaMipmappedArray the cone tracer samples
+//   dead variants      setVoxelOpacity.comp, temporalRadianceFilter.comp, filter3d.comp, normalizeVoxels.comp
+//
+// Data layout: every volume level is a linear uint32[d^3], x fastest (RGBA8, R in bits 0-7).  All streaming
+// kernels move 16 bytes per thread per access (4 voxels) and are launched with enough CTAs to fill 148 SMs
+// several times over; grid-stride where the element count is large.
+#include <cuda_fp16.h>
+
+#include "raster.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+static inline int grid_for(size_t items, int threads, int max_waves = 16) {
+    size_t g = (items + threads - 1) / threads;
+    const size_t cap = (size_t)VCT_SM_COUNT * 8 * max_waves;      // 8 CTAs of 256 threads per SM
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+// ------------------------------------------------------------------------------------------------ clear
+__global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4* __restrict__ b, size_t n16) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        a[i] = z;
+        if (b) b[i] = z;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- transfer
+// One thread = 4 voxels (one 16-byte load of voxelColor).  Writes voxelColor back only where a fragment
+// landed; writes EVERY radiance voxel (0 where empty), which is the reference's clear + conditional store.
+__global__ void __launch_bounds__(kThreads) k_transfer(uint4* __restrict__ color, uint4* __restrict__ radiance, size_t n16,
+                                                       float opacity, int temporal, float decay, Counters* __restrict__ counters) {
+    unsigned uniq = 0, maxfrag = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 cw = color[i];
+        uint32_t c[4] = {cw.x, cw.y, cw.z, cw.w};
+        uint32_t r[4] = {0, 0, 0, 0};
+        uint4 pw = make_uint4(0, 0, 0, 0);
+        if (temporal) pw = radiance[i];
+        const uint32_t prev[4] = {pw.x, pw.y, pw.z, pw.w};
+        bool dirty = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            V4 v = unpack_unorm(c[k]);
+            if (v.w > 0.0f) {
+                uniq++;
+                maxfrag = max(maxfrag, f2u_trunc(255.0f * v.w));
+                if (opacity > 0.0f) v.w = opacity;
+                c[k] = pack_unorm(v);
+                dirty = true;
+            }
+            v.x = v.y = v.z = 0.0f;
+            if (temporal) {
+                const V4 p = unpack_unorm(prev[k]);
+                const float a = 1.0f - decay;
+                v = mk4(mixf(p.x, v.x, a), mixf(p.y, v.y, a), mixf(p.z, v.z, a), mixf(p.w, v.w, a));
+                r[k] = pack_unorm(v);
+            } else if (v.w > 0.0f) r[k] = pack_unorm(v);
+        }
+        if (dirty) color[i] = make_uint4(c[0], c[1], c[2], c[3]);
+        radiance[i] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    // block reduction -> one atomic pair per CTA
+    __shared__ unsigned s_u[kThreads / 32], s_m[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { uniq += __shfl_xor_sync(0xffffffffu, uniq, o); maxfrag = max(maxfrag, __shfl_xor_sync(0xffffffffu, maxfrag, o)); }
+    if ((threadIdx.x & 31) == 0) { s_u[threadIdx.x >> 5] = uniq; s_m[threadIdx.x >> 5] = maxfrag; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned u = 0, m = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { u += s_u[w]; m = max(m, s_m[w]); }
+        if (u) atomicAdd(&counters->unique_voxels, u);
+        if (m) atomicMax(&counters->max_fragments_per_voxel, m);
+    }
+}
+
+// setVoxelOpacity.comp:18-35 (dead variant)
+__global__ void __launch_bounds__(kThreads) k_set_voxel_opacity(uint32_t* __restrict__ color, uint32_t* __restrict__ radiance, size_t n,
+                                                                float opacity, Counters* __restrict__ counters) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        V4 v = unpack_unorm(color[i]);
+        if (v.w > 0.0f) {
+            atomicAdd(&counters->unique_voxels, 1u);
+            atomicMax(&counters->max_fragments_per_voxel, f2u_trunc(255.0f * v.w));
+            if (opacity > 0.0f) v.w = opacity;
+            color[i] = pack_unorm(v);
+            radiance[i] = pack_unorm(mk4(0.f, 0.f, 0.f, v.w));
+        }
+    }
+}
+// temporalRadianceFilter.comp:9-19 (dead variant)
+__global__ void __launch_bounds__(kThreads) k_temporal_decay(uint32_t* __restrict__ vol, size_t n, float decay) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const V4 v = unpack_unorm(vol[i]);
+        vol[i] = pack_unorm(mk4(v.x * decay, v.y * decay, v.z * decay, v.w * decay));
+    }
+}
+// normalizeVoxels.comp:19-42 (dead variant; RGBA16F volumes)
+__global__ void __launch_bounds__(kThreads) k_normalize_f16(__half* __restrict__ col, __half* __restrict__ nrm, uint32_t* __restrict__ radiance,
+                                                            size_t n, float opacity, Counters* __restrict__ counters) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = __half2float(col[4 * i + k]);
+        if (c[3] > 0.0f) {
+            atomicAdd(&counters->unique_voxels, 1u);
+            atomicMax(&counters->max_fragments_per_voxel, f2u_trunc(c[3]));
+            const float a = c[3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[k] = c[k] / a;
+            if (opacity > 0.0f) c[3] = opacity;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) col[4 * i + k] = __float2half_rn(c[k]);
+            radiance[i] = pack_unorm(mk4(0.f, 0.f, 0.f, c[3]));
+        }
+        float m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = __half2float(nrm[4 * i + k]);
+        if (m[3] > 0.0f) {
+            const float a = m[3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nrm[4 * i + k] = __float2half_rn(m[k] / a);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- inject
+// One thread per shadow-map texel, 32x8 tiles so that a warp reads one 128-byte row segment of depth.
+// The bilinear fetch at a texel CORNER averages the 2x2 neighbourhood (x-1..x, y-1..y): staged through a
+// (32+1)x(8+1) shared tile so each depth value is read from HBM once.
+__global__ void __launch_bounds__(256) k_inject(const FrameConst* __restrict__ fcp, const float* __restrict__ shadow,
+                                                const uint32_t* __restrict__ color, const uint32_t* __restrict__ normal,
+                                                const uint16_t* __restrict__ warpmap, uint32_t* __restrict__ radiance) {
+    const FrameConst& fc = *fcp;
+    const int S = fc.S, D = fc.D;
+    __shared__ float tile[9][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+    for (int i = threadIdx.x; i < 9 * 33; i += 256) {
+        const int lx = i % 33, ly = i / 33;
+        tile[ly][lx] = shadow_texel(shadow, S, bx + lx - 1, by + ly - 1);
+    }
+    __syncthreads();
+    const int x = bx + tx, y = by + ty;
+    if (x >= S || y >= S) return;
+    const float tu = (float)x / (float)S, tv = (float)y / (float)S;
+    float d;
+    {   // shadow_linear(tu, tv) with texels taken from the tile when the footprint is the expected one
+        const float fxp = tu * (float)S - 0.5f, fyp = tv * (float)S - 0.5f;
+        const float fx0 = floorf(fxp), fy0 = floorf(fyp);
+        const int x0 = (int)fx0, y0 = (int)fy0; const float fx = fxp - fx0, fy = fyp - fy0;
+        const int lx = x0 - bx + 1, ly = y0 - by + 1;
+        if (lx >= 0 && lx + 1 < 33 && ly >= 0 && ly + 1 < 9) {
+            const float top = tile[ly][lx] * (1.0f - fx) + tile[ly][lx + 1] * fx;
+            const float bot = tile[ly + 1][lx] * (1.0f - fx) + tile[ly + 1][lx + 1] * fx;
+            d = top * (1.0f - fy) + bot * fy;
+        } else d = shadow_linear(shadow, S, tu, tv, 0, 0);
+    }
+    const float nx = tu * 2.0f - 1.0f, ny = tv * 2.0f - 1.0f, nz = d * 2.0f - 1.0f;
+    const V4 w = mul44(fc.ls_inverse, mk4(nx, ny, nz, 1.0f));
+    V3 vp = get_voxel_position(mk3(w.x, w.y, w.z), fc.p, warpmap);
+    vp = mk3((float)D * vp.x, (float)D * vp.y, (float)D * vp.z);
+    int ix, iy, iz;
+    if (!to_voxel_index(vp, D, ix, iy, iz)) return;
+    if (iz < fc.z_lo || iz >= fc.z_hi) return;                    // z-slab ownership (multi-GPU)
+    const size_t o = ((size_t)iz * D + iy) * D + ix;
+    const uint32_t cw = __ldg(color + o);
+    if (!fc.p.radiance_lighting) { radiance[o] = cw; return; }   // packUnorm4x8(unpackUnorm4x8(c)) == c for every byte
+    V4 c = unpack_unorm(cw);
+    const V4 n4 = unpack_unorm(__ldg(normal + o));
+    const V3 n = mk3(2.0f * n4.x - 1.0f, 2.0f * n4.y - 1.0f, 2.0f * n4.z - 1.0f);
+    const vct_light& L0 = fc.lights[0];
+    V3 lpv = get_voxel_position(mk3(L0.position[0], L0.position[1], L0.position[2]), fc.p, warpmap);
+    lpv = mk3((float)D * lpv.x, (float)D * lpv.y, (float)D * lpv.z);
+    const V3 lv = normalize3(lpv - mk3((float)ix, (float)iy, (float)iz));
+    const float diff = maxsel(dot3(n, lv), 0.0f);
+    c.x = (diff * L0.color[0]) * c.x; c.y = (diff * L0.color[1]) * c.y; c.z = (diff * L0.color[2]) * c.z;
+    radiance[o] = pack_unorm(c);
+}
+
+// ------------------------------------------------------------------------------------------- fill holes
+__global__ void __launch_bounds__(kThreads) k_fill_holes(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int D, int z_lo, int z_hi) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = z_lo + blockIdx.z;
+    if (x >= D || y >= D || z >= z_hi) return;
+    const size_t o = ((size_t)z * D + y) * D + x;
+    const uint32_t w = __ldg(src + o);
+    V4 cur = unpack_unorm(w);
+    if (cur.w == 0.0f) {
+        float count = 0.0f;
+        for (int i = -1; i <= 1; ++i) for (int j = -1; j <= 1; ++j) for (int k = -1; k <= 1; ++k) {
+            const int xx = x + i, yy = y + j, zz = z + k;
+            if (xx < 0 || yy < 0 || zz < 0 || xx >= D || yy >= D || zz >= D) continue;
+            const uint32_t nw = __ldg(src + ((size_t)zz * D + yy) * D + xx);
+            if ((nw >> 24) != 0u) { const V4 v = unpack_unorm(nw); cur = mk4(cur.x + v.x, cur.y + v.y, cur.z + v.z, cur.w + v.w); count += 1.0f; }
+        }
+        if (count > 0.0f) cur = mk4(cur.x / count, cur.y / count, cur.z / count, cur.w / count);
+    }
+    dst[o] = pack_unorm(cur);
+}
+
+// -------------------------------------------------------------------------------------------------- mip
+// BOX2: dst texel = 0.125 * sum of 8 children, accumulated in the shader's offset order
+// (0,0,0),(0,0,1),(0,1,0),(0,1,1),(1,0,0),(1,0,1),(1,1,0),(1,1,1) where each (i,j,k) is an (x,y,z) offset.
+// A 256-entry table of b/255.0f lives in shared memory (the division is exact-rounded, a table read is cheaper).
+__device__ __forceinline__ void acc_word(float acc[4], uint32_t w, const float* __restrict__ lut) {
+    acc[0] += lut[w & 255u]; acc[1] += lut[(w >> 8) & 255u]; acc[2] += lut[(w >> 16) & 255u]; acc[3] += lut[w >> 24];
+}
+__device__ __forceinline__ uint32_t finish_word(const float acc[4], float k) {
+    return pack_unorm(mk4(acc[0] * k, acc[1] * k, acc[2] * k, acc[3] * k));
+}
+// one thread -> 4 consecutive dst texels in x: 8 x 16-byte loads, 1 x 16-byte store.  Requires Dd % 4 == 0.
+__global__ void __launch_bounds__(kThreads) k_mip_box2(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int Ds, int zd_lo, int zd_hi) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
+    const int Dd = Ds >> 1, qx = Dd >> 2;                       // quads per dst row
+    const size_t total = (size_t)qx * Dd * (zd_hi - zd_lo);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % qx); const size_t r = i / qx;
+        const int y = (int)(r % Dd), z = zd_lo + (int)(r / Dd);
+        const uint4* row00 = reinterpret_cast<const uint4*>(src + ((size_t)(2 * z) * Ds + 2 * y) * Ds) + 2 * q;        // (y0,z0)
+        const uint4* row10 = reinterpret_cast<const uint4*>(src + ((size_t)(2 * z) * Ds + 2 * y + 1) * Ds) + 2 * q;    // (y1,z0)
+        const uint4* row01 = reinterpret_cast<const uint4*>(src + ((size_t)(2 * z + 1) * Ds + 2 * y) * Ds) + 2 * q;    // (y0,z1)
+        const uint4* row11 = reinterpret_cast<const uint4*>(src + ((size_t)(2 * z + 1) * Ds + 2 * y + 1) * Ds) + 2 * q;
+        uint4 a[2], b[2], c[2], d[2];
+        a[0] = __ldg(row00); a[1] = __ldg(row00 + 1); b[0] = __ldg(row01); b[1] = __ldg(row01 + 1);
+        c[0] = __ldg(row10); c[1] = __ldg(row10 + 1); d[0] = __ldg(row11); d[1] = __ldg(row11 + 1);
+        const uint32_t* A = reinterpret_cast<const uint32_t*>(a); const uint32_t* B = reinterpret_cast<const uint32_t*>(b);
+        const uint32_t* Cc = reinterpret_cast<const uint32_t*>(c); const uint32_t* Dv = reinterpret_cast<const uint32_t*>(d);
+        uint32_t out[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            // offsets in shader order: x0:(y0z0),(y0z1),(y1z0),(y1z1) then x1: same
+            acc_word(acc, A[2 * t], lut); acc_word(acc, B[2 * t], lut); acc_word(acc, Cc[2 * t], lut); acc_word(acc, Dv[2 * t], lut);
+            acc_word(acc, A[2 * t + 1], lut); acc_word(acc, B[2 * t + 1], lut); acc_word(acc, Cc[2 * t + 1], lut); acc_word(acc, Dv[2 * t + 1], lut);
+            out[t] = finish_word(acc, 0.125f);
+        }
+        reinterpret_cast<uint4*>(dst + ((size_t)z * Dd + y) * Dd)[q] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+}
+// generic (any size, any kernel mode) — used for the small top levels and for BOX3 / CUBE
+__global__ void __launch_bounds__(kThreads) k_mip_generic(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int Ds, int mode, int zd_lo, int zd_hi) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
+    const int Dd = Ds >> 1;
+    const size_t total = (size_t)Dd * Dd * (zd_hi - zd_lo);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % Dd); const size_t r = i / Dd; const int y = (int)(r % Dd), z = zd_lo + (int)(r / Dd);
+        const int sx = 2 * x, sy = 2 * y, sz = 2 * z;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}; float k = 0.125f;
+        auto ld = [&](int xx, int yy, int zz) { if (xx < 0 || yy < 0 || zz < 0 || xx >= Ds || yy >= Ds || zz >= Ds) return; acc_word(acc, __ldg(src + ((size_t)zz * Ds + yy) * Ds + xx), lut); };
+        if (mode == 0) { for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) ld(sx + a, sy + b, sz + c); }
+        else if (mode == 1) { for (int a = -1; a <= 1; ++a) for (int b = -1; b <= 1; ++b) for (int c = -1; c <= 1; ++c) ld(sx + a, sy + b, sz + c); k = 0.037f; }
+        else { ld(sx, sy, sz); ld(sx, sy, sz + 1); ld(sx, sy + 1, sz); ld(sx + 1, sy, sz); ld(sx, sy, sz - 1); ld(sx, sy - 1, sz); ld(sx - 1, sy, sz); k = 0.143f; }
+        dst[((size_t)z * Dd + y) * Dd + x] = finish_word(acc, k);
+    }
+}
+// filter3d.comp:16-47 (dead variant): sampler fetches at texel centres with lod 0 -> mag NEAREST -> texel reads
+__global__ void __launch_bounds__(kThreads) k_filter3d(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int Ds) {
+    const int Dd = Ds >> 1;
+    const size_t total = (size_t)Dd * Dd * Dd;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % Dd); const size_t r = i / Dd; const int y = (int)(r % Dd), z = (int)(r / Dd);
+        const float h = 0.5f * (1.0f / (float)Ds);
+        const int bx = (int)floorf(((float)x / (float)Dd + h) * (float)Ds), by = (int)floorf(((float)y / (float)Dd + h) * (float)Ds),
+                  bz = (int)floorf(((float)z / (float)Dd + h) * (float)Ds);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) {
+            const int xx = bx + a, yy = by + b, zz = bz + c;
+            if (xx < 0 || yy < 0 || zz < 0 || xx >= Ds || yy >= Ds || zz >= Ds) continue;
+            const V4 t = unpack_unorm(__ldg(src + ((size_t)zz * Ds + yy) * Ds + xx));
+            acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+        }
+        dst[i] = finish_word(acc, 0.125f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- publish
+// linear level -> surface of the mipmapped array (block-linear), 16 bytes per thread along x
+__global__ void __launch_bounds__(kThreads) k_publish(const uint32_t* __restrict__ src, cudaSurfaceObject_t surf, int d) {
+    const int qx = d >= 4 ? d >> 2 : 1;
+    const size_t total = (size_t)qx * d * d;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % qx); const size_t r = i / qx; const int y = (int)(r % d), z = (int)(r / d);
+        if (d >= 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)z * d + y) * d) + q);
+            surf3Dwrite(v, surf, q * 16, y, z);
+        } else {
+            for (int x = 0; x < d; ++x) surf3Dwrite(__ldg(src + ((size_t)z * d + y) * d + x), surf, x * 4, y, z);
+        }
+    }
+}
+
+}  // namespace
+
+// ============================================================================================ host side
+int vctk_clear_voxels(vct_ctx* c) {
+    // only this rank's z-slab of level 0 is cleared (single GPU: the whole volume)
+    const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
+    k_clear<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_normal + off), n / 4);
+    VCT_LAUNCH_CHECK(c);
+    return 0;
+}
+int vctk_transfer(vct_ctx* c) {
+    const vct_frame_params& p = c->h_fc.p;
+    const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
+    k_transfer<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_radiance + off), n / 4,
+                                                                    p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters);
+    VCT_LAUNCH_CHECK(c);
+    return 0;
+}
+int vctk_inject(vct_ctx* c) {
+    dim3 grid((c->S + 31) / 32, (c->S + 7) / 8);
+    k_inject<<<grid, 256, 0, c->stream>>>(c->d_fc, c->d_shadow, c->d_color, c->d_normal, c->d_warpmap, c->d_radiance);
+    VCT_LAUNCH_CHECK(c);
+    return 0;
+}
+int vctk_fill_holes(vct_ctx* c) {
+    dim3 grid((c->D + 31) / 32, (c->D + 7) / 8, c->z_hi - c->z_lo);
+    k_fill_holes<<<grid, kThreads, 0, c->stream>>>(c->d_radiance, c->d_scratch, c->D, c->z_lo, c->z_hi);
+    VCT_LAUNCH_CHECK(c);
+    const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
+    VCT_CHECK(c, cudaMemcpyAsync(c->d_radiance + off, c->d_scratch + off, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+// levels 1..L-1 (the reference's last loop iteration targets a non-existent level: Application.cpp:889-902)
+int vctk_mip(vct_ctx* c, int which, int mode) {
+    uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
+    for (int l = 0; l + 1 < c->L; ++l) {
+        const int Ds = level_dim(c->D, l), Dd = Ds >> 1;
+        if (Dd < 1) break;
+        // z-slab of the destination level owned by this rank (whole level when the slab is thinner than a texel)
+        int zd_lo = c->z_lo >> (l + 1), zd_hi = c->z_hi >> (l + 1);
+        if (c->cfg.world_size <= 1 || zd_hi <= zd_lo) { zd_lo = 0; zd_hi = Dd; }
+        const uint32_t* src = base + c->level_off[l]; uint32_t* dst = base + c->level_off[l + 1];
+        if (mode == 0 && Dd % 4 == 0) {
+            const size_t items = (size_t)(Dd / 4) * Dd * (zd_hi - zd_lo);
+            k_mip_box2<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, zd_lo, zd_hi);
+        } else {
+            const size_t items = (size_t)Dd * Dd * (zd_hi - zd_lo);
+            k_mip_generic<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, mode, zd_lo, zd_hi);
+        }
+        VCT_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+int vctk_publish(vct_ctx* c, int which) {
+    uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
+    cudaSurfaceObject_t* surf = which == VCT_VOL_COLOR ? c->color_surf : c->radiance_surf;
+    for (int l = 0; l < c->L; ++l) {
+        const int d = level_dim(c->D, l);
+        const size_t items = (size_t)(d >= 4 ? d / 4 : 1) * d * d;
+        k_publish<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(base + c->level_off[l], surf[l], d);
+        VCT_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+int vctk_set_voxel_opacity(vct_ctx* c, float opacity) {
+    const size_t n = (size_t)c->D * c->D * c->D;
+    k_set_voxel_opacity<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(c->d_color, c->d_radiance, n, opacity, c->d_counters);
+    VCT_LAUNCH_CHECK(c);
+    return 0;
+}
+int vctk_temporal_radiance_filter(vct_ctx* c, float decay) {
+    const size_t n = (size_t)c->D * c->D * c->D;
+    k_temporal_decay<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(c->d_radiance, n, decay);
+    VCT_LAUNCH_CHECK(c);
+    return 0;
+}
+int vctk_filter3d(vct_ctx* c, int which, int src_level) {
+    if (src_level < 0 || src_level + 1 >= c->L) { c->error = "filter3d: level out of range"; return 1; }
+    uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
+    const int Ds = level_dim(c->D, src_level);
+    const size_t n = (size_t)(Ds / 2) * (Ds / 2) * (Ds / 2);
+    k_filter3d<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(base + c->level_off[src_level], base + c->level_off[src_level + 1], Ds);
+    VCT_LAUNCH_CHECK(c);
+    return 0;
+}
+int vctk_normalize_voxels_f16(vct_ctx* c, void* col, void* nrm, float opacity) {
+    const size_t n = (size_t)c->D * c->D * c->D;
+    k_normalize_f16<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>((__half*)col, (__half*)nrm, c->d_radiance, n, opacity, c->d_counters);
+    VCT_LAUNCH_CHECK(c);
+    return 0;
+}
