@@ -717,6 +717,45 @@ extern "C" void orc_filter3d(int Ds, const unsigned* src, unsigned* dst) {
 }
 
 // =================================================================================================== a9
+namespace {
+// One axis of calculateWarpPosition (src/main.cpp:101-123) == generateWarpmap.frag:77-90:
+//   previousPartial = occupied ? partial-1 : partial ; offset = l*(index-previousPartial) + h*previousPartial ;
+//   inner = fract*(occupied ? h : l) ; warped = (offset+inner)/dim
+inline float warp_axis(float lo, float hi, bool occd, int part, int cid, float fr, int n) {
+    const float res = occd ? hi : lo;
+    const float prev = occd ? (float)part - 1.0f : (float)part;
+    const float off = lo * ((float)cid - prev) + hi * prev;
+    const float inner = fr * res;
+    return (off + inner) / (float)n;
+}
+}  // namespace
+
+// The reference's only worked example of the warp algorithm: the `#if 0` 2D rig of src/main.cpp:20-127 (same
+// arithmetic as shaders/testWarpTexture.frag:21-56).  cells = n x n row-major [y][x]; fixed_low > 0 reproduces
+// the rig's constant l (main.cpp:77-81), otherwise the production table (Application.cpp:346-370) is used.
+extern "C" void orc_warp_rig(int n, const float* cells, float fixed_low, float high, float low, const float* tc, int npts,
+                             float* out, int* part_x, int* part_y, float* wl, float* wh) {
+    for (int row = 0; row < n; ++row) { int s = 0; for (int x = 0; x < n; ++x) { s += cells[row * n + x] > 0.5f ? 1 : 0; part_x[row * n + x] = s; } }
+    for (int col = 0; col < n; ++col) { int s = 0; for (int y = 0; y < n; ++y) { s += cells[y * n + col] > 0.5f ? 1 : 0; part_y[y * n + col] = s; } }
+    if (fixed_low > 0.0f) {
+        for (int occ = 0; occ <= n; ++occ) {
+            if (occ == 0 || occ == n) { wl[occ] = wh[occ] = 1.0f; continue; }
+            const int empty = n - occ;
+            wl[occ] = fixed_low; wh[occ] = ((float)n - fixed_low * (float)empty) / (float)occ;
+        }
+    } else orc_warp_weight_table(n, high, low, wl, wh);
+    for (int i = 0; i < npts; ++i) {
+        float idx[2], fr[2];
+        for (int k = 0; k < 2; ++k) { const float lt = tc[2 * i + k] * (float)n; idx[k] = std::trunc(lt); fr[k] = lt - idx[k]; }
+        const int x = (int)idx[0], y = (int)idx[1];
+        const bool occd = cells[y * n + x] > 0.5f;
+        const int tot[2] = {part_x[y * n + n - 1], part_y[(n - 1) * n + x]};
+        const int part[2] = {part_x[y * n + x], part_y[y * n + x]};
+        const int cid[2] = {x, y};
+        for (int k = 0; k < 2; ++k) out[2 * i + k] = warp_axis(wl[tot[k]], wh[tot[k]], occd, part[k], cid[k], fr[k], n);
+    }
+}
+
 extern "C" void orc_warp_weight_table(int dim, float high, float low, float* lo, float* hi) {     // Application.cpp:346-370
     for (int occ = 0; occ <= dim; ++occ) {
         if (occ == 0 || occ == dim) { lo[occ] = hi[occ] = 1.0f; continue; }
@@ -774,11 +813,7 @@ extern "C" void orc_warpmap(const unsigned* occ, const vct_frame_params* fp, uns
         const int cid[3] = {c.x, c.y, c.z};
         float out[4];
         for (int k = 0; k < 3; ++k) {
-            const float res = c.occd ? hi[k] : lo[k];
-            const float prev = c.occd ? (float)part[k] - 1.0f : (float)part[k];
-            const float off = lo[k] * ((float)cid[k] - prev) + hi[k] * prev;
-            const float inner = fr[k] * res;
-            const float warped = (off + inner) / (float)n;
+            const float warped = warp_axis(lo[k], hi[k], c.occd, part[k], cid[k], fr[k], n);
             const bool use = fp->warp_texture_linear ? false : fp->warp_texture_axes[k] != 0;
             out[k] = use ? warped : tc[k];
         }

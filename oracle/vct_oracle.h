@@ -73,6 +73,8 @@ void orc_shade(const orc_scene*, const vct_frame_params*, int W, int H, const un
 unsigned orc_rgba8_avg(unsigned stored, float r, float g, float b);     /* voxelize.frag:111-139, one insertion */
 unsigned orc_pack_unorm4x8(float r, float g, float b, float a);
 void orc_warp_weight_table(int dim, float high, float low, float* low_out, float* high_out); /* Application.cpp:346-370 */
+void orc_warp_rig(int n, const float* cells, float fixed_low, float high, float low, const float* tc, int npts,
+                  float* out, int* part_x, int* part_y, float* wl, float* wh);                 /* src/main.cpp:20-127 */
 float orc_cone_trace_const(int D, int L, unsigned voxel_word, const vct_cone_settings* cs, int* steps_out);
 int orc_num_threads(void);
 

@@ -179,15 +179,6 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
         alloc((void**)&c->d_tile_queue, c->tile_queue_cap * 16) || alloc((void**)&c->d_fc, sizeof(FrameConst)) || alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
-    {   // warp map texture: RGBA16 unorm, LINEAR, CLAMP_TO_EDGE (reference src/Application.cpp:383-389)
-        cudaChannelFormatDesc fd = cudaCreateChannelDesc<ushort4>();
-        if (cudaMalloc3DArray(&c->warp_arr, &fd, make_cudaExtent(N, N, N)) != cudaSuccess) return bail("warp array");
-        cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeArray; rd.res.array.array = c->warp_arr;
-        cudaTextureDesc td = {};
-        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-        td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
-        if (cudaCreateTextureObject(&c->warp_tex, &rd, &td, nullptr) != cudaSuccess) return bail("warp texture");
-    }
     for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("sync");
     *out = c;
@@ -199,8 +190,6 @@ int vct_destroy(vct_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
-    if (c->warp_tex) cudaDestroyTextureObject(c->warp_tex);
-    if (c->warp_arr) cudaFreeArray(c->warp_arr);
     for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, (void*)c->d_key[0], (void*)c->d_key[1],
                     (void*)c->d_val[0], (void*)c->d_val[1], (void*)c->d_frag_color, (void*)c->d_frag_normal, (void*)c->d_hist, (void*)c->d_tile_queue, (void*)c->d_fc, (void*)c->d_counters,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_models, (void*)c->d_nmats, (void*)c->d_wpos,
@@ -385,11 +374,6 @@ int vct_write_volume(vct_ctx* c, int which, int level, const void* in) {
     cudaSetDevice(c->cfg.device);
     void* p; size_t b; if (volume_ptr(c, which, level, &p, &b)) return 1;
     VCT_CHECK(c, cudaMemcpyAsync(p, in, b, cudaMemcpyHostToDevice, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
-    if (which == VCT_VOL_WARPMAP) {
-        cudaMemcpy3DParms cp = {}; cp.srcPtr = make_cudaPitchedPtr(c->d_warpmap, VCT_WARP_DIM * 8, VCT_WARP_DIM, VCT_WARP_DIM);
-        cp.dstArray = c->warp_arr; cp.extent = make_cudaExtent(VCT_WARP_DIM, VCT_WARP_DIM, VCT_WARP_DIM); cp.kind = cudaMemcpyDeviceToDevice;
-        VCT_CHECK(c, cudaMemcpy3DAsync(&cp, c->stream));
-    }
     return 0;
 }
 int vct_read_image(vct_ctx* c, void* rgba8) {

@@ -119,7 +119,6 @@ struct vct_ctx {
     cudaSurfaceObject_t radiance_surf[VCT_MAX_LEVELS]{}, color_surf[VCT_MAX_LEVELS]{};
     // warp
     uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
-    cudaArray_t warp_arr = nullptr; cudaTextureObject_t warp_tex = 0;
     // shadow map / visibility / image
     float* d_shadow = nullptr; unsigned long long* d_vis = nullptr; uint32_t* d_image = nullptr;
     // voxel fragments

@@ -121,10 +121,5 @@ int vctk_warpmap(vct_ctx* c) {
     k_warpmap<<<1, 1024, 0, c->stream>>>(c->d_occ, c->d_fc, reinterpret_cast<ushort4*>(c->d_warpmap), reinterpret_cast<ushort4*>(c->d_wlo),
                                          reinterpret_cast<ushort4*>(c->d_whi), reinterpret_cast<uint8_t*>(c->d_scan_tmp));
     VCT_LAUNCH_CHECK(c);
-    // the cone tracer samples the warp map through a hardware 3D texture (LINEAR, CLAMP_TO_EDGE)
-    cudaMemcpy3DParms cp = {};
-    cp.srcPtr = make_cudaPitchedPtr(c->d_warpmap, N * sizeof(ushort4), N, N);
-    cp.dstArray = c->warp_arr; cp.extent = make_cudaExtent(N, N, N); cp.kind = cudaMemcpyDeviceToDevice;
-    VCT_CHECK(c, cudaMemcpy3DAsync(&cp, c->stream));
     return 0;
 }
