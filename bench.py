@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""bench.py — GI frame time of the B200 pipeline on the BASELINE.json configuration (Sponza, 256^3 voxels, 1920x1080).
+
+One "step" = one frame of the GI hot path (BASELINE metric): clear + voxelise + transferVoxels + injectRadiance +
+mip chain(s) + per-pixel cone trace, everything recomputed every frame.  The shadow map and the visibility buffer
+(producer passes of the reference's render(), SURVEY.md §8 a0/a0') are inputs: they are generated on the device
+during warm-up and their cost is reported separately in `passes_ms`.
+
+  value      device-timed ms/frame (CUDA events on the library's stream), inputs resident in HBM
+  e2e        the same frame through the C ABI with HOST buffers: frame parameters + lights + actor transforms go
+             host->device and the final RGBA8 image comes back into pinned host memory, every step
+  roofline   dominant kernel of the step vs the measured HBM copy peak; `roofline_passes` lists every kernel
+  cpu_baseline / --impl reference   the CPU oracle (a port of the reference's GLSL; the GLSL itself needs an
+             OpenGL stack that neither the build container nor the GPU box has) on the box's host cores
+
+N > 1 (torchrun, one rank per GPU): the volume is sharded by z-slab for clear/voxelise/transfer/inject/mip, the
+radiance pyramid is all-gathered over NVLink (NCCL), the cone trace is sharded by screen band, and rank 0 gathers
+the image bands.  Same frame, so scaling is "strong".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "GI frame ms (voxelize+inject+mip+cone trace) Sponza 256^3 @1080p"
+CONFIG_INDEX = 3          # SURVEY.md §8(d) numbering (BASELINE.json configs[2])
+LEVELS, SHADOW = 6, 4096
+
+
+def peaks():
+    try:
+        m = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(m["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_workload(width=None, height=None, dim=None):
+    from vct_b200 import params as P
+    from vct_b200 import scene as S
+    sc, cam, (vmin, vmax, vc), D, (W, H), extra = S.config_scene(CONFIG_INDEX)
+    W, H, D = width or W, height or H, dim or D
+    p = P.default_params(W, H, cam, sc.lights[0], voxel_min=vmin, voxel_max=vmax, voxel_center=vc)
+    return sc, p, D, W, H, extra.get("data", "procedural")
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1])); pw.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------- algorithmic bytes
+def algorithmic_bytes(D, L, S, W, H, T, F, U, chains):
+    """SURVEY.md §8(d) / BASELINE.md §4 per-pass byte counts, attributed to this build's kernels."""
+    d3 = D ** 3
+    mip = sum(4 * (D >> l) ** 3 * (1 + 1 / 8) for l in range(L - 1))
+    pyr = sum(4 * (D >> l) ** 3 for l in range(L))
+    return {
+        "k_clear": 8 * d3,                                   # voxelColor + voxelNormal level 0
+        "voxelize": 96 * T + 16 * F,                         # all voxeliser kernels together
+        "k_transfer": 4 * d3 + 4 * d3 + 8 * U,               # colour read + (fused) radiance clear + 2 stores per occupied voxel
+        "k_inject": 4 * S * S,                               # + 8 N_in scattered (not counted: lower bound)
+        "k_mip_box2": mip * chains,
+        "k_publish": 2 * pyr,                                # linear pyramid -> texture array (this build's extra copy)
+        "k_cone_trace": pyr + 8 * W * H + 4 * W * H,         # compulsory HBM: pyramid once + visibility + image
+    }
+
+
+VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_raster_count", "k_scan_reduce", "k_scan_apply", "k_set_frag_count", "k_voxel_raster_emit",
+                    "k_sort_hist", "k_sort_rowscan", "k_sort_scatter", "k_voxel_apply", "k_voxel_raster_cas", "k_voxel_raster_max")
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def oracle_gi_frame(o, p, rows_stride=1):
+    """The five GI passes of the metric on the CPU oracle; returns per-pass seconds (shade scaled to the full image
+    when only every rows_stride-th row is shaded)."""
+    t = {}
+    for name, fn in (("voxelize", lambda: o.voxelize(p)), ("transfer", lambda: o.transfer(p)), ("inject", lambda: o.inject(p)),
+                     ("mip", lambda: (o.mip("radiance"), o.mip("color") if p.mip_color_chain else None)),
+                     ("cone_trace", lambda: o.shade(p, 0, None, rows_stride))):
+        t0 = time.perf_counter(); fn(); t[name] = time.perf_counter() - t0
+    t["cone_trace"] *= rows_stride
+    return t
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (oracle port; the GLSL reference needs OpenGL, absent
+    on this image) on all host cores.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from tests.oracle_lib import Oracle, lib
+    sc, p, D, W, H, data = build_workload()
+    o = Oracle(sc, D, LEVELS, SHADOW, W, H)
+    cores = lib().orc_num_threads()
+    o.shadowmap(p); o.visibility(p)                              # producers: inputs of the step
+    t0 = time.perf_counter(); first = oracle_gi_frame(o, p); full = time.perf_counter() - t0     # untimed probe = warm-up 0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    stride = 1
+    other = sum(v for k, v in first.items() if k != "cone_trace")
+    while other + first["cone_trace"] / stride > budget and stride < 64:
+        stride *= 2
+    for _ in range(max(0, args.warmup - 1)):
+        oracle_gi_frame(o, p, stride)
+    per, tot = [], 0.0
+    for _ in range(args.steps):
+        t = oracle_gi_frame(o, p, stride); per.append(t); tot += sum(t.values())
+    ms = 1e3 * tot / args.steps
+    sample = (f"full frame: voxelize+transfer+inject+mip at full size; cone trace on every {stride}th image row, time x{stride}"
+              if stride > 1 else "full frame, all five GI passes at full size")
+    passes = {k: round(1e3 * statistics.mean(t[k] for t in per), 3) for k in per[0]}
+    line = {"impl": "reference", "metric": METRIC, "value": round(ms, 3), "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": data,
+            "config": {"workload": "config 3: PBR Sponza, 256^3 voxels, 6 levels, 1920x1080, 4096^2 shadow map, diffuse+specular cones", "dim": D, "width": W, "height": H},
+            "cpu_baseline": {"value": round(ms, 3), "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(ms, 3), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "passes_ms": passes, "gpu_launches": 0,
+            "note": "CPU oracle (C++/OpenMP restatement of the reference GLSL); the reference's own GLSL cannot run: no OpenGL/EGL/Mesa on this image"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from vct_b200 import params as P
+    from vct_b200.pipeline import Pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(1, args.gpus) and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sc, p, D, W, H, data = build_workload(args.width, args.height, args.dim)
+    chains = 2 if p.mip_color_chain else 1
+    g = Pipeline(sc, D, LEVELS, SHADOW, W, H, device=local, rank=rank, world_size=world)
+    from vct_b200.sharded import ShardedFrame
+    fr = ShardedFrame(g, p, world, rank)                          # world == 1: plain vct_gi_passes on the library stream
+    stream = fr.stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # producers + warm-up (whole reference frame graph, so every buffer the step reads exists)
+    fr.producers()
+    for _ in range(max(3, args.warmup)):
+        fr.step()
+    barrier()
+
+    # ---- timed region: exactly K steps, device events on the launching stream, max over ranks
+    g.set_profiling(0)
+    g.launch_count(reset=True)
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        fr.step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = g.launch_count()
+    clk = clocks.stop() if clocks else None
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_total = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64); dist.all_reduce(lt); launches = int(lt.item())
+    ms = ms_total / args.steps
+
+    # ---- e2e: host buffers in, image out, every step
+    host_img = torch.empty(W * H, dtype=torch.int32).pin_memory()
+    h2d = C.sizeof(P.FrameParams) + 80 * len(sc.lights) + (64 + 36) * len(sc.meshes)
+    d2h = W * H * 4
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        fr.step_e2e(host_img)
+    e1.record(stream)
+    barrier()
+    e2e_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_total], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_total = float(t.item())
+    e2e_ms = e2e_total / args.steps
+
+    # ---- per-kernel breakdown: profiled frames (one event per kernel) right after the timed region
+    kern, passes = {}, {}
+    nprof = args.profile_frames
+    g.set_profiling(2)
+    for _ in range(nprof):
+        for name, (ns, n) in fr.profiled_step().items():
+            a = kern.setdefault(name, [0.0, 0]); a[0] += ns / 1e6 / nprof; a[1] += n / nprof
+    g.set_profiling(1)
+    passes = fr.pass_times()
+    info = g.counters()
+    steps_cone = g.cone_steps()
+    g.set_profiling(0)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        T = sc.n_tris
+        ab = algorithmic_bytes(D, LEVELS, SHADOW, W, H, T, info.total_fragments, info.unique_voxels, chains)
+        kt = {k: v[0] for k, v in kern.items()}
+        kt["voxelize"] = sum(kt.get(k, 0.0) for k in VOXELIZE_KERNELS)
+        roofs = []
+        for name, nbytes in ab.items():
+            t_ms = kt.get(name, 0.0)
+            if t_ms <= 0:
+                continue
+            ach = nbytes / (t_ms * 1e-3) / 1e9
+            roofs.append({"kernel": name, "bound": "hbm" if name != "k_cone_trace" else "hbm (compulsory bytes; the kernel is L1/texture-bound)",
+                          "ms": round(t_ms, 4), "algorithmic_bytes": int(nbytes), "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4)})
+        step_kernel_ms = sum(v[0] for k, v in kern.items() if not k.startswith(("memset", "h2d", "<")))
+        dom = max((r for r in roofs), key=lambda r: r["ms"]) if roofs else None
+        roofline = None
+        if dom:
+            roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                        "traffic": None, "peak_source": peak_src, "ms": dom["ms"], "share_of_step": round(dom["ms"] / max(step_kernel_ms, 1e-9), 3),
+                        "algorithmic_bytes": dom["algorithmic_bytes"],
+                        "timing": f"per-kernel CUDA events on the library stream, mean of {nprof} profiled frames run right after the timed region"}
+            if dom["kernel"] == "k_cone_trace":
+                roofline["note"] = "cone trace is bound by L1/texture + L2 throughput (the pyramid is re-read ~100x per frame from cache), see cone_steps_per_s"
+        voxel_bytes = sum(ab[k] for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_box2"))
+        voxel_ms = sum(kt.get(k, 0.0) for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_box2"))
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from tests.oracle_lib import Oracle, lib
+            o = Oracle(sc, D, LEVELS, SHADOW, W, H)
+            o.shadowmap(p); o.visibility(p)
+            t = oracle_gi_frame(o, p)
+            cpu = {"value": round(1e3 * sum(t.values()), 1), "unit": "ms", "cores": lib().orc_num_threads(), "kind": "port",
+                   "sample": "one full frame of the five GI passes at full size (producers excluded), single run",
+                   "passes_ms": {k: round(1e3 * v, 1) for k, v in t.items()}}
+        line = {"metric": METRIC, "value": round(ms, 4), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": round(ms, 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": data,
+                "config": {"workload": "config 3: PBR Sponza, 256^3 voxels, 6 levels, 1920x1080, 4096^2 shadow map, diffuse+specular cones, full per-frame revoxelisation",
+                           "dim": D, "levels": LEVELS, "width": W, "height": H, "shadow": SHADOW, "triangles": T,
+                           "voxelize_mode": "deterministic running average (canonical draw order)" if p.deterministic else "free-running CAS",
+                           "mip_chains": chains, "parallelism": fr.describe(),
+                           "l2": "no explicit flush: one frame touches ~370 MiB (3 voxel volumes + 2 pyramids + texture array + shadow map) > 126 MB L2, and each frame starts by clearing 128 MiB"},
+                "e2e": {"value": round(e2e_ms, 4), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_passes": roofs,
+                "voxel_passes": {"ms": round(voxel_ms, 4), "algorithmic_bytes": int(voxel_bytes), "achieved_gbs": round(voxel_bytes / max(voxel_ms, 1e-9) / 1e6, 1),
+                                 "frac_of_hbm_peak": round(voxel_bytes / max(voxel_ms, 1e-9) / 1e6 / peak, 4)},
+                "kernels_ms": {k: round(v[0], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},
+                "passes_ms": passes, "cone_steps": steps_cone, "cone_steps_per_s": round(steps_cone / max(kt.get("k_cone_trace", 0.0), 1e-9) * 1e3, 0),
+                "counters": {"total_fragments": info.total_fragments, "unique_voxels": info.unique_voxels, "max_fragments_per_voxel": info.max_fragments_per_voxel},
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile-frames", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 200 and args.warmup == 20:
+            args.steps, args.warmup = 10, 3
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -114,8 +114,11 @@ typedef struct {
     double transfer_ns, gbuffer_ns, warpmap_ns, clear_ns, exchange_ns;
 } vct_timings;
 
+typedef struct { char name[40]; double ns; unsigned launches; unsigned _pad; } vct_kernel_time;
+
 enum { VCT_VOL_COLOR = 0, VCT_VOL_NORMAL = 1, VCT_VOL_RADIANCE = 2, VCT_VOL_OCCUPANCY = 3, VCT_VOL_WARPMAP = 4,
-       VCT_VOL_WARP_WEIGHTS_LOW = 5, VCT_VOL_WARP_WEIGHTS_HIGH = 6 };
+       VCT_VOL_WARP_WEIGHTS_LOW = 5, VCT_VOL_WARP_WEIGHTS_HIGH = 6,
+       VCT_BUF_IMAGE = 7 /* device pointer only: RGBA8 rows, padded to world_size equal bands of 8-row tiles */ };
 
 /* ---- lifetime: VCT ctor/dtor/remake, Application::init --------------------------- Application.h:109-156 */
 int  vct_create(const vct_config* cfg, vct_ctx** out);
@@ -174,8 +177,13 @@ int  vct_sync(vct_ctx*);
 void*  vct_device_ptr(vct_ctx*, int which, int level);
 size_t vct_level_bytes(vct_ctx*, int which, int level);
 void*  vct_stream(vct_ctx*);                                        /* cudaStream_t */
+int    vct_set_stream(vct_ctx*, void* cuda_stream);                 /* enqueue on a caller-owned stream (NULL: private) */
 /* kernels of this library launched since the last reset (bench.py's gpu_launches) */
 unsigned long long vct_launch_count(vct_ctx*, int reset);
+/* GLTimer granularity (reference src/Graphics/GLTimer.h:6-87 brackets passes): 0 = no events, 1 = one event per
+ * pass (default; feeds vct_get_timings), 2 = additionally one event per kernel (feeds vct_get_kernel_times). */
+int    vct_set_profiling(vct_ctx*, int level);
+int    vct_get_kernel_times(vct_ctx*, vct_kernel_time* out, int max_entries);   /* returns the entry count, <0 on error */
 
 #ifdef __cplusplus
 }

@@ -1008,9 +1008,18 @@ inline V3 postprocess(V3 c) {                            // phong.frag:210-218
 }
 }  // namespace
 
+extern "C" void orc_shade_rows(const orc_scene* sc, const vct_frame_params* fp, int W, int H, int y_lo, int y_hi, int y_stride,
+                               const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
+                               const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps);
 extern "C" void orc_shade(const orc_scene* sc, const vct_frame_params* fp, int W, int H, const unsigned long long* vis, int D, int L,
                           const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
                           const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps) {
+    orc_shade_rows(sc, fp, W, H, 0, H, 1, vis, D, L, radiance_pyr, color_pyr, shadow, S, warpmap, image, cone_steps);
+}
+// rows y_lo, y_lo + y_stride, ... < y_hi only (bench.py's bounded CPU sample; other rows of `image` are untouched)
+extern "C" void orc_shade_rows(const orc_scene* sc, const vct_frame_params* fp, int W, int H, int y_lo, int y_hi, int y_stride,
+                               const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
+                               const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps) {
     Prepared P = prepare(sc, true);
     Vol rad, colv; rad.D = colv.D = D; rad.L = colv.L = L;
     { size_t off = 0; for (int l = 0; l < L; ++l) { rad.lv[l] = radiance_pyr + off; colv.lv[l] = color_pyr ? color_pyr + off : nullptr; const size_t d = std::max(1, D >> l); off += d * d * d; } }
@@ -1018,7 +1027,7 @@ extern "C" void orc_shade(const orc_scene* sc, const vct_frame_params* fp, int W
     const unsigned clear = pack_unorm({fp->clear_color[0], fp->clear_color[1], fp->clear_color[2], 1.0f});
     unsigned long long fetch_total = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : fetch_total)
-    for (int py = 0; py < H; ++py)
+    for (int py = y_lo; py < y_hi; py += y_stride)
         for (int px = 0; px < W; ++px) {
             const unsigned long long key = vis[(size_t)py * W + px];
             unsigned& out = image[(size_t)py * W + px];

@@ -69,6 +69,10 @@ void orc_shade(const orc_scene*, const vct_frame_params*, int W, int H, const un
                int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
                const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps);
 
+void orc_shade_rows(const orc_scene*, const vct_frame_params*, int W, int H, int y_lo, int y_hi, int y_stride,
+                    const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
+                    const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps);
+
 /* KAT helpers */
 unsigned orc_rgba8_avg(unsigned stored, float r, float g, float b);     /* voxelize.frag:111-139, one insertion */
 unsigned orc_pack_unorm4x8(float r, float g, float b, float a);

@@ -8,6 +8,7 @@
 
 thread_local std::string g_create_error;
 size_t vctk_tile_setup_bytes();
+size_t vctk_image_rows(const vct_ctx*);
 
 namespace {
 
@@ -105,14 +106,17 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     f.n_lights = c->n_lights; std::memcpy(f.lights, c->h_lights, sizeof f.lights);
     f.z_lo = c->z_lo; f.z_hi = c->z_hi;
     VCT_CHECK(c, cudaMemcpyAsync(c->d_fc, &f, sizeof f, cudaMemcpyHostToDevice, c->stream));
-    VCT_CHECK(c, cudaMemcpyAsync(c->d_tex, c->h_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES, cudaMemcpyHostToDevice, c->stream));
-    VCT_CHECK(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS, cudaMemcpyHostToDevice, c->stream));
+    if (c->tables_dirty) {                      // texture / material tables change only on upload
+        VCT_CHECK(c, cudaMemcpyAsync(c->d_tex, c->h_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES, cudaMemcpyHostToDevice, c->stream));
+        VCT_CHECK(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS, cudaMemcpyHostToDevice, c->stream));
+        c->tables_dirty = false;
+    }
     return 0;
 }
 
 enum { EV_START, EV_SHADOW, EV_WARP, EV_CLEAR, EV_VOXEL, EV_TRANSFER, EV_INJECT, EV_MIP, EV_GBUF, EV_TRACE, EV_COUNT };
 
-struct Graph { vct_ctx* c; bool timed; int rec(int e) { if (timed) { cudaError_t r = cudaEventRecord(c->ev[e], c->stream); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } } return 0; } };
+struct Graph { vct_ctx* c; bool timed; int rec(int e) { if (timed && c->profiling >= 1) { cudaError_t r = cudaEventRecord(c->ev[e], c->stream); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } } return 0; } };
 
 int ensure_color_texture(vct_ctx* c) {
     if (c->color_arr) return 0;
@@ -125,6 +129,7 @@ int ensure_scratch(vct_ctx* c) {
 }
 int zero_info(vct_ctx* c) {
     VCT_CHECK(c, cudaMemsetAsync(c->d_counters, 0, 3 * sizeof(unsigned), c->stream));     // glClearNamedBufferData, Application.cpp:581
+    vct_prof_mark(c, "memset");
     return 0;
 }
 int gi_body(vct_ctx* c, Graph& g) {
@@ -173,7 +178,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
     c->tile_queue_cap = (size_t)4 << 20;
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * 8) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
-        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, (size_t)c->W * c->H * 4) ||
+        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
         alloc((void**)&c->d_key[0], c->frag_cap * 4) || alloc((void**)&c->d_key[1], c->frag_cap * 4) || alloc((void**)&c->d_val[0], c->frag_cap * 4) || alloc((void**)&c->d_val[1], c->frag_cap * 4) ||
         alloc((void**)&c->d_frag_color, c->frag_cap * 16) || alloc((void**)&c->d_frag_normal, c->frag_cap * 16) || alloc((void**)&c->d_hist, (256 * 592 + 256) * 4) ||
         alloc((void**)&c->d_tile_queue, c->tile_queue_cap * 16) || alloc((void**)&c->d_fc, sizeof(FrameConst)) || alloc((void**)&c->d_counters, sizeof(Counters)) ||
@@ -197,7 +202,8 @@ int vct_destroy(vct_ctx* c) {
         cudaFree(p);
     for (void* p : c->tex_allocs) cudaFree(p);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto& ev : c->prof_pool) cudaEventDestroy(ev);
+    if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
@@ -244,6 +250,7 @@ int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels,
     size_t off = 0;
     for (int l = 0; l < levels; ++l) { t.level[l] = d + off; off += (size_t)std::max(1, width >> l) * std::max(1, height >> l) * channels; }
     c->n_textures = std::max(c->n_textures, tex + 1);
+    c->tables_dirty = true;
     return 0;
 }
 
@@ -254,6 +261,7 @@ int vct_set_material(vct_ctx* c, int material, const vct_material* m) {
     d.diffuse_tex = m->diffuse_tex; d.specular_tex = m->specular_tex; d.normal_tex = m->normal_tex; d.roughness_tex = m->roughness_tex; d.metallic_tex = m->metallic_tex; d.alpha_tex = m->alpha_tex;
     d.shininess = m->shininess; std::memcpy(d.diffuse, m->diffuse, 12);
     c->n_materials = std::max(c->n_materials, material + 1);
+    c->tables_dirty = true;
     return 0;
 }
 
@@ -276,7 +284,9 @@ int vct_set_lights(vct_ctx* c, const vct_light* lights, int n) {
 #define PASS_PROLOGUE                                   \
     if (!c) return 1;                                   \
     cudaSetDevice(c->cfg.device);                       \
-    if (upload_frame(c, p)) return 1;
+    vct_prof_begin(c);                                  \
+    if (upload_frame(c, p)) return 1;                   \
+    vct_prof_mark(c, "h2d_params");
 
 int vct_shadowmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_shadowmap(c); }
 int vct_occupancy(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_voxelize(c, true); }
@@ -290,6 +300,7 @@ int vct_cone_trace(vct_ctx* c, const vct_frame_params* p) {
     PASS_PROLOGUE;
     if (!p->draw_radiance && !c->color_arr) { if (ensure_color_texture(c) || vctk_publish(c, VCT_VOL_COLOR)) return 1; }
     VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
+    vct_prof_mark(c, "memset");
     return vctk_cone_trace(c);
 }
 int vct_mip(vct_ctx* c, int which) {
@@ -304,6 +315,7 @@ int vct_mip(vct_ctx* c, int which) {
 int vct_exchange(vct_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);
+    vct_prof_begin(c);
     const bool rad = c->h_fc.p.draw_radiance != 0;
     if (!rad && ensure_color_texture(c)) return 1;
     return vctk_publish(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR);
@@ -318,6 +330,7 @@ int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
     if (c->cfg.world_size > 1) return 0;                      // caller all-gathers, then vct_exchange + vct_cone_trace
     if (g.rec(EV_GBUF)) return 1;
     VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
+    vct_prof_mark(c, "memset");
     if (vctk_cone_trace(c)) return 1;
     return g.rec(EV_TRACE);
 }
@@ -334,6 +347,7 @@ int vct_frame(vct_ctx* c, const vct_frame_params* p) {
     if (c->cfg.world_size > 1) return 0;
     if (vctk_visibility(c) || g.rec(EV_GBUF)) return 1;
     VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
+    vct_prof_mark(c, "memset");
     if (vctk_cone_trace(c)) return 1;
     return g.rec(EV_TRACE);
 }
@@ -358,6 +372,7 @@ static int volume_ptr(vct_ctx* c, int which, int level, void** ptr, size_t* byte
         case VCT_VOL_WARPMAP: *ptr = c->d_warpmap; *bytes = N * N * N * 8; return 0;
         case VCT_VOL_WARP_WEIGHTS_LOW: *ptr = c->d_wlo; *bytes = N * N * N * 8; return 0;
         case VCT_VOL_WARP_WEIGHTS_HIGH: *ptr = c->d_whi; *bytes = N * N * N * 8; return 0;
+        case VCT_BUF_IMAGE: *ptr = c->d_image; *bytes = vctk_image_rows(c) * (size_t)c->W * 4; return 0;
     }
     return fail(c, "unknown volume");
 }
@@ -433,6 +448,40 @@ int vct_get_timings(vct_ctx* c, vct_timings* t) {
 void* vct_device_ptr(vct_ctx* c, int which, int level) { if (!c) return nullptr; void* p; size_t b; return volume_ptr(c, which, level, &p, &b) ? nullptr : p; }
 size_t vct_level_bytes(vct_ctx* c, int which, int level) { if (!c) return 0; void* p; size_t b; return volume_ptr(c, which, level, &p, &b) ? 0 : b; }
 void* vct_stream(vct_ctx* c) { return c ? (void*)c->stream : nullptr; }
+// Enqueue on a caller-owned stream (e.g. the stream torch.distributed's NCCL collectives run on) so that the
+// slab exchange needs no host synchronisation.  NULL restores a private stream.
+int vct_set_stream(vct_ctx* c, void* stream) {
+    if (!c) return 1;
+    cudaSetDevice(c->cfg.device);
+    VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { VCT_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    return 0;
+}
+int vct_set_profiling(vct_ctx* c, int level) {
+    if (!c) return 1;
+    if (level < 0 || level > 2) return fail(c, "vct_set_profiling: level 0 (off), 1 (per pass) or 2 (per kernel)");
+    c->profiling = level; c->prof_marks.clear(); c->prof_used = 0;
+    return 0;
+}
+// per-kernel device time of the calls since the last pass entry point (profiling level 2); returns the count
+int vct_get_kernel_times(vct_ctx* c, vct_kernel_time* out, int max_entries) {
+    if (!c || !out || max_entries < 1) return -1;
+    cudaSetDevice(c->cfg.device);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    int n = 0;
+    for (size_t i = 1; i < c->prof_marks.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->prof_marks[i - 1].second, c->prof_marks[i].second) != cudaSuccess) { cudaGetLastError(); continue; }
+        const char* name = c->prof_marks[i].first;
+        int k = 0;
+        while (k < n && std::strncmp(out[k].name, name, sizeof out[k].name - 1)) k++;
+        if (k == n) { if (n == max_entries) continue; std::memset(&out[n], 0, sizeof out[n]); std::strncpy(out[n].name, name, sizeof out[n].name - 1); n++; }
+        out[k].ns += (double)ms * 1e6; out[k].launches++;
+    }
+    return n;
+}
 unsigned long long vct_launch_count(vct_ctx* c, int reset) { if (!c) return 0; const unsigned long long n = c->launches; if (reset) c->launches = 0; return n; }
 
 }  // extern "C"

@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/vct_b200.h"
@@ -99,7 +100,7 @@ struct vct_ctx {
     // scene
     std::vector<HostMesh> meshes;
     std::vector<float> h_vertices; std::vector<uint32_t> h_indices; std::vector<int32_t> h_trimat; std::vector<int32_t> h_vactor;
-    bool scene_dirty = true;
+    bool scene_dirty = true, tables_dirty = true;
     size_t n_vertices = 0, n_tris = 0;
     float* d_vertices = nullptr;      // n x 14
     int32_t* d_vactor = nullptr;
@@ -134,6 +135,10 @@ struct vct_ctx {
     Counters* d_counters = nullptr; Counters h_counters{};
     // timing
     cudaEvent_t ev[32]{}; vct_timings timings{};
+    int profiling = 1;               // 0 none, 1 pass-level events (reference GLTimer semantics), 2 + one event per kernel
+    bool own_stream = true;
+    std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
+    std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
 };
 
 extern thread_local std::string g_create_error;
@@ -149,16 +154,28 @@ extern thread_local std::string g_create_error;
         }                                                                                       \
     } while (0)
 
-#define VCT_LAUNCH_CHECK(ctx)                                                                   \
+// Per-kernel profiling (vct_set_profiling level 2): one event is recorded after every launch; the time between
+// consecutive marks is attributed to the kernel named by the later mark (launches on one stream run back to back).
+static inline void vct_prof_mark(vct_ctx* c, const char* name) {
+    if (c->profiling < 2) return;
+    if (c->prof_used == c->prof_pool.size()) { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) return; c->prof_pool.push_back(e); }
+    cudaEvent_t e = c->prof_pool[c->prof_used++];
+    cudaEventRecord(e, c->stream);
+    c->prof_marks.push_back(std::make_pair(name, e));
+}
+static inline void vct_prof_begin(vct_ctx* c) { c->prof_used = 0; c->prof_marks.clear(); vct_prof_mark(c, "<begin>"); }
+
+#define VCT_LAUNCH_CHECK(ctx, name)                                                             \
     do {                                                                                        \
         (ctx)->launches++;                                                                      \
         cudaError_t e__ = cudaGetLastError();                                                   \
         if (e__ != cudaSuccess) {                                                               \
             char b__[512];                                                                      \
-            snprintf(b__, sizeof b__, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            snprintf(b__, sizeof b__, "%s:%d launch of %s -> %s", __FILE__, __LINE__, name, cudaGetErrorString(e__)); \
             (ctx)->error = b__;                                                                 \
             return 1;                                                                           \
         }                                                                                       \
+        vct_prof_mark((ctx), name);                                                             \
     } while (0)
 
 static inline int level_dim(int D, int l) { int d = D >> l; return d < 1 ? 1 : d; }
@@ -176,6 +193,7 @@ int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);
 int vctk_warpmap(vct_ctx*);
 int vctk_cone_trace(vct_ctx*);
+size_t vctk_image_rows(const vct_ctx*);
 int vctk_set_voxel_opacity(vct_ctx*, float);
 int vctk_temporal_radiance_filter(vct_ctx*, float);
 int vctk_filter3d(vct_ctx*, int which, int src_level);

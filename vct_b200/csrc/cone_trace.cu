@@ -14,6 +14,8 @@
 // otherwise trilinear + mip-linear, lambda clamped to the last level.
 // Thread mapping: a warp shades an 8x4 pixel tile so that the 32 cones marched in lock-step (same cone index,
 // same step) stay spatially coherent in the texture cache; a CTA of 8 warps covers 32x8 pixels.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -324,12 +326,19 @@ __global__ void __launch_bounds__(kThreads) k_cone_trace(TraceArgs a) {
 
 }  // namespace
 
+// rows of the image buffer: H rounded up so that it splits into world_size equal bands of whole 8-row tiles
+size_t vctk_image_rows(const vct_ctx* c) {
+    const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, rows8 = (c->H + 7) / 8;
+    return (size_t)((rows8 + ws - 1) / ws) * 8 * ws;
+}
+
 int vctk_cone_trace(vct_ctx* c) {
     TraceArgs a{};
     a.fc = c->d_fc; a.W = c->W; a.H = c->H;
-    // screen-tile sharding across ranks: contiguous bands of 8-row tiles
-    const int rows8 = (c->H + 7) / 8, ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
-    a.y_lo = (int)((long long)rows8 * r / ws) * 8; a.y_hi = (int)((long long)rows8 * (r + 1) / ws) * 8; if (a.y_hi > c->H) a.y_hi = c->H;
+    // screen sharding across ranks: world_size equal bands of whole 8-row tiles (the last may be short)
+    const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
+    const int band = (int)(vctk_image_rows(c) / ws);
+    a.y_lo = std::min(c->H, r * band); a.y_hi = std::min(c->H, (r + 1) * band);
     a.vis = c->d_vis; a.indices = c->d_indices; a.trimat = c->d_trimat; a.verts = c->d_vertices;
     a.wpos = c->d_wpos; a.wnrm = c->d_wnrm; a.wT = c->d_wT; a.wB = c->d_wB; a.tex = c->d_tex; a.mats = c->d_mat; a.shadow = c->d_shadow;
     const bool rad = c->h_fc.p.draw_radiance != 0;
@@ -338,6 +347,6 @@ int vctk_cone_trace(vct_ctx* c) {
     if (a.y_hi <= a.y_lo) return 0;
     dim3 grid((c->W + 31) / 32, (a.y_hi - a.y_lo + 7) / 8);
     k_cone_trace<<<grid, kThreads, 0, c->stream>>>(a);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_cone_trace");
     return 0;
 }

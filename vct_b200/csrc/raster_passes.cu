@@ -287,12 +287,12 @@ int run_raster(vct_ctx* c) {
     const int fill_grid = (int)std::min<size_t>((npx + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 32);
     if (CAMERA) k_fill_u64<<<fill_grid, kThreads, 0, c->stream>>>(c->d_vis, npx, ~0ull);
     else k_fill_u32<<<fill_grid, kThreads, 0, c->stream>>>(a.depth_bits, npx, 0x3F800000u);
-    VCT_LAUNCH_CHECK(c);
-    k_reset_queue<<<1, 1, 0, c->stream>>>(c->d_counters, a.setup_count); VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, CAMERA ? "k_fill_u64" : "k_fill_u32");
+    k_reset_queue<<<1, 1, 0, c->stream>>>(c->d_counters, a.setup_count); VCT_LAUNCH_CHECK(c, "k_reset_queue");
     if (!c->n_tris) return 0;
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
-    k_raster_bin<CAMERA><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c);
-    k_raster_tiles<CAMERA><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c);
+    k_raster_bin<CAMERA><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, CAMERA ? "k_raster_bin_camera" : "k_raster_bin_light");
+    k_raster_tiles<CAMERA><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, CAMERA ? "k_raster_tiles_camera" : "k_raster_tiles_light");
     return 0;
 }
 

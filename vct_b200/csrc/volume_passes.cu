@@ -309,7 +309,7 @@ int vctk_clear_voxels(vct_ctx* c) {
     // only this rank's z-slab of level 0 is cleared (single GPU: the whole volume)
     const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
     k_clear<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_normal + off), n / 4);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_clear");
     return 0;
 }
 int vctk_transfer(vct_ctx* c) {
@@ -317,21 +317,22 @@ int vctk_transfer(vct_ctx* c) {
     const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
     k_transfer<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_radiance + off), n / 4,
                                                                     p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_transfer");
     return 0;
 }
 int vctk_inject(vct_ctx* c) {
     dim3 grid((c->S + 31) / 32, (c->S + 7) / 8);
     k_inject<<<grid, 256, 0, c->stream>>>(c->d_fc, c->d_shadow, c->d_color, c->d_normal, c->d_warpmap, c->d_radiance);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_inject");
     return 0;
 }
 int vctk_fill_holes(vct_ctx* c) {
     dim3 grid((c->D + 31) / 32, (c->D + 7) / 8, c->z_hi - c->z_lo);
     k_fill_holes<<<grid, kThreads, 0, c->stream>>>(c->d_radiance, c->d_scratch, c->D, c->z_lo, c->z_hi);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_fill_holes");
     const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
     VCT_CHECK(c, cudaMemcpyAsync(c->d_radiance + off, c->d_scratch + off, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    vct_prof_mark(c, "memcpy_d2d");
     return 0;
 }
 // levels 1..L-1 (the reference's last loop iteration targets a non-existent level: Application.cpp:889-902)
@@ -342,16 +343,18 @@ int vctk_mip(vct_ctx* c, int which, int mode) {
         if (Dd < 1) break;
         // z-slab of the destination level owned by this rank (whole level when the slab is thinner than a texel)
         int zd_lo = c->z_lo >> (l + 1), zd_hi = c->z_hi >> (l + 1);
-        if (c->cfg.world_size <= 1 || zd_hi <= zd_lo) { zd_lo = 0; zd_hi = Dd; }
+        if (c->cfg.world_size <= 1) { zd_lo = 0; zd_hi = Dd; }
+        else if (zd_hi <= zd_lo) { c->error = "vct_mip: a mip level is thinner than one z-slab per rank (levels > log2(dim/world_size)+1 need a coarse-level exchange)"; return 1; }
         const uint32_t* src = base + c->level_off[l]; uint32_t* dst = base + c->level_off[l + 1];
         if (mode == 0 && Dd % 4 == 0) {
             const size_t items = (size_t)(Dd / 4) * Dd * (zd_hi - zd_lo);
             k_mip_box2<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, zd_lo, zd_hi);
+            VCT_LAUNCH_CHECK(c, "k_mip_box2");
         } else {
             const size_t items = (size_t)Dd * Dd * (zd_hi - zd_lo);
             k_mip_generic<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, mode, zd_lo, zd_hi);
+            VCT_LAUNCH_CHECK(c, "k_mip_generic");
         }
-        VCT_LAUNCH_CHECK(c);
     }
     return 0;
 }
@@ -362,20 +365,20 @@ int vctk_publish(vct_ctx* c, int which) {
         const int d = level_dim(c->D, l);
         const size_t items = (size_t)(d >= 4 ? d / 4 : 1) * d * d;
         k_publish<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(base + c->level_off[l], surf[l], d);
-        VCT_LAUNCH_CHECK(c);
+        VCT_LAUNCH_CHECK(c, "k_publish");
     }
     return 0;
 }
 int vctk_set_voxel_opacity(vct_ctx* c, float opacity) {
     const size_t n = (size_t)c->D * c->D * c->D;
     k_set_voxel_opacity<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(c->d_color, c->d_radiance, n, opacity, c->d_counters);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_set_voxel_opacity");
     return 0;
 }
 int vctk_temporal_radiance_filter(vct_ctx* c, float decay) {
     const size_t n = (size_t)c->D * c->D * c->D;
     k_temporal_decay<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(c->d_radiance, n, decay);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_temporal_decay");
     return 0;
 }
 int vctk_filter3d(vct_ctx* c, int which, int src_level) {
@@ -384,12 +387,12 @@ int vctk_filter3d(vct_ctx* c, int which, int src_level) {
     const int Ds = level_dim(c->D, src_level);
     const size_t n = (size_t)(Ds / 2) * (Ds / 2) * (Ds / 2);
     k_filter3d<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(base + c->level_off[src_level], base + c->level_off[src_level + 1], Ds);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_filter3d");
     return 0;
 }
 int vctk_normalize_voxels_f16(vct_ctx* c, void* col, void* nrm, float opacity) {
     const size_t n = (size_t)c->D * c->D * c->D;
     k_normalize_f16<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>((__half*)col, (__half*)nrm, c->d_radiance, n, opacity, c->d_counters);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_normalize_f16");
     return 0;
 }

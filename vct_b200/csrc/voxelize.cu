@@ -408,12 +408,12 @@ __global__ void k_set_frag_count(Counters* c, unsigned cap) {
 int exclusive_scan(vct_ctx* c, const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp, uint32_t* total_out) {
     const int nb = (int)((n + kScanTile - 1) / kScanTile);
     if (nb <= 1) {
-        k_scan_apply<<<1, kThreads, 0, c->stream>>>(in, out, nullptr, n, total_out); VCT_LAUNCH_CHECK(c);
+        k_scan_apply<<<1, kThreads, 0, c->stream>>>(in, out, nullptr, n, total_out); VCT_LAUNCH_CHECK(c, "k_scan_apply");
         return 0;
     }
-    k_scan_reduce<<<nb, kThreads, 0, c->stream>>>(in, tmp, n); VCT_LAUNCH_CHECK(c);
+    k_scan_reduce<<<nb, kThreads, 0, c->stream>>>(in, tmp, n); VCT_LAUNCH_CHECK(c, "k_scan_reduce");
     if (exclusive_scan(c, tmp, tmp, (size_t)nb, tmp + ((nb + 31) & ~31), nullptr)) return 1;
-    k_scan_apply<<<nb, kThreads, 0, c->stream>>>(in, out, tmp, n, total_out); VCT_LAUNCH_CHECK(c);
+    k_scan_apply<<<nb, kThreads, 0, c->stream>>>(in, out, tmp, n, total_out); VCT_LAUNCH_CHECK(c, "k_scan_apply");
     return 0;
 }
 
@@ -437,9 +437,10 @@ int vctk_transform_vertices(vct_ctx* c) {
     for (auto& m : c->meshes) { models[m.actor] = m.model; normal_matrix_host(m.model.m, &nm[9 * (size_t)m.actor]); }
     VCT_CHECK(c, cudaMemcpyAsync(c->d_models, models.data(), models.size() * sizeof(Mat4), cudaMemcpyHostToDevice, c->stream));
     VCT_CHECK(c, cudaMemcpyAsync(c->d_nmats, nm.data(), nm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    vct_prof_mark(c, "h2d_params");
     const int grid = (int)std::min<size_t>((c->n_vertices + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_transform_vertices<<<grid, kThreads, 0, c->stream>>>(c->d_vertices, c->d_vactor, c->d_models, c->d_nmats, c->n_vertices, c->d_wpos, c->d_wnrm, c->d_wT, c->d_wB);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_transform_vertices");
     return 0;
 }
 
@@ -456,27 +457,28 @@ int vctk_voxelize(vct_ctx* c, bool occupancy) {
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     if (occupancy) {
         VCT_CHECK(c, cudaMemsetAsync(c->d_occ, 0, sizeof(uint32_t) * VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM, c->stream));
-        k_voxel_raster<false, MODE_OCC><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c);
+        vct_prof_mark(c, "memset");
+        k_voxel_raster<false, MODE_OCC><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, "k_voxel_raster_occ");
         return 0;
     }
-    if (p.voxelize_atomic_max) { k_voxel_raster<false, MODE_MAX><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c); return 0; }
-    if (!p.deterministic) { k_voxel_raster<false, MODE_CAS><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c); return 0; }
+    if (p.voxelize_atomic_max) { k_voxel_raster<false, MODE_MAX><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, "k_voxel_raster_max"); return 0; }
+    if (!p.deterministic) { k_voxel_raster<false, MODE_CAS><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, "k_voxel_raster_cas"); return 0; }
     // deterministic running average: count -> scan -> emit -> sort by voxel -> sequential apply
-    k_voxel_raster<true, MODE_SORTED><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c);
+    k_voxel_raster<true, MODE_SORTED><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, "k_voxel_raster_count");
     if (exclusive_scan(c, c->d_tri_count, c->d_tri_base, c->n_tris, c->d_scan_tmp, &c->d_counters->n_frag_slots)) return 1;
-    k_set_frag_count<<<1, 1, 0, c->stream>>>(c->d_counters, (unsigned)c->frag_cap); VCT_LAUNCH_CHECK(c);
-    k_voxel_raster<false, MODE_SORTED><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c);
+    k_set_frag_count<<<1, 1, 0, c->stream>>>(c->d_counters, (unsigned)c->frag_cap); VCT_LAUNCH_CHECK(c, "k_set_frag_count");
+    k_voxel_raster<false, MODE_SORTED><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, "k_voxel_raster_emit");
     int bits = 0; while ((1ull << bits) < (unsigned long long)c->D * c->D * c->D) bits++;
     int cur = 0;
     for (int shift = 0; shift < bits; shift += 8) {
-        k_sort_hist<<<kSortBlocks, kThreads, 0, c->stream>>>(c->d_key[cur], &c->d_counters->n_frag_slots, shift, c->d_hist); VCT_LAUNCH_CHECK(c);
-        k_sort_rowscan<<<256, kThreads, 0, c->stream>>>(c->d_hist, c->d_hist + 256 * kSortBlocks); VCT_LAUNCH_CHECK(c);
+        k_sort_hist<<<kSortBlocks, kThreads, 0, c->stream>>>(c->d_key[cur], &c->d_counters->n_frag_slots, shift, c->d_hist); VCT_LAUNCH_CHECK(c, "k_sort_hist");
+        k_sort_rowscan<<<256, kThreads, 0, c->stream>>>(c->d_hist, c->d_hist + 256 * kSortBlocks); VCT_LAUNCH_CHECK(c, "k_sort_rowscan");
         k_sort_scatter<<<kSortBlocks, kThreads, 0, c->stream>>>(c->d_key[cur], c->d_val[cur], c->d_key[cur ^ 1], c->d_val[cur ^ 1], &c->d_counters->n_frag_slots, shift,
                                                                 c->d_hist, c->d_hist + 256 * kSortBlocks);
-        VCT_LAUNCH_CHECK(c);
+        VCT_LAUNCH_CHECK(c, "k_sort_scatter");
         cur ^= 1;
     }
     k_voxel_apply<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(c->d_key[cur], c->d_val[cur], &c->d_counters->n_frag_slots, c->d_frag_color, c->d_frag_normal, c->d_color, c->d_normal);
-    VCT_LAUNCH_CHECK(c);
+    VCT_LAUNCH_CHECK(c, "k_voxel_apply");
     return 0;
 }

@@ -17,6 +17,7 @@ SYMBOLS = [
     "vct_filter3d", "vct_normalize_voxels_f16", "vct_read_image", "vct_read_volume", "vct_write_volume",
     "vct_read_shadowmap", "vct_write_shadowmap", "vct_read_visibility", "vct_get_counters", "vct_get_timings",
     "vct_get_cone_steps", "vct_sync", "vct_device_ptr", "vct_level_bytes", "vct_stream", "vct_launch_count",
+    "vct_set_stream", "vct_set_profiling", "vct_get_kernel_times",
 ]
 
 _lib = None
@@ -52,6 +53,8 @@ def load():
         "vct_get_cone_steps": (ci, [vp, C.POINTER(C.c_ulonglong)]), "vct_sync": (ci, [vp]),
         "vct_device_ptr": (vp, [vp, ci, ci]), "vct_level_bytes": (C.c_size_t, [vp, ci, ci]), "vct_stream": (vp, [vp]),
         "vct_launch_count": (C.c_ulonglong, [vp, ci]),
+        "vct_set_stream": (ci, [vp, vp]), "vct_set_profiling": (ci, [vp, ci]),
+        "vct_get_kernel_times": (ci, [vp, C.POINTER(P.KernelTime), ci]),
     }
     for name in ("vct_shadowmap", "vct_occupancy", "vct_warpmap", "vct_voxelize", "vct_transfer", "vct_inject", "vct_fill_holes",
                  "vct_gbuffer", "vct_cone_trace", "vct_frame", "vct_gi_passes"):

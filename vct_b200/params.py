@@ -13,7 +13,7 @@ WARP_DIM = 32
 F16 = C.c_float * 16
 F3 = C.c_float * 3
 
-VOL_COLOR, VOL_NORMAL, VOL_RADIANCE, VOL_OCCUPANCY, VOL_WARPMAP, VOL_WARP_WEIGHTS_LOW, VOL_WARP_WEIGHTS_HIGH = range(7)
+VOL_COLOR, VOL_NORMAL, VOL_RADIANCE, VOL_OCCUPANCY, VOL_WARPMAP, VOL_WARP_WEIGHTS_LOW, VOL_WARP_WEIGHTS_HIGH, BUF_IMAGE = range(8)
 
 
 class Config(C.Structure):
@@ -72,6 +72,10 @@ class Timings(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("voxelize_ns", "shadowmap_ns", "radiance_ns", "mipmap_ns", "render_ns",
                                           "total_ns", "transfer_ns", "gbuffer_ns", "warpmap_ns", "clear_ns",
                                           "exchange_ns")]
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ns", C.c_double), ("launches", C.c_uint), ("_pad", C.c_uint)]
 
 
 # --------------------------------------------------------------------------------- GLM-equivalent helpers

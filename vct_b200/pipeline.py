@@ -117,6 +117,20 @@ class Pipeline:
     def timings(self):
         t = P.Timings(); self._ck(self.lib.vct_get_timings(self.h, C.byref(t))); return {k: getattr(t, k) for k, _ in P.Timings._fields_}
 
+    def set_profiling(self, level):
+        self._ck(self.lib.vct_set_profiling(self.h, level))
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.lib.vct_set_stream(self.h, stream_ptr))
+
+    def kernel_times(self):
+        """{kernel name: (ns, launches)} of the last pass call (profiling level 2)."""
+        buf = (P.KernelTime * 64)()
+        n = self.lib.vct_get_kernel_times(self.h, buf, 64)
+        if n < 0:
+            raise VctError("vct_get_kernel_times failed")
+        return {buf[i].name.decode(): (buf[i].ns, buf[i].launches) for i in range(n)}
+
     def launch_count(self, reset=False):
         return int(self.lib.vct_launch_count(self.h, int(reset)))
 

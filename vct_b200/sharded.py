@@ -1,0 +1,153 @@
+"""One frame of the GI hot path on 1..N GPUs, one process per GPU.
+
+world_size == 1   the frame is `vct_gi_passes` on the library's own stream.
+world_size  > 1   z-slab sharding: every rank clears / voxelises / transfers / injects / mip-filters the slab
+                  z in [rank*D/N, (rank+1)*D/N) of every level (BOX2 mips are aligned 2x2x2 reductions, so no
+                  halo is needed while a slab is at least one texel thick at the coarsest level); then ONE exchange
+                  step — an in-place NCCL all-gather per pyramid level, coalesced into a single group launch over
+                  NVLink — gives every rank the whole radiance pyramid; `vct_exchange` publishes it to the 3D
+                  texture; the cone trace is sharded by screen band and the bands are all-gathered into the image.
+                  The library enqueues on torch's current stream, so the collectives need no host synchronisation.
+
+The partition maths (`slab_range`, `level_chunks`, `image_bands`) is pure Python and is unit-tested on CPU with gloo.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import params as P
+
+
+# ------------------------------------------------------------------------------------- partition maths
+def slab_range(dim, world, rank):
+    """z-slab [lo, hi) owned by `rank` (vct_create uses the same rule; dim % world == 0 is required)."""
+    if dim % world:
+        raise ValueError("dim must be divisible by world_size")
+    return dim * rank // world, dim * (rank + 1) // world
+
+
+def level_chunks(dim, levels, world):
+    """Per level: (offset_in_voxels_of_rank0_chunk_relative_to_level_start, voxels_per_rank).  Level l is a linear
+    [z][y][x] array of (dim>>l)^3 voxels; a rank's slab of it is one contiguous chunk of d^3/world voxels."""
+    out = []
+    for l in range(levels):
+        d = max(1, dim >> l)
+        if d % world:
+            raise ValueError(f"level {l} ({d}^3) is thinner than one slab per rank: use levels <= log2(dim/world)+1")
+        out.append(d * d * d // world)
+    return out
+
+
+def image_bands(height, world):
+    """Equal bands of whole 8-row tiles; returns (band_rows, [(y_lo, y_hi) per rank]) — mirrors vctk_image_rows."""
+    rows8 = (height + 7) // 8
+    band = (rows8 + world - 1) // world * 8
+    return band, [(min(height, r * band), min(height, (r + 1) * band)) for r in range(world)]
+
+
+def all_gather_levels(dist, level_tensors, chunks, rank):
+    """In-place all-gather of every level (rank r's chunk lives at [r*chunk, (r+1)*chunk) of the level tensor).
+    Works for any backend (gloo on CPU in the tests, NCCL over NVLink in production)."""
+    for t, n in zip(level_tensors, chunks):
+        dist.all_gather_into_tensor(t, t[rank * n:(rank + 1) * n].clone() if t.device.type == "cpu" else t[rank * n:(rank + 1) * n])
+
+
+class _DevMem:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, nbytes):
+    import torch
+    return torch.as_tensor(_DevMem(ptr, nbytes), device="cuda")
+
+
+# ------------------------------------------------------------------------------------------- the frame
+class ShardedFrame:
+    def __init__(self, pipeline, params, world=1, rank=0):
+        import torch
+        self.g, self.p, self.world, self.rank = pipeline, params, world, rank
+        self.torch = torch
+        g = pipeline
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            self.stream = torch.cuda.current_stream()
+            g.set_stream(self.stream.cuda_stream)
+            which = P.VOL_RADIANCE if params.draw_radiance else P.VOL_COLOR
+            self.levels = [device_tensor(g.device_ptr(which, l), g.level_bytes(which, l)) for l in range(g.L)]
+            self.chunks = level_chunks(g.D, g.L, world)
+            self.band, self.bands = image_bands(g.H, world)
+            self.image = device_tensor(g.device_ptr(P.BUF_IMAGE, 0), g.level_bytes(P.BUF_IMAGE, 0))
+            self.band_px = self.band * g.W
+        else:
+            self.stream = torch.cuda.ExternalStream(g.lib.vct_stream(g.h))
+
+    def describe(self):
+        if self.world == 1:
+            return "1 GPU"
+        return (f"{self.world} GPUs: z-slab sharding of clear/voxelise/transfer/inject/mip, coalesced NCCL all-gather of the radiance pyramid, "
+                f"cone trace sharded by {self.band}-row screen band, NCCL all-gather of the image bands")
+
+    # producers of the reference frame graph that the GI step consumes (replicated on every rank)
+    def producers(self):
+        g, p = self.g, self.p
+        g.shadowmap(p)
+        if p.warp_texture:
+            g.occupancy(p); g.warpmap(p)
+        g.gbuffer(p)
+
+    def _exchange(self):
+        dist, r = self.dist, self.rank
+        try:
+            with dist._coalescing_manager(device=self.levels[0].device):
+                for t, n in zip(self.levels, self.chunks):
+                    dist.all_gather_into_tensor(t, t[r * n:(r + 1) * n])
+        except (AttributeError, TypeError, RuntimeError):
+            for t, n in zip(self.levels, self.chunks):
+                dist.all_gather_into_tensor(t, t[r * n:(r + 1) * n])
+
+    def step(self):
+        g, p = self.g, self.p
+        g.gi_passes(p)
+        if self.world == 1:
+            return
+        self._exchange()
+        g.exchange()
+        g.cone_trace(p)
+        r, n = self.rank, self.band_px
+        self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
+
+    def step_e2e(self, host_img):
+        """host_img: pinned int32 tensor of W*H pixels.  Frame parameters go host->device inside vct_gi_passes."""
+        self.step()
+        g = self.g
+        if self.world == 1:
+            g._ck(g.lib.vct_read_image(g.h, host_img.data_ptr()))
+        elif self.rank == 0:
+            host_img.copy_(self.image[: g.W * g.H], non_blocking=True)
+            self.stream.synchronize()
+
+    def profiled_step(self):
+        """Per-kernel times {name: (ns, launches)} of one step (library profiling level 2)."""
+        g, p = self.g, self.p
+        g.gi_passes(p)
+        kt = g.kernel_times()
+        if self.world > 1:
+            self._exchange()
+            g.exchange(); kt2 = g.kernel_times()
+            g.cone_trace(p); kt3 = g.kernel_times()
+            for extra in (kt2, kt3):
+                for k, (ns, n) in extra.items():
+                    a = kt.get(k, (0.0, 0)); kt[k] = (a[0] + ns, a[1] + n)
+            r, n = self.rank, self.band_px
+            self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
+        return kt
+
+    def pass_times(self):
+        """Per-pass ms of one whole reference frame graph (GLTimer semantics; profiling level 1), incl. producers."""
+        g, p = self.g, self.p
+        if self.world > 1:
+            return {}
+        g.frame(p)
+        return {k.replace("_ns", ""): round(v / 1e6, 4) for k, v in g.timings().items() if v > 0}
