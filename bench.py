@@ -106,14 +106,13 @@ def algorithmic_bytes(D, L, S, W, H, T, F, U, chains):
         "voxelize": 96 * T + 16 * F,                         # all voxeliser kernels together
         "k_transfer": 4 * d3 + 4 * d3 + 8 * U,               # colour read + (fused) radiance clear + 2 stores per occupied voxel
         "k_inject": 4 * S * S,                               # + 8 N_in scattered (not counted: lower bound)
-        "k_mip_box2": mip * chains,
-        "k_publish": 2 * pyr,                                # linear pyramid -> texture array (this build's extra copy)
+        "k_mip_chain": mip * chains,                         # (the fused kernel also feeds the texture array: not counted)
         "k_cone_trace": pyr + 8 * W * H + 4 * W * H,         # compulsory HBM: pyramid once + visibility + image
     }
 
 
-VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_raster_count", "k_scan_reduce", "k_scan_apply", "k_set_frag_count", "k_voxel_raster_emit",
-                    "k_sort_hist", "k_sort_rowscan", "k_sort_scatter", "k_voxel_apply", "k_voxel_raster_cas", "k_voxel_raster_max")
+VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_tiles", "k_voxel_resolve_a", "k_voxel_resolve_b",
+                    "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_bin_max", "k_voxel_tiles_max")
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
@@ -268,8 +267,8 @@ def run_b200(args):
                         "timing": f"per-kernel CUDA events on the library stream, mean of {nprof} profiled frames run right after the timed region"}
             if dom["kernel"] == "k_cone_trace":
                 roofline["note"] = "cone trace is bound by L1/texture + L2 throughput (the pyramid is re-read ~100x per frame from cache), see cone_steps_per_s"
-        voxel_bytes = sum(ab[k] for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_box2"))
-        voxel_ms = sum(kt.get(k, 0.0) for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_box2"))
+        voxel_bytes = sum(ab[k] for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_chain"))
+        voxel_ms = sum(kt.get(k, 0.0) for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_chain"))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from tests.oracle_lib import Oracle, lib

@@ -8,6 +8,8 @@
 
 thread_local std::string g_create_error;
 size_t vctk_tile_setup_bytes();
+size_t vctk_vox_setup_bytes();
+size_t vctk_frag_bytes();
 size_t vctk_image_rows(const vct_ctx*);
 
 namespace {
@@ -74,7 +76,7 @@ int finalize_scene(vct_ctx* c) {
     if (!c->scene_dirty) return 0;
     std::sort(c->meshes.begin(), c->meshes.end(), [](const HostMesh& a, const HostMesh& b) { return a.actor < b.actor; });
     for (void** p : {(void**)&c->d_vertices, (void**)&c->d_vactor, (void**)&c->d_indices, (void**)&c->d_trimat, (void**)&c->d_models, (void**)&c->d_nmats, (void**)&c->d_wpos,
-                     (void**)&c->d_wnrm, (void**)&c->d_wT, (void**)&c->d_wB, (void**)&c->d_tri_count, (void**)&c->d_tri_base, (void**)&c->d_scan_tmp, (void**)&c->d_setup}) { cudaFree(*p); *p = nullptr; }
+                     (void**)&c->d_wnrm, (void**)&c->d_wT, (void**)&c->d_wB, (void**)&c->d_setup, (void**)&c->d_tile_queue, (void**)&c->d_expand_queue}) { cudaFree(*p); *p = nullptr; }
     c->n_vertices = c->h_vertices.size() / 14; c->n_tris = c->h_trimat.size();
     c->n_actors = 0; for (auto& m : c->meshes) c->n_actors = std::max(c->n_actors, m.actor + 1);
     if (!c->n_vertices || !c->n_tris) { c->scene_dirty = false; return 0; }
@@ -83,9 +85,14 @@ int finalize_scene(vct_ctx* c) {
     VCT_CHECK(c, cudaMalloc(&c->d_indices, nt * 12)); VCT_CHECK(c, cudaMalloc(&c->d_trimat, nt * 4));
     VCT_CHECK(c, cudaMalloc(&c->d_models, c->n_actors * sizeof(Mat4))); VCT_CHECK(c, cudaMalloc(&c->d_nmats, c->n_actors * 36));
     VCT_CHECK(c, cudaMalloc(&c->d_wpos, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wnrm, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wT, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wB, nv * 16));
-    VCT_CHECK(c, cudaMalloc(&c->d_tri_count, nt * 4)); VCT_CHECK(c, cudaMalloc(&c->d_tri_base, nt * 4));
-    VCT_CHECK(c, cudaMalloc(&c->d_scan_tmp, (nt / 1024 + 65536) * 4));
-    VCT_CHECK(c, cudaMalloc(&c->d_setup, (2 * nt + 64) * vctk_tile_setup_bytes()));
+    // one setup per queued (sub-)triangle (camera pass: up to two after near clipping); tile queue sized for the
+    // scene: every triangle may push one tile, plus headroom for the multi-tile ones
+    c->setup_cap = 2 * nt + 64;
+    c->tile_queue_cap = 2 * nt + ((size_t)8 << 20);
+    VCT_CHECK(c, cudaMalloc(&c->d_setup, c->setup_cap * std::max(vctk_tile_setup_bytes(), vctk_vox_setup_bytes())));
+    VCT_CHECK(c, cudaMalloc(&c->d_tile_queue, c->tile_queue_cap * 8));
+    c->expand_cap = 2 * nt + ((size_t)1 << 20);
+    VCT_CHECK(c, cudaMalloc(&c->d_expand_queue, c->expand_cap * 8));
     VCT_CHECK(c, cudaMemcpy(c->d_vertices, c->h_vertices.data(), nv * 56, cudaMemcpyHostToDevice));
     VCT_CHECK(c, cudaMemcpy(c->d_vactor, c->h_vactor.data(), nv * 4, cudaMemcpyHostToDevice));
     VCT_CHECK(c, cudaMemcpy(c->d_indices, c->h_indices.data(), nt * 12, cudaMemcpyHostToDevice));
@@ -141,12 +148,11 @@ int gi_body(vct_ctx* c, Graph& g) {
     if (vctk_inject(c)) return 1;
     if (p.voxel_fill_holes) { if (ensure_scratch(c) || vctk_fill_holes(c)) return 1; }
     if (g.rec(EV_INJECT)) return 1;
-    if (vctk_mip(c, VCT_VOL_RADIANCE, 0)) return 1;
-    if (p.mip_color_chain && vctk_mip(c, VCT_VOL_COLOR, 0)) return 1;
-    if (c->cfg.world_size <= 1) {
-        if (!p.draw_radiance) { if (ensure_color_texture(c) || vctk_publish(c, VCT_VOL_COLOR)) return 1; }
-        else if (vctk_publish(c, VCT_VOL_RADIANCE)) return 1;
-    }
+    // single GPU: the chain that the cone tracer samples is written straight into its texture array
+    const bool single = c->cfg.world_size <= 1;
+    if (single && !p.draw_radiance && ensure_color_texture(c)) return 1;
+    if (vctk_mip(c, VCT_VOL_RADIANCE, 0, single && p.draw_radiance)) return 1;
+    if (p.mip_color_chain || !p.draw_radiance) { if (vctk_mip(c, VCT_VOL_COLOR, 0, single && !p.draw_radiance)) return 1; }
     return g.rec(EV_MIP);
 }
 
@@ -176,12 +182,10 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     const int N = VCT_WARP_DIM;
     auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
-    c->tile_queue_cap = (size_t)4 << 20;
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * 8) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
         alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
-        alloc((void**)&c->d_key[0], c->frag_cap * 4) || alloc((void**)&c->d_key[1], c->frag_cap * 4) || alloc((void**)&c->d_val[0], c->frag_cap * 4) || alloc((void**)&c->d_val[1], c->frag_cap * 4) ||
-        alloc((void**)&c->d_frag_color, c->frag_cap * 16) || alloc((void**)&c->d_frag_normal, c->frag_cap * 16) || alloc((void**)&c->d_hist, (256 * 592 + 256) * 4) ||
-        alloc((void**)&c->d_tile_queue, c->tile_queue_cap * 16) || alloc((void**)&c->d_fc, sizeof(FrameConst)) || alloc((void**)&c->d_counters, sizeof(Counters)) ||
+        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
+        alloc((void**)&c->d_fc, sizeof(FrameConst)) || alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
     for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }
@@ -195,10 +199,10 @@ int vct_destroy(vct_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
-    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, (void*)c->d_key[0], (void*)c->d_key[1],
-                    (void*)c->d_val[0], (void*)c->d_val[1], (void*)c->d_frag_color, (void*)c->d_frag_normal, (void*)c->d_hist, (void*)c->d_tile_queue, (void*)c->d_fc, (void*)c->d_counters,
+    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_warp_scratch,
+                    c->d_tile_queue, c->d_expand_queue, (void*)c->d_fc, (void*)c->d_counters,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_models, (void*)c->d_nmats, (void*)c->d_wpos,
-                    (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, (void*)c->d_tri_count, (void*)c->d_tri_base, (void*)c->d_scan_tmp, c->d_setup})
+                    (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})
         cudaFree(p);
     for (void* p : c->tex_allocs) cudaFree(p);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -307,10 +311,8 @@ int vct_mip(vct_ctx* c, int which) {
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);
     if (which != VCT_VOL_RADIANCE && which != VCT_VOL_COLOR) return fail(c, "vct_mip: radiance or colour volume only");
-    if (vctk_mip(c, which, 0)) return 1;
-    if (c->cfg.world_size > 1) return 0;
-    if (which == VCT_VOL_COLOR && !c->color_arr) return 0;
-    return vctk_publish(c, which);
+    const bool publish = c->cfg.world_size <= 1 && !(which == VCT_VOL_COLOR && !c->color_arr);
+    return vctk_mip(c, which, 0, publish);
 }
 int vct_exchange(vct_ctx* c) {
     if (!c) return 1;

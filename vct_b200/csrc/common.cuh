@@ -75,7 +75,8 @@ struct FrameConst {
 struct Counters {                // device-resident, zeroed per frame
     unsigned total_fragments, unique_voxels, max_fragments_per_voxel;
     unsigned n_frag_slots;       // fragments emitted (== total_fragments within this slab)
-    unsigned tile_queue_count;   // raster work queue
+    unsigned tile_queue_count;   // raster work queue (fine tiles)
+    unsigned expand_count;       // raster work queue (bands of tile rows still to be enumerated)
     unsigned setup_count;        // big-triangle setups written by k_raster_bin
     unsigned overflow;           // set when a fixed-capacity buffer was too small
     unsigned long long cone_steps;
@@ -122,14 +123,12 @@ struct vct_ctx {
     uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
     // shadow map / visibility / image
     float* d_shadow = nullptr; unsigned long long* d_vis = nullptr; uint32_t* d_image = nullptr;
-    // voxel fragments
-    size_t frag_cap = 0;
-    uint32_t *d_tri_count = nullptr, *d_tri_base = nullptr, *d_scan_tmp = nullptr;
-    uint32_t *d_key[2] = {nullptr, nullptr}, *d_val[2] = {nullptr, nullptr};
-    float4 *d_frag_color = nullptr, *d_frag_normal = nullptr;
-    uint32_t* d_hist = nullptr;
-    // raster work queue
-    uint4* d_tile_queue = nullptr; size_t tile_queue_cap = 0; void* d_setup = nullptr;
+    // voxel fragments (per-voxel linked lists of the deterministic running average)
+    size_t frag_cap = 0; void* d_frags = nullptr;
+    uint32_t* d_warp_scratch = nullptr;
+    // raster work queue: 8-byte tile items + one setup record per queued (sub-)triangle
+    void* d_tile_queue = nullptr; size_t tile_queue_cap = 0; void* d_expand_queue = nullptr; size_t expand_cap = 0;
+    void* d_setup = nullptr; size_t setup_cap = 0;
     // per-frame constants + counters
     FrameConst* d_fc = nullptr; FrameConst h_fc{};
     Counters* d_counters = nullptr; Counters h_counters{};
@@ -187,7 +186,7 @@ int vctk_voxelize(vct_ctx*, bool occupancy);
 int vctk_transfer(vct_ctx*);
 int vctk_inject(vct_ctx*);
 int vctk_fill_holes(vct_ctx*);
-int vctk_mip(vct_ctx*, int which, int mode);
+int vctk_mip(vct_ctx*, int which, int mode, int publish);
 int vctk_publish(vct_ctx*, int which);
 int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);

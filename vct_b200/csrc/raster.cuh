@@ -71,6 +71,116 @@ __device__ __forceinline__ bool tri_cover(const TriSetup& s, int px, int py, flo
     l[0] = e0; l[1] = s.swapped ? e2 : e1; l[2] = s.swapped ? e1 : e2;
     return true;
 }
+// ---------------------------------------------------------------------------------------- tile work queue
+// Rasterisation work is cut into 8x4-pixel tiles = 32 pixels = one warp with ONE LANE PER PIXEL.  A tile item is
+// 8 bytes: (setup slot, origin x | y << 16); origins are absolute pixels and need not be grid aligned — a
+// triangle's tiles start at its bounding-box corner.  Three kernels keep every warp's serial work short:
+//   bin     one thread per triangle: setup; single-tile triangles push their tile directly; multi-tile ones push
+//           EXPAND items, each covering a band of tile rows with at most ~kExpandTiles tiles
+//   expand  one warp per expand item: enumerates the band's tiles 32 at a time, drops trivially rejected ones,
+//           pushes the rest (one atomic per 32 candidates)
+//   tiles   one warp per tile
+constexpr int kTileW = 8, kTileH = 4;
+constexpr int kExpandTiles = 512;
+
+struct TileQueues {
+    uint2* tiles; unsigned tile_cap; unsigned* tile_count;
+    uint2* expand; unsigned expand_cap; unsigned* expand_count;
+    unsigned* overflow;
+};
+
+// Is the pixel-centre box [bx0,bx1]x[by0,by1] entirely outside one of the edges?
+__device__ __forceinline__ bool tile_rejected(const TriSetup& s, int bx0, int by0, int bx1, int by1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+        const long long ex = s.X[b] - s.X[a], ey = s.Y[b] - s.Y[a];
+        // E = ex*(Py - Ya) - ey*(Px - Xa) is maximised at Py = (ex>0 ? top : bottom), Px = (ey>0 ? left : right)
+        const long long Py = 256ll * (ex > 0 ? by1 : by0) + 128, Px = 256ll * (ey > 0 ? bx0 : bx1) + 128;
+        if (ex * (Py - s.Y[a]) - ey * (Px - s.X[a]) + s.bias[k] < 0) return true;
+    }
+    return false;
+}
+
+// Called by a CONVERGED warp.  Lanes with `queued` own a triangle setup `s` already published in slot `sslot`.
+__device__ __forceinline__ void enqueue_tiles(bool queued, const TriSetup& s, uint32_t sslot, const TileQueues& q) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int bw = queued ? s.x1 - s.x0 + 1 : 0, bh = queued ? s.y1 - s.y0 + 1 : 0;
+    const int ntx = (bw + kTileW - 1) / kTileW, nty = (bh + kTileH - 1) / kTileH;
+    const bool single = queued && ntx * nty == 1;
+    const unsigned sm = __ballot_sync(0xffffffffu, single);
+    if (sm) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(q.tile_count, (unsigned)__popc(sm));
+        const uint32_t pos = __shfl_sync(0xffffffffu, base, 0) + __popc(sm & lt_mask);
+        if (single) { if (pos < q.tile_cap) q.tiles[pos] = make_uint2(sslot, (unsigned)s.x0 | (unsigned)s.y0 << 16); else *q.overflow = 1u; }
+    }
+    // multi-tile: bands of tile rows, <= kExpandTiles tiles each (at least one row)
+    const bool multi = queued && ntx * nty > 1;
+    const int rows = multi ? max(1, kExpandTiles / ntx) : 1;
+    int nitems = multi ? (nty + rows - 1) / rows : 0;
+    int inc = nitems;                                                       // warp prefix sum -> one atomic per warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    if (!total) return;
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(q.expand_count, (unsigned)total);
+    uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(inc - nitems);
+    for (int r = 0; r < nty && nitems; r += rows, ++pos) {
+        if (pos < q.expand_cap) q.expand[pos] = make_uint2(sslot, (unsigned)r | (unsigned)min(rows, nty - r) << 16); else *q.overflow = 1u;
+    }
+}
+// expand: one warp per item.  `setups` is an array of records of `stride` bytes that begin with a TriSetup.
+__device__ __forceinline__ void expand_items(const unsigned char* __restrict__ setups, size_t stride, const TileQueues& q) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned n_items = min(*q.expand_count, q.expand_cap);
+    const unsigned warps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items; item += warps) {
+        const uint2 it = __ldg(q.expand + item);
+        const TriSetup s = *reinterpret_cast<const TriSetup*>(setups + (size_t)it.x * stride);
+        const int ntx = (s.x1 - s.x0 + kTileW) / kTileW;
+        const int r0 = (int)(it.y & 0xFFFFu), nr = (int)(it.y >> 16), nt = ntx * nr;
+        int ty = 0, tx = lane;                                              // tile (tx, ty) of this lane, advanced without divisions
+        while (tx >= ntx) { tx -= ntx; ty++; }
+        for (int tb = 0; tb < nt; tb += 32) {
+            bool keep = false; int ox = 0, oy = 0;
+            if (tb + lane < nt) {
+                ox = s.x0 + tx * kTileW; oy = s.y0 + (r0 + ty) * kTileH;
+                keep = !tile_rejected(s, ox, oy, min(ox + kTileW - 1, s.x1), min(oy + kTileH - 1, s.y1));
+            }
+            tx += 32; while (tx >= ntx) { tx -= ntx; ty++; }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (!m) continue;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(q.tile_count, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) {
+                const uint32_t pos = base + __popc(m & lt_mask);
+                if (pos < q.tile_cap) q.tiles[pos] = make_uint2(it.x, (unsigned)ox | (unsigned)oy << 16); else *q.overflow = 1u;
+            }
+        }
+    }
+}
+static inline TileQueues vctk_tile_queues(vct_ctx* c) {
+    TileQueues q;
+    q.tiles = reinterpret_cast<uint2*>(c->d_tile_queue); q.tile_cap = (unsigned)c->tile_queue_cap; q.tile_count = &c->d_counters->tile_queue_count;
+    q.expand = reinterpret_cast<uint2*>(c->d_expand_queue); q.expand_cap = (unsigned)c->expand_cap; q.expand_count = &c->d_counters->expand_count;
+    q.overflow = &c->d_counters->overflow;
+    return q;
+}
+// reserve one setup slot per lane with `want` (one atomic per warp); returns the lane's slot
+__device__ __forceinline__ uint32_t reserve_slots(bool want, unsigned* __restrict__ counter) {
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return 0u;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(m));
+    return __shfl_sync(0xffffffffu, base, 0) + __popc(m & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ float interp1(const float l[3], float a0, float a1, float a2) { return (l[0] * a0 + l[1] * a1) + l[2] * a2; }
 __device__ __forceinline__ V3 interp3(const float l[3], V3 a, V3 b, V3 c) {
     return mk3(interp1(l, a.x, b.x, c.x), interp1(l, a.y, b.y, c.y), interp1(l, a.z, b.z, c.z));

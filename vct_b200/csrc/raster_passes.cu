@@ -8,29 +8,28 @@
 //                depthbits<<32 | (0xFFFFFFFF - drawIndex) and resolved with one 64-bit atomicMin
 //
 // Two kernels per pass.  k_raster_bin: one thread per triangle — transform, (near-)clip, fixed-point setup;
-// triangles with a small bounding box are rasterised on the spot, the others are cut into 32x8-pixel tiles
-// (trivially rejected tiles skipped) that the whole warp pushes onto a device work queue.  k_raster_tiles: a
-// persistent grid (CTAs = multiple of 148 SMs) pops tiles, one warp per tile, lane = pixel column, edge
-// functions stepped incrementally down the 8 rows.
+// (sub-)triangles whose bounding box is <= kInlineArea pixels are rasterised on the spot, the others publish their
+// setup and are cut into 8x4-pixel tiles (trivially rejected tiles skipped) pushed to a device work queue.
+// k_raster_tiles: a persistent grid (CTAs = multiple of 148 SMs) pops tiles, one warp per tile, ONE LANE PER PIXEL.
 #include "raster.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSmallArea = 64;
-constexpr int kTileW = 32, kTileH = 8;
+constexpr int kInlineArea = 4;
 
-struct TileSetup {               // 96 bytes, written once per big (sub-)triangle
+struct __align__(16) TileSetup { // 96 bytes, written once per queued (sub-)triangle
     TriSetup s;
-    uint32_t tri; int alpha_tex;
+    uint32_t tri; int alpha_tex; uint32_t pad[2];
 };
+static_assert(sizeof(TileSetup) == 96, "TileSetup is broadcast-loaded as 6 x 16 bytes");
 
 struct RasterArgs {
     const FrameConst* fc; int W, H;
     const uint32_t* indices; const int32_t* trimat; const float* verts; uint32_t n_tris;
     const float4* wpos; const DevTexture* tex; const DevMaterial* mats;
     unsigned* depth_bits; unsigned long long* vis;
-    TileSetup* setups; uint4* queue; unsigned queue_cap; unsigned setup_cap;
+    TileSetup* setups; TileQueues q; unsigned setup_cap;
     Counters* counters; unsigned* setup_count;
 };
 
@@ -123,6 +122,14 @@ __device__ __forceinline__ bool alpha_pass(const RasterArgs& a, const AlphaCtx& 
     return !(sample2d(*ac.tex, u, v, maxsel(ax * ax + bx * bx, ay * ay + by * by)).x < 0.1f);
 }
 
+// out-of-line so that the tile kernel's common path stays light on registers
+template <bool CAMERA>
+__device__ __noinline__ bool alpha_test_slow(const RasterArgs& a, uint32_t tri, int alpha_tex, int px, int py, const float l[3]) {
+    RV cv[3]; clip_verts(a, CAMERA, tri, cv);
+    AlphaCtx ac; alpha_setup<CAMERA>(a, tri, alpha_tex, cv, ac);
+    return alpha_pass<CAMERA>(a, ac, px, py, l);
+}
+
 template <bool CAMERA>
 __device__ __forceinline__ void depth_write(const RasterArgs& a, int px, int py, float z, uint32_t t) {
     const float d = z * 0.5f + 0.5f;
@@ -136,42 +143,28 @@ __device__ __forceinline__ void depth_write(const RasterArgs& a, int px, int py,
     }
 }
 
-// Is the pixel-centre box [bx0,bx1]x[by0,by1] entirely outside one of the edges?
-__device__ __forceinline__ bool tile_rejected(const TriSetup& s, int bx0, int by0, int bx1, int by1) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int a = (k + 1) % 3, b = (k + 2) % 3;
-        const long long ex = s.X[b] - s.X[a], ey = s.Y[b] - s.Y[a];
-        // E = ex*(Py - Ya) - ey*(Px - Xa) is maximised at Py = (ex>0 ? top : bottom), Px = (ey>0 ? left : right)
-        const long long Py = 256ll * (ex > 0 ? by1 : by0) + 128, Px = 256ll * (ey > 0 ? bx0 : bx1) + 128;
-        if (ex * (Py - s.Y[a]) - ey * (Px - s.X[a]) + s.bias[k] < 0) return true;
-    }
-    return false;
-}
-
 template <bool CAMERA>
 __global__ void __launch_bounds__(kThreads) k_raster_bin(RasterArgs a) {
-    const int lane = threadIdx.x & 31;
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n_round = (a.n_tris + 31u) & ~31u;
+    const uint32_t n_round = (a.n_tris + 31u) & ~31u;                       // whole warps stay converged for the votes
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
         RV cv[3]; RV sub[2][3]; int nsub = 0; int alpha_tex = -1;
-        TriSetup S[2]; bool valid[2] = {false, false}, big[2] = {false, false};
+        TriSetup S[2]; bool valid[2] = {false, false}, tiny[2] = {false, false};
         if (t < a.n_tris) {
             clip_verts(a, CAMERA, t, cv);
             if (CAMERA) nsub = clip_near(cv, sub);
             else { nsub = 1; sub[0][0] = cv[0]; sub[0][1] = cv[1]; sub[0][2] = cv[2]; }
             for (int q = 0; q < nsub; ++q) {
                 valid[q] = tri_setup(sub[q], a.W, a.H, true, S[q]);
-                if (valid[q]) big[q] = (S[q].x1 - S[q].x0 + 1) * (S[q].y1 - S[q].y0 + 1) > kSmallArea;
+                if (valid[q]) tiny[q] = (S[q].x1 - S[q].x0 + 1) * (S[q].y1 - S[q].y0 + 1) <= kInlineArea;
             }
             if (valid[0] || valid[1]) alpha_tex = a.mats[__ldg(a.trimat + t)].alpha_tex;
         }
-        // ---- small (sub-)triangles: rasterise now
-        if ((valid[0] && !big[0]) || (valid[1] && !big[1])) {
+        // ---- tiny (sub-)triangles: rasterise now
+        if ((valid[0] && tiny[0]) || (valid[1] && tiny[1])) {
             AlphaCtx ac; alpha_setup<CAMERA>(a, t, alpha_tex, cv, ac);
             for (int q = 0; q < nsub; ++q) {
-                if (!valid[q] || big[q]) continue;
+                if (!valid[q] || !tiny[q]) continue;
                 const TriSetup& s = S[q];
                 for (int py = s.y0; py <= s.y1; ++py)
                     for (int px = s.x0; px <= s.x1; ++px) {
@@ -184,45 +177,18 @@ __global__ void __launch_bounds__(kThreads) k_raster_bin(RasterArgs a) {
                     }
             }
         }
-        // ---- big (sub-)triangles: the warp enumerates their tiles together
+        // ---- the others: publish the setup, cut the bounding box into tiles
+#pragma unroll
         for (int q = 0; q < 2; ++q) {
-            unsigned todo = __ballot_sync(0xffffffffu, big[q]);
-            while (todo) {
-                const int src = __ffs(todo) - 1; todo &= todo - 1;
-                unsigned slot = 0;
-                if (lane == src) {
-                    slot = atomicAdd(a.setup_count, 1u);
-                    if (slot < a.setup_cap) { TileSetup ts; ts.s = S[q]; ts.tri = t; ts.alpha_tex = alpha_tex; a.setups[slot] = ts; }
-                    else a.counters->overflow = 1u;
-                }
-                slot = __shfl_sync(0xffffffffu, slot, src);
-                const int x0 = __shfl_sync(0xffffffffu, S[q].x0, src), x1 = __shfl_sync(0xffffffffu, S[q].x1, src);
-                const int y0 = __shfl_sync(0xffffffffu, S[q].y0, src), y1 = __shfl_sync(0xffffffffu, S[q].y1, src);
-                if (slot >= a.setup_cap) continue;
-                __syncwarp();
-                __threadfence_block();
-                const TriSetup s = a.setups[slot].s;                       // L1/L2 hit; written by lane `src` above
-                const int tx0 = x0 / kTileW, tx1 = x1 / kTileW, ty0 = y0 / kTileH, ty1 = y1 / kTileH;
-                const int ntx = tx1 - tx0 + 1, nt = ntx * (ty1 - ty0 + 1);
-                for (int base = 0; base < nt; base += 32) {
-                    const int i = base + lane;
-                    bool keep = false; int tx = 0, ty = 0;
-                    if (i < nt) {
-                        tx = tx0 + i % ntx; ty = ty0 + i / ntx;
-                        keep = !tile_rejected(s, max(tx * kTileW, x0), max(ty * kTileH, y0), min(tx * kTileW + kTileW - 1, x1), min(ty * kTileH + kTileH - 1, y1));
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    if (!m) continue;
-                    unsigned qbase = 0;
-                    if (lane == 0) qbase = atomicAdd(&a.counters->tile_queue_count, (unsigned)__popc(m));
-                    qbase = __shfl_sync(0xffffffffu, qbase, 0);
-                    if (keep) {
-                        const unsigned pos = qbase + __popc(m & ((1u << lane) - 1u));
-                        if (pos < a.queue_cap) a.queue[pos] = make_uint4(slot, (unsigned)tx, (unsigned)ty, 0u);
-                        else a.counters->overflow = 1u;
-                    }
-                }
+            if (!CAMERA && q == 1) break;
+            const bool queued = valid[q] && !tiny[q];
+            const uint32_t slot = reserve_slots(queued, a.setup_count);
+            bool stored = false;
+            if (queued) {
+                if (slot < a.setup_cap) { TileSetup ts; ts.s = S[q]; ts.tri = t; ts.alpha_tex = alpha_tex; ts.pad[0] = ts.pad[1] = 0u; a.setups[slot] = ts; stored = true; }
+                else a.counters->overflow = 1u;
             }
+            enqueue_tiles(stored, S[q], slot, a.q);
         }
     }
 }
@@ -230,39 +196,23 @@ __global__ void __launch_bounds__(kThreads) k_raster_bin(RasterArgs a) {
 template <bool CAMERA>
 __global__ void __launch_bounds__(kThreads) k_raster_tiles(RasterArgs a) {
     const int lane = threadIdx.x & 31;
-    const unsigned n_items = min(a.counters->tile_queue_count, a.queue_cap);
+    const unsigned n_items = min(*a.q.tile_count, a.q.tile_cap);
     const unsigned warps = gridDim.x * (kThreads / 32);
     for (unsigned item = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); item < n_items; item += warps) {
-        const uint4 it = __ldg(a.queue + item);
-        const TileSetup& ts = a.setups[it.x];
-        const TriSetup s = ts.s;
-        const uint32_t t = ts.tri; const int alpha_tex = ts.alpha_tex;
-        AlphaCtx ac; ac.on = false;
-        if (alpha_tex >= 0) { RV cv[3]; clip_verts(a, CAMERA, t, cv); alpha_setup<CAMERA>(a, t, alpha_tex, cv, ac); }
-        const int px = (int)it.y * kTileW + lane;
-        const int py0 = max((int)it.z * kTileH, s.y0), py1 = min((int)it.z * kTileH + kTileH - 1, s.y1);
-        if (px < s.x0 || px > s.x1) continue;
-        // incremental edge functions down the column (exact: integers)
-        long long E[3], dEy[3];
-        const long long Px = 256ll * px + 128, Py = 256ll * py0 + 128;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int aa = (k + 1) % 3, bb = (k + 2) % 3;
-            E[k] = (long long)(s.X[bb] - s.X[aa]) * (Py - s.Y[aa]) - (long long)(s.Y[bb] - s.Y[aa]) * (Px - s.X[aa]);
-            dEy[k] = 256ll * (s.X[bb] - s.X[aa]);
-        }
-        const float fa = (float)s.area;
-        for (int py = py0; py <= py1; ++py) {
-            if (E[0] + s.bias[0] >= 0 && E[1] + s.bias[1] >= 0 && E[2] + s.bias[2] >= 0) {
-                const float e0 = (float)E[0] / fa, e1 = (float)E[1] / fa, e2 = (float)E[2] / fa;
-                float l[3]; l[0] = e0; l[1] = s.swapped ? e2 : e1; l[2] = s.swapped ? e1 : e2;
-                const float z = interp1(l, s.z[0], s.z[1], s.z[2]);
-                if (!(z < -1.0f || z > 1.0f) && alpha_pass<CAMERA>(a, ac, px, py, l)) depth_write<CAMERA>(a, px, py, z, t);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) E[k] += dEy[k];
-        }
+        const uint2 it = __ldg(a.q.tiles + item);
+        const TileSetup ts = a.setups[it.x];                                // same address in every lane: broadcast
+        const TriSetup& s = ts.s;
+        const int px = (int)(it.y & 0xFFFFu) + (lane & (kTileW - 1)), py = (int)(it.y >> 16) + (lane >> 3);
+        float l[3];
+        if (px > s.x1 || py > s.y1 || !tri_cover(s, px, py, l)) continue;
+        const float z = interp1(l, s.z[0], s.z[1], s.z[2]);
+        if (z < -1.0f || z > 1.0f) continue;
+        if (ts.alpha_tex >= 0 && !alpha_test_slow<CAMERA>(a, ts.tri, ts.alpha_tex, px, py, l)) continue;   // rare: masked materials only
+        depth_write<CAMERA>(a, px, py, z, ts.tri);
     }
+}
+__global__ void __launch_bounds__(kThreads) k_raster_expand(const TileSetup* __restrict__ setups, TileQueues q) {
+    expand_items(reinterpret_cast<const unsigned char*>(setups), sizeof(TileSetup), q);
 }
 
 __global__ void __launch_bounds__(kThreads) k_fill_u32(unsigned* __restrict__ p, size_t n, unsigned v) {
@@ -271,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) k_fill_u32(unsigned* __restrict__ p,
 __global__ void __launch_bounds__(kThreads) k_fill_u64(unsigned long long* __restrict__ p, size_t n, unsigned long long v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
-__global__ void k_reset_queue(Counters* c, unsigned* setup_count) { c->tile_queue_count = 0; *setup_count = 0; }
+__global__ void k_reset_queue(Counters* c) { c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; }
 
 template <bool CAMERA>
 int run_raster(vct_ctx* c) {
@@ -280,18 +230,19 @@ int run_raster(vct_ctx* c) {
     a.indices = c->d_indices; a.trimat = c->d_trimat; a.verts = c->d_vertices; a.n_tris = (uint32_t)c->n_tris;
     a.wpos = c->d_wpos; a.tex = c->d_tex; a.mats = c->d_mat;
     a.depth_bits = reinterpret_cast<unsigned*>(c->d_shadow); a.vis = c->d_vis;
-    a.setups = reinterpret_cast<TileSetup*>(c->d_setup); a.queue = c->d_tile_queue; a.queue_cap = (unsigned)c->tile_queue_cap;
-    a.setup_cap = (unsigned)(2 * c->n_tris + 64); a.counters = c->d_counters;
+    a.setups = reinterpret_cast<TileSetup*>(c->d_setup); a.q = vctk_tile_queues(c);
+    a.setup_cap = (unsigned)c->setup_cap; a.counters = c->d_counters;
     a.setup_count = &c->d_counters->setup_count;
     const size_t npx = (size_t)a.W * a.H;
     const int fill_grid = (int)std::min<size_t>((npx + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 32);
     if (CAMERA) k_fill_u64<<<fill_grid, kThreads, 0, c->stream>>>(c->d_vis, npx, ~0ull);
     else k_fill_u32<<<fill_grid, kThreads, 0, c->stream>>>(a.depth_bits, npx, 0x3F800000u);
     VCT_LAUNCH_CHECK(c, CAMERA ? "k_fill_u64" : "k_fill_u32");
-    k_reset_queue<<<1, 1, 0, c->stream>>>(c->d_counters, a.setup_count); VCT_LAUNCH_CHECK(c, "k_reset_queue");
+    k_reset_queue<<<1, 1, 0, c->stream>>>(c->d_counters); VCT_LAUNCH_CHECK(c, "k_reset_queue");
     if (!c->n_tris) return 0;
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_raster_bin<CAMERA><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, CAMERA ? "k_raster_bin_camera" : "k_raster_bin_light");
+    k_raster_expand<<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a.setups, a.q); VCT_LAUNCH_CHECK(c, CAMERA ? "k_raster_expand_camera" : "k_raster_expand_light");
     k_raster_tiles<CAMERA><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, CAMERA ? "k_raster_tiles_camera" : "k_raster_tiles_light");
     return 0;
 }

@@ -40,34 +40,50 @@ __global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4
 __global__ void __launch_bounds__(kThreads) k_transfer(uint4* __restrict__ color, uint4* __restrict__ radiance, size_t n16,
                                                        float opacity, int temporal, float decay, Counters* __restrict__ counters) {
     unsigned uniq = 0, maxfrag = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
-        uint4 cw = color[i];
-        uint32_t c[4] = {cw.x, cw.y, cw.z, cw.w};
-        uint32_t r[4] = {0, 0, 0, 0};
-        uint4 pw = make_uint4(0, 0, 0, 0);
-        if (temporal) pw = radiance[i];
-        const uint32_t prev[4] = {pw.x, pw.y, pw.z, pw.w};
-        bool dirty = false;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n16; i0 += 2 * stride) {
+        // two independent 16-byte items per thread per trip: both loads are in flight before any arithmetic
+        const size_t i1 = i0 + stride; const bool has1 = i1 < n16;
+        uint4 cws[2], pws[2];
+        cws[0] = color[i0]; cws[1] = has1 ? color[i1] : make_uint4(0, 0, 0, 0);
+        pws[0] = pws[1] = make_uint4(0, 0, 0, 0);
+        if (temporal) { pws[0] = radiance[i0]; if (has1) pws[1] = radiance[i1]; }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            V4 v = unpack_unorm(c[k]);
-            if (v.w > 0.0f) {
-                uniq++;
-                maxfrag = max(maxfrag, f2u_trunc(255.0f * v.w));
-                if (opacity > 0.0f) v.w = opacity;
-                c[k] = pack_unorm(v);
-                dirty = true;
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has1) break;
+            const size_t i = u ? i1 : i0;
+            const uint4 cw = cws[u], pw = pws[u];
+            if ((cw.x | cw.y | cw.z | cw.w) == 0u) {                       // ~97 % of the grid: four empty voxels
+                if (!temporal) { radiance[i] = make_uint4(0, 0, 0, 0); continue; }      // = the reference's clear
+                if ((pw.x | pw.y | pw.z | pw.w) == 0u) continue;                        // mix(0, 0, a) = 0: already stored
             }
-            v.x = v.y = v.z = 0.0f;
-            if (temporal) {
-                const V4 p = unpack_unorm(prev[k]);
-                const float a = 1.0f - decay;
-                v = mk4(mixf(p.x, v.x, a), mixf(p.y, v.y, a), mixf(p.z, v.z, a), mixf(p.w, v.w, a));
-                r[k] = pack_unorm(v);
-            } else if (v.w > 0.0f) r[k] = pack_unorm(v);
+            uint32_t c[4] = {cw.x, cw.y, cw.z, cw.w};
+            uint32_t r[4] = {0, 0, 0, 0};
+            const uint32_t prev[4] = {pw.x, pw.y, pw.z, pw.w};
+            bool dirty = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // imageLoad -> float -> imageStore of an unchanged channel returns the same byte
+                // (round(b/255*255) == b), so only alpha needs arithmetic: transferVoxels.comp:39-50
+                const uint32_t a8 = c[k] >> 24;
+                float aw = 0.0f;
+                if (a8) {
+                    uniq++;
+                    aw = (float)a8 / 255.0f;
+                    maxfrag = max(maxfrag, f2u_trunc(255.0f * aw));
+                    if (opacity > 0.0f) aw = opacity;
+                    c[k] = (c[k] & 0x00FFFFFFu) | unorm8(aw) << 24;
+                    dirty = true;
+                }
+                if (temporal) {                                             // mix(prev, vec4(0,0,0,aw), 1 - decay), :55-62
+                    const V4 p = unpack_unorm(prev[k]);
+                    const float a = 1.0f - decay;
+                    r[k] = pack_unorm(mk4(mixf(p.x, 0.0f, a), mixf(p.y, 0.0f, a), mixf(p.z, 0.0f, a), mixf(p.w, aw, a)));
+                } else if (aw > 0.0f) r[k] = unorm8(aw) << 24;
+            }
+            if (dirty) color[i] = make_uint4(c[0], c[1], c[2], c[3]);
+            radiance[i] = make_uint4(r[0], r[1], r[2], r[3]);
         }
-        if (dirty) color[i] = make_uint4(c[0], c[1], c[2], c[3]);
-        radiance[i] = make_uint4(r[0], r[1], r[2], r[3]);
     }
     // block reduction -> one atomic pair per CTA
     __shared__ unsigned s_u[kThreads / 32], s_m[kThreads / 32];
@@ -151,28 +167,37 @@ __global__ void __launch_bounds__(256) k_inject(const FrameConst* __restrict__ f
     }
     __syncthreads();
     const int x = bx + tx, y = by + ty;
-    if (x >= S || y >= S) return;
-    const float tu = (float)x / (float)S, tv = (float)y / (float)S;
-    float d;
-    {   // shadow_linear(tu, tv) with texels taken from the tile when the footprint is the expected one
-        const float fxp = tu * (float)S - 0.5f, fyp = tv * (float)S - 0.5f;
-        const float fx0 = floorf(fxp), fy0 = floorf(fyp);
-        const int x0 = (int)fx0, y0 = (int)fy0; const float fx = fxp - fx0, fy = fyp - fy0;
-        const int lx = x0 - bx + 1, ly = y0 - by + 1;
-        if (lx >= 0 && lx + 1 < 33 && ly >= 0 && ly + 1 < 9) {
-            const float top = tile[ly][lx] * (1.0f - fx) + tile[ly][lx + 1] * fx;
-            const float bot = tile[ly + 1][lx] * (1.0f - fx) + tile[ly + 1][lx + 1] * fx;
-            d = top * (1.0f - fy) + bot * fy;
-        } else d = shadow_linear(shadow, S, tu, tv, 0, 0);
+    bool valid = x < S && y < S;
+    uint32_t o = 0xFFFFFFFFu;
+    int ix = 0, iy = 0, iz = 0;
+    if (valid) {
+        // x/S: S is a power of two in every configuration, where the division is an exact scaling (bit-identical)
+        const bool pow2 = (S & (S - 1)) == 0;
+        const float inv = 1.0f / (float)S;
+        const float tu = pow2 ? (float)x * inv : (float)x / (float)S, tv = pow2 ? (float)y * inv : (float)y / (float)S;
+        float d;
+        {   // shadow_linear(tu, tv) with texels taken from the tile when the footprint is the expected one
+            const float fxp = tu * (float)S - 0.5f, fyp = tv * (float)S - 0.5f;
+            const float fx0 = floorf(fxp), fy0 = floorf(fyp);
+            const int x0 = (int)fx0, y0 = (int)fy0; const float fx = fxp - fx0, fy = fyp - fy0;
+            const int lx = x0 - bx + 1, ly = y0 - by + 1;
+            if (lx >= 0 && lx + 1 < 33 && ly >= 0 && ly + 1 < 9) {
+                const float top = tile[ly][lx] * (1.0f - fx) + tile[ly][lx + 1] * fx;
+                const float bot = tile[ly + 1][lx] * (1.0f - fx) + tile[ly + 1][lx + 1] * fx;
+                d = top * (1.0f - fy) + bot * fy;
+            } else d = shadow_linear(shadow, S, tu, tv, 0, 0);
+        }
+        const float nx = tu * 2.0f - 1.0f, ny = tv * 2.0f - 1.0f, nz = d * 2.0f - 1.0f;
+        const V4 w = mul44(fc.ls_inverse, mk4(nx, ny, nz, 1.0f));
+        V3 vp = get_voxel_position(mk3(w.x, w.y, w.z), fc.p, warpmap);
+        vp = mk3((float)D * vp.x, (float)D * vp.y, (float)D * vp.z);
+        valid = to_voxel_index(vp, D, ix, iy, iz) && iz >= fc.z_lo && iz < fc.z_hi;      // z-slab ownership (multi-GPU)
+        if (valid) o = (uint32_t)(((size_t)iz * D + iy) * D + ix);
     }
-    const float nx = tu * 2.0f - 1.0f, ny = tv * 2.0f - 1.0f, nz = d * 2.0f - 1.0f;
-    const V4 w = mul44(fc.ls_inverse, mk4(nx, ny, nz, 1.0f));
-    V3 vp = get_voxel_position(mk3(w.x, w.y, w.z), fc.p, warpmap);
-    vp = mk3((float)D * vp.x, (float)D * vp.y, (float)D * vp.z);
-    int ix, iy, iz;
-    if (!to_voxel_index(vp, D, ix, iy, iz)) return;
-    if (iz < fc.z_lo || iz >= fc.z_hi) return;                    // z-slab ownership (multi-GPU)
-    const size_t o = ((size_t)iz * D + iy) * D + ix;
+    // Neighbouring texels of a row mostly land in the same voxel (4096^2 texels onto ~4e5 voxels) and every writer
+    // stores the same word, so a lane whose left neighbour targets the same voxel leaves the store to it.
+    const uint32_t left = __shfl_up_sync(0xffffffffu, o, 1);
+    if (!valid || (tx > 0 && left == o)) return;
     const uint32_t cw = __ldg(color + o);
     if (!fc.p.radiance_lighting) { radiance[o] = cw; return; }   // packUnorm4x8(unpackUnorm4x8(c)) == c for every byte
     V4 c = unpack_unorm(cw);
@@ -248,6 +273,88 @@ __global__ void __launch_bounds__(kThreads) k_mip_box2(const uint32_t* __restric
         reinterpret_cast<uint4*>(dst + ((size_t)z * Dd + y) * Dd)[q] = make_uint4(out[0], out[1], out[2], out[3]);
     }
 }
+// Whole BOX2 chain in ONE launch: a CTA owns a B^3 block of level 0 (B = 2^R <= 32), streams it once from HBM,
+// writes its (B/2)^3 block of level 1 and keeps it in shared memory, from which levels 2..R follow without
+// touching HBM again.  Every level is computed from the ROUNDED unorm8 words of the level below, exactly like the
+// reference's one-dispatch-per-level loop (src/Application.cpp:889-902).  With `publish`, the level-0 words that
+// pass through registers and every produced level are also written to the surfaces of the mipmapped array the
+// cone tracer samples, which replaces the separate linear -> array copy.
+struct MipChainArgs {
+    const uint32_t* src0; uint32_t* lvl[6];       // lvl[k] = linear level k (k >= 1 written)
+    cudaSurfaceObject_t surf[6];
+    int D, R, z0, publish;
+};
+__device__ __forceinline__ uint32_t box2_words(const uint32_t w[8], const float* __restrict__ lut) {
+    if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0u) return 0u;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc_word(acc, w[k], lut);
+    return finish_word(acc, 0.125f);
+}
+__global__ void __launch_bounds__(kThreads) k_mip_chain(MipChainArgs a) {
+    __shared__ float lut[256];
+    __shared__ uint32_t s1[16 * 16 * 16], s2[8 * 8 * 8], s3[4 * 4 * 4], s4[2 * 2 * 2];
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __syncthreads();
+    const int B = 1 << a.R, H = B >> 1, D = a.D;
+    const int bx = blockIdx.x * B, by = blockIdx.y * B, bz = a.z0 + blockIdx.z * B;
+    // ---- level 0 -> 1: one thread = 4 consecutive level-1 texels (8 x 16-byte loads, 1 x 16-byte store)
+    const int qx = H >> 2, nquads = qx * H * H, D1 = D >> 1;
+    for (int q = threadIdx.x; q < nquads; q += kThreads) {
+        const int lx = (q % qx) * 4, ly = (q / qx) % H, lz = q / (qx * H);
+        const int x0 = bx + 2 * lx, y0 = by + 2 * ly, z0 = bz + 2 * lz;
+        const uint4* r00 = reinterpret_cast<const uint4*>(a.src0 + ((size_t)z0 * D + y0) * D + x0);
+        const uint4* r10 = reinterpret_cast<const uint4*>(a.src0 + ((size_t)z0 * D + y0 + 1) * D + x0);
+        const uint4* r01 = reinterpret_cast<const uint4*>(a.src0 + ((size_t)(z0 + 1) * D + y0) * D + x0);
+        const uint4* r11 = reinterpret_cast<const uint4*>(a.src0 + ((size_t)(z0 + 1) * D + y0 + 1) * D + x0);
+        uint4 v[8];
+        v[0] = __ldg(r00); v[1] = __ldg(r00 + 1); v[2] = __ldg(r01); v[3] = __ldg(r01 + 1);
+        v[4] = __ldg(r10); v[5] = __ldg(r10 + 1); v[6] = __ldg(r11); v[7] = __ldg(r11 + 1);
+        if (a.publish) {
+            surf3Dwrite(v[0], a.surf[0], x0 * 4, y0, z0); surf3Dwrite(v[1], a.surf[0], x0 * 4 + 16, y0, z0);
+            surf3Dwrite(v[2], a.surf[0], x0 * 4, y0, z0 + 1); surf3Dwrite(v[3], a.surf[0], x0 * 4 + 16, y0, z0 + 1);
+            surf3Dwrite(v[4], a.surf[0], x0 * 4, y0 + 1, z0); surf3Dwrite(v[5], a.surf[0], x0 * 4 + 16, y0 + 1, z0);
+            surf3Dwrite(v[6], a.surf[0], x0 * 4, y0 + 1, z0 + 1); surf3Dwrite(v[7], a.surf[0], x0 * 4 + 16, y0 + 1, z0 + 1);
+        }
+        const uint32_t A[8] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w};      // (y0,z0)
+        const uint32_t Bq[8] = {v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};    // (y0,z1)
+        const uint32_t Cq[8] = {v[4].x, v[4].y, v[4].z, v[4].w, v[5].x, v[5].y, v[5].z, v[5].w};    // (y1,z0)
+        const uint32_t Dq[8] = {v[6].x, v[6].y, v[6].z, v[6].w, v[7].x, v[7].y, v[7].z, v[7].w};    // (y1,z1)
+        uint32_t out[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            // shader offset order (x,y,z): (0,0,0),(0,0,1),(0,1,0),(0,1,1),(1,0,0),(1,0,1),(1,1,0),(1,1,1)
+            const uint32_t w[8] = {A[2 * t], Bq[2 * t], Cq[2 * t], Dq[2 * t], A[2 * t + 1], Bq[2 * t + 1], Cq[2 * t + 1], Dq[2 * t + 1]};
+            out[t] = box2_words(w, lut);
+        }
+        const uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
+        const int gx = (bx >> 1) + lx, gy = (by >> 1) + ly, gz = (bz >> 1) + lz;
+        *reinterpret_cast<uint4*>(a.lvl[1] + ((size_t)gz * D1 + gy) * D1 + gx) = o;
+        if (a.publish) surf3Dwrite(o, a.surf[1], gx * 4, gy, gz);
+        *reinterpret_cast<uint4*>(s1 + (lz * H + ly) * H + lx) = o;
+    }
+    // ---- levels 1 -> 2 -> ... -> R from shared memory
+    for (int k = 1; k < a.R; ++k) {
+        __syncthreads();
+        const int Hs = B >> k, Hd = Hs >> 1, Dd = D >> (k + 1);
+        const uint32_t* src = k == 1 ? s1 : k == 2 ? s2 : k == 3 ? s3 : s4;
+        uint32_t* dsts = k == 1 ? s2 : k == 2 ? s3 : k == 3 ? s4 : nullptr;
+        uint32_t* gl = k == 1 ? a.lvl[2] : k == 2 ? a.lvl[3] : k == 3 ? a.lvl[4] : a.lvl[5];
+        const cudaSurfaceObject_t gs = k == 1 ? a.surf[2] : k == 2 ? a.surf[3] : k == 3 ? a.surf[4] : a.surf[5];
+        for (int i = threadIdx.x; i < Hd * Hd * Hd; i += kThreads) {
+            const int lx = i % Hd, ly = (i / Hd) % Hd, lz = i / (Hd * Hd);
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = src[((2 * lz + (j & 1)) * Hs + 2 * ly + ((j >> 1) & 1)) * Hs + 2 * lx + (j >> 2)];
+            const uint32_t o = box2_words(w, lut);
+            const int gx = (bx >> (k + 1)) + lx, gy = (by >> (k + 1)) + ly, gz = (bz >> (k + 1)) + lz;
+            gl[((size_t)gz * Dd + gy) * Dd + gx] = o;
+            if (a.publish) surf3Dwrite(o, gs, gx * 4, gy, gz);
+            if (dsts) dsts[(lz * Hd + ly) * Hd + lx] = o;
+        }
+    }
+}
+
 // generic (any size, any kernel mode) — used for the small top levels and for BOX3 / CUBE
 __global__ void __launch_bounds__(kThreads) k_mip_generic(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int Ds, int mode, int zd_lo, int zd_hi) {
     __shared__ float lut[256];
@@ -315,7 +422,7 @@ int vctk_clear_voxels(vct_ctx* c) {
 int vctk_transfer(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
     const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
-    k_transfer<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_radiance + off), n / 4,
+    k_transfer<<<grid_for(n / 8, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_radiance + off), n / 4,
                                                                     p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_transfer");
     return 0;
@@ -335,13 +442,45 @@ int vctk_fill_holes(vct_ctx* c) {
     vct_prof_mark(c, "memcpy_d2d");
     return 0;
 }
-// levels 1..L-1 (the reference's last loop iteration targets a non-existent level: Application.cpp:889-902)
-int vctk_mip(vct_ctx* c, int which, int mode) {
+static int publish_levels(vct_ctx* c, int which, int l_begin, int l_end) {
     uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
-    for (int l = 0; l + 1 < c->L; ++l) {
+    cudaSurfaceObject_t* surf = which == VCT_VOL_COLOR ? c->color_surf : c->radiance_surf;
+    for (int l = l_begin; l < l_end; ++l) {
+        const int d = level_dim(c->D, l);
+        const size_t items = (size_t)(d >= 4 ? d / 4 : 1) * d * d;
+        k_publish<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(base + c->level_off[l], surf[l], d);
+        VCT_LAUNCH_CHECK(c, "k_publish");
+    }
+    return 0;
+}
+// levels 1..L-1 (the reference's last loop iteration targets a non-existent level: Application.cpp:889-902).
+// publish != 0 (single GPU): the pyramid also lands in the mipmapped array the cone tracer samples.
+int vctk_mip(vct_ctx* c, int which, int mode, int publish) {
+    uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
+    cudaSurfaceObject_t* surf = which == VCT_VOL_COLOR ? c->color_surf : c->radiance_surf;
+    if (publish && !surf[0]) publish = 0;
+    int first = 0;                                  // first source level still to be filtered
+    int published_upto = 0;                         // levels [0, published_upto) are already in the array
+    // fused chain: R reductions per CTA, block edge 2^R; needs whole blocks inside this rank's slab
+    int R = c->L - 1 < 5 ? c->L - 1 : 5;
+    while (R >= 3 && ((c->z_hi - c->z_lo) % (1 << R) || c->z_lo % (1 << R) || c->D % (1 << R))) R--;
+    if (mode == 0 && R >= 3) {
+        MipChainArgs a{};
+        a.src0 = base + c->level_off[0];
+        for (int k = 1; k <= R; ++k) a.lvl[k] = base + c->level_off[k];
+        for (int k = 0; k <= R; ++k) a.surf[k] = surf[k];
+        a.D = c->D; a.R = R; a.z0 = c->z_lo; a.publish = publish;
+        const int B = 1 << R;
+        dim3 grid(c->D / B, c->D / B, (c->z_hi - c->z_lo) / B);
+        k_mip_chain<<<grid, kThreads, 0, c->stream>>>(a);
+        VCT_LAUNCH_CHECK(c, "k_mip_chain");
+        first = R;
+        if (publish) published_upto = R + 1;
+    }
+    for (int l = first; l + 1 < c->L; ++l) {
         const int Ds = level_dim(c->D, l), Dd = Ds >> 1;
         if (Dd < 1) break;
-        // z-slab of the destination level owned by this rank (whole level when the slab is thinner than a texel)
+        // z-slab of the destination level owned by this rank
         int zd_lo = c->z_lo >> (l + 1), zd_hi = c->z_hi >> (l + 1);
         if (c->cfg.world_size <= 1) { zd_lo = 0; zd_hi = Dd; }
         else if (zd_hi <= zd_lo) { c->error = "vct_mip: a mip level is thinner than one z-slab per rank (levels > log2(dim/world_size)+1 need a coarse-level exchange)"; return 1; }
@@ -356,19 +495,10 @@ int vctk_mip(vct_ctx* c, int which, int mode) {
             VCT_LAUNCH_CHECK(c, "k_mip_generic");
         }
     }
+    if (publish && published_upto < c->L) return publish_levels(c, which, published_upto, c->L);
     return 0;
 }
-int vctk_publish(vct_ctx* c, int which) {
-    uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
-    cudaSurfaceObject_t* surf = which == VCT_VOL_COLOR ? c->color_surf : c->radiance_surf;
-    for (int l = 0; l < c->L; ++l) {
-        const int d = level_dim(c->D, l);
-        const size_t items = (size_t)(d >= 4 ? d / 4 : 1) * d * d;
-        k_publish<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(base + c->level_off[l], surf[l], d);
-        VCT_LAUNCH_CHECK(c, "k_publish");
-    }
-    return 0;
-}
+int vctk_publish(vct_ctx* c, int which) { return publish_levels(c, which, 0, c->L); }
 int vctk_set_voxel_opacity(vct_ctx* c, float opacity) {
     const size_t n = (size_t)c->D * c->D * c->D;
     k_set_voxel_opacity<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(c->d_color, c->d_radiance, n, opacity, c->d_counters);

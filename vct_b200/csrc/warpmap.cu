@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(1024) k_warpmap(const uint32_t* __restrict__ o
 
 int vctk_warpmap(vct_ctx* c) {
     k_warpmap<<<1, 1024, 0, c->stream>>>(c->d_occ, c->d_fc, reinterpret_cast<ushort4*>(c->d_warpmap), reinterpret_cast<ushort4*>(c->d_wlo),
-                                         reinterpret_cast<ushort4*>(c->d_whi), reinterpret_cast<uint8_t*>(c->d_scan_tmp));
+                                         reinterpret_cast<ushort4*>(c->d_whi), reinterpret_cast<uint8_t*>(c->d_warp_scratch));
     VCT_LAUNCH_CHECK(c, "k_warpmap");
     return 0;
 }
