@@ -173,3 +173,88 @@ def test_error_paths(room):
     q = type(p).from_buffer_copy(p); q.radiance_dilate = 1
     with pytest.raises(VctError):
         g.inject(q)
+
+
+def test_non_power_of_two_shadow_map_and_odd_frame():
+    """Generic (non power-of-two) injectRadiance path and a frame size that is not a multiple of the 8x4 tiles."""
+    from vct_b200.pipeline import Pipeline
+    sc = S.room_scene(seed=3)
+    w, h, ss = 203, 117, 500
+    p = S.room_params(w, h)
+    o = Oracle(sc, 32, 4, ss, w, h)
+    g = Pipeline(sc, 32, 4, ss, w, h)
+    try:
+        o.frame(p); g.frame(p)
+        assert np.array_equal(g.read_shadowmap().view(np.uint32), o.shadow.view(np.uint32))
+        assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0]) and np.array_equal(g.read_volume(P.VOL_RADIANCE), o.radiance[0])
+        for l in range(1, 4):
+            assert np.array_equal(g.read_volume(P.VOL_RADIANCE, l), o.radiance[l])
+        assert np.array_equal(g.read_visibility(), o.vis)
+        assert psnr(g.read_image(), o.image) >= 45.0
+    finally:
+        g.close()
+
+
+def test_empty_scene_and_degenerate_triangles():
+    """Edge cases: no geometry at all, zero-area and off-volume triangles produce no fragments and no errors."""
+    from vct_b200.pipeline import Pipeline
+    sc = S.Scene()
+    m = sc.add_material(diffuse=sc.add_texture(np.full((2, 2, 3), 200, np.uint8)))
+    v = np.zeros((9, 14), np.float32)
+    v[0:3, 0:3] = [[0, 0, 0], [0, 0, 0], [0, 0, 0]]                      # zero-area
+    v[3:6, 0:3] = [[50, 50, 50], [51, 50, 50], [50, 51, 50]]             # outside the volume
+    v[6:9, 0:3] = [[0.1, 0.1, 0.1], [0.1001, 0.1, 0.1], [0.1, 0.1001, 0.1]]   # sub-voxel sliver
+    v[:, 3:6] = [0, 0, 1]
+    sc.add_actor(S.Mesh(v, np.arange(9, dtype=np.uint32), np.full(3, m, np.int32)))
+    sc.lights = [P.make_light(position=(1.2, 4.0, 0.7), direction=(-0.28, -0.9, -0.2), shadow_caster=True, type_=1)]
+    p = S.room_params(64, 48)
+    o = Oracle(sc, 32, 4, 128, 64, 48)
+    g = Pipeline(sc, 32, 4, 128, 64, 48)
+    try:
+        o.frame(p); g.frame(p)
+        assert g.counters().total_fragments == o.info.total_fragments
+        assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0])
+        assert np.array_equal(g.read_image(), o.image)
+    finally:
+        g.close()
+    g = Pipeline(S.Scene(), 32, 4, 128, 64, 48)              # nothing uploaded at all
+    try:
+        g.set_lights([]); g.frame(p)
+        assert not g.read_volume(P.VOL_RADIANCE).any()
+        assert len(set(g.read_image().tolist())) == 1        # clear colour everywhere
+    finally:
+        g.close()
+
+
+@pytest.mark.skipif(not S.baked_available("sponza_pbr"), reason="assets/_baked/sponza_pbr missing (run tools/bake_assets.py where /root/reference exists)")
+def test_sponza_256_1080p_full_size_gates():
+    """BASELINE.json config: PBR Sponza, 256^3, 1920x1080 — the north-star gates at full size against the oracle:
+    occupancy mask bit-exact, RGBA8 volumes max|delta| <= 2 (this build: 0), final image PSNR >= 45 dB."""
+    import bench
+    from vct_b200.pipeline import Pipeline
+    sc, p, D, W, H, _ = bench.build_workload()
+    o = Oracle(sc, D, bench.LEVELS, bench.SHADOW, W, H)
+    g = Pipeline(sc, D, bench.LEVELS, bench.SHADOW, W, H)
+    try:
+        o.frame(p); g.frame(p)
+        col, rad, nrm = g.read_volume(P.VOL_COLOR), g.read_volume(P.VOL_RADIANCE), g.read_volume(P.VOL_NORMAL)
+        assert np.array_equal((col >> 24) != 0, (o.color[0] >> 24) != 0), "occupancy mask must be bit-exact"
+        info = g.counters()
+        assert (info.total_fragments, info.unique_voxels, info.max_fragments_per_voxel) == (o.info.total_fragments, o.info.unique_voxels, o.info.max_fragments_per_voxel)
+        assert info.unique_voxels > 400000
+        d = max(max_byte_delta(col, o.color[0]), max_byte_delta(rad, o.radiance[0]), max_byte_delta(nrm, o.normal))
+        assert d <= 2
+        for l in range(1, bench.LEVELS):
+            assert np.array_equal(g.read_volume(P.VOL_RADIANCE, l), o.radiance[l])
+        assert np.array_equal(g.read_shadowmap().view(np.uint32), o.shadow.view(np.uint32))
+        vis_diff = int((g.read_visibility() != o.vis).sum())
+        q = psnr(g.read_image(), o.image)
+        print(f"sponza: volumes max byte delta {d}, visibility pixels differing {vis_diff}, image PSNR {q:.2f} dB, cone steps gpu {g.cone_steps()} oracle {o.cone_steps}")
+        assert vis_diff == 0
+        assert q >= 45.0
+        # size-independent properties at full size: level l+1 alpha mass never exceeds level l (box filter), counters add up
+        a0 = int((rad >> 24).astype(np.uint64).sum())
+        a1 = int((g.read_volume(P.VOL_RADIANCE, 1) >> 24).astype(np.uint64).sum())
+        assert abs(a1 * 8 - a0) <= 0.02 * a0 + 4 * (D // 2) ** 3 * 0      # mean preserved up to rounding
+    finally:
+        g.close()

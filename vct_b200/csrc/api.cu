@@ -2,6 +2,7 @@
 // upload (Mesh VAO/EBO/texture creation), the per-pass entry points that replace the GL dispatch blocks of
 // Application::render (src/Application.cpp:196-1085) and the whole-frame graph in the reference's pass order.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "common.cuh"
@@ -22,14 +23,18 @@ void free_volumes(vct_ctx* c) {
         if (c->color_surf[l]) cudaDestroySurfaceObject(c->color_surf[l]);
         c->radiance_surf[l] = c->color_surf[l] = 0;
     }
-    for (cudaTextureObject_t* t : {&c->radiance_tex, &c->radiance_tex_point, &c->color_tex, &c->color_tex_point}) { if (*t) cudaDestroyTextureObject(*t); *t = 0; }
+    for (cudaTextureObject_t* t : {&c->radiance_tex, &c->radiance_tex_point, &c->radiance_tex_last, &c->color_tex, &c->color_tex_point, &c->color_tex_last}) { if (*t) cudaDestroyTextureObject(*t); *t = 0; }
     if (c->radiance_arr) cudaFreeMipmappedArray(c->radiance_arr);
     if (c->color_arr) cudaFreeMipmappedArray(c->color_arr);
     c->radiance_arr = c->color_arr = nullptr;
     for (uint32_t** p : {&c->d_color, &c->d_radiance, &c->d_normal, &c->d_scratch}) { cudaFree(*p); *p = nullptr; }
+    for (uint8_t** p : {&c->d_pub_mask_radiance, &c->d_pub_mask_color}) { cudaFree(*p); *p = nullptr; }
 }
 
-int make_pyramid_texture(vct_ctx* c, cudaMipmappedArray_t* arr, cudaTextureObject_t* lin, cudaTextureObject_t* pt, cudaSurfaceObject_t* surf) {
+int make_pyramid_texture(vct_ctx* c, cudaMipmappedArray_t* arr, cudaTextureObject_t* lin, cudaTextureObject_t* pt, cudaTextureObject_t* last, cudaSurfaceObject_t* surf, uint8_t** mask) {
+    // array contents are undefined until the first publish: mask = everything may be non-zero
+    VCT_CHECK(c, cudaMalloc(mask, (size_t)c->D * c->D * c->D / 8));
+    VCT_CHECK(c, cudaMemsetAsync(*mask, 0xFF, (size_t)c->D * c->D * c->D / 8, c->stream));
     cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
     VCT_CHECK(c, cudaMallocMipmappedArray(arr, &fd, make_cudaExtent(c->D, c->D, c->D), c->L, cudaArraySurfaceLoadStore));
     for (int l = 0; l < c->L; ++l) {
@@ -46,6 +51,9 @@ int make_pyramid_texture(vct_ctx* c, cudaMipmappedArray_t* arr, cudaTextureObjec
     VCT_CHECK(c, cudaCreateTextureObject(lin, &rd, &td, nullptr));
     td.filterMode = cudaFilterModePoint; td.mipmapFilterMode = cudaFilterModePoint;          // mag NEAREST
     VCT_CHECK(c, cudaCreateTextureObject(pt, &rd, &td, nullptr));
+    td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModePoint;         // one level, trilinear: lambda >= L-1
+    td.minMipmapLevelClamp = td.maxMipmapLevelClamp = (float)(c->L - 1);
+    VCT_CHECK(c, cudaCreateTextureObject(last, &rd, &td, nullptr));
     return 0;
 }
 
@@ -60,7 +68,7 @@ int make_volumes(vct_ctx* c) {
     VCT_CHECK(c, cudaMalloc(&c->d_color, off * 4)); VCT_CHECK(c, cudaMalloc(&c->d_radiance, off * 4)); VCT_CHECK(c, cudaMalloc(&c->d_normal, n0 * 4));
     VCT_CHECK(c, cudaMemsetAsync(c->d_color, 0, off * 4, c->stream)); VCT_CHECK(c, cudaMemsetAsync(c->d_radiance, 0, off * 4, c->stream));
     VCT_CHECK(c, cudaMemsetAsync(c->d_normal, 0, n0 * 4, c->stream));
-    if (make_pyramid_texture(c, &c->radiance_arr, &c->radiance_tex, &c->radiance_tex_point, c->radiance_surf)) return 1;
+    if (make_pyramid_texture(c, &c->radiance_arr, &c->radiance_tex, &c->radiance_tex_point, &c->radiance_tex_last, c->radiance_surf, &c->d_pub_mask_radiance)) return 1;
     const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
     c->z_lo = (int)((long long)c->D * r / ws); c->z_hi = (int)((long long)c->D * (r + 1) / ws);
     return 0;
@@ -76,7 +84,7 @@ int finalize_scene(vct_ctx* c) {
     if (!c->scene_dirty) return 0;
     std::sort(c->meshes.begin(), c->meshes.end(), [](const HostMesh& a, const HostMesh& b) { return a.actor < b.actor; });
     for (void** p : {(void**)&c->d_vertices, (void**)&c->d_vactor, (void**)&c->d_indices, (void**)&c->d_trimat, (void**)&c->d_models, (void**)&c->d_nmats, (void**)&c->d_wpos,
-                     (void**)&c->d_wnrm, (void**)&c->d_wT, (void**)&c->d_wB, (void**)&c->d_setup, (void**)&c->d_tile_queue, (void**)&c->d_expand_queue}) { cudaFree(*p); *p = nullptr; }
+                     (void**)&c->d_wnrm, (void**)&c->d_wT, (void**)&c->d_wB, (void**)&c->d_setup, (void**)&c->d_tile_queue, (void**)&c->d_expand_queue, (void**)&c->d_pixel_queue}) { cudaFree(*p); *p = nullptr; }
     c->n_vertices = c->h_vertices.size() / 14; c->n_tris = c->h_trimat.size();
     c->n_actors = 0; for (auto& m : c->meshes) c->n_actors = std::max(c->n_actors, m.actor + 1);
     if (!c->n_vertices || !c->n_tris) { c->scene_dirty = false; return 0; }
@@ -93,6 +101,8 @@ int finalize_scene(vct_ctx* c) {
     VCT_CHECK(c, cudaMalloc(&c->d_tile_queue, c->tile_queue_cap * 8));
     c->expand_cap = 2 * nt + ((size_t)1 << 20);
     VCT_CHECK(c, cudaMalloc(&c->d_expand_queue, c->expand_cap * 8));
+    c->pixel_cap = 2 * nt + ((size_t)1 << 20);
+    VCT_CHECK(c, cudaMalloc(&c->d_pixel_queue, c->pixel_cap * 8));
     VCT_CHECK(c, cudaMemcpy(c->d_vertices, c->h_vertices.data(), nv * 56, cudaMemcpyHostToDevice));
     VCT_CHECK(c, cudaMemcpy(c->d_vactor, c->h_vactor.data(), nv * 4, cudaMemcpyHostToDevice));
     VCT_CHECK(c, cudaMemcpy(c->d_indices, c->h_indices.data(), nt * 12, cudaMemcpyHostToDevice));
@@ -101,8 +111,29 @@ int finalize_scene(vct_ctx* c) {
     return 0;
 }
 
+// phong.frag:145-177 in fp32, one rounding per operation: r = h*tan(theta/2); lod = log2(max(1, 2r)); h += r
+void build_schedule(ConeSchedule& t, const vct_cone_settings& cs, int levels) {
+    const float tan_half = std::tan(cs.cone_angle / 2.0f), max_lod = (float)(levels - 1);
+    const int steps = std::min(std::max(cs.steps, 0), VCT_MAX_CONE_STEPS);
+    int np = 0, nl = steps;
+    volatile float h = cs.cone_initial_height;
+    for (int i = 0; i < steps; ++i) {
+        volatile float r = h * tan_half;
+        volatile float two_r = 2.0f * r;
+        volatile float lod = std::log2(two_r > 1.0f ? two_r : 1.0f);
+        volatile float lambda = lod + cs.lod_offset;
+        t.h[i] = h; t.lambda[i] = lambda;
+        if (!(lambda > 0.5f) && np == i) np = i + 1;
+        if (lambda >= max_lod && nl == steps) nl = i;
+        h = h + r;
+    }
+    if (nl < np) nl = np;
+    t.n_point = np; t.n_last = nl; t.steps = steps; t.pad = 0;
+}
+
 int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     if (!p) return fail(c, "null frame params");
+    if (p->diffuse_cone.steps > 64 || p->specular_cone.steps > 64 || p->diffuse_cone.steps < 0 || p->specular_cone.steps < 0) return fail(c, "cone steps must be in [0,64]");
     if (p->radiance_dilate) return fail(c, "radianceDilate is malformed in the reference (injectRadiance.comp:59-64) and is not supported");
     if (finalize_scene(c)) return 1;
     FrameConst& f = c->h_fc;
@@ -112,6 +143,7 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     f.p = *p; f.D = c->D; f.L = c->L; f.S = c->S; f.W = c->W; f.H = c->H;
     f.n_lights = c->n_lights; std::memcpy(f.lights, c->h_lights, sizeof f.lights);
     f.z_lo = c->z_lo; f.z_hi = c->z_hi;
+    build_schedule(f.sched_diffuse, p->diffuse_cone, c->L); build_schedule(f.sched_specular, p->specular_cone, c->L);
     VCT_CHECK(c, cudaMemcpyAsync(c->d_fc, &f, sizeof f, cudaMemcpyHostToDevice, c->stream));
     if (c->tables_dirty) {                      // texture / material tables change only on upload
         VCT_CHECK(c, cudaMemcpyAsync(c->d_tex, c->h_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES, cudaMemcpyHostToDevice, c->stream));
@@ -127,7 +159,7 @@ struct Graph { vct_ctx* c; bool timed; int rec(int e) { if (timed && c->profilin
 
 int ensure_color_texture(vct_ctx* c) {
     if (c->color_arr) return 0;
-    return make_pyramid_texture(c, &c->color_arr, &c->color_tex, &c->color_tex_point, c->color_surf);
+    return make_pyramid_texture(c, &c->color_arr, &c->color_tex, &c->color_tex_point, &c->color_tex_last, c->color_surf, &c->d_pub_mask_color);
 }
 int ensure_scratch(vct_ctx* c) {
     if (c->d_scratch) return 0;
@@ -151,8 +183,9 @@ int gi_body(vct_ctx* c, Graph& g) {
     // single GPU: the chain that the cone tracer samples is written straight into its texture array
     const bool single = c->cfg.world_size <= 1;
     if (single && !p.draw_radiance && ensure_color_texture(c)) return 1;
-    if (vctk_mip(c, VCT_VOL_RADIANCE, 0, single && p.draw_radiance)) return 1;
-    if (p.mip_color_chain || !p.draw_radiance) { if (vctk_mip(c, VCT_VOL_COLOR, 0, single && !p.draw_radiance)) return 1; }
+    const int which[2] = {VCT_VOL_RADIANCE, VCT_VOL_COLOR};
+    const int publish[2] = {single && p.draw_radiance, single && !p.draw_radiance};
+    if (vctk_mip_chains(c, (p.mip_color_chain || !p.draw_radiance) ? 2 : 1, which, publish, 0)) return 1;   // both pyramids, one launch
     return g.rec(EV_MIP);
 }
 
@@ -200,7 +233,7 @@ int vct_destroy(vct_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
     for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_warp_scratch,
-                    c->d_tile_queue, c->d_expand_queue, (void*)c->d_fc, (void*)c->d_counters,
+                    c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, (void*)c->d_fc, (void*)c->d_counters,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_models, (void*)c->d_nmats, (void*)c->d_wpos,
                     (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})
         cudaFree(p);

@@ -63,6 +63,12 @@ struct DevTexture { const uint8_t* level[16]; int w, h, ch, levels; };
 struct DevMaterial { int diffuse_tex, specular_tex, normal_tex, roughness_tex, metallic_tex, alpha_tex; float shininess; float diffuse[3]; };
 
 // Per-frame constants every pass reads (uploaded once per frame into __constant__-like global struct).
+// Step schedule of a cone (phong.frag:145-177): height h_i and lambda_i = lod_i + lodOffset depend only on the cone
+// settings, so the host builds them once per frame.  lambda is non-decreasing: [0,n_point) NEAREST on level 0,
+// [n_point,n_last) trilinear + mip-linear, [n_last,steps) last level only.
+#define VCT_MAX_CONE_STEPS 64
+struct ConeSchedule { float h[VCT_MAX_CONE_STEPS]; float lambda[VCT_MAX_CONE_STEPS]; int n_point, n_last, steps, pad; };
+
 struct FrameConst {
     Mat4 projection, view, lp, lv, ls, ls_inverse, mvp_x, mvp_y, mvp_z;
     vct_frame_params p;          // scalar settings (matrices inside are unused on the device)
@@ -70,6 +76,7 @@ struct FrameConst {
     int n_lights;
     vct_light lights[8];
     int z_lo, z_hi;              // z-slab [z_lo, z_hi) owned by this rank
+    ConeSchedule sched_diffuse, sched_specular;
 };
 
 struct Counters {                // device-resident, zeroed per frame
@@ -77,8 +84,10 @@ struct Counters {                // device-resident, zeroed per frame
     unsigned n_frag_slots;       // fragments emitted (== total_fragments within this slab)
     unsigned tile_queue_count;   // raster work queue (fine tiles)
     unsigned expand_count;       // raster work queue (bands of tile rows still to be enumerated)
+    unsigned pixel_count;        // raster work queue (single pixels of tiny triangles)
     unsigned setup_count;        // big-triangle setups written by k_raster_bin
     unsigned overflow;           // set when a fixed-capacity buffer was too small
+    unsigned mip_ticket;         // k_mip_chain last-CTA detection (self-resetting)
     unsigned long long cone_steps;
 };
 
@@ -117,8 +126,9 @@ struct vct_ctx {
     uint32_t *d_color = nullptr, *d_radiance = nullptr, *d_normal = nullptr, *d_scratch = nullptr;
     size_t level_off[VCT_MAX_LEVELS + 1]{};
     cudaMipmappedArray_t radiance_arr = nullptr, color_arr = nullptr;
-    cudaTextureObject_t radiance_tex = 0, radiance_tex_point = 0, color_tex = 0, color_tex_point = 0;
+    cudaTextureObject_t radiance_tex = 0, radiance_tex_point = 0, radiance_tex_last = 0, color_tex = 0, color_tex_point = 0, color_tex_last = 0;
     cudaSurfaceObject_t radiance_surf[VCT_MAX_LEVELS]{}, color_surf[VCT_MAX_LEVELS]{};
+    uint8_t *d_pub_mask_radiance = nullptr, *d_pub_mask_color = nullptr;   // see k_mip_chain
     // warp
     uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
     // shadow map / visibility / image
@@ -128,6 +138,7 @@ struct vct_ctx {
     uint32_t* d_warp_scratch = nullptr;
     // raster work queue: 8-byte tile items + one setup record per queued (sub-)triangle
     void* d_tile_queue = nullptr; size_t tile_queue_cap = 0; void* d_expand_queue = nullptr; size_t expand_cap = 0;
+    void* d_pixel_queue = nullptr; size_t pixel_cap = 0;
     void* d_setup = nullptr; size_t setup_cap = 0;
     // per-frame constants + counters
     FrameConst* d_fc = nullptr; FrameConst h_fc{};
@@ -187,6 +198,7 @@ int vctk_transfer(vct_ctx*);
 int vctk_inject(vct_ctx*);
 int vctk_fill_holes(vct_ctx*);
 int vctk_mip(vct_ctx*, int which, int mode, int publish);
+int vctk_mip_chains(vct_ctx*, int n, const int* which, const int* publish, int mode);
 int vctk_publish(vct_ctx*, int which);
 int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);

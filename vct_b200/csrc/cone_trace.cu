@@ -13,14 +13,14 @@
 // NEAREST, CLAMP_TO_BORDER(0): lambda <= 0.5 is a magnification -> point fetch of level 0 (GL 4.5 §8.14),
 // otherwise trilinear + mip-linear, lambda clamped to the last level.
 // Thread mapping: a warp shades an 8x4 pixel tile so that the 32 cones marched in lock-step (same cone index,
-// same step) stay spatially coherent in the texture cache; a CTA of 8 warps covers 32x8 pixels.
+// same step) stay spatially coherent in the texture cache; a CTA of 4 warps covers 32x4 pixels.
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;          // 4 warps = 32x4 pixels; ~164 registers/thread -> 3 CTAs (12 warps) per SM
 __device__ const float kPI = 3.1415982f;                 // common.glsl:1 [sic]
 
 struct TraceArgs {
@@ -29,7 +29,7 @@ struct TraceArgs {
     const uint32_t* indices; const int32_t* trimat; const float* verts;
     const float4 *wpos, *wnrm, *wT, *wB;
     const DevTexture* tex; const DevMaterial* mats; const float* shadow;
-    cudaTextureObject_t vol, vol_point; const ushort4* warp;
+    cudaTextureObject_t vol, vol_point, vol_last; const ushort4* warp;
     uint32_t* image; Counters* counters;
 };
 
@@ -38,7 +38,10 @@ __device__ __forceinline__ float ip(const float l[3], float a, float b, float c)
 __device__ __forceinline__ V3 ip3(const float l[3], V3 a, V3 b, V3 c) { return mk3(ip(l, a.x, b.x, c.x), ip(l, a.y, b.y, c.y), ip(l, a.z, b.z, c.z)); }
 
 // ---- 2D material textures: LINEAR_MIPMAP_NEAREST / NEAREST / REPEAT, software-filtered from linear memory
-__device__ __forceinline__ int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
+__device__ __forceinline__ int wrapi(int i, int n) {
+    if ((n & (n - 1)) == 0) return i & (n - 1);                            // power-of-two sizes (every Sponza map): REPEAT is a mask
+    int r = i % n; return r < 0 ? r + n : r;
+}
 __device__ __forceinline__ V4 texel2d(const DevTexture& t, int level, int x, int y) {
     const int w = max(1, t.w >> level), h = max(1, t.h >> level);
     const uint8_t* p = t.level[level] + ((size_t)wrapi(y, h) * w + wrapi(x, w)) * t.ch;
@@ -134,9 +137,12 @@ __device__ __forceinline__ V3 warp_sample(const ushort4* __restrict__ wm, V3 tc)
     return lerp3x(lerp3x(c00, c10, fy), lerp3x(c01, c11, fy), fz);
 }
 
+enum { WARP_NONE = 0, WARP_TEXTURE = 1, WARP_VOXELS = 2 };      // common.glsl:44-60 priority: warpVoxels > warpTexture
+
 // ---- traceCone, phong.frag:135-180
-struct ConeCtx { cudaTextureObject_t vol, vol_point; const ushort4* warp; int D, L; int warp_texture, warp_voxels; V3 eye_tc; };
-__device__ __forceinline__ V4 trace_cone(const ConeCtx& cx, V3 position, V3 normal, V3 direction, int steps, float bias, float cone_angle,
+struct ConeCtx { cudaTextureObject_t vol, vol_point, vol_last; const ushort4* warp; int D, L; int warp_texture, warp_voxels; V3 eye_tc; };
+template <int WM>
+__device__ __noinline__ V4 trace_cone(const ConeCtx& cx, V3 position, V3 normal, V3 direction, int steps, float bias, float cone_angle,
                                          float cone_height, float lod_offset, unsigned& fetches) {
     direction = normalize3(direction);
     V3 color = mk3(0.f, 0.f, 0.f); float alpha = 0.0f;
@@ -149,8 +155,8 @@ __device__ __forceinline__ V4 trace_cone(const ConeCtx& cx, V3 position, V3 norm
         const float lod = log2f(fmaxf(1.0f, 2.0f * cone_radius));
         V3 sp = start + (direction * cone_height) * scale;
         if (!(sp.x >= 0.0f && sp.x <= 1.0f && sp.y >= 0.0f && sp.y <= 1.0f && sp.z >= 0.0f && sp.z <= 1.0f)) break;   // also NaN
-        if (cx.warp_texture) sp = warp_sample(cx.warp, sp);
-        else if (cx.warp_voxels) sp = voxel_warp(sp, cx.eye_tc);
+        if (WM == WARP_TEXTURE) sp = warp_sample(cx.warp, sp);
+        else if (WM == WARP_VOXELS) sp = voxel_warp(sp, cx.eye_tc);
         const float lambda = lod + lod_offset;
         float4 sc;
         if (!(lambda > 0.5f)) sc = tex3DLod<float4>(cx.vol_point, sp.x, sp.y, sp.z, 0.0f);
@@ -162,6 +168,109 @@ __device__ __forceinline__ V4 trace_cone(const ConeCtx& cx, V3 position, V3 norm
         cone_height += cone_radius;
     }
     return mk4(color.x, color.y, color.z, alpha);
+}
+
+// ---- table-driven marching.  The step schedule of a cone (height h_i, lambda_i = lod_i + lodOffset) depends only on
+// the cone settings, not on the pixel (phong.frag:145-177: r = h*tan(theta/2); lod = log2(max(1,2r)); h += r), so the
+// host builds it once per frame (api.cu build_schedule) and every CTA copies it to shared memory.  lambda is
+// non-decreasing along the march, which splits the steps into three runs by sampler state
+// (Application.cpp:1094-1098): [0,n_point) lambda <= 0.5 magnifies -> NEAREST on level 0; [n_point,n_last)
+// trilinear + mip-linear; [n_last,steps) lambda >= L-1 -> the last level only (one trilinear fetch, not two).
+typedef ConeSchedule Schedule;
+__device__ __forceinline__ bool inside_unit(V3 p) { return p.x >= 0.0f && p.x <= 1.0f && p.y >= 0.0f && p.y <= 1.0f && p.z >= 0.0f && p.z <= 1.0f; }   // false for NaN
+// Largest march height (in voxels) up to which start + ds*h certainly passes the reference's per-component test
+// s == clamp(s,0,1): a slab test against the unit cube shrunk by 1e-5.  Steps beyond it take the exact test.
+__device__ __forceinline__ float safe_height(V3 start, V3 ds) {
+    const float lo = 1e-5f, hi = 1.0f - 1e-5f;
+    auto axis = [&](float s, float d) {
+        if (!(s > lo && s < hi)) return -1.0f;                              // also NaN
+        if (d > 0.0f) return __fdividef(hi - s, d);
+        if (d < 0.0f) return __fdividef(lo - s, d);
+        return d == 0.0f ? 3.0e38f : -1.0f;                                 // NaN direction: never safe
+    };
+    return fminf(axis(start.x, ds.x), fminf(axis(start.y, ds.y), axis(start.z, ds.z)));
+}
+enum { SAMPLE_POINT = 0, SAMPLE_MIP = 1, SAMPLE_LAST = 2 };
+template <int KIND, int WM>
+__device__ __forceinline__ float4 fetch_volume(const ConeCtx& cx, V3 sp, float lambda, float max_lod) {
+    if (WM == WARP_TEXTURE) sp = warp_sample(cx.warp, sp);
+    else if (WM == WARP_VOXELS) sp = voxel_warp(sp, cx.eye_tc);
+    if (KIND == SAMPLE_POINT) return tex3DLod<float4>(cx.vol_point, sp.x, sp.y, sp.z, 0.0f);
+    if (KIND == SAMPLE_LAST) return tex3DLod<float4>(cx.vol_last, sp.x, sp.y, sp.z, max_lod);
+    return tex3DLod<float4>(cx.vol, sp.x, sp.y, sp.z, lambda);
+}
+// N cones sharing one schedule, marched in lock step: N independent texture fetches are in flight per thread.
+// Each cone's own accumulation sequence is exactly the reference's (front-to-back, stop at alpha >= 0.95 or when
+// the sample leaves the unit cube).
+template <int N> struct ConeSet { V3 ds[N]; float hsafe[N]; V4 acc[N]; bool alive[N]; };
+template <int N, int KIND, int WM>
+__device__ __forceinline__ void march_run(const ConeCtx& cx, const Schedule& t, int i0, int i1, V3 start, ConeSet<N>& cs, unsigned& fetches) {
+    const float max_lod = (float)(cx.L - 1);
+    for (int i = i0; i < i1; ++i) {
+        const float hs = t.h[i], lambda = t.lambda[i];
+        float4 smp[N]; bool got[N]; bool any = false;
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            got[c] = false;
+            if (!cs.alive[c]) continue;
+            const V3 sp = mk3(fmaf(cs.ds[c].x, hs, start.x), fmaf(cs.ds[c].y, hs, start.y), fmaf(cs.ds[c].z, hs, start.z));
+            if (!(hs <= cs.hsafe[c]) && !inside_unit(sp)) { cs.alive[c] = false; continue; }
+            smp[c] = fetch_volume<KIND, WM>(cx, sp, lambda, max_lod); got[c] = true; any = true;
+        }
+        if (!any) return;
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            if (!got[c]) continue;
+            const float a = 1.0f - cs.acc[c].w;
+            cs.acc[c].x = fmaf(a, smp[c].x, cs.acc[c].x); cs.acc[c].y = fmaf(a, smp[c].y, cs.acc[c].y);
+            cs.acc[c].z = fmaf(a, smp[c].z, cs.acc[c].z); cs.acc[c].w = fmaf(a, smp[c].w, cs.acc[c].w);
+            fetches++;
+            if (!(cs.acc[c].w < 0.95f)) cs.alive[c] = false;
+        }
+    }
+}
+template <int N, int WM>
+__device__ __forceinline__ void trace_cones(const ConeCtx& cx, const Schedule& t, V3 start, ConeSet<N>& cs, unsigned& fetches) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) { cs.acc[c] = mk4(0.f, 0.f, 0.f, 0.f); cs.alive[c] = true; cs.hsafe[c] = safe_height(start, cs.ds[c]); }
+    march_run<N, SAMPLE_POINT, WM>(cx, t, 0, t.n_point, start, cs, fetches);
+    march_run<N, SAMPLE_MIP, WM>(cx, t, t.n_point, t.n_last, start, cs, fetches);
+    march_run<N, SAMPLE_LAST, WM>(cx, t, t.n_last, t.steps, start, cs, fetches);
+}
+// One cone, K steps fetched ahead: the sample positions do not depend on earlier samples, only the decision to go on
+// does, so up to K-1 fetches may be discarded when the cone saturates.
+template <int K, int KIND, int WM>
+__device__ __forceinline__ void march_ahead(const ConeCtx& cx, const Schedule& t, int i0, int i1, V3 start, V3 ds, float hsafe, V4& acc, bool& alive, unsigned& fetches) {
+    const float max_lod = (float)(cx.L - 1);
+    for (int i = i0; i < i1 && alive; i += K) {
+        float4 smp[K]; int nvalid = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (nvalid != k || i + k >= i1) continue;                       // stop issuing after the first miss
+            const float hs = t.h[i + k];
+            const V3 sp = mk3(fmaf(ds.x, hs, start.x), fmaf(ds.y, hs, start.y), fmaf(ds.z, hs, start.z));
+            if (!(hs <= hsafe) && !inside_unit(sp)) continue;
+            smp[k] = fetch_volume<KIND, WM>(cx, sp, t.lambda[i + k], max_lod); nvalid = k + 1;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k >= nvalid || !alive) continue;
+            const float a = 1.0f - acc.w;
+            acc.x = fmaf(a, smp[k].x, acc.x); acc.y = fmaf(a, smp[k].y, acc.y); acc.z = fmaf(a, smp[k].z, acc.z); acc.w = fmaf(a, smp[k].w, acc.w);
+            fetches++;
+            if (!(acc.w < 0.95f)) alive = false;
+        }
+        if (nvalid < K && i + nvalid < i1) alive = false;                   // left the volume
+    }
+}
+template <int K, int WM>
+__device__ __forceinline__ V4 trace_cone_ahead(const ConeCtx& cx, const Schedule& t, V3 start, V3 ds, unsigned& fetches) {
+    V4 acc = mk4(0.f, 0.f, 0.f, 0.f); bool alive = true;
+    const float hsafe = safe_height(start, ds);
+    march_ahead<K, SAMPLE_POINT, WM>(cx, t, 0, t.n_point, start, ds, hsafe, acc, alive, fetches);
+    march_ahead<K, SAMPLE_MIP, WM>(cx, t, t.n_point, t.n_last, start, ds, hsafe, acc, alive, fetches);
+    march_ahead<K, SAMPLE_LAST, WM>(cx, t, t.n_last, t.steps, start, ds, hsafe, acc, alive, fetches);
+    return acc;
 }
 
 __device__ __forceinline__ float pow2f(float x) { return x * x; }
@@ -188,12 +297,21 @@ __device__ __forceinline__ LR cook_torrance(V3 dc, V3 lc, V3 N, V3 V, V3 L, V3 H
     return r;
 }
 
-__global__ void __launch_bounds__(kThreads) k_cone_trace(TraceArgs a) {
+template <int WM>
+__global__ void __launch_bounds__(kThreads, 4) k_cone_trace(TraceArgs a) {
     const FrameConst& fc = *a.fc;
     const vct_frame_params& fp = fc.p;
+    __shared__ Schedule s_diffuse, s_specular;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&fc.sched_diffuse);          // the two tables are adjacent
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_diffuse);
+        static_assert(sizeof(Schedule) % 4 == 0, "schedule copy");
+        for (int i = threadIdx.x; i < (int)(sizeof(Schedule) / 4); i += kThreads) { dst[i] = __ldg(src + i); reinterpret_cast<uint32_t*>(&s_specular)[i] = __ldg(src + sizeof(Schedule) / 4 + i); }
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int px = blockIdx.x * 32 + (w & 3) * 8 + (lane & 7);
-    const int py = a.y_lo + blockIdx.y * 8 + (w >> 2) * 4 + (lane >> 3);
+    const int px = blockIdx.x * 32 + w * 8 + (lane & 7);
+    const int py = a.y_lo + blockIdx.y * 4 + (lane >> 3);
     unsigned fetches = 0;
     if (px < a.W && py < a.y_hi) {
         const size_t o = (size_t)py * a.W + px;
@@ -284,27 +402,35 @@ __global__ void __launch_bounds__(kThreads) k_cone_trace(TraceArgs a) {
             if (!fp.enable_specular) ssum = mk3(0.f, 0.f, 0.f);
             V3 col;
             if (fp.enable_indirect) {
-                ConeCtx cx; cx.vol = a.vol; cx.vol_point = a.vol_point; cx.warp = a.warp; cx.D = fc.D; cx.L = fc.L;
+                ConeCtx cx; cx.vol = a.vol; cx.vol_point = a.vol_point; cx.vol_last = a.vol_last; cx.warp = a.warp; cx.D = fc.D; cx.L = fc.L;
                 cx.warp_texture = fp.warp_texture; cx.warp_voxels = fp.warp_voxels; cx.eye_tc = voxel_linear_position(eye, fp);
                 const V3 vp = voxel_linear_position(Pw, fp);
+                const float scale = 1.0f / (float)fc.D;
                 const float dirs[6][3] = {{0.f, 1.f, 0.f}, {0.f, 0.5f, 0.866025f}, {0.823639f, 0.5f, 0.267617f}, {0.509037f, 0.5f, -0.700629f},
                                           {-0.5909037f, 0.5f, -0.700629f}, {-0.823639f, 0.5f, 0.267617f}};
                 const float wts[6] = {0.25f, 0.15f, 0.15f, 0.15f, 0.15f, 0.15f};
                 V4 ind = mk4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-                for (int i = 0; i < 6; ++i) {
-                    const V3 dir = normalize3(tbn(mk3(dirs[i][0], dirs[i][1], dirs[i][2])));
-                    const V4 c = trace_cone(cx, vp, N, dir, fp.diffuse_cone.steps, fp.diffuse_cone.bias, fp.diffuse_cone.cone_angle, fp.diffuse_cone.cone_initial_height,
-                                            fp.diffuse_cone.lod_offset, fetches);
-                    ind = mk4(ind.x + wts[i] * c.x, ind.y + wts[i] * c.y, ind.z + wts[i] * c.z, ind.w + wts[i] * c.w);
+                {
+                    ConeSet<6> cs;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) cs.ds[i] = normalize3(normalize3(tbn(mk3(dirs[i][0], dirs[i][1], dirs[i][2])))) * scale;   // main() and traceCone() both normalise
+                    const V3 start = vp + (N * fp.diffuse_cone.bias) * scale;
+                    trace_cones<6, WM>(cx, s_diffuse, start, cs, fetches);
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) ind = mk4(ind.x + wts[i] * cs.acc[i].x, ind.y + wts[i] * cs.acc[i].y, ind.z + wts[i] * cs.acc[i].z, ind.w + wts[i] * cs.acc[i].w);
                 }
                 const float occl = 1.0f - clampf(ind.w, 0.0f, 1.0f);
                 if (fp.enable_reflections) {
-                    float ang = fp.specular_cone.cone_angle;
-                    if (fp.specular_cone_angle_from_roughness && mat.roughness_tex >= 0) ang = fetch(mat.roughness_tex).x * kPI * 0.1f;
                     const V3 I = Pw - eye;
                     const V3 R = I - N * (2.0f * dot3(N, I));
-                    const V4 rc = trace_cone(cx, vp, N, R, fp.specular_cone.steps, fp.specular_cone.bias, ang, fp.specular_cone.cone_initial_height, fp.specular_cone.lod_offset, fetches);
+                    V4 rc;
+                    if (fp.specular_cone_angle_from_roughness && mat.roughness_tex >= 0) {          // per-pixel cone angle: per-pixel schedule
+                        const float ang = fetch(mat.roughness_tex).x * kPI * 0.1f;
+                        rc = trace_cone<WM>(cx, vp, N, R, fp.specular_cone.steps, fp.specular_cone.bias, ang, fp.specular_cone.cone_initial_height, fp.specular_cone.lod_offset, fetches);
+                    } else {
+                        const V3 start = vp + (N * fp.specular_cone.bias) * scale;
+                        rc = trace_cone_ahead<4, WM>(cx, s_specular, start, normalize3(R) * scale, fetches);
+                    }
                     ind.x += rc.x * fp.reflect_scale; ind.y += rc.y * fp.reflect_scale; ind.z += rc.z * fp.reflect_scale;
                 }
                 const V3 indc = mk3(ind.x, ind.y, ind.z) * (dc * fp.ambient_scale);
@@ -342,11 +468,15 @@ int vctk_cone_trace(vct_ctx* c) {
     a.vis = c->d_vis; a.indices = c->d_indices; a.trimat = c->d_trimat; a.verts = c->d_vertices;
     a.wpos = c->d_wpos; a.wnrm = c->d_wnrm; a.wT = c->d_wT; a.wB = c->d_wB; a.tex = c->d_tex; a.mats = c->d_mat; a.shadow = c->d_shadow;
     const bool rad = c->h_fc.p.draw_radiance != 0;
-    a.vol = rad ? c->radiance_tex : c->color_tex; a.vol_point = rad ? c->radiance_tex_point : c->color_tex_point; a.warp = reinterpret_cast<const ushort4*>(c->d_warpmap);
+    a.vol = rad ? c->radiance_tex : c->color_tex; a.vol_point = rad ? c->radiance_tex_point : c->color_tex_point;
+    a.vol_last = rad ? c->radiance_tex_last : c->color_tex_last; a.warp = reinterpret_cast<const ushort4*>(c->d_warpmap);
     a.image = c->d_image; a.counters = c->d_counters;
     if (a.y_hi <= a.y_lo) return 0;
-    dim3 grid((c->W + 31) / 32, (a.y_hi - a.y_lo + 7) / 8);
-    k_cone_trace<<<grid, kThreads, 0, c->stream>>>(a);
+    dim3 grid((c->W + 31) / 32, (a.y_hi - a.y_lo + 3) / 4);
+    const vct_frame_params& p = c->h_fc.p;
+    if (p.warp_voxels) k_cone_trace<WARP_VOXELS><<<grid, kThreads, 0, c->stream>>>(a);
+    else if (p.warp_texture) k_cone_trace<WARP_TEXTURE><<<grid, kThreads, 0, c->stream>>>(a);
+    else k_cone_trace<WARP_NONE><<<grid, kThreads, 0, c->stream>>>(a);
     VCT_LAUNCH_CHECK(c, "k_cone_trace");
     return 0;
 }

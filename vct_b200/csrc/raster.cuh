@@ -86,6 +86,7 @@ constexpr int kExpandTiles = 512;
 struct TileQueues {
     uint2* tiles; unsigned tile_cap; unsigned* tile_count;
     uint2* expand; unsigned expand_cap; unsigned* expand_count;
+    uint2* pixels; unsigned pixel_cap; unsigned* pixel_count;      // single pixels of tiny triangles: (slot, x | y << 16)
     unsigned* overflow;
 };
 
@@ -168,6 +169,7 @@ static inline TileQueues vctk_tile_queues(vct_ctx* c) {
     TileQueues q;
     q.tiles = reinterpret_cast<uint2*>(c->d_tile_queue); q.tile_cap = (unsigned)c->tile_queue_cap; q.tile_count = &c->d_counters->tile_queue_count;
     q.expand = reinterpret_cast<uint2*>(c->d_expand_queue); q.expand_cap = (unsigned)c->expand_cap; q.expand_count = &c->d_counters->expand_count;
+    q.pixels = reinterpret_cast<uint2*>(c->d_pixel_queue); q.pixel_cap = (unsigned)c->pixel_cap; q.pixel_count = &c->d_counters->pixel_count;
     q.overflow = &c->d_counters->overflow;
     return q;
 }
@@ -189,7 +191,10 @@ __device__ __forceinline__ V3 interp3(const float l[3], V3 a, V3 b, V3 c) {
 // ---------------------------------------------------------------------------------- 2D material textures
 // min LINEAR_MIPMAP_NEAREST, mag NEAREST, REPEAT (reference src/Graphics/GLHelper.cpp:180-183); rho2 is the
 // squared GL scale factor; level selection by comparisons only (no log2).
-__device__ __forceinline__ int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
+__device__ __forceinline__ int wrapi(int i, int n) {
+    if ((n & (n - 1)) == 0) return i & (n - 1);                            // power-of-two sizes: REPEAT is a mask (same result)
+    int r = i % n; return r < 0 ? r + n : r;
+}
 __device__ __forceinline__ V4 texel2d(const DevTexture& t, int level, int x, int y) {
     const int w = max(1, t.w >> level), h = max(1, t.h >> level);
     const uint8_t* p = t.level[level] + ((size_t)wrapi(y, h) * w + wrapi(x, w)) * t.ch;
@@ -244,17 +249,34 @@ __device__ __forceinline__ float shadow_linear(const float* __restrict__ sm, int
     const float bot = shadow_texel(sm, S, x0, y0 + 1) * (1.0f - fx) + shadow_texel(sm, S, x0 + 1, y0 + 1) * fx;
     return top * (1.0f - fy) + bot * fy;
 }
-// voxelize.frag:160-184 == phong.frag:183-207
+// voxelize.frag:160-184 == phong.frag:183-207.  The five LINEAR taps (offsets (0,0),(1,0),(0,1),(-1,0),(0,-1)) share a
+// 4x4 texel neighbourhood: its 12 distinct texels are fetched once; every tap is then evaluated with exactly the
+// arithmetic of shadow_linear().
 __device__ __forceinline__ float calc_shadow_factor(const float* __restrict__ sm, int S, V4 lsp) {
     const float sx = (lsp.x / lsp.w + 1.0f) * 0.5f, sy = (lsp.y / lsp.w + 1.0f) * 0.5f, sz = (lsp.z / lsp.w + 1.0f) * 0.5f;
     const float frag_depth = sz - 0.01f;
     if (frag_depth > 1.0f) return 0.0f;
+    const float x = sx * (float)S - 0.5f, y = sy * (float)S - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    if (!(fabsf(fx0) < 1e9f) || !(fabsf(fy0) < 1e9f)) return 0.0f;          // every tap reads the border (1.0): frag_depth <= 1 is never greater
+    const int x0 = (int)fx0, y0 = (int)fy0; const float fx = x - fx0, fy = y - fy0;
+    float t[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[j][i] = ((i == 0 || i == 3) && (j == 0 || j == 3)) ? 0.0f : shadow_texel(sm, S, x0 - 1 + i, y0 - 1 + j);
+    auto tap = [&](int ox, int oy) {
+        const int i = 1 + ox, j = 1 + oy;
+        const float top = t[j][i] * (1.0f - fx) + t[j][i + 1] * fx;
+        const float bot = t[j + 1][i] * (1.0f - fx) + t[j + 1][i + 1] * fx;
+        return top * (1.0f - fy) + bot * fy;
+    };
     float f = 0.0f;
-    if (frag_depth > shadow_linear(sm, S, sx, sy, 0, 0)) f += 1.0f;
-    if (frag_depth > shadow_linear(sm, S, sx, sy, 1, 0)) f += 1.0f;
-    if (frag_depth > shadow_linear(sm, S, sx, sy, 0, 1)) f += 1.0f;
-    if (frag_depth > shadow_linear(sm, S, sx, sy, -1, 0)) f += 1.0f;
-    if (frag_depth > shadow_linear(sm, S, sx, sy, 0, -1)) f += 1.0f;
+    if (frag_depth > tap(0, 0)) f += 1.0f;
+    if (frag_depth > tap(1, 0)) f += 1.0f;
+    if (frag_depth > tap(0, 1)) f += 1.0f;
+    if (frag_depth > tap(-1, 0)) f += 1.0f;
+    if (frag_depth > tap(0, -1)) f += 1.0f;
     return f / 5.0f;
 }
 

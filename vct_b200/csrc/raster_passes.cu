@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) k_fill_u32(unsigned* __restrict__ p,
 __global__ void __launch_bounds__(kThreads) k_fill_u64(unsigned long long* __restrict__ p, size_t n, unsigned long long v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
-__global__ void k_reset_queue(Counters* c) { c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; }
+__global__ void k_reset_queue(Counters* c) { c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
 
 template <bool CAMERA>
 int run_raster(vct_ctx* c) {

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads) k_normalize_f16(__half* __restrict__
 // One thread per shadow-map texel, 32x8 tiles so that a warp reads one 128-byte row segment of depth.
 // The bilinear fetch at a texel CORNER averages the 2x2 neighbourhood (x-1..x, y-1..y): staged through a
 // (32+1)x(8+1) shared tile so each depth value is read from HBM once.
-__global__ void __launch_bounds__(256) k_inject(const FrameConst* __restrict__ fcp, const float* __restrict__ shadow,
+__global__ void __launch_bounds__(256) k_inject_generic(const FrameConst* __restrict__ fcp, const float* __restrict__ shadow,
                                                 const uint32_t* __restrict__ color, const uint32_t* __restrict__ normal,
                                                 const uint16_t* __restrict__ warpmap, uint32_t* __restrict__ radiance) {
     const FrameConst& fc = *fcp;
@@ -210,6 +210,68 @@ __global__ void __launch_bounds__(256) k_inject(const FrameConst* __restrict__ f
     const float diff = maxsel(dot3(n, lv), 0.0f);
     c.x = (diff * L0.color[0]) * c.x; c.y = (diff * L0.color[1]) * c.y; c.z = (diff * L0.color[2]) * c.z;
     radiance[o] = pack_unorm(c);
+}
+
+// Fast path for power-of-two shadow maps (every configuration): one thread = 4 consecutive texels of a row.
+// With S = 2^k the texel-corner coordinate x/S is exact, so the LINEAR footprint is exactly texels (x-1..x, y-1..y)
+// with weights 0.5 — the same expressions as shadow_linear() are evaluated, only the addressing is simplified: two
+// 16-byte loads + two scalars feed four texels, and nothing is staged through shared memory.
+__device__ __forceinline__ uint32_t inject_target(const FrameConst& fc, const uint16_t* __restrict__ warpmap, int x, int y, float t00, float t10, float t01, float t11,
+                                                  float inv_s, int& ix, int& iy, int& iz) {
+    const int D = fc.D;
+    const float tu = (float)x * inv_s, tv = (float)y * inv_s;
+    const float fx = 0.5f, fy = 0.5f;
+    const float top = t00 * (1.0f - fx) + t10 * fx, bot = t01 * (1.0f - fx) + t11 * fx;
+    const float d = top * (1.0f - fy) + bot * fy;
+    const float nx = tu * 2.0f - 1.0f, ny = tv * 2.0f - 1.0f, nz = d * 2.0f - 1.0f;
+    const V4 w = mul44(fc.ls_inverse, mk4(nx, ny, nz, 1.0f));
+    V3 vp = get_voxel_position(mk3(w.x, w.y, w.z), fc.p, warpmap);
+    vp = mk3((float)D * vp.x, (float)D * vp.y, (float)D * vp.z);
+    if (!to_voxel_index(vp, D, ix, iy, iz) || iz < fc.z_lo || iz >= fc.z_hi) return 0xFFFFFFFFu;   // z-slab ownership (multi-GPU)
+    return (uint32_t)(((size_t)iz * D + iy) * D + ix);
+}
+__device__ __forceinline__ void inject_store(const FrameConst& fc, const uint16_t* __restrict__ warpmap, const uint32_t* __restrict__ color,
+                                             const uint32_t* __restrict__ normal, uint32_t* __restrict__ radiance, uint32_t o, int ix, int iy, int iz) {
+    const int D = fc.D;
+    const uint32_t cw = __ldg(color + o);
+    if (!fc.p.radiance_lighting) { radiance[o] = cw; return; }   // packUnorm4x8(unpackUnorm4x8(c)) == c for every byte
+    V4 c = unpack_unorm(cw);
+    const V4 n4 = unpack_unorm(__ldg(normal + o));
+    const V3 n = mk3(2.0f * n4.x - 1.0f, 2.0f * n4.y - 1.0f, 2.0f * n4.z - 1.0f);
+    const vct_light& L0 = fc.lights[0];
+    V3 lpv = get_voxel_position(mk3(L0.position[0], L0.position[1], L0.position[2]), fc.p, warpmap);
+    lpv = mk3((float)D * lpv.x, (float)D * lpv.y, (float)D * lpv.z);
+    const V3 lv = normalize3(lpv - mk3((float)ix, (float)iy, (float)iz));
+    const float diff = maxsel(dot3(n, lv), 0.0f);
+    c.x = (diff * L0.color[0]) * c.x; c.y = (diff * L0.color[1]) * c.y; c.z = (diff * L0.color[2]) * c.z;
+    radiance[o] = pack_unorm(c);
+}
+__global__ void __launch_bounds__(256) k_inject(const FrameConst* __restrict__ fcp, const float* __restrict__ shadow,
+                                                const uint32_t* __restrict__ color, const uint32_t* __restrict__ normal,
+                                                const uint16_t* __restrict__ warpmap, uint32_t* __restrict__ radiance) {
+    const FrameConst& fc = *fcp;
+    const int S = fc.S, qx = S >> 2;
+    const float inv_s = 1.0f / (float)S;                                    // exact: S is a power of two
+    const int q = blockIdx.x * 256 + threadIdx.x;                           // grid covers exactly S*S/4 quads (S >= 32)
+    const int x0 = (q % qx) * 4, y = q / qx;
+    const float* row1 = shadow + (size_t)y * S + x0;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(row1));
+    const float bm1 = x0 > 0 ? __ldg(row1 - 1) : 1.0f;                      // CLAMP_TO_BORDER, border 1
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f); float am1 = 1.0f;
+    if (y > 0) { a = __ldg(reinterpret_cast<const float4*>(row1 - S)); if (x0 > 0) am1 = __ldg(row1 - S - 1); }
+    const float ta[5] = {am1, a.x, a.y, a.z, a.w}, tb[5] = {bm1, b.x, b.y, b.z, b.w};
+    uint32_t o[4]; int ix[4], iy[4], iz[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = inject_target(fc, warpmap, x0 + k, y, ta[k], ta[k + 1], tb[k], tb[k + 1], inv_s, ix[k], iy[k], iz[k]);
+    // Neighbouring texels of a row mostly land in the same voxel (4096^2 texels onto ~4e5 voxels) and every writer
+    // stores the same word, so a texel whose left neighbour targets the same voxel leaves the store to it.
+    uint32_t left = __shfl_up_sync(0xffffffffu, o[3], 1);
+    if ((threadIdx.x & 31) == 0) left = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (o[k] != 0xFFFFFFFFu && o[k] != left) inject_store(fc, warpmap, color, normal, radiance, o[k], ix[k], iy[k], iz[k]);
+        left = o[k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------- fill holes
@@ -273,16 +335,24 @@ __global__ void __launch_bounds__(kThreads) k_mip_box2(const uint32_t* __restric
         reinterpret_cast<uint4*>(dst + ((size_t)z * Dd + y) * Dd)[q] = make_uint4(out[0], out[1], out[2], out[3]);
     }
 }
-// Whole BOX2 chain in ONE launch: a CTA owns a B^3 block of level 0 (B = 2^R <= 32), streams it once from HBM,
-// writes its (B/2)^3 block of level 1 and keeps it in shared memory, from which levels 2..R follow without
-// touching HBM again.  Every level is computed from the ROUNDED unorm8 words of the level below, exactly like the
-// reference's one-dispatch-per-level loop (src/Application.cpp:889-902).  With `publish`, the level-0 words that
-// pass through registers and every produced level are also written to the surfaces of the mipmapped array the
-// cone tracer samples, which replaces the separate linear -> array copy.
+// Whole BOX2 chain in ONE launch: a CTA of 128 threads owns a B^3 block of level 0 (B = 2^R, R <= 4), streams it
+// once from HBM (one thread = 8 x 16-byte loads in flight), writes its (B/2)^3 block of level 1 and keeps it in
+// shared memory, from which levels 2..R follow without touching HBM again; the last CTA to finish (ticket counter)
+// reduces the few remaining coarse levels.  Every level is computed from the ROUNDED unorm8 words of the level below,
+// exactly like the reference's one-dispatch-per-level loop (src/Application.cpp:889-902).  With `publish`, the
+// level-0 words that pass through registers and every produced level are also written to the surfaces of the
+// mipmapped array the cone tracer samples, which replaces the separate linear -> array copy.
+constexpr int kMipThreads = 128;
+struct MipChain {
+    const uint32_t* src0; uint32_t* lvl[VCT_MAX_LEVELS];      // lvl[k] = linear level k (k >= 1 written)
+    cudaSurfaceObject_t surf[VCT_MAX_LEVELS];
+    uint8_t* pub_mask;                            // 1 byte per 8 level-0 texels of a row: array holds non-zero data there
+    int publish;
+};
 struct MipChainArgs {
-    const uint32_t* src0; uint32_t* lvl[6];       // lvl[k] = linear level k (k >= 1 written)
-    cudaSurfaceObject_t surf[6];
-    int D, R, z0, publish;
+    MipChain chain[2]; int n_chains;              // radiance and colour pyramids filtered by one launch
+    unsigned* ticket;                             // last-CTA detection for the tail levels
+    int D, R, L, z0, nbz, tail;                   // tail: reduce levels R..L-2 -> R+1..L-1 in the last CTA
 };
 __device__ __forceinline__ uint32_t box2_words(const uint32_t w[8], const float* __restrict__ lut) {
     if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0u) return 0u;
@@ -291,16 +361,19 @@ __device__ __forceinline__ uint32_t box2_words(const uint32_t w[8], const float*
     for (int k = 0; k < 8; ++k) acc_word(acc, w[k], lut);
     return finish_word(acc, 0.125f);
 }
-__global__ void __launch_bounds__(kThreads) k_mip_chain(MipChainArgs a) {
+__global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant__ MipChainArgs args) {
     __shared__ float lut[256];
-    __shared__ uint32_t s1[16 * 16 * 16], s2[8 * 8 * 8], s3[4 * 4 * 4], s4[2 * 2 * 2];
-    lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    __shared__ uint32_t s1[8 * 8 * 8], s2[4 * 4 * 4], s3[2 * 2 * 2];
+    __shared__ unsigned s_last;
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f; lut[threadIdx.x + 128] = (float)(threadIdx.x + 128) / 255.0f;
     __syncthreads();
-    const int B = 1 << a.R, H = B >> 1, D = a.D;
-    const int bx = blockIdx.x * B, by = blockIdx.y * B, bz = a.z0 + blockIdx.z * B;
+    const int which = blockIdx.z / args.nbz;
+    const MipChain& a = args.chain[which];
+    const int B = 1 << args.R, H = B >> 1, D = args.D;
+    const int bx = blockIdx.x * B, by = blockIdx.y * B, bz = args.z0 + (blockIdx.z - which * args.nbz) * B;
     // ---- level 0 -> 1: one thread = 4 consecutive level-1 texels (8 x 16-byte loads, 1 x 16-byte store)
     const int qx = H >> 2, nquads = qx * H * H, D1 = D >> 1;
-    for (int q = threadIdx.x; q < nquads; q += kThreads) {
+    for (int q = threadIdx.x; q < nquads; q += kMipThreads) {
         const int lx = (q % qx) * 4, ly = (q / qx) % H, lz = q / (qx * H);
         const int x0 = bx + 2 * lx, y0 = by + 2 * ly, z0 = bz + 2 * lz;
         const uint4* r00 = reinterpret_cast<const uint4*>(a.src0 + ((size_t)z0 * D + y0) * D + x0);
@@ -311,10 +384,18 @@ __global__ void __launch_bounds__(kThreads) k_mip_chain(MipChainArgs a) {
         v[0] = __ldg(r00); v[1] = __ldg(r00 + 1); v[2] = __ldg(r01); v[3] = __ldg(r01 + 1);
         v[4] = __ldg(r10); v[5] = __ldg(r10 + 1); v[6] = __ldg(r11); v[7] = __ldg(r11 + 1);
         if (a.publish) {
-            surf3Dwrite(v[0], a.surf[0], x0 * 4, y0, z0); surf3Dwrite(v[1], a.surf[0], x0 * 4 + 16, y0, z0);
-            surf3Dwrite(v[2], a.surf[0], x0 * 4, y0, z0 + 1); surf3Dwrite(v[3], a.surf[0], x0 * 4 + 16, y0, z0 + 1);
-            surf3Dwrite(v[4], a.surf[0], x0 * 4, y0 + 1, z0); surf3Dwrite(v[5], a.surf[0], x0 * 4 + 16, y0 + 1, z0);
-            surf3Dwrite(v[6], a.surf[0], x0 * 4, y0 + 1, z0 + 1); surf3Dwrite(v[7], a.surf[0], x0 * 4 + 16, y0 + 1, z0 + 1);
+            // Level 0 goes to the texture array only where it is non-zero now or was non-zero in the array (the
+            // volume is ~97 % empty and surface stores are the slowest part of this kernel): array == linear always.
+            uint8_t* m[4]; uint8_t was[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { m[j] = a.pub_mask + (((size_t)(z0 + (j & 1)) * D + y0 + (j >> 1)) * D + x0) / 8; was[j] = *m[j]; }   // loads in flight with v[]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                                   // rows (y0,z0) (y0,z1) (y1,z0) (y1,z1)
+                const int yy = y0 + (j >> 1), zz = z0 + (j & 1);
+                const uint4 p = v[2 * j], r = v[2 * j + 1];
+                const bool now = (p.x | p.y | p.z | p.w | r.x | r.y | r.z | r.w) != 0u;
+                if (now || was[j]) { surf3Dwrite(p, a.surf[0], x0 * 4, yy, zz); surf3Dwrite(r, a.surf[0], x0 * 4 + 16, yy, zz); *m[j] = now ? 1 : 0; }
+            }
         }
         const uint32_t A[8] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w};      // (y0,z0)
         const uint32_t Bq[8] = {v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};    // (y0,z1)
@@ -334,14 +415,14 @@ __global__ void __launch_bounds__(kThreads) k_mip_chain(MipChainArgs a) {
         *reinterpret_cast<uint4*>(s1 + (lz * H + ly) * H + lx) = o;
     }
     // ---- levels 1 -> 2 -> ... -> R from shared memory
-    for (int k = 1; k < a.R; ++k) {
+    for (int k = 1; k < args.R; ++k) {
         __syncthreads();
         const int Hs = B >> k, Hd = Hs >> 1, Dd = D >> (k + 1);
-        const uint32_t* src = k == 1 ? s1 : k == 2 ? s2 : k == 3 ? s3 : s4;
-        uint32_t* dsts = k == 1 ? s2 : k == 2 ? s3 : k == 3 ? s4 : nullptr;
-        uint32_t* gl = k == 1 ? a.lvl[2] : k == 2 ? a.lvl[3] : k == 3 ? a.lvl[4] : a.lvl[5];
-        const cudaSurfaceObject_t gs = k == 1 ? a.surf[2] : k == 2 ? a.surf[3] : k == 3 ? a.surf[4] : a.surf[5];
-        for (int i = threadIdx.x; i < Hd * Hd * Hd; i += kThreads) {
+        const uint32_t* src = k == 1 ? s1 : k == 2 ? s2 : s3;
+        uint32_t* dsts = k == 1 ? s2 : k == 2 ? s3 : nullptr;
+        uint32_t* gl = a.lvl[k + 1];
+        const cudaSurfaceObject_t gs = a.surf[k + 1];
+        for (int i = threadIdx.x; i < Hd * Hd * Hd; i += kMipThreads) {
             const int lx = i % Hd, ly = (i / Hd) % Hd, lz = i / (Hd * Hd);
             uint32_t w[8];
 #pragma unroll
@@ -351,6 +432,37 @@ __global__ void __launch_bounds__(kThreads) k_mip_chain(MipChainArgs a) {
             gl[((size_t)gz * Dd + gy) * Dd + gx] = o;
             if (a.publish) surf3Dwrite(o, gs, gx * 4, gy, gz);
             if (dsts) dsts[(lz * Hd + ly) * Hd + lx] = o;
+        }
+    }
+    // ---- tail: the last CTA reduces the remaining coarse levels (a few thousand texels) straight from L2
+    if (!args.tail) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned t = atomicAdd(args.ticket, 1u);
+        s_last = t == total - 1u;
+        if (s_last) *args.ticket = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int ch = 0; ch < args.n_chains; ++ch) {
+        const MipChain& c = args.chain[ch];
+        for (int l = args.R; l + 1 < args.L; ++l) {
+            const int Ds = D >> l, Dd = Ds >> 1;
+            const uint32_t* src = c.lvl[l]; uint32_t* dst = c.lvl[l + 1];
+            for (int i = threadIdx.x; i < Dd * Dd * Dd; i += kMipThreads) {
+                const int x = i % Dd, y = (i / Dd) % Dd, z = i / (Dd * Dd);
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = __ldcg(src + ((size_t)(2 * z + (j & 1)) * Ds + 2 * y + ((j >> 1) & 1)) * Ds + 2 * x + (j >> 2));
+                const uint32_t o = box2_words(w, lut);
+                dst[i] = o;
+                if (c.publish) surf3Dwrite(o, c.surf[l + 1], x * 4, y, z);
+            }
+            __threadfence();
+            __syncthreads();
         }
     }
 }
@@ -428,9 +540,14 @@ int vctk_transfer(vct_ctx* c) {
     return 0;
 }
 int vctk_inject(vct_ctx* c) {
+    if ((c->S & (c->S - 1)) == 0 && c->S >= 32) {
+        k_inject<<<(unsigned)((size_t)c->S * c->S / 4 / 256), 256, 0, c->stream>>>(c->d_fc, c->d_shadow, c->d_color, c->d_normal, c->d_warpmap, c->d_radiance);
+        VCT_LAUNCH_CHECK(c, "k_inject");
+        return 0;
+    }
     dim3 grid((c->S + 31) / 32, (c->S + 7) / 8);
-    k_inject<<<grid, 256, 0, c->stream>>>(c->d_fc, c->d_shadow, c->d_color, c->d_normal, c->d_warpmap, c->d_radiance);
-    VCT_LAUNCH_CHECK(c, "k_inject");
+    k_inject_generic<<<grid, 256, 0, c->stream>>>(c->d_fc, c->d_shadow, c->d_color, c->d_normal, c->d_warpmap, c->d_radiance);
+    VCT_LAUNCH_CHECK(c, "k_inject_generic");
     return 0;
 }
 int vctk_fill_holes(vct_ctx* c) {
@@ -444,6 +561,11 @@ int vctk_fill_holes(vct_ctx* c) {
 }
 static int publish_levels(vct_ctx* c, int which, int l_begin, int l_end) {
     uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
+    uint8_t* mask = which == VCT_VOL_COLOR ? c->d_pub_mask_color : c->d_pub_mask_radiance;
+    if (l_begin == 0 && mask) {                     // the array now mirrors the linear level 0: anything may be non-zero
+        VCT_CHECK(c, cudaMemsetAsync(mask, 0xFF, (size_t)c->D * c->D * c->D / 8, c->stream));
+        vct_prof_mark(c, "memset");
+    }
     cudaSurfaceObject_t* surf = which == VCT_VOL_COLOR ? c->color_surf : c->radiance_surf;
     for (int l = l_begin; l < l_end; ++l) {
         const int d = level_dim(c->D, l);
@@ -453,51 +575,67 @@ static int publish_levels(vct_ctx* c, int which, int l_begin, int l_end) {
     }
     return 0;
 }
-// levels 1..L-1 (the reference's last loop iteration targets a non-existent level: Application.cpp:889-902).
-// publish != 0 (single GPU): the pyramid also lands in the mipmapped array the cone tracer samples.
-int vctk_mip(vct_ctx* c, int which, int mode, int publish) {
-    uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
-    cudaSurfaceObject_t* surf = which == VCT_VOL_COLOR ? c->color_surf : c->radiance_surf;
-    if (publish && !surf[0]) publish = 0;
+// levels 1..L-1 (the reference's last loop iteration targets a non-existent level: Application.cpp:889-902) of up to
+// two pyramids.  publish[i] != 0 (single GPU): that pyramid also lands in the mipmapped array the cone tracer samples.
+int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, int mode) {
+    int publish[2] = {0, 0};
+    uint32_t* base[2]; cudaSurfaceObject_t* surf[2];
+    for (int i = 0; i < n; ++i) {
+        base[i] = which[i] == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
+        surf[i] = which[i] == VCT_VOL_COLOR ? c->color_surf : c->radiance_surf;
+        publish[i] = publish_in[i] && surf[i][0];
+    }
     int first = 0;                                  // first source level still to be filtered
     int published_upto = 0;                         // levels [0, published_upto) are already in the array
     // fused chain: R reductions per CTA, block edge 2^R; needs whole blocks inside this rank's slab
-    int R = c->L - 1 < 5 ? c->L - 1 : 5;
+    int R = c->L - 1 < 4 ? c->L - 1 : 4;
     while (R >= 3 && ((c->z_hi - c->z_lo) % (1 << R) || c->z_lo % (1 << R) || c->D % (1 << R))) R--;
     if (mode == 0 && R >= 3) {
         MipChainArgs a{};
-        a.src0 = base + c->level_off[0];
-        for (int k = 1; k <= R; ++k) a.lvl[k] = base + c->level_off[k];
-        for (int k = 0; k <= R; ++k) a.surf[k] = surf[k];
-        a.D = c->D; a.R = R; a.z0 = c->z_lo; a.publish = publish;
-        const int B = 1 << R;
-        dim3 grid(c->D / B, c->D / B, (c->z_hi - c->z_lo) / B);
-        k_mip_chain<<<grid, kThreads, 0, c->stream>>>(a);
-        VCT_LAUNCH_CHECK(c, "k_mip_chain");
-        first = R;
-        if (publish) published_upto = R + 1;
-    }
-    for (int l = first; l + 1 < c->L; ++l) {
-        const int Ds = level_dim(c->D, l), Dd = Ds >> 1;
-        if (Dd < 1) break;
-        // z-slab of the destination level owned by this rank
-        int zd_lo = c->z_lo >> (l + 1), zd_hi = c->z_hi >> (l + 1);
-        if (c->cfg.world_size <= 1) { zd_lo = 0; zd_hi = Dd; }
-        else if (zd_hi <= zd_lo) { c->error = "vct_mip: a mip level is thinner than one z-slab per rank (levels > log2(dim/world_size)+1 need a coarse-level exchange)"; return 1; }
-        const uint32_t* src = base + c->level_off[l]; uint32_t* dst = base + c->level_off[l + 1];
-        if (mode == 0 && Dd % 4 == 0) {
-            const size_t items = (size_t)(Dd / 4) * Dd * (zd_hi - zd_lo);
-            k_mip_box2<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, zd_lo, zd_hi);
-            VCT_LAUNCH_CHECK(c, "k_mip_box2");
-        } else {
-            const size_t items = (size_t)Dd * Dd * (zd_hi - zd_lo);
-            k_mip_generic<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, mode, zd_lo, zd_hi);
-            VCT_LAUNCH_CHECK(c, "k_mip_generic");
+        for (int i = 0; i < n; ++i) {
+            MipChain& ch = a.chain[i];
+            ch.src0 = base[i] + c->level_off[0];
+            for (int k = 1; k < c->L; ++k) ch.lvl[k] = base[i] + c->level_off[k];
+            for (int k = 0; k < c->L; ++k) ch.surf[k] = surf[i][k];
+            ch.publish = publish[i];
+            ch.pub_mask = which[i] == VCT_VOL_COLOR ? c->d_pub_mask_color : c->d_pub_mask_radiance;
+            if (publish[i] && !ch.pub_mask) { c->error = "vct_mip: publish mask missing"; return 1; }
         }
+        a.n_chains = n; a.D = c->D; a.R = R; a.L = c->L; a.z0 = c->z_lo;
+        a.tail = c->cfg.world_size <= 1 && c->L - 1 > R;        // slabs keep one launch per remaining level (below)
+        a.ticket = &c->d_counters->mip_ticket;
+        const int B = 1 << R;
+        a.nbz = (c->z_hi - c->z_lo) / B;
+        dim3 grid(c->D / B, c->D / B, a.nbz * n);
+        k_mip_chain<<<grid, kMipThreads, 0, c->stream>>>(a);
+        VCT_LAUNCH_CHECK(c, "k_mip_chain");
+        first = a.tail ? c->L - 1 : R;
+        published_upto = first + 1;
     }
-    if (publish && published_upto < c->L) return publish_levels(c, which, published_upto, c->L);
+    for (int i = 0; i < n; ++i) {
+        for (int l = first; l + 1 < c->L; ++l) {
+            const int Ds = level_dim(c->D, l), Dd = Ds >> 1;
+            if (Dd < 1) break;
+            // z-slab of the destination level owned by this rank
+            int zd_lo = c->z_lo >> (l + 1), zd_hi = c->z_hi >> (l + 1);
+            if (c->cfg.world_size <= 1) { zd_lo = 0; zd_hi = Dd; }
+            else if (zd_hi <= zd_lo) { c->error = "vct_mip: a mip level is thinner than one z-slab per rank (levels > log2(dim/world_size)+1 need a coarse-level exchange)"; return 1; }
+            const uint32_t* src = base[i] + c->level_off[l]; uint32_t* dst = base[i] + c->level_off[l + 1];
+            if (mode == 0 && Dd % 4 == 0) {
+                const size_t items = (size_t)(Dd / 4) * Dd * (zd_hi - zd_lo);
+                k_mip_box2<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, zd_lo, zd_hi);
+                VCT_LAUNCH_CHECK(c, "k_mip_box2");
+            } else {
+                const size_t items = (size_t)Dd * Dd * (zd_hi - zd_lo);
+                k_mip_generic<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, mode, zd_lo, zd_hi);
+                VCT_LAUNCH_CHECK(c, "k_mip_generic");
+            }
+        }
+        if (publish[i] && published_upto < c->L && publish_levels(c, which[i], published_upto, c->L)) return 1;
+    }
     return 0;
 }
+int vctk_mip(vct_ctx* c, int which, int mode, int publish) { return vctk_mip_chains(c, 1, &which, &publish, mode); }
 int vctk_publish(vct_ctx* c, int which) { return publish_levels(c, which, 0, c->L); }
 int vctk_set_voxel_opacity(vct_ctx* c, float opacity) {
     const size_t n = (size_t)c->D * c->D * c->D;

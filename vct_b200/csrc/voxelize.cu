@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(kThreads) k_voxel_bin(VoxArgs a) {
         const bool valid = t < a.n_tris && make_setup(a, fc, t, S);
         const int bw = valid ? S.s.x1 - S.s.x0 + 1 : 0, bh = valid ? S.s.y1 - S.s.y0 + 1 : 0;
         const bool tiny = valid && bw * bh <= kInlineArea;
-        // ---- tiny bounding boxes: coverage here, then the warp reserves fragment slots together
+        // ---- tiny bounding boxes: coverage here; every fragment becomes one item of the pixel queue, so that the
+        //      (divergent, sparse) hits of many triangles are shaded by full warps in k_voxel_pixels
         unsigned hits = 0;                                                   // bit i: pixel i of the (<= 4 pixel) box is a fragment
         if (tiny) {
             for (int i = 0; i < bw * bh; ++i) {
@@ -249,38 +250,34 @@ __global__ void __launch_bounds__(kThreads) k_voxel_bin(VoxArgs a) {
                 if (frag_test(fc, S, S.s.x0 + i % bw, S.s.y0 + i / bw, D, a.warpmap, occupancy, l, oob, ix, iy, iz)) { counted++; if (!oob) hits |= 1u << i; }
             }
         }
-        const int nh = __popc(hits);
-        uint32_t slot = 0;
-        if (MODE == MODE_SORTED) {                                           // warp-aggregated reservation
+        // ---- publish the setup of every triangle that still has work
+        const bool queued = valid && !tiny;
+        const bool need_slot = queued || hits != 0u;
+        const uint32_t sslot = reserve_slots(need_slot, &a.counters->setup_count);
+        bool stored = false;
+        if (need_slot) {
+            if (sslot < a.setup_cap) { if (MODE != MODE_OCC) make_shading_setup(a, S); a.setups[sslot] = S; stored = true; }
+            else a.counters->overflow = 1u;
+        }
+        {   // pixel items: warp prefix sum -> one atomic per warp
+            const int nh = stored ? __popc(hits) : 0;
             int inc = nh;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
             const int total = __shfl_sync(0xffffffffu, inc, 31);
-            uint32_t base = 0;
-            if (lane == 31 && total) base = atomicAdd(&a.counters->n_frag_slots, (unsigned)total);
-            slot = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(inc - nh);
-        }
-        if (hits) {
-            ShadeIn I;
-            if (MODE != MODE_OCC) { make_shading_setup(a, S); load_shade_in(a, t, I); }
-            for (int i = 0; i < bw * bh; ++i) {
-                if (!(hits >> i & 1u)) continue;
-                const int px = S.s.x0 + i % bw, py = S.s.y0 + i / bw;
-                float l[3]; bool oob; int ix, iy, iz;
-                frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
-                if (MODE == MODE_OCC) { atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); continue; }
-                const Shaded sh = shade_fragment(fc, S, I, l, a.tex, a.mats, a.shadow);
-                store_fragment<MODE>(a, S, sh, D, px, py, ix, iy, iz, slot++);
+            if (total) {
+                uint32_t base = 0;
+                if (lane == 31) base = atomicAdd(a.q.pixel_count, (unsigned)total);
+                uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(inc - nh);
+                for (int i = 0; i < bw * bh && nh; ++i) {
+                    if (!(hits >> i & 1u)) continue;
+                    if (pos < a.q.pixel_cap) a.q.pixels[pos] = make_uint2(sslot, (unsigned)(S.s.x0 + i % bw) | (unsigned)(S.s.y0 + i / bw) << 16); else a.counters->overflow = 1u;
+                    ++pos;
+                }
             }
         }
-        // ---- everything else: publish the setup, cut the bounding box into 8x4 tiles
-        const bool queued = valid && !tiny;
-        const uint32_t sslot = reserve_slots(queued, &a.counters->setup_count);
-        bool stored = false;
-        if (queued) {
-            if (sslot < a.setup_cap) { if (MODE != MODE_OCC) make_shading_setup(a, S); a.setups[sslot] = S; stored = true; }
-            else a.counters->overflow = 1u;
-        }
+        // ---- everything else is cut into 8x4 tiles
+        stored = stored && queued;
         enqueue_tiles(stored, S.s, sslot, a.q);
     }
     if (MODE != MODE_OCC) {
@@ -325,6 +322,43 @@ __global__ void __launch_bounds__(kThreads, 1) k_voxel_tiles(VoxArgs a) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
         if (lane == 0 && counted) atomicAdd(&a.counters->total_fragments, counted);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- pixels
+// One lane per queued pixel of a tiny triangle: every lane works on a different triangle (gathered loads), but the
+// control flow is uniform, so the shading runs at full warp efficiency.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) k_voxel_pixels(VoxArgs a) {
+    const FrameConst& fc = *a.fc;
+    const int D = a.D, lane = threadIdx.x & 31;
+    const bool occupancy = MODE == MODE_OCC;
+    const unsigned n_items = min(*a.q.pixel_count, a.q.pixel_cap);
+    const unsigned stride = gridDim.x * kThreads;
+    for (unsigned base = blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n_items; base += stride) {
+        const unsigned item = base + lane;
+        bool hit = false; float l[3]; int ix = 0, iy = 0, iz = 0, px = 0, py = 0;
+        VoxSetup S;
+        if (item < n_items) {
+            const uint2 it = __ldg(a.q.pixels + item);
+            S = a.setups[it.x];
+            px = (int)(it.y & 0xFFFFu); py = (int)(it.y >> 16);
+            bool oob = false;
+            hit = frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz) && !oob;      // true by construction
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (!m) continue;
+        if (MODE == MODE_OCC) { if (hit) atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); continue; }
+        uint32_t slot0 = 0;
+        if (MODE == MODE_SORTED) {
+            if (lane == 0) slot0 = atomicAdd(&a.counters->n_frag_slots, (unsigned)__popc(m));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        }
+        if (hit) {
+            ShadeIn I; load_shade_in(a, S.tri, I);
+            const Shaded sh = shade_fragment(fc, S, I, l, a.tex, a.mats, a.shadow);
+            store_fragment<MODE>(a, S, sh, D, px, py, ix, iy, iz, slot0 + __popc(m & ((1u << lane) - 1u)));
+        }
     }
 }
 
@@ -388,14 +422,15 @@ __global__ void __launch_bounds__(kThreads) k_voxel_resolve_b(const Frag* __rest
 __global__ void __launch_bounds__(kThreads) k_voxel_expand(const VoxSetup* __restrict__ setups, TileQueues q) {
     expand_items(reinterpret_cast<const unsigned char*>(setups), sizeof(VoxSetup), q);
 }
-__global__ void k_voxel_reset(Counters* c) { c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; }
+__global__ void k_voxel_reset(Counters* c) { c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
 
 template <int MODE>
-int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* tiles_name) {
+int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* tiles_name, const char* pixels_name) {
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_voxel_bin<MODE><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, bin_name);
     k_voxel_expand<<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a.setups, a.q); VCT_LAUNCH_CHECK(c, "k_voxel_expand");
     k_voxel_tiles<MODE><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, tiles_name);
+    k_voxel_pixels<MODE><<<VCT_SM_COUNT * 2, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, pixels_name);
     return 0;
 }
 
@@ -444,12 +479,12 @@ int vctk_voxelize(vct_ctx* c, bool occupancy) {
     if (occupancy) {
         VCT_CHECK(c, cudaMemsetAsync(c->d_occ, 0, sizeof(uint32_t) * VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM, c->stream));
         vct_prof_mark(c, "memset");
-        return run_mode<MODE_OCC>(c, a, "k_voxel_bin_occ", "k_voxel_tiles_occ");
+        return run_mode<MODE_OCC>(c, a, "k_voxel_bin_occ", "k_voxel_tiles_occ", "k_voxel_pixels_occ");
     }
-    if (p.voxelize_atomic_max) return run_mode<MODE_MAX>(c, a, "k_voxel_bin_max", "k_voxel_tiles_max");
-    if (!p.deterministic) return run_mode<MODE_CAS>(c, a, "k_voxel_bin_cas", "k_voxel_tiles_cas");
+    if (p.voxelize_atomic_max) return run_mode<MODE_MAX>(c, a, "k_voxel_bin_max", "k_voxel_tiles_max", "k_voxel_pixels_max");
+    if (!p.deterministic) return run_mode<MODE_CAS>(c, a, "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_pixels_cas");
     // deterministic running average: per-voxel lists, then ordered sequential replay
-    if (run_mode<MODE_SORTED>(c, a, "k_voxel_bin", "k_voxel_tiles")) return 1;
+    if (run_mode<MODE_SORTED>(c, a, "k_voxel_bin", "k_voxel_tiles", "k_voxel_pixels")) return 1;
     k_voxel_resolve_a<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, c->d_color); VCT_LAUNCH_CHECK(c, "k_voxel_resolve_a");
     k_voxel_resolve_b<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, c->d_color, c->d_normal); VCT_LAUNCH_CHECK(c, "k_voxel_resolve_b");
     return 0;
