@@ -1,4 +1,5 @@
-// vct_oracle.cpp — CPU ORACLE (test infrastructure only; see vct_oracle.h header comment).  PARITY UNPINNED.
+// vct_oracle.cpp — CPU ORACLE (test infrastructure only).  Pinned bit-for-bit against the reference's own host C++ for the
+// warp tables/example (oracle/_ref, see vct_oracle.h); PARITY UNPINNED for the passes that are GLSL in the reference.
 //
 // A restatement of the reference's GLSL passes in plain C++ with OpenGL's implementation-defined behaviour
 // fixed to one explicit definition (DESIGN.md "Canonical GL semantics").  Compile with -ffp-contract=off:
@@ -765,13 +766,25 @@ extern "C" void orc_warp_weight_table(int dim, float high, float low, float* lo,
         lo[occ] = l; hi[occ] = h;
     }
 }
+// inclusive per-axis prefix counts of occupied cells, Application.cpp:311-343
+static void warp_partials(const unsigned* occ, int* px, int* py, int* pz) {
+    const int n = VCT_WARP_DIM;
+    auto at = [&](int x, int y, int z) { return ((size_t)z * n + y) * n + x; };
+    for (int z = 0; z < n; ++z) for (int y = 0; y < n; ++y) { int s = 0; for (int x = 0; x < n; ++x) { s += occ[at(x, y, z)] > 0 ? 1 : 0; px[at(x, y, z)] = s; } }
+    for (int z = 0; z < n; ++z) for (int x = 0; x < n; ++x) { int s = 0; for (int y = 0; y < n; ++y) { s += occ[at(x, y, z)] > 0 ? 1 : 0; py[at(x, y, z)] = s; } }
+    for (int y = 0; y < n; ++y) for (int x = 0; x < n; ++x) { int s = 0; for (int z = 0; z < n; ++z) { s += occ[at(x, y, z)] > 0 ? 1 : 0; pz[at(x, y, z)] = s; } }
+}
+extern "C" void orc_warp_partials(const unsigned* occ, int* xyz /* 32^3 x 3, interleaved like glm::ivec3 */) {
+    const int n = VCT_WARP_DIM, N = n * n * n;
+    std::vector<int> px(N), py(N), pz(N);
+    warp_partials(occ, px.data(), py.data(), pz.data());
+    for (int i = 0; i < N; ++i) { xyz[3 * i] = px[i]; xyz[3 * i + 1] = py[i]; xyz[3 * i + 2] = pz[i]; }
+}
 extern "C" void orc_warpmap(const unsigned* occ, const vct_frame_params* fp, unsigned short* warpmap, unsigned short* wlo16, unsigned short* whi16) {
     const int n = VCT_WARP_DIM;
     auto at = [&](int x, int y, int z) { return ((size_t)z * n + y) * n + x; };
     std::vector<int> px(n * n * n), py(n * n * n), pz(n * n * n);
-    for (int z = 0; z < n; ++z) for (int y = 0; y < n; ++y) { int s = 0; for (int x = 0; x < n; ++x) { s += occ[at(x, y, z)] > 0 ? 1 : 0; px[at(x, y, z)] = s; } }
-    for (int z = 0; z < n; ++z) for (int x = 0; x < n; ++x) { int s = 0; for (int y = 0; y < n; ++y) { s += occ[at(x, y, z)] > 0 ? 1 : 0; py[at(x, y, z)] = s; } }
-    for (int y = 0; y < n; ++y) for (int x = 0; x < n; ++x) { int s = 0; for (int z = 0; z < n; ++z) { s += occ[at(x, y, z)] > 0 ? 1 : 0; pz[at(x, y, z)] = s; } }
+    warp_partials(occ, px.data(), py.data(), pz.data());
     float wl[VCT_WARP_DIM + 1], wh[VCT_WARP_DIM + 1];
     orc_warp_weight_table(n, fp->warp_texture_high_resolution, fp->warp_texture_low_resolution, wl, wh);
     std::memset(warpmap, 0, sizeof(unsigned short) * 4 * n * n * n);    // unwritten texels: defined as 0 (quirk a9)

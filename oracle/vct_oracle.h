@@ -3,11 +3,18 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * library; the product (vct_b200/) never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference (sfreed141/vct @ c5c763d) has no tests, no golden vectors and cannot run in the
- * build container or on the GPU box (no GL stack), so this oracle is a line-by-line restatement of the GLSL
- * with OpenGL's semantics made explicit (DESIGN.md §"Canonical GL semantics").  It is pinned only by the
- * known-answer values derived by hand from the reference's `#if 0` warp rig (src/main.cpp:20-127) and shader
- * arithmetic, checked in tests/test_oracle_kat.py.
+ * PINNING.  The reference (sfreed141/vct @ c5c763d) has no tests and no golden vectors, and its GLSL cannot run in
+ * the build container or on the GPU box (no OpenGL/EGL/Mesa, no GLM/GLFW).  What CAN run is the host C++ the path
+ * contains, and the oracle is pinned against it bit for bit:
+ *   - src/main.cpp:21-128 (the `#if 0` CPU warp example: partial sums, weights, calculateWarpPosition) and
+ *   - src/Application.cpp:311-370 (per-frame warp-map tables: per-axis prefix counts + low/high weight table)
+ *   are compiled FROM WHERE THEY LIE by oracle/Makefile into oracle/_ref/{warp_rig,warpmap_cpu}; their outputs are
+ *   committed as tests/golden/warp_rig_ref.json and warpmap_cpu_ref.npz (generators next to them) and checked by
+ *   tests/test_oracle_kat.py against orc_warp_rig / orc_warp_partials / orc_warp_weight_table.
+ * PARITY UNPINNED for everything that is GLSL in the reference (voxelise, transfer, inject, mip, cone trace, the
+ * two generateWarpmap fragment shaders): those functions are a line-by-line restatement with OpenGL's semantics
+ * made explicit (DESIGN.md "Canonical GL semantics"), pinned only by known-answer values derived from the shader
+ * arithmetic (tests/golden/kat.json, independent numpy restatement in tests/golden/make_kat.py).
  *
  * POD parameter structs are shared with the product's public header (the boundary spec); no code is.
  */
@@ -80,6 +87,7 @@ void orc_warp_weight_table(int dim, float high, float low, float* low_out, float
 void orc_warp_rig(int n, const float* cells, float fixed_low, float high, float low, const float* tc, int npts,
                   float* out, int* part_x, int* part_y, float* wl, float* wh);                 /* src/main.cpp:20-127 */
 float orc_cone_trace_const(int D, int L, unsigned voxel_word, const vct_cone_settings* cs, int* steps_out);
+void orc_warp_partials(const unsigned* occ, int* xyz);                                          /* Application.cpp:311-343 */
 int orc_num_threads(void);
 
 #ifdef __cplusplus

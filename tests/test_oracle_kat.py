@@ -110,6 +110,68 @@ def test_warp_rig_known_answers(L):
         assert o == pytest.approx(w, abs=2e-6), t
 
 
+def _check_rig_against(L, ref):
+    n = ref["dim"]
+    cells = np.array(ref["cells"], np.float32).reshape(n, n)
+    w = np.array(ref["warp"], np.float32)
+    out, px, py, wl, wh = run_rig(L, cells, np.ascontiguousarray(w[:, :2]))
+    part = np.array(ref["partials"], np.int32).reshape(n, n, 2)
+    assert np.array_equal(px, part[:, :, 0]) and np.array_equal(py, part[:, :, 1])
+    wt = np.array(ref["weights"], np.float32)
+    assert np.array_equal(wl, wt[:, 0]) and np.array_equal(wh, wt[:, 1])
+    assert np.array_equal(out.view(np.uint32), np.ascontiguousarray(w[:, 2:]).view(np.uint32)), \
+        f"max |delta| {np.abs(out - w[:, 2:]).max()} vs the reference's own warp code"
+
+
+def test_warp_rig_matches_reference_run_fixture(L):
+    """tests/golden/warp_rig_ref.json holds outputs of the reference's OWN C++ (src/main.cpp:21-128 compiled in place,
+    see tests/golden/make_ref_rig.py): partial sums, weights and 576 warped texcoords must match BIT FOR BIT."""
+    _check_rig_against(L, json.load(open(os.path.join(os.path.dirname(__file__), "golden", "warp_rig_ref.json"))))
+
+
+def test_warp_rig_matches_reference_binary(L):
+    """Same check against a fresh run of oracle/_ref/warp_rig on a denser grid (where the binary was built)."""
+    rig = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "warp_rig")
+    if not os.path.isfile(rig):
+        pytest.skip("oracle/_ref/warp_rig not built (needs /root/reference at build time)")
+    from tests.golden import make_ref_rig
+    _check_rig_against(L, make_ref_rig.run(61))
+
+
+def _check_warpmap_tables(L, occ, part_ref, hl, weights_ref):
+    n = P.WARP_DIM if hasattr(P, "WARP_DIM") else 32
+    L.orc_warp_partials.argtypes = [C.c_void_p, C.c_void_p]
+    for o, pr in zip(occ, part_ref):
+        got = np.zeros((n ** 3, 3), np.int32)
+        L.orc_warp_partials(ol.ptr(np.ascontiguousarray(o, np.uint32)), ol.ptr(got))
+        assert np.array_equal(got, pr.astype(np.int32))
+    for (h, l), wr in zip(hl, weights_ref):
+        lo = np.zeros(n + 1, np.float32); hi = np.zeros(n + 1, np.float32)
+        L.orc_warp_weight_table(n, h, l, ol.ptr(lo), ol.ptr(hi))
+        assert np.array_equal(lo.view(np.uint32), wr[0].view(np.uint32)) and np.array_equal(hi.view(np.uint32), wr[1].view(np.uint32))
+
+
+def test_warpmap_cpu_tables_match_reference_run_fixture(L):
+    """tests/golden/warpmap_cpu_ref.npz holds outputs of the reference's OWN C++ (src/Application.cpp:311-370 compiled
+    in place): per-axis partial sums of five 32^3 occupancy grids and two weight tables, matched bit for bit."""
+    from tests.golden import make_ref_warpmap as M
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "warpmap_cpu_ref.npz"))
+    occ, hl = M.cases()
+    for i, o in enumerate(occ):
+        assert np.array_equal(np.packbits(o > 0), z[f"occ{i}"]), "fixture inputs drifted from make_ref_warpmap.cases()"
+    _check_warpmap_tables(L, occ, [z[f"part{i}"] for i in range(len(occ))], hl, [z[f"weights{j}"] for j in range(len(hl))])
+
+
+def test_warpmap_cpu_tables_match_reference_binary(L):
+    if not os.path.isfile(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "warpmap_cpu")):
+        pytest.skip("oracle/_ref/warpmap_cpu not built (needs /root/reference at build time)")
+    from tests.golden import make_ref_warpmap as M
+    rng = np.random.default_rng(77)
+    occ = [(rng.random(32 ** 3) < d).astype(np.uint32) for d in (0.01, 0.3, 0.9)]
+    hl = [(2.0, 0.5), (1.5, 0.75), (4.0, 0.1)]
+    _check_warpmap_tables(L, occ, [M.run(o, 2.0, 0.5)[0] for o in occ], hl, [M.run(occ[0], h, l)[1] for h, l in hl])
+
+
 def test_warp_rig_is_a_bijection_per_row(L):
     cells = np.array(GOLD["warp_rig"]["cells"], np.float32)
     for row in range(4):

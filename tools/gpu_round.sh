@@ -17,6 +17,8 @@ try:
     print("cpu",j["cpu_baseline"])
 except Exception as e: print("bench parse failed",e)
 PY
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --profile-frames 1 > gpurun_out/launches_bench.log 2>&1
+tail -2 gpurun_out/launches_bench.log
 if [ -n "$1" ]; then
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:$1 --launch-skip ${SKIP:-0} -c ${COUNT:-12} -f -o gpurun_out/$2 python tools/profile_frame.py 2 > gpurun_out/ncu_$2.log 2>&1
 tail -2 gpurun_out/ncu_$2.log; ls -la gpurun_out/*.ncu-rep
