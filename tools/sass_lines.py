@@ -16,7 +16,10 @@ for l in open(dis):
 rows = list(csv.reader(open(src_csv)))
 hi = next(i for i, r in enumerate(rows) if 'Source' in r and 'Instructions Executed' in r)
 hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
+data = []
+for r in rows[hi + 1:]:
+    if len(r) < len(hdr) or not r[0].startswith('0x'): break       # the dump repeats the table per view: keep the first
+    data.append(r)
 print("sass rows", len(data), "disasm instr", len(seq))
 agg = collections.defaultdict(lambda: [0, 0, 0])
 for k, r in enumerate(data):

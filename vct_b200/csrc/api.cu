@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 thread_local std::string g_create_error;
@@ -209,6 +211,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     vct_ctx* c = new vct_ctx();
     c->cfg = *cfg; c->D = cfg->dim; c->L = clamp_levels(cfg->dim, cfg->levels); c->S = cfg->shadow_size; c->W = cfg->width; c->H = cfg->height;
     auto bail = [&](const char* what) { g_create_error = std::string("vct_create: ") + what + ": " + c->error; vct_destroy(c); return 1; };
+    if (const char* v = getenv("VCT_TRACE_VARIANT")) c->trace_variant = atoi(v);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
     for (auto& ev : c->ev) if (cudaEventCreate(&ev) != cudaSuccess) return bail("event");
     if (make_volumes(c)) return bail("volumes");

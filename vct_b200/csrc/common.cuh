@@ -147,6 +147,7 @@ struct vct_ctx {
     cudaEvent_t ev[32]{}; vct_timings timings{};
     int profiling = 1;               // 0 none, 1 pass-level events (reference GLTimer semantics), 2 + one event per kernel
     bool own_stream = true;
+    int trace_variant = 0;           // VCT_TRACE_VARIANT (tuning knob, see cone_trace.cu)
     std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
 };

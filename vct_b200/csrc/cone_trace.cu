@@ -30,6 +30,7 @@ struct TraceArgs {
     const float4 *wpos, *wnrm, *wT, *wB;
     const DevTexture* tex; const DevMaterial* mats; const float* shadow;
     cudaTextureObject_t vol, vol_point, vol_last; const ushort4* warp;
+    const uint32_t* last_level; int n_last;      // linear copy of pyramid level L-1 (n_last^3 words) for the shared-memory sampler
     uint32_t* image; Counters* counters;
 };
 
@@ -140,7 +141,43 @@ __device__ __forceinline__ V3 warp_sample(const ushort4* __restrict__ wm, V3 tc)
 enum { WARP_NONE = 0, WARP_TEXTURE = 1, WARP_VOXELS = 2 };      // common.glsl:44-60 priority: warpVoxels > warpTexture
 
 // ---- traceCone, phong.frag:135-180
-struct ConeCtx { cudaTextureObject_t vol, vol_point, vol_last; const ushort4* warp; int D, L; int warp_texture, warp_voxels; V3 eye_tc; };
+struct ConeCtx { cudaTextureObject_t vol, vol_point, vol_last; const ushort4* warp; int D, L; int warp_texture, warp_voxels; V3 eye_tc;
+                 const float4* s_last; float n_last; };
+
+// ---- last pyramid level from shared memory.  A third of all cone steps have lambda >= L-1 (phong.frag:160: the lod grows
+// with the march) and read only the coarsest level, which is tiny (8^3 texels at 256^3/6 levels).  Every CTA keeps it
+// unpacked as float4 with a one-texel zero border (CLAMP_TO_BORDER(0)) and filters it in fp32 on the FMA pipe: the
+// steps leave the texture pipe (the kernel's bound), see no texture latency, and use exact fp32 weights like the
+// oracle's vol_linear() instead of the texture unit's 8-bit ones.
+constexpr int kLastMax = 8;                       // largest last-level edge kept in shared memory
+constexpr int kLastP = kLastMax + 2;              // padded edge
+constexpr int kLastTexels = kLastP * kLastP * kLastP;
+template <bool CLAMP>
+__device__ __forceinline__ float4 sample_last_smem(const float4* __restrict__ s, float n, V3 sp) {
+    const float x = fmaf(sp.x, n, -0.5f), y = fmaf(sp.y, n, -0.5f), z = fmaf(sp.z, n, -0.5f);
+    float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
+    const float fx = x - fx0, fy = y - fy0, fz = z - fz0;
+    if (CLAMP) {                                   // warped sample positions are in [0,1] up to rounding; NaN -> texel 0
+        fx0 = fminf(fmaxf(fx0, -1.0f), n - 1.0f); fy0 = fminf(fmaxf(fy0, -1.0f), n - 1.0f); fz0 = fminf(fmaxf(fz0, -1.0f), n - 1.0f);
+    }
+    // padded index of texel (x0,y0,z0) = ((z0+1)*P + (y0+1))*P + (x0+1), formed exactly in fp32
+    const int i0 = __float2int_rz(fmaf(fz0, (float)(kLastP * kLastP), fmaf(fy0, (float)kLastP, fx0)) + (float)(kLastP * kLastP + kLastP + 1));
+    const float4* q = s + i0;
+    const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+    const float w00 = gy * gz, w10 = fy * gz, w01 = gy * fz, w11 = fy * fz;
+    float4 r, t; float w;
+    t = q[0]; w = gx * w00; r.x = w * t.x; r.y = w * t.y; r.z = w * t.z; r.w = w * t.w;
+#define VCT_ACC(OFF, W) t = q[OFF]; w = (W); r.x = fmaf(w, t.x, r.x); r.y = fmaf(w, t.y, r.y); r.z = fmaf(w, t.z, r.z); r.w = fmaf(w, t.w, r.w);
+    VCT_ACC(1, fx * w00)
+    VCT_ACC(kLastP, gx * w10)
+    VCT_ACC(kLastP + 1, fx * w10)
+    VCT_ACC(kLastP * kLastP, gx * w01)
+    VCT_ACC(kLastP * kLastP + 1, fx * w01)
+    VCT_ACC(kLastP * kLastP + kLastP, gx * w11)
+    VCT_ACC(kLastP * kLastP + kLastP + 1, fx * w11)
+#undef VCT_ACC
+    return r;
+}
 template <int WM>
 __device__ __noinline__ V4 trace_cone(const ConeCtx& cx, V3 position, V3 normal, V3 direction, int steps, float bias, float cone_angle,
                                          float cone_height, float lod_offset, unsigned& fetches) {
@@ -178,6 +215,12 @@ __device__ __noinline__ V4 trace_cone(const ConeCtx& cx, V3 position, V3 normal,
 // trilinear + mip-linear; [n_last,steps) lambda >= L-1 -> the last level only (one trilinear fetch, not two).
 typedef ConeSchedule Schedule;
 __device__ __forceinline__ bool inside_unit(V3 p) { return p.x >= 0.0f && p.x <= 1.0f && p.y >= 0.0f && p.y <= 1.0f && p.z >= 0.0f && p.z <= 1.0f; }   // false for NaN
+// the same test for a position known to be free of NaN (cones with NaN start/direction never enter the marching loops)
+__device__ __forceinline__ bool inside_unit_finite(V3 p) { return fminf(fminf(p.x, p.y), p.z) >= 0.0f && fmaxf(fmaxf(p.x, p.y), p.z) <= 1.0f; }
+__device__ __forceinline__ bool has_nan(V3 a, V3 b) {     // NaN or infinity anywhere: the cone's first sample fails the s == clamp(s,0,1) test
+    const float m = 3.0e38f;
+    return !(fabsf(a.x) <= m && fabsf(a.y) <= m && fabsf(a.z) <= m && fabsf(b.x) <= m && fabsf(b.y) <= m && fabsf(b.z) <= m);
+}
 // Largest march height (in voxels) up to which start + ds*h certainly passes the reference's per-component test
 // s == clamp(s,0,1): a slab test against the unit cube shrunk by 1e-5.  Steps beyond it take the exact test.
 __device__ __forceinline__ float safe_height(V3 start, V3 ds) {
@@ -190,86 +233,96 @@ __device__ __forceinline__ float safe_height(V3 start, V3 ds) {
     };
     return fminf(axis(start.x, ds.x), fminf(axis(start.y, ds.y), axis(start.z, ds.z)));
 }
-enum { SAMPLE_POINT = 0, SAMPLE_MIP = 1, SAMPLE_LAST = 2 };
+enum { SAMPLE_POINT = 0, SAMPLE_MIP = 1, SAMPLE_LAST = 2, SAMPLE_LAST_SMEM = 3 };
 template <int KIND, int WM>
 __device__ __forceinline__ float4 fetch_volume(const ConeCtx& cx, V3 sp, float lambda, float max_lod) {
     if (WM == WARP_TEXTURE) sp = warp_sample(cx.warp, sp);
     else if (WM == WARP_VOXELS) sp = voxel_warp(sp, cx.eye_tc);
     if (KIND == SAMPLE_POINT) return tex3DLod<float4>(cx.vol_point, sp.x, sp.y, sp.z, 0.0f);
+    if (KIND == SAMPLE_LAST_SMEM) return sample_last_smem<WM != WARP_NONE>(cx.s_last, cx.n_last, sp);
     if (KIND == SAMPLE_LAST) return tex3DLod<float4>(cx.vol_last, sp.x, sp.y, sp.z, max_lod);
     return tex3DLod<float4>(cx.vol, sp.x, sp.y, sp.z, lambda);
 }
 // N cones sharing one schedule, marched in lock step: N independent texture fetches are in flight per thread.
 // Each cone's own accumulation sequence is exactly the reference's (front-to-back, stop at alpha >= 0.95 or when
 // the sample leaves the unit cube).
-template <int N> struct ConeSet { V3 ds[N]; float hsafe[N]; V4 acc[N]; bool alive[N]; };
+template <int N> struct ConeSet { V3 ds[N]; float hsafe[N]; V4 acc[N]; unsigned alive; };     // alive: bit c = cone c still marching
+// Branch-free inner loop: liveness is a bit mask, dead cones fetch nothing (predicated TEX) and accumulate with weight 0,
+// so the N fetches of a step issue back to back and the compiler keeps every per-cone value in registers.
 template <int N, int KIND, int WM>
 __device__ __forceinline__ void march_run(const ConeCtx& cx, const Schedule& t, int i0, int i1, V3 start, ConeSet<N>& cs, unsigned& fetches) {
     const float max_lod = (float)(cx.L - 1);
-    for (int i = i0; i < i1; ++i) {
+    unsigned live = cs.alive;
+    for (int i = i0; i < i1 && live; ++i) {
         const float hs = t.h[i], lambda = t.lambda[i];
-        float4 smp[N]; bool got[N]; bool any = false;
+        float4 smp[N];
 #pragma unroll
         for (int c = 0; c < N; ++c) {
-            got[c] = false;
-            if (!cs.alive[c]) continue;
             const V3 sp = mk3(fmaf(cs.ds[c].x, hs, start.x), fmaf(cs.ds[c].y, hs, start.y), fmaf(cs.ds[c].z, hs, start.z));
-            if (!(hs <= cs.hsafe[c]) && !inside_unit(sp)) { cs.alive[c] = false; continue; }
-            smp[c] = fetch_volume<KIND, WM>(cx, sp, lambda, max_lod); got[c] = true; any = true;
+            if (!((hs <= cs.hsafe[c]) | inside_unit_finite(sp))) live &= ~(1u << c);     // left the volume: phong.frag:163-165 break
+            smp[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live >> c & 1u) smp[c] = fetch_volume<KIND, WM>(cx, sp, lambda, max_lod);
         }
-        if (!any) return;
+        fetches += __popc(live);
 #pragma unroll
         for (int c = 0; c < N; ++c) {
-            if (!got[c]) continue;
-            const float a = 1.0f - cs.acc[c].w;
+            const float a = (live >> c & 1u) ? 1.0f - cs.acc[c].w : 0.0f;
             cs.acc[c].x = fmaf(a, smp[c].x, cs.acc[c].x); cs.acc[c].y = fmaf(a, smp[c].y, cs.acc[c].y);
             cs.acc[c].z = fmaf(a, smp[c].z, cs.acc[c].z); cs.acc[c].w = fmaf(a, smp[c].w, cs.acc[c].w);
-            fetches++;
-            if (!(cs.acc[c].w < 0.95f)) cs.alive[c] = false;
+            if (!(cs.acc[c].w < 0.95f)) live &= ~(1u << c);                       // loop condition alpha < 0.95
         }
     }
+    cs.alive = live;
 }
-template <int N, int WM>
+template <int N, int WM, bool SL>
 __device__ __forceinline__ void trace_cones(const ConeCtx& cx, const Schedule& t, V3 start, ConeSet<N>& cs, unsigned& fetches) {
 #pragma unroll
-    for (int c = 0; c < N; ++c) { cs.acc[c] = mk4(0.f, 0.f, 0.f, 0.f); cs.alive[c] = true; cs.hsafe[c] = safe_height(start, cs.ds[c]); }
+    cs.alive = (1u << N) - 1u;
+    for (int c = 0; c < N; ++c) {
+        cs.acc[c] = mk4(0.f, 0.f, 0.f, 0.f); cs.hsafe[c] = safe_height(start, cs.ds[c]);
+        if (has_nan(start, cs.ds[c])) cs.alive &= ~(1u << c);               // the first sample is NaN: immediate break (phong.frag:163-165)
+    }
     march_run<N, SAMPLE_POINT, WM>(cx, t, 0, t.n_point, start, cs, fetches);
     march_run<N, SAMPLE_MIP, WM>(cx, t, t.n_point, t.n_last, start, cs, fetches);
-    march_run<N, SAMPLE_LAST, WM>(cx, t, t.n_last, t.steps, start, cs, fetches);
+    march_run<N, SL ? SAMPLE_LAST_SMEM : SAMPLE_LAST, WM>(cx, t, t.n_last, t.steps, start, cs, fetches);
 }
 // One cone, K steps fetched ahead: the sample positions do not depend on earlier samples, only the decision to go on
-// does, so up to K-1 fetches may be discarded when the cone saturates.
+// does, so up to K-1 fetches may be discarded when the cone saturates.  Same branch-free form: `valid` is the prefix
+// mask of the steps that were inside the volume (issuing stops at the first miss).
 template <int K, int KIND, int WM>
 __device__ __forceinline__ void march_ahead(const ConeCtx& cx, const Schedule& t, int i0, int i1, V3 start, V3 ds, float hsafe, V4& acc, bool& alive, unsigned& fetches) {
     const float max_lod = (float)(cx.L - 1);
     for (int i = i0; i < i1 && alive; i += K) {
-        float4 smp[K]; int nvalid = 0;
+        float4 smp[K]; unsigned valid = 0u; bool open = true;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            if (nvalid != k || i + k >= i1) continue;                       // stop issuing after the first miss
-            const float hs = t.h[i + k];
+            const int j = min(i + k, i1 - 1);
+            const float hs = t.h[j];
             const V3 sp = mk3(fmaf(ds.x, hs, start.x), fmaf(ds.y, hs, start.y), fmaf(ds.z, hs, start.z));
-            if (!(hs <= hsafe) && !inside_unit(sp)) continue;
-            smp[k] = fetch_volume<KIND, WM>(cx, sp, t.lambda[i + k], max_lod); nvalid = k + 1;
+            open = open & (i + k < i1) & ((hs <= hsafe) | inside_unit_finite(sp));
+            smp[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (open) { smp[k] = fetch_volume<KIND, WM>(cx, sp, t.lambda[j], max_lod); valid |= 1u << k; }
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            if (k >= nvalid || !alive) continue;
-            const float a = 1.0f - acc.w;
+            const bool use = (valid >> k & 1u) && alive;
+            const float a = use ? 1.0f - acc.w : 0.0f;
             acc.x = fmaf(a, smp[k].x, acc.x); acc.y = fmaf(a, smp[k].y, acc.y); acc.z = fmaf(a, smp[k].z, acc.z); acc.w = fmaf(a, smp[k].w, acc.w);
-            fetches++;
+            fetches += use ? 1u : 0u;
             if (!(acc.w < 0.95f)) alive = false;
         }
+        const int nvalid = __popc(valid);
         if (nvalid < K && i + nvalid < i1) alive = false;                   // left the volume
     }
 }
-template <int K, int WM>
+template <int K, int WM, bool SL>
 __device__ __forceinline__ V4 trace_cone_ahead(const ConeCtx& cx, const Schedule& t, V3 start, V3 ds, unsigned& fetches) {
-    V4 acc = mk4(0.f, 0.f, 0.f, 0.f); bool alive = true;
+    V4 acc = mk4(0.f, 0.f, 0.f, 0.f); bool alive = !has_nan(start, ds);
     const float hsafe = safe_height(start, ds);
     march_ahead<K, SAMPLE_POINT, WM>(cx, t, 0, t.n_point, start, ds, hsafe, acc, alive, fetches);
     march_ahead<K, SAMPLE_MIP, WM>(cx, t, t.n_point, t.n_last, start, ds, hsafe, acc, alive, fetches);
-    march_ahead<K, SAMPLE_LAST, WM>(cx, t, t.n_last, t.steps, start, ds, hsafe, acc, alive, fetches);
+    if (SL) march_ahead<1, SAMPLE_LAST_SMEM, WM>(cx, t, t.n_last, t.steps, start, ds, hsafe, acc, alive, fetches);   // no latency to hide: never fetch past the cone's end
+    else march_ahead<K, SAMPLE_LAST, WM>(cx, t, t.n_last, t.steps, start, ds, hsafe, acc, alive, fetches);
     return acc;
 }
 
@@ -297,11 +350,24 @@ __device__ __forceinline__ LR cook_torrance(V3 dc, V3 lc, V3 N, V3 V, V3 L, V3 H
     return r;
 }
 
-template <int WM>
-__global__ void __launch_bounds__(kThreads, 4) k_cone_trace(TraceArgs a) {
+template <int WM, bool SL, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_cone_trace(TraceArgs a) {
     const FrameConst& fc = *a.fc;
     const vct_frame_params& fp = fc.p;
     __shared__ Schedule s_diffuse, s_specular;
+    __shared__ float4 s_last[SL ? kLastTexels : 1];
+    if (SL) {
+        const int n = a.n_last;
+        for (int i = threadIdx.x; i < kLastTexels; i += kThreads) {
+            const int x = i % kLastP - 1, y = (i / kLastP) % kLastP - 1, z = i / (kLastP * kLastP) - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (x >= 0 && y >= 0 && z >= 0 && x < n && y < n && z < n) {
+                const uint32_t w = __ldg(a.last_level + (z * n + y) * n + x);
+                v = make_float4(__fdiv_rn((float)(w & 255u), 255.0f), __fdiv_rn((float)((w >> 8) & 255u), 255.0f), __fdiv_rn((float)((w >> 16) & 255u), 255.0f), __fdiv_rn((float)(w >> 24), 255.0f));
+            }
+            s_last[i] = v;
+        }
+    }
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&fc.sched_diffuse);          // the two tables are adjacent
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_diffuse);
@@ -404,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_cone_trace(TraceArgs a) {
             if (fp.enable_indirect) {
                 ConeCtx cx; cx.vol = a.vol; cx.vol_point = a.vol_point; cx.vol_last = a.vol_last; cx.warp = a.warp; cx.D = fc.D; cx.L = fc.L;
                 cx.warp_texture = fp.warp_texture; cx.warp_voxels = fp.warp_voxels; cx.eye_tc = voxel_linear_position(eye, fp);
+                cx.s_last = s_last; cx.n_last = (float)a.n_last;
                 const V3 vp = voxel_linear_position(Pw, fp);
                 const float scale = 1.0f / (float)fc.D;
                 const float dirs[6][3] = {{0.f, 1.f, 0.f}, {0.f, 0.5f, 0.866025f}, {0.823639f, 0.5f, 0.267617f}, {0.509037f, 0.5f, -0.700629f},
@@ -415,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_cone_trace(TraceArgs a) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) cs.ds[i] = normalize3(normalize3(tbn(mk3(dirs[i][0], dirs[i][1], dirs[i][2])))) * scale;   // main() and traceCone() both normalise
                     const V3 start = vp + (N * fp.diffuse_cone.bias) * scale;
-                    trace_cones<6, WM>(cx, s_diffuse, start, cs, fetches);
+                    trace_cones<6, WM, SL>(cx, s_diffuse, start, cs, fetches);
 #pragma unroll
                     for (int i = 0; i < 6; ++i) ind = mk4(ind.x + wts[i] * cs.acc[i].x, ind.y + wts[i] * cs.acc[i].y, ind.z + wts[i] * cs.acc[i].z, ind.w + wts[i] * cs.acc[i].w);
                 }
@@ -429,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_cone_trace(TraceArgs a) {
                         rc = trace_cone<WM>(cx, vp, N, R, fp.specular_cone.steps, fp.specular_cone.bias, ang, fp.specular_cone.cone_initial_height, fp.specular_cone.lod_offset, fetches);
                     } else {
                         const V3 start = vp + (N * fp.specular_cone.bias) * scale;
-                        rc = trace_cone_ahead<4, WM>(cx, s_specular, start, normalize3(R) * scale, fetches);
+                        rc = trace_cone_ahead<4, WM, SL>(cx, s_specular, start, normalize3(R) * scale, fetches);
                     }
                     ind.x += rc.x * fp.reflect_scale; ind.y += rc.y * fp.reflect_scale; ind.z += rc.z * fp.reflect_scale;
                 }
@@ -474,9 +541,25 @@ int vctk_cone_trace(vct_ctx* c) {
     if (a.y_hi <= a.y_lo) return 0;
     dim3 grid((c->W + 31) / 32, (a.y_hi - a.y_lo + 3) / 4);
     const vct_frame_params& p = c->h_fc.p;
-    if (p.warp_voxels) k_cone_trace<WARP_VOXELS><<<grid, kThreads, 0, c->stream>>>(a);
-    else if (p.warp_texture) k_cone_trace<WARP_TEXTURE><<<grid, kThreads, 0, c->stream>>>(a);
-    else k_cone_trace<WARP_NONE><<<grid, kThreads, 0, c->stream>>>(a);
+    // the coarsest level goes to shared memory when it fits (edge <= 8: 256^3 with 6 levels, 128^3 with 5, ...)
+    a.n_last = level_dim(c->D, c->L - 1);
+    a.last_level = (rad ? c->d_radiance : c->d_color) + c->level_off[c->L - 1];
+    const int variant = c->trace_variant;          // tuning knob (VCT_TRACE_VARIANT): bit 0 = shared-memory last level (measured slower, off), bits 1-2 = CTAs/SM target
+    const bool sl = a.n_last <= kLastMax && (variant & 1) && !p.warp_voxels;
+    const int occ = (variant >> 1) & 3;
+#define VCT_TRACE(WM)                                                                                          \
+    do {                                                                                                       \
+        if (sl) { if (occ == 1) k_cone_trace<WM, true, 3><<<grid, kThreads, 0, c->stream>>>(a);                \
+                  else if (occ == 2) k_cone_trace<WM, true, 5><<<grid, kThreads, 0, c->stream>>>(a);           \
+                  else k_cone_trace<WM, true, 4><<<grid, kThreads, 0, c->stream>>>(a); }                       \
+        else    { if (occ == 1) k_cone_trace<WM, false, 3><<<grid, kThreads, 0, c->stream>>>(a);               \
+                  else if (occ == 2) k_cone_trace<WM, false, 5><<<grid, kThreads, 0, c->stream>>>(a);          \
+                  else k_cone_trace<WM, false, 4><<<grid, kThreads, 0, c->stream>>>(a); }                      \
+    } while (0)
+    if (p.warp_voxels) VCT_TRACE(WARP_VOXELS);
+    else if (p.warp_texture) VCT_TRACE(WARP_TEXTURE);
+    else VCT_TRACE(WARP_NONE);
+#undef VCT_TRACE
     VCT_LAUNCH_CHECK(c, "k_cone_trace");
     return 0;
 }
