@@ -30,7 +30,8 @@ void free_volumes(vct_ctx* c) {
     if (c->color_arr) cudaFreeMipmappedArray(c->color_arr);
     c->radiance_arr = c->color_arr = nullptr;
     for (uint32_t** p : {&c->d_color, &c->d_radiance, &c->d_normal, &c->d_scratch}) { cudaFree(*p); *p = nullptr; }
-    for (uint8_t** p : {&c->d_pub_mask_radiance, &c->d_pub_mask_color}) { cudaFree(*p); *p = nullptr; }
+    for (uint8_t** p : {&c->d_pub_mask_radiance, &c->d_pub_mask_color, &c->d_seg[0], &c->d_seg[1]}) { cudaFree(*p); *p = nullptr; }
+    c->seg_valid = false; c->seg_disabled = false; c->seg_cur = 0;
 }
 
 int make_pyramid_texture(vct_ctx* c, cudaMipmappedArray_t* arr, cudaTextureObject_t* lin, cudaTextureObject_t* pt, cudaTextureObject_t* last, cudaSurfaceObject_t* surf, uint8_t** mask) {
@@ -70,6 +71,8 @@ int make_volumes(vct_ctx* c) {
     VCT_CHECK(c, cudaMalloc(&c->d_color, off * 4)); VCT_CHECK(c, cudaMalloc(&c->d_radiance, off * 4)); VCT_CHECK(c, cudaMalloc(&c->d_normal, n0 * 4));
     VCT_CHECK(c, cudaMemsetAsync(c->d_color, 0, off * 4, c->stream)); VCT_CHECK(c, cudaMemsetAsync(c->d_radiance, 0, off * 4, c->stream));
     VCT_CHECK(c, cudaMemsetAsync(c->d_normal, 0, n0 * 4, c->stream));
+    for (int i = 0; i < 2; ++i) { const size_t nb = std::max<size_t>(n0 / 8, 64); VCT_CHECK(c, cudaMalloc(&c->d_seg[i], nb)); VCT_CHECK(c, cudaMemsetAsync(c->d_seg[i], 0, nb, c->stream)); }
+    c->seg_valid = false; c->seg_cur = 0;
     if (make_pyramid_texture(c, &c->radiance_arr, &c->radiance_tex, &c->radiance_tex_point, &c->radiance_tex_last, c->radiance_surf, &c->d_pub_mask_radiance)) return 1;
     const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
     c->z_lo = (int)((long long)c->D * r / ws); c->z_hi = (int)((long long)c->D * (r + 1) / ws);
@@ -81,19 +84,37 @@ int clamp_levels(int dim, int levels) {
     return std::min(std::max(levels, 1), std::min(lg + 1, VCT_MAX_LEVELS));
 }
 
+// device blob [FrameConst | models | nmats] + its pinned staging ring, sized for the current actor count
+int make_frame_blob(vct_ctx* c) {
+    const size_t bytes = sizeof(FrameConst) + (size_t)c->n_actors * (sizeof(Mat4) + 36);
+    if (c->d_frame_blob && bytes <= c->frame_blob_bytes) {
+        c->d_models = reinterpret_cast<Mat4*>((char*)c->d_frame_blob + sizeof(FrameConst)); c->d_nmats = reinterpret_cast<float*>(c->d_models + c->n_actors);
+        return 0;
+    }
+    VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_frame_blob); c->d_frame_blob = nullptr;
+    if (c->h_stage) { cudaFreeHost(c->h_stage); c->h_stage = nullptr; }
+    VCT_CHECK(c, cudaMalloc(&c->d_frame_blob, bytes));
+    VCT_CHECK(c, cudaMallocHost((void**)&c->h_stage, 4 * bytes));
+    c->frame_blob_bytes = bytes;
+    c->d_fc = reinterpret_cast<FrameConst*>(c->d_frame_blob);
+    c->d_models = reinterpret_cast<Mat4*>((char*)c->d_frame_blob + sizeof(FrameConst)); c->d_nmats = reinterpret_cast<float*>(c->d_models + c->n_actors);
+    return 0;
+}
+
 // concatenate the per-actor meshes into the device arrays the kernels index
 int finalize_scene(vct_ctx* c) {
     if (!c->scene_dirty) return 0;
     std::sort(c->meshes.begin(), c->meshes.end(), [](const HostMesh& a, const HostMesh& b) { return a.actor < b.actor; });
-    for (void** p : {(void**)&c->d_vertices, (void**)&c->d_vactor, (void**)&c->d_indices, (void**)&c->d_trimat, (void**)&c->d_models, (void**)&c->d_nmats, (void**)&c->d_wpos,
+    for (void** p : {(void**)&c->d_vertices, (void**)&c->d_vactor, (void**)&c->d_indices, (void**)&c->d_trimat, (void**)&c->d_wpos,
                      (void**)&c->d_wnrm, (void**)&c->d_wT, (void**)&c->d_wB, (void**)&c->d_setup, (void**)&c->d_tile_queue, (void**)&c->d_expand_queue, (void**)&c->d_pixel_queue}) { cudaFree(*p); *p = nullptr; }
     c->n_vertices = c->h_vertices.size() / 14; c->n_tris = c->h_trimat.size();
     c->n_actors = 0; for (auto& m : c->meshes) c->n_actors = std::max(c->n_actors, m.actor + 1);
+    if (make_frame_blob(c)) return 1;
     if (!c->n_vertices || !c->n_tris) { c->scene_dirty = false; return 0; }
     const size_t nv = c->n_vertices, nt = c->n_tris;
     VCT_CHECK(c, cudaMalloc(&c->d_vertices, nv * 56)); VCT_CHECK(c, cudaMalloc(&c->d_vactor, nv * 4));
     VCT_CHECK(c, cudaMalloc(&c->d_indices, nt * 12)); VCT_CHECK(c, cudaMalloc(&c->d_trimat, nt * 4));
-    VCT_CHECK(c, cudaMalloc(&c->d_models, c->n_actors * sizeof(Mat4))); VCT_CHECK(c, cudaMalloc(&c->d_nmats, c->n_actors * 36));
     VCT_CHECK(c, cudaMalloc(&c->d_wpos, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wnrm, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wT, nv * 16)); VCT_CHECK(c, cudaMalloc(&c->d_wB, nv * 16));
     // one setup per queued (sub-)triangle (camera pass: up to two after near clipping); tile queue sized for the
     // scene: every triangle may push one tile, plus headroom for the multi-tile ones
@@ -146,7 +167,15 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     f.n_lights = c->n_lights; std::memcpy(f.lights, c->h_lights, sizeof f.lights);
     f.z_lo = c->z_lo; f.z_hi = c->z_hi;
     build_schedule(f.sched_diffuse, p->diffuse_cone, c->L); build_schedule(f.sched_specular, p->specular_cone, c->L);
-    VCT_CHECK(c, cudaMemcpyAsync(c->d_fc, &f, sizeof f, cudaMemcpyHostToDevice, c->stream));
+    {   // one pinned, asynchronous copy: frame constants + per-actor matrices
+        const unsigned slot = c->stage_next++ & 3u;
+        VCT_CHECK(c, cudaEventSynchronize(c->stage_ev[slot]));               // the copy that last read this slot (4 calls ago) is done
+        unsigned char* h = c->h_stage + (size_t)slot * c->frame_blob_bytes;
+        std::memcpy(h, &f, sizeof f);
+        vctk_fill_models(c, reinterpret_cast<Mat4*>(h + sizeof f), reinterpret_cast<float*>(h + sizeof f + (size_t)c->n_actors * sizeof(Mat4)));
+        VCT_CHECK(c, cudaMemcpyAsync(c->d_frame_blob, h, sizeof f + (size_t)c->n_actors * (sizeof(Mat4) + 36), cudaMemcpyHostToDevice, c->stream));
+        VCT_CHECK(c, cudaEventRecord(c->stage_ev[slot], c->stream));
+    }
     if (c->tables_dirty) {                      // texture / material tables change only on upload
         VCT_CHECK(c, cudaMemcpyAsync(c->d_tex, c->h_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES, cudaMemcpyHostToDevice, c->stream));
         VCT_CHECK(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS, cudaMemcpyHostToDevice, c->stream));
@@ -173,21 +202,38 @@ int zero_info(vct_ctx* c) {
     vct_prof_mark(c, "memset");
     return 0;
 }
+// The GI passes of one frame.  Sparse frame (DESIGN.md "segment masks"): clear, transfer and the mip chain visit only the
+// x-row segments that hold (or held last frame) a fragment.  The first frame, and any frame after something wrote a
+// volume behind the library's back, runs the dense kernels and (re)builds the masks.
 int gi_body(vct_ctx* c, Graph& g) {
     const vct_frame_params& p = c->h_fc.p;
-    if (zero_info(c)) return 1;
-    if (vctk_clear_voxels(c) || g.rec(EV_CLEAR)) return 1;
-    if (vctk_voxelize(c, false) || g.rec(EV_VOXEL)) return 1;
-    if (vctk_transfer(c) || g.rec(EV_TRANSFER)) return 1;
+    const bool single = c->cfg.world_size <= 1;
+    const int n_chains = (p.mip_color_chain || !p.draw_radiance) ? 2 : 1;
+    const int key = n_chains * 2 + (p.draw_radiance ? 1 : 0);           // which pyramids are filtered / published
+    const bool maskable = vctk_sparse_supported(c) && !c->sparse_off && !p.voxel_fill_holes;
+    const bool sparse = maskable && c->seg_valid && c->seg_key == key;
+    if (sparse) {
+        if (vctk_clear_masked(c) || g.rec(EV_CLEAR)) return 1;              // also zeroes VoxelizeInfo, the raster queues, cone_steps
+    } else {
+        const size_t nb = std::max<size_t>((size_t)c->D * c->D * c->D / 8, 64);
+        VCT_CHECK(c, cudaMemsetAsync(c->d_seg[c->seg_cur], 0, nb, c->stream));
+        vct_prof_mark(c, "memset");
+        if (vctk_clear_voxels(c, true) || g.rec(EV_CLEAR)) return 1;
+    }
+    if (vctk_voxelize(c, false, true) || g.rec(EV_VOXEL)) return 1;
+    if ((sparse ? vctk_transfer_masked(c) : vctk_transfer(c)) || g.rec(EV_TRANSFER)) return 1;
     if (vctk_inject(c)) return 1;
     if (p.voxel_fill_holes) { if (ensure_scratch(c) || vctk_fill_holes(c)) return 1; }
     if (g.rec(EV_INJECT)) return 1;
     // single GPU: the chain that the cone tracer samples is written straight into its texture array
-    const bool single = c->cfg.world_size <= 1;
     if (single && !p.draw_radiance && ensure_color_texture(c)) return 1;
     const int which[2] = {VCT_VOL_RADIANCE, VCT_VOL_COLOR};
     const int publish[2] = {single && p.draw_radiance, single && !p.draw_radiance};
-    if (vctk_mip_chains(c, (p.mip_color_chain || !p.draw_radiance) ? 2 : 1, which, publish, 0)) return 1;   // both pyramids, one launch
+    if (vctk_mip_chains(c, n_chains, which, publish, 0, sparse)) return 1;   // both pyramids, one launch
+    // this frame's mask bounds the support of all three level-0 volumes (dense temporal frames: k_transfer flagged the history)
+    c->seg_valid = maskable;
+    c->seg_key = key;
+    c->seg_cur ^= 1;
     return g.rec(EV_MIP);
 }
 
@@ -212,8 +258,11 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     c->cfg = *cfg; c->D = cfg->dim; c->L = clamp_levels(cfg->dim, cfg->levels); c->S = cfg->shadow_size; c->W = cfg->width; c->H = cfg->height;
     auto bail = [&](const char* what) { g_create_error = std::string("vct_create: ") + what + ": " + c->error; vct_destroy(c); return 1; };
     if (const char* v = getenv("VCT_TRACE_VARIANT")) c->trace_variant = atoi(v);
+    if (const char* v = getenv("VCT_SPARSE")) c->sparse_off = atoi(v) == 0;   // VCT_SPARSE=0: dense kernels every frame (A/B and tests)
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
     for (auto& ev : c->ev) if (cudaEventCreate(&ev) != cudaSuccess) return bail("event");
+    for (auto& ev : c->stage_ev) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    if (make_frame_blob(c)) return bail("frame constants");
     if (make_volumes(c)) return bail("volumes");
     const int N = VCT_WARP_DIM;
     auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
@@ -221,7 +270,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * 8) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
         alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
         alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
-        alloc((void**)&c->d_fc, sizeof(FrameConst)) || alloc((void**)&c->d_counters, sizeof(Counters)) ||
+        alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
     for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }
@@ -236,12 +285,14 @@ int vct_destroy(vct_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
     for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_warp_scratch,
-                    c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, (void*)c->d_fc, (void*)c->d_counters,
-                    (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_models, (void*)c->d_nmats, (void*)c->d_wpos,
+                    c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters,
+                    (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_wpos,
                     (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})
         cudaFree(p);
     for (void* p : c->tex_allocs) cudaFree(p);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->stage_ev) if (ev) cudaEventDestroy(ev);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto& ev : c->prof_pool) cudaEventDestroy(ev);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -331,10 +382,10 @@ int vct_set_lights(vct_ctx* c, const vct_light* lights, int n) {
 int vct_shadowmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_shadowmap(c); }
 int vct_occupancy(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_voxelize(c, true); }
 int vct_warpmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_warpmap(c); }
-int vct_voxelize(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return zero_info(c) || vctk_transform_vertices(c) || vctk_clear_voxels(c) || vctk_voxelize(c, false); }
-int vct_transfer(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transfer(c); }
-int vct_inject(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_inject(c); }
-int vct_fill_holes(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return ensure_scratch(c) || vctk_fill_holes(c); }
+int vct_voxelize(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; c->seg_valid = false; return zero_info(c) || vctk_transform_vertices(c) || vctk_clear_voxels(c) || vctk_voxelize(c, false); }
+int vct_transfer(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; c->seg_valid = false; return vctk_transfer(c); }
+int vct_inject(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; c->seg_valid = false; return vctk_inject(c); }
+int vct_fill_holes(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; c->seg_valid = false; return ensure_scratch(c) || vctk_fill_holes(c); }
 int vct_gbuffer(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_visibility(c); }
 int vct_cone_trace(vct_ctx* c, const vct_frame_params* p) {
     PASS_PROLOGUE;
@@ -347,6 +398,7 @@ int vct_mip(vct_ctx* c, int which) {
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);
     if (which != VCT_VOL_RADIANCE && which != VCT_VOL_COLOR) return fail(c, "vct_mip: radiance or colour volume only");
+    c->seg_valid = false;
     const bool publish = c->cfg.world_size <= 1 && !(which == VCT_VOL_COLOR && !c->color_arr);
     return vctk_mip(c, which, 0, publish);
 }
@@ -367,9 +419,7 @@ int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
     if (gi_body(c, g)) return 1;
     if (c->cfg.world_size > 1) return 0;                      // caller all-gathers, then vct_exchange + vct_cone_trace
     if (g.rec(EV_GBUF)) return 1;
-    VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
-    vct_prof_mark(c, "memset");
-    if (vctk_cone_trace(c)) return 1;
+    if (vctk_cone_trace(c)) return 1;                         // cone_steps was zeroed by gi_body's clear
     return g.rec(EV_TRACE);
 }
 
@@ -384,17 +434,15 @@ int vct_frame(vct_ctx* c, const vct_frame_params* p) {
     if (gi_body(c, g)) return 1;
     if (c->cfg.world_size > 1) return 0;
     if (vctk_visibility(c) || g.rec(EV_GBUF)) return 1;
-    VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
-    vct_prof_mark(c, "memset");
-    if (vctk_cone_trace(c)) return 1;
+    if (vctk_cone_trace(c)) return 1;                         // cone_steps was zeroed by gi_body's clear
     return g.rec(EV_TRACE);
 }
 
 // dead-shader equivalents
-int vct_set_voxel_opacity(vct_ctx* c, float o) { if (!c) return 1; cudaSetDevice(c->cfg.device); return zero_info(c) || vctk_set_voxel_opacity(c, o); }
-int vct_temporal_radiance_filter(vct_ctx* c, float d) { if (!c) return 1; cudaSetDevice(c->cfg.device); return vctk_temporal_radiance_filter(c, d); }
-int vct_filter3d(vct_ctx* c, int which, int src_level) { if (!c) return 1; cudaSetDevice(c->cfg.device); return vctk_filter3d(c, which, src_level); }
-int vct_normalize_voxels_f16(vct_ctx* c, void* col, void* nrm, float o) { if (!c) return 1; cudaSetDevice(c->cfg.device); return zero_info(c) || vctk_normalize_voxels_f16(c, col, nrm, o); }
+int vct_set_voxel_opacity(vct_ctx* c, float o) { if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return zero_info(c) || vctk_set_voxel_opacity(c, o); }
+int vct_temporal_radiance_filter(vct_ctx* c, float d) { if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return vctk_temporal_radiance_filter(c, d); }
+int vct_filter3d(vct_ctx* c, int which, int src_level) { if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return vctk_filter3d(c, which, src_level); }
+int vct_normalize_voxels_f16(vct_ctx* c, void* col, void* nrm, float o) { if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return zero_info(c) || vctk_normalize_voxels_f16(c, col, nrm, o); }
 
 // ------------------------------------------------------------------------------------------ outputs
 static int volume_ptr(vct_ctx* c, int which, int level, void** ptr, size_t* bytes) {
@@ -426,6 +474,7 @@ int vct_write_volume(vct_ctx* c, int which, int level, const void* in) {
     if (!c || !in) return 1;
     cudaSetDevice(c->cfg.device);
     void* p; size_t b; if (volume_ptr(c, which, level, &p, &b)) return 1;
+    c->seg_valid = false;
     VCT_CHECK(c, cudaMemcpyAsync(p, in, b, cudaMemcpyHostToDevice, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -483,7 +532,14 @@ int vct_get_timings(vct_ctx* c, vct_timings* t) {
     t->mipmap_ns = ms(EV_INJECT, EV_MIP); t->gbuffer_ns = ms(EV_MIP, EV_GBUF); t->render_ns = ms(EV_GBUF, EV_TRACE); t->total_ns = ms(EV_START, EV_TRACE);
     return 0;
 }
-void* vct_device_ptr(vct_ctx* c, int which, int level) { if (!c) return nullptr; void* p; size_t b; return volume_ptr(c, which, level, &p, &b) ? nullptr : p; }
+// A raw pointer lets the caller write the volume at any time: sparse frames are switched off for good (until vct_remake).
+void* vct_device_ptr(vct_ctx* c, int which, int level) {
+    if (!c) return nullptr;
+    void* p; size_t b;
+    if (volume_ptr(c, which, level, &p, &b)) return nullptr;
+    if (which == VCT_VOL_COLOR || which == VCT_VOL_NORMAL || which == VCT_VOL_RADIANCE) { c->seg_disabled = true; c->seg_valid = false; }
+    return p;
+}
 size_t vct_level_bytes(vct_ctx* c, int which, int level) { if (!c) return 0; void* p; size_t b; return volume_ptr(c, which, level, &p, &b) ? 0 : b; }
 void* vct_stream(vct_ctx* c) { return c ? (void*)c->stream : nullptr; }
 // Enqueue on a caller-owned stream (e.g. the stream torch.distributed's NCCL collectives run on) so that the

@@ -116,7 +116,6 @@ struct vct_ctx {
     int32_t* d_vactor = nullptr;
     uint32_t* d_indices = nullptr; int32_t* d_trimat = nullptr;
     Mat4* d_models = nullptr; float* d_nmats = nullptr; int n_actors = 0;
-    std::vector<Mat4> h_models; std::vector<float> h_nmats;
     float4 *d_wpos = nullptr, *d_wnrm = nullptr, *d_wT = nullptr, *d_wB = nullptr;   // per-vertex world-space attributes
     DevTexture h_tex[VCT_MAX_TEXTURES]{}; DevTexture* d_tex = nullptr; std::vector<void*> tex_allocs; int n_textures = 0;
     DevMaterial h_mat[VCT_MAX_MATERIALS]{}; DevMaterial* d_mat = nullptr; int n_materials = 0;
@@ -129,6 +128,12 @@ struct vct_ctx {
     cudaTextureObject_t radiance_tex = 0, radiance_tex_point = 0, radiance_tex_last = 0, color_tex = 0, color_tex_point = 0, color_tex_last = 0;
     cudaSurfaceObject_t radiance_surf[VCT_MAX_LEVELS]{}, color_surf[VCT_MAX_LEVELS]{};
     uint8_t *d_pub_mask_radiance = nullptr, *d_pub_mask_color = nullptr;   // see k_mip_chain
+    // Segment masks (sparse frames): one byte per 8 level-0 voxels of an x-row.  d_seg[seg_cur] is written by this frame's
+    // voxeliser ("a fragment landed here"), d_seg[seg_cur ^ 1] is last frame's.  While seg_valid, every non-zero word of
+    // voxelColor / voxelNormal / voxelRadiance level 0 lies in a segment flagged in the previous mask, so clear, transfer
+    // and the mip chain touch only flagged segments (the volume is ~97 % empty).  Anything that writes a volume outside
+    // vct_frame / vct_gi_passes invalidates the masks; the next frame then runs the dense kernels once.
+    uint8_t* d_seg[2] = {nullptr, nullptr}; int seg_cur = 0, seg_key = -1; bool seg_valid = false, seg_disabled = false, sparse_off = false;
     // warp
     uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
     // shadow map / visibility / image
@@ -142,6 +147,10 @@ struct vct_ctx {
     void* d_setup = nullptr; size_t setup_cap = 0;
     // per-frame constants + counters
     FrameConst* d_fc = nullptr; FrameConst h_fc{};
+    // One host->device copy per pass call: [FrameConst | Mat4 models[n_actors] | float nmats[9 n_actors]] is staged in a
+    // ring of pinned slots (a slot is reused only after the copy that read it has completed) and lands in one device blob.
+    void* d_frame_blob = nullptr; size_t frame_blob_bytes = 0;
+    unsigned char* h_stage = nullptr; cudaEvent_t stage_ev[4]{}; unsigned stage_next = 0;
     Counters* d_counters = nullptr; Counters h_counters{};
     // timing
     cudaEvent_t ev[32]{}; vct_timings timings{};
@@ -193,13 +202,17 @@ static inline int level_dim(int D, int l) { int d = D >> l; return d < 1 ? 1 : d
 
 // pass entry points implemented across the .cu files (all enqueue on ctx->stream)
 int vctk_transform_vertices(vct_ctx*);
-int vctk_clear_voxels(vct_ctx*);
-int vctk_voxelize(vct_ctx*, bool occupancy);
+int vctk_clear_voxels(vct_ctx*, bool reset_frame_counters = false);   // true: the same launch zeroes VoxelizeInfo, the raster queues and cone_steps
+int vctk_voxelize(vct_ctx*, bool occupancy, bool counters_already_reset = false);
+void vctk_fill_models(vct_ctx*, Mat4* models, float* nmats);
 int vctk_transfer(vct_ctx*);
+int vctk_clear_masked(vct_ctx*);        // sparse frames: clear flagged segments of all three volumes, reset the new mask and the frame counters
+int vctk_transfer_masked(vct_ctx*);
+bool vctk_sparse_supported(const vct_ctx*);
 int vctk_inject(vct_ctx*);
 int vctk_fill_holes(vct_ctx*);
 int vctk_mip(vct_ctx*, int which, int mode, int publish);
-int vctk_mip_chains(vct_ctx*, int n, const int* which, const int* publish, int mode);
+int vctk_mip_chains(vct_ctx*, int n, const int* which, const int* publish, int mode, bool masked = false);
 int vctk_publish(vct_ctx*, int which);
 int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);

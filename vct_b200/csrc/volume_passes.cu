@@ -12,6 +12,7 @@
 // kernels move 16 bytes per thread per access (4 voxels) and are launched with enough CTAs to fill 148 SMs
 // several times over; grid-stride where the element count is large.
 #include <cuda_fp16.h>
+#include <string.h>
 
 #include "raster.cuh"
 
@@ -26,7 +27,15 @@ static inline int grid_for(size_t items, int threads, int max_waves = 16) {
 }
 
 // ------------------------------------------------------------------------------------------------ clear
-__global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4* __restrict__ b, size_t n16) {
+// `reset` (whole-frame entry points): the first thread also zeroes the per-frame counters — VoxelizeInfo
+// (glClearNamedBufferData, Application.cpp:581), the raster work queues and the cone-step count — which saves two memsets
+// and a one-thread kernel per frame.
+__global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4* __restrict__ b, size_t n16, Counters* __restrict__ reset) {
+    if (reset && blockIdx.x == 0 && threadIdx.x == 0) {
+        reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
+        reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
+        reset->cone_steps = 0ull;
+    }
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
         a[i] = z;
@@ -34,11 +43,81 @@ __global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4
     }
 }
 
+// Sparse frame: one thread = 4 consecutive segments (32 voxels, 128 bytes per volume).  Segments flagged in last frame's
+// mask are zeroed in voxelColor, voxelNormal and (unless the temporal filter keeps it) voxelRadiance; this frame's mask
+// starts empty (temporal: inherits, because the decaying radiance keeps its support).  Also resets the frame counters.
+__global__ void __launch_bounds__(kThreads) k_clear_masked(uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
+                                                           const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t n_words, int temporal,
+                                                           Counters* __restrict__ reset) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
+        reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
+        reset->cone_steps = 0ull;
+    }
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t flags = __ldg(seg_prev + t);
+        seg_cur[t] = temporal ? flags : 0u;
+        if (!flags) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (!(flags >> (8 * (j >> 1)) & 0xFFu)) continue;
+            color[8 * t + j] = z; normal[8 * t + j] = z;
+            if (!temporal) radiance[8 * t + j] = z;
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------------------- transfer
+// transferVoxels.comp:39-62 on four voxels (one 16-byte word group).  Returns true when voxelColor must be written back.
+__device__ __forceinline__ bool transfer_quad(uint4& cw, const uint4 pw, uint4& rw, float opacity, int temporal, float decay, unsigned& uniq, unsigned& maxfrag) {
+    uint32_t c[4] = {cw.x, cw.y, cw.z, cw.w};
+    uint32_t r[4] = {0, 0, 0, 0};
+    const uint32_t prev[4] = {pw.x, pw.y, pw.z, pw.w};
+    bool dirty = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // imageLoad -> float -> imageStore of an unchanged channel returns the same byte
+        // (round(b/255*255) == b), so only alpha needs arithmetic: transferVoxels.comp:39-50
+        const uint32_t a8 = c[k] >> 24;
+        float aw = 0.0f;
+        if (a8) {
+            uniq++;
+            aw = (float)a8 / 255.0f;
+            maxfrag = max(maxfrag, f2u_trunc(255.0f * aw));
+            if (opacity > 0.0f) aw = opacity;
+            c[k] = (c[k] & 0x00FFFFFFu) | unorm8(aw) << 24;
+            dirty = true;
+        }
+        if (temporal) {                                             // mix(prev, vec4(0,0,0,aw), 1 - decay), :55-62
+            const V4 p = unpack_unorm(prev[k]);
+            const float a = 1.0f - decay;
+            r[k] = pack_unorm(mk4(mixf(p.x, 0.0f, a), mixf(p.y, 0.0f, a), mixf(p.z, 0.0f, a), mixf(p.w, aw, a)));
+        } else if (aw > 0.0f) r[k] = unorm8(aw) << 24;
+    }
+    cw = make_uint4(c[0], c[1], c[2], c[3]); rw = make_uint4(r[0], r[1], r[2], r[3]);
+    return dirty;
+}
+// block reduction of the VoxelizeInfo counters -> one atomic pair per CTA
+__device__ __forceinline__ void transfer_counters(unsigned uniq, unsigned maxfrag, Counters* __restrict__ counters) {
+    __shared__ unsigned s_u[kThreads / 32], s_m[kThreads / 32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { uniq += __shfl_xor_sync(0xffffffffu, uniq, o); maxfrag = max(maxfrag, __shfl_xor_sync(0xffffffffu, maxfrag, o)); }
+    if ((threadIdx.x & 31) == 0) { s_u[threadIdx.x >> 5] = uniq; s_m[threadIdx.x >> 5] = maxfrag; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned u = 0, m = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { u += s_u[w]; m = max(m, s_m[w]); }
+        if (u) atomicAdd(&counters->unique_voxels, u);
+        if (m) atomicMax(&counters->max_fragments_per_voxel, m);
+    }
+}
 // One thread = 4 voxels (one 16-byte load of voxelColor).  Writes voxelColor back only where a fragment
 // landed; writes EVERY radiance voxel (0 where empty), which is the reference's clear + conditional store.
+// `seg_mark` (temporal filter, dense frame): segments whose decayed radiance is still non-zero are flagged in this frame's
+// mask, so that the mask bounds the radiance support and the next frame can be sparse.
 __global__ void __launch_bounds__(kThreads) k_transfer(uint4* __restrict__ color, uint4* __restrict__ radiance, size_t n16,
-                                                       float opacity, int temporal, float decay, Counters* __restrict__ counters) {
+                                                       float opacity, int temporal, float decay, Counters* __restrict__ counters, uint8_t* __restrict__ seg_mark) {
     unsigned uniq = 0, maxfrag = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n16; i0 += 2 * stride) {
@@ -52,51 +131,44 @@ __global__ void __launch_bounds__(kThreads) k_transfer(uint4* __restrict__ color
         for (int u = 0; u < 2; ++u) {
             if (u == 1 && !has1) break;
             const size_t i = u ? i1 : i0;
-            const uint4 cw = cws[u], pw = pws[u];
+            uint4 cw = cws[u]; const uint4 pw = pws[u];
             if ((cw.x | cw.y | cw.z | cw.w) == 0u) {                       // ~97 % of the grid: four empty voxels
                 if (!temporal) { radiance[i] = make_uint4(0, 0, 0, 0); continue; }      // = the reference's clear
                 if ((pw.x | pw.y | pw.z | pw.w) == 0u) continue;                        // mix(0, 0, a) = 0: already stored
             }
-            uint32_t c[4] = {cw.x, cw.y, cw.z, cw.w};
-            uint32_t r[4] = {0, 0, 0, 0};
-            const uint32_t prev[4] = {pw.x, pw.y, pw.z, pw.w};
-            bool dirty = false;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // imageLoad -> float -> imageStore of an unchanged channel returns the same byte
-                // (round(b/255*255) == b), so only alpha needs arithmetic: transferVoxels.comp:39-50
-                const uint32_t a8 = c[k] >> 24;
-                float aw = 0.0f;
-                if (a8) {
-                    uniq++;
-                    aw = (float)a8 / 255.0f;
-                    maxfrag = max(maxfrag, f2u_trunc(255.0f * aw));
-                    if (opacity > 0.0f) aw = opacity;
-                    c[k] = (c[k] & 0x00FFFFFFu) | unorm8(aw) << 24;
-                    dirty = true;
-                }
-                if (temporal) {                                             // mix(prev, vec4(0,0,0,aw), 1 - decay), :55-62
-                    const V4 p = unpack_unorm(prev[k]);
-                    const float a = 1.0f - decay;
-                    r[k] = pack_unorm(mk4(mixf(p.x, 0.0f, a), mixf(p.y, 0.0f, a), mixf(p.z, 0.0f, a), mixf(p.w, aw, a)));
-                } else if (aw > 0.0f) r[k] = unorm8(aw) << 24;
-            }
-            if (dirty) color[i] = make_uint4(c[0], c[1], c[2], c[3]);
-            radiance[i] = make_uint4(r[0], r[1], r[2], r[3]);
+            uint4 rw;
+            if (transfer_quad(cw, pw, rw, opacity, temporal, decay, uniq, maxfrag)) color[i] = cw;
+            radiance[i] = rw;
+            if (seg_mark && (rw.x | rw.y | rw.z | rw.w) != 0u) seg_mark[i >> 1] = 1;
         }
     }
-    // block reduction -> one atomic pair per CTA
-    __shared__ unsigned s_u[kThreads / 32], s_m[kThreads / 32];
+    transfer_counters(uniq, maxfrag, counters);
+}
+// Sparse frame: one thread = 4 consecutive segments (32 voxels) of the current mask.  Only flagged segments can hold a
+// fragment; their radiance was zeroed by k_clear_masked (non-temporal) or holds last frame's value (temporal).
+__global__ void __launch_bounds__(kThreads) k_transfer_masked(uint4* __restrict__ color, uint4* __restrict__ radiance, const uint32_t* __restrict__ seg, size_t n_words,
+                                                              float opacity, int temporal, float decay, Counters* __restrict__ counters) {
+    unsigned uniq = 0, maxfrag = 0;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t flags = __ldg(seg + t);
+        if (!flags) continue;
+        uint4 cws[8], pws[8];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { uniq += __shfl_xor_sync(0xffffffffu, uniq, o); maxfrag = max(maxfrag, __shfl_xor_sync(0xffffffffu, maxfrag, o)); }
-    if ((threadIdx.x & 31) == 0) { s_u[threadIdx.x >> 5] = uniq; s_m[threadIdx.x >> 5] = maxfrag; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned u = 0, m = 0;
-        for (int w = 0; w < kThreads / 32; ++w) { u += s_u[w]; m = max(m, s_m[w]); }
-        if (u) atomicAdd(&counters->unique_voxels, u);
-        if (m) atomicMax(&counters->max_fragments_per_voxel, m);
+        for (int j = 0; j < 8; ++j) {                                      // all loads of the flagged segments in flight first
+            cws[j] = pws[j] = make_uint4(0, 0, 0, 0);
+            if (flags >> (8 * (j >> 1)) & 0xFFu) { cws[j] = color[8 * t + j]; if (temporal) pws[j] = radiance[8 * t + j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (!(flags >> (8 * (j >> 1)) & 0xFFu)) continue;
+            uint4 cw = cws[j]; const uint4 pw = pws[j];
+            if ((cw.x | cw.y | cw.z | cw.w) == 0u && (!temporal || (pw.x | pw.y | pw.z | pw.w) == 0u)) continue;
+            uint4 rw;
+            if (transfer_quad(cw, pw, rw, opacity, temporal, decay, uniq, maxfrag)) color[8 * t + j] = cw;
+            radiance[8 * t + j] = rw;
+        }
     }
+    transfer_counters(uniq, maxfrag, counters);
 }
 
 // setVoxelOpacity.comp:18-35 (dead variant)
@@ -274,6 +346,64 @@ __global__ void __launch_bounds__(256) k_inject(const FrameConst* __restrict__ f
     }
 }
 
+// Linear voxel mapping (no warp mode), the case of every benchmark configuration.  Same IEEE results as k_inject with
+// about half the instructions: the three divisions by (max - min) of voxelLinearPosition (common.glsl:6-9) use the
+// host-rounded reciprocal and two FMA residual corrections — q0 = a*rc; q1 = q0 + (a - q0*c)*rc; q = q1 + (a - q1*c)*rc —
+// which is the correctly rounded quotient (Markstein; checked against a/c for every float mantissa), and
+// the warp-mode branches are gone.  Results that differ from a/c only for non-finite a are rejected by the bounds test
+// either way.
+struct InjectLinear {                                 // passed by value: no dependent loads of the frame constants
+    float rc[3], c[3], sub0[3], sub1[3];              // per axis: 1/(max-min), max-min, center, min
+    float m[16];                                      // ls_inverse, column-major
+    int S, log2_qx, D, z_lo, z_hi;
+};
+__device__ __forceinline__ float div_by_const(float a, float c, float rc) {
+    const float q0 = __fmul_rn(a, rc);
+    const float q1 = __fmaf_rn(__fmaf_rn(-q0, c, a), rc, q0);
+    return __fmaf_rn(__fmaf_rn(-q1, c, a), rc, q1);
+}
+__global__ void __launch_bounds__(256) k_inject_linear(const float* __restrict__ shadow, const uint32_t* __restrict__ color, uint32_t* __restrict__ radiance,
+                                                       const __grid_constant__ InjectLinear lin) {
+    const int S = lin.S, D = lin.D;
+    const float inv_s = 1.0f / (float)S, fd = (float)D;                     // exact: S is a power of two
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    const int x0 = (q & ((1 << lin.log2_qx) - 1)) * 4, y = q >> lin.log2_qx;
+    const float* row1 = shadow + (size_t)y * S + x0;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(row1));
+    const float bm1 = x0 > 0 ? __ldg(row1 - 1) : 1.0f;                      // CLAMP_TO_BORDER, border 1
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f); float am1 = 1.0f;
+    if (y > 0) { a = __ldg(reinterpret_cast<const float4*>(row1 - S)); if (x0 > 0) am1 = __ldg(row1 - S - 1); }
+    const float ta[5] = {am1, a.x, a.y, a.z, a.w}, tb[5] = {bm1, b.x, b.y, b.z, b.w};
+    const float* m = lin.m;
+    const float ny = ((float)y * inv_s) * 2.0f - 1.0f;
+    const float my0 = m[4] * ny, my1 = m[5] * ny, my2 = m[6] * ny;
+    const int z_lo = lin.z_lo, z_hi = lin.z_hi;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // shadow_linear() at the texel corner: weights 0.5/0.5 (k_inject), then injectRadiance.comp:46-52
+        const float top = ta[k] * 0.5f + ta[k + 1] * 0.5f, bot = tb[k] * 0.5f + tb[k + 1] * 0.5f;
+        const float d = top * 0.5f + bot * 0.5f;
+        const float nx = ((float)(x0 + k) * inv_s) * 2.0f - 1.0f, nz = d * 2.0f - 1.0f;
+        const float wx = ((m[0] * nx + my0) + m[8] * nz) + m[12];           // mul44 with w == 1
+        const float wy = ((m[1] * nx + my1) + m[9] * nz) + m[13];
+        const float wz = ((m[2] * nx + my2) + m[10] * nz) + m[14];
+        const float px = fd * div_by_const(wx - lin.sub0[0] - lin.sub1[0], lin.c[0], lin.rc[0]);
+        const float py = fd * div_by_const(wy - lin.sub0[1] - lin.sub1[1], lin.c[1], lin.rc[1]);
+        const float pz = fd * div_by_const(wz - lin.sub0[2] - lin.sub1[2], lin.c[2], lin.rc[2]);
+        int ix, iy, iz;
+        o[k] = 0xFFFFFFFFu;
+        if (to_voxel_index(mk3(px, py, pz), D, ix, iy, iz) && iz >= z_lo && iz < z_hi) o[k] = (uint32_t)((iz * D + iy) * D + ix);
+    }
+    uint32_t left = __shfl_up_sync(0xffffffffu, o[3], 1);
+    if ((threadIdx.x & 31) == 0) left = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (o[k] != 0xFFFFFFFFu && o[k] != left) radiance[o[k]] = __ldg(color + o[k]);     // packUnorm4x8(unpackUnorm4x8(c)) == c
+        left = o[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------- fill holes
 __global__ void __launch_bounds__(kThreads) k_fill_holes(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int D, int z_lo, int z_hi) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = z_lo + blockIdx.z;
@@ -353,6 +483,7 @@ struct MipChainArgs {
     MipChain chain[2]; int n_chains;              // radiance and colour pyramids filtered by one launch
     unsigned* ticket;                             // last-CTA detection for the tail levels
     int D, R, L, z0, nbz, tail;                   // tail: reduce levels R..L-2 -> R+1..L-1 in the last CTA
+    const uint8_t *seg_a, *seg_b;                 // sparse frames: this and last frame's segment masks (nullptr: dense)
 };
 __device__ __forceinline__ uint32_t box2_words(const uint32_t w[8], const float* __restrict__ lut) {
     if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0u) return 0u;
@@ -373,6 +504,25 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
     const int bx = blockIdx.x * B, by = blockIdx.y * B, bz = args.z0 + (blockIdx.z - which * args.nbz) * B;
     // ---- level 0 -> 1: one thread = 4 consecutive level-1 texels (8 x 16-byte loads, 1 x 16-byte store)
     const int qx = H >> 2, nquads = qx * H * H, D1 = D >> 1;
+    const bool masked = args.seg_a != nullptr;
+    bool block_active = !masked;
+    if (masked) {
+        // A thread's four source rows are four mask segments.  Unflagged (now and last frame) means: zero in the linear
+        // level, in the texture array, and in everything above it that this CTA would write.  A CTA with no flagged
+        // segment at all has nothing to read and nothing to change.
+        int any = 0;
+        for (int q = threadIdx.x; q < nquads; q += kMipThreads) {
+            const int lx = (q % qx) * 4, ly = (q / qx) % H, lz = q / (qx * H);
+            const int x0 = bx + 2 * lx, y0 = by + 2 * ly, z0 = bz + 2 * lz;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const size_t sidx = (((size_t)(z0 + (j & 1)) * D + y0 + (j >> 1)) * D + x0) >> 3;
+                any |= args.seg_a[sidx] | args.seg_b[sidx];
+            }
+        }
+        block_active = __syncthreads_or(any) != 0;
+    }
+    if (block_active) {
     for (int q = threadIdx.x; q < nquads; q += kMipThreads) {
         const int lx = (q % qx) * 4, ly = (q / qx) % H, lz = q / (qx * H);
         const int x0 = bx + 2 * lx, y0 = by + 2 * ly, z0 = bz + 2 * lz;
@@ -380,17 +530,27 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
         const uint4* r10 = reinterpret_cast<const uint4*>(a.src0 + ((size_t)z0 * D + y0 + 1) * D + x0);
         const uint4* r01 = reinterpret_cast<const uint4*>(a.src0 + ((size_t)(z0 + 1) * D + y0) * D + x0);
         const uint4* r11 = reinterpret_cast<const uint4*>(a.src0 + ((size_t)(z0 + 1) * D + y0 + 1) * D + x0);
+        bool f[4] = {true, true, true, true};                               // rows (y0,z0) (y0,z1) (y1,z0) (y1,z1)
+        if (masked) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const size_t sidx = (((size_t)(z0 + (j & 1)) * D + y0 + (j >> 1)) * D + x0) >> 3;
+                f[j] = (args.seg_a[sidx] | args.seg_b[sidx]) != 0;
+            }
+        }
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
         uint4 v[8];
-        v[0] = __ldg(r00); v[1] = __ldg(r00 + 1); v[2] = __ldg(r01); v[3] = __ldg(r01 + 1);
-        v[4] = __ldg(r10); v[5] = __ldg(r10 + 1); v[6] = __ldg(r11); v[7] = __ldg(r11 + 1);
+        v[0] = f[0] ? __ldg(r00) : zero4; v[1] = f[0] ? __ldg(r00 + 1) : zero4; v[2] = f[1] ? __ldg(r01) : zero4; v[3] = f[1] ? __ldg(r01 + 1) : zero4;
+        v[4] = f[2] ? __ldg(r10) : zero4; v[5] = f[2] ? __ldg(r10 + 1) : zero4; v[6] = f[3] ? __ldg(r11) : zero4; v[7] = f[3] ? __ldg(r11 + 1) : zero4;
         if (a.publish) {
             // Level 0 goes to the texture array only where it is non-zero now or was non-zero in the array (the
             // volume is ~97 % empty and surface stores are the slowest part of this kernel): array == linear always.
             uint8_t* m[4]; uint8_t was[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { m[j] = a.pub_mask + (((size_t)(z0 + (j & 1)) * D + y0 + (j >> 1)) * D + x0) / 8; was[j] = *m[j]; }   // loads in flight with v[]
+            for (int j = 0; j < 4; ++j) { m[j] = a.pub_mask + (((size_t)(z0 + (j & 1)) * D + y0 + (j >> 1)) * D + x0) / 8; was[j] = f[j] ? *m[j] : (uint8_t)0; }   // loads in flight with v[]
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                                   // rows (y0,z0) (y0,z1) (y1,z0) (y1,z1)
+                if (!f[j]) continue;
                 const int yy = y0 + (j >> 1), zz = z0 + (j & 1);
                 const uint4 p = v[2 * j], r = v[2 * j + 1];
                 const bool now = (p.x | p.y | p.z | p.w | r.x | r.y | r.z | r.w) != 0u;
@@ -410,8 +570,10 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
         }
         const uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
         const int gx = (bx >> 1) + lx, gy = (by >> 1) + ly, gz = (bz >> 1) + lz;
-        *reinterpret_cast<uint4*>(a.lvl[1] + ((size_t)gz * D1 + gy) * D1 + gx) = o;
-        if (a.publish) surf3Dwrite(o, a.surf[1], gx * 4, gy, gz);
+        if (f[0] || f[1] || f[2] || f[3]) {                                  // otherwise level 1 is, and stays, zero here
+            *reinterpret_cast<uint4*>(a.lvl[1] + ((size_t)gz * D1 + gy) * D1 + gx) = o;
+            if (a.publish) surf3Dwrite(o, a.surf[1], gx * 4, gy, gz);
+        }
         *reinterpret_cast<uint4*>(s1 + (lz * H + ly) * H + lx) = o;
     }
     // ---- levels 1 -> 2 -> ... -> R from shared memory
@@ -434,6 +596,7 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
             if (dsts) dsts[(lz * Hd + ly) * Hd + lx] = o;
         }
     }
+    }   // block_active
     // ---- tail: the last CTA reduces the remaining coarse levels (a few thousand texels) straight from L2
     if (!args.tail) return;
     __threadfence();
@@ -524,23 +687,67 @@ __global__ void __launch_bounds__(kThreads) k_publish(const uint32_t* __restrict
 }  // namespace
 
 // ============================================================================================ host side
-int vctk_clear_voxels(vct_ctx* c) {
+int vctk_clear_voxels(vct_ctx* c, bool reset_frame_counters) {
     // only this rank's z-slab of level 0 is cleared (single GPU: the whole volume)
     const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
-    k_clear<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_normal + off), n / 4);
+    k_clear<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_normal + off), n / 4,
+                                                                  reset_frame_counters ? c->d_counters : nullptr);
     VCT_LAUNCH_CHECK(c, "k_clear");
     return 0;
 }
 int vctk_transfer(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
     const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
+    // seg_mark is indexed like the volume: only valid for a whole-volume launch (off == 0, single GPU)
     k_transfer<<<grid_for(n / 8, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_radiance + off), n / 4,
-                                                                    p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters);
+                                                                    p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters,
+                                                                    (p.temporal_filter_radiance && c->cfg.world_size <= 1 && c->d_seg[c->seg_cur]) ? c->d_seg[c->seg_cur] : nullptr);
+    VCT_LAUNCH_CHECK(c, "k_transfer");
+    return 0;
+}
+// Sparse frames need whole segments per x-row, the fused mip-chain kernel with 16^3 blocks, and one GPU (the slab
+// exchange still moves dense levels).
+bool vctk_sparse_supported(const vct_ctx* c) {
+    return !c->seg_disabled && c->cfg.world_size <= 1 && c->D >= 16 && c->D % 16 == 0 && c->L >= 5 && c->d_seg[0] && c->d_seg[1];
+}
+int vctk_clear_masked(vct_ctx* c) {
+    const size_t n_words = (size_t)c->D * c->D * c->D / 32;
+    const int temporal = c->h_fc.p.temporal_filter_radiance;
+    k_clear_masked<<<grid_for(n_words, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_normal), reinterpret_cast<uint4*>(c->d_radiance),
+                                                                            reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), n_words,
+                                                                            temporal, c->d_counters);
+    VCT_LAUNCH_CHECK(c, "k_clear");
+    return 0;
+}
+int vctk_transfer_masked(vct_ctx* c) {
+    const vct_frame_params& p = c->h_fc.p;
+    const size_t n_words = (size_t)c->D * c->D * c->D / 32;
+    k_transfer_masked<<<grid_for(n_words, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_radiance),
+                                                                               reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), n_words,
+                                                                               p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_transfer");
     return 0;
 }
 int vctk_inject(vct_ctx* c) {
-    if ((c->S & (c->S - 1)) == 0 && c->S >= 32) {
+    const vct_frame_params& p = c->h_fc.p;
+    const bool pow2 = (c->S & (c->S - 1)) == 0 && c->S >= 32;
+    if (pow2 && !p.warp_voxels && !p.warp_texture && !p.radiance_lighting && c->D <= 1024) {
+        InjectLinear lin; bool sane = true;
+        for (int i = 0; i < 3; ++i) {
+            volatile float ext = p.voxel_max[i] - p.voxel_min[i];           // one fp32 rounding, like the shader's (max - min)
+            lin.c[i] = ext; lin.rc[i] = (float)(1.0 / (double)lin.c[i]); lin.sub0[i] = p.voxel_center[i]; lin.sub1[i] = p.voxel_min[i];
+            sane = sane && lin.c[i] > 1e-6f && lin.c[i] < 1e6f;            // well inside the normal range: no under/overflow in the corrections
+        }
+        if (sane) {
+            memcpy(lin.m, c->h_fc.ls_inverse.m, 64);
+            lin.S = c->S; lin.D = c->D; lin.z_lo = c->z_lo; lin.z_hi = c->z_hi;
+            lin.log2_qx = 0; while ((4 << lin.log2_qx) < c->S) lin.log2_qx++;
+            k_inject_linear<<<(unsigned)((size_t)c->S * c->S / 4 / 256), 256, 0, c->stream>>>(c->d_shadow, c->d_color, c->d_radiance, lin);
+            VCT_LAUNCH_CHECK(c, "k_inject");
+            return 0;
+        }
+    }
+    if (pow2) {
         k_inject<<<(unsigned)((size_t)c->S * c->S / 4 / 256), 256, 0, c->stream>>>(c->d_fc, c->d_shadow, c->d_color, c->d_normal, c->d_warpmap, c->d_radiance);
         VCT_LAUNCH_CHECK(c, "k_inject");
         return 0;
@@ -577,7 +784,7 @@ static int publish_levels(vct_ctx* c, int which, int l_begin, int l_end) {
 }
 // levels 1..L-1 (the reference's last loop iteration targets a non-existent level: Application.cpp:889-902) of up to
 // two pyramids.  publish[i] != 0 (single GPU): that pyramid also lands in the mipmapped array the cone tracer samples.
-int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, int mode) {
+int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, int mode, bool masked) {
     int publish[2] = {0, 0};
     uint32_t* base[2]; cudaSurfaceObject_t* surf[2];
     for (int i = 0; i < n; ++i) {
@@ -604,6 +811,7 @@ int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, 
         a.n_chains = n; a.D = c->D; a.R = R; a.L = c->L; a.z0 = c->z_lo;
         a.tail = c->cfg.world_size <= 1 && c->L - 1 > R;        // slabs keep one launch per remaining level (below)
         a.ticket = &c->d_counters->mip_ticket;
+        a.seg_a = masked && R == 4 ? c->d_seg[c->seg_cur] : nullptr; a.seg_b = masked && R == 4 ? c->d_seg[c->seg_cur ^ 1] : nullptr;
         const int B = 1 << R;
         a.nbz = (c->z_hi - c->z_lo) / B;
         dim3 grid(c->D / B, c->D / B, a.nbz * n);

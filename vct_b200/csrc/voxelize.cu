@@ -78,6 +78,7 @@ struct VoxArgs {
     VoxSetup* setups; unsigned setup_cap; TileQueues q;
     Frag* frags; unsigned frag_cap;
     uint32_t *color, *normal, *occ;
+    uint8_t* seg;             // segment mask of this frame (common.cuh): one byte per 8 voxels of an x-row
     Counters* counters;
 };
 
@@ -210,6 +211,7 @@ __device__ __forceinline__ void rgba8_avg_atomic(uint32_t* addr, float r, float 
 template <int MODE>
 __device__ __forceinline__ void store_fragment(const VoxArgs& a, const VoxSetup& S, const Shaded& sh, int D, int px, int py, int ix, int iy, int iz, uint32_t slot) {
     const uint32_t o = (uint32_t)(((size_t)iz * D + iy) * D + ix);
+    a.seg[o >> 3] = 1;                                                      // every writer stores the same byte
     if (MODE == MODE_SORTED) {
         if (slot >= a.frag_cap) { a.counters->overflow = 1u; return; }
         Frag f;
@@ -450,21 +452,21 @@ static void normal_matrix_host(const float* m, float n[9]) {
     n[6] = c20 / det; n[7] = c21 / det; n[8] = c22 / det;
 }
 
+// per-actor model and normal matrices of this frame, in the layout k_transform_vertices reads (uploaded by upload_frame)
+void vctk_fill_models(vct_ctx* c, Mat4* models, float* nmats) {
+    for (int a = 0; a < c->n_actors; ++a) { for (int i = 0; i < 16; ++i) models[a].m[i] = (i % 5 == 0) ? 1.0f : 0.0f; for (int i = 0; i < 9; ++i) nmats[9 * a + i] = (i % 4 == 0) ? 1.0f : 0.0f; }
+    for (auto& m : c->meshes) { models[m.actor] = m.model; normal_matrix_host(m.model.m, &nmats[9 * (size_t)m.actor]); }
+}
+
 int vctk_transform_vertices(vct_ctx* c) {
     if (!c->n_vertices) return 0;
-    std::vector<Mat4>& models = c->h_models; std::vector<float>& nm = c->h_nmats;
-    models.resize(c->n_actors); nm.resize((size_t)c->n_actors * 9);
-    for (auto& m : c->meshes) { models[m.actor] = m.model; normal_matrix_host(m.model.m, &nm[9 * (size_t)m.actor]); }
-    VCT_CHECK(c, cudaMemcpyAsync(c->d_models, models.data(), models.size() * sizeof(Mat4), cudaMemcpyHostToDevice, c->stream));
-    VCT_CHECK(c, cudaMemcpyAsync(c->d_nmats, nm.data(), nm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    vct_prof_mark(c, "h2d_params");
     const int grid = (int)std::min<size_t>((c->n_vertices + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_transform_vertices<<<grid, kThreads, 0, c->stream>>>(c->d_vertices, c->d_vactor, c->d_models, c->d_nmats, c->n_vertices, c->d_wpos, c->d_wnrm, c->d_wT, c->d_wB);
     VCT_LAUNCH_CHECK(c, "k_transform_vertices");
     return 0;
 }
 
-int vctk_voxelize(vct_ctx* c, bool occupancy) {
+int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset) {
     if (!c->n_tris) return 0;
     const vct_frame_params& p = c->h_fc.p;
     VoxArgs a{};
@@ -474,8 +476,8 @@ int vctk_voxelize(vct_ctx* c, bool occupancy) {
     a.setups = reinterpret_cast<VoxSetup*>(c->d_setup); a.setup_cap = (unsigned)c->setup_cap;
     a.q = vctk_tile_queues(c);
     a.frags = reinterpret_cast<Frag*>(c->d_frags); a.frag_cap = (unsigned)c->frag_cap;
-    a.color = c->d_color; a.normal = c->d_normal; a.occ = c->d_occ; a.counters = c->d_counters;
-    k_voxel_reset<<<1, 1, 0, c->stream>>>(c->d_counters); VCT_LAUNCH_CHECK(c, "k_voxel_reset");
+    a.color = c->d_color; a.normal = c->d_normal; a.occ = c->d_occ; a.counters = c->d_counters; a.seg = c->d_seg[c->seg_cur];
+    if (!counters_already_reset) { k_voxel_reset<<<1, 1, 0, c->stream>>>(c->d_counters); VCT_LAUNCH_CHECK(c, "k_voxel_reset"); }
     if (occupancy) {
         VCT_CHECK(c, cudaMemsetAsync(c->d_occ, 0, sizeof(uint32_t) * VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM, c->stream));
         vct_prof_mark(c, "memset");
