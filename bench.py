@@ -111,7 +111,7 @@ def algorithmic_bytes(D, L, S, W, H, T, F, U, chains):
     }
 
 
-VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_expand", "k_voxel_tiles", "k_voxel_pixels", "k_voxel_resolve_a",
+VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_expand", "k_voxel_tiles", "k_voxel_pixels", "k_voxel_resolve",
                     "k_voxel_resolve_b", "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_pixels_cas", "k_voxel_bin_max", "k_voxel_tiles_max", "k_voxel_pixels_max")
 
 

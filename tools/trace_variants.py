@@ -17,14 +17,18 @@ for v in variants:
     g = Pipeline(sc, D, bench.LEVELS, bench.SHADOW, W, H)
     g.frame(p); g.frame(p)
     g.set_profiling(2)
-    ts = []
+    ts, tf, tp = [], [], []
     for _ in range(frames):
         g.cone_trace(p); g.sync()
         ts.append(g.kernel_times()["k_cone_trace"][0] / 1e3)
+    for _ in range(frames):                      # inside whole GI steps: the voxel passes evict the trace's inputs from L2
+        g.gi_passes(p); g.sync()
+        kt = g.kernel_times()
+        tf.append(kt["k_cone_trace"][0] / 1e3); tp.append(kt.get("k_l2_prefetch", (0, 0))[0] / 1e3)
     img = g.read_image().view(np.uint8).reshape(-1, 4)[:, :3].astype(np.float64)
     if ref is None:
         ref = img
     mse = ((img - ref) ** 2).mean()
     psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
-    print(f"variant {v}: k_cone_trace median {statistics.median(ts):8.1f} us  min {min(ts):8.1f} us   PSNR vs first {psnr:6.2f} dB  steps {g.cone_steps()}", flush=True)
+    print(f"variant {v}: k_cone_trace standalone median {statistics.median(ts):8.1f} us  min {min(ts):8.1f} us | in GI step {statistics.median(tf):8.1f} us (+ prefetch {statistics.median(tp):5.1f} us)   PSNR vs first {psnr:6.2f} dB  steps {g.cone_steps()}", flush=True)
     g.close()

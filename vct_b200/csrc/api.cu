@@ -7,6 +7,8 @@
 
 #include <stdlib.h>
 
+#include <cstddef>
+
 #include "common.cuh"
 
 thread_local std::string g_create_error;
@@ -82,6 +84,17 @@ int make_volumes(vct_ctx* c) {
 int clamp_levels(int dim, int levels) {
     int lg = 0; while ((1 << (lg + 1)) <= dim) lg++;
     return std::min(std::max(levels, 1), std::min(lg + 1, VCT_MAX_LEVELS));
+}
+
+// Frame constants travel as a KERNEL PARAMETER when they fit (<= 8 actors: 3972 bytes): a copy-engine transfer in front
+// of the first kernel of a frame costs a copy->compute dependency (~10 us on B200), a one-block kernel does not.
+constexpr int kBlobActors = 8;
+struct FrameBlob { FrameConst fc; Mat4 models[kBlobActors]; float nmats[9 * kBlobActors]; };
+static_assert(sizeof(FrameBlob) <= 4096, "kernel parameter space");
+static_assert(sizeof(FrameConst) % 4 == 0 && sizeof(FrameBlob) % 4 == 0, "blob layout");
+__global__ void k_upload_frame(const __grid_constant__ FrameBlob blob, uint32_t* __restrict__ dst, int n_words) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&blob);
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
 }
 
 // device blob [FrameConst | models | nmats] + its pinned staging ring, sized for the current actor count
@@ -167,7 +180,20 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     f.n_lights = c->n_lights; std::memcpy(f.lights, c->h_lights, sizeof f.lights);
     f.z_lo = c->z_lo; f.z_hi = c->z_hi;
     build_schedule(f.sched_diffuse, p->diffuse_cone, c->L); build_schedule(f.sched_specular, p->specular_cone, c->L);
-    {   // one pinned, asynchronous copy: frame constants + per-actor matrices
+    if (c->n_actors <= kBlobActors) {                    // by value through the launch: no copy engine on the frame's critical path
+        static_assert(offsetof(FrameBlob, models) == sizeof(FrameConst), "blob layout");
+        FrameBlob b; b.fc = f;
+        std::vector<Mat4> models(std::max(c->n_actors, 1)); std::vector<float> nm((size_t)std::max(c->n_actors, 1) * 9);
+        vctk_fill_models(c, models.data(), nm.data());
+        // device layout is [FrameConst | models[n_actors] | nmats[9 n_actors]] (make_frame_blob): pack the same way
+        unsigned char* raw = reinterpret_cast<unsigned char*>(&b) + sizeof(FrameConst);
+        std::memcpy(raw, models.data(), (size_t)c->n_actors * sizeof(Mat4));
+        std::memcpy(raw + (size_t)c->n_actors * sizeof(Mat4), nm.data(), (size_t)c->n_actors * 36);
+        const int n_words = (int)((sizeof(FrameConst) + (size_t)c->n_actors * (sizeof(Mat4) + 36)) / 4);
+        k_upload_frame<<<1, 256, 0, c->stream>>>(b, reinterpret_cast<uint32_t*>(c->d_frame_blob), n_words);
+        c->launches++;
+        if (cudaGetLastError() != cudaSuccess) return fail(c, "k_upload_frame launch failed");
+    } else {   // one pinned, asynchronous copy: frame constants + per-actor matrices
         const unsigned slot = c->stage_next++ & 3u;
         VCT_CHECK(c, cudaEventSynchronize(c->stage_ev[slot]));               // the copy that last read this slot (4 calls ago) is done
         unsigned char* h = c->h_stage + (size_t)slot * c->frame_blob_bytes;
@@ -269,7 +295,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * 8) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
         alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
-        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
+        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
@@ -284,7 +310,7 @@ int vct_destroy(vct_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
-    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_warp_scratch,
+    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, (void*)c->d_warp_scratch,
                     c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_wpos,
                     (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})

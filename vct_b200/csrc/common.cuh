@@ -139,7 +139,7 @@ struct vct_ctx {
     // shadow map / visibility / image
     float* d_shadow = nullptr; unsigned long long* d_vis = nullptr; uint32_t* d_image = nullptr;
     // voxel fragments (per-voxel linked lists of the deterministic running average)
-    size_t frag_cap = 0; void* d_frags = nullptr;
+    size_t frag_cap = 0; void* d_frags = nullptr; uint8_t* d_displaced = nullptr;
     uint32_t* d_warp_scratch = nullptr;
     // raster work queue: 8-byte tile items + one setup record per queued (sub-)triangle
     void* d_tile_queue = nullptr; size_t tile_queue_cap = 0; void* d_expand_queue = nullptr; size_t expand_cap = 0;

@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int kThreads = 128;          // 4 warps = 32x4 pixels; ~164 registers/thread -> 3 CTAs (12 warps) per SM
+constexpr int kThreads = 128;          // default CTA: 4 warps = 32x4 pixels; 128 registers/thread -> 16 warps per SM
 __device__ const float kPI = 3.1415982f;                 // common.glsl:1 [sic]
 
 struct TraceArgs {
@@ -350,15 +350,16 @@ __device__ __forceinline__ LR cook_torrance(V3 dc, V3 lc, V3 N, V3 V, V3 L, V3 H
     return r;
 }
 
-template <int WM, bool SL, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) k_cone_trace(TraceArgs a) {
+// TPB threads per CTA (TPB/32 warps side by side, each an 8x4 pixel tile); 512/TPB CTAs per SM = 16 warps at 128 registers.
+template <int WM, bool SL, int TPB>
+__global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
     const FrameConst& fc = *a.fc;
     const vct_frame_params& fp = fc.p;
     __shared__ Schedule s_diffuse, s_specular;
     __shared__ float4 s_last[SL ? kLastTexels : 1];
     if (SL) {
         const int n = a.n_last;
-        for (int i = threadIdx.x; i < kLastTexels; i += kThreads) {
+        for (int i = threadIdx.x; i < kLastTexels; i += TPB) {
             const int x = i % kLastP - 1, y = (i / kLastP) % kLastP - 1, z = i / (kLastP * kLastP) - 1;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (x >= 0 && y >= 0 && z >= 0 && x < n && y < n && z < n) {
@@ -372,11 +373,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_cone_trace(TraceArgs a) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&fc.sched_diffuse);          // the two tables are adjacent
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_diffuse);
         static_assert(sizeof(Schedule) % 4 == 0, "schedule copy");
-        for (int i = threadIdx.x; i < (int)(sizeof(Schedule) / 4); i += kThreads) { dst[i] = __ldg(src + i); reinterpret_cast<uint32_t*>(&s_specular)[i] = __ldg(src + sizeof(Schedule) / 4 + i); }
+        for (int i = threadIdx.x; i < (int)(sizeof(Schedule) / 4); i += TPB) { dst[i] = __ldg(src + i); reinterpret_cast<uint32_t*>(&s_specular)[i] = __ldg(src + sizeof(Schedule) / 4 + i); }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int px = blockIdx.x * 32 + w * 8 + (lane & 7);
+    const int px = blockIdx.x * (TPB / 4) + w * 8 + (lane & 7);
     const int py = a.y_lo + blockIdx.y * 4 + (lane >> 3);
     unsigned fetches = 0;
     if (px < a.W && py < a.y_hi) {
@@ -519,6 +520,19 @@ __global__ void __launch_bounds__(kThreads, MINB) k_cone_trace(TraceArgs a) {
 
 }  // namespace
 
+// The shading preamble of every pixel walks visibility -> indices -> vertex attributes, all evicted from L2 by the voxel
+// passes of the same frame; a warp then waits on DRAM four dependent times with only 16 warps per SM to hide it.  One
+// prefetch.global.L2 per 128-byte line of those buffers (~40 MB, a few microseconds at HBM rate) right before the
+// trace turns the misses into L2 hits.
+struct PrefetchRanges { const char* p[8]; unsigned long long lines[8]; int n; };
+__global__ void __launch_bounds__(256) k_l2_prefetch(const __grid_constant__ PrefetchRanges r) {
+    for (int k = 0; k < r.n; ++k) {
+        const char* base = r.p[k];
+        for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < r.lines[k]; i += (unsigned long long)gridDim.x * 256ull)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 128ull));
+    }
+}
+
 // rows of the image buffer: H rounded up so that it splits into world_size equal bands of whole 8-row tiles
 size_t vctk_image_rows(const vct_ctx* c) {
     const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, rows8 = (c->H + 7) / 8;
@@ -539,27 +553,38 @@ int vctk_cone_trace(vct_ctx* c) {
     a.vol_last = rad ? c->radiance_tex_last : c->color_tex_last; a.warp = reinterpret_cast<const ushort4*>(c->d_warpmap);
     a.image = c->d_image; a.counters = c->d_counters;
     if (a.y_hi <= a.y_lo) return 0;
-    dim3 grid((c->W + 31) / 32, (a.y_hi - a.y_lo + 3) / 4);
+    if ((c->trace_variant & 8) && c->n_vertices) {               // VCT_TRACE_VARIANT bit 3: L2 prefetch (measured: -14 us in the trace, +13 us for itself: off)
+        PrefetchRanges r{};
+        auto add = [&](const void* p, size_t bytes) { if (p && bytes) { r.p[r.n] = (const char*)p; r.lines[r.n] = (bytes + 127) / 128; r.n++; } };
+        add(c->d_vis + (size_t)a.y_lo * c->W, (size_t)(a.y_hi - a.y_lo) * c->W * 8);
+        add(c->d_indices, c->n_tris * 12); add(c->d_trimat, c->n_tris * 4);
+        add(c->d_wpos, c->n_vertices * 16); add(c->d_wnrm, c->n_vertices * 16); add(c->d_wT, c->n_vertices * 16); add(c->d_wB, c->n_vertices * 16);
+        add(c->d_vertices, c->n_vertices * 56);
+        k_l2_prefetch<<<VCT_SM_COUNT * 8, 256, 0, c->stream>>>(r);
+        VCT_LAUNCH_CHECK(c, "k_l2_prefetch");
+    }
     const vct_frame_params& p = c->h_fc.p;
     // the coarsest level goes to shared memory when it fits (edge <= 8: 256^3 with 6 levels, 128^3 with 5, ...)
     a.n_last = level_dim(c->D, c->L - 1);
     a.last_level = (rad ? c->d_radiance : c->d_color) + c->level_off[c->L - 1];
-    const int variant = c->trace_variant;          // tuning knob (VCT_TRACE_VARIANT): bit 0 = shared-memory last level (measured slower, off), bits 1-2 = CTAs/SM target
+    // tuning knobs (VCT_TRACE_VARIANT): bit 0 = shared-memory last level (measured slower, off), bit 3 = L2 prefetch (off),
+    // bits 4-5 = CTA size 128 / 64 / 32 threads
+    const int variant = c->trace_variant;
     const bool sl = a.n_last <= kLastMax && (variant & 1) && !p.warp_voxels;
-    const int occ = (variant >> 1) & 3;
-#define VCT_TRACE(WM)                                                                                          \
+    const int tpb = ((variant >> 4) & 3) == 1 ? 64 : ((variant >> 4) & 3) == 2 ? 32 : kThreads;
+    dim3 grid((c->W + tpb / 4 - 1) / (tpb / 4), (a.y_hi - a.y_lo + 3) / 4);
+#define VCT_TRACE2(WM, SLV)                                                                                    \
     do {                                                                                                       \
-        if (sl) { if (occ == 1) k_cone_trace<WM, true, 3><<<grid, kThreads, 0, c->stream>>>(a);                \
-                  else if (occ == 2) k_cone_trace<WM, true, 5><<<grid, kThreads, 0, c->stream>>>(a);           \
-                  else k_cone_trace<WM, true, 4><<<grid, kThreads, 0, c->stream>>>(a); }                       \
-        else    { if (occ == 1) k_cone_trace<WM, false, 3><<<grid, kThreads, 0, c->stream>>>(a);               \
-                  else if (occ == 2) k_cone_trace<WM, false, 5><<<grid, kThreads, 0, c->stream>>>(a);          \
-                  else k_cone_trace<WM, false, 4><<<grid, kThreads, 0, c->stream>>>(a); }                      \
+        if (tpb == 64) k_cone_trace<WM, SLV, 64><<<grid, 64, 0, c->stream>>>(a);                               \
+        else if (tpb == 32) k_cone_trace<WM, SLV, 32><<<grid, 32, 0, c->stream>>>(a);                          \
+        else k_cone_trace<WM, SLV, kThreads><<<grid, kThreads, 0, c->stream>>>(a);                             \
     } while (0)
+#define VCT_TRACE(WM) do { if (sl) VCT_TRACE2(WM, true); else VCT_TRACE2(WM, false); } while (0)
     if (p.warp_voxels) VCT_TRACE(WARP_VOXELS);
     else if (p.warp_texture) VCT_TRACE(WARP_TEXTURE);
     else VCT_TRACE(WARP_NONE);
 #undef VCT_TRACE
+#undef VCT_TRACE2
     VCT_LAUNCH_CHECK(c, "k_cone_trace");
     return 0;
 }

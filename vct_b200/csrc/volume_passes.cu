@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(kThreads) k_clear_masked(uint4* __restrict__ c
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (!(flags >> (8 * (j >> 1)) & 0xFFu)) continue;
-            color[8 * t + j] = z; normal[8 * t + j] = z;
-            if (!temporal) radiance[8 * t + j] = z;
+            __stcs(color + 8 * t + j, z); __stcs(normal + 8 * t + j, z);
+            if (!temporal) __stcs(radiance + 8 * t + j, z);
         }
     }
 }
@@ -144,29 +144,39 @@ __global__ void __launch_bounds__(kThreads) k_transfer(uint4* __restrict__ color
     }
     transfer_counters(uniq, maxfrag, counters);
 }
-// Sparse frame: one thread = 4 consecutive segments (32 voxels) of the current mask.  Only flagged segments can hold a
-// fragment; their radiance was zeroed by k_clear_masked (non-temporal) or holds last frame's value (temporal).
+// Sparse frame.  A warp scans 32 mask words (128 segments), compacts the flagged segments into a shared list, and then
+// works through their 16-byte quads with all lanes (about one segment in ten is flagged: without the compaction most
+// lanes would idle behind the few that found work).  Only flagged segments can hold a fragment; their radiance was
+// zeroed by k_clear_masked (non-temporal) or holds last frame's value (temporal).
 __global__ void __launch_bounds__(kThreads) k_transfer_masked(uint4* __restrict__ color, uint4* __restrict__ radiance, const uint32_t* __restrict__ seg, size_t n_words,
                                                               float opacity, int temporal, float decay, Counters* __restrict__ counters) {
+    __shared__ uint32_t s_list[kThreads / 32][128];
     unsigned uniq = 0, maxfrag = 0;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t flags = __ldg(seg + t);
-        if (!flags) continue;
-        uint4 cws[8], pws[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t n_round = (n_words + 31) & ~(size_t)31;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_round; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t flags = t < n_words ? __ldg(seg + t) : 0u;
+        const unsigned nz = (flags & 0xFFu ? 1u : 0u) | (flags & 0xFF00u ? 2u : 0u) | (flags & 0xFF0000u ? 4u : 0u) | (flags & 0xFF000000u ? 8u : 0u);
+        int inc = __popc(nz);
+        const int mine = inc;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                                      // all loads of the flagged segments in flight first
-            cws[j] = pws[j] = make_uint4(0, 0, 0, 0);
-            if (flags >> (8 * (j >> 1)) & 0xFFu) { cws[j] = color[8 * t + j]; if (temporal) pws[j] = radiance[8 * t + j]; }
-        }
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (!total) continue;
+        int pos = inc - mine;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (!(flags >> (8 * (j >> 1)) & 0xFFu)) continue;
-            uint4 cw = cws[j]; const uint4 pw = pws[j];
+        for (int j = 0; j < 4; ++j) if (nz >> j & 1u) s_list[w][pos++] = (uint32_t)(4 * t + j);
+        __syncwarp();
+        for (int q = lane; q < 2 * total; q += 32) {
+            const size_t i = 2 * (size_t)s_list[w][q >> 1] + (q & 1);
+            uint4 cw = __ldcs(color + i);
+            const uint4 pw = temporal ? __ldcs(radiance + i) : make_uint4(0, 0, 0, 0);
             if ((cw.x | cw.y | cw.z | cw.w) == 0u && (!temporal || (pw.x | pw.y | pw.z | pw.w) == 0u)) continue;
             uint4 rw;
-            if (transfer_quad(cw, pw, rw, opacity, temporal, decay, uniq, maxfrag)) color[8 * t + j] = cw;
-            radiance[8 * t + j] = rw;
+            if (transfer_quad(cw, pw, rw, opacity, temporal, decay, uniq, maxfrag)) color[i] = cw;
+            radiance[i] = rw;
         }
+        __syncwarp();
     }
     transfer_counters(uniq, maxfrag, counters);
 }
@@ -356,6 +366,7 @@ struct InjectLinear {                                 // passed by value: no dep
     float rc[3], c[3], sub0[3], sub1[3];              // per axis: 1/(max-min), max-min, center, min
     float m[16];                                      // ls_inverse, column-major
     int S, log2_qx, D, z_lo, z_hi;
+    int skip_far;                                     // the light's far plane (depth 1 = nothing rendered) misses the volume by > 1 voxel
 };
 __device__ __forceinline__ float div_by_const(float a, float c, float rc) {
     const float q0 = __fmul_rn(a, rc);
@@ -369,11 +380,14 @@ __global__ void __launch_bounds__(256) k_inject_linear(const float* __restrict__
     const int q = blockIdx.x * 256 + threadIdx.x;
     const int x0 = (q & ((1 << lin.log2_qx) - 1)) * 4, y = q >> lin.log2_qx;
     const float* row1 = shadow + (size_t)y * S + x0;
-    const float4 b = __ldg(reinterpret_cast<const float4*>(row1));
-    const float bm1 = x0 > 0 ? __ldg(row1 - 1) : 1.0f;                      // CLAMP_TO_BORDER, border 1
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(row1));        // one-touch stream: evict first, keep L2 for the cone tracer's inputs
+    const float bm1 = x0 > 0 ? __ldcs(row1 - 1) : 1.0f;                      // CLAMP_TO_BORDER, border 1
     float4 a = make_float4(1.f, 1.f, 1.f, 1.f); float am1 = 1.0f;
-    if (y > 0) { a = __ldg(reinterpret_cast<const float4*>(row1 - S)); if (x0 > 0) am1 = __ldg(row1 - S - 1); }
+    if (y > 0) { a = __ldcs(reinterpret_cast<const float4*>(row1 - S)); if (x0 > 0) am1 = __ldcs(row1 - S - 1); }
     const float ta[5] = {am1, a.x, a.y, a.z, a.w}, tb[5] = {bm1, b.x, b.y, b.z, b.w};
+    // Texels that saw no geometry (all four depths exactly 1) unproject onto the far plane; when the host has shown that
+    // plane to lie outside the volume, the bounds test below would reject them anyway.
+    if (lin.skip_far && fminf(fminf(fminf(am1, bm1), fminf(fminf(a.x, a.y), fminf(a.z, a.w))), fminf(fminf(b.x, b.y), fminf(b.z, b.w))) == 1.0f) return;
     const float* m = lin.m;
     const float ny = ((float)y * inv_s) * 2.0f - 1.0f;
     const float my0 = m[4] * ny, my1 = m[5] * ny, my2 = m[6] * ny;
@@ -496,8 +510,7 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
     __shared__ float lut[256];
     __shared__ uint32_t s1[8 * 8 * 8], s2[4 * 4 * 4], s3[2 * 2 * 2];
     __shared__ unsigned s_last;
-    lut[threadIdx.x] = (float)threadIdx.x / 255.0f; lut[threadIdx.x + 128] = (float)(threadIdx.x + 128) / 255.0f;
-    __syncthreads();
+    lut[threadIdx.x] = (float)threadIdx.x / 255.0f; lut[threadIdx.x + 128] = (float)(threadIdx.x + 128) / 255.0f;   // visible after the first barrier below
     const int which = blockIdx.z / args.nbz;
     const MipChain& a = args.chain[which];
     const int B = 1 << args.R, H = B >> 1, D = args.D;
@@ -521,7 +534,7 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
             }
         }
         block_active = __syncthreads_or(any) != 0;
-    }
+    } else __syncthreads();
     if (block_active) {
     for (int q = threadIdx.x; q < nquads; q += kMipThreads) {
         const int lx = (q % qx) * 4, ly = (q / qx) % H, lz = q / (qx * H);
@@ -540,8 +553,8 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
         }
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
         uint4 v[8];
-        v[0] = f[0] ? __ldg(r00) : zero4; v[1] = f[0] ? __ldg(r00 + 1) : zero4; v[2] = f[1] ? __ldg(r01) : zero4; v[3] = f[1] ? __ldg(r01 + 1) : zero4;
-        v[4] = f[2] ? __ldg(r10) : zero4; v[5] = f[2] ? __ldg(r10 + 1) : zero4; v[6] = f[3] ? __ldg(r11) : zero4; v[7] = f[3] ? __ldg(r11 + 1) : zero4;
+        v[0] = f[0] ? __ldcs(r00) : zero4; v[1] = f[0] ? __ldcs(r00 + 1) : zero4; v[2] = f[1] ? __ldcs(r01) : zero4; v[3] = f[1] ? __ldcs(r01 + 1) : zero4;
+        v[4] = f[2] ? __ldcs(r10) : zero4; v[5] = f[2] ? __ldcs(r10 + 1) : zero4; v[6] = f[3] ? __ldcs(r11) : zero4; v[7] = f[3] ? __ldcs(r11 + 1) : zero4;
         if (a.publish) {
             // Level 0 goes to the texture array only where it is non-zero now or was non-zero in the array (the
             // volume is ~97 % empty and surface stores are the slowest part of this kernel): array == linear always.
@@ -599,7 +612,7 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
     }   // block_active
     // ---- tail: the last CTA reduces the remaining coarse levels (a few thousand texels) straight from L2
     if (!args.tail) return;
-    __threadfence();
+    if (block_active) __threadfence();                                     // an inactive CTA wrote nothing
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned total = gridDim.x * gridDim.y * gridDim.z;
@@ -742,6 +755,19 @@ int vctk_inject(vct_ctx* c) {
             memcpy(lin.m, c->h_fc.ls_inverse.m, 64);
             lin.S = c->S; lin.D = c->D; lin.z_lo = c->z_lo; lin.z_hi = c->z_hi;
             lin.log2_qx = 0; while ((4 << lin.log2_qx) < c->S) lin.log2_qx++;
+            {   // far plane (ndc z = 1) of the light frustum in voxel coordinates: affine image of a quad, extremes at the corners
+                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+                for (int k = 0; k < 4; ++k) {
+                    const double nx = (k & 1) ? 1.0 : -1.0, ny = (k & 2) ? 1.0 : -1.0;
+                    for (int i = 0; i < 3; ++i) {
+                        const double w = lin.m[i] * nx + lin.m[4 + i] * ny + lin.m[8 + i] + lin.m[12 + i];
+                        const double v = (w - lin.sub0[i] - lin.sub1[i]) / lin.c[i] * c->D;
+                        lo[i] = std::min(lo[i], v); hi[i] = std::max(hi[i], v);
+                    }
+                }
+                lin.skip_far = 0;
+                for (int i = 0; i < 3; ++i) if (hi[i] < -2.0 || lo[i] > c->D + 2.0) lin.skip_far = 1;      // (NaN compares false: no skip)
+            }
             k_inject_linear<<<(unsigned)((size_t)c->S * c->S / 4 / 256), 256, 0, c->stream>>>(c->d_shadow, c->d_color, c->d_radiance, lin);
             VCT_LAUNCH_CHECK(c, "k_inject");
             return 0;

@@ -10,22 +10,20 @@
 //                         are cut into 8x4-pixel tiles (trivially rejected tiles skipped) pushed to a work queue.
 //   k_voxel_tiles         persistent grid, one warp per tile, ONE LANE PER PIXEL: coverage, voxel index,
 //                         voxelize.frag:186-280 shading, then the image atomic of the selected mode
-//   k_voxel_resolve_a/_b  deterministic running average only (see below)
+//   k_voxel_resolve       deterministic running average only (see below)
 //
 // Deterministic running average.  imageAtomicRGBA8Avg (voxelize.frag:111-139) truncates on every insertion, so
 // the result depends on insertion order; the oracle fixes the canonical order "triangles in draw order,
 // fragments of a triangle in raster-scan order".  Instead of sorting all fragments globally, every fragment is
 // appended to a per-voxel linked list (head pointers live in the cleared voxelColor volume, one atomicExch per
-// fragment); resolve_a lets the thread that owns a voxel's head walk its list (Sponza: <= 10 entries), order
-// it by (triangle, raster rank) in registers and replay the insertions sequentially; resolve_b scatters the final
-// words.  Two kernels because resolve_a identifies heads by reading voxelColor, which resolve_b overwrites.
+// fragment); k_voxel_resolve lets the thread that owns a voxel's head walk its list (Sponza: <= 10 entries), order
+// it by (triangle, raster rank) in registers, replay the insertions sequentially and store the final words.
 #include "raster.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kInlineArea = 4;                   // bounding boxes up to this many pixels are rasterised by the bin thread
-constexpr unsigned kHeadFlag = 0x80000000u;
 enum { MODE_SORTED = 0, MODE_CAS = 1, MODE_MAX = 2, MODE_OCC = 3 };
 
 // ------------------------------------------------------------------------------------ vertex transform
@@ -51,16 +49,20 @@ __global__ void __launch_bounds__(kThreads) k_transform_vertices(const float* __
 
 // ------------------------------------------------------------------------------------------- per-triangle
 // What a tile needs to know about its triangle (written once by k_voxel_bin, broadcast-loaded by the tile warp).
-struct __align__(16) VoxSetup {
+struct ShadeIn { V3 w[3], n[3]; float uv[3][2]; };          // world position, normalMatrix*normal, uv per source vertex (96 B)
+struct __align__(16) VoxHead {  // what coverage and the voxel index need: 128 B, broadcast-loaded as 8 x 16 bytes
     TriSetup s;               // 80 B
     float cvx[3], cvy[3];     // clip-space x,y per source vertex (w == 1 for the orthographic views; z is s.z)
     uint32_t tri; int axis; int material; float rho2;
     uint32_t pad[2];
 };
-static_assert(sizeof(VoxSetup) == 128, "VoxSetup is broadcast-loaded as 8 x 16 bytes");
+struct __align__(16) VoxSetup : VoxHead {
+    ShadeIn in;               // shading inputs, gathered once by the bin thread: tile warps see no dependent vertex loads
+};                            // and fetch them (6 x 16 bytes) only when the tile has a fragment
+static_assert(sizeof(VoxHead) == 128 && sizeof(VoxSetup) == 224, "VoxSetup layout");
 
 struct __align__(16) Frag {   // 48 B
-    uint32_t key;             // voxel index (bit 31: set by resolve_a on the fragment that owns the voxel's head)
+    uint32_t key;             // voxel index
     uint32_t tri, rank;       // canonical order: draw index, then py*D+px
     uint32_t next;            // index+1 of the next fragment of the same voxel, 0 = end
     float cr, cg, cb; uint32_t cw;      // shaded colour      | final packed colour word (head only)
@@ -76,7 +78,7 @@ struct VoxArgs {
     const float4 *wpos, *wnrm;
     const DevTexture* tex; const DevMaterial* mats; const float* shadow; const uint16_t* warpmap;
     VoxSetup* setups; unsigned setup_cap; TileQueues q;
-    Frag* frags; unsigned frag_cap;
+    Frag* frags; unsigned frag_cap; uint8_t* displaced;       // displaced[slot] = 1: a later fragment took over the head of that voxel's list
     uint32_t *color, *normal, *occ;
     uint8_t* seg;             // segment mask of this frame (common.cuh): one byte per 8 voxels of an x-row
     Counters* counters;
@@ -87,6 +89,7 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
     const uint32_t i0 = __ldg(a.indices + 3 * (size_t)t), i1 = __ldg(a.indices + 3 * (size_t)t + 1), i2 = __ldg(a.indices + 3 * (size_t)t + 2);
     const V3 w[3] = {ld3(a.wpos, i0), ld3(a.wpos, i1), ld3(a.wpos, i2)};
     const V3 n0 = ld3(a.wnrm, i0), n1 = ld3(a.wnrm, i1), n2 = ld3(a.wnrm, i2);
+    S.in.w[0] = w[0]; S.in.w[1] = w[1]; S.in.w[2] = w[2]; S.in.n[0] = n0; S.in.n[1] = n1; S.in.n[2] = n2;
     const V3 f = normalize3((n0 + n1) + n2);
     const float ax = fabsf(f.x), ay = fabsf(f.y), az = fabsf(f.z);
     int axis;
@@ -105,20 +108,20 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
 // texture LOD input of the triangle (voxelize.frag:197 implicit derivatives; affine in an orthographic view)
 __device__ __forceinline__ void make_shading_setup(const VoxArgs& a, VoxSetup& S) {
     S.material = __ldg(a.trimat + S.tri);
-    const int dt = a.mats[S.material].diffuse_tex;
-    if (dt < 0) return;
-    RV cv[3]; float uv[3][2];
+    RV cv[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const uint32_t vi = __ldg(a.indices + 3 * (size_t)S.tri + k);
-        uv[k][0] = __ldg(a.verts + 14 * (size_t)vi + 6); uv[k][1] = __ldg(a.verts + 14 * (size_t)vi + 7);
+        S.in.uv[k][0] = __ldg(a.verts + 14 * (size_t)vi + 6); S.in.uv[k][1] = __ldg(a.verts + 14 * (size_t)vi + 7);
         cv[k].x = S.cvx[k]; cv[k].y = S.cvy[k]; cv[k].z = S.s.z[k]; cv[k].w = 1.0f;
     }
-    S.rho2 = tri_rho2_affine(cv, uv, a.D, a.D, a.tex[dt]);
+    const int dt = a.mats[S.material].diffuse_tex;
+    if (dt < 0) return;
+    S.rho2 = tri_rho2_affine(cv, S.in.uv, a.D, a.D, a.tex[dt]);
 }
 
 // voxelize.frag:79-108
-__device__ __forceinline__ bool frag_voxel(const FrameConst& fc, const VoxSetup& S, const float l[3], int D, const uint16_t* __restrict__ warpmap, bool occupancy,
+__device__ __forceinline__ bool frag_voxel(const FrameConst& fc, const VoxHead& S, const float l[3], int D, const uint16_t* __restrict__ warpmap, bool occupancy,
                                            int& ix, int& iy, int& iz) {
     const V3 ndc = mk3(interp1(l, S.cvx[0], S.cvx[1], S.cvx[2]), interp1(l, S.cvy[0], S.cvy[1], S.cvy[2]), interp1(l, S.s.z[0], S.s.z[1], S.s.z[2]));
     V3 u = mk3((ndc.x + 1.0f) * 0.5f, (ndc.y + 1.0f) * 0.5f, (ndc.z + 1.0f) * 0.5f);
@@ -130,7 +133,7 @@ __device__ __forceinline__ bool frag_voxel(const FrameConst& fc, const VoxSetup&
     return to_voxel_index(mk3((float)D * u.x, (float)D * u.y, (float)D * u.z), D, ix, iy, iz);
 }
 // fragment exists (coverage + near/far clip) and belongs to this rank's slab
-__device__ __forceinline__ bool frag_test(const FrameConst& fc, const VoxSetup& S, int px, int py, int D, const uint16_t* __restrict__ warpmap, bool occupancy,
+__device__ __forceinline__ bool frag_test(const FrameConst& fc, const VoxHead& S, int px, int py, int D, const uint16_t* __restrict__ warpmap, bool occupancy,
                                           float l[3], bool& oob, int& ix, int& iy, int& iz) {
     if (!tri_cover(S.s, px, py, l)) return false;
     const float z = interp1(l, S.s.z[0], S.s.z[1], S.s.z[2]);
@@ -140,18 +143,9 @@ __device__ __forceinline__ bool frag_test(const FrameConst& fc, const VoxSetup& 
     return iz >= fc.z_lo && iz < fc.z_hi;
 }
 
-struct ShadeIn { V3 w[3], n[3]; float uv[3][2]; };
-__device__ __forceinline__ void load_shade_in(const VoxArgs& a, uint32_t t, ShadeIn& I) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const uint32_t vi = __ldg(a.indices + 3 * (size_t)t + k);
-        I.w[k] = ld3(a.wpos, vi); I.n[k] = ld3(a.wnrm, vi);
-        I.uv[k][0] = __ldg(a.verts + 14 * (size_t)vi + 6); I.uv[k][1] = __ldg(a.verts + 14 * (size_t)vi + 7);
-    }
-}
 struct Shaded { V3 color, nenc; };
 // voxelize.frag:195-228
-__device__ __forceinline__ Shaded shade_fragment(const FrameConst& fc, const VoxSetup& S, const ShadeIn& I, const float l[3], const DevTexture* __restrict__ tex,
+__device__ __forceinline__ Shaded shade_fragment(const FrameConst& fc, const VoxHead& S, const ShadeIn& I, const float l[3], const DevTexture* __restrict__ tex,
                                                  const DevMaterial* __restrict__ mats, const float* __restrict__ shadow) {
     const V3 wp = interp3(l, I.w[0], I.w[1], I.w[2]);
     const V3 nn = interp3(l, I.n[0], I.n[1], I.n[2]);
@@ -209,7 +203,7 @@ __device__ __forceinline__ void rgba8_avg_atomic(uint32_t* addr, float r, float 
 
 // the image atomic of the selected mode; `slot` is the fragment record reserved for MODE_SORTED
 template <int MODE>
-__device__ __forceinline__ void store_fragment(const VoxArgs& a, const VoxSetup& S, const Shaded& sh, int D, int px, int py, int ix, int iy, int iz, uint32_t slot) {
+__device__ __forceinline__ void store_fragment(const VoxArgs& a, const VoxHead& S, const Shaded& sh, int D, int px, int py, int ix, int iy, int iz, uint32_t slot) {
     const uint32_t o = (uint32_t)(((size_t)iz * D + iy) * D + ix);
     a.seg[o >> 3] = 1;                                                      // every writer stores the same byte
     if (MODE == MODE_SORTED) {
@@ -217,9 +211,13 @@ __device__ __forceinline__ void store_fragment(const VoxArgs& a, const VoxSetup&
         Frag f;
         f.key = o; f.tri = S.tri; f.rank = (uint32_t)(py * D + px);
         f.next = atomicExch(a.color + o, slot + 1u);                       // push on the voxel's list
+        if (f.next) a.displaced[f.next - 1u] = 1;                          // the previous head is no head any more
         f.cr = sh.color.x; f.cg = sh.color.y; f.cb = sh.color.z; f.cw = 0u;
         f.nr = sh.nenc.x; f.ng = sh.nenc.y; f.nb = sh.nenc.z; f.nw = 0u;
-        a.frags[slot] = f;
+        {   // streaming store of the 48-byte record (read once by k_voxel_resolve)
+            const uint4* src = reinterpret_cast<const uint4*>(&f); uint4* dst = reinterpret_cast<uint4*>(a.frags + slot);
+            __stcs(dst, src[0]); __stcs(dst + 1, src[1]); __stcs(dst + 2, src[2]);
+        }
     } else if (MODE == MODE_CAS) {
         rgba8_avg_atomic(a.color + o, sh.color.x, sh.color.y, sh.color.z);
         rgba8_avg_atomic(a.normal + o, sh.nenc.x, sh.nenc.y, sh.nenc.z);
@@ -231,7 +229,7 @@ __device__ __forceinline__ void store_fragment(const VoxArgs& a, const VoxSetup&
 
 // ------------------------------------------------------------------------------------------------- bin
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_voxel_bin(VoxArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
     const FrameConst& fc = *a.fc;
     const int D = a.D, lane = threadIdx.x & 31;
     const bool occupancy = MODE == MODE_OCC;
@@ -291,16 +289,16 @@ __global__ void __launch_bounds__(kThreads) k_voxel_bin(VoxArgs a) {
 
 // ----------------------------------------------------------------------------------------------- tiles
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) k_voxel_tiles(VoxArgs a) {
+__device__ __forceinline__ void voxel_tiles_part(const VoxArgs& a, unsigned block, unsigned n_blocks) {
     const FrameConst& fc = *a.fc;
     const int D = a.D, lane = threadIdx.x & 31;
     const bool occupancy = MODE == MODE_OCC;
     const unsigned n_items = min(*a.q.tile_count, a.q.tile_cap);
-    const unsigned warps = gridDim.x * (kThreads / 32);
+    const unsigned warps = n_blocks * (kThreads / 32);
     unsigned counted = 0;
-    for (unsigned item = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); item < n_items; item += warps) {
+    for (unsigned item = block * (kThreads / 32) + (threadIdx.x >> 5); item < n_items; item += warps) {
         const uint2 it = __ldg(a.q.tiles + item);
-        const VoxSetup S = a.setups[it.x];                                  // same address in every lane: broadcast
+        const VoxHead S = a.setups[it.x];                                   // same address in every lane: broadcast
         const int px = (int)(it.y & 0xFFFFu) + (lane & (kTileW - 1)), py = (int)(it.y >> 16) + (lane >> 3);
         float l[3]; bool oob = false; int ix = 0, iy = 0, iz = 0;
         const bool frag = px <= S.s.x1 && py <= S.s.y1 && frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
@@ -314,8 +312,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_voxel_tiles(VoxArgs a) {
             if (lane == 0) base = atomicAdd(&a.counters->n_frag_slots, (unsigned)__popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
         }
-        ShadeIn I; load_shade_in(a, S.tri, I);                              // uniform addresses: broadcast loads
         if (hit) {
+            const ShadeIn I = a.setups[it.x].in;
             const Shaded sh = shade_fragment(fc, S, I, l, a.tex, a.mats, a.shadow);
             store_fragment<MODE>(a, S, sh, D, px, py, ix, iy, iz, base + __popc(m & ((1u << lane) - 1u)));
         }
@@ -331,18 +329,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_voxel_tiles(VoxArgs a) {
 // One lane per queued pixel of a tiny triangle: every lane works on a different triangle (gathered loads), but the
 // control flow is uniform, so the shading runs at full warp efficiency.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) k_voxel_pixels(VoxArgs a) {
+__device__ __forceinline__ void voxel_pixels_part(const VoxArgs& a, unsigned block, unsigned n_blocks) {
     const FrameConst& fc = *a.fc;
     const int D = a.D, lane = threadIdx.x & 31;
     const bool occupancy = MODE == MODE_OCC;
     const unsigned n_items = min(*a.q.pixel_count, a.q.pixel_cap);
-    const unsigned stride = gridDim.x * kThreads;
-    for (unsigned base = blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n_items; base += stride) {
+    const unsigned stride = n_blocks * kThreads;
+    for (unsigned base = block * kThreads + (threadIdx.x & ~31u); base < n_items; base += stride) {
         const unsigned item = base + lane;
         bool hit = false; float l[3]; int ix = 0, iy = 0, iz = 0, px = 0, py = 0;
-        VoxSetup S;
+        VoxHead S; unsigned sslot = 0;
         if (item < n_items) {
             const uint2 it = __ldg(a.q.pixels + item);
+            sslot = it.x;
             S = a.setups[it.x];
             px = (int)(it.y & 0xFFFFu); py = (int)(it.y >> 16);
             bool oob = false;
@@ -357,27 +356,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_voxel_pixels(VoxArgs a) {
             slot0 = __shfl_sync(0xffffffffu, slot0, 0);
         }
         if (hit) {
-            ShadeIn I; load_shade_in(a, S.tri, I);
+            const ShadeIn I = a.setups[sslot].in;
             const Shaded sh = shade_fragment(fc, S, I, l, a.tex, a.mats, a.shadow);
             store_fragment<MODE>(a, S, sh, D, px, py, ix, iy, iz, slot0 + __popc(m & ((1u << lane) - 1u)));
         }
     }
 }
 
+// Tile items and single-pixel items are independent work queues: one launch, the first `tile_blocks` CTAs take tiles,
+// the rest take pixels, so the short pixel pass overlaps the tail of the tile pass instead of following it.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) k_voxel_tiles(VoxArgs a, unsigned tile_blocks) {
+    if (blockIdx.x < tile_blocks) voxel_tiles_part<MODE>(a, blockIdx.x, tile_blocks);
+    else voxel_pixels_part<MODE>(a, blockIdx.x - tile_blocks, gridDim.x - tile_blocks);
+}
+
 // --------------------------------------------------------------------------------------------- resolve
 // One thread per fragment; the thread whose fragment is the head of its voxel's list replays the whole list in
-// canonical order.  Lists are short (Sponza max 10, typical 1); longer ones take the O(n^2) selection path.
+// canonical order and stores the final words.  Lists are short (Sponza max 10, typical 1); longer ones take the O(n^2)
+// selection path.  A head is a fragment that no later push displaced (`displaced` is set by the pusher and cleared
+// again here, so it needs no per-frame memset); voxelColor is not consulted, so the head can overwrite the list
+// pointer with the final colour in the same kernel.
 constexpr int kSortMax = 24;
-__global__ void __launch_bounds__(kThreads) k_voxel_resolve_a(Frag* __restrict__ frags, const Counters* __restrict__ counters, unsigned frag_cap,
-                                                              const uint32_t* __restrict__ heads) {
+__global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restrict__ frags, const Counters* __restrict__ counters, unsigned frag_cap,
+                                                            uint8_t* __restrict__ displaced, uint32_t* __restrict__ color, uint32_t* __restrict__ normal) {
     const unsigned n = min(counters->n_frag_slots, frag_cap);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t key = frags[i].key;
-        if (heads[key] != i + 1u) continue;
+        const uint4* rec = reinterpret_cast<const uint4*>(frags + i);      // flag and record loads in flight together
+        const uint4 r0 = __ldcs(rec), r1 = __ldcs(rec + 1), r2 = __ldcs(rec + 2);
+        if (displaced[i]) { displaced[i] = 0; continue; }
+        const uint32_t key = r0.x;
         uint32_t cw = 0u, nw = 0u;
-        if (frags[i].next == 0u) {                                          // the common case: a single fragment
-            const Frag f = frags[i];
-            cw = rgba8_avg_insert(0u, f.cr, f.cg, f.cb); nw = rgba8_avg_insert(0u, f.nr, f.ng, f.nb);
+        if (r0.w == 0u) {                                                   // next == 0, the common case: a single fragment
+            cw = rgba8_avg_insert(0u, __uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z));
+            nw = rgba8_avg_insert(0u, __uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z));
         } else {
             unsigned long long ord[kSortMax]; uint32_t idx[kSortMax];
             int cnt = 0; bool fits = true;
@@ -408,16 +420,7 @@ __global__ void __launch_bounds__(kThreads) k_voxel_resolve_a(Frag* __restrict__
                 }
             }
         }
-        frags[i].cw = cw; frags[i].nw = nw; frags[i].key = key | kHeadFlag;
-    }
-}
-__global__ void __launch_bounds__(kThreads) k_voxel_resolve_b(const Frag* __restrict__ frags, const Counters* __restrict__ counters, unsigned frag_cap,
-                                                              uint32_t* __restrict__ color, uint32_t* __restrict__ normal) {
-    const unsigned n = min(counters->n_frag_slots, frag_cap);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t key = frags[i].key;
-        if (!(key & kHeadFlag)) continue;
-        color[key & ~kHeadFlag] = frags[i].cw; normal[key & ~kHeadFlag] = frags[i].nw;
+        color[key] = cw; normal[key] = nw;
     }
 }
 
@@ -431,8 +434,8 @@ int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* til
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_voxel_bin<MODE><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, bin_name);
     k_voxel_expand<<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a.setups, a.q); VCT_LAUNCH_CHECK(c, "k_voxel_expand");
-    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, tiles_name);
-    k_voxel_pixels<MODE><<<VCT_SM_COUNT * 2, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, pixels_name);
+    (void)pixels_name;
+    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 10, kThreads, 0, c->stream>>>(a, VCT_SM_COUNT * 8); VCT_LAUNCH_CHECK(c, tiles_name);   // tiles + pixels
     return 0;
 }
 
@@ -475,7 +478,7 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset) {
     a.wpos = c->d_wpos; a.wnrm = c->d_wnrm; a.tex = c->d_tex; a.mats = c->d_mat; a.shadow = c->d_shadow; a.warpmap = c->d_warpmap;
     a.setups = reinterpret_cast<VoxSetup*>(c->d_setup); a.setup_cap = (unsigned)c->setup_cap;
     a.q = vctk_tile_queues(c);
-    a.frags = reinterpret_cast<Frag*>(c->d_frags); a.frag_cap = (unsigned)c->frag_cap;
+    a.frags = reinterpret_cast<Frag*>(c->d_frags); a.frag_cap = (unsigned)c->frag_cap; a.displaced = c->d_displaced;
     a.color = c->d_color; a.normal = c->d_normal; a.occ = c->d_occ; a.counters = c->d_counters; a.seg = c->d_seg[c->seg_cur];
     if (!counters_already_reset) { k_voxel_reset<<<1, 1, 0, c->stream>>>(c->d_counters); VCT_LAUNCH_CHECK(c, "k_voxel_reset"); }
     if (occupancy) {
@@ -487,7 +490,6 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset) {
     if (!p.deterministic) return run_mode<MODE_CAS>(c, a, "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_pixels_cas");
     // deterministic running average: per-voxel lists, then ordered sequential replay
     if (run_mode<MODE_SORTED>(c, a, "k_voxel_bin", "k_voxel_tiles", "k_voxel_pixels")) return 1;
-    k_voxel_resolve_a<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, c->d_color); VCT_LAUNCH_CHECK(c, "k_voxel_resolve_a");
-    k_voxel_resolve_b<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, c->d_color, c->d_normal); VCT_LAUNCH_CHECK(c, "k_voxel_resolve_b");
+    k_voxel_resolve<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal); VCT_LAUNCH_CHECK(c, "k_voxel_resolve");
     return 0;
 }
