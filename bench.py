@@ -62,7 +62,7 @@ class ClockSampler:
     def __init__(self, device):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -111,8 +111,17 @@ def algorithmic_bytes(D, L, S, W, H, T, F, U, chains):
     }
 
 
-VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_expand", "k_voxel_tiles", "k_voxel_pixels", "k_voxel_resolve",
-                    "k_voxel_resolve_b", "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_pixels_cas", "k_voxel_bin_max", "k_voxel_tiles_max", "k_voxel_pixels_max")
+VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_expand", "k_voxel_tiles", "k_voxel_resolve",
+                    "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_bin_max", "k_voxel_tiles_max")
+
+
+def measured_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed
+    `ncu --set full` capture of one frame of this same workload (profiles/traffic.json, written by tools/ncu_traffic.py)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
@@ -262,9 +271,10 @@ def run_b200(args):
         roofline = None
         if dom:
             roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                        "traffic": None, "peak_source": peak_src, "ms": dom["ms"], "share_of_step": round(dom["ms"] / max(step_kernel_ms, 1e-9), 3),
+                        "traffic": measured_traffic().get(dom["kernel"]), "peak_source": peak_src, "ms": dom["ms"], "share_of_step": round(dom["ms"] / max(step_kernel_ms, 1e-9), 3),
                         "algorithmic_bytes": dom["algorithmic_bytes"],
                         "timing": f"per-kernel CUDA events on the library stream, mean of {nprof} profiled frames run right after the timed region"}
+            roofline["traffic_source"] = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of one frame"
             if dom["kernel"] == "k_cone_trace":
                 roofline["note"] = "cone trace is bound by L1/texture + L2 throughput (the pyramid is re-read ~100x per frame from cache), see cone_steps_per_s"
         voxel_bytes = sum(ab[k] for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_chain"))
@@ -284,7 +294,9 @@ def run_b200(args):
                            "dim": D, "levels": LEVELS, "width": W, "height": H, "shadow": SHADOW, "triangles": T,
                            "voxelize_mode": "deterministic running average (canonical draw order)" if p.deterministic else "free-running CAS",
                            "mip_chains": chains, "parallelism": fr.describe(),
-                           "l2": "no explicit flush: one frame touches ~370 MiB (3 voxel volumes + 2 pyramids + texture array + shadow map) > 126 MB L2, and each frame starts by clearing 128 MiB"},
+                           "sparse_frames": os.environ.get("VCT_SPARSE", "1") != "0",
+                           "l2": "no explicit flush: the inputs of one step exceed the 126 MB L2 (shadow map 64 MiB + fragment records 24 MB + visibility 17 MB + scene geometry 40 MB + 73 MiB texture pyramid + material textures), "
+                                 "so every pass starts L2-cold for its own inputs; k_cone_trace measured standalone with warm L2 is ~60 us faster than inside the step"},
                 "e2e": {"value": round(e2e_ms, 4), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_passes": roofs,
                 "voxel_passes": {"ms": round(voxel_ms, 4), "algorithmic_bytes": int(voxel_bytes), "achieved_gbs": round(voxel_bytes / max(voxel_ms, 1e-9) / 1e6, 1),

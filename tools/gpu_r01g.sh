@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.txt
-timeout 600 python tools/trace_variants.py 20 0 16 32 2>&1 | tail -12 | tee gpurun_out/trace_variants.txt
+timeout 600 python tools/trace_variants.py 10 0 2>&1 | tail -12 | tee gpurun_out/trace_variants.txt
 python tools/profile_frame.py 4 --kernels 2>&1 | tail -32 | tee gpurun_out/kernels_frame.txt
 timeout 600 python bench.py --steps ${STEPS:-200} --warmup 20 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -5 gpurun_out/bench.err

@@ -231,14 +231,25 @@ int zero_info(vct_ctx* c) {
 // The GI passes of one frame.  Sparse frame (DESIGN.md "segment masks"): clear, transfer and the mip chain visit only the
 // x-row segments that hold (or held last frame) a fragment.  The first frame, and any frame after something wrote a
 // volume behind the library's back, runs the dense kernels and (re)builds the masks.
-int gi_body(vct_ctx* c, Graph& g) {
+struct FramePlan { int n_chains, key; bool maskable, sparse; };
+FramePlan plan_frame(const vct_ctx* c) {
+    const vct_frame_params& p = c->h_fc.p;
+    FramePlan f;
+    f.n_chains = (p.mip_color_chain || !p.draw_radiance) ? 2 : 1;
+    f.key = f.n_chains * 2 + (p.draw_radiance ? 1 : 0);                   // which pyramids are filtered / published
+    f.maskable = vctk_sparse_supported(c) && !c->sparse_off && !p.voxel_fill_holes;
+    f.sparse = f.maskable && c->seg_valid && c->seg_key == f.key;
+    return f;
+}
+int gi_body(vct_ctx* c, Graph& g, bool cleared_by_frame_begin = false) {
     const vct_frame_params& p = c->h_fc.p;
     const bool single = c->cfg.world_size <= 1;
-    const int n_chains = (p.mip_color_chain || !p.draw_radiance) ? 2 : 1;
-    const int key = n_chains * 2 + (p.draw_radiance ? 1 : 0);           // which pyramids are filtered / published
-    const bool maskable = vctk_sparse_supported(c) && !c->sparse_off && !p.voxel_fill_holes;
-    const bool sparse = maskable && c->seg_valid && c->seg_key == key;
-    if (sparse) {
+    const FramePlan plan = plan_frame(c);
+    const int n_chains = plan.n_chains, key = plan.key;
+    const bool maskable = plan.maskable, sparse = plan.sparse;
+    if (cleared_by_frame_begin) {
+        if (g.rec(EV_CLEAR)) return 1;
+    } else if (sparse) {
         if (vctk_clear_masked(c) || g.rec(EV_CLEAR)) return 1;              // also zeroes VoxelizeInfo, the raster queues, cone_steps
     } else {
         const size_t nb = std::max<size_t>((size_t)c->D * c->D * c->D / 8, 64);
@@ -441,8 +452,10 @@ int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
     PASS_PROLOGUE;
     Graph g{c, true};
     if (g.rec(EV_START) || g.rec(EV_SHADOW) || g.rec(EV_WARP)) return 1;
-    if (vctk_transform_vertices(c)) return 1;
-    if (gi_body(c, g)) return 1;
+    // sparse frame: vertex transform and masked clear share one launch (kept apart under per-kernel profiling)
+    const bool fused_begin = plan_frame(c).sparse && c->profiling < 2 && c->n_vertices > 0;
+    if (fused_begin ? vctk_frame_begin_masked(c) : vctk_transform_vertices(c)) return 1;
+    if (gi_body(c, g, fused_begin)) return 1;
     if (c->cfg.world_size > 1) return 0;                      // caller all-gathers, then vct_exchange + vct_cone_trace
     if (g.rec(EV_GBUF)) return 1;
     if (vctk_cone_trace(c)) return 1;                         // cone_steps was zeroed by gi_body's clear

@@ -208,6 +208,7 @@ void vctk_fill_models(vct_ctx*, Mat4* models, float* nmats);
 int vctk_transfer(vct_ctx*);
 int vctk_clear_masked(vct_ctx*);        // sparse frames: clear flagged segments of all three volumes, reset the new mask and the frame counters
 int vctk_transfer_masked(vct_ctx*);
+int vctk_frame_begin_masked(vct_ctx*);   // vertex transform + masked clear in one launch
 bool vctk_sparse_supported(const vct_ctx*);
 int vctk_inject(vct_ctx*);
 int vctk_fill_holes(vct_ctx*);

@@ -568,15 +568,16 @@ int vctk_cone_trace(vct_ctx* c) {
     a.n_last = level_dim(c->D, c->L - 1);
     a.last_level = (rad ? c->d_radiance : c->d_color) + c->level_off[c->L - 1];
     // tuning knobs (VCT_TRACE_VARIANT): bit 0 = shared-memory last level (measured slower, off), bit 3 = L2 prefetch (off),
-    // bits 4-5 = CTA size 128 / 64 / 32 threads
+    // bits 4-5 = CTA size 128 / 64 / 32 / 256 threads
     const int variant = c->trace_variant;
     const bool sl = a.n_last <= kLastMax && (variant & 1) && !p.warp_voxels;
-    const int tpb = ((variant >> 4) & 3) == 1 ? 64 : ((variant >> 4) & 3) == 2 ? 32 : kThreads;
+    const int tpb = ((variant >> 4) & 3) == 1 ? 64 : ((variant >> 4) & 3) == 2 ? 32 : ((variant >> 4) & 3) == 3 ? 256 : kThreads;
     dim3 grid((c->W + tpb / 4 - 1) / (tpb / 4), (a.y_hi - a.y_lo + 3) / 4);
 #define VCT_TRACE2(WM, SLV)                                                                                    \
     do {                                                                                                       \
         if (tpb == 64) k_cone_trace<WM, SLV, 64><<<grid, 64, 0, c->stream>>>(a);                               \
         else if (tpb == 32) k_cone_trace<WM, SLV, 32><<<grid, 32, 0, c->stream>>>(a);                          \
+        else if (tpb == 256) k_cone_trace<WM, SLV, 256><<<grid, 256, 0, c->stream>>>(a);                       \
         else k_cone_trace<WM, SLV, kThreads><<<grid, kThreads, 0, c->stream>>>(a);                             \
     } while (0)
 #define VCT_TRACE(WM) do { if (sl) VCT_TRACE2(WM, true); else VCT_TRACE2(WM, false); } while (0)

@@ -104,7 +104,7 @@ __device__ __forceinline__ bool tile_rejected(const TriSetup& s, int bx0, int by
 }
 
 // Called by a CONVERGED warp.  Lanes with `queued` own a triangle setup `s` already published in slot `sslot`.
-__device__ __forceinline__ void enqueue_tiles(bool queued, const TriSetup& s, uint32_t sslot, const TileQueues& q) {
+__device__ __forceinline__ void enqueue_tiles(bool queued, const TriSetup& s, uint32_t sslot, const TileQueues& q, int max_tiles = kExpandTiles) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int bw = queued ? s.x1 - s.x0 + 1 : 0, bh = queued ? s.y1 - s.y0 + 1 : 0;
@@ -117,9 +117,9 @@ __device__ __forceinline__ void enqueue_tiles(bool queued, const TriSetup& s, ui
         const uint32_t pos = __shfl_sync(0xffffffffu, base, 0) + __popc(sm & lt_mask);
         if (single) { if (pos < q.tile_cap) q.tiles[pos] = make_uint2(sslot, (unsigned)s.x0 | (unsigned)s.y0 << 16); else *q.overflow = 1u; }
     }
-    // multi-tile: bands of tile rows, <= kExpandTiles tiles each (at least one row)
+    // multi-tile: bands of tile rows, <= max_tiles tiles each (at least one row)
     const bool multi = queued && ntx * nty > 1;
-    const int rows = multi ? max(1, kExpandTiles / ntx) : 1;
+    const int rows = multi ? max(1, max_tiles / ntx) : 1;
     int nitems = multi ? (nty + rows - 1) / rows : 0;
     int inc = nitems;                                                       // warp prefix sum -> one atomic per warp
 #pragma unroll
@@ -186,6 +186,29 @@ __device__ __forceinline__ uint32_t reserve_slots(bool want, unsigned* __restric
 __device__ __forceinline__ float interp1(const float l[3], float a0, float a1, float a2) { return (l[0] * a0 + l[1] * a1) + l[2] * a2; }
 __device__ __forceinline__ V3 interp3(const float l[3], V3 a, V3 b, V3 c) {
     return mk3(interp1(l, a.x, b.x, c.x), interp1(l, a.y, b.y, c.y), interp1(l, a.z, b.z, c.z));
+}
+
+// ------------------------------------------------------------------------------------ vertex transform
+// voxelize.vert:15-23 / phong.vert:37-54: world position, normalMatrix*normal, Gram-Schmidt tangent, bitangent.
+// A device function so that the frame-begin launch (volume_passes.cu) can run it next to the sparse clear.
+__device__ __forceinline__ void transform_vertices_part(const float* __restrict__ verts, const int32_t* __restrict__ vactor, const Mat4* __restrict__ models,
+                                                        const float* __restrict__ nmats, size_t n, float4* __restrict__ wpos, float4* __restrict__ wnrm,
+                                                        float4* __restrict__ wT, float4* __restrict__ wB, unsigned block, unsigned n_blocks) {
+    for (size_t i = block * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)n_blocks * blockDim.x) {
+        const float* v = verts + 14 * i;
+        const int a = vactor[i];
+        const V4 w = mul44(models[a], mk4(v[0], v[1], v[2], 1.0f));
+        const float* m = nmats + 9 * a;
+        auto mul3 = [&](V3 q) { return mk3((m[0] * q.x + m[1] * q.y) + m[2] * q.z, (m[3] * q.x + m[4] * q.y) + m[5] * q.z, (m[6] * q.x + m[7] * q.y) + m[8] * q.z); };
+        const V3 N = mul3(mk3(v[3], v[4], v[5]));
+        V3 T = mul3(mk3(v[8], v[9], v[10]));
+        T = normalize3(T - N * dot3(T, N));                               // phong.vert:52
+        const V3 B = cross3(N, T);                                        // phong.vert:53
+        wpos[i] = make_float4(w.x, w.y, w.z, 1.0f);
+        wnrm[i] = make_float4(N.x, N.y, N.z, 0.0f);
+        wT[i] = make_float4(T.x, T.y, T.z, 0.0f);
+        wB[i] = make_float4(B.x, B.y, B.z, 0.0f);
+    }
 }
 
 // ---------------------------------------------------------------------------------- 2D material textures

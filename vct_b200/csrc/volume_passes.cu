@@ -11,6 +11,7 @@
 // Data layout: every volume level is a linear uint32[d^3], x fastest (RGBA8, R in bits 0-7).  All streaming
 // kernels move 16 bytes per thread per access (4 voxels) and are launched with enough CTAs to fill 148 SMs
 // several times over; grid-stride where the element count is large.
+#include <algorithm>
 #include <cuda_fp16.h>
 #include <string.h>
 
@@ -46,16 +47,16 @@ __global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4
 // Sparse frame: one thread = 4 consecutive segments (32 voxels, 128 bytes per volume).  Segments flagged in last frame's
 // mask are zeroed in voxelColor, voxelNormal and (unless the temporal filter keeps it) voxelRadiance; this frame's mask
 // starts empty (temporal: inherits, because the decaying radiance keeps its support).  Also resets the frame counters.
-__global__ void __launch_bounds__(kThreads) k_clear_masked(uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
-                                                           const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t n_words, int temporal,
-                                                           Counters* __restrict__ reset) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+__device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
+                                                  const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t n_words, int temporal,
+                                                  Counters* __restrict__ reset, unsigned block, unsigned n_blocks) {
+    if (block == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
         reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
         reset->cone_steps = 0ull;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)gridDim.x * blockDim.x) {
+    for (size_t t = block * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)n_blocks * blockDim.x) {
         const uint32_t flags = __ldg(seg_prev + t);
         seg_cur[t] = temporal ? flags : 0u;
         if (!flags) continue;
@@ -66,6 +67,20 @@ __global__ void __launch_bounds__(kThreads) k_clear_masked(uint4* __restrict__ c
             if (!temporal) __stcs(radiance + 8 * t + j, z);
         }
     }
+}
+__global__ void __launch_bounds__(kThreads) k_clear_masked(uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
+                                                           const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t n_words, int temporal,
+                                                           Counters* __restrict__ reset) {
+    clear_masked_part(color, normal, radiance, seg_prev, seg_cur, n_words, temporal, reset, blockIdx.x, gridDim.x);
+}
+// Frame begin of vct_gi_passes on a sparse frame: the vertex transform and the masked clear are independent, both are
+// short and neither fills the GPU, so they share one launch (the first `t_blocks` CTAs transform, the rest clear).
+struct TransformArgs { const float* verts; const int32_t* vactor; const Mat4* models; const float* nmats; size_t n; float4 *wpos, *wnrm, *wT, *wB; };
+__global__ void __launch_bounds__(kThreads) k_frame_begin(TransformArgs t, unsigned t_blocks, uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
+                                                          const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t n_words, int temporal,
+                                                          Counters* __restrict__ reset) {
+    if (blockIdx.x < t_blocks) transform_vertices_part(t.verts, t.vactor, t.models, t.nmats, t.n, t.wpos, t.wnrm, t.wT, t.wB, blockIdx.x, t_blocks);
+    else clear_masked_part(color, normal, radiance, seg_prev, seg_cur, n_words, temporal, reset, blockIdx.x - t_blocks, gridDim.x - t_blocks);
 }
 
 // --------------------------------------------------------------------------------------------- transfer
@@ -730,6 +745,17 @@ int vctk_clear_masked(vct_ctx* c) {
                                                                             reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), n_words,
                                                                             temporal, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_clear");
+    return 0;
+}
+int vctk_frame_begin_masked(vct_ctx* c) {
+    const size_t n_words = (size_t)c->D * c->D * c->D / 32;
+    TransformArgs t{c->d_vertices, c->d_vactor, c->d_models, c->d_nmats, c->n_vertices, c->d_wpos, c->d_wnrm, c->d_wT, c->d_wB};
+    const unsigned tb = (unsigned)std::min<size_t>((c->n_vertices + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
+    const unsigned cb = (unsigned)grid_for(n_words, kThreads);
+    k_frame_begin<<<tb + cb, kThreads, 0, c->stream>>>(t, tb, reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_normal), reinterpret_cast<uint4*>(c->d_radiance),
+                                                       reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), n_words,
+                                                       c->h_fc.p.temporal_filter_radiance, c->d_counters);
+    VCT_LAUNCH_CHECK(c, "k_frame_begin");
     return 0;
 }
 int vctk_transfer_masked(vct_ctx* c) {

@@ -30,21 +30,7 @@ enum { MODE_SORTED = 0, MODE_CAS = 1, MODE_MAX = 2, MODE_OCC = 3 };
 __global__ void __launch_bounds__(kThreads) k_transform_vertices(const float* __restrict__ verts, const int32_t* __restrict__ vactor,
                                                                  const Mat4* __restrict__ models, const float* __restrict__ nmats, size_t n,
                                                                  float4* __restrict__ wpos, float4* __restrict__ wnrm, float4* __restrict__ wT, float4* __restrict__ wB) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float* v = verts + 14 * i;
-        const int a = vactor[i];
-        const V4 w = mul44(models[a], mk4(v[0], v[1], v[2], 1.0f));
-        const float* m = nmats + 9 * a;
-        auto mul3 = [&](V3 q) { return mk3((m[0] * q.x + m[1] * q.y) + m[2] * q.z, (m[3] * q.x + m[4] * q.y) + m[5] * q.z, (m[6] * q.x + m[7] * q.y) + m[8] * q.z); };
-        const V3 N = mul3(mk3(v[3], v[4], v[5]));
-        V3 T = mul3(mk3(v[8], v[9], v[10]));
-        T = normalize3(T - N * dot3(T, N));                               // phong.vert:52
-        const V3 B = cross3(N, T);                                        // phong.vert:53
-        wpos[i] = make_float4(w.x, w.y, w.z, 1.0f);
-        wnrm[i] = make_float4(N.x, N.y, N.z, 0.0f);
-        wT[i] = make_float4(T.x, T.y, T.z, 0.0f);
-        wB[i] = make_float4(B.x, B.y, B.z, 0.0f);
-    }
+    transform_vertices_part(verts, vactor, models, nmats, n, wpos, wnrm, wT, wB, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------- per-triangle
@@ -288,43 +274,51 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
 }
 
 // ----------------------------------------------------------------------------------------------- tiles
+// one 8x4 tile of one triangle, one lane per pixel: coverage, voxel index, shading, image atomic
+template <int MODE>
+__device__ __forceinline__ void process_tile(const VoxArgs& a, const FrameConst& fc, unsigned sslot, int ox, int oy, unsigned& counted) {
+    const VoxHead S = a.setups[sslot];                                      // same address in every lane: broadcast
+    const int D = a.D, lane = threadIdx.x & 31;
+    const bool occupancy = MODE == MODE_OCC;
+    const int px = ox + (lane & (kTileW - 1)), py = oy + (lane >> 3);
+    float l[3]; bool oob = false; int ix = 0, iy = 0, iz = 0;
+    const bool frag = px <= S.s.x1 && py <= S.s.y1 && frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
+    const bool hit = frag && !oob;
+    if (frag) counted++;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (!m) return;
+    if (MODE == MODE_OCC) { if (hit) atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); return; }
+    uint32_t base = 0;
+    if (MODE == MODE_SORTED) {
+        if (lane == 0) base = atomicAdd(&a.counters->n_frag_slots, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+    }
+    if (hit) {
+        const ShadeIn I = a.setups[sslot].in;
+        const Shaded sh = shade_fragment(fc, S, I, l, a.tex, a.mats, a.shadow);
+        store_fragment<MODE>(a, S, sh, D, px, py, ix, iy, iz, base + __popc(m & ((1u << lane) - 1u)));
+    }
+}
+template <int MODE>
+__device__ __forceinline__ void flush_counted(const VoxArgs& a, unsigned counted) {
+    if (MODE == MODE_OCC) return;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
+    if ((threadIdx.x & 31) == 0 && counted) atomicAdd(&a.counters->total_fragments, counted);
+}
+// single-tile triangles: the bin thread queued the tile itself
 template <int MODE>
 __device__ __forceinline__ void voxel_tiles_part(const VoxArgs& a, unsigned block, unsigned n_blocks) {
     const FrameConst& fc = *a.fc;
-    const int D = a.D, lane = threadIdx.x & 31;
-    const bool occupancy = MODE == MODE_OCC;
     const unsigned n_items = min(*a.q.tile_count, a.q.tile_cap);
     const unsigned warps = n_blocks * (kThreads / 32);
     unsigned counted = 0;
     for (unsigned item = block * (kThreads / 32) + (threadIdx.x >> 5); item < n_items; item += warps) {
         const uint2 it = __ldg(a.q.tiles + item);
-        const VoxHead S = a.setups[it.x];                                   // same address in every lane: broadcast
-        const int px = (int)(it.y & 0xFFFFu) + (lane & (kTileW - 1)), py = (int)(it.y >> 16) + (lane >> 3);
-        float l[3]; bool oob = false; int ix = 0, iy = 0, iz = 0;
-        const bool frag = px <= S.s.x1 && py <= S.s.y1 && frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
-        const bool hit = frag && !oob;
-        if (frag) counted++;
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (!m) continue;
-        if (MODE == MODE_OCC) { if (hit) atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); continue; }
-        uint32_t base = 0;
-        if (MODE == MODE_SORTED) {
-            if (lane == 0) base = atomicAdd(&a.counters->n_frag_slots, (unsigned)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-        }
-        if (hit) {
-            const ShadeIn I = a.setups[it.x].in;
-            const Shaded sh = shade_fragment(fc, S, I, l, a.tex, a.mats, a.shadow);
-            store_fragment<MODE>(a, S, sh, D, px, py, ix, iy, iz, base + __popc(m & ((1u << lane) - 1u)));
-        }
+        process_tile<MODE>(a, fc, it.x, (int)(it.y & 0xFFFFu), (int)(it.y >> 16), counted);
     }
-    if (MODE != MODE_OCC) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
-        if (lane == 0 && counted) atomicAdd(&a.counters->total_fragments, counted);
-    }
+    flush_counted<MODE>(a, counted);
 }
-
 // ---------------------------------------------------------------------------------------------- pixels
 // One lane per queued pixel of a tiny triangle: every lane works on a different triangle (gathered loads), but the
 // control flow is uniform, so the shading runs at full warp efficiency.
@@ -365,8 +359,10 @@ __device__ __forceinline__ void voxel_pixels_part(const VoxArgs& a, unsigned blo
 
 // Tile items and single-pixel items are independent work queues: one launch, the first `tile_blocks` CTAs take tiles,
 // the rest take pixels, so the short pixel pass overlaps the tail of the tile pass instead of following it.
+// (Rasterising the bands of multi-tile triangles in here as well, instead of expanding them into the tile queue first,
+// was measured: 88 -> 195 us — a warp that owns a band works through its tiles one dependent chain after the other.)
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) k_voxel_tiles(VoxArgs a, unsigned tile_blocks) {
+__global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a, unsigned tile_blocks) {
     if (blockIdx.x < tile_blocks) voxel_tiles_part<MODE>(a, blockIdx.x, tile_blocks);
     else voxel_pixels_part<MODE>(a, blockIdx.x - tile_blocks, gridDim.x - tile_blocks);
 }
