@@ -72,7 +72,11 @@ class ShardedFrame:
         if world > 1:
             import torch.distributed as dist
             self.dist = dist
-            self.stream = torch.cuda.current_stream()
+            # A dedicated (non-default) stream shared by the library and the NCCL collectives: torch's default stream has
+            # handle 0, which vct_set_stream reads as "use a private stream" — the collectives would then not be ordered
+            # after the kernels that produce their input.
+            self.stream = torch.cuda.Stream()
+            self.stream.wait_stream(torch.cuda.current_stream())
             g.set_stream(self.stream.cuda_stream)
             which = P.VOL_RADIANCE if params.draw_radiance else P.VOL_COLOR
             self.levels = [device_tensor(g.device_ptr(which, l), g.level_bytes(which, l)) for l in range(g.L)]
@@ -109,14 +113,16 @@ class ShardedFrame:
 
     def step(self):
         g, p = self.g, self.p
-        g.gi_passes(p)
         if self.world == 1:
+            g.gi_passes(p)
             return
-        self._exchange()
-        g.exchange()
-        g.cone_trace(p)
-        r, n = self.rank, self.band_px
-        self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
+        with self.torch.cuda.stream(self.stream):
+            g.gi_passes(p)
+            self._exchange()
+            g.exchange()
+            g.cone_trace(p)
+            r, n = self.rank, self.band_px
+            self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
 
     def step_e2e(self, host_img):
         """host_img: pinned int32 tensor of W*H pixels.  Frame parameters go host->device inside vct_gi_passes."""
@@ -125,15 +131,19 @@ class ShardedFrame:
         if self.world == 1:
             g._ck(g.lib.vct_read_image(g.h, host_img.data_ptr()))
         elif self.rank == 0:
-            host_img.copy_(self.image[: g.W * g.H], non_blocking=True)
+            with self.torch.cuda.stream(self.stream):
+                host_img.copy_(self.image[: g.W * g.H], non_blocking=True)
             self.stream.synchronize()
 
     def profiled_step(self):
         """Per-kernel times {name: (ns, launches)} of one step (library profiling level 2)."""
         g, p = self.g, self.p
-        g.gi_passes(p)
-        kt = g.kernel_times()
-        if self.world > 1:
+        if self.world == 1:
+            g.gi_passes(p)
+            return g.kernel_times()
+        with self.torch.cuda.stream(self.stream):
+            g.gi_passes(p)
+            kt = g.kernel_times()
             self._exchange()
             g.exchange(); kt2 = g.kernel_times()
             g.cone_trace(p); kt3 = g.kernel_times()
