@@ -147,6 +147,17 @@ int  vct_fill_holes(vct_ctx*, const vct_frame_params*);    /* :839-875 */
 int  vct_mip(vct_ctx*, int which_volume);                  /* :877-921  (VCT_VOL_RADIANCE or VCT_VOL_COLOR) */
 int  vct_exchange(vct_ctx*);                               /* multi-GPU only: publish slab pyramid to the 3D texture
                                                               after the caller's all-gather */
+/* multi-GPU, sparse frames: level 0 of the traced pyramid travels as the flagged x-row segments of each rank's slab, pushed
+ * into staging buffers in every peer's memory (NVLink, cudaIpc) instead of a dense all-gather.  Per frame:
+ *   vct_gi_passes; if vct_frame_was_sparse: vct_exchange_push, all-gather levels >= 1 (the barrier), vct_exchange_unpack;
+ *   else: all-gather every level, vct_exchange.  Then vct_cone_trace.  Setup once: vct_exchange_setup, then hand every
+ *   rank's 64-byte handle (vct_exchange_export) to every other rank (vct_exchange_import). */
+int  vct_exchange_setup(vct_ctx*);
+int  vct_exchange_export(vct_ctx*, void* ipc_handle_64_bytes);
+int  vct_exchange_import(vct_ctx*, int rank, const void* ipc_handle_64_bytes);
+int  vct_exchange_push(vct_ctx*);
+int  vct_exchange_unpack(vct_ctx*);                        /* scatter the records of all ranks + publish levels >= 1 */
+int  vct_frame_was_sparse(vct_ctx*);                       /* 1: the last vct_frame / vct_gi_passes visited flagged segments only */
 int  vct_gbuffer(vct_ctx*, const vct_frame_params*);       /* :936-965  depth prepass -> visibility buffer */
 int  vct_cone_trace(vct_ctx*, const vct_frame_params*);    /* :967-1067 phong + cone tracing */
 int  vct_frame(vct_ctx*, const vct_frame_params*);         /* the whole graph, in reference order */

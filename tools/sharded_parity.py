@@ -43,14 +43,14 @@ def main():
     g = Pipeline(sc, D, L, SS, W, H, device=local, rank=rank, world_size=world)
     fr = ShardedFrame(g, p, world, rank)
     fr.producers()
-    for _ in range(2):                       # second frame: steady state (publish masks, temporal history) also matches
+    for _ in range(3):                       # later frames: steady state (sparse exchange, publish masks, temporal history) also matches
         fr.step()
     torch.cuda.synchronize()
     info = g.counters()
     cnt = torch.tensor([info.total_fragments, info.unique_voxels], device="cuda", dtype=torch.int64)
     mx = torch.tensor([info.max_fragments_per_voxel], device="cuda", dtype=torch.int64)
     dist.all_reduce(cnt); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    ok, report = True, {"workload": name, "world": world}
+    ok, report = True, {"workload": name, "world": world, "exchange": fr.describe()[:120]}
     if rank == 0:
         which = P.VOL_RADIANCE if p.draw_radiance else P.VOL_COLOR
         sharded_levels = [g.read_volume(which, l) for l in range(g.L)]
@@ -61,7 +61,7 @@ def main():
             if p.warp_texture:
                 one.occupancy(p); one.warpmap(p)
             one.gbuffer(p)
-            for _ in range(2):
+            for _ in range(3):
                 one.gi_passes(p)
             ref_info = one.counters()
             for l in range(one.L):

@@ -269,6 +269,7 @@ int gi_body(vct_ctx* c, Graph& g, bool cleared_by_frame_begin = false) {
     if (vctk_mip_chains(c, n_chains, which, publish, 0, sparse)) return 1;   // both pyramids, one launch
     // this frame's mask bounds the support of all three level-0 volumes (dense temporal frames: k_transfer flagged the history)
     c->seg_valid = maskable;
+    c->last_frame_sparse = sparse;
     c->seg_key = key;
     c->seg_cur ^= 1;
     return g.rec(EV_MIP);
@@ -321,6 +322,7 @@ int vct_destroy(vct_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
+    vctk_xchg_free(c);
     for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, (void*)c->d_warp_scratch,
                     c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_wpos,
@@ -342,6 +344,7 @@ int vct_remake(vct_ctx* c, int dim, int levels) {
     if (dim < 4 || (dim & (dim - 1)) || dim > 1024) return fail(c, "vct_remake: dim must be a power of two in [4,1024]");
     VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     free_volumes(c);
+    vctk_xchg_free(c);
     c->D = dim; c->L = clamp_levels(dim, levels); c->cfg.dim = dim; c->cfg.levels = c->L;
     return make_volumes(c);
 }
@@ -446,6 +449,47 @@ int vct_exchange(vct_ctx* c) {
     const bool rad = c->h_fc.p.draw_radiance != 0;
     if (!rad && ensure_color_texture(c)) return 1;
     return vctk_publish(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR);
+}
+
+// ---- sparse slab exchange over peer memory (exchange.cu); the caller (vct_b200/sharded.py, or the host application's
+// process launcher) only moves the 64-byte cudaIpc handles between the ranks.
+int vct_exchange_setup(vct_ctx* c) { if (!c) return 1; cudaSetDevice(c->cfg.device); return vctk_xchg_setup(c); }
+int vct_exchange_export(vct_ctx* c, void* handle64) {
+    if (!c || !handle64) return 1;
+    cudaSetDevice(c->cfg.device);
+    if (!c->d_xchg) return fail(c, "vct_exchange_export: call vct_exchange_setup first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    VCT_CHECK(c, cudaIpcGetMemHandle(&h, c->d_xchg));
+    std::memcpy(handle64, &h, 64);
+    return 0;
+}
+int vct_exchange_import(vct_ctx* c, int rank, const void* handle64) {
+    if (!c || !handle64) return 1;
+    cudaSetDevice(c->cfg.device);
+    if (!c->d_xchg) return fail(c, "vct_exchange_import: call vct_exchange_setup first");
+    if (rank < 0 || rank >= c->cfg.world_size) return fail(c, "vct_exchange_import: bad rank");
+    if (rank == c->cfg.rank) return 0;
+    cudaIpcMemHandle_t h; std::memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    VCT_CHECK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_xchg[rank] = p;
+    return 0;
+}
+int vct_frame_was_sparse(vct_ctx* c) { return c && c->last_frame_sparse ? 1 : 0; }
+int vct_exchange_push(vct_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->cfg.device);
+    vct_prof_begin(c);
+    if (!c->last_frame_sparse) return fail(c, "vct_exchange_push: the last frame was dense; all-gather the levels and call vct_exchange");
+    return vctk_xchg_push(c);
+}
+int vct_exchange_unpack(vct_ctx* c) {
+    if (!c) return 1;
+    cudaSetDevice(c->cfg.device);
+    vct_prof_begin(c);
+    const bool rad = c->h_fc.p.draw_radiance != 0;
+    return vctk_xchg_unpack(c) || vctk_publish_upper(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR);
 }
 
 int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
@@ -576,7 +620,8 @@ void* vct_device_ptr(vct_ctx* c, int which, int level) {
     if (!c) return nullptr;
     void* p; size_t b;
     if (volume_ptr(c, which, level, &p, &b)) return nullptr;
-    if (which == VCT_VOL_COLOR || which == VCT_VOL_NORMAL || which == VCT_VOL_RADIANCE) { c->seg_disabled = true; c->seg_valid = false; }
+    // (multi-GPU: the caller all-gathers the remote slabs into the levels, which the own slab's masks do not describe anyway)
+    if (c->cfg.world_size <= 1 && (which == VCT_VOL_COLOR || which == VCT_VOL_NORMAL || which == VCT_VOL_RADIANCE)) { c->seg_disabled = true; c->seg_valid = false; }
     return p;
 }
 size_t vct_level_bytes(vct_ctx* c, int which, int level) { if (!c) return 0; void* p; size_t b; return volume_ptr(c, which, level, &p, &b) ? 0 : b; }

@@ -7,6 +7,7 @@
 // is compiled with FMA contraction on.
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -16,6 +17,7 @@
 #include "../../include/vct_b200.h"
 
 #define VCT_SM_COUNT 148
+#define VCT_MAX_PEERS 8
 
 // ------------------------------------------------------------------------------------------- small vectors
 struct V3 { float x, y, z; };
@@ -133,6 +135,9 @@ struct vct_ctx {
     // voxelColor / voxelNormal / voxelRadiance level 0 lies in a segment flagged in the previous mask, so clear, transfer
     // and the mip chain touch only flagged segments (the volume is ~97 % empty).  Anything that writes a volume outside
     // vct_frame / vct_gi_passes invalidates the masks; the next frame then runs the dense kernels once.
+    // sparse slab exchange (exchange.cu): local staging, the peers' staging mapped through cudaIpc, record counter
+    void* d_xchg = nullptr; size_t xchg_region_bytes = 0; unsigned xchg_cap = 0; void* peer_xchg[VCT_MAX_PEERS]{}; unsigned* d_xchg_count = nullptr;
+    bool last_frame_sparse = false;
     uint8_t* d_seg[2] = {nullptr, nullptr}; int seg_cur = 0, seg_key = -1; bool seg_valid = false, seg_disabled = false, sparse_off = false;
     // warp
     uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
@@ -215,6 +220,11 @@ int vctk_fill_holes(vct_ctx*);
 int vctk_mip(vct_ctx*, int which, int mode, int publish);
 int vctk_mip_chains(vct_ctx*, int n, const int* which, const int* publish, int mode, bool masked = false);
 int vctk_publish(vct_ctx*, int which);
+int vctk_publish_upper(vct_ctx*, int which);   // levels 1..L-1 only
+int vctk_xchg_setup(vct_ctx*);
+void vctk_xchg_free(vct_ctx*);
+int vctk_xchg_push(vct_ctx*);
+int vctk_xchg_unpack(vct_ctx*);
 int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);
 int vctk_warpmap(vct_ctx*);

@@ -733,10 +733,10 @@ int vctk_transfer(vct_ctx* c) {
     VCT_LAUNCH_CHECK(c, "k_transfer");
     return 0;
 }
-// Sparse frames need whole segments per x-row, the fused mip-chain kernel with 16^3 blocks, and one GPU (the slab
-// exchange still moves dense levels).
+// Sparse frames need whole segments per x-row and the fused mip-chain kernel with 16^3 blocks (multi-GPU: inside the slab).
 bool vctk_sparse_supported(const vct_ctx* c) {
-    return !c->seg_disabled && c->cfg.world_size <= 1 && c->D >= 16 && c->D % 16 == 0 && c->L >= 5 && c->d_seg[0] && c->d_seg[1];
+    if (c->cfg.world_size > 1 && (c->z_lo % 16 || (c->z_hi - c->z_lo) % 16 || c->z_hi <= c->z_lo)) return false;   // whole 16^3 blocks per slab
+    return !c->seg_disabled && c->D >= 16 && c->D % 16 == 0 && c->L >= 5 && c->d_seg[0] && c->d_seg[1];
 }
 int vctk_clear_masked(vct_ctx* c) {
     const size_t n_words = (size_t)c->D * c->D * c->D / 32;
@@ -897,6 +897,7 @@ int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, 
 }
 int vctk_mip(vct_ctx* c, int which, int mode, int publish) { return vctk_mip_chains(c, 1, &which, &publish, mode); }
 int vctk_publish(vct_ctx* c, int which) { return publish_levels(c, which, 0, c->L); }
+int vctk_publish_upper(vct_ctx* c, int which) { return c->L > 1 ? publish_levels(c, which, 1, c->L) : 0; }
 int vctk_set_voxel_opacity(vct_ctx* c, float opacity) {
     const size_t n = (size_t)c->D * c->D * c->D;
     k_set_voxel_opacity<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(c->d_color, c->d_radiance, n, opacity, c->d_counters);

@@ -70,6 +70,19 @@ class Pipeline:
     def fill_holes(self, p): self._ck(self.lib.vct_fill_holes(self.h, C.byref(p)))
     def mip(self, which=P.VOL_RADIANCE): self._ck(self.lib.vct_mip(self.h, which))
     def exchange(self): self._ck(self.lib.vct_exchange(self.h))
+    def frame_was_sparse(self): return bool(self.lib.vct_frame_was_sparse(self.h))
+    def exchange_push(self): self._ck(self.lib.vct_exchange_push(self.h))
+    def exchange_unpack(self): self._ck(self.lib.vct_exchange_unpack(self.h))
+
+    def exchange_setup(self):
+        """Allocate the sparse-exchange staging buffer and return its 64-byte cudaIpc handle."""
+        self._ck(self.lib.vct_exchange_setup(self.h))
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.vct_exchange_export(self.h, buf))
+        return bytes(buf.raw)
+
+    def exchange_import(self, rank, handle):
+        self._ck(self.lib.vct_exchange_import(self.h, rank, C.create_string_buffer(handle, 64)))
     def gbuffer(self, p): self._ck(self.lib.vct_gbuffer(self.h, C.byref(p)))
     def cone_trace(self, p): self._ck(self.lib.vct_cone_trace(self.h, C.byref(p)))
     def frame(self, p): self._ck(self.lib.vct_frame(self.h, C.byref(p)))

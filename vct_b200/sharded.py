@@ -12,6 +12,7 @@ world_size  > 1   z-slab sharding: every rank clears / voxelises / transfers / i
 The partition maths (`slab_range`, `level_chunks`, `image_bands`) is pure Python and is unit-tested on CPU with gloo.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -84,13 +85,23 @@ class ShardedFrame:
             self.band, self.bands = image_bands(g.H, world)
             self.image = device_tensor(g.device_ptr(P.BUF_IMAGE, 0), g.level_bytes(P.BUF_IMAGE, 0))
             self.band_px = self.band * g.W
+            # sparse exchange of level 0 over peer memory (exchange.cu): every rank maps every other rank's staging buffer
+            self.sparse_exchange = False
+            if os.environ.get("VCT_SPARSE_EXCHANGE", "1") != "0" and dist.get_backend() == "nccl":
+                handles = [None] * world
+                dist.all_gather_object(handles, g.exchange_setup())
+                for r, h in enumerate(handles):
+                    g.exchange_import(r, h)
+                self.sparse_exchange = True
         else:
             self.stream = torch.cuda.ExternalStream(g.lib.vct_stream(g.h))
 
     def describe(self):
         if self.world == 1:
             return "1 GPU"
-        return (f"{self.world} GPUs: z-slab sharding of clear/voxelise/transfer/inject/mip, coalesced NCCL all-gather of the radiance pyramid, "
+        ex = ("level 0 pushed as flagged x-row segments into every peer's memory over NVLink (cudaIpc), levels >= 1 by coalesced NCCL all-gather"
+              if self.sparse_exchange else "coalesced NCCL all-gather of the radiance pyramid")
+        return (f"{self.world} GPUs: z-slab sharding of clear/voxelise/transfer/inject/mip, {ex}, "
                 f"cone trace sharded by {self.band}-row screen band, NCCL all-gather of the image bands")
 
     # producers of the reference frame graph that the GI step consumes (replicated on every rank)
@@ -101,15 +112,31 @@ class ShardedFrame:
             g.occupancy(p); g.warpmap(p)
         g.gbuffer(p)
 
-    def _exchange(self):
+    def _gather_levels(self, first):
         dist, r = self.dist, self.rank
+        levels, chunks = self.levels[first:], self.chunks[first:]
         try:
             with dist._coalescing_manager(device=self.levels[0].device):
-                for t, n in zip(self.levels, self.chunks):
+                for t, n in zip(levels, chunks):
                     dist.all_gather_into_tensor(t, t[r * n:(r + 1) * n])
         except (AttributeError, TypeError, RuntimeError):
-            for t, n in zip(self.levels, self.chunks):
+            for t, n in zip(levels, chunks):
                 dist.all_gather_into_tensor(t, t[r * n:(r + 1) * n])
+
+    def _exchange(self):
+        """After vct_gi_passes: give every rank the whole traced pyramid, in its 3D texture.  Sparse frame: level 0 goes
+        as flagged segments through peer memory; the all-gather of the small levels in between is the barrier that
+        orders every rank's pushes before every rank's unpack.  Dense frame (the first, or after an invalidation): all
+        levels by all-gather, dense publish.  All ranks take the same branch (same call history)."""
+        g = self.g
+        if self.sparse_exchange and g.frame_was_sparse():
+            g.exchange_push()
+            self._gather_levels(1)
+            g.exchange_unpack()
+            return {}
+        self._gather_levels(0)
+        g.exchange()
+        return {}
 
     def step(self):
         g, p = self.g, self.p
@@ -119,7 +146,6 @@ class ShardedFrame:
         with self.torch.cuda.stream(self.stream):
             g.gi_passes(p)
             self._exchange()
-            g.exchange()
             g.cone_trace(p)
             r, n = self.rank, self.band_px
             self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
@@ -144,8 +170,7 @@ class ShardedFrame:
         with self.torch.cuda.stream(self.stream):
             g.gi_passes(p)
             kt = g.kernel_times()
-            self._exchange()
-            g.exchange(); kt2 = g.kernel_times()
+            self._exchange(); kt2 = g.kernel_times()          # (kernels of the last library call of the exchange)
             g.cone_trace(p); kt3 = g.kernel_times()
             for extra in (kt2, kt3):
                 for k, (ns, n) in extra.items():
