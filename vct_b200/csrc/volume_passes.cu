@@ -712,6 +712,23 @@ __global__ void __launch_bounds__(kThreads) k_publish(const uint32_t* __restrict
     }
 }
 
+// levels 1..L-1 in one launch (they are small: 1/7 of level 0 together; one launch per level is launch-bound)
+struct PublishUpper { const uint32_t* src[VCT_MAX_LEVELS]; cudaSurfaceObject_t surf[VCT_MAX_LEVELS]; int d[VCT_MAX_LEVELS]; unsigned long long first[VCT_MAX_LEVELS + 1]; int n; };
+__global__ void __launch_bounds__(kThreads) k_publish_upper(const __grid_constant__ PublishUpper p) {
+    const unsigned long long total = p.first[p.n];
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k + 1 < p.n && i >= p.first[k + 1]) ++k;
+        const int d = p.d[k];
+        const unsigned long long j = i - p.first[k];
+        const int qx = d >= 4 ? d >> 2 : 1;
+        const int q = (int)(j % qx); const unsigned long long r = j / qx; const int y = (int)(r % d), z = (int)(r / d);
+        const uint32_t* src = p.src[k];
+        if (d >= 4) surf3Dwrite(__ldg(reinterpret_cast<const uint4*>(src + ((size_t)z * d + y) * d) + q), p.surf[k], q * 16, y, z);
+        else for (int x = 0; x < d; ++x) surf3Dwrite(__ldg(src + ((size_t)z * d + y) * d + x), p.surf[k], x * 4, y, z);
+    }
+}
+
 }  // namespace
 
 // ============================================================================================ host side
@@ -897,7 +914,22 @@ int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, 
 }
 int vctk_mip(vct_ctx* c, int which, int mode, int publish) { return vctk_mip_chains(c, 1, &which, &publish, mode); }
 int vctk_publish(vct_ctx* c, int which) { return publish_levels(c, which, 0, c->L); }
-int vctk_publish_upper(vct_ctx* c, int which) { return c->L > 1 ? publish_levels(c, which, 1, c->L) : 0; }
+int vctk_publish_upper(vct_ctx* c, int which) {
+    if (c->L < 2) return 0;
+    uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
+    cudaSurfaceObject_t* surf = which == VCT_VOL_COLOR ? c->color_surf : c->radiance_surf;
+    PublishUpper p{};
+    unsigned long long off = 0;
+    for (int l = 1; l < c->L; ++l) {
+        const int d = level_dim(c->D, l), k = p.n++;
+        p.src[k] = base + c->level_off[l]; p.surf[k] = surf[l]; p.d[k] = d; p.first[k] = off;
+        off += (unsigned long long)(d >= 4 ? d / 4 : 1) * d * d;
+    }
+    p.first[p.n] = off;
+    k_publish_upper<<<grid_for((size_t)off, kThreads), kThreads, 0, c->stream>>>(p);
+    VCT_LAUNCH_CHECK(c, "k_publish");
+    return 0;
+}
 int vctk_set_voxel_opacity(vct_ctx* c, float opacity) {
     const size_t n = (size_t)c->D * c->D * c->D;
     k_set_voxel_opacity<<<grid_for(n, kThreads), kThreads, 0, c->stream>>>(c->d_color, c->d_radiance, n, opacity, c->d_counters);

@@ -67,6 +67,7 @@ struct VoxArgs {
     Frag* frags; unsigned frag_cap; uint8_t* displaced;       // displaced[slot] = 1: a later fragment took over the head of that voxel's list
     uint32_t *color, *normal, *occ;
     uint8_t* seg;             // segment mask of this frame (common.cuh): one byte per 8 voxels of an x-row
+    int slab_cull;            // multi-GPU, linear mapping: triangles that cannot touch this rank's z-slab stop at the bin kernel
     Counters* counters;
 };
 
@@ -75,6 +76,22 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
     const uint32_t i0 = __ldg(a.indices + 3 * (size_t)t), i1 = __ldg(a.indices + 3 * (size_t)t + 1), i2 = __ldg(a.indices + 3 * (size_t)t + 2);
     const V3 w[3] = {ld3(a.wpos, i0), ld3(a.wpos, i1), ld3(a.wpos, i2)};
     const V3 n0 = ld3(a.wnrm, i0), n1 = ld3(a.wnrm, i1), n2 = ld3(a.wnrm, i2);
+    if (a.slab_cull) {
+        // Multi-GPU: a triangle whose voxel-space box (1.5 voxels of slack) lies inside the volume but misses this rank's
+        // z-slab can produce no fragment here — neither an owned one nor one outside the volume (those are counted by the
+        // rank that owns z = 0) — so it skips setup, binning and tiles.  Linear mapping only (no warp mode).
+        const float fd = (float)a.D;
+        float lo[3], hi[3];
+        const float wc[3][3] = {{w[0].x, w[1].x, w[2].x}, {w[0].y, w[1].y, w[2].y}, {w[0].z, w[1].z, w[2].z}};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float sc = fd / (fc.p.voxel_max[k] - fc.p.voxel_min[k]), of = fc.p.voxel_center[k] + fc.p.voxel_min[k];
+            const float v0 = (wc[k][0] - of) * sc, v1 = (wc[k][1] - of) * sc, v2 = (wc[k][2] - of) * sc;
+            lo[k] = fminf(v0, fminf(v1, v2)) - 1.5f; hi[k] = fmaxf(v0, fmaxf(v1, v2)) + 1.5f;
+        }
+        const bool inside = lo[0] >= 0.0f && lo[1] >= 0.0f && lo[2] >= 0.0f && hi[0] <= fd && hi[1] <= fd && hi[2] <= fd;   // false for NaN
+        if (inside && (hi[2] < (float)fc.z_lo || lo[2] > (float)fc.z_hi)) return false;
+    }
     S.in.w[0] = w[0]; S.in.w[1] = w[1]; S.in.w[2] = w[2]; S.in.n[0] = n0; S.in.n[1] = n1; S.in.n[2] = n2;
     const V3 f = normalize3((n0 + n1) + n2);
     const float ax = fabsf(f.x), ay = fabsf(f.y), az = fabsf(f.z);
@@ -476,6 +493,10 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset) {
     a.q = vctk_tile_queues(c);
     a.frags = reinterpret_cast<Frag*>(c->d_frags); a.frag_cap = (unsigned)c->frag_cap; a.displaced = c->d_displaced;
     a.color = c->d_color; a.normal = c->d_normal; a.occ = c->d_occ; a.counters = c->d_counters; a.seg = c->d_seg[c->seg_cur];
+    // the three ortho views reproduce the linear mapping only for a symmetric cube: cull only then
+    const bool cube = p.voxel_min[0] == -p.voxel_max[0] && p.voxel_min[1] == -p.voxel_max[1] && p.voxel_min[2] == -p.voxel_max[2] &&
+                      p.voxel_max[0] == p.voxel_max[1] && p.voxel_max[1] == p.voxel_max[2] && p.voxel_max[0] > 0.0f;
+    a.slab_cull = !occupancy && c->cfg.world_size > 1 && !p.warp_voxels && !p.warp_texture && cube && p.axis_override < 0;
     if (!counters_already_reset) { k_voxel_reset<<<1, 1, 0, c->stream>>>(c->d_counters); VCT_LAUNCH_CHECK(c, "k_voxel_reset"); }
     if (occupancy) {
         VCT_CHECK(c, cudaMemsetAsync(c->d_occ, 0, sizeof(uint32_t) * VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM, c->stream));
