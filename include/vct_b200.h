@@ -158,6 +158,8 @@ int  vct_exchange_import(vct_ctx*, int rank, const void* ipc_handle_64_bytes);
 int  vct_exchange_push(vct_ctx*);
 int  vct_exchange_unpack(vct_ctx*);                        /* scatter the records of all ranks + publish levels >= 1 */
 int  vct_frame_was_sparse(vct_ctx*);                       /* 1: the last vct_frame / vct_gi_passes visited flagged segments only */
+int  vct_mask_parity(vct_ctx*);                            /* which of the two segment masks the NEXT frame writes (0/1): a CUDA graph that
+                                                              captured frames must be replayed at the parity it was captured at */
 int  vct_gbuffer(vct_ctx*, const vct_frame_params*);       /* :936-965  depth prepass -> visibility buffer */
 int  vct_cone_trace(vct_ctx*, const vct_frame_params*);    /* :967-1067 phong + cone tracing */
 int  vct_frame(vct_ctx*, const vct_frame_params*);         /* the whole graph, in reference order */

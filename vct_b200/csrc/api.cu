@@ -477,6 +477,7 @@ int vct_exchange_import(vct_ctx* c, int rank, const void* handle64) {
     return 0;
 }
 int vct_frame_was_sparse(vct_ctx* c) { return c && c->last_frame_sparse ? 1 : 0; }
+int vct_mask_parity(vct_ctx* c) { return c ? c->seg_cur : 0; }
 int vct_exchange_push(vct_ctx* c) {
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);

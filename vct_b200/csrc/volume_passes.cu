@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4
 // mask are zeroed in voxelColor, voxelNormal and (unless the temporal filter keeps it) voxelRadiance; this frame's mask
 // starts empty (temporal: inherits, because the decaying radiance keeps its support).  Also resets the frame counters.
 __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
-                                                  const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t n_words, int temporal,
+                                                  const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t w_lo, size_t n_words, int temporal,
                                                   Counters* __restrict__ reset, unsigned block, unsigned n_blocks) {
     if (block == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
@@ -56,7 +56,7 @@ __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uin
         reset->cone_steps = 0ull;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (size_t t = block * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)n_blocks * blockDim.x) {
+    for (size_t t = w_lo + block * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)n_blocks * blockDim.x) {      // [w_lo, n_words): this rank's slab
         const uint32_t flags = __ldg(seg_prev + t);
         seg_cur[t] = temporal ? flags : 0u;
         if (!flags) continue;
@@ -69,18 +69,18 @@ __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uin
     }
 }
 __global__ void __launch_bounds__(kThreads) k_clear_masked(uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
-                                                           const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t n_words, int temporal,
+                                                           const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t w_lo, size_t n_words, int temporal,
                                                            Counters* __restrict__ reset) {
-    clear_masked_part(color, normal, radiance, seg_prev, seg_cur, n_words, temporal, reset, blockIdx.x, gridDim.x);
+    clear_masked_part(color, normal, radiance, seg_prev, seg_cur, w_lo, n_words, temporal, reset, blockIdx.x, gridDim.x);
 }
 // Frame begin of vct_gi_passes on a sparse frame: the vertex transform and the masked clear are independent, both are
 // short and neither fills the GPU, so they share one launch (the first `t_blocks` CTAs transform, the rest clear).
 struct TransformArgs { const float* verts; const int32_t* vactor; const Mat4* models; const float* nmats; size_t n; float4 *wpos, *wnrm, *wT, *wB; };
 __global__ void __launch_bounds__(kThreads) k_frame_begin(TransformArgs t, unsigned t_blocks, uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
-                                                          const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t n_words, int temporal,
+                                                          const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t w_lo, size_t n_words, int temporal,
                                                           Counters* __restrict__ reset) {
     if (blockIdx.x < t_blocks) transform_vertices_part(t.verts, t.vactor, t.models, t.nmats, t.n, t.wpos, t.wnrm, t.wT, t.wB, blockIdx.x, t_blocks);
-    else clear_masked_part(color, normal, radiance, seg_prev, seg_cur, n_words, temporal, reset, blockIdx.x - t_blocks, gridDim.x - t_blocks);
+    else clear_masked_part(color, normal, radiance, seg_prev, seg_cur, w_lo, n_words, temporal, reset, blockIdx.x - t_blocks, gridDim.x - t_blocks);
 }
 
 // --------------------------------------------------------------------------------------------- transfer
@@ -163,13 +163,13 @@ __global__ void __launch_bounds__(kThreads) k_transfer(uint4* __restrict__ color
 // works through their 16-byte quads with all lanes (about one segment in ten is flagged: without the compaction most
 // lanes would idle behind the few that found work).  Only flagged segments can hold a fragment; their radiance was
 // zeroed by k_clear_masked (non-temporal) or holds last frame's value (temporal).
-__global__ void __launch_bounds__(kThreads) k_transfer_masked(uint4* __restrict__ color, uint4* __restrict__ radiance, const uint32_t* __restrict__ seg, size_t n_words,
+__global__ void __launch_bounds__(kThreads) k_transfer_masked(uint4* __restrict__ color, uint4* __restrict__ radiance, const uint32_t* __restrict__ seg, size_t w_lo, size_t n_words,
                                                               float opacity, int temporal, float decay, Counters* __restrict__ counters) {
     __shared__ uint32_t s_list[kThreads / 32][128];
     unsigned uniq = 0, maxfrag = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t n_round = (n_words + 31) & ~(size_t)31;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_round; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t n_round = w_lo + ((n_words - w_lo + 31) & ~(size_t)31);                     // [w_lo, n_words): this rank's slab
+    for (size_t t = w_lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_round; t += (size_t)gridDim.x * blockDim.x) {
         const uint32_t flags = t < n_words ? __ldg(seg + t) : 0u;
         const unsigned nz = (flags & 0xFFu ? 1u : 0u) | (flags & 0xFF00u ? 2u : 0u) | (flags & 0xFF0000u ? 4u : 0u) | (flags & 0xFF000000u ? 8u : 0u);
         int inc = __popc(nz);
@@ -756,30 +756,30 @@ bool vctk_sparse_supported(const vct_ctx* c) {
     return !c->seg_disabled && c->D >= 16 && c->D % 16 == 0 && c->L >= 5 && c->d_seg[0] && c->d_seg[1];
 }
 int vctk_clear_masked(vct_ctx* c) {
-    const size_t n_words = (size_t)c->D * c->D * c->D / 32;
+    const size_t wps = (size_t)c->D * c->D / 32, w_lo = c->z_lo * wps, n_words = c->z_hi * wps;   // mask words of this rank's slab
     const int temporal = c->h_fc.p.temporal_filter_radiance;
-    k_clear_masked<<<grid_for(n_words, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_normal), reinterpret_cast<uint4*>(c->d_radiance),
-                                                                            reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), n_words,
+    k_clear_masked<<<grid_for(n_words - w_lo, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_normal), reinterpret_cast<uint4*>(c->d_radiance),
+                                                                            reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), w_lo, n_words,
                                                                             temporal, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_clear");
     return 0;
 }
 int vctk_frame_begin_masked(vct_ctx* c) {
-    const size_t n_words = (size_t)c->D * c->D * c->D / 32;
+    const size_t wps = (size_t)c->D * c->D / 32, w_lo = c->z_lo * wps, n_words = c->z_hi * wps;
     TransformArgs t{c->d_vertices, c->d_vactor, c->d_models, c->d_nmats, c->n_vertices, c->d_wpos, c->d_wnrm, c->d_wT, c->d_wB};
     const unsigned tb = (unsigned)std::min<size_t>((c->n_vertices + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
-    const unsigned cb = (unsigned)grid_for(n_words, kThreads);
+    const unsigned cb = (unsigned)grid_for(n_words - w_lo, kThreads);
     k_frame_begin<<<tb + cb, kThreads, 0, c->stream>>>(t, tb, reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_normal), reinterpret_cast<uint4*>(c->d_radiance),
-                                                       reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), n_words,
+                                                       reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), w_lo, n_words,
                                                        c->h_fc.p.temporal_filter_radiance, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_frame_begin");
     return 0;
 }
 int vctk_transfer_masked(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
-    const size_t n_words = (size_t)c->D * c->D * c->D / 32;
-    k_transfer_masked<<<grid_for(n_words, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_radiance),
-                                                                               reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), n_words,
+    const size_t wps = (size_t)c->D * c->D / 32, w_lo = c->z_lo * wps, n_words = c->z_hi * wps;
+    k_transfer_masked<<<grid_for(n_words - w_lo, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_radiance),
+                                                                               reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), w_lo, n_words,
                                                                                p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_transfer");
     return 0;

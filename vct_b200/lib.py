@@ -19,7 +19,7 @@ SYMBOLS = [
     "vct_get_cone_steps", "vct_sync", "vct_device_ptr", "vct_level_bytes", "vct_stream", "vct_launch_count",
     "vct_set_stream", "vct_set_profiling", "vct_get_kernel_times",
     "vct_exchange_setup", "vct_exchange_export", "vct_exchange_import", "vct_exchange_push", "vct_exchange_unpack",
-    "vct_frame_was_sparse",
+    "vct_frame_was_sparse", "vct_mask_parity",
 ]
 
 _lib = None
@@ -58,7 +58,7 @@ def load():
         "vct_set_stream": (ci, [vp, vp]), "vct_set_profiling": (ci, [vp, ci]),
         "vct_get_kernel_times": (ci, [vp, C.POINTER(P.KernelTime), ci]),
         "vct_exchange_setup": (ci, [vp]), "vct_exchange_export": (ci, [vp, vp]), "vct_exchange_import": (ci, [vp, ci, vp]),
-        "vct_exchange_push": (ci, [vp]), "vct_exchange_unpack": (ci, [vp]), "vct_frame_was_sparse": (ci, [vp]),
+        "vct_exchange_push": (ci, [vp]), "vct_exchange_unpack": (ci, [vp]), "vct_frame_was_sparse": (ci, [vp]), "vct_mask_parity": (ci, [vp]),
     }
     for name in ("vct_shadowmap", "vct_occupancy", "vct_warpmap", "vct_voxelize", "vct_transfer", "vct_inject", "vct_fill_holes",
                  "vct_gbuffer", "vct_cone_trace", "vct_frame", "vct_gi_passes"):

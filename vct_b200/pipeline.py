@@ -71,6 +71,7 @@ class Pipeline:
     def mip(self, which=P.VOL_RADIANCE): self._ck(self.lib.vct_mip(self.h, which))
     def exchange(self): self._ck(self.lib.vct_exchange(self.h))
     def frame_was_sparse(self): return bool(self.lib.vct_frame_was_sparse(self.h))
+    def mask_parity(self): return int(self.lib.vct_mask_parity(self.h))
     def exchange_push(self): self._ck(self.lib.vct_exchange_push(self.h))
     def exchange_unpack(self): self._ck(self.lib.vct_exchange_unpack(self.h))
 

@@ -138,6 +138,40 @@ class ShardedFrame:
         g.exchange()
         return {}
 
+    # ---- CUDA graph: the step is ~25 short launches (+ 2 collectives); replaying a captured pair of steps removes the
+    # host from the loop.  TWO steps per graph because the segment masks swap roles every frame; the graph is only
+    # replayed at the mask parity it was captured at, and only while the frame parameters stay what they were.
+    def enable_graph(self):
+        torch = self.torch
+        self.graph, self.graph_error = None, None
+        try:
+            self.g.set_profiling(0)
+            torch.cuda.synchronize()
+            parity = self.g.mask_parity()
+            n0 = self.g.launch_count()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=self.stream):
+                self.step(); self.step()
+            self.graph_launches_per_step = (self.g.launch_count() - n0) // 2
+            self.graph, self.graph_parity = gr, parity
+            torch.cuda.synchronize()
+        except Exception as e:                                   # capture unsupported here: stay eager
+            self.graph, self.graph_error = None, f"{type(e).__name__}: {e}"
+            torch.cuda.synchronize()
+        return self.graph is not None
+
+    def run_steps(self, k):
+        """k steps; pairs go through the captured graph when there is one.  Returns how many steps were replayed."""
+        replayed = 0
+        while k > 0:
+            if getattr(self, "graph", None) is not None and k >= 2 and self.g.mask_parity() == self.graph_parity:
+                with self.torch.cuda.stream(self.stream):
+                    self.graph.replay()
+                k -= 2; replayed += 2
+            else:
+                self.step(); k -= 1
+        return replayed
+
     def step(self):
         g, p = self.g, self.p
         if self.world == 1:
