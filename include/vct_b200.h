@@ -198,6 +198,45 @@ unsigned long long vct_launch_count(vct_ctx*, int reset);
 int    vct_set_profiling(vct_ctx*, int level);
 int    vct_get_kernel_times(vct_ctx*, vct_kernel_time* out, int max_entries);   /* returns the entry count, <0 on error */
 
+/* ---- scene ingest (host only, no CUDA call): what the reference does when it constructs a Mesh ------------------
+ * Mesh::loadMesh (src/Graphics/Mesh.cpp:42-206: tinyobjloader OBJ/MTL -> de-duplicated Vertex array, one index list per
+ * material, tangent frames, trailing "default" material), GLHelper::createTextureFromImage (src/Graphics/GLHelper.cpp:
+ * 165-211: stb_image PNG decode -> R8/RGB8/RGBA8 + generated mips) and ResourceLoader::loadDDS (src/ResourceLoader.h:
+ * 26-108: DXT1/DXT3/DXT5 with the file's mips).  Implemented in vct_b200/host/vct_ingest{,_image}.hpp; byte-for-byte
+ * parity with the reference's own tinyobjloader and stb_image is tested in tests/test_ingest.py. */
+typedef struct vct_ingest vct_ingest;    /* opaque: one loaded OBJ (or one decoded image) */
+typedef struct {
+    const float*    vertices;            /* n_vertices x 14 floats = the 56-byte Vertex of Mesh.h:72-76 */
+    size_t          n_vertices;
+    const uint32_t* indices;             /* draw order: material by material (Mesh.cpp:340-371) */
+    size_t          n_indices;
+    const int32_t*  material_of_triangle;
+    int             n_materials;         /* the file's materials + the trailing default */
+    int             n_textures;
+    float           bounds_min[3], bounds_max[3], radius;   /* Mesh.cpp:127-128, 197-204 */
+} vct_ingest_mesh;
+typedef struct {
+    int width, height, channels, levels; /* as vct_upload_texture takes them */
+    const void* pixels;                  /* all levels packed, level 0 first */
+    size_t bytes;
+    const char* name;                    /* as written in the MTL ("@default_texture.png" for the default material) */
+} vct_ingest_texture;
+enum { VCT_INGEST_NO_TEXTURES = 1 /* parse names only, decode nothing */ };
+/* resource_dir: where default_texture.png lives (RESOURCE_DIR, src/common.h:13-15).  Returns 0 and a handle, or 1 and
+ * a handle that only carries the log (free it too); a missing MTL or texture is a log line, not an error. */
+int  vct_ingest_obj(const char* obj_path, const char* resource_dir, int flags, vct_ingest** out);
+int  vct_ingest_image(const char* path, int generate_mips, vct_ingest** out);   /* one PNG / DDS file as texture 0 */
+void vct_ingest_free(vct_ingest*);
+const char* vct_ingest_log(const vct_ingest*);
+int  vct_ingest_get_mesh(const vct_ingest*, vct_ingest_mesh* out);
+/* texture ids inside `out` are local to this ingest (0 .. n_textures-1, -1 = no map) */
+int  vct_ingest_get_material(const vct_ingest*, int material, vct_material* out, const char** name);
+int  vct_ingest_get_texture(const vct_ingest*, int texture, vct_ingest_texture* out);
+/* Mesh VAO/EBO/texture creation for one actor: vct_upload_texture for every texture at texture_base + local id,
+ * vct_set_material at material_base + local id (texture ids rebased), vct_upload_mesh with material ids rebased, then
+ * vct_set_actor_transform(model) (NULL: identity). */
+int  vct_ingest_upload(vct_ctx*, const vct_ingest*, int actor, int material_base, int texture_base, const float model[16]);
+
 #ifdef __cplusplus
 }
 #endif

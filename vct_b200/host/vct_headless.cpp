@@ -1,8 +1,9 @@
 // vct_headless — headless driver over vct_host::Application (the reference's main.cpp render loop without a window,
-// src/main.cpp:229-240): loads a VCTS scene file, renders N frames through the C ABI, prints the GLBufferedTimer-style
+// src/main.cpp:229-240): loads a VCTS scene file — or an OBJ through the library's own ingest, with the reference's two
+// lights, like Application::init (src/Application.cpp:96-136) —, renders N frames through the C ABI, prints the GLBufferedTimer-style
 // pass times and the VoxelizeInfo counters as one JSON line, and dumps the last frame as a binary PPM.
 //
-//   vct_headless scene.vcts [--dim 256] [--levels 6] [--size 1920x1080] [--shadow 4096] [--frames 3]
+//   vct_headless scene.vcts|mesh.obj [--scale s] [--resources dir] [--dim 256] [--levels 6] [--size 1920x1080] [--shadow 4096] [--frames 3]
 //                [--camera x y z yaw pitch | --eye x y z --front fx fy fz] [--volume min max] [--center x y z]
 //                [--no-reflections] [--atomic-max] [--warp-texture] [--temporal] [--fused] [--out frame.ppm]
 // Exit status: 0 ok, 1 a pass reported an error (message on stderr), 2 usage.  There is no CPU fallback: without a
@@ -27,7 +28,7 @@ static bool write_ppm(const char* path, const std::vector<uint8_t>& rgba, int w,
 int main(int argc, char** argv) {
     if (argc < 2 || !std::strcmp(argv[1], "--help") || !std::strcmp(argv[1], "-h")) {
         std::fprintf(argc < 2 ? stderr : stdout,
-                     "usage: vct_headless scene.vcts [--dim D] [--levels L] [--size WxH] [--shadow S] [--frames N]\n"
+                     "usage: vct_headless scene.vcts|mesh.obj [--scale s] [--resources dir] [--dim D] [--levels L] [--size WxH] [--shadow S] [--frames N]\n"
                      "       [--camera x y z yaw pitch | --eye x y z --front fx fy fz] [--volume min max] [--center x y z]\n"
                      "       [--no-reflections] [--atomic-max] [--warp-texture] [--temporal] [--fused] [--out frame.ppm]\n");
         return argc < 2 ? 2 : 0;
@@ -36,10 +37,13 @@ int main(int argc, char** argv) {
     app.width = 1920; app.height = 1080;
     app.camera.position = {5, 1, 0}; app.camera.yaw = 180.0f;           // reference start pose, Application.cpp:139-141
     int frames = 3, shadow = Application::SHADOWMAP_WIDTH; bool fused = false; const char* out = nullptr;
+    float scale = 1.0f; std::string resources;
     auto need = [&](int i, int n) { if (i + n >= argc) { std::fprintf(stderr, "missing value after %s\n", argv[i]); std::exit(2); } };
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "--dim") { need(i, 1); app.vct.voxelDim = std::atoi(argv[++i]); }
+        else if (a == "--scale") { need(i, 1); scale = (float)std::atof(argv[++i]); }
+        else if (a == "--resources") { need(i, 1); resources = argv[++i]; }
         else if (a == "--levels") { need(i, 1); app.vct.voxelLevels = std::atoi(argv[++i]); }
         else if (a == "--size") { need(i, 1); if (std::sscanf(argv[++i], "%dx%d", &app.width, &app.height) != 2) return 2; }
         else if (a == "--shadow") { need(i, 1); shadow = std::atoi(argv[++i]); }
@@ -58,7 +62,12 @@ int main(int argc, char** argv) {
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     Scene scene;
-    if (!scene.load(argv[1])) return 1;
+    const std::string input = argv[1];
+    if (input.size() > 4 && input.compare(input.size() - 4, 4, ".obj") == 0) {
+        if (resources.empty()) resources = input.substr(0, input.find_last_of('/') + 1);
+        if (!scene.addObj(argv[1], resources.c_str(), scale)) return 1;
+        scene.addReferenceLights();
+    } else if (!scene.load(argv[1])) return 1;
     if (scene.lights.empty()) { std::fprintf(stderr, "[ERROR] scene has no light (Application.cpp:125-130 needs the shadow-casting main light)\n"); return 1; }
     if (!app.init(&scene, shadow)) return 1;
     bool ok = true;

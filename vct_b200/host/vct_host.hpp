@@ -183,6 +183,53 @@ struct Scene {
         if (!ok) std::fprintf(stderr, "[ERROR] %s is not a version-1 VCTS scene file\n", path);
         return ok;
     }
+
+    // StaticMeshActor{path} + scene->addActor (Application.cpp:96-99): the OBJ goes through the library's own ingest
+    // (vct_ingest_obj: tinyobjloader/stb_image/DDS behaviour restated, include/vct_b200.h) and is appended as one actor
+    // with its materials and textures; `resource_dir` is RESOURCE_DIR (common.h:13-15, home of default_texture.png).
+    bool addObj(const char* path, const char* resource_dir, float uniform_scale = 1.0f) {
+        vct_ingest* g = nullptr;
+        const int rc = vct_ingest_obj(path, resource_dir, 0, &g);
+        if (g && vct_ingest_log(g)[0]) std::fprintf(stderr, "[%s] %s", rc ? "ERROR" : "WARN", vct_ingest_log(g));
+        if (rc) { if (g) vct_ingest_free(g); std::fprintf(stderr, "[ERROR] Failed to load mesh: %s\n", path); return false; }
+        vct_ingest_mesh m;
+        vct_ingest_get_mesh(g, &m);
+        const int tex_base = (int)textures.size(), mat_base = (int)materials.size();
+        for (int t = 0; t < m.n_textures; ++t) {
+            vct_ingest_texture it;
+            vct_ingest_get_texture(g, t, &it);
+            Texture tx; tx.width = it.width; tx.height = it.height; tx.channels = it.channels; tx.levels = it.levels;
+            tx.pixels.assign((const uint8_t*)it.pixels, (const uint8_t*)it.pixels + it.bytes);
+            textures.push_back(std::move(tx));
+        }
+        for (int k = 0; k < m.n_materials; ++k) {
+            vct_material mat;
+            vct_ingest_get_material(g, k, &mat, nullptr);
+            int* ids[6] = {&mat.diffuse_tex, &mat.specular_tex, &mat.normal_tex, &mat.roughness_tex, &mat.metallic_tex, &mat.alpha_tex};
+            for (int* id : ids) if (*id >= 0) *id += tex_base;
+            materials.push_back(mat);
+        }
+        Actor a;
+        a.vertices.assign(m.vertices, m.vertices + m.n_vertices * 14);
+        a.indices.assign(m.indices, m.indices + m.n_indices);
+        a.tri_material.assign(m.material_of_triangle, m.material_of_triangle + m.n_indices / 3);
+        for (int32_t& id : a.tri_material) id += mat_base;
+        a.model.at(0, 0) = a.model.at(1, 1) = a.model.at(2, 2) = uniform_scale;      // transform.setScale(vec3(s)), Application.cpp:98
+        actors.push_back(std::move(a));
+        vct_ingest_free(g);
+        return true;
+    }
+
+    // the two lights Application::init adds (Application.cpp:125-136); Light defaults from Scene.h:13-29
+    void addReferenceLights() {
+        vct_light main{}; main.type = 1; main.shadow_caster = 1; main.enabled = 1; main.range = 5.0f; main.intensity = 1.0f;
+        main.position[0] = 12.0f; main.position[1] = 40.0f; main.position[2] = -7.0f;
+        main.direction[0] = -0.38f; main.direction[1] = -0.88f; main.direction[2] = 0.2f;
+        main.color[0] = main.color[1] = main.color[2] = 1.0f;
+        vct_light test{}; test.type = 0; test.enabled = 1; test.range = 5.0f; test.intensity = 1.0f;
+        test.position[1] = 10.0f; test.direction[2] = -1.0f; test.color[0] = 1.0f; test.color[2] = 1.0f;
+        lights.push_back(main); lights.push_back(test);
+    }
 };
 
 struct Timers { double voxelize = 0, shadowmap = 0, radiance = 0, mipmap = 0, render = 0, total = 0; };   // ms, GLBufferedTimer names

@@ -20,6 +20,8 @@ SYMBOLS = [
     "vct_set_stream", "vct_set_profiling", "vct_get_kernel_times",
     "vct_exchange_setup", "vct_exchange_export", "vct_exchange_import", "vct_exchange_push", "vct_exchange_unpack",
     "vct_frame_was_sparse", "vct_mask_parity",
+    "vct_ingest_obj", "vct_ingest_image", "vct_ingest_free", "vct_ingest_log", "vct_ingest_get_mesh",
+    "vct_ingest_get_material", "vct_ingest_get_texture", "vct_ingest_upload",
 ]
 
 _lib = None
@@ -58,6 +60,12 @@ def load():
         "vct_set_stream": (ci, [vp, vp]), "vct_set_profiling": (ci, [vp, ci]),
         "vct_get_kernel_times": (ci, [vp, C.POINTER(P.KernelTime), ci]),
         "vct_exchange_setup": (ci, [vp]), "vct_exchange_export": (ci, [vp, vp]), "vct_exchange_import": (ci, [vp, ci, vp]),
+        "vct_ingest_obj": (ci, [C.c_char_p, C.c_char_p, ci, C.POINTER(vp)]), "vct_ingest_image": (ci, [C.c_char_p, ci, C.POINTER(vp)]),
+        "vct_ingest_free": (None, [vp]), "vct_ingest_log": (C.c_char_p, [vp]),
+        "vct_ingest_get_mesh": (ci, [vp, C.POINTER(P.IngestMesh)]),
+        "vct_ingest_get_material": (ci, [vp, ci, C.POINTER(P.Material), C.POINTER(C.c_char_p)]),
+        "vct_ingest_get_texture": (ci, [vp, ci, C.POINTER(P.IngestTexture)]),
+        "vct_ingest_upload": (ci, [vp, vp, ci, ci, ci, C.POINTER(cf)]),
         "vct_exchange_push": (ci, [vp]), "vct_exchange_unpack": (ci, [vp]), "vct_frame_was_sparse": (ci, [vp]), "vct_mask_parity": (ci, [vp]),
     }
     for name in ("vct_shadowmap", "vct_occupancy", "vct_warpmap", "vct_voxelize", "vct_transfer", "vct_inject", "vct_fill_holes",

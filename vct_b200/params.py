@@ -37,6 +37,17 @@ class Material(C.Structure):
                 ("shininess", C.c_float), ("diffuse", F3)]
 
 
+class IngestMesh(C.Structure):        # vct_ingest_mesh
+    _fields_ = [("vertices", C.POINTER(C.c_float)), ("n_vertices", C.c_size_t), ("indices", C.POINTER(C.c_uint32)),
+                ("n_indices", C.c_size_t), ("material_of_triangle", C.POINTER(C.c_int32)), ("n_materials", C.c_int),
+                ("n_textures", C.c_int), ("bounds_min", F3), ("bounds_max", F3), ("radius", C.c_float)]
+
+
+class IngestTexture(C.Structure):     # vct_ingest_texture
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("levels", C.c_int),
+                ("pixels", C.c_void_p), ("bytes", C.c_size_t), ("name", C.c_char_p)]
+
+
 class VoxelizeInfo(C.Structure):
     _fields_ = [("total_fragments", C.c_uint), ("unique_voxels", C.c_uint), ("max_fragments_per_voxel", C.c_uint)]
 

@@ -118,7 +118,7 @@ def load_baked(scene, name, model=None, max_texture=None):
     for line in open(os.path.join(d, "materials.txt")):
         f = (line.rstrip("\n").split("|") + [""] * 7)[:7]
         scene.add_material(diffuse=tex(f[1]), specular=tex(f[2]), normal=tex(f[3]), roughness=tex(f[4]),
-                           metallic=tex(f[5]), alpha=tex(f[6]), shininess=1.0 if f[0] == "default" else 32.0)
+                           metallic=tex(f[5]), alpha=tex(f[6]), shininess=32.0)   # Material(material_t) self-assigns: always 32 (Mesh.h:33-43)
     return scene.add_actor(Mesh(verts, idx, tmat + mat_base), model)
 
 
