@@ -1,0 +1,135 @@
+#!/usr/bin/env python3
+"""glsl2cpp.py <shader dir> <shader file> <driver.inc> <out.cpp>
+
+Turns ONE of the reference's GLSL shaders — read from where it lies under /root/reference/shaders — into a C++20
+translation unit that compiles against oracle/ref_rig/glsl_shim.h.  The output goes to oracle/_ref/ only (git-ignored);
+no reference source is stored in the repository.  TEST INFRASTRUCTURE (see glsl_shim.h).
+
+The shader BODY is not rewritten: every expression, branch, constant and statement order is the reference's.  Only
+the parts of GLSL that are not C++ are mapped, mechanically:
+  * `#pragma include "x"` is resolved like GLHelper::preprocessShader does (src/Graphics/GLHelper.cpp:265-283), `#version` /
+    `#extension` lines are dropped and the text is run through the C preprocessor (g++ -E), so `#if USE_RGBA16F`, `#ifdef
+    NORMAL_MAP`, `#define POINT_LIGHT 0` … select and expand exactly what a GLSL compiler would see;
+  * interface declarations become namespace-level variables the driver sets: `layout(...) uniform T x [= v];`, `in`/`out`
+    variables, `in NAME {...} inst;`, `layout(...) buffer/uniform NAME {...};` (an unsized `T a[];` member becomes
+    ssbo_array<T>), `layout(local_size...) in;` is dropped;
+  * array constructors `T[](a, b, c)` -> `{a, b, c}`;  `x.length()` -> glsl_length(x);
+  * `out` / `inout` parameters -> references; `discard` -> throw Discard();
+  * floating literals get an `f` suffix (GLSL literals are fp32; C++ would evaluate in double);
+  * `imageLoad` on a `uimage3D` -> imageLoadU (returns uvec4);  `void main()` -> `void shader_main()`.
+"""
+import os
+import re
+import subprocess
+import sys
+
+
+def resolve_includes(shader_dir, name, depth=0):
+    out = []
+    for line in open(os.path.join(shader_dir, name), encoding="utf-8", errors="replace").read().splitlines():
+        m = re.match(r'\s*#\s*pragma\s+include\s+"([^"]+)"', line)
+        if m and depth < 8:
+            out.extend(resolve_includes(shader_dir, m.group(1), depth + 1))
+        elif re.match(r"\s*#\s*(version|extension)\b", line):
+            continue
+        else:
+            out.append(line)
+    return out
+
+
+def match_paren(text, open_at):
+    depth = 0
+    for i in range(open_at, len(text)):
+        if text[i] == "(":
+            depth += 1
+        elif text[i] == ")":
+            depth -= 1
+            if depth == 0:
+                return i
+    raise ValueError("unbalanced parenthesis")
+
+
+TYPES = r"(?:float|int|uint|bool|vec[234]|ivec[234]|uvec[234]|mat[34])"
+
+
+def array_constructors(text):
+    pat = re.compile(TYPES + r"\s*\[\s*\w*\s*\]\s*\(")
+    while True:
+        m = pat.search(text)
+        if not m:
+            return text
+        close = match_paren(text, m.end() - 1)
+        text = text[:m.start()] + "{" + text[m.end():close] + "}" + text[close + 1:]
+
+
+def interface_blocks(text):
+    def block(m):
+        body = m.group("body")
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            a = re.match(r"(\w+)\s+(\w+)\s*\[\s*\]$", decl)
+            out.append(f"static ssbo_array<{a.group(1)}> {a.group(2)};" if a else f"static {decl};")
+        return "\n".join(out)
+    text = re.sub(r"(?:layout\s*\([^)]*\)\s*)?(?:buffer|uniform)\s+\w+\s*\{(?P<body>[^}]*)\}\s*;", block, text)
+    text = re.sub(r"(?:flat\s+)?\b(?:in|out)\s+(\w+)\s*\{([^}]*)\}\s*(\w+)\s*;", r"static struct \1 {\2} \3;", text)
+    return text
+
+
+def global_declarations(text):
+    out, depth = [], 0
+    qual = re.compile(r"^\s*(?:layout\s*\([^)]*\)\s*)?((?:(?:uniform|readonly|writeonly|coherent|restrict|flat|smooth|in|out)\s+)+)")
+    for line in text.splitlines():
+        if depth == 0:
+            if re.match(r"^\s*layout\s*\([^)]*\)\s*in\s*;", line):
+                line = ""
+            else:
+                m = qual.match(line)
+                if m:
+                    line = "static " + line[m.end():]
+        depth += line.count("{") - line.count("}")
+        out.append(line)
+    return "\n".join(out)
+
+
+def float_suffix(text):
+    lit = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])")
+    return lit.sub(lambda m: m.group(1) + "f", text)
+
+
+def translate(shader_dir, name):
+    src = "\n".join(resolve_includes(shader_dir, name)) + "\n"
+    pre = subprocess.run(["g++", "-E", "-P", "-undef", "-x", "c++", "-"], input=src, capture_output=True, text=True, check=True).stdout
+    t = interface_blocks(pre)
+    t = global_declarations(t)
+    t = array_constructors(t)
+    t = re.sub(r"\b(\w+)\.length\(\)", r"glsl_length(\1)", t)
+    t = re.sub(r"\b(?:out|inout)\s+(\w+)\s+(\w+)", r"\1& \2", t)
+    t = re.sub(r"([(,]\s*)in\s+(\w+\s+\w+)", r"\1\2", t)
+    t = re.sub(r"\bdiscard\s*;", "throw Discard();", t)
+    t = float_suffix(t)
+    for u in re.findall(r"\buimage3D\s+(\w+)\s*;", t):
+        t = re.sub(r"\bimageLoad\s*\(\s*" + u + r"\b", "imageLoadU(" + u, t)
+    t = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", t)
+    return t
+
+
+def main():
+    shader_dir, name, driver, out = sys.argv[1:5]
+    ns = re.sub(r"\W", "_", name)
+    body = translate(shader_dir, name)
+    with open(out, "w") as f:
+        f.write(f"// GENERATED by oracle/ref_rig/glsl2cpp.py from {os.path.join(shader_dir, name)} — do not commit.\n")
+        f.write('#include "glsl_shim.h"\n#include <vector>\n#include <cstdio>\n')
+        f.write("namespace glsl {\nnamespace " + ns + " {\n")
+        f.write("static ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\nstatic vec4 gl_FragCoord;\n")
+        f.write(body)
+        f.write("\n// ---- driver (this repository's code)\n")
+        f.write(open(driver).read())
+        f.write("\n}  // namespace " + ns + "\n}  // namespace glsl\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+#!/usr/bin/env python3
+"""Writes tests/golden/glsl_ref.npz: the outputs of the reference's GLSL shaders, compiled as C++ into
+oracle/_ref/libvct_glsl_ref.so (oracle/Makefile; needs /root/reference), on the seeded inputs of tests/test_glsl_ref.py."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from tests import test_glsl_ref as T  # noqa: E402
+
+if __name__ == "__main__":
+    out = T.run_cases("glsl")
+    np.savez_compressed(T.GOLD, **out)
+    print(len(out), "arrays,", os.path.getsize(T.GOLD), "bytes")

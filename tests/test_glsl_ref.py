@@ -1,0 +1,176 @@
+"""The CPU oracle against the REFERENCE'S OWN GLSL, compiled as C++.
+
+oracle/Makefile reads each shader from /root/reference/shaders where it lies, maps the GLSL syntax that is not C++ with
+oracle/ref_rig/glsl2cpp.py (the shader bodies stay the reference's: every expression, branch and constant), and compiles it
+against oracle/ref_rig/glsl_shim.h into oracle/_ref/libvct_glsl_ref.so.  These tests run the oracle's restatement
+(oracle/vct_oracle.cpp) and the compiled shader on the same seeded inputs and require identical words / texels.
+Where /root/reference is absent (the GPU box) the live comparison is skipped and the committed outputs of the compiled
+shaders (tests/golden/glsl_ref.npz, generator tests/golden/make_glsl_ref.py, same seeds) pin the oracle instead.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+from vct_b200 import params as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "_ref", "libvct_glsl_ref.so")
+GOLD = os.path.join(ROOT, "tests", "golden", "glsl_ref.npz")
+live = pytest.mark.skipif(not os.path.isfile(SO), reason="oracle/_ref/libvct_glsl_ref.so not built (needs /root/reference)")
+_g = None
+
+
+def glsl():
+    global _g
+    if _g is None:
+        _g = C.CDLL(SO)
+        _g.glsl_set_voxel_opacity.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        _g.glsl_normalize_voxels_f16.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _g.glsl_temporal_radiance_filter.argtypes = [C.c_int, C.c_float, C.c_void_p]
+    return _g
+
+
+ptr = O.ptr
+
+
+# ------------------------------------------------------------------------------------------------ seeded inputs
+def voxel_volume(D, seed, fill=0.12, counts=True):
+    """RGBA8 words: `fill` of the voxels occupied; alpha = fragment count (1..40, a few at 255) like the voxeliser leaves it."""
+    rng = np.random.default_rng(seed)
+    occ = rng.random(D ** 3) < fill
+    rgb = rng.integers(0, 256, (D ** 3, 3), dtype=np.uint32)
+    a = rng.integers(1, 41, D ** 3, dtype=np.uint32) if counts else rng.integers(1, 256, D ** 3, dtype=np.uint32)
+    a[rng.random(D ** 3) < 0.01] = 255
+    w = rgb[:, 0] | rgb[:, 1] << 8 | rgb[:, 2] << 16 | a << 24
+    return np.where(occ, w, 0).astype(np.uint32)
+
+
+def frame_params(D, **kw):
+    cam = P.Camera(position=(1.5, 1.0, 2.0), front=(-1.5, -0.8, -2.0))
+    light = P.reference_lights()[0]
+    light.position = P.F3(3.0, 9.0, 2.0); light.direction = P.F3(-0.3, -0.9, -0.25)
+    p = P.default_params(64, 48, cam, light, voxel_min=-4.0, voxel_max=4.0, voxel_center=(0.25, 1.0, -0.5))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p, light
+
+
+def shadow_map(S, seed):
+    """Depths of a bumpy surface seen from the light + holes at the far plane (1.0)."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:S, 0:S].astype(np.float32) / S
+    d = 0.08 + 0.03 * np.sin(9 * x) * np.cos(7 * y) + 0.02 * rng.random((S, S), dtype=np.float32)
+    d[rng.random((S, S)) < 0.05] = 1.0
+    return np.ascontiguousarray(d.astype(np.float32).reshape(-1))
+
+
+def warp_map(seed):
+    """A monotone, non-trivial 32^3 RGBA16 warp map (piecewise-linear per axis, like generateWarpmap produces)."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((32, 32, 32, 4), np.uint16)
+    for axis in range(3):
+        w = rng.choice([0.5, 1.0, 2.0], 32)
+        edges = np.concatenate([[0.0], np.cumsum(w) / w.sum()])
+        centres = (edges[:-1] + edges[1:]) / 2
+        shape = [1, 1, 1]; shape[2 - axis] = 32
+        out[..., axis] = np.round(centres.reshape(shape) * 65535).astype(np.uint16)
+    out[..., 3] = 65535
+    return np.ascontiguousarray(out.reshape(-1))
+
+
+# ------------------------------------------------------------------------------------------------------- cases
+def run_cases(impl):
+    """impl: 'oracle' or 'glsl' -> dict name -> array.  Same inputs, same call order for both."""
+    lib = O.lib() if impl == "oracle" else glsl()
+    f = (lambda n: getattr(lib, "orc_" + n)) if impl == "oracle" else (lambda n: getattr(lib, "glsl_" + n))
+    out = {}
+    # a3 transferVoxels.comp — plain, temporal (radiance history kept), opacity 0 (alpha kept)
+    for name, kw in (("plain", {}), ("temporal", {"temporal_filter_radiance": 1, "temporal_decay": 0.8}),
+                     ("opacity0", {"voxel_set_opacity": 0.0}), ("temporal_decay_third", {"temporal_filter_radiance": 1, "temporal_decay": 1.0 / 3.0})):
+        for D in (16, 20):                                              # 20: dispatch overhang past the image
+            p, _ = frame_params(D, **kw)
+            col, rad = voxel_volume(D, 1), voxel_volume(D, 2, fill=0.3, counts=False)
+            info = P.VoxelizeInfo(7, 0, 0)
+            f("transfer")(C.byref(p), D, ptr(col), ptr(rad), C.byref(info))
+            out[f"transfer_{name}_{D}_color"] = col; out[f"transfer_{name}_{D}_radiance"] = rad
+            out[f"transfer_{name}_{D}_info"] = np.array([info.total_fragments, info.unique_voxels, info.max_fragments_per_voxel], np.uint32)
+    # a6 filterRadiance.comp — BOX2 (live), BOX3, CUBE; a whole chain 32 -> 1
+    for mode in (0, 1, 2):
+        src = voxel_volume(32, 3 + mode, fill=0.4, counts=False)
+        Ds = 32
+        while Ds > 1:
+            dst = np.zeros((Ds // 2) ** 3, np.uint32)
+            f("mip")(Ds, ptr(src), ptr(dst), mode)
+            out[f"mip_mode{mode}_{Ds}"] = dst
+            src, Ds = dst, Ds // 2
+    # a4 voxelFillHoles.comp
+    for D in (16, 12):
+        rad = voxel_volume(D, 9, fill=0.2, counts=False)
+        f("fill_holes")(D, ptr(rad))
+        out[f"fill_holes_{D}"] = rad
+    # a5 injectRadiance.comp — linear mapping, cubic camera warp, warp texture, radianceLighting.  (radianceLighting together
+    # with the temporal filter is left out: injectRadiance.comp:87-94 reads back voxelRadiance that other invocations of the
+    # same dispatch write without atomics — order-dependent in the reference, whose own comment says it "doesn't work".)
+    S = 96
+    for name, kw in (("linear", {}), ("warp_voxels", {"warp_voxels": 1}), ("warp_texture", {"warp_texture": 1}),
+                     ("lighting", {"radiance_lighting": 1})):
+        D = 24
+        p, light = frame_params(D, **kw)
+        col, nrm = voxel_volume(D, 11, fill=0.5), voxel_volume(D, 12, fill=1.0, counts=False)
+        rad = voxel_volume(D, 13, fill=0.2, counts=False)
+        sm, wm = shadow_map(S, 14), warp_map(15)
+        lp = (C.c_float * 3)(*light.position); li = (C.c_float * 3)(0.9, 0.8, 0.7)
+        f("inject")(C.byref(p), D, ptr(col), ptr(nrm), ptr(sm), S, ptr(wm) if p.warp_texture else None, lp, li, ptr(rad))
+        out[f"inject_{name}"] = rad
+    # dead variants: setVoxelOpacity.comp, temporalRadianceFilter.comp, normalizeVoxels.comp (RGBA16F)
+    for D in (8, 10):
+        col, rad = voxel_volume(D, 21), np.zeros(D ** 3, np.uint32)
+        info = P.VoxelizeInfo(0, 0, 0)
+        f("set_voxel_opacity")(D, 0.5, ptr(col), ptr(rad), C.byref(info))
+        out[f"set_opacity_{D}_color"] = col; out[f"set_opacity_{D}_radiance"] = rad
+        out[f"set_opacity_{D}_info"] = np.array([info.unique_voxels, info.max_fragments_per_voxel], np.uint32)
+        vol = voxel_volume(D, 22, fill=0.6, counts=False)
+        f("temporal_radiance_filter")(D, 0.8, ptr(vol))
+        out[f"temporal_filter_{D}"] = vol
+        rng = np.random.default_rng(23)
+        cnt = np.where(rng.random(D ** 3) < 0.3, rng.integers(1, 30, D ** 3), 0).astype(np.float32)
+        c16 = (rng.random((D ** 3, 4), dtype=np.float32) * cnt[:, None]).astype(np.float16); c16[:, 3] = cnt.astype(np.float16)
+        n16 = (rng.random((D ** 3, 4), dtype=np.float32) * cnt[:, None]).astype(np.float16); n16[:, 3] = cnt.astype(np.float16)
+        c16, n16 = np.ascontiguousarray(c16.view(np.uint16).reshape(-1)), np.ascontiguousarray(n16.view(np.uint16).reshape(-1))
+        rad = np.zeros(D ** 3, np.uint32); info = P.VoxelizeInfo(0, 0, 0)
+        f("normalize_voxels_f16")(D, 0.5, ptr(c16), ptr(n16), ptr(rad), C.byref(info))
+        out[f"normalize_{D}_color"] = c16; out[f"normalize_{D}_normal"] = n16; out[f"normalize_{D}_radiance"] = rad
+        out[f"normalize_{D}_info"] = np.array([info.unique_voxels, info.max_fragments_per_voxel], np.uint32)
+    return out
+
+
+def compare(a, b, what):
+    assert sorted(a) == sorted(b)
+    bad = [k for k in sorted(a) if not np.array_equal(a[k], b[k])]
+    detail = ""
+    if bad:
+        k = bad[0]; d = np.flatnonzero(a[k] != b[k])
+        detail = f"; first: {k} differs in {d.size} of {a[k].size} words, e.g. [{d[0]}] {a[k][d[0]]:#x} vs {b[k][d[0]]:#x}"
+    assert not bad, f"{what}: {len(bad)} of {len(a)} outputs differ: {bad[:6]}{detail}"
+
+
+@live
+def test_oracle_equals_the_reference_glsl_compiled_as_cpp():
+    compare(run_cases("oracle"), run_cases("glsl"), "oracle vs compiled reference GLSL")
+
+
+def test_oracle_equals_the_committed_outputs_of_the_reference_glsl():
+    gold = dict(np.load(GOLD))
+    compare(run_cases("oracle"), gold, "oracle vs tests/golden/glsl_ref.npz")
+
+
+def test_cases_are_not_vacuous():
+    o = run_cases("oracle")
+    assert (o["transfer_plain_16_radiance"] >> 24 != 0).sum() > 100 and o["transfer_plain_16_info"][1] > 100
+    assert (o["inject_linear"] != voxel_volume(24, 13, fill=0.2, counts=False)).sum() > 50       # texels landed and wrote
+    assert len({o[k].tobytes() for k in o if k.startswith("inject_")}) == 4                        # every mode differs
+    assert (o["fill_holes_16"] != voxel_volume(16, 9, fill=0.2, counts=False)).sum() > 500
+    assert all((o[f"mip_mode{m}_2"] != 0).any() for m in (0, 1, 2))
