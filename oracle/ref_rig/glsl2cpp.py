@@ -14,7 +14,8 @@ the parts of GLSL that are not C++ are mapped, mechanically:
     variables, `in NAME {...} inst;`, `layout(...) buffer/uniform NAME {...};` (an unsized `T a[];` member becomes
     ssbo_array<T>), `layout(local_size...) in;` is dropped;
   * array constructors `T[](a, b, c)` -> `{a, b, c}`;  `x.length()` -> glsl_length(x);
-  * `out` / `inout` parameters -> references; `discard` -> throw Discard();
+  * `out` / `inout` parameters -> references; `discard` -> throw Discard(); `flat`, and `layout(..) coherent volatile` on image
+    parameters, are dropped;
   * floating literals get an `f` suffix (GLSL literals are fp32; C++ would evaluate in double);
   * `imageLoad` on a `uimage3D` -> imageLoadU (returns uvec4);  `void main()` -> `void shader_main()`.
 """
@@ -102,12 +103,15 @@ def float_suffix(text):
 def translate(shader_dir, name):
     src = "\n".join(resolve_includes(shader_dir, name)) + "\n"
     pre = subprocess.run(["g++", "-E", "-P", "-undef", "-x", "c++", "-"], input=src, capture_output=True, text=True, check=True).stdout
+    pre = re.sub(r"\bflat\s+", "", pre)                                            # interpolation qualifier inside interface blocks
     t = interface_blocks(pre)
     t = global_declarations(t)
     t = array_constructors(t)
     t = re.sub(r"\b(\w+)\.length\(\)", r"glsl_length(\1)", t)
     t = re.sub(r"\b(?:out|inout)\s+(\w+)\s+(\w+)", r"\1& \2", t)
     t = re.sub(r"([(,]\s*)in\s+(\w+\s+\w+)", r"\1\2", t)
+    t = re.sub(r"\blayout\s*\([^)]*\)\s*", "", t)                                   # what is left: qualifiers on image parameters
+    t = re.sub(r"\b(?:coherent|volatile)\s+", "", t)
     t = re.sub(r"\bdiscard\s*;", "throw Discard();", t)
     t = float_suffix(t)
     for u in re.findall(r"\buimage3D\s+(\w+)\s*;", t):

@@ -313,6 +313,7 @@ inline vec4 texel2d(const sampler2D& s, int l, int x, int y) {
 }
 inline vec4 lerp4(const vec4& a, const vec4& b, float t) { const float s = 1.0f - t; vec4 r; for (int i = 0; i < 4; ++i) r[i] = a[i] * s + b[i] * t; return r; }
 inline vec4 textureOffset(const sampler2D& s, const vec2& tc, const ivec2& off) {
+    if (!s.depth && !s.level) return vec4(0, 0, 0, 1);          // no texture bound to the unit
     if (s.depth) {
         const float x = tc.x * (float)s.size - 0.5f, y = tc.y * (float)s.size - 0.5f;
         const float fx = std::floor(x), fy = std::floor(y);

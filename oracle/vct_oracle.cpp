@@ -471,8 +471,9 @@ extern "C" void orc_occupancy(const orc_scene* sc, const vct_frame_params* fp, u
 }
 
 // Canonical fragment order: triangles in draw order, fragments of a triangle in raster-scan order.
-extern "C" void orc_voxelize(const orc_scene* sc, const vct_frame_params* fp, int D, const float* shadow, int S,
-                             const unsigned short* warpmap, unsigned* color, unsigned* normal, vct_voxelize_info* info) {
+static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D, const float* shadow, int S,
+                          const unsigned short* warpmap, unsigned* color, unsigned* normal, vct_voxelize_info* info,
+                          float* frag_rec, long long frag_cap, long long* frag_count) {
     Prepared P = prepare(sc, false);
     std::memset(color, 0, sizeof(unsigned) * (size_t)D * D * D);       // glClearTexImage, Application.cpp:686-687
     std::memset(normal, 0, sizeof(unsigned) * (size_t)D * D * D);
@@ -498,6 +499,11 @@ extern "C" void orc_voxelize(const orc_scene* sc, const vct_frame_params* fp, in
             V3 wp = interp3(l, w[0], w[1], w[2]);
             V3 nn = interp3(l, n[0], n[1], n[2]);
             const float u = interp(l, uv[0][0], uv[1][0], uv[2][0]), v = interp(l, uv[0][1], uv[1][1], uv[2][1]);
+            if (frag_rec && (long long)total <= frag_cap) {               // fragment-stage inputs (GS_OUT block + sampler state)
+                float* r = frag_rec + 16 * (size_t)(total - 1);
+                r[0] = ndc.x; r[1] = ndc.y; r[2] = ndc.z; r[3] = wp.x; r[4] = wp.y; r[5] = wp.z; r[6] = nn.x; r[7] = nn.y; r[8] = nn.z;
+                r[9] = u; r[10] = v; r[11] = (float)va.axis; r[12] = rho2; r[13] = (float)mat.diffuse_tex; r[14] = r[15] = 0.0f;
+            }
             V3 col = {0, 0, 0};
             if (dt) { V4 a = sample2d(*dt, u, v, rho2); col = {a.x, a.y, a.z}; }
             V3 N = normalize(nn);
@@ -541,6 +547,19 @@ extern "C" void orc_voxelize(const orc_scene* sc, const vct_frame_params* fp, in
         });
     }
     if (info) { info->total_fragments = total; info->unique_voxels = 0; info->max_fragments_per_voxel = 0; }
+    if (frag_count) *frag_count = total;
+}
+extern "C" void orc_voxelize(const orc_scene* sc, const vct_frame_params* fp, int D, const float* shadow, int S,
+                             const unsigned short* warpmap, unsigned* color, unsigned* normal, vct_voxelize_info* info) {
+    voxelize_impl(sc, fp, D, shadow, S, warpmap, color, normal, info, nullptr, 0, nullptr);
+}
+// Same pass, additionally recording what the rasteriser hands the fragment stage for every fragment, in canonical order:
+// 16 floats = GS_OUT{position(ndc) 3, worldPosition 3, normal 3, texcoord 2, axis} + rho2 of the diffuse lookup + diffuse
+// texture id (tests/test_glsl_ref.py replays them through the reference's voxelize.frag compiled as C++).
+extern "C" void orc_voxelize_trace(const orc_scene* sc, const vct_frame_params* fp, int D, const float* shadow, int S,
+                                   const unsigned short* warpmap, unsigned* color, unsigned* normal, vct_voxelize_info* info,
+                                   float* frag_rec, long long frag_cap, long long* frag_count) {
+    voxelize_impl(sc, fp, D, shadow, S, warpmap, color, normal, info, frag_rec, frag_cap, frag_count);
 }
 
 // =================================================================================================== a3
@@ -1030,9 +1049,9 @@ extern "C" void orc_shade(const orc_scene* sc, const vct_frame_params* fp, int W
     orc_shade_rows(sc, fp, W, H, 0, H, 1, vis, D, L, radiance_pyr, color_pyr, shadow, S, warpmap, image, cone_steps);
 }
 // rows y_lo, y_lo + y_stride, ... < y_hi only (bench.py's bounded CPU sample; other rows of `image` are untouched)
-extern "C" void orc_shade_rows(const orc_scene* sc, const vct_frame_params* fp, int W, int H, int y_lo, int y_hi, int y_stride,
-                               const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
-                               const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps) {
+static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, int H, int y_lo, int y_hi, int y_stride,
+                       const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
+                       const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec) {
     Prepared P = prepare(sc, true);
     Vol rad, colv; rad.D = colv.D = D; rad.L = colv.L = L;
     { size_t off = 0; for (int l = 0; l < L; ++l) { rad.lv[l] = radiance_pyr + off; colv.lv[l] = color_pyr ? color_pyr + off : nullptr; const size_t d = std::max(1, D >> l); off += d * d * d; } }
@@ -1071,6 +1090,12 @@ extern "C" void orc_shade_rows(const orc_scene* sc, const vct_frame_params* fp, 
             V3 fn = interp3(l, P.wnrm[ix[0]], P.wnrm[ix[1]], P.wnrm[ix[2]]);
             V3 Tt = interp3(l, P.T[ix[0]], P.T[ix[1]], P.T[ix[2]]), Bt = interp3(l, P.B[ix[0]], P.B[ix[1]], P.B[ix[2]]);
             V4 lsp = {interp(l, lfp[0].x, lfp[1].x, lfp[2].x), interp(l, lfp[0].y, lfp[1].y, lfp[2].y), interp(l, lfp[0].z, lfp[1].z, lfp[2].z), interp(l, lfp[0].w, lfp[1].w, lfp[2].w)};
+            if (frag_rec) {                                                   // VS_OUT block + material + uv footprint of this pixel
+                float* r = frag_rec + 28 * ((size_t)py * W + px);
+                const float rec[28] = {Pw.x, Pw.y, Pw.z, fn.x, fn.y, fn.z, u, v, lsp.x, lsp.y, lsp.z, lsp.w, Tt.x, Tt.y, Tt.z, Bt.x, Bt.y, Bt.z,
+                                     ux, vx, uy, vy, (float)sc->tri_material[t], 1.0f, 0, 0, 0, 0};
+                std::memcpy(r, rec, sizeof rec);
+            }
             auto tbn = [&](V3 d) -> V3 { return (Tt * d.x + Bt * d.y) + fn * d.z; };   // mat3(T,B,N) * d
             // phong.frag:427-439
             V3 N;
@@ -1149,6 +1174,20 @@ extern "C" void orc_shade_rows(const orc_scene* sc, const vct_frame_params* fp, 
             out = pack_unorm({col.x, col.y, col.z, 1.0f});
         }
     if (cone_steps) *cone_steps = fetch_total;
+}
+extern "C" void orc_shade_rows(const orc_scene* sc, const vct_frame_params* fp, int W, int H, int y_lo, int y_hi, int y_stride,
+                               const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
+                               const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps) {
+    shade_impl(sc, fp, W, H, y_lo, y_hi, y_stride, vis, D, L, radiance_pyr, color_pyr, shadow, S, warpmap, image, cone_steps, nullptr);
+}
+// Same pass, additionally recording the fragment-stage inputs of every covered pixel: 28 floats per pixel =
+// VS_OUT{fragPosition 3, fragNormal 3, fragTexcoord 2, lightFragPos 4, TBN columns T 3 and B 3 (the third is fragNormal)},
+// the uv differences to the right / upper neighbour pixel (du_x, dv_x, du_y, dv_y), material id, covered flag
+// (tests/test_glsl_ref.py replays them through the reference's phong.frag compiled as C++).
+extern "C" void orc_shade_trace(const orc_scene* sc, const vct_frame_params* fp, int W, int H, const unsigned long long* vis, int D, int L,
+                                const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
+                                const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec) {
+    shade_impl(sc, fp, W, H, 0, H, 1, vis, D, L, radiance_pyr, color_pyr, shadow, S, warpmap, image, cone_steps, frag_rec);
 }
 
 // closed-form KAT helper: one cone marched through a volume whose every level holds the same word

@@ -80,6 +80,15 @@ void orc_shade_rows(const orc_scene*, const vct_frame_params*, int W, int H, int
                     const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
                     const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps);
 
+/* Fragment-stage taps (tests/test_glsl_ref.py): the same passes, additionally recording what the rasteriser hands the
+ * fragment shader — 16 floats per voxel fragment in canonical order, 28 floats per pixel (layouts next to the definitions). */
+void orc_voxelize_trace(const orc_scene*, const vct_frame_params*, int D, const float* shadow, int S,
+                        const unsigned short* warpmap, unsigned* color, unsigned* normal, vct_voxelize_info* info,
+                        float* frag_rec, long long frag_cap, long long* frag_count);
+void orc_shade_trace(const orc_scene*, const vct_frame_params*, int W, int H, const unsigned long long* vis, int D, int L,
+                     const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
+                     const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec);
+
 /* KAT helpers */
 unsigned orc_rgba8_avg(unsigned stored, float r, float g, float b);     /* voxelize.frag:111-139, one insertion */
 unsigned orc_pack_unorm4x8(float r, float g, float b, float a);

@@ -174,3 +174,89 @@ def test_cases_are_not_vacuous():
     assert len({o[k].tobytes() for k in o if k.startswith("inject_")}) == 4                        # every mode differs
     assert (o["fill_holes_16"] != voxel_volume(16, 9, fill=0.2, counts=False)).sum() > 500
     assert all((o[f"mip_mode{m}_2"] != 0).any() for m in (0, 1, 2))
+
+
+# ============================================================ fragment shaders: voxelize.frag (a2) and phong.frag (a7)
+# The rasteriser (fixed function) is the oracle's: orc_voxelize_trace / orc_shade_trace record what it hands the fragment
+# stage; the reference's fragment shaders, compiled as C++, are then run on exactly those inputs, fragment by fragment in
+# the same order, and must leave the same voxel words / the same RGBA8 pixels.
+def pbr_room():
+    """tests' room scene with normal, roughness and metallic maps on two materials (every phong.frag branch is reachable)."""
+    from vct_b200 import scene as S
+    sc = S.room_scene()
+    rng = np.random.default_rng(77)
+    nm = np.clip(np.array([128, 128, 235]) + rng.integers(-60, 61, (32, 32, 3)), 0, 255).astype(np.uint8)
+    t_n = sc.add_texture(nm)
+    t_r = sc.add_texture(rng.integers(20, 256, (16, 16), dtype=np.uint8).astype(np.uint8))
+    t_m = sc.add_texture(rng.integers(0, 256, (8, 8), dtype=np.uint8).astype(np.uint8))
+    sc.materials[0].normal_tex = t_n; sc.materials[0].roughness_tex = t_r; sc.materials[0].metallic_tex = t_m
+    sc.materials[1].roughness_tex = t_r
+    return sc
+
+
+FRAG_MODES = {
+    "default": {},
+    "atomic_max": {"voxelize_atomic_max": 1},
+    "no_voxel_lighting": {"voxelize_lighting": 0},
+    "warp_voxels": {"warp_voxels": 1},
+    "warp_texture": {"warp_texture": 1},
+    "blinn_no_post": {"cooktorrance": 0, "enable_postprocess": 0},
+    "direct_only": {"enable_indirect": 0},
+    "no_reflections_no_normal_map": {"enable_reflections": 0, "enable_normal_map": 0, "draw_occlusion": 0},
+    "color_volume": {"draw_radiance": 0},
+    "fixed_specular_angle": {"specular_cone_angle_from_roughness": 0},
+}
+
+
+def run_fragment_cases(impl, modes=None):
+    from vct_b200 import scene as S
+    D, Lv, SS, W, H = 32, 5, 256, 96, 64
+    sc = pbr_room()
+    out = {}
+    for name, kw in FRAG_MODES.items():
+        if modes and name not in modes:
+            continue
+        p = S.room_params(W, H)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        o = O.Oracle(sc, D, Lv, SS, W, H)
+        o.shadowmap(p)
+        if p.warp_texture:
+            o.occupancy(p); o.warpmap_pass(p)
+        wm = ptr(o.warpmap) if p.warp_texture else None
+        cap = 1 << 18
+        rec = np.zeros(cap * 16, np.float32); n = C.c_longlong(0)
+        O.lib().orc_voxelize_trace(C.byref(o.s.c), C.byref(p), D, ptr(o.shadow), SS, wm, ptr(o.color[0]), ptr(o.normal), C.byref(o.info),
+                                   ptr(rec), C.c_longlong(cap), C.byref(n))
+        assert 1000 < n.value <= cap
+        if impl == "glsl":
+            col, nrm, info = np.zeros(D ** 3, np.uint32), np.zeros(D ** 3, np.uint32), P.VoxelizeInfo()
+            glsl().glsl_voxelize_fragments(C.byref(o.s.c), C.byref(p), D, ptr(o.shadow), SS, wm, ptr(rec), C.c_longlong(n.value), ptr(col), ptr(nrm), C.byref(info))
+            out[f"vox_{name}_color"], out[f"vox_{name}_normal"], out[f"vox_{name}_fragments"] = col, nrm, np.array([info.total_fragments], np.uint32)
+        else:
+            out[f"vox_{name}_color"], out[f"vox_{name}_normal"] = o.color[0].copy(), o.normal.copy()
+            out[f"vox_{name}_fragments"] = np.array([o.info.total_fragments], np.uint32)
+        o.transfer(p); o.inject(p); o.mip("radiance"); o.mip("color"); o.visibility(p)
+        rad, colp = np.concatenate(o.radiance), np.concatenate(o.color)
+        prec = np.zeros(W * H * 28, np.float32); steps = C.c_ulonglong(0)
+        O.lib().orc_shade_trace(C.byref(o.s.c), C.byref(p), W, H, ptr(o.vis), D, Lv, ptr(rad), ptr(colp), ptr(o.shadow), SS, wm, ptr(o.image), C.byref(steps), ptr(prec))
+        if impl == "glsl":
+            img = np.zeros(W * H, np.uint32); gsteps = C.c_ulonglong(0)
+            glsl().glsl_shade_pixels(C.byref(o.s.c), C.byref(p), W, H, ptr(prec), D, Lv, ptr(rad), ptr(colp), ptr(o.shadow), SS, wm, ptr(img), C.byref(gsteps))
+            out[f"shade_{name}_image"], out[f"shade_{name}_cone_steps"] = img, np.array([gsteps.value], np.uint64)
+        else:
+            out[f"shade_{name}_image"], out[f"shade_{name}_cone_steps"] = o.image.copy(), np.array([steps.value], np.uint64)
+    return out
+
+
+GOLD_FRAG = os.path.join(ROOT, "tests", "golden", "glsl_ref_fragment.npz")
+
+
+@live
+def test_oracle_fragment_stages_equal_the_reference_glsl_compiled_as_cpp():
+    compare(run_fragment_cases("oracle"), run_fragment_cases("glsl"), "oracle vs compiled voxelize.frag / phong.frag")
+
+
+def test_oracle_fragment_stages_equal_the_committed_outputs_of_the_reference_glsl():
+    gold = dict(np.load(GOLD_FRAG))
+    compare(run_fragment_cases("oracle"), gold, "oracle vs tests/golden/glsl_ref_fragment.npz")
