@@ -3,18 +3,27 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * library; the product (vct_b200/) never links, imports or calls it.
  *
- * PINNING.  The reference (sfreed141/vct @ c5c763d) has no tests and no golden vectors, and its GLSL cannot run in
- * the build container or on the GPU box (no OpenGL/EGL/Mesa, no GLM/GLFW).  What CAN run is the host C++ the path
- * contains, and the oracle is pinned against it bit for bit:
- *   - src/main.cpp:21-128 (the `#if 0` CPU warp example: partial sums, weights, calculateWarpPosition) and
- *   - src/Application.cpp:311-370 (per-frame warp-map tables: per-axis prefix counts + low/high weight table)
- *   are compiled FROM WHERE THEY LIE by oracle/Makefile into oracle/_ref/{warp_rig,warpmap_cpu}; their outputs are
- *   committed as tests/golden/warp_rig_ref.json and warpmap_cpu_ref.npz (generators next to them) and checked by
- *   tests/test_oracle_kat.py against orc_warp_rig / orc_warp_partials / orc_warp_weight_table.
- * PARITY UNPINNED for everything that is GLSL in the reference (voxelise, transfer, inject, mip, cone trace, the
- * two generateWarpmap fragment shaders): those functions are a line-by-line restatement with OpenGL's semantics
- * made explicit (DESIGN.md "Canonical GL semantics"), pinned only by known-answer values derived from the shader
- * arithmetic (tests/golden/kat.json, independent numpy restatement in tests/golden/make_kat.py).
+ * PINNING.  The reference (sfreed141/vct @ c5c763d) has no tests and no golden vectors, and no OpenGL stack exists in the
+ * build container or on the GPU box (no libGL/EGL/Mesa, no GLM/GLFW), so its binary cannot run.  Its SOURCES for the hot
+ * path can be compiled, though, and the oracle is pinned against them bit for bit (oracle/Makefile builds everything FROM
+ * WHERE THE SOURCES LIE into oracle/_ref/; nothing of the reference is stored in this repository):
+ *   - host C++: src/main.cpp:21-128 (the `#if 0` CPU warp example) and src/Application.cpp:311-370 (per-frame warp-map
+ *     tables) -> _ref/{warp_rig,warpmap_cpu}; fixtures tests/golden/warp_rig_ref.json, warpmap_cpu_ref.npz;
+ *     tests/test_oracle_kat.py checks orc_warp_rig / orc_warp_partials / orc_warp_weight_table against them;
+ *   - GLSL: transferVoxels.comp, filterRadiance.comp (BOX2/BOX3/CUBE), voxelFillHoles.comp, injectRadiance.comp,
+ *     setVoxelOpacity.comp, normalizeVoxels.comp, temporalRadianceFilter.comp, voxelize.frag and phong.frag (+ common.glsl)
+ *     are mapped to C++ SYNTAX by ref_rig/glsl2cpp.py (bodies untouched), compiled against ref_rig/glsl_shim.h into
+ *     _ref/libvct_glsl_ref.so and run on the same seeded inputs as the orc_* functions (compute shaders: whole dispatches;
+ *     fragment shaders: replayed on the fragment-stage inputs recorded by orc_voxelize_trace / orc_shade_trace);
+ *     tests/test_glsl_ref.py requires identical voxel words, counters, RGBA8 pixels and cone-step counts, live and against
+ *     the committed outputs tests/golden/glsl_ref.npz / glsl_ref_fragment.npz.
+ * What this pins: every expression, branch, constant and evaluation order of the shaders.  What it cannot pin, because it
+ * is the OpenGL IMPLEMENTATION's and not the reference's: rasteriser coverage/interpolation, texture filtering and LOD
+ * selection, unorm conversion, built-in function precision.  Those follow the OpenGL 4.5 specification with the canonical
+ * choices listed in DESIGN.md §2 ("Canonical GL semantics"), stated once in glsl_shim.h and once here.
+ * STILL UNPINNED (restated from the source, known-answer tests only, tests/golden/kat.json): the vertex/geometry stages
+ * (simple.vert, voxelize.vert/geom, phong.vert: matrix products and the dominant-axis pick), dither.frag /
+ * reflectiveShadowMap.frag (one alpha test each), generateWarpmap{,Weights}.frag and filter3d.comp.
  *
  * POD parameter structs are shared with the product's public header (the boundary spec); no code is.
  */
