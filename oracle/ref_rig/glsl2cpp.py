@@ -17,7 +17,7 @@ the parts of GLSL that are not C++ are mapped, mechanically:
   * `out` / `inout` parameters -> references; `discard` -> throw Discard(); `flat`, and `layout(..) coherent volatile` on image
     parameters, are dropped;
   * floating literals get an `f` suffix (GLSL literals are fp32; C++ would evaluate in double);
-  * `imageLoad` on a `uimage3D` -> imageLoadU (returns uvec4);  `void main()` -> `void shader_main()`.
+  * `imageLoad` on a `uimage3D` / `iimage3D` -> imageLoadU / imageLoadI (uvec4 / ivec4);  `void main()` -> `void shader_main()`.
 """
 import os
 import re
@@ -116,6 +116,8 @@ def translate(shader_dir, name):
     t = float_suffix(t)
     for u in re.findall(r"\buimage3D\s+(\w+)\s*;", t):
         t = re.sub(r"\bimageLoad\s*\(\s*" + u + r"\b", "imageLoadU(" + u, t)
+    for u in re.findall(r"\biimage3D\s+(\w+)\s*;", t):
+        t = re.sub(r"\bimageLoad\s*\(\s*" + u + r"\b", "imageLoadI(" + u, t)
     t = re.sub(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", t)
     return t
 
@@ -128,7 +130,7 @@ def main():
         f.write(f"// GENERATED by oracle/ref_rig/glsl2cpp.py from {os.path.join(shader_dir, name)} — do not commit.\n")
         f.write('#include "glsl_shim.h"\n#include <vector>\n#include <cstdio>\n')
         f.write("namespace glsl {\nnamespace " + ns + " {\n")
-        f.write("static ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\nstatic vec4 gl_FragCoord;\n")
+        f.write("static ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\nstatic vec4 gl_FragCoord; static int gl_Layer;\n")
         f.write(body)
         f.write("\n// ---- driver (this repository's code)\n")
         f.write(open(driver).read())

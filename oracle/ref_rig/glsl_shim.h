@@ -37,6 +37,9 @@ struct Swz {
     Swz& operator*=(T s) { return *this = V(*this) * s; }
     Swz& operator/=(T s) { return *this = V(*this) / s; }
     T operator[](int i) const { const int ix[4] = {A, B, C, D}; return d[ix[i]]; }
+    // GLSL converts an integer vector to the float vector of the same size implicitly: vec3 v = ivec4_value.xyz;
+    template <class F, class = std::enable_if_t<std::is_integral_v<T> && std::is_same_v<F, typename V::float_type>>>
+    operator F() const { return F(V(*this)); }
 };
 
 template <class T> struct tvec2;
@@ -44,6 +47,7 @@ template <class T> struct tvec3;
 template <class T> struct tvec4;
 
 template <class T> struct tvec2 {
+    typedef tvec2<float> float_type;
     union { T d[2]; struct { T x, y; }; struct { T r, g; }; struct { T s, t; }; Swz<tvec2<T>, T, 2, 2, 0, 1> xy; };
     tvec2() : d{T(0), T(0)} {}
     tvec2(const tvec2& o) : d{o.d[0], o.d[1]} {}
@@ -56,6 +60,7 @@ template <class T> struct tvec2 {
     T operator[](int i) const { return d[i]; }
 };
 template <class T> struct tvec3 {
+    typedef tvec3<float> float_type;
     union { T d[3]; struct { T x, y, z; }; struct { T r, g, b; };
             Swz<tvec2<T>, T, 3, 2, 0, 1> xy; Swz<tvec2<T>, T, 3, 2, 0, 2> xz; Swz<tvec2<T>, T, 3, 2, 1, 2> yz;
             Swz<tvec3<T>, T, 3, 3, 0, 1, 2> xyz, rgb; };
@@ -71,6 +76,7 @@ template <class T> struct tvec3 {
     T operator[](int i) const { return d[i]; }
 };
 template <class T> struct tvec4 {
+    typedef tvec4<float> float_type;
     union { T d[4]; struct { T x, y, z, w; }; struct { T r, g, b, a; };
             Swz<tvec2<T>, T, 4, 2, 0, 1> xy; Swz<tvec3<T>, T, 4, 3, 0, 1, 2> xyz, rgb; Swz<tvec4<T>, T, 4, 4, 0, 1, 2, 3> xyzw, rgba; };
     tvec4() : d{T(0), T(0), T(0), T(0)} {}
@@ -79,6 +85,7 @@ template <class T> struct tvec4 {
     template <class S, class = std::enable_if_t<std::is_arithmetic_v<S>>> explicit tvec4(S v) : d{T(v), T(v), T(v), T(v)} {}
     template <class S1, class S2, class S3, class S4, class = std::enable_if_t<std::is_arithmetic_v<S1> && std::is_arithmetic_v<S2> && std::is_arithmetic_v<S3> && std::is_arithmetic_v<S4>>>
     tvec4(S1 a, S2 b, S3 c, S4 e) : d{T(a), T(b), T(c), T(e)} {}
+    template <class U, class = std::enable_if_t<!std::is_same_v<U, T>>> tvec4(const tvec4<U>& o, std::enable_if_t<std::is_floating_point_v<T> && std::is_integral_v<U>, int> = 0) : d{T(o.d[0]), T(o.d[1]), T(o.d[2]), T(o.d[3])} {}
     template <class S, class = std::enable_if_t<std::is_arithmetic_v<S>>> tvec4(const tvec3<T>& a, S e) : d{a.d[0], a.d[1], a.d[2], T(e)} {}
     template <class S1, class S2, class = std::enable_if_t<std::is_arithmetic_v<S1> && std::is_arithmetic_v<S2>>> tvec4(const tvec2<T>& a, S1 c, S2 e) : d{a.d[0], a.d[1], T(c), T(e)} {}
     T& operator[](int i) { return d[i]; }
@@ -208,6 +215,7 @@ inline float sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f);
     inline V normalize(const V& a) { const float l = std::sqrt(dot(a, a)); V r; for (int i = 0; i < N; ++i) r[i] = a[i] / l; return r; } \
     inline V reflect(const V& I, const V& Nn) { return I - 2.0f * dot(Nn, I) * Nn; }
 GLSL_VEC_FUNCS(vec2, 2) GLSL_VEC_FUNCS(vec3, 3) GLSL_VEC_FUNCS(vec4, 4)
+inline vec3 mix(const vec3& a, const vec3& b, const tvec3<bool>& sel) { return vec3(sel[0] ? b.x : a.x, sel[1] ? b.y : a.y, sel[2] ? b.z : a.z); }
 inline vec3 cross(const vec3& a, const vec3& b) { return vec3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
 
 #define GLSL_REL(V, BV, N)                                                                                                      \
@@ -277,6 +285,18 @@ inline vec4 imageLoadF(const image3D& im, const ivec3& p) {
 inline vec4 imageLoad(const image3D& im, const ivec3& p) { return imageLoadF(im, p); }
 // imageLoad on a uimage3D (r32ui view): glsl2cpp.py routes those call sites here
 inline uvec4 imageLoadU(const image3D& im, const ivec3& p) { return uvec4(im.inside(p) ? ((const uint32_t*)im.data)[im.at(p)] : 0u, 0u, 0u, 1u); }
+// rgba32i volume (warpPartials; uploaded as GL_RGB_INTEGER, so alpha reads 1) and r32f 2D image (warpWeights)
+struct iimage3D { const int* data = nullptr; int w = 0, h = 0, d = 0, comps = 3; };
+inline ivec4 imageLoadI(const iimage3D& im, const ivec3& p) {
+    if (p.x < 0 || p.y < 0 || p.z < 0 || p.x >= im.w || p.y >= im.h || p.z >= im.d) return ivec4(0, 0, 0, 0);
+    const int* q = im.data + (((size_t)p.z * im.h + p.y) * im.w + p.x) * im.comps;
+    return ivec4(q[0], q[1], q[2], 1);
+}
+struct image2D { const float* data = nullptr; int w = 0, h = 0; };
+inline vec4 imageLoad(const image2D& im, const ivec2& p) {
+    if (p.x < 0 || p.y < 0 || p.x >= im.w || p.y >= im.h) return vec4(0);
+    return vec4(im.data[(size_t)p.y * im.w + p.x], 0, 0, 1);
+}
 inline void imageStore(image3D& im, const ivec3& p, const vec4& v) {
     if (!im.inside(p)) return;
     if (im.fmt == FMT_RGBA8) ((uint32_t*)im.data)[im.at(p)] = packUnorm4x8(v);
@@ -344,6 +364,7 @@ inline vec4 texture(const sampler2D& s, const vec2& tc) { return textureOffset(s
 struct sampler3D {
     const uint32_t* const* level = nullptr; int dim = 0, levels = 0;              // voxel pyramid
     const uint16_t* warp = nullptr; int wdim = 0;                                // warp map
+    const uint16_t* f16 = nullptr; int fdim = 0;                                  // RGBA16F render target sampled NEAREST / CLAMP_TO_EDGE
     unsigned long long* fetches = nullptr;
 };
 inline ivec3 textureSize(const sampler3D& s, int) { return s.warp ? ivec3(s.wdim) : ivec3(s.dim); }
@@ -382,7 +403,15 @@ inline vec4 textureOffset(const sampler3D& s, const vec3& tc, const ivec3& off) 
                          lerp3(warp_texel(s, x0, y0 + 1, z0 + k), warp_texel(s, x0 + 1, y0 + 1, z0 + k), ax), ay);
     return vec4(lerp3(plane[0], plane[1], az), 1.0f);
 }
-inline vec4 texture(const sampler3D& s, const vec3& tc) { return textureOffset(s, tc, ivec3(0, 0, 0)); }   // warp map only (level 0, LINEAR)
+inline vec4 texture(const sampler3D& s, const vec3& tc) {
+    if (s.f16) {                                                // warp-weight targets: NEAREST, CLAMP_TO_EDGE (Application.cpp:437-449)
+        int t[3];
+        for (int k = 0; k < 3; ++k) { t[k] = (int)std::floor(tc[k] * (float)s.fdim); t[k] = t[k] < 0 ? 0 : (t[k] >= s.fdim ? s.fdim - 1 : t[k]); }
+        const uint16_t* p = s.f16 + 4 * (((size_t)t[2] * s.fdim + t[1]) * s.fdim + t[0]);
+        return vec4(half_to_float(p[0]), half_to_float(p[1]), half_to_float(p[2]), half_to_float(p[3]));
+    }
+    return textureOffset(s, tc, ivec3(0, 0, 0));                 // warp map (level 0, LINEAR, CLAMP_TO_EDGE)
+}
 inline vec4 textureLod(const sampler3D& s, const vec3& tc, float lambda) {
     if (s.fetches) ++*s.fetches;
     const float top = (float)(s.levels - 1);

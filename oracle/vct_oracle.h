@@ -11,7 +11,8 @@
  *     tables) -> _ref/{warp_rig,warpmap_cpu}; fixtures tests/golden/warp_rig_ref.json, warpmap_cpu_ref.npz;
  *     tests/test_oracle_kat.py checks orc_warp_rig / orc_warp_partials / orc_warp_weight_table against them;
  *   - GLSL: transferVoxels.comp, filterRadiance.comp (BOX2/BOX3/CUBE), voxelFillHoles.comp, injectRadiance.comp,
- *     setVoxelOpacity.comp, normalizeVoxels.comp, temporalRadianceFilter.comp, voxelize.frag and phong.frag (+ common.glsl)
+ *     setVoxelOpacity.comp, normalizeVoxels.comp, temporalRadianceFilter.comp, voxelize.frag, phong.frag (+ common.glsl) and
+ *     generateWarpmapWeights.frag / generateWarpmap.frag
  *     are mapped to C++ SYNTAX by ref_rig/glsl2cpp.py (bodies untouched), compiled against ref_rig/glsl_shim.h into
  *     _ref/libvct_glsl_ref.so and run on the same seeded inputs as the orc_* functions (compute shaders: whole dispatches;
  *     fragment shaders: replayed on the fragment-stage inputs recorded by orc_voxelize_trace / orc_shade_trace);
@@ -23,7 +24,7 @@
  * choices listed in DESIGN.md §2 ("Canonical GL semantics"), stated once in glsl_shim.h and once here.
  * STILL UNPINNED (restated from the source, known-answer tests only, tests/golden/kat.json): the vertex/geometry stages
  * (simple.vert, voxelize.vert/geom, phong.vert: matrix products and the dominant-axis pick), dither.frag /
- * reflectiveShadowMap.frag (one alpha test each), generateWarpmap{,Weights}.frag and filter3d.comp.
+ * reflectiveShadowMap.frag (one alpha test each) and filter3d.comp (dead; uses textureLodOffset).
  *
  * POD parameter structs are shared with the product's public header (the boundary spec); no code is.
  */

@@ -260,3 +260,58 @@ def test_oracle_fragment_stages_equal_the_reference_glsl_compiled_as_cpp():
 def test_oracle_fragment_stages_equal_the_committed_outputs_of_the_reference_glsl():
     gold = dict(np.load(GOLD_FRAG))
     compare(run_fragment_cases("oracle"), gold, "oracle vs tests/golden/glsl_ref_fragment.npz")
+
+
+# ===================================================== a9: generateWarpmapWeights.frag + generateWarpmap.frag (thesis pass)
+def run_warpmap_cases(impl):
+    """Occupancy grids -> (CPU prefix sums + weight table, already pinned to Application.cpp:311-370) -> the two layered
+    fragment passes.  The oracle does everything inside orc_warpmap; the GLSL side gets the tables from the oracle's
+    orc_warp_partials / orc_warp_weight_table and runs the reference's two fragment shaders."""
+    out = {}
+    rng = np.random.default_rng(99)
+    grids = {"random10": (rng.random(32 ** 3) < 0.10), "random60": (rng.random(32 ** 3) < 0.60),
+             "empty": np.zeros(32 ** 3, bool), "full": np.ones(32 ** 3, bool)}
+    slab = np.zeros((32, 32, 32), bool); slab[4:9, :, 10:30] = True; slab[20, 3:7, :] = True
+    grids["slabs"] = slab.reshape(-1)
+    variants = {"default": {}, "no_weights_texture": {"use_warpmap_weights_texture": 0}, "linear": {"warp_texture_linear": 1},
+                "axes_x_only": {"warp_texture_axes": (1, 0, 0)}, "high3_low025": {"warp_texture_high_resolution": 3.0, "warp_texture_low_resolution": 0.25}}
+    for gname, g in grids.items():
+        occ = np.ascontiguousarray(g.astype(np.uint32))
+        for vname, kw in variants.items():
+            if gname not in ("random10", "slabs") and vname != "default":
+                continue
+            p, _ = frame_params(32, warp_texture=1)
+            for k, v in kw.items():
+                if k == "warp_texture_axes":
+                    for i in range(3):
+                        p.warp_texture_axes[i] = v[i]
+                else:
+                    setattr(p, k, v)
+            wm, lo, hi = np.zeros(32 ** 3 * 4, np.uint16), np.zeros(32 ** 3 * 4, np.uint16), np.zeros(32 ** 3 * 4, np.uint16)
+            if impl == "oracle":
+                O.lib().orc_warpmap(ptr(occ), C.byref(p), ptr(wm), ptr(lo), ptr(hi))
+            else:
+                parts = np.zeros(32 ** 3 * 3, np.int32)
+                O.lib().orc_warp_partials(ptr(occ), ptr(parts))
+                wl, wh = np.zeros(33, np.float32), np.zeros(33, np.float32)
+                O.lib().orc_warp_weight_table(32, C.c_float(p.warp_texture_high_resolution), C.c_float(p.warp_texture_low_resolution), ptr(wl), ptr(wh))
+                table = np.ascontiguousarray(np.concatenate([wl, wh]))
+                g_ = glsl()
+                g_.glsl_warp_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+                if p.use_warpmap_weights_texture:
+                    g_.glsl_warp_weights(ptr(occ), ptr(parts), ptr(table), p.warp_texture_high_resolution, ptr(lo), ptr(hi))
+                g_.glsl_warpmap(ptr(occ), ptr(parts), ptr(table), C.byref(p), ptr(lo), ptr(hi), ptr(wm))
+            out[f"warp_{gname}_{vname}_map"], out[f"warp_{gname}_{vname}_low"], out[f"warp_{gname}_{vname}_high"] = wm, lo, hi
+    return out
+
+
+GOLD_WARP = os.path.join(ROOT, "tests", "golden", "glsl_ref_warpmap.npz")
+
+
+@live
+def test_oracle_warpmap_equals_the_reference_glsl_compiled_as_cpp():
+    compare(run_warpmap_cases("oracle"), run_warpmap_cases("glsl"), "oracle vs compiled generateWarpmap{,Weights}.frag")
+
+
+def test_oracle_warpmap_equals_the_committed_outputs_of_the_reference_glsl():
+    compare(run_warpmap_cases("oracle"), dict(np.load(GOLD_WARP)), "oracle vs tests/golden/glsl_ref_warpmap.npz")
