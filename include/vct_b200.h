@@ -106,7 +106,22 @@ typedef struct {
     float ambient_scale, reflect_scale;
     vct_cone_settings diffuse_cone, specular_cone;
     int   specular_cone_angle_from_roughness;
+    /* debug views of phong.frag (Settings::drawVoxels/drawNormals/drawDominantAxis/debug*, Application.cpp:992-1005;
+     * Overlay.cpp toggles): one VCT_VIEW_* value instead of nine booleans, in the shader's own priority order. */
+    int   debug_view;       /* VCT_VIEW_SHADED (0) = the normal frame */
+    float miplevel;         /* Settings::miplevel: lod of VCT_VIEW_VOXELS (phong.frag:350-401) */
 } vct_frame_params;
+
+enum { VCT_VIEW_SHADED = 0,
+       VCT_VIEW_VOXELS = 1,            /* `voxelize`: the traced volume sampled at the fragment's voxel, lod = miplevel   phong.frag:347-404 */
+       VCT_VIEW_MATERIAL_DIFFUSE = 2,  /* debugMaterialDiffuse / Roughness / Metallic                                    :405-425 */
+       VCT_VIEW_MATERIAL_ROUGHNESS = 3,
+       VCT_VIEW_MATERIAL_METALLIC = 4,
+       VCT_VIEW_NORMALS = 5,           /* `normals`: the shading normal after normal mapping                              :441-443 */
+       VCT_VIEW_DOMINANT_AXIS = 6,     /* `dominant_axis`                                                                 :444-447 */
+       VCT_VIEW_INDIRECT = 7,          /* debugIndirect: the six diffuse cones (x occlusion if draw_occlusion)            :489 */
+       VCT_VIEW_OCCLUSION = 8,         /* debugOcclusion                                                                  :490 */
+       VCT_VIEW_REFLECTIONS = 9 };     /* debugReflections: the specular cone                                             :505 */
 
 /* GLBufferedTimer results in ns, same names as reference src/Application.h:192 (+ producers). */
 typedef struct {

@@ -1099,6 +1099,24 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
                 std::memcpy(r, rec, sizeof rec);
             }
             auto tbn = [&](V3 d) -> V3 { return (Tt * d.x + Bt * d.y) + fn * d.z; };   // mat3(T,B,N) * d
+            const int view = fp->debug_view;
+            if (view == VCT_VIEW_VOXELS) {                                    // phong.frag:347-404 (`voxelize`; normals/warp-slope sub-views not built)
+                V3 gp = get_voxel_position(Pw, fp, warpmap);
+                const float Df = (float)D;
+                V3 vi = {(Df * gp.x) / Df, (Df * gp.y) / Df, (Df * gp.z) / Df};   // voxelIndex(...) / voxelDim
+                V4 c = vol_sample(vol, vi, fp->miplevel);
+                fetch_total += 1;                                             // a volume fetch like any cone step
+                out = pack_unorm({c.x, c.y, c.z, 1.0f});
+                continue;
+            }
+            if (view == VCT_VIEW_MATERIAL_DIFFUSE || view == VCT_VIEW_MATERIAL_ROUGHNESS || view == VCT_VIEW_MATERIAL_METALLIC) {   // :405-425
+                V3 c = {0.5f, 0.0f, 0.5f};
+                if (view == VCT_VIEW_MATERIAL_DIFFUSE && mat.diffuse_tex >= 0) { V4 t4 = fetch(mat.diffuse_tex); c = {t4.x, t4.y, t4.z}; }
+                if (view == VCT_VIEW_MATERIAL_ROUGHNESS && mat.roughness_tex >= 0) { const float r = fetch(mat.roughness_tex).x; c = {r, r, r}; }
+                if (view == VCT_VIEW_MATERIAL_METALLIC && mat.metallic_tex >= 0) { const float r = fetch(mat.metallic_tex).x; c = {r, r, r}; }
+                out = pack_unorm({c.x, c.y, c.z, 1.0f});
+                continue;
+            }
             // phong.frag:427-439
             V3 N;
             if (fp->enable_normal_map && mat.normal_tex >= 0) {
@@ -1106,6 +1124,12 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
                 V3 n = normalize(v3(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f));
                 N = normalize(tbn(n));
             } else N = normalize(fn);
+            if (view == VCT_VIEW_NORMALS) { out = pack_unorm({N.x, N.y, N.z, 1.0f}); continue; }   // :441-443
+            if (view == VCT_VIEW_DOMINANT_AXIS) {                            // :444-447  step(vec3(max component), |n|)
+                const float ax = std::fabs(N.x), ay = std::fabs(N.y), az = std::fabs(N.z), m = maxf(maxf(ax, ay), az);
+                out = pack_unorm({ax < m ? 0.0f : 1.0f, ay < m ? 0.0f : 1.0f, az < m ? 0.0f : 1.0f, 1.0f});
+                continue;
+            }
             V4 dc4 = mat.diffuse_tex >= 0 ? fetch(mat.diffuse_tex) : V4{mat.diffuse[0], mat.diffuse[1], mat.diffuse[2], 1.0f};
             V3 dc = {dc4.x, dc4.y, dc4.z};
             // calculateDirectLighting, phong.frag:305-344
@@ -1158,6 +1182,11 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
                     ind = {ind.x + wts[i] * c.x, ind.y + wts[i] * c.y, ind.z + wts[i] * c.z, ind.w + wts[i] * c.w};
                 }
                 const float occl = 1.0f - clampf(ind.w, 0.0f, 1.0f);
+                if (view == VCT_VIEW_INDIRECT) {                              // :489  (returns before reflections and post-processing)
+                    const float k = fp->draw_occlusion ? occl : 1.0f;
+                    fetch_total += f; out = pack_unorm({ind.x * k, ind.y * k, ind.z * k, 1.0f}); continue;
+                }
+                if (view == VCT_VIEW_OCCLUSION) { fetch_total += f; out = pack_unorm({occl, occl, occl, 1.0f}); continue; }   // :490
                 if (fp->enable_reflections) {
                     float ang = fp->specular_cone.cone_angle;
                     if (fp->specular_cone_angle_from_roughness && mat.roughness_tex >= 0) ang = (fetch(mat.roughness_tex).x * PI_REF) * 0.1f;
@@ -1166,6 +1195,7 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
                     V4 rc = trace_cone(vol, fp, warpmap, vp, N, R, fp->specular_cone.steps, fp->specular_cone.bias, ang,
                                        fp->specular_cone.cone_initial_height, fp->specular_cone.lod_offset, f);
                     ind.x += rc.x * fp->reflect_scale; ind.y += rc.y * fp->reflect_scale; ind.z += rc.z * fp->reflect_scale;
+                    if (view == VCT_VIEW_REFLECTIONS) { fetch_total += f; out = pack_unorm({rc.x, rc.y, rc.z, 1.0f}); continue; }   // :505
                 }
                 fetch_total += f;
                 V3 indc = v3(ind.x, ind.y, ind.z) * (dc * fp->ambient_scale);  // indirect.rgb *= ambientScale * diffuseColor.rgb

@@ -205,6 +205,20 @@ FRAG_MODES = {
     "no_reflections_no_normal_map": {"enable_reflections": 0, "enable_normal_map": 0, "draw_occlusion": 0},
     "color_volume": {"draw_radiance": 0},
     "fixed_specular_angle": {"specular_cone_angle_from_roughness": 0},
+    # debug views of phong.frag
+    "view_voxels_point": {"debug_view": P.VIEW_VOXELS, "miplevel": 0.0},
+    "view_voxels_lod1_7": {"debug_view": P.VIEW_VOXELS, "miplevel": 1.7},
+    "view_voxels_color_warp": {"debug_view": P.VIEW_VOXELS, "miplevel": 0.8, "draw_radiance": 0, "warp_voxels": 1},
+    "view_material_diffuse": {"debug_view": P.VIEW_MATERIAL_DIFFUSE},
+    "view_material_roughness": {"debug_view": P.VIEW_MATERIAL_ROUGHNESS},
+    "view_material_metallic": {"debug_view": P.VIEW_MATERIAL_METALLIC},
+    "view_normals": {"debug_view": P.VIEW_NORMALS},
+    "view_dominant_axis": {"debug_view": P.VIEW_DOMINANT_AXIS},
+    "view_indirect": {"debug_view": P.VIEW_INDIRECT},
+    "view_indirect_no_occlusion": {"debug_view": P.VIEW_INDIRECT, "draw_occlusion": 0},
+    "view_occlusion": {"debug_view": P.VIEW_OCCLUSION},
+    "view_reflections": {"debug_view": P.VIEW_REFLECTIONS},
+    "view_reflections_off": {"debug_view": P.VIEW_REFLECTIONS, "enable_reflections": 0},
 }
 
 

@@ -351,7 +351,9 @@ __device__ __forceinline__ LR cook_torrance(V3 dc, V3 lc, V3 N, V3 V, V3 L, V3 H
 }
 
 // TPB threads per CTA (TPB/32 warps side by side, each an 8x4 pixel tile); 512/TPB CTAs per SM = 16 warps at 128 registers.
-template <int WM, bool SL, int TPB>
+// DBG: the debug views of phong.frag (vct_frame_params::debug_view != 0; :346-447, 489-505) live in their own instantiation,
+// so the shaded frame's code is the same with or without them (every DBG test below is a compile-time constant).
+template <int WM, bool SL, int TPB, bool DBG = false>
 __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
     const FrameConst& fc = *a.fc;
     const vct_frame_params& fp = fc.p;
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
         const size_t o = (size_t)py * a.W + px;
         const unsigned long long key = a.vis[o];
         if (key == ~0ull) a.image[o] = pack_unorm(mk4(fp.clear_color[0], fp.clear_color[1], fp.clear_color[2], 1.0f));
-        else {
+        else do {                                                         // `break` = the shader's early `return`
             const uint32_t t = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
             const uint32_t i0 = __ldg(a.indices + 3 * (size_t)t), i1 = __ldg(a.indices + 3 * (size_t)t + 1), i2 = __ldg(a.indices + 3 * (size_t)t + 2);
             const V3 w0 = f4to3(__ldg(a.wpos + i0)), w1 = f4to3(__ldg(a.wpos + i1)), w2 = f4to3(__ldg(a.wpos + i2));
@@ -425,11 +427,40 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
             const V4 lf0 = mul44(fc.ls, mk4(w0.x, w0.y, w0.z, 1.0f)), lf1 = mul44(fc.ls, mk4(w1.x, w1.y, w1.z, 1.0f)), lf2 = mul44(fc.ls, mk4(w2.x, w2.y, w2.z, 1.0f));
             const V4 lsp = mk4(ip(l, lf0.x, lf1.x, lf2.x), ip(l, lf0.y, lf1.y, lf2.y), ip(l, lf0.z, lf1.z, lf2.z), ip(l, lf0.w, lf1.w, lf2.w));
             auto tbn = [&](V3 d) { return (Tt * d.x + Bt * d.y) + fn * d.z; };
+            const int view = DBG ? fp.debug_view : 0;
+            if (DBG && view == VCT_VIEW_VOXELS) {                            // phong.frag:347-404: the traced volume at this fragment's voxel
+                V3 gp = voxel_linear_position(Pw, fp);
+                if (WM == WARP_VOXELS) gp = voxel_warp(gp, voxel_linear_position(mk3(fp.eye[0], fp.eye[1], fp.eye[2]), fp));
+                else if (WM == WARP_TEXTURE) gp = warp_sample(reinterpret_cast<const ushort4*>(a.warp), gp);
+                const float Df = (float)fc.D;
+                const V3 vi = mk3(__fdiv_rn(__fmul_rn(Df, gp.x), Df), __fdiv_rn(__fmul_rn(Df, gp.y), Df), __fdiv_rn(__fmul_rn(Df, gp.z), Df));   // voxelIndex(..) / voxelDim
+                const float lambda = fp.miplevel;
+                float4 sc;
+                if (!(lambda > 0.5f)) sc = tex3DLod<float4>(a.vol_point, vi.x, vi.y, vi.z, 0.0f);
+                else sc = tex3DLod<float4>(a.vol, vi.x, vi.y, vi.z, fminf(lambda, (float)(fc.L - 1)));
+                fetches++;
+                a.image[o] = pack_unorm(mk4(sc.x, sc.y, sc.z, 1.0f));
+                break;
+            }
+            if (DBG && (view == VCT_VIEW_MATERIAL_DIFFUSE || view == VCT_VIEW_MATERIAL_ROUGHNESS || view == VCT_VIEW_MATERIAL_METALLIC)) {   // :405-425
+                V3 c = mk3(0.5f, 0.0f, 0.5f);
+                if (view == VCT_VIEW_MATERIAL_DIFFUSE && mat.diffuse_tex >= 0) { const V4 t4 = fetch(mat.diffuse_tex); c = mk3(t4.x, t4.y, t4.z); }
+                if (view == VCT_VIEW_MATERIAL_ROUGHNESS && mat.roughness_tex >= 0) { const float r = fetch(mat.roughness_tex).x; c = mk3(r, r, r); }
+                if (view == VCT_VIEW_MATERIAL_METALLIC && mat.metallic_tex >= 0) { const float r = fetch(mat.metallic_tex).x; c = mk3(r, r, r); }
+                a.image[o] = pack_unorm(mk4(c.x, c.y, c.z, 1.0f));
+                break;
+            }
             V3 N;
             if (fp.enable_normal_map && mat.normal_tex >= 0) {
                 const V4 nm = fetch(mat.normal_tex);
                 N = normalize3(tbn(normalize3(mk3(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f))));
             } else N = normalize3(fn);
+            if (DBG && view == VCT_VIEW_NORMALS) { a.image[o] = pack_unorm(mk4(N.x, N.y, N.z, 1.0f)); break; }     // :441-443
+            if (DBG && view == VCT_VIEW_DOMINANT_AXIS) {                     // :444-447  step(vec3(max component), |n|)
+                const float ax = fabsf(N.x), ay = fabsf(N.y), az = fabsf(N.z), m = fmaxf(fmaxf(ax, ay), az);
+                a.image[o] = pack_unorm(mk4(ax < m ? 0.0f : 1.0f, ay < m ? 0.0f : 1.0f, az < m ? 0.0f : 1.0f, 1.0f));
+                break;
+            }
             const V4 dc4 = mat.diffuse_tex >= 0 ? fetch(mat.diffuse_tex) : mk4(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2], 1.0f);
             const V3 dc = mk3(dc4.x, dc4.y, dc4.z);
             const V3 eye = mk3(fp.eye[0], fp.eye[1], fp.eye[2]);
@@ -488,6 +519,12 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
                     for (int i = 0; i < 6; ++i) ind = mk4(ind.x + wts[i] * cs.acc[i].x, ind.y + wts[i] * cs.acc[i].y, ind.z + wts[i] * cs.acc[i].z, ind.w + wts[i] * cs.acc[i].w);
                 }
                 const float occl = 1.0f - clampf(ind.w, 0.0f, 1.0f);
+                if (DBG && view == VCT_VIEW_INDIRECT) {                      // :489 (before reflections and post-processing)
+                    const float k = fp.draw_occlusion ? occl : 1.0f;
+                    a.image[o] = pack_unorm(mk4(ind.x * k, ind.y * k, ind.z * k, 1.0f));
+                    break;
+                }
+                if (DBG && view == VCT_VIEW_OCCLUSION) { a.image[o] = pack_unorm(mk4(occl, occl, occl, 1.0f)); break; }   // :490
                 if (fp.enable_reflections) {
                     const V3 I = Pw - eye;
                     const V3 R = I - N * (2.0f * dot3(N, I));
@@ -500,6 +537,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
                         rc = trace_cone_ahead<4, WM, SL>(cx, s_specular, start, normalize3(R) * scale, fetches);
                     }
                     ind.x += rc.x * fp.reflect_scale; ind.y += rc.y * fp.reflect_scale; ind.z += rc.z * fp.reflect_scale;
+                    if (DBG && view == VCT_VIEW_REFLECTIONS) { a.image[o] = pack_unorm(mk4(rc.x, rc.y, rc.z, 1.0f)); break; }   // :505
                 }
                 const V3 indc = mk3(ind.x, ind.y, ind.z) * (dc * fp.ambient_scale);
                 col = (indc + dsum) + ssum;
@@ -511,7 +549,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
                 col = mk3(powf(col.x, g), powf(col.y, g), powf(col.z, g));
             }
             a.image[o] = pack_unorm(mk4(col.x, col.y, col.z, 1.0f));
-        }
+        } while (0);
     }
 #pragma unroll
     for (int s = 16; s; s >>= 1) fetches += __shfl_xor_sync(0xffffffffu, fetches, s);
@@ -581,7 +619,14 @@ int vctk_cone_trace(vct_ctx* c) {
         else k_cone_trace<WM, SLV, kThreads><<<grid, kThreads, 0, c->stream>>>(a);                             \
     } while (0)
 #define VCT_TRACE(WM) do { if (sl) VCT_TRACE2(WM, true); else VCT_TRACE2(WM, false); } while (0)
-    if (p.warp_voxels) VCT_TRACE(WARP_VOXELS);
+    if (p.debug_view != VCT_VIEW_SHADED) {                      // debug views: own instantiation, default CTA size, no shared-memory last level
+        if (p.debug_view < 0 || p.debug_view > VCT_VIEW_REFLECTIONS) { c->error = "vct_cone_trace: unknown debug_view"; return 1; }
+        dim3 dgrid((c->W + kThreads / 4 - 1) / (kThreads / 4), (a.y_hi - a.y_lo + 3) / 4);
+        if (p.warp_voxels) k_cone_trace<WARP_VOXELS, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
+        else if (p.warp_texture) k_cone_trace<WARP_TEXTURE, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
+        else k_cone_trace<WARP_NONE, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
+    }
+    else if (p.warp_voxels) VCT_TRACE(WARP_VOXELS);
     else if (p.warp_texture) VCT_TRACE(WARP_TEXTURE);
     else VCT_TRACE(WARP_NONE);
 #undef VCT_TRACE

@@ -30,7 +30,8 @@ int main(int argc, char** argv) {
         std::fprintf(argc < 2 ? stderr : stdout,
                      "usage: vct_headless scene.vcts|mesh.obj [--scale s] [--resources dir] [--dim D] [--levels L] [--size WxH] [--shadow S] [--frames N]\n"
                      "       [--camera x y z yaw pitch | --eye x y z --front fx fy fz] [--volume min max] [--center x y z]\n"
-                     "       [--no-reflections] [--atomic-max] [--warp-texture] [--temporal] [--fused] [--out frame.ppm]\n");
+                     "       [--no-reflections] [--atomic-max] [--warp-texture] [--temporal] [--fused] [--out frame.ppm]\n"
+                     "       [--view voxels|normals|dominant-axis|occlusion|indirect|reflections|material-diffuse|material-roughness|material-metallic] [--miplevel x]\n");
         return argc < 2 ? 2 : 0;
     }
     Application app;
@@ -57,6 +58,16 @@ int main(int argc, char** argv) {
         else if (a == "--atomic-max") app.settings.voxelizeAtomicMax = true;
         else if (a == "--warp-texture") app.settings.warpTexture = true;
         else if (a == "--temporal") app.settings.temporalFilterRadiance = true;
+        else if (a == "--view") {                                           // one of the reference's debug toggles (Overlay.cpp), by name
+            need(i, 1); const std::string v = argv[++i];
+            Settings& st = app.settings;
+            if (v == "voxels") st.drawVoxels = true; else if (v == "normals") st.drawNormals = true; else if (v == "dominant-axis") st.drawDominantAxis = true;
+            else if (v == "occlusion") st.debugOcclusion = true; else if (v == "indirect") st.debugIndirect = true; else if (v == "reflections") st.debugReflections = true;
+            else if (v == "material-diffuse") st.debugMaterialDiffuse = true; else if (v == "material-roughness") st.debugMaterialRoughness = true;
+            else if (v == "material-metallic") st.debugMaterialMetallic = true;
+            else { std::fprintf(stderr, "unknown view %s\n", v.c_str()); return 2; }
+        }
+        else if (a == "--miplevel") { need(i, 1); app.settings.miplevel = (float)std::atof(argv[++i]); }
         else if (a == "--fused") fused = true;
         else if (a == "--out") { need(i, 1); out = argv[++i]; }
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }

@@ -95,6 +95,10 @@ inline mat4 inverse(const mat4& a) {                                           /
 struct VCTSettings { int steps; float coneAngle, bias, coneInitialHeight, lodOffset; };
 struct Settings {
     int drawRadiance = true, axisOverride = -1, drawOcclusion = true;
+    // debug views, Application.h:40-60 (all false by default); frameParams() folds them into vct_frame_params::debug_view
+    int drawVoxels = false, drawNormals = false, drawDominantAxis = false, debugOcclusion = false, debugIndirect = false, debugReflections = false;
+    int debugMaterialDiffuse = false, debugMaterialRoughness = false, debugMaterialMetallic = false;
+    float miplevel = 0.0f;
     int cooktorrance = true, enablePostprocess = true, enableNormalMap = true;
     int enableIndirect = true, enableDiffuse = true, enableSpecular = true, enableReflections = true;
     float ambientScale = 1.0f, reflectScale = 1.0f;
@@ -303,6 +307,11 @@ public:
         auto cone = [](const VCTSettings& c) { vct_cone_settings o; o.steps = c.steps; o.cone_angle = c.coneAngle; o.bias = c.bias; o.cone_initial_height = c.coneInitialHeight; o.lod_offset = c.lodOffset; return o; };
         p.diffuse_cone = cone(s.diffuseConeSettings); p.specular_cone = cone(s.specularConeSettings);
         p.specular_cone_angle_from_roughness = s.specularConeAngleFromRoughness;
+        // phong.frag tests its debug uniforms in this order (:346-447, 489-505)
+        p.debug_view = s.drawVoxels ? VCT_VIEW_VOXELS : s.debugMaterialDiffuse ? VCT_VIEW_MATERIAL_DIFFUSE : s.debugMaterialRoughness ? VCT_VIEW_MATERIAL_ROUGHNESS
+                     : s.debugMaterialMetallic ? VCT_VIEW_MATERIAL_METALLIC : s.drawNormals ? VCT_VIEW_NORMALS : s.drawDominantAxis ? VCT_VIEW_DOMINANT_AXIS
+                     : s.debugIndirect ? VCT_VIEW_INDIRECT : s.debugOcclusion ? VCT_VIEW_OCCLUSION : s.debugReflections ? VCT_VIEW_REFLECTIONS : VCT_VIEW_SHADED;
+        p.miplevel = s.miplevel;
         return p;
     }
 

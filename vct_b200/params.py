@@ -13,6 +13,8 @@ WARP_DIM = 32
 F16 = C.c_float * 16
 F3 = C.c_float * 3
 
+VIEW_SHADED, VIEW_VOXELS, VIEW_MATERIAL_DIFFUSE, VIEW_MATERIAL_ROUGHNESS, VIEW_MATERIAL_METALLIC = 0, 1, 2, 3, 4
+VIEW_NORMALS, VIEW_DOMINANT_AXIS, VIEW_INDIRECT, VIEW_OCCLUSION, VIEW_REFLECTIONS = 5, 6, 7, 8, 9
 VOL_COLOR, VOL_NORMAL, VOL_RADIANCE, VOL_OCCUPANCY, VOL_WARPMAP, VOL_WARP_WEIGHTS_LOW, VOL_WARP_WEIGHTS_HIGH, BUF_IMAGE = range(8)
 
 
@@ -76,6 +78,7 @@ class FrameParams(C.Structure):
         ("enable_reflections", C.c_int), ("ambient_scale", C.c_float), ("reflect_scale", C.c_float),
         ("diffuse_cone", ConeSettings), ("specular_cone", ConeSettings),
         ("specular_cone_angle_from_roughness", C.c_int),
+        ("debug_view", C.c_int), ("miplevel", C.c_float),
     ]
 
 
