@@ -394,3 +394,72 @@ def test_vct_ingest_upload_renders_like_the_oracle(tmp_path):
     mse = ((a - b) ** 2).mean()
     assert mse == 0 or 10 * np.log10(255.0 ** 2 / mse) >= 45.0
     g.close(); ref.close()
+
+
+def test_hostile_files_never_crash_the_host_process(tmp_path):
+    """The reference's loaders index unchecked (tinyobjloader, Mesh::loadMesh) and trust image headers; a library must not:
+    byte-mutated OBJ/MTL/DDS files, out-of-range and huge relative indices, PNG headers promising terabytes and a
+    decompression bomb all end in a status + log line (or a smaller mesh), in-process."""
+    import struct
+    import zlib
+    rng = np.random.default_rng(2024)
+    lib = L.load()
+
+    def obj_status(data, name="f.obj"):
+        p = tmp_path / name; p.write_bytes(data)
+        h = C.c_void_p()
+        rc = lib.vct_ingest_obj(str(p).encode(), str(tmp_path).encode(), 1, C.byref(h))      # 1 = VCT_INGEST_NO_TEXTURES
+        m = P.IngestMesh(); lib.vct_ingest_get_mesh(h, C.byref(m))
+        n = (m.n_vertices, m.n_indices)
+        if m.n_indices:                                                     # every index must address a vertex
+            idx = np.ctypeslib.as_array(m.indices, (m.n_indices,))
+            assert idx.max() < m.n_vertices
+        log = lib.vct_ingest_log(h).decode(errors="replace")
+        lib.vct_ingest_free(h)
+        return rc, n, log
+
+    good = open(os.path.join(GOLD, "fan.obj"), "rb").read()
+    (tmp_path / "mats.mtl").write_bytes(open(os.path.join(GOLD, "mats.mtl"), "rb").read())
+    assert obj_status(good)[1] == (18, 24)
+    rc, n, log = obj_status(b"v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1 2 3\nf 1 2 9\nf -7 1 2\nf 1/5/1 2/1/9 3//-4\nf 2147483647 1 2\nf -2147483648 1 2\n")
+    assert rc == 0 and n == (4, 6) and "dropped" in log                     # two valid triangles survive; out-of-range vt / vn read as absent
+    for k in range(300):
+        d = bytearray(good)
+        for _ in range(1 + k % 6):
+            d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+        obj_status(bytes(d))
+    mtl = bytearray(open(os.path.join(GOLD, "mats.mtl"), "rb").read())
+    for k in range(100):
+        d = bytearray(mtl)
+        for _ in range(1 + k % 4):
+            d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+        (tmp_path / "mats.mtl").write_bytes(bytes(d))
+        obj_status(good)
+
+    def img_status(data, name):
+        p = tmp_path / name; p.write_bytes(data)
+        h = C.c_void_p()
+        rc = lib.vct_ingest_image(str(p).encode(), 1, C.byref(h))
+        log = lib.vct_ingest_log(h).decode(errors="replace")
+        lib.vct_ingest_free(h)
+        return rc, log
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xFFFFFFFF)
+    sig = b"\x89PNG\r\n\x1a\n"
+    huge = sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 1 << 23, 1 << 23, 16, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    rc, log = img_status(huge, "huge.png")
+    assert rc == 1 and "too large" in log
+    bomb = sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 4, 4, 8, 0, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * (64 << 20), 9)) + chunk(b"IEND", b"")
+    assert len(bomb) < 100000
+    rc, log = img_status(bomb, "bomb.png")
+    assert rc == 1 and "more data than the image needs" in log
+    short = sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 64, 64, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 100)) + chunk(b"IEND", b"")
+    assert img_status(short, "short.png") == (1, "png: not enough pixel data")
+    dds = bytearray(_dds(16, 16, b"DXT5", 3, bytes(rng.integers(0, 256, 16 * 16 + 64 + 16, dtype=np.uint8))))
+    assert img_status(bytes(dds), "ok.dds")[0] == 0
+    for k in range(200):
+        d = bytearray(dds)
+        for _ in range(1 + k % 5):
+            d[int(rng.integers(0, 128))] = int(rng.integers(0, 256))       # header bytes: sizes, mip counts, fourcc
+        img_status(bytes(d), "m.dds")

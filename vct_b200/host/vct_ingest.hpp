@@ -266,8 +266,19 @@ inline bool load_obj(const std::string& path, IngestMesh& out) {
     std::vector<std::vector<uint32_t>> per_material(n_mat);
     std::map<std::tuple<int, int, int>, uint32_t> seen;
     std::vector<float>& V = out.vertices;
-    for (const Tri& tr : tris) {
+    const int nv = (int)(v.size() / 3), nvn = (int)(vn.size() / 3), nvt = (int)(vt.size() / 2);
+    size_t dropped = 0;
+    for (Tri tr : tris) {
         if (tr.material >= (int)n_mat - 1) continue;                   // cannot happen: ids come from this file's materials
+        // A corner that names a vertex the file does not have is undefined behaviour in the reference (tinyobjloader and
+        // Mesh::loadMesh index their arrays unchecked).  Here: the triangle is dropped, a missing normal / uv reads as absent.
+        bool bad = false;
+        for (Corner& c : tr.c) {
+            if (c.v < 0 || c.v >= nv) bad = true;
+            if (c.vn >= nvn || c.vn < -1) c.vn = -1;
+            if (c.vt >= nvt || c.vt < -1) c.vt = -1;
+        }
+        if (bad) { ++dropped; continue; }
         std::vector<uint32_t>& list = per_material[tr.material < 0 ? n_mat - 1 : (size_t)tr.material];
         uint32_t id[3];
         for (int k = 0; k < 3; ++k) {
@@ -296,6 +307,7 @@ inline bool load_obj(const std::string& path, IngestMesh& out) {
         for (int a = 0; a < 3; ++a) { tg[a] = inv * (dv2 * e1[a] - dv1 * e2[a]); bt[a] = inv * (du2 * e1[a] - du1 * e2[a]); }
         for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) { V[14 * (size_t)id[k] + 8 + a] += tg[a]; V[14 * (size_t)id[k] + 11 + a] += bt[a]; }
     }
+    if (dropped) out.warnings += std::to_string(dropped) + " triangle(s) reference vertices the file does not define: dropped\n";
     float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
     float hi[3] = {1.175494351e-38f, 1.175494351e-38f, 1.175494351e-38f};                               // numeric_limits<float>::min() [sic], Mesh.cpp:128
     for (size_t i = 0; i < V.size() / 14; ++i) {

@@ -78,7 +78,8 @@ struct Huffman {
     }
 };
 
-inline bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out, std::string& err) {
+// `max_out`: the caller knows how many bytes a valid stream produces; anything longer is an error (no decompression bombs)
+inline bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out, std::string& err, size_t max_out = ~(size_t)0) {
     static const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     static const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
     static const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -94,6 +95,7 @@ inline bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out,
             const uint32_t len = br.bits(16), nlen = br.bits(16);
             if ((len ^ 0xFFFFu) != nlen) { err = "inflate: stored block length check failed"; return false; }
             if (br.used + (size_t)len * 8 > br.total) { err = "inflate: truncated stored block"; return false; }
+            if (out.size() + len > max_out) { err = "inflate: more data than the image needs"; return false; }
             for (uint32_t i = 0; i < len; ++i) out.push_back((uint8_t)br.bits(8));
             continue;
         }
@@ -131,7 +133,12 @@ inline bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out,
         for (;;) {
             const int s = lit.decode(br);
             if (s < 0) { err = "inflate: invalid literal/length code"; return false; }
-            if (s < 256) { out.push_back((uint8_t)s); if (br.exhausted()) { err = "inflate: truncated stream"; return false; } continue; }
+            if (s < 256) {
+                if (out.size() >= max_out) { err = "inflate: more data than the image needs"; return false; }
+                out.push_back((uint8_t)s);
+                if (br.exhausted()) { err = "inflate: truncated stream"; return false; }
+                continue;
+            }
             if (s == 256) break;
             if (s > 285) { err = "inflate: invalid length symbol"; return false; }
             const uint32_t len = len_base[s - 257] + br.bits(len_extra[s - 257]);
@@ -139,6 +146,7 @@ inline bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out,
             if (d < 0 || d > 29) { err = "inflate: invalid distance code"; return false; }
             const size_t back = dist_base[d] + br.bits(dist_extra[d]);
             if (back > out.size()) { err = "inflate: distance reaches before the start of the output"; return false; }
+            if (out.size() + len > max_out) { err = "inflate: more data than the image needs"; return false; }
             const size_t at = out.size();
             out.resize(at + len);
             for (uint32_t i = 0; i < len; ++i) out[at + i] = out[at + i - back];       // overlapping copies replicate
@@ -151,13 +159,13 @@ inline bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out,
 
 // zlib wrapper (RFC 1950): 2-byte header checked like stb_image does (multiple of 31, method 8, no preset dictionary);
 // the Adler-32 trailer is not verified (stb_image does not verify it either).
-inline bool inflate_zlib(const uint8_t* src, size_t n, std::vector<uint8_t>& out, std::string& err) {
+inline bool inflate_zlib(const uint8_t* src, size_t n, std::vector<uint8_t>& out, std::string& err, size_t max_out = ~(size_t)0) {
     if (n < 2) { err = "zlib: stream too short"; return false; }
     const int cmf = src[0], flg = src[1];
     if ((cmf * 256 + flg) % 31 != 0) { err = "zlib: bad header"; return false; }
     if (flg & 32) { err = "zlib: preset dictionary not allowed"; return false; }
     if ((cmf & 15) != 8) { err = "zlib: bad compression method"; return false; }
-    return inflate_raw(src + 2, n - 2, out, err);
+    return inflate_raw(src + 2, n - 2, out, err, max_out);
 }
 
 inline uint32_t be32(const uint8_t* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
@@ -251,13 +259,25 @@ inline Image decode_png(const uint8_t* data, size_t size) {
     }
     if (w == 0 || idat.empty()) { im.error = "png: no image data"; return im; }
     if (color == 3 && pal_len == 0) { im.error = "png: palette image without PLTE"; return im; }
-    std::vector<uint8_t> raw;
-    raw.reserve((size_t)w * h * 4 + h);
-    if (!inflate_zlib(idat.data(), idat.size(), raw, im.error)) return im;
-
     const int file_ch = color == 3 ? 1 : ((color & 2) ? 3 : 1) + ((color & 4) ? 1 : 0);
     const int out_ch = color == 3 ? (has_trns ? 4 : 3) : file_ch + ((has_trns && !(color & 4)) ? 1 : 0);
     const int bits = file_ch * depth;
+    // bytes a valid IDAT stream inflates to: one filter byte + the packed row, per row (per Adam7 pass when interlaced)
+    size_t expected = 0;
+    if (!interlace) expected = (size_t)h * (((size_t)w * bits + 7) / 8 + 1);
+    else {
+        static const int xo[7] = {0, 4, 0, 2, 0, 1, 0}, yo[7] = {0, 0, 4, 0, 2, 0, 1}, xs[7] = {8, 8, 4, 4, 2, 2, 1}, ys[7] = {8, 8, 8, 4, 4, 2, 2};
+        for (int p = 0; p < 7; ++p) {
+            const size_t pw = ((size_t)w + xs[p] - 1 - xo[p]) / xs[p], ph = ((size_t)h + ys[p] - 1 - yo[p]) / ys[p];
+            if ((int)w > xo[p] && (int)h > yo[p]) expected += ph * ((pw * bits + 7) / 8 + 1);
+        }
+    }
+    if (expected > ((size_t)1 << 31) || (size_t)w * h * out_ch > ((size_t)1 << 31)) { im.error = "png: image too large"; return im; }
+    std::vector<uint8_t> raw;
+    raw.reserve(expected);
+    if (!inflate_zlib(idat.data(), idat.size(), raw, im.error, expected)) return im;
+    if (raw.size() < expected) { im.error = "png: not enough pixel data"; return im; }
+
     im.width = (int)w; im.height = (int)h; im.channels = out_ch; im.levels = 1;
     im.pixels.assign((size_t)w * h * out_ch, 0);
 
