@@ -16,6 +16,7 @@ the parts of GLSL that are not C++ are mapped, mechanically:
   * array constructors `T[](a, b, c)` -> `{a, b, c}`;  `x.length()` -> glsl_length(x);
   * `out` / `inout` parameters -> references; `discard` -> throw Discard(); `flat`, and `layout(..) coherent volatile` on image
     parameters, are dropped;
+  * unsized per-vertex arrays of tessellation stages get the patch size 3; `T x = x(...)` calls the function x (GLSL scoping);
   * floating literals get an `f` suffix (GLSL literals are fp32; C++ would evaluate in double);
   * `imageLoad` on a `uimage3D` / `iimage3D` -> imageLoadU / imageLoadI (uvec4 / ivec4);  `void main()` -> `void shader_main()`.
 """
@@ -84,12 +85,13 @@ def global_declarations(text):
     qual = re.compile(r"^\s*(?:layout\s*\([^)]*\)\s*)?((?:(?:uniform|readonly|writeonly|coherent|restrict|flat|smooth|in|out)\s+)+)")
     for line in text.splitlines():
         if depth == 0:
-            if re.match(r"^\s*layout\s*\([^)]*\)\s*in\s*;", line):
+            if re.match(r"^\s*layout\s*\([^)]*\)\s*(?:in|out)\s*;", line):
                 line = ""
             else:
                 m = qual.match(line)
                 if m:
                     line = "static " + line[m.end():]
+                    line = re.sub(r"\[\s*\]\s*;", "[3];", line)                  # per-vertex arrays of a 3-vertex patch
         depth += line.count("{") - line.count("}")
         out.append(line)
     return "\n".join(out)
@@ -100,13 +102,15 @@ def float_suffix(text):
     return lit.sub(lambda m: m.group(1) + "f", text)
 
 
-def translate(shader_dir, name):
+def translate(shader_dir, name, ns):
     src = "\n".join(resolve_includes(shader_dir, name)) + "\n"
     pre = subprocess.run(["g++", "-E", "-P", "-undef", "-x", "c++", "-"], input=src, capture_output=True, text=True, check=True).stdout
     pre = re.sub(r"\bflat\s+", "", pre)                                            # interpolation qualifier inside interface blocks
     t = interface_blocks(pre)
     t = global_declarations(t)
     t = array_constructors(t)
+    # `T name = name(...)`: in GLSL the variable is not yet in scope in its own initialiser and the call finds the function
+    t = re.sub(r"\b(\w+)\s+(\w+)\s*=\s*\2\s*\(", lambda m: f"{m.group(1)} {m.group(2)} = {ns}::{m.group(2)}(", t)
     t = re.sub(r"\b(\w+)\.length\(\)", r"glsl_length(\1)", t)
     t = re.sub(r"\b(?:out|inout)\s+(\w+)\s+(\w+)", r"\1& \2", t)
     t = re.sub(r"([(,]\s*)in\s+(\w+\s+\w+)", r"\1\2", t)
@@ -125,12 +129,13 @@ def translate(shader_dir, name):
 def main():
     shader_dir, name, driver, out = sys.argv[1:5]
     ns = re.sub(r"\W", "_", name)
-    body = translate(shader_dir, name)
+    body = translate(shader_dir, name, ns)
     with open(out, "w") as f:
         f.write(f"// GENERATED by oracle/ref_rig/glsl2cpp.py from {os.path.join(shader_dir, name)} — do not commit.\n")
         f.write('#include "glsl_shim.h"\n#include <vector>\n#include <cstdio>\n')
         f.write("namespace glsl {\nnamespace " + ns + " {\n")
-        f.write("static ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\nstatic vec4 gl_FragCoord; static int gl_Layer;\n")
+        f.write("static ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\nstatic vec4 gl_FragCoord; static int gl_Layer;\n"
+                "static int gl_InvocationID; static float gl_TessLevelInner[2], gl_TessLevelOuter[4]; static vec3 gl_TessCoord; static vec4 gl_Position;\n")
         f.write(body)
         f.write("\n// ---- driver (this repository's code)\n")
         f.write(open(driver).read())

@@ -564,6 +564,153 @@ extern "C" void orc_voxelize_trace(const orc_scene* sc, const vct_frame_params* 
     voxelize_impl(sc, fp, D, shadow, S, warpmap, color, normal, info, frag_rec, frag_cap, frag_count);
 }
 
+// ============================================================================= a1'/a2' tessellation voxeliser (N4)
+// The reference's DEFAULT voxeliser (Settings::voxelizeTesselation = true, src/Application.cpp:585-665): every triangle is a
+// patch; testTesselation.tesc picks tessellation levels from its size in voxels; the fixed-function tessellator
+// (triangles, equal_spacing, point_mode) emits one point per distinct vertex of the subdivision; testTesselation.tese stores
+// the UNLIT diffuse texel at each point's voxel (atomicMax by default).  Nothing is rasterised.
+// Canonical fixed function (OpenGL 4.5 §11.2.2, GL_MAX_TESS_GEN_LEVEL = 64):
+//   * a patch with an outer level <= 0 (or NaN) is discarded;
+//   * equal_spacing: every level is clamped to [1, 64] and rounded up to an integer; inner level 1 with an outer level > 1 counts
+//     as 2; inner = outer = 1 yields the three corners only;
+//   * concentric triangles: ring j >= 1 of inner level n is the triangle with corners (1-4j/(3n), 2j/(3n), 2j/(3n)) (and cyclic)
+//     whose edges carry m = n-2j segments (m = 0: the single centre point); ring 0 is the patch itself with outer[0] segments on
+//     the u = 0 edge, outer[1] on v = 0, outer[2] on w = 0;
+//   * every barycentric coordinate is ONE fp32 division of two exactly representable integers (numerator/denominator below), so the
+//     three coordinates of a point are symmetric under relabelling;
+//   * emission order (only matters for the running average): ring 0 corners (1,0,0), (0,1,0), (0,0,1), then the interior points of
+//     the edges w = 0 (from u=1 to v=1), u = 0 (v=1 to w=1), v = 0 (w=1 to u=1); then rings 1, 2, ... each walked A->B->C->A.
+namespace {
+inline float glsl_max(float x, float y) { return x < y ? y : x; }          // GLSL max(x, y): y if x < y, otherwise x
+struct TessLevels { float inner, outer[3]; };
+// testTesselation.tesc:32-78
+inline TessLevels tess_control(const V3 w[3], const vct_frame_params* fp, float voxelDim) {
+    TessLevels t = {1.0f, {1.0f, 1.0f, 1.0f}};
+    int vox[3][3];
+    for (int k = 0; k < 3; ++k) {
+        V3 vp = voxel_linear_position(w[k], fp);                           // tcVoxelPosition
+        const float c[3] = {voxelDim * vp.x, voxelDim * vp.y, voxelDim * vp.z};
+        for (int a = 0; a < 3; ++a) vox[k][a] = (int)c[a];                 // ivec3(vec3): truncation (values are finite for finite input)
+    }
+    bool same = true;
+    for (int a = 0; a < 3; ++a) same = same && vox[0][a] == vox[1][a] && vox[0][a] == vox[2][a];
+    if (same) { t.inner = 0.0f; t.outer[0] = t.outer[1] = t.outer[2] = 0.0f; return t; }
+    const V3 a = w[0], b = w[1], c = w[2];
+    const V3 A = c - b, B = c - a, C = b - a;
+    const float lx = length(A), ly = length(B), lz = length(C);
+    const float s = ((lx + ly) + lz) * 0.5f;
+    const float area = std::sqrt(((s * (s - lx)) * (s - ly)) * (s - lz));
+    const float ax = (2.0f * area) / lx, ay = (2.0f * area) / ly, az = (2.0f * area) / lz;
+    const float max_alt = glsl_max(ax, glsl_max(ay, az));
+    const V3 vs = {(fp->voxel_max[0] - fp->voxel_min[0]) / voxelDim, (fp->voxel_max[1] - fp->voxel_min[1]) / voxelDim, (fp->voxel_max[2] - fp->voxel_min[2]) / voxelDim};
+    const float dx = std::fabs(length(normalize(A) * vs)), dy = std::fabs(length(normalize(B) * vs)), dz = std::fabs(length(normalize(C) * vs));
+    const float ox = glsl_max(1.0f, lx / dx), oy = glsl_max(1.0f, ly / dy), oz = glsl_max(1.0f, lz / dz);
+    t.inner = glsl_max(1.0f, max_alt / vs.x);
+    t.outer[0] = oz; t.outer[1] = ox; t.outer[2] = oy;
+    return t;
+}
+inline int tess_round(float level) {                                        // equal_spacing: clamp to [1, 64], round up
+    if (!(level > 1.0f)) return 1;
+    if (level >= 64.0f) return 64;
+    return (int)std::ceil(level);
+}
+// calls emit(u, v, w) for every distinct vertex of the subdivision, in the canonical order
+template <class F>
+inline void tess_points(const TessLevels& t, F&& emit) {
+    for (int k = 0; k < 3; ++k) if (!(t.outer[k] > 0.0f)) return;          // discarded patch (also NaN)
+    int n = tess_round(t.inner);
+    const int o[3] = {tess_round(t.outer[0]), tess_round(t.outer[1]), tess_round(t.outer[2])};
+    emit(1.0f, 0.0f, 0.0f); emit(0.0f, 1.0f, 0.0f); emit(0.0f, 0.0f, 1.0f);
+    if (n == 1 && o[0] == 1 && o[1] == 1 && o[2] == 1) return;
+    if (n == 1) n = 2;
+    for (int i = 1; i < o[2]; ++i) { const float q = (float)i / (float)o[2], r = (float)(o[2] - i) / (float)o[2]; emit(r, q, 0.0f); }   // w = 0: u=1 -> v=1
+    for (int i = 1; i < o[0]; ++i) { const float q = (float)i / (float)o[0], r = (float)(o[0] - i) / (float)o[0]; emit(0.0f, r, q); }   // u = 0: v=1 -> w=1
+    for (int i = 1; i < o[1]; ++i) { const float q = (float)i / (float)o[1], r = (float)(o[1] - i) / (float)o[1]; emit(q, 0.0f, r); }   // v = 0: w=1 -> u=1
+    for (int j = 1; n - 2 * j >= 0; ++j) {
+        const int m = n - 2 * j;
+        if (m == 0) { const float third = 1.0f / 3.0f; emit(third, third, third); break; }
+        const float den = (float)(3 * n * m), small = (float)(2 * j) / (float)(3 * n);
+        for (int e = 0; e < 3; ++e)
+            for (int i = 0; i < m; ++i) {
+                const float big = (float)((3 * n - 4 * j) * (m - i) + 2 * j * i) / den;      // coordinate falling from the ring corner
+                const float rise = (float)(2 * j * (m - i) + (3 * n - 4 * j) * i) / den;     // coordinate rising towards the next corner
+                if (e == 0) emit(big, rise, small); else if (e == 1) emit(small, big, rise); else emit(rise, small, big);
+            }
+    }
+}
+}  // namespace
+
+// testTesselation.tese:82-147 per point; voxelStore (:60-80).  frag_rec (optional): 8 floats per point = triangle id, u, v, w, pad.
+static void voxelize_tess_impl(const orc_scene* sc, const vct_frame_params* fp, int D, unsigned* color, unsigned* normal, vct_voxelize_info* info,
+                               float* rec, long long rec_cap, long long* rec_count) {
+    Prepared P = prepare(sc, false);
+    std::memset(color, 0, sizeof(unsigned) * (size_t)D * D * D);           // glClearTexImage, Application.cpp:626-627
+    std::memset(normal, 0, sizeof(unsigned) * (size_t)D * D * D);
+    const float voxelDim = (float)D;                                       // uniform float voxelDim
+    long long count = 0;
+    for (int t = 0; t < sc->n_tris; ++t) {
+        const unsigned* ix = sc->indices + 3 * (size_t)t;
+        const V3 w[3] = {P.wpos[ix[0]], P.wpos[ix[1]], P.wpos[ix[2]]}, n[3] = {P.wnrm[ix[0]], P.wnrm[ix[1]], P.wnrm[ix[2]]};
+        float uv[3][2];
+        for (int k = 0; k < 3; ++k) { uv[k][0] = sc->vertices[14 * (size_t)ix[k] + 6]; uv[k][1] = sc->vertices[14 * (size_t)ix[k] + 7]; }
+        const TessLevels tl = tess_control(w, fp, voxelDim);
+        const vct_material& mat = sc->materials[sc->tri_material[t]];
+        const Tex* dt = mat.diffuse_tex >= 0 ? &P.tex[mat.diffuse_tex] : nullptr;
+        tess_points(tl, [&](float u, float v, float ww) {
+            if (rec && count < rec_cap) { float* r = rec + 8 * (size_t)count; r[0] = (float)t; r[1] = u; r[2] = v; r[3] = ww; r[4] = r[5] = r[6] = r[7] = 0.0f; }
+            ++count;
+            if (!color) return;
+            const V3 pos = (w[0] * u + w[1] * v) + w[2] * ww;               // gl_TessCoord.x * tcPosition[0] + .y * [1] + .z * [2]
+            const V3 nn = (n[0] * u + n[1] * v) + n[2] * ww;
+            const float tu = (u * uv[0][0] + v * uv[1][0]) + ww * uv[2][0], tv = (u * uv[0][1] + v * uv[1][1]) + ww * uv[2][1];
+            V4 col = {0, 0, 0, 1};
+            if (dt) col = sample2d(*dt, tu, tv, 0.0f);                     // no derivatives in a TES: base level, magnification -> NEAREST
+            // (the branch for patches inside one voxel, :128-131, is unreachable: those patches have tessellation level 0)
+            V3 vp = get_voxel_position(pos, fp, nullptr);                  // voxelIndex(position, int(voxelDim), ..., false): warpVoxels off
+            vp = {voxelDim * vp.x, voxelDim * vp.y, voxelDim * vp.z};      // (int(voxelDim) * pos with an integral voxelDim)
+            int idx[3];
+            if (!to_index(vp, D, idx)) return;
+            const size_t o = ((size_t)idx[2] * D + idx[1]) * D + idx[0];
+            const V3 N = normalize(nn);
+            const V3 nenc = {N.x * 0.5f + 0.5f, N.y * 0.5f + 0.5f, N.z * 0.5f + 0.5f};
+            if (fp->voxelize_atomic_max) {                                  // :69-74 (texture alpha is part of the packed word)
+                color[o] = std::max(color[o], pack_unorm(col));
+                normal[o] = std::max(normal[o], pack_unorm({nenc.x, nenc.y, nenc.z, 1.0f}));
+            } else {                                                        // :75-78
+                color[o] = rgba8_avg_insert(color[o], col.x, col.y, col.z);
+                normal[o] = rgba8_avg_insert(normal[o], nenc.x, nenc.y, nenc.z);
+            }
+        });
+    }
+    if (info) { info->total_fragments = 0; info->unique_voxels = 0; info->max_fragments_per_voxel = 0; }   // the TES counts nothing
+    if (rec_count) *rec_count = count;
+}
+// vertex stage of simpleTesselated.vert / voxelize.vert for every vertex: world position and normalMatrix * normal (3 floats each)
+extern "C" void orc_world_vertices(const orc_scene* sc, float* wpos, float* wnrm) {
+    Prepared P = prepare(sc, false);
+    for (int i = 0; i < sc->n_vertices; ++i) {
+        wpos[3 * i] = P.wpos[i].x; wpos[3 * i + 1] = P.wpos[i].y; wpos[3 * i + 2] = P.wpos[i].z;
+        wnrm[3 * i] = P.wnrm[i].x; wnrm[3 * i + 1] = P.wnrm[i].y; wnrm[3 * i + 2] = P.wnrm[i].z;
+    }
+}
+extern "C" void orc_voxelize_tess(const orc_scene* sc, const vct_frame_params* fp, int D, unsigned* color, unsigned* normal, vct_voxelize_info* info) {
+    voxelize_tess_impl(sc, fp, D, color, normal, info, nullptr, 0, nullptr);
+}
+// the same pass, additionally recording (triangle, u, v, w) of every emitted point; with color == NULL only the points are produced
+extern "C" void orc_voxelize_tess_trace(const orc_scene* sc, const vct_frame_params* fp, int D, unsigned* color, unsigned* normal, vct_voxelize_info* info,
+                                        float* rec, long long rec_cap, long long* rec_count) {
+    voxelize_tess_impl(sc, fp, D, color, normal, info, rec, rec_cap, rec_count);
+}
+// fixed function + TCS of one triangle given by world positions (tests): levels[4] = inner, outer[0..2]; returns the point count
+extern "C" long long orc_tess_patch(const float* wpos9, const vct_frame_params* fp, int D, float* levels4, float* uvw, long long cap) {
+    const V3 w[3] = {{wpos9[0], wpos9[1], wpos9[2]}, {wpos9[3], wpos9[4], wpos9[5]}, {wpos9[6], wpos9[7], wpos9[8]}};
+    const TessLevels tl = tess_control(w, fp, (float)D);
+    if (levels4) { levels4[0] = tl.inner; levels4[1] = tl.outer[0]; levels4[2] = tl.outer[1]; levels4[3] = tl.outer[2]; }
+    long long n = 0;
+    tess_points(tl, [&](float u, float v, float ww) { if (uvw && n < cap) { uvw[3 * n] = u; uvw[3 * n + 1] = v; uvw[3 * n + 2] = ww; } ++n; });
+    return n;
+}
+
 // =================================================================================================== a3
 // transferVoxels.comp:29-70 (RGBA8 build) + radiance clear unless temporal (Application.cpp:762-764)
 extern "C" void orc_transfer(const vct_frame_params* fp, int D, unsigned* color, unsigned* radiance, vct_voxelize_info* info) {

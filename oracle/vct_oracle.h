@@ -58,6 +58,13 @@ void orc_shadowmap(const orc_scene*, const vct_frame_params*, int S, float* dept
 /* a1+a2 voxelise (raster path) — voxelize.vert/geom/frag.  warpmap = 32^3 x 4 u16 or NULL. */
 void orc_voxelize(const orc_scene*, const vct_frame_params*, int D, const float* shadow, int S,
                   const unsigned short* warpmap, unsigned* color, unsigned* normal, vct_voxelize_info* info);
+/* a1'/a2' tessellation voxeliser (reference default) — simpleTesselated.vert, testTesselation.tesc/.tese,
+ * Application.cpp:585-665; canonical fixed-function tessellation stated next to the definition */
+void orc_voxelize_tess(const orc_scene*, const vct_frame_params*, int D, unsigned* color, unsigned* normal, vct_voxelize_info* info);
+void orc_voxelize_tess_trace(const orc_scene*, const vct_frame_params*, int D, unsigned* color, unsigned* normal, vct_voxelize_info* info,
+                             float* rec, long long rec_cap, long long* rec_count);
+void orc_world_vertices(const orc_scene*, float* wpos3, float* wnrm3);
+long long orc_tess_patch(const float* wpos9, const vct_frame_params*, int D, float* levels4, float* uvw, long long cap);
 /* a9(1) occupancy voxelise at 32^3 — voxelize.frag:187-193 */
 void orc_occupancy(const orc_scene*, const vct_frame_params*, unsigned* occ);
 /* a9(2-4) warpmap — Application.cpp:303-370 + generateWarpmap{Weights}.frag.  outputs 32^3 x 4 */

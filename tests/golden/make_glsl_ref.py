@@ -20,3 +20,6 @@ if __name__ == "__main__":
     out = T.run_warpmap_cases("glsl")
     np.savez_compressed(T.GOLD_WARP, **out)
     print(len(out), "arrays,", os.path.getsize(T.GOLD_WARP), "bytes")
+    out = T.run_tess_cases("glsl")
+    np.savez_compressed(T.GOLD_TESS, **out)
+    print(len(out), "arrays,", os.path.getsize(T.GOLD_TESS), "bytes")

@@ -329,3 +329,105 @@ def test_oracle_warpmap_equals_the_reference_glsl_compiled_as_cpp():
 
 def test_oracle_warpmap_equals_the_committed_outputs_of_the_reference_glsl():
     compare(run_warpmap_cases("oracle"), dict(np.load(GOLD_WARP)), "oracle vs tests/golden/glsl_ref_warpmap.npz")
+
+
+# ========================================== N4: tessellation voxeliser — testTesselation.tesc / .tese (the reference's default)
+def _tess_patch(w9, p, D, cap=8192):
+    lev = np.zeros(4, np.float32); uvw = np.zeros(cap * 3, np.float32)
+    O.lib().orc_tess_patch.restype = C.c_longlong
+    n = O.lib().orc_tess_patch(ptr(np.ascontiguousarray(w9, np.float32)), C.byref(p), D, ptr(lev), ptr(uvw), C.c_longlong(cap))
+    return lev, uvw[:3 * min(n, cap)].reshape(-1, 3), n
+
+
+def random_triangles(n, seed, scale):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-3.0, 3.0, (n, 1, 3)); e = rng.normal(0, 1, (n, 3, 3)) * rng.choice(scale, (n, 1, 1))
+    t = (c + e).astype(np.float32)
+    t[0] = [[0, 0, 0], [0, 0, 0], [0, 0, 0]]; t[1] = [[1, 1, 1], [2, 2, 2], [3, 3, 3]]          # degenerate: point, collinear
+    t[2] = [[0.1, 0.1, 0.1], [0.1001, 0.1, 0.1], [0.1, 0.1001, 0.1]]                           # inside one voxel: discarded
+    return t.reshape(n, 9)
+
+
+def test_canonical_tessellator_invariants():
+    """OpenGL 4.5 §11.2.2.1 (triangles, equal_spacing, point_mode) as the oracle states it: point counts, no duplicates,
+    barycentric sums, symmetry under relabelling, and the spec's special cases."""
+    p, _ = frame_params(64)
+    D = 64
+    counts = {}
+    for w9 in random_triangles(200, 5, [0.02, 0.1, 0.4, 1.5]):
+        lev, uvw, n = _tess_patch(w9, p, D)
+        if not (lev[1:] > 0).all():
+            assert n == 0                                                   # discarded patch
+            continue
+        rnd = lambda x: 1 if not x > 1 else 64 if x >= 64 else int(np.ceil(x))
+        ni, o = rnd(lev[0]), [rnd(x) for x in lev[1:]]
+        if ni == 1 and o == [1, 1, 1]:
+            want = 3
+        else:
+            ni = max(ni, 2)
+            want = 3 + sum(x - 1 for x in o) + sum(3 * (ni - 2 * j) if ni - 2 * j > 0 else 1 for j in range(1, ni // 2 + 1))
+        assert n == want == len(uvw), (lev, n, want)
+        assert np.abs(uvw.sum(axis=1) - 1).max() < 3e-7 and uvw.min() >= 0 and uvw.max() <= 1
+        assert len({tuple(r) for r in uvw.tolist()}) == n                    # distinct vertices, each emitted once
+        counts[n] = counts.get(n, 0) + 1
+        # inner rings are invariant under cyclic relabelling of the corners
+        inner = uvw[3 + sum(x - 1 for x in o):]
+        assert {tuple(r) for r in inner.tolist()} == {tuple(np.roll(r, 1)) for r in inner.tolist()}
+    assert len(counts) > 20 and max(counts) > 1000
+    lev, uvw, n = _tess_patch([0, 0, 0, 0.2, 0, 0, 0, 0.2, 0], p, D)       # ~1.6 voxels per edge -> outer 2.., inner small
+    assert n >= 4 and (uvw[:3] == np.eye(3, dtype=np.float32)).all()
+
+
+@live
+def test_tess_control_shader_equals_the_reference_glsl():
+    """testTesselation.tesc:32-78 (levels from edge lengths / altitudes in voxels; 0 for a patch inside one voxel), bit for bit,
+    incl. degenerate triangles (NaN altitudes go through GLSL max(1.0, NaN) = 1.0)."""
+    g = glsl(); g.glsl_tess_control.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    for D in (32, 256):
+        p, _ = frame_params(D)
+        for w9 in random_triangles(400, 7, [0.01, 0.05, 0.3, 2.0, 6.0]):
+            lev, _, _ = _tess_patch(w9, p, D, cap=1)
+            ref = np.zeros(4, np.float32)
+            g.glsl_tess_control(ptr(np.ascontiguousarray(w9, np.float32)), C.byref(p), D, ptr(ref))
+            assert np.array_equal(lev.view(np.uint32), ref.view(np.uint32)), (w9, lev, ref)
+
+
+def run_tess_cases(impl):
+    from vct_b200 import scene as S
+    D, SS, W, H = 32, 64, 32, 32
+    sc = pbr_room()
+    out = {}
+    for name, kw in (("max", {"voxelize_atomic_max": 1}), ("avg", {"voxelize_atomic_max": 0})):
+        p = S.room_params(W, H)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        o = O.Oracle(sc, D, 5, SS, W, H)
+        cap = 1 << 20
+        rec = np.zeros(cap * 8, np.float32); n = C.c_longlong(0)
+        O.lib().orc_voxelize_tess_trace(C.byref(o.s.c), C.byref(p), D, ptr(o.color[0]), ptr(o.normal), C.byref(o.info), ptr(rec), C.c_longlong(cap), C.byref(n))
+        assert 5000 < n.value <= cap
+        if impl == "glsl":
+            nv = o.s.verts.shape[0]
+            wpos, wnrm = np.zeros(nv * 3, np.float32), np.zeros(nv * 3, np.float32)
+            O.lib().orc_world_vertices(C.byref(o.s.c), ptr(wpos), ptr(wnrm))
+            col, nrm = np.zeros(D ** 3, np.uint32), np.zeros(D ** 3, np.uint32)
+            glsl().glsl_tess_eval(C.byref(o.s.c), C.byref(p), D, ptr(wpos), ptr(wnrm), ptr(rec), C.c_longlong(n.value), ptr(col), ptr(nrm))
+            out[f"tess_{name}_color"], out[f"tess_{name}_normal"] = col, nrm
+        else:
+            out[f"tess_{name}_color"], out[f"tess_{name}_normal"] = o.color[0].copy(), o.normal.copy()
+        out[f"tess_{name}_points"] = np.array([n.value], np.uint64)
+    return out
+
+
+GOLD_TESS = os.path.join(ROOT, "tests", "golden", "glsl_ref_tess.npz")
+
+
+@live
+def test_oracle_tess_evaluation_equals_the_reference_glsl_compiled_as_cpp():
+    a = run_tess_cases("oracle")
+    assert (a["tess_max_color"] >> 24 != 0).sum() > 1500 and not np.array_equal(a["tess_max_color"], a["tess_avg_color"])
+    compare(a, run_tess_cases("glsl"), "oracle vs compiled testTesselation.tese")
+
+
+def test_oracle_tess_evaluation_equals_the_committed_outputs_of_the_reference_glsl():
+    compare(run_tess_cases("oracle"), dict(np.load(GOLD_TESS)), "oracle vs tests/golden/glsl_ref_tess.npz")
