@@ -110,6 +110,10 @@ typedef struct {
      * Overlay.cpp toggles): one VCT_VIEW_* value instead of nine booleans, in the shader's own priority order. */
     int   debug_view;       /* VCT_VIEW_SHADED (0) = the normal frame */
     float miplevel;         /* Settings::miplevel: lod of VCT_VIEW_VOXELS (phong.frag:350-401) */
+    /* Settings::voxelizeTesselation (Application.h:85, reference default TRUE; parity mode false = the raster path):
+     * patches through testTesselation.tesc/.tese instead of voxelize.vert/geom/frag (Application.cpp:585-665).  Unlit albedo,
+     * atomicMax (voxelize_atomic_max, bit-reproducible) or the free-running running average (order-dependent like the GLSL). */
+    int   voxelize_tesselation;
 } vct_frame_params;
 
 enum { VCT_VIEW_SHADED = 0,

@@ -119,6 +119,9 @@ class Oracle:
         lib().orc_warpmap(ptr(self.occ), C.byref(p), ptr(self.warpmap), ptr(self.wlo), ptr(self.whi))
 
     def voxelize(self, p):
+        if p.voxelize_tesselation:            # the reference's default voxeliser (Application.cpp:585-665)
+            lib().orc_voxelize_tess(C.byref(self.s.c), C.byref(p), self.D, ptr(self.color[0]), ptr(self.normal), C.byref(self.info))
+            return
         lib().orc_voxelize(C.byref(self.s.c), C.byref(p), self.D, ptr(self.shadow), self.S, self._wm(p),
                            ptr(self.color[0]), ptr(self.normal), C.byref(self.info))
 

@@ -442,6 +442,101 @@ __global__ void __launch_bounds__(kThreads) k_voxel_expand(const VoxSetup* __res
 }
 __global__ void k_voxel_reset(Counters* c) { c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
 
+// ================================================================ tessellation voxeliser (reference default)
+// testTesselation.tesc/.tese + the fixed-function tessellator (triangles, equal_spacing, point_mode), Application.cpp:585-665.
+// One warp per patch: every lane evaluates the control shader (levels from the triangle's size in voxels; a patch inside one
+// voxel gets level 0 and is discarded), then the lanes stride over the distinct vertices of the subdivision — ring 0 with the
+// outer levels, concentric rings j >= 1 of the inner level n with corners (1-4j/3n, 2j/3n, 2j/3n) and n-2j segments — and
+// run the evaluation shader on each: unlit diffuse texel (base level, NEAREST) stored at the point's voxel.  Barycentrics are
+// single fp32 divisions of small integers ("canonical tessellator").
+__device__ __forceinline__ float glsl_max(float x, float y) { return x < y ? y : x; }
+__device__ __forceinline__ int tess_round(float level) { return !(level > 1.0f) ? 1 : (level >= 64.0f ? 64 : (int)ceilf(level)); }
+struct TessPatch { V3 w[3], n[3]; float uv[3][2]; int dt; };
+template <int MODE>
+__device__ __forceinline__ void tess_eval(const VoxArgs& a, const FrameConst& fc, const TessPatch& P, float u, float v, float ww) {
+    const V3 pos = (P.w[0] * u + P.w[1] * v) + P.w[2] * ww;
+    const V3 nn = (P.n[0] * u + P.n[1] * v) + P.n[2] * ww;
+    const float tu = (u * P.uv[0][0] + v * P.uv[1][0]) + ww * P.uv[2][0], tv = (u * P.uv[0][1] + v * P.uv[1][1]) + ww * P.uv[2][1];
+    V4 col = mk4(0.f, 0.f, 0.f, 1.f);
+    if (P.dt >= 0) col = sample2d(a.tex[P.dt], tu, tv, 0.0f);
+    const V3 vp = voxel_linear_position(pos, fc.p);
+    const float Df = (float)a.D;
+    int ix, iy, iz;
+    if (!to_voxel_index(mk3(Df * vp.x, Df * vp.y, Df * vp.z), a.D, ix, iy, iz)) return;
+    if (iz < fc.z_lo || iz >= fc.z_hi) return;                                   // another rank's slab
+    const uint32_t o = (uint32_t)(((size_t)iz * a.D + iy) * a.D + ix);
+    a.seg[o >> 3] = 1;
+    const V3 N = normalize3(nn);
+    const V3 nenc = mk3(N.x * 0.5f + 0.5f, N.y * 0.5f + 0.5f, N.z * 0.5f + 0.5f);
+    if (MODE == MODE_MAX) {                                                       // tese:69-74 (the texel's alpha is part of the word)
+        atomicMax(a.color + o, pack_unorm(col));
+        atomicMax(a.normal + o, pack_unorm(mk4(nenc.x, nenc.y, nenc.z, 1.0f)));
+    } else {                                                                      // tese:75-78, the CAS loop as written
+        rgba8_avg_atomic(a.color + o, col.x, col.y, col.z);
+        rgba8_avg_atomic(a.normal + o, nenc.x, nenc.y, nenc.z);
+    }
+}
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_voxel_tess(VoxArgs a) {
+    const FrameConst& fc = *a.fc;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kThreads) >> 5;
+    const float Df = (float)a.D;
+    for (uint32_t t = warp; t < a.n_tris; t += n_warps) {
+        TessPatch P;
+        uint32_t ix[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ix[k] = __ldg(a.indices + 3 * (size_t)t + k);
+            const float4 w4 = __ldg(a.wpos + ix[k]), n4 = __ldg(a.wnrm + ix[k]);
+            P.w[k] = mk3(w4.x, w4.y, w4.z); P.n[k] = mk3(n4.x, n4.y, n4.z);
+            P.uv[k][0] = __ldg(a.verts + 14 * (size_t)ix[k] + 6); P.uv[k][1] = __ldg(a.verts + 14 * (size_t)ix[k] + 7);
+        }
+        // ---- testTesselation.tesc:32-78
+        int vox[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const V3 vp = voxel_linear_position(P.w[k], fc.p);
+            vox[k][0] = __float2int_rz(Df * vp.x); vox[k][1] = __float2int_rz(Df * vp.y); vox[k][2] = __float2int_rz(Df * vp.z);
+        }
+        if (vox[0][0] == vox[1][0] && vox[0][0] == vox[2][0] && vox[0][1] == vox[1][1] && vox[0][1] == vox[2][1] && vox[0][2] == vox[1][2] && vox[0][2] == vox[2][2]) continue;   // levels 0: discarded
+        const V3 A = P.w[2] - P.w[1], B = P.w[2] - P.w[0], C = P.w[1] - P.w[0];
+        const float lx = length3(A), ly = length3(B), lz = length3(C);
+        const float s = ((lx + ly) + lz) * 0.5f;
+        const float area = sqrtf(((s * (s - lx)) * (s - ly)) * (s - lz));
+        const float max_alt = glsl_max((2.0f * area) / lx, glsl_max((2.0f * area) / ly, (2.0f * area) / lz));
+        const V3 vs = mk3((fc.p.voxel_max[0] - fc.p.voxel_min[0]) / Df, (fc.p.voxel_max[1] - fc.p.voxel_min[1]) / Df, (fc.p.voxel_max[2] - fc.p.voxel_min[2]) / Df);
+        const float dx = fabsf(length3(normalize3(A) * vs)), dy = fabsf(length3(normalize3(B) * vs)), dz = fabsf(length3(normalize3(C) * vs));
+        const float lev_in = glsl_max(1.0f, max_alt / vs.x);
+        const float lev_o[3] = {glsl_max(1.0f, lz / dz), glsl_max(1.0f, lx / dx), glsl_max(1.0f, ly / dy)};   // outer[0] = C, [1] = A, [2] = B
+        if (!(lev_o[0] > 0.0f) || !(lev_o[1] > 0.0f) || !(lev_o[2] > 0.0f)) continue;
+        // ---- fixed function: clamp, round, enumerate the distinct vertices
+        int n = tess_round(lev_in);
+        const int o0 = tess_round(lev_o[0]), o1 = tess_round(lev_o[1]), o2 = tess_round(lev_o[2]);
+        P.dt = a.mats[__ldg(a.trimat + t)].diffuse_tex;
+        if (lane < 3) tess_eval<MODE>(a, fc, P, lane == 0 ? 1.0f : 0.0f, lane == 1 ? 1.0f : 0.0f, lane == 2 ? 1.0f : 0.0f);
+        if (n == 1 && o0 == 1 && o1 == 1 && o2 == 1) continue;
+        if (n == 1) n = 2;
+        const int e2 = o2 - 1, e0 = o0 - 1, e1 = o1 - 1;                          // interior points of the edges w = 0, u = 0, v = 0
+        for (int q = lane; q < e2 + e0 + e1; q += 32) {
+            if (q < e2) { const int i = q + 1; tess_eval<MODE>(a, fc, P, (float)(o2 - i) / (float)o2, (float)i / (float)o2, 0.0f); }
+            else if (q < e2 + e0) { const int i = q - e2 + 1; tess_eval<MODE>(a, fc, P, 0.0f, (float)(o0 - i) / (float)o0, (float)i / (float)o0); }
+            else { const int i = q - e2 - e0 + 1; tess_eval<MODE>(a, fc, P, (float)i / (float)o1, 0.0f, (float)(o1 - i) / (float)o1); }
+        }
+        for (int j = 1; n - 2 * j >= 0; ++j) {
+            const int m = n - 2 * j;
+            if (m == 0) { if (lane == 0) { const float third = 1.0f / 3.0f; tess_eval<MODE>(a, fc, P, third, third, third); } break; }
+            const float den = (float)(3 * n * m), small = (float)(2 * j) / (float)(3 * n);
+            for (int q = lane; q < 3 * m; q += 32) {
+                const int e = q / m, i = q - e * m;
+                const float big = (float)((3 * n - 4 * j) * (m - i) + 2 * j * i) / den;
+                const float rise = (float)(2 * j * (m - i) + (3 * n - 4 * j) * i) / den;
+                if (e == 0) tess_eval<MODE>(a, fc, P, big, rise, small); else if (e == 1) tess_eval<MODE>(a, fc, P, small, big, rise); else tess_eval<MODE>(a, fc, P, rise, small, big);
+            }
+        }
+    }
+}
+
 template <int MODE>
 int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* tiles_name, const char* pixels_name) {
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
@@ -502,6 +597,12 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset) {
         VCT_CHECK(c, cudaMemsetAsync(c->d_occ, 0, sizeof(uint32_t) * VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM, c->stream));
         vct_prof_mark(c, "memset");
         return run_mode<MODE_OCC>(c, a, "k_voxel_bin_occ", "k_voxel_tiles_occ", "k_voxel_pixels_occ");
+    }
+    if (p.voxelize_tesselation) {                               // the reference's default voxeliser: no rasterisation at all
+        const int grid = (int)std::min<size_t>((c->n_tris * 32 + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
+        if (p.voxelize_atomic_max) { k_voxel_tess<MODE_MAX><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, "k_voxel_tess_max"); }
+        else { k_voxel_tess<MODE_CAS><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, "k_voxel_tess_cas"); }
+        return 0;
     }
     if (p.voxelize_atomic_max) return run_mode<MODE_MAX>(c, a, "k_voxel_bin_max", "k_voxel_tiles_max", "k_voxel_pixels_max");
     if (!p.deterministic) return run_mode<MODE_CAS>(c, a, "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_pixels_cas");

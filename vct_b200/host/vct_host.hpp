@@ -99,6 +99,7 @@ struct Settings {
     int drawVoxels = false, drawNormals = false, drawDominantAxis = false, debugOcclusion = false, debugIndirect = false, debugReflections = false;
     int debugMaterialDiffuse = false, debugMaterialRoughness = false, debugMaterialMetallic = false;
     float miplevel = 0.0f;
+    int voxelizeTesselation = false;    // Application.h:85 (reference default true; this host defaults to the north star's raster path)
     int cooktorrance = true, enablePostprocess = true, enableNormalMap = true;
     int enableIndirect = true, enableDiffuse = true, enableSpecular = true, enableReflections = true;
     float ambientScale = 1.0f, reflectScale = 1.0f;
@@ -312,6 +313,7 @@ public:
                      : s.debugMaterialMetallic ? VCT_VIEW_MATERIAL_METALLIC : s.drawNormals ? VCT_VIEW_NORMALS : s.drawDominantAxis ? VCT_VIEW_DOMINANT_AXIS
                      : s.debugIndirect ? VCT_VIEW_INDIRECT : s.debugOcclusion ? VCT_VIEW_OCCLUSION : s.debugReflections ? VCT_VIEW_REFLECTIONS : VCT_VIEW_SHADED;
         p.miplevel = s.miplevel;
+        p.voxelize_tesselation = s.voxelizeTesselation;
         return p;
     }
 
