@@ -10,7 +10,8 @@ the parts of GLSL that are not C++ are mapped, mechanically:
   * `#pragma include "x"` is resolved like GLHelper::preprocessShader does (src/Graphics/GLHelper.cpp:265-283), `#version` /
     `#extension` lines are dropped and the text is run through the C preprocessor (g++ -E), so `#if USE_RGBA16F`, `#ifdef
     NORMAL_MAP`, `#define POINT_LIGHT 0` … select and expand exactly what a GLSL compiler would see;
-  * interface declarations become namespace-level variables the driver sets: `layout(...) uniform T x [= v];`, `in`/`out`
+  * interface declarations become namespace-level variables the driver sets (uniforms shared, `in`/`out` and built-ins
+    thread_local: the drivers run the invocations of a dispatch on all host threads): `layout(...) uniform T x [= v];`, `in`/`out`
     variables, `in NAME {...} inst;`, `layout(...) buffer/uniform NAME {...};` (an unsized `T a[];` member becomes
     ssbo_array<T>), `layout(local_size...) in;` is dropped;
   * array constructors `T[](a, b, c)` -> `{a, b, c}`;  `x.length()` -> glsl_length(x);
@@ -76,7 +77,7 @@ def interface_blocks(text):
             out.append(f"static ssbo_array<{a.group(1)}> {a.group(2)};" if a else f"static {decl};")
         return "\n".join(out)
     text = re.sub(r"(?:layout\s*\([^)]*\)\s*)?(?:buffer|uniform)\s+\w+\s*\{(?P<body>[^}]*)\}\s*;", block, text)
-    text = re.sub(r"(?:flat\s+)?\b(?:in|out)\s+(\w+)\s*\{([^}]*)\}\s*(\w+)\s*;", r"static struct \1 {\2} \3;", text)
+    text = re.sub(r"(?:flat\s+)?\b(?:in|out)\s+(\w+)\s*\{([^}]*)\}\s*(\w+)\s*;", r"static thread_local struct \1 {\2} \3;", text)
     return text
 
 
@@ -90,7 +91,9 @@ def global_declarations(text):
             else:
                 m = qual.match(line)
                 if m:
-                    line = "static " + line[m.end():]
+                    # uniforms are shared by all invocations; `in` / `out` variables are per-invocation state (one copy per host thread)
+                    per_invocation = re.search(r"\b(?:in|out)\b", m.group(1)) is not None
+                    line = ("static thread_local " if per_invocation else "static ") + line[m.end():]
                     line = re.sub(r"\[\s*\]\s*;", "[3];", line)                  # per-vertex arrays of a 3-vertex patch
         depth += line.count("{") - line.count("}")
         out.append(line)
@@ -130,12 +133,22 @@ def main():
     shader_dir, name, driver, out = sys.argv[1:5]
     ns = re.sub(r"\W", "_", name)
     body = translate(shader_dir, name, ns)
+    # a driver that re-binds some uniforms per invocation (texture units, the material block) lists them:
+    #   // glsl2cpp: per-invocation diffuseMap material ...
+    for names in re.findall(r"//\s*glsl2cpp:\s*per-invocation\s+([^\n]*)", open(driver).read()):
+        for n in names.split():
+            body, k = re.subn(r"^static (?!thread_local)([^;=\n]*\b" + n + r"\b)", r"static thread_local \1", body, flags=re.M)
+            if k != 1:
+                raise SystemExit(f"glsl2cpp: per-invocation name {n} matched {k} declarations in {name}")
     with open(out, "w") as f:
         f.write(f"// GENERATED by oracle/ref_rig/glsl2cpp.py from {os.path.join(shader_dir, name)} — do not commit.\n")
         f.write('#include "glsl_shim.h"\n#include <vector>\n#include <cstdio>\n')
         f.write("namespace glsl {\nnamespace " + ns + " {\n")
-        f.write("static ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\nstatic vec4 gl_FragCoord; static int gl_Layer;\n"
-                "static int gl_InvocationID; static float gl_TessLevelInner[2], gl_TessLevelOuter[4]; static vec3 gl_TessCoord; static vec4 gl_Position;\n")
+        f.write("// built-in per-invocation variables: one copy per host thread (the drivers run invocations under OpenMP)\n"
+                "static thread_local ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\n"
+                "static thread_local vec4 gl_FragCoord; static thread_local int gl_Layer;\n"
+                "static thread_local int gl_InvocationID; static thread_local float gl_TessLevelInner[2], gl_TessLevelOuter[4];\n"
+                "static thread_local vec3 gl_TessCoord; static thread_local vec4 gl_Position;\n")
         f.write(body)
         f.write("\n// ---- driver (this repository's code)\n")
         f.write(open(driver).read())

@@ -309,8 +309,13 @@ inline uint imageAtomicCompSwap(image3D& im, const ivec3& p, uint compare, uint 
 }
 inline uint imageAtomicMax(image3D& im, const ivec3& p, uint value) { if (!im.inside(p)) return 0u; uint32_t& w = ((uint32_t*)im.data)[im.at(p)]; const uint old = w; if (value > old) w = value; return old; }
 inline uint imageAtomicOr(image3D& im, const ivec3& p, uint value) { if (!im.inside(p)) return 0u; uint32_t& w = ((uint32_t*)im.data)[im.at(p)]; const uint old = w; w |= value; return old; }
-inline uint atomicAdd(uint& mem, uint v) { const uint old = mem; mem += v; return old; }
-inline uint atomicMax(uint& mem, uint v) { const uint old = mem; if (v > mem) mem = v; return old; }
+// buffer-variable atomics: real ones, the compute drivers run a dispatch on all host threads
+inline uint atomicAdd(uint& mem, uint v) { return __atomic_fetch_add(&mem, v, __ATOMIC_RELAXED); }
+inline uint atomicMax(uint& mem, uint v) {
+    uint old = __atomic_load_n(&mem, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(&mem, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 
 // ----------------------------------------------------------------------------------------------------------- samplers
 // 2D: either a float depth map (shadow map: LINEAR, CLAMP_TO_BORDER border 1) or an 8-bit material texture with mips

@@ -477,8 +477,10 @@ static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D
                           const unsigned short* warpmap, unsigned* color, unsigned* normal, vct_voxelize_info* info,
                           float* frag_rec, long long frag_cap, long long* frag_count) {
     Prepared P = prepare(sc, false);
-    std::memset(color, 0, sizeof(unsigned) * (size_t)D * D * D);       // glClearTexImage, Application.cpp:686-687
-    std::memset(normal, 0, sizeof(unsigned) * (size_t)D * D * D);
+    if (color) {
+        std::memset(color, 0, sizeof(unsigned) * (size_t)D * D * D);   // glClearTexImage, Application.cpp:686-687
+        std::memset(normal, 0, sizeof(unsigned) * (size_t)D * D * D);
+    }
     unsigned total = 0;
     for (int t = 0; t < sc->n_tris; ++t) {
         const unsigned* ix = sc->indices + 3 * (size_t)t;
@@ -506,6 +508,7 @@ static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D
                 r[0] = ndc.x; r[1] = ndc.y; r[2] = ndc.z; r[3] = wp.x; r[4] = wp.y; r[5] = wp.z; r[6] = nn.x; r[7] = nn.y; r[8] = nn.z;
                 r[9] = u; r[10] = v; r[11] = (float)va.axis; r[12] = rho2; r[13] = (float)mat.diffuse_tex; r[14] = r[15] = 0.0f;
             }
+            if (!color) return;                                           // record only: rasteriser without the fragment stage
             V3 col = {0, 0, 0};
             if (dt) { V4 a = sample2d(*dt, u, v, rho2); col = {a.x, a.y, a.z}; }
             V3 N = normalize(nn);
@@ -1211,7 +1214,8 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
     for (int py = y_lo; py < y_hi; py += y_stride)
         for (int px = 0; px < W; ++px) {
             const unsigned long long key = vis[(size_t)py * W + px];
-            unsigned& out = image[(size_t)py * W + px];
+            unsigned scratch = 0;
+            unsigned& out = image ? image[(size_t)py * W + px] : scratch;     // image == NULL: record only
             if (key == ~0ull) { out = clear; continue; }
             const int t = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu));
             const unsigned* ix = sc->indices + 3 * (size_t)t;
@@ -1244,6 +1248,7 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
                 const float rec[28] = {Pw.x, Pw.y, Pw.z, fn.x, fn.y, fn.z, u, v, lsp.x, lsp.y, lsp.z, lsp.w, Tt.x, Tt.y, Tt.z, Bt.x, Bt.y, Bt.z,
                                      ux, vx, uy, vy, (float)sc->tri_material[t], 1.0f, 0, 0, 0, 0};
                 std::memcpy(r, rec, sizeof rec);
+                if (!image) continue;                                         // rasteriser + interpolation without the fragment stage
             }
             auto tbn = [&](V3 d) -> V3 { return (Tt * d.x + Bt * d.y) + fn * d.z; };   // mat3(T,B,N) * d
             const int view = fp->debug_view;
@@ -1367,6 +1372,12 @@ extern "C" void orc_shade_trace(const orc_scene* sc, const vct_frame_params* fp,
                                 const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
                                 const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec) {
     shade_impl(sc, fp, W, H, 0, H, 1, vis, D, L, radiance_pyr, color_pyr, shadow, S, warpmap, image, cone_steps, frag_rec);
+}
+// rows y_lo, y_lo + y_stride, ... only; image may be NULL (record only)
+extern "C" void orc_shade_trace_rows(const orc_scene* sc, const vct_frame_params* fp, int W, int H, int y_lo, int y_hi, int y_stride,
+                                     const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
+                                     const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec) {
+    shade_impl(sc, fp, W, H, y_lo, y_hi, y_stride, vis, D, L, radiance_pyr, color_pyr, shadow, S, warpmap, image, cone_steps, frag_rec);
 }
 
 // closed-form KAT helper: one cone marched through a volume whose every level holds the same word

@@ -106,6 +106,11 @@ void orc_shade_trace(const orc_scene*, const vct_frame_params*, int W, int H, co
                      const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
                      const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec);
 
+void orc_shade_trace_rows(const orc_scene*, const vct_frame_params*, int W, int H, int y_lo, int y_hi, int y_stride,
+                          const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
+                          const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec);
+/* In the three *_trace functions the output volume / image may be NULL: only the fixed-function stage runs and records. */
+
 /* KAT helpers */
 unsigned orc_rgba8_avg(unsigned stored, float r, float g, float b);     /* voxelize.frag:111-139, one insertion */
 unsigned orc_pack_unorm4x8(float r, float g, float b, float a);

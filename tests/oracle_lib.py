@@ -167,3 +167,64 @@ class Oracle:
 
     def image_rgba(self):
         return self.image.view(np.uint8).reshape(self.H, self.W, 4)[::-1]      # flip: row 0 of the buffer is the bottom
+
+
+# ------------------------------------------------------------------------------------------------------------------
+GLSL_SO = os.path.join(ROOT, "oracle", "_ref", "libvct_glsl_ref.so")
+
+
+class GlslReference:
+    """The GI frame on the CPU with the REFERENCE'S OWN SHADERS: oracle/_ref/libvct_glsl_ref.so holds the reference's GLSL
+    (transferVoxels.comp, injectRadiance.comp, filterRadiance.comp, voxelize.frag, phong.frag, ...) compiled as C++ from
+    where it lies (oracle/Makefile, oracle/ref_rig/).  What OpenGL's fixed function would do — rasterise, interpolate, sample
+    — comes from the oracle's recorders (orc_voxelize_trace / orc_shade_trace_rows with NULL outputs: no shading there).
+    Compute dispatches and the per-pixel pass run on all host threads (OpenMP); voxelize.frag's fragments run on one thread in
+    canonical order (its running-average atomic is order-dependent).  bench.py times this as cpu_baseline kind "reference"."""
+
+    FRAG_CAP = 1 << 21
+
+    def __init__(self, oracle):
+        if not os.path.isfile(GLSL_SO):
+            raise FileNotFoundError(GLSL_SO)
+        self.o = oracle
+        self.g = C.CDLL(GLSL_SO)
+        o = oracle
+        self.frag = np.zeros(self.FRAG_CAP * 16, np.float32)
+        self.prec = np.zeros(o.W * o.H * 28, np.float32)
+        self.image = np.zeros(o.W * o.H, np.uint32)
+        self.cone_steps = 0
+
+    def voxelize(self, p):
+        o, n = self.o, C.c_longlong(0)
+        lib().orc_voxelize_trace(C.byref(o.s.c), C.byref(p), o.D, ptr(o.shadow), o.S, o._wm(p), None, None, C.byref(o.info),
+                                 ptr(self.frag), C.c_longlong(self.FRAG_CAP), C.byref(n))
+        if n.value > self.FRAG_CAP:
+            raise RuntimeError("fragment record buffer too small")
+        self.g.glsl_voxelize_fragments(C.byref(o.s.c), C.byref(p), o.D, ptr(o.shadow), o.S, o._wm(p), ptr(self.frag), C.c_longlong(n.value),
+                                       ptr(o.color[0]), ptr(o.normal), C.byref(o.info))
+
+    def transfer(self, p):
+        o = self.o
+        self.g.glsl_transfer(C.byref(p), o.D, ptr(o.color[0]), ptr(o.radiance[0]), C.byref(o.info))
+
+    def inject(self, p):
+        o, l0 = self.o, self.o.s.light0
+        lp = (C.c_float * 3)(*l0.position); li = (C.c_float * 3)(*l0.color)
+        self.g.glsl_inject(C.byref(p), o.D, ptr(o.color[0]), ptr(o.normal), ptr(o.shadow), o.S, o._wm(p), lp, li, ptr(o.radiance[0]))
+
+    def mip(self, which="radiance"):
+        o = self.o
+        vol = o.radiance if which == "radiance" else o.color
+        for l in range(o.L - 1):
+            self.g.glsl_mip(max(1, o.D >> l), ptr(vol[l]), ptr(vol[l + 1]), 0)
+
+    def shade(self, p, y_lo=0, y_hi=None, y_stride=1):
+        o = self.o
+        self.prec[23::28] = 2.0                                         # "row not sampled"; the recorder flags covered pixels of sampled rows with 1
+        steps = C.c_ulonglong(0)
+        rad = np.concatenate(o.radiance); col = np.concatenate(o.color)
+        lib().orc_shade_trace_rows(C.byref(o.s.c), C.byref(p), o.W, o.H, y_lo, o.H if y_hi is None else y_hi, y_stride, ptr(o.vis), o.D, o.L,
+                                   ptr(rad), ptr(col), ptr(o.shadow), o.S, o._wm(p), None, None, ptr(self.prec))
+        self.g.glsl_shade_pixels(C.byref(o.s.c), C.byref(p), o.W, o.H, ptr(self.prec), o.D, o.L, ptr(rad), ptr(col), ptr(o.shadow), o.S, o._wm(p),
+                                 ptr(self.image), C.byref(steps))
+        self.cone_steps = steps.value

@@ -431,3 +431,30 @@ def test_oracle_tess_evaluation_equals_the_reference_glsl_compiled_as_cpp():
 
 def test_oracle_tess_evaluation_equals_the_committed_outputs_of_the_reference_glsl():
     compare(run_tess_cases("oracle"), dict(np.load(GOLD_TESS)), "oracle vs tests/golden/glsl_ref_tess.npz")
+
+
+def test_reference_cpu_frame_equals_the_oracle_frame():
+    """bench.py's CPU arm (tests/oracle_lib.GlslReference: the compiled reference shaders around the oracle's fixed function)
+    produces the oracle's frame: every pyramid level, counters, and the sampled image rows."""
+    if not os.path.isfile(SO):
+        pytest.skip("oracle/_ref/libvct_glsl_ref.so not built")
+    import bench
+    from vct_b200 import scene as S
+    D, Lv, SS, W, H = 32, 5, 256, 96, 64
+    sc = pbr_room()
+    p = S.room_params(W, H)
+    a, b = O.Oracle(sc, D, Lv, SS, W, H), O.Oracle(sc, D, Lv, SS, W, H)
+    for o in (a, b):
+        o.shadowmap(p); o.visibility(p)
+    bench.oracle_gi_frame(a, p, 2)
+    r = O.GlslReference(b)
+    t = bench.reference_gi_frame(r, p, 2)
+    assert set(t) == {"voxelize", "transfer", "inject", "mip", "cone_trace"} and all(v > 0 for v in t.values())
+    for l in range(Lv):
+        assert np.array_equal(a.radiance[l], b.radiance[l]) and np.array_equal(a.color[l], b.color[l]), l
+    assert np.array_equal(a.normal, b.normal)
+    assert (a.info.total_fragments, a.info.unique_voxels, a.info.max_fragments_per_voxel) == (b.info.total_fragments, b.info.unique_voxels, b.info.max_fragments_per_voxel)
+    rows = np.arange(0, H, 2)
+    ia, ib = a.image.reshape(H, W)[rows], r.image.reshape(H, W)[rows]
+    covered = b.vis.reshape(H, W)[rows] != np.uint64(0xFFFFFFFFFFFFFFFF)
+    assert covered.sum() > 1000 and np.array_equal(ia[covered], ib[covered]) and a.cone_steps == r.cone_steps
