@@ -77,6 +77,7 @@ def interface_blocks(text):
             out.append(f"static ssbo_array<{a.group(1)}> {a.group(2)};" if a else f"static {decl};")
         return "\n".join(out)
     text = re.sub(r"(?:layout\s*\([^)]*\)\s*)?(?:buffer|uniform)\s+\w+\s*\{(?P<body>[^}]*)\}\s*;", block, text)
+    text = re.sub(r"(?:flat\s+)?\b(?:in|out)\s+(\w+)\s*\{([^}]*)\}\s*(\w+)\s*\[\s*\]\s*;", r"static thread_local struct \1 {\2} \3[3];", text)   # gs_in[]
     text = re.sub(r"(?:flat\s+)?\b(?:in|out)\s+(\w+)\s*\{([^}]*)\}\s*(\w+)\s*;", r"static thread_local struct \1 {\2} \3;", text)
     return text
 
@@ -148,7 +149,9 @@ def main():
                 "static thread_local ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\n"
                 "static thread_local vec4 gl_FragCoord; static thread_local int gl_Layer;\n"
                 "static thread_local int gl_InvocationID; static thread_local float gl_TessLevelInner[2], gl_TessLevelOuter[4];\n"
-                "static thread_local vec3 gl_TessCoord; static thread_local vec4 gl_Position;\n")
+                "static thread_local vec3 gl_TessCoord; static thread_local vec4 gl_Position;\n"
+                "struct gl_PerVertex { vec4 gl_Position; }; static thread_local gl_PerVertex gl_in[3];\n"
+                "static void EmitVertex(); static void EndPrimitive();   // geometry stage: defined by the driver\n")
         f.write(body)
         f.write("\n// ---- driver (this repository's code)\n")
         f.write(open(driver).read())

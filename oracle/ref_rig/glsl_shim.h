@@ -70,6 +70,7 @@ template <class T> struct tvec3 {
     template <class S, class = std::enable_if_t<std::is_arithmetic_v<S>>> explicit tvec3(S v) : d{T(v), T(v), T(v)} {}
     template <class S1, class S2, class S3, class = std::enable_if_t<std::is_arithmetic_v<S1> && std::is_arithmetic_v<S2> && std::is_arithmetic_v<S3>>> tvec3(S1 a, S2 b, S3 c) : d{T(a), T(b), T(c)} {}
     template <class S, class = std::enable_if_t<std::is_arithmetic_v<S>>> tvec3(const tvec2<T>& a, S c) : d{a.d[0], a.d[1], T(c)} {}
+    explicit tvec3(const tvec4<T>& a);                                     // vec3(vec4): drops w
     template <class U, class = std::enable_if_t<!std::is_same_v<U, T>>> tvec3(const tvec3<U>& o, std::enable_if_t<std::is_floating_point_v<T> && std::is_integral_v<U>, int> = 0) : d{T(o.d[0]), T(o.d[1]), T(o.d[2])} {}
     template <class U, class = std::enable_if_t<!std::is_same_v<U, T>>> explicit tvec3(const tvec3<U>& o, std::enable_if_t<!(std::is_floating_point_v<T> && std::is_integral_v<U>), long> = 0) : d{T(o.d[0]), T(o.d[1]), T(o.d[2])} {}
     T& operator[](int i) { return d[i]; }
@@ -91,6 +92,7 @@ template <class T> struct tvec4 {
     T& operator[](int i) { return d[i]; }
     T operator[](int i) const { return d[i]; }
 };
+template <class T> inline tvec3<T>::tvec3(const tvec4<T>& a) : d{a.d[0], a.d[1], a.d[2]} {}
 typedef tvec2<float> vec2; typedef tvec3<float> vec3; typedef tvec4<float> vec4;
 typedef tvec2<int> ivec2; typedef tvec3<int> ivec3; typedef tvec4<int> ivec4;
 typedef tvec2<uint> uvec2; typedef tvec3<uint> uvec3; typedef tvec4<uint> uvec4;
@@ -151,6 +153,7 @@ struct mat3 {
     vec3 c[3];
     mat3() { c[0] = vec3(1, 0, 0); c[1] = vec3(0, 1, 0); c[2] = vec3(0, 0, 1); }
     mat3(const vec3& a, const vec3& b, const vec3& e) { c[0] = a; c[1] = b; c[2] = e; }
+    explicit mat3(const struct mat4& m);                                   // upper-left 3x3
     vec3& operator[](int i) { return c[i]; }
     const vec3& operator[](int i) const { return c[i]; }
 };
@@ -161,10 +164,56 @@ struct mat4 {
     vec4& operator[](int i) { return c[i]; }
     const vec4& operator[](int i) const { return c[i]; }
 };
+inline mat3::mat3(const mat4& m) { for (int i = 0; i < 3; ++i) c[i] = vec3(m.c[i].x, m.c[i].y, m.c[i].z); }
 // M * v: sum over columns, left to right
 inline vec3 operator*(const mat3& m, const vec3& v) { return (m.c[0] * v.x + m.c[1] * v.y) + m.c[2] * v.z; }
 inline vec4 operator*(const mat4& m, const vec4& v) { return ((m.c[0] * v.x + m.c[1] * v.y) + m.c[2] * v.z) + m.c[3] * v.w; }
 inline mat4 operator*(const mat4& a, const mat4& b) { mat4 r; for (int i = 0; i < 4; ++i) r.c[i] = a * b.c[i]; return r; }
+inline mat4 transpose(const mat4& m) { mat4 r; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.c[i][j] = m.c[j][i]; return r; }
+// inverse(mat4): every use in the reference is mat3(transpose(inverse(model))) with an affine model matrix (last row 0 0 0 1).
+// For those the upper-left 3x3 of the inverse is adj(A)/det(A) of the upper-left block A (canonical evaluation: cofactors as
+// differences of two products, det = (a*c00 + b*c01) + c*c02, one division per entry) and the last column is -A^-1 t; a
+// non-affine matrix falls back to the general cofactor expansion.
+inline mat4 inverse(const mat4& M) {
+    mat4 R;
+    if (M.c[0].w == 0.0f && M.c[1].w == 0.0f && M.c[2].w == 0.0f && M.c[3].w == 1.0f) {
+        const float a = M.c[0].x, b = M.c[1].x, c = M.c[2].x, d = M.c[0].y, e = M.c[1].y, f = M.c[2].y, g = M.c[0].z, h = M.c[1].z, i = M.c[2].z;
+        const float c00 = e * i - f * h, c01 = f * g - d * i, c02 = d * h - e * g;
+        const float c10 = c * h - b * i, c11 = a * i - c * g, c12 = b * g - a * h;
+        const float c20 = b * f - c * e, c21 = c * d - a * f, c22 = a * e - b * d;
+        const float det = (a * c00 + b * c01) + c * c02;
+        // inverse = transpose(cofactor)/det: entry (row r, col k) = cofactor(k, r)/det; columns of R:
+        R.c[0] = vec4(c00 / det, c01 / det, c02 / det, 0.0f);
+        R.c[1] = vec4(c10 / det, c11 / det, c12 / det, 0.0f);
+        R.c[2] = vec4(c20 / det, c21 / det, c22 / det, 0.0f);
+        const vec3 t(M.c[3].x, M.c[3].y, M.c[3].z);
+        const vec3 it = vec3(R.c[0].x, R.c[0].y, R.c[0].z) * t.x + vec3(R.c[1].x, R.c[1].y, R.c[1].z) * t.y + vec3(R.c[2].x, R.c[2].y, R.c[2].z) * t.z;
+        R.c[3] = vec4(-it.x, -it.y, -it.z, 1.0f);
+        return R;
+    }
+    const float* m = &M.c[0].x; float inv[16];                 // columns are contiguous: m[4*col + row]
+    float mm[16]; for (int k = 0; k < 4; ++k) { mm[4 * k] = M.c[k].x; mm[4 * k + 1] = M.c[k].y; mm[4 * k + 2] = M.c[k].z; mm[4 * k + 3] = M.c[k].w; }
+    m = mm;
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    for (int k = 0; k < 4; ++k) R.c[k] = vec4(inv[4 * k] / det, inv[4 * k + 1] / det, inv[4 * k + 2] / det, inv[4 * k + 3] / det);
+    return R;
+}
 inline mat3 transpose(const mat3& m) { return mat3(vec3(m[0].x, m[1].x, m[2].x), vec3(m[0].y, m[1].y, m[2].y), vec3(m[0].z, m[1].z, m[2].z)); }
 
 // ---------------------------------------------------------------------------------------------------------- built-ins

@@ -1,7 +1,7 @@
 // vct_oracle.cpp — CPU ORACLE (test infrastructure only).  Pinned bit for bit against the reference's own sources compiled in
 // place (oracle/_ref, see vct_oracle.h): the host C++ of the warp tables/example, and the GLSL of transferVoxels,
 // filterRadiance, voxelFillHoles, injectRadiance, the dead post-pass variants, voxelize.frag and phong.frag compiled as C++
-// and generateWarpmap{,Weights}.frag (tests/test_glsl_ref.py).  Still unpinned: vertex/geometry stages, the two alpha tests, filter3d.comp.
+// and generateWarpmap{,Weights}.frag (tests/test_glsl_ref.py).  Vertex/geometry stages: see vct_oracle.h.  Still unpinned: the two alpha tests, filter3d.comp.
 //
 // A restatement of the reference's GLSL passes in plain C++ with OpenGL's implementation-defined behaviour
 // fixed to one explicit definition (DESIGN.md "Canonical GL semantics").  Compile with -ffp-contract=off:
@@ -694,6 +694,32 @@ extern "C" void orc_world_vertices(const orc_scene* sc, float* wpos, float* wnrm
     for (int i = 0; i < sc->n_vertices; ++i) {
         wpos[3 * i] = P.wpos[i].x; wpos[3 * i + 1] = P.wpos[i].y; wpos[3 * i + 2] = P.wpos[i].z;
         wnrm[3 * i] = P.wnrm[i].x; wnrm[3 * i + 1] = P.wnrm[i].y; wnrm[3 * i + 2] = P.wnrm[i].z;
+    }
+}
+// The vertex / geometry stages as the passes above evaluate them, for tests/test_glsl_ref.py (any output may be NULL):
+//   voxel  n_tris x 13     : dominant axis, then gl_Position (x, y, z, w) of the three vertices      voxelize.vert + voxelize.geom
+//   light  n_vertices x 4  : gl_Position of the shadow-map pass                                      simple.vert with lp, lv
+//   cam    n_vertices x 4  : gl_Position of the depth prepass / phong pass                           simple.vert / phong.vert
+//   phong  n_vertices x 16 : fragPosition 3, fragNormal 3, lightFragPos 4, TBN columns T 3 and B 3   phong.vert:36-58
+extern "C" void orc_vertex_stage(const orc_scene* sc, const vct_frame_params* fp, float* voxel, float* light, float* cam, float* phong) {
+    Prepared P = prepare(sc, true);
+    if (voxel)
+        for (int t = 0; t < sc->n_tris; ++t) {
+            const unsigned* ix = sc->indices + 3 * (size_t)t;
+            VoxAxis va = pick_axis(fp, P.wnrm[ix[0]], P.wnrm[ix[1]], P.wnrm[ix[2]]);
+            float* o = voxel + 13 * (size_t)t;
+            o[0] = (float)va.axis;
+            for (int k = 0; k < 3; ++k) { V3 w = P.wpos[ix[k]]; V4 c = mul(va.mvp, {w.x, w.y, w.z, 1.0f}); o[1 + 4 * k] = c.x; o[2 + 4 * k] = c.y; o[3 + 4 * k] = c.z; o[4 + 4 * k] = c.w; }
+        }
+    for (int i = 0; i < sc->n_vertices; ++i) {
+        const V3 w = P.wpos[i];
+        if (light) { V4 c = mul(fp->lp, mul(fp->lv, {w.x, w.y, w.z, 1.0f})); float* o = light + 4 * (size_t)i; o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w; }
+        if (cam) { V4 c = mul(fp->projection, mul(fp->view, {w.x, w.y, w.z, 1.0f})); float* o = cam + 4 * (size_t)i; o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w; }
+        if (phong) {
+            V4 l = mul(fp->ls, {w.x, w.y, w.z, 1.0f});
+            const float v[16] = {w.x, w.y, w.z, P.wnrm[i].x, P.wnrm[i].y, P.wnrm[i].z, l.x, l.y, l.z, l.w, P.T[i].x, P.T[i].y, P.T[i].z, P.B[i].x, P.B[i].y, P.B[i].z};
+            std::memcpy(phong + 16 * (size_t)i, v, sizeof v);
+        }
     }
 }
 extern "C" void orc_voxelize_tess(const orc_scene* sc, const vct_frame_params* fp, int D, unsigned* color, unsigned* normal, vct_voxelize_info* info) {

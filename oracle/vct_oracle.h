@@ -12,7 +12,7 @@
  *     tests/test_oracle_kat.py checks orc_warp_rig / orc_warp_partials / orc_warp_weight_table against them;
  *   - GLSL: transferVoxels.comp, filterRadiance.comp (BOX2/BOX3/CUBE), voxelFillHoles.comp, injectRadiance.comp,
  *     setVoxelOpacity.comp, normalizeVoxels.comp, temporalRadianceFilter.comp, voxelize.frag, phong.frag (+ common.glsl) and
- *     generateWarpmapWeights.frag / generateWarpmap.frag
+ *     generateWarpmapWeights.frag / generateWarpmap.frag, testTesselation.tesc / .tese
  *     are mapped to C++ SYNTAX by ref_rig/glsl2cpp.py (bodies untouched), compiled against ref_rig/glsl_shim.h into
  *     _ref/libvct_glsl_ref.so and run on the same seeded inputs as the orc_* functions (compute shaders: whole dispatches;
  *     fragment shaders: replayed on the fragment-stage inputs recorded by orc_voxelize_trace / orc_shade_trace);
@@ -22,8 +22,10 @@
  * is the OpenGL IMPLEMENTATION's and not the reference's: rasteriser coverage/interpolation, texture filtering and LOD
  * selection, unorm conversion, built-in function precision.  Those follow the OpenGL 4.5 specification with the canonical
  * choices listed in DESIGN.md §2 ("Canonical GL semantics"), stated once in glsl_shim.h and once here.
- * STILL UNPINNED (restated from the source, known-answer tests only, tests/golden/kat.json): the vertex/geometry stages
- * (simple.vert, voxelize.vert/geom, phong.vert: matrix products and the dominant-axis pick), dither.frag /
+ *   - vertex / geometry stages (voxelize.vert/.geom, simple.vert, phong.vert) are compiled too: the voxelisation path is
+ *     identical; the camera / light clip transforms differ by association order only (the shaders multiply the matrices first,
+ *     the passes here transform the vector step by step): <= 2e-7 relative, bounded by the test, see DESIGN.md section 2.
+ * STILL UNPINNED (restated from the source, known-answer tests only, tests/golden/kat.json): dither.frag /
  * reflectiveShadowMap.frag (one alpha test each) and filter3d.comp (dead; uses textureLodOffset).
  *
  * POD parameter structs are shared with the product's public header (the boundary spec); no code is.
@@ -64,6 +66,7 @@ void orc_voxelize_tess(const orc_scene*, const vct_frame_params*, int D, unsigne
 void orc_voxelize_tess_trace(const orc_scene*, const vct_frame_params*, int D, unsigned* color, unsigned* normal, vct_voxelize_info* info,
                              float* rec, long long rec_cap, long long* rec_count);
 void orc_world_vertices(const orc_scene*, float* wpos3, float* wnrm3);
+void orc_vertex_stage(const orc_scene*, const vct_frame_params*, float* voxel13, float* light4, float* cam4, float* phong16);
 long long orc_tess_patch(const float* wpos9, const vct_frame_params*, int D, float* levels4, float* uvw, long long cap);
 /* a9(1) occupancy voxelise at 32^3 — voxelize.frag:187-193 */
 void orc_occupancy(const orc_scene*, const vct_frame_params*, unsigned* occ);

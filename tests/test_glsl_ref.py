@@ -458,3 +458,77 @@ def test_reference_cpu_frame_equals_the_oracle_frame():
     ia, ib = a.image.reshape(H, W)[rows], r.image.reshape(H, W)[rows]
     covered = b.vis.reshape(H, W)[rows] != np.uint64(0xFFFFFFFFFFFFFFFF)
     assert covered.sum() > 1000 and np.array_equal(ia[covered], ib[covered]) and a.cone_steps == r.cone_steps
+
+
+# ===================================================== vertex / geometry stages: voxelize.vert/.geom, simple.vert, phong.vert
+def _ulp_distance(a, b):
+    """distance in representable fp32 values between two arrays (finite values)"""
+    ia, ib = a.view(np.int32).astype(np.int64), b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia); ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return np.abs(ia - ib)
+
+
+def vertex_stage_scene():
+    """pbr_room with rotated, non-uniformly scaled and translated actors (the normal matrix and the TBN re-orthogonalisation matter)"""
+    sc = pbr_room()
+    rng = np.random.default_rng(31)
+    for i in range(1, len(sc.models)):
+        a = rng.uniform(0, 2 * np.pi)
+        rot = np.array([[np.cos(a), 0, np.sin(a), 0], [0, 1, 0, 0], [-np.sin(a), 0, np.cos(a), 0], [0, 0, 0, 1]], np.float32)
+        scl = np.diag(np.append(rng.uniform(0.5, 1.5, 3), 1.0)).astype(np.float32)
+        m = np.asarray(sc.models[i], np.float32).reshape(4, 4).T                 # column-major storage -> maths layout
+        sc.models[i] = np.ascontiguousarray((m @ rot @ scl).T.astype(np.float32))
+    return sc
+
+
+@live
+def test_vertex_and_geometry_stages_against_the_reference_glsl():
+    """voxelize.vert + voxelize.geom (the voxelisation path): world positions, normals, dominant axis and clip positions
+    IDENTICAL.  phong.vert: fragPosition, fragNormal and the re-orthogonalised T / B identical.  simple.vert / phong.vert clip
+    positions and lightFragPos: the shaders write `projection * view * model * vec4(position, 1)` (left to right: two matrix
+    products first), this repository's passes apply the matrices to the vector one after the other — the same real-number
+    result, different fp32 rounding; GLSL guarantees neither order without `precise`.  The difference is bounded here."""
+    from vct_b200 import scene as S
+    sc = vertex_stage_scene()
+    W, H = 96, 64
+    p = S.room_params(W, H)
+    o = O.Oracle(sc, 32, 5, 64, W, H)
+    nv, nt = o.s.verts.shape[0], o.s.tmat.shape[0]
+    vox, light, cam, ph = np.zeros(nt * 13, np.float32), np.zeros(nv * 4, np.float32), np.zeros(nv * 4, np.float32), np.zeros(nv * 16, np.float32)
+    O.lib().orc_vertex_stage(C.byref(o.s.c), C.byref(p), ptr(vox), ptr(light), ptr(cam), ptr(ph))
+    g = glsl()
+    vs6 = np.zeros(nv * 6, np.float32); g.glsl_voxelize_vert(C.byref(o.s.c), ptr(vs6))
+    wpos, wnrm = np.zeros(nv * 3, np.float32), np.zeros(nv * 3, np.float32)
+    O.lib().orc_world_vertices(C.byref(o.s.c), ptr(wpos), ptr(wnrm))
+    assert np.array_equal(vs6.reshape(nv, 6)[:, :3].view(np.uint32), wpos.reshape(nv, 3).view(np.uint32))       # model * position
+    assert np.array_equal(vs6.reshape(nv, 6)[:, 3:].view(np.uint32), wnrm.reshape(nv, 3).view(np.uint32))       # mat3(transpose(inverse(model))) * normal
+    gvox = np.zeros(nt * 13, np.float32); g.glsl_voxelize_geom(C.byref(o.s.c), C.byref(p), ptr(vs6), ptr(gvox))
+    assert len(set(vox.reshape(nt, 13)[:, 0].tolist())) == 3                                                       # all three axes occur
+    assert np.array_equal(gvox.view(np.uint32), vox.view(np.uint32)), "voxelize.geom: axis / clip positions differ"
+    for ax in (0, 1, 2):                                                                                           # axis_override (Application.cpp:713)
+        p.axis_override = ax
+        O.lib().orc_vertex_stage(C.byref(o.s.c), C.byref(p), ptr(vox), None, None, None)
+        g.glsl_voxelize_geom(C.byref(o.s.c), C.byref(p), ptr(vs6), ptr(gvox))
+        assert np.array_equal(gvox.view(np.uint32), vox.view(np.uint32)) and (vox.reshape(nt, 13)[:, 0] == ax).all()
+    p.axis_override = -1
+    g16, g4 = np.zeros(nv * 16, np.float32), np.zeros(nv * 4, np.float32)
+    g.glsl_phong_vert(C.byref(o.s.c), C.byref(p), ptr(g16), ptr(g4))
+    a, b = ph.reshape(nv, 16), g16.reshape(nv, 16)
+    exact = [0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15]                                                             # fragPosition, fragNormal, T, B
+    finite = np.isfinite(a[:, exact]).all(axis=1)
+    assert finite.sum() > 0.9 * nv
+    assert np.array_equal(a[finite][:, exact].view(np.uint32), b[finite][:, exact].view(np.uint32)), "phong.vert world-space outputs differ"
+    assert np.array_equal(np.isnan(a[:, exact]), np.isnan(b[:, exact]))
+    gl4 = np.zeros(nv * 4, np.float32)
+    g.glsl_simple_vert(C.byref(o.s.c), p.lp, p.lv, ptr(gl4))
+    gc4 = np.zeros(nv * 4, np.float32)
+    g.glsl_simple_vert(C.byref(o.s.c), p.projection, p.view, ptr(gc4))
+    assert np.array_equal(gc4.view(np.uint32), g4.view(np.uint32))                                                 # simple.vert and phong.vert agree with each other
+    report = {}
+    for name, ours, ref in (("shadow clip", light, gl4), ("camera clip", cam, gc4), ("lightFragPos", a[:, 6:10].reshape(-1).copy(), b[:, 6:10].reshape(-1).copy())):
+        d = _ulp_distance(ours, ref)
+        scale = np.abs(ref).reshape(-1, 4).max(axis=1).repeat(4)                                                    # cancellation: compare against the vector's magnitude
+        rel = np.abs(ours.astype(np.float64) - ref.astype(np.float64)) / np.maximum(scale, 1e-30)
+        report[name] = (int((d != 0).sum()), int(d.size), float(rel.max()))
+        assert rel.max() < 4e-7, (name, report[name])                                                              # a few units of 2^-24 relative to the vector
+    print("association-order differences (values differing, of, max relative):", report)
