@@ -334,9 +334,9 @@ def test_headless_host_loads_an_obj_through_the_ingest(tmp_path):
 @needs_ref
 @pytest.mark.parametrize("name,rel", [("cube", "cube.obj"), ("sponza_pbr", "sponza/sponza_pbr.obj")])
 def test_ingested_scene_equals_the_baked_scene_the_benchmark_reads(name, rel):
-    """The scene bench.py reads from assets/_baked (reference tinyobjloader + Pillow PNG decode) and the scene the
-    library's own ingest builds from the reference's files are the same inputs: arrays identical, and for every
-    material slot the same texels in every mip level."""
+    """The scene bench.py reads from assets/_baked (arrays written by the reference's tinyobjloader, textures decoded by the
+    library) and the scene the library's own ingest builds from the reference's files are the same inputs: arrays identical,
+    and for every material slot the same texels in every mip level."""
     if not S.baked_available(name):
         pytest.skip("assets/_baked missing")
     a, b = S.Scene(), S.Scene()
@@ -354,9 +354,9 @@ def test_ingested_scene_equals_the_baked_scene_the_benchmark_reads(name, rel):
                 continue
             ta, tb = a.textures[i], b.textures[j]
             assert (ta.width, ta.height, len(ta.levels)) == (tb.width, tb.height, len(tb.levels))
-            ch = min(ta.channels, tb.channels)              # Pillow widens 1-bit grey to RGB; stb_image keeps one channel
+            assert ta.channels == tb.channels
             for la, lb in zip(ta.levels, tb.levels):
-                assert np.array_equal(la[..., :ch], lb[..., :ch])
+                assert np.array_equal(la, lb)
             checked += 1
     assert checked >= 1
 

@@ -93,9 +93,11 @@ def baked_available(name):
     return os.path.isfile(os.path.join(BAKED, name, "vertices.f32"))
 
 
-def load_baked(scene, name, model=None, max_texture=None):
-    """Append the baked mesh `name` as a new actor (its materials/textures are appended to the scene)."""
-    from PIL import Image
+def load_baked(scene, name, model=None):
+    """Append the baked mesh `name` as a new actor (its materials/textures are appended to the scene).
+    Textures are decoded by the library's own PNG reader (vct_ingest_image: the reference's stb_image behaviour,
+    tests/test_ingest.py) and get its generated mips — no image library of the harness is involved."""
+    from . import ingest
     d = os.path.join(BAKED, name)
     verts = np.fromfile(os.path.join(d, "vertices.f32"), np.float32).reshape(-1, 14)
     idx = np.fromfile(os.path.join(d, "indices.u32"), np.uint32)
@@ -106,13 +108,11 @@ def load_baked(scene, name, model=None, max_texture=None):
         if not fn:
             return -1
         if fn not in cache:
-            im = Image.open(os.path.join(d, "textures", fn))
-            if im.mode not in ("L", "RGB", "RGBA"):
-                im = im.convert("RGBA" if "A" in im.mode or im.mode == "P" else "RGB")
-            a = np.asarray(im)
-            if max_texture and max(a.shape[:2]) > max_texture:
-                im = im.resize((max_texture, max_texture), Image.BOX); a = np.asarray(im)
-            cache[fn] = scene.add_texture(a)
+            t = ingest.load_image(os.path.join(d, "textures", fn))
+            if t["channels"] not in (1, 3, 4):                     # grey + alpha: the reference allocates no storage for it (GLHelper.cpp:194-205)
+                cache[fn] = -1
+            else:
+                scene.textures.append(ingest._texture_from_packed(t)); cache[fn] = len(scene.textures) - 1
         return cache[fn]
 
     for line in open(os.path.join(d, "materials.txt")):
