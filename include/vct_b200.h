@@ -195,6 +195,13 @@ int  vct_normalize_voxels_f16(vct_ctx*, void* color_rgba16f, void* normal_rgba16
 
 /* ---- outputs ------------------------------------------------------------------------------------------- */
 int  vct_read_image(vct_ctx*, void* rgba8 /* width*height*4, row 0 = bottom like glReadPixels */);
+/* Pipelined read-back for render loops (the reference's glfwSwapBuffers never blocks on the frame either, main.cpp:229-240):
+ * enqueue the copy of the current image into PINNED host memory on the library's copy stream and return at once; the library
+ * stream carries on with the next frame and only the next cone trace waits for the copy.  vct_read_image_wait orders the
+ * library stream behind the last copy (block_host != 0: also blocks the host until the pixels are in `pinned_rgba8`).
+ * Not for use while the library stream is being captured into a CUDA graph. */
+int  vct_read_image_async(vct_ctx*, void* pinned_rgba8);
+int  vct_read_image_wait(vct_ctx*, int block_host);
 int  vct_read_volume(vct_ctx*, int which, int level, void* out);   /* RGBA8 words / u32 occupancy / u16x4 warpmap / f16x4 */
 int  vct_write_volume(vct_ctx*, int which, int level, const void* in);   /* test hook: seed a volume */
 int  vct_read_shadowmap(vct_ctx*, float* depth /* S*S */);

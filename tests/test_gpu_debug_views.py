@@ -66,3 +66,30 @@ def test_debug_views_match_the_oracle():
     with pytest.raises(VctError, match="debug_view"):
         g.frame(p)
     g.close()
+
+
+def test_pipelined_image_readback_is_ordered_with_the_next_frame():
+    """vct_read_image_async: frame A's image is copied on the copy stream while frame B (a different view, so every pixel
+    differs) is already being computed; B's cone trace must wait for A's copy.  Both host buffers hold their own frame."""
+    import torch
+    from vct_b200.pipeline import Pipeline
+    sc = pbr_room()
+    g = Pipeline(sc, D, L, SS, W, H)
+    pa = S.room_params(W, H)
+    pb = S.room_params(W, H); pb.debug_view = P.VIEW_NORMALS
+    g.frame(pa); want_a = g.read_image().copy()
+    g.frame(pb); want_b = g.read_image().copy()
+    assert (want_a != want_b).mean() > 0.5
+    bufs = [torch.zeros(W * H, dtype=torch.int32).pin_memory() for _ in range(2)]
+    for rounds in range(20):                                     # many back-to-back pairs: a missing wait shows up as torn images
+        g.frame(pa); g.read_image_async(bufs[0].data_ptr())
+        g.frame(pb); g.read_image_async(bufs[1].data_ptr())
+        g.gi_passes(pa)                                          # a third frame in flight behind both copies
+        g.read_image_wait(block_host=True)
+        g.sync()
+        assert np.array_equal(bufs[0].numpy().view(np.uint32), want_a), f"round {rounds}: buffer A torn"
+        assert np.array_equal(bufs[1].numpy().view(np.uint32), want_b), f"round {rounds}: buffer B torn"
+        bufs[0].zero_(); bufs[1].zero_()
+    g.read_image_wait(block_host=False)                          # nothing pending: a no-op
+    assert np.array_equal(g.read_image(), want_a)                # the blocking call still works (image of the last frame: pa)
+    g.close()

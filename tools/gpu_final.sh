@@ -6,8 +6,10 @@ timeout 400 python -m pytest tests -m gpu -x -q -s 2>&1 | grep -v "^$" | tail -2
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/${TAG}_smoke.txt
 timeout 300 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -3 gpurun_out/${TAG}_bench.err
+if [ "${REF_ARM:-0}" = "1" ]; then
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 tail -2 gpurun_out/${TAG}_bench_reference.err; cut -c1-400 gpurun_out/${TAG}_bench_reference.json
+fi
 python - <<PY
 import json
 try:

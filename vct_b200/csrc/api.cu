@@ -300,6 +300,8 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
     for (auto& ev : c->ev) if (cudaEventCreate(&ev) != cudaSuccess) return bail("event");
     for (auto& ev : c->stage_ev) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail("copy stream");
+    if (cudaEventCreateWithFlags(&c->ev_image_ready, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (make_frame_blob(c)) return bail("frame constants");
     if (make_volumes(c)) return bail("volumes");
     const int N = VCT_WARP_DIM;
@@ -331,6 +333,9 @@ int vct_destroy(vct_ctx* c) {
     for (void* p : c->tex_allocs) cudaFree(p);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->stage_ev) if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_image_ready) cudaEventDestroy(c->ev_image_ready);
+    if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto& ev : c->prof_pool) cudaEventDestroy(ev);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
@@ -566,6 +571,25 @@ int vct_read_image(vct_ctx* c, void* rgba8) {
     if (!c || !rgba8) return 1;
     cudaSetDevice(c->cfg.device);
     VCT_CHECK(c, cudaMemcpyAsync(rgba8, c->d_image, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+// Pipelined read-back: the copy of this frame's image runs on a second stream while the library stream goes on with the next
+// frame's voxel passes; only the next cone trace (the next writer of the image) waits for it.
+int vct_read_image_async(vct_ctx* c, void* pinned_rgba8) {
+    if (!c || !pinned_rgba8) return 1;
+    cudaSetDevice(c->cfg.device);
+    VCT_CHECK(c, cudaEventRecord(c->ev_image_ready, c->stream));
+    VCT_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_image_ready, 0));
+    VCT_CHECK(c, cudaMemcpyAsync(pinned_rgba8, c->d_image, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    VCT_CHECK(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    c->copy_pending = true;
+    return 0;
+}
+int vct_read_image_wait(vct_ctx* c, int block_host) {
+    if (!c) return 1;
+    cudaSetDevice(c->cfg.device);
+    if (c->copy_pending) { VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0)); c->copy_pending = false; }
+    if (block_host) VCT_CHECK(c, cudaStreamSynchronize(c->copy_stream));
     return 0;
 }
 int vct_read_shadowmap(vct_ctx* c, float* d) {

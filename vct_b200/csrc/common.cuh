@@ -161,6 +161,9 @@ struct vct_ctx {
     cudaEvent_t ev[32]{}; vct_timings timings{};
     int profiling = 1;               // 0 none, 1 pass-level events (reference GLTimer semantics), 2 + one event per kernel
     bool own_stream = true;
+    // asynchronous image read-back (vct_read_image_async): the copy runs on its own stream behind the frame and the next
+    // cone trace waits for it before it overwrites d_image
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_image_ready = nullptr, ev_copy_done = nullptr; bool copy_pending = false;
     int trace_variant = 0;           // VCT_TRACE_VARIANT (tuning knob, see cone_trace.cu)
     std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;

@@ -591,6 +591,10 @@ int vctk_cone_trace(vct_ctx* c) {
     a.vol_last = rad ? c->radiance_tex_last : c->color_tex_last; a.warp = reinterpret_cast<const ushort4*>(c->d_warpmap);
     a.image = c->d_image; a.counters = c->d_counters;
     if (a.y_hi <= a.y_lo) return 0;
+    if (c->copy_pending) {                                      // vct_read_image_async: the previous frame's image is still being read back
+        VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+        c->copy_pending = false;
+    }
     if ((c->trace_variant & 8) && c->n_vertices) {               // VCT_TRACE_VARIANT bit 3: L2 prefetch (measured: -14 us in the trace, +13 us for itself: off)
         PrefetchRanges r{};
         auto add = [&](const void* p, size_t bytes) { if (p && bytes) { r.p[r.n] = (const char*)p; r.lines[r.n] = (bytes + 127) / 128; r.n++; } };

@@ -20,6 +20,7 @@ SYMBOLS = [
     "vct_set_stream", "vct_set_profiling", "vct_get_kernel_times",
     "vct_exchange_setup", "vct_exchange_export", "vct_exchange_import", "vct_exchange_push", "vct_exchange_unpack",
     "vct_frame_was_sparse", "vct_mask_parity",
+    "vct_read_image_async", "vct_read_image_wait",
     "vct_ingest_obj", "vct_ingest_image", "vct_ingest_free", "vct_ingest_log", "vct_ingest_get_mesh",
     "vct_ingest_get_material", "vct_ingest_get_texture", "vct_ingest_upload",
 ]
@@ -51,7 +52,7 @@ def load():
         "vct_mip": (ci, [vp, ci]), "vct_exchange": (ci, [vp]),
         "vct_set_voxel_opacity": (ci, [vp, cf]), "vct_temporal_radiance_filter": (ci, [vp, cf]), "vct_filter3d": (ci, [vp, ci, ci]),
         "vct_normalize_voxels_f16": (ci, [vp, vp, vp, cf]),
-        "vct_read_image": (ci, [vp, vp]), "vct_read_volume": (ci, [vp, ci, ci, vp]), "vct_write_volume": (ci, [vp, ci, ci, vp]),
+        "vct_read_image": (ci, [vp, vp]), "vct_read_image_async": (ci, [vp, vp]), "vct_read_image_wait": (ci, [vp, ci]), "vct_read_volume": (ci, [vp, ci, ci, vp]), "vct_write_volume": (ci, [vp, ci, ci, vp]),
         "vct_read_shadowmap": (ci, [vp, vp]), "vct_write_shadowmap": (ci, [vp, vp]), "vct_read_visibility": (ci, [vp, vp]),
         "vct_get_counters": (ci, [vp, C.POINTER(P.VoxelizeInfo)]), "vct_get_timings": (ci, [vp, C.POINTER(P.Timings)]),
         "vct_get_cone_steps": (ci, [vp, C.POINTER(C.c_ulonglong)]), "vct_sync": (ci, [vp]),

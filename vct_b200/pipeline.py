@@ -119,6 +119,13 @@ class Pipeline:
             out = np.empty(self.W * self.H, np.uint32)
         self._ck(self.lib.vct_read_image(self.h, out.ctypes.data)); return out
 
+    def read_image_async(self, pinned_ptr):
+        """Enqueue the read-back of the current image into pinned host memory (int address); returns at once."""
+        self._ck(self.lib.vct_read_image_async(self.h, pinned_ptr))
+
+    def read_image_wait(self, block_host=True):
+        self._ck(self.lib.vct_read_image_wait(self.h, 1 if block_host else 0))
+
     def image_rgba(self):
         return self.read_image().view(np.uint8).reshape(self.H, self.W, 4)[::-1]
 

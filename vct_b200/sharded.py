@@ -184,16 +184,26 @@ class ShardedFrame:
             r, n = self.rank, self.band_px
             self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
 
-    def step_e2e(self, host_img):
-        """host_img: pinned int32 tensor of W*H pixels.  Frame parameters go host->device inside vct_gi_passes."""
+    def step_e2e(self, host_img, pipelined=False):
+        """host_img: pinned int32 tensor of W*H pixels.  Frame parameters go host->device inside vct_gi_passes.
+        pipelined (one GPU): the read-back is enqueued on the library's copy stream (vct_read_image_async) and overlaps the next
+        step's voxel passes; the caller alternates two host buffers and ends the loop with finish_e2e()."""
         self.step()
         g = self.g
         if self.world == 1:
-            g._ck(g.lib.vct_read_image(g.h, host_img.data_ptr()))
+            if pipelined:
+                g.read_image_async(host_img.data_ptr())
+            else:
+                g._ck(g.lib.vct_read_image(g.h, host_img.data_ptr()))
         elif self.rank == 0:
             with self.torch.cuda.stream(self.stream):
                 host_img.copy_(self.image[: g.W * g.H], non_blocking=True)
             self.stream.synchronize()
+
+    def finish_e2e(self):
+        """Order the library stream behind the last pipelined read-back (so that an event recorded next covers it)."""
+        if self.world == 1:
+            self.g.read_image_wait(block_host=False)
 
     def profiled_step(self):
         """Per-kernel times {name: (ns, launches)} of one step (library profiling level 2)."""
