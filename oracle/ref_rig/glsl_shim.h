@@ -479,6 +479,16 @@ inline vec4 textureLod(const sampler3D& s, const vec3& tc, float lambda) {
     return lerp4(vol_linear(s, l0, tc), vol_linear(s, l0 + 1, tc), lambda - fl);
 }
 
+// textureLodOffset on a voxel volume (filter3d.comp): explicit lod, integer texel offset; lod <= 0.5 magnifies -> NEAREST on level 0
+inline vec4 textureLodOffset(const sampler3D& s, const vec3& tc, float lambda, const ivec3& off) {
+    if (!(lambda > 0.5f)) {
+        const int d = s.dim;
+        return vol_texel(s, 0, (int)std::floor(tc.x * (float)d) + off.x, (int)std::floor(tc.y * (float)d) + off.y, (int)std::floor(tc.z * (float)d) + off.z);
+    }
+    const int l = lambda >= (float)(s.levels - 1) ? s.levels - 1 : (int)std::floor(lambda);
+    const int d = s.dim >> l ? s.dim >> l : 1;
+    return vol_linear(s, l, vec3(tc.x + (float)off.x / (float)d, tc.y + (float)off.y / (float)d, tc.z + (float)off.z / (float)d));
+}
 template <class T> struct ssbo_array { const T* data = nullptr; int n = 0; const T& operator[](int i) const { return data[i]; } int length() const { return n; } };
 template <class T> inline int glsl_length(const ssbo_array<T>& a) { return a.n; }
 

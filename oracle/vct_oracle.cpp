@@ -1,7 +1,7 @@
 // vct_oracle.cpp — CPU ORACLE (test infrastructure only).  Pinned bit for bit against the reference's own sources compiled in
 // place (oracle/_ref, see vct_oracle.h): the host C++ of the warp tables/example, and the GLSL of transferVoxels,
 // filterRadiance, voxelFillHoles, injectRadiance, the dead post-pass variants, voxelize.frag and phong.frag compiled as C++
-// and generateWarpmap{,Weights}.frag (tests/test_glsl_ref.py).  Vertex/geometry stages: see vct_oracle.h.  Still unpinned: the two alpha tests, filter3d.comp.
+// and generateWarpmap{,Weights}.frag (tests/test_glsl_ref.py).  Vertex/geometry stages: see vct_oracle.h.  Still unpinned: the two alpha tests.
 //
 // A restatement of the reference's GLSL passes in plain C++ with OpenGL's implementation-defined behaviour
 // fixed to one explicit definition (DESIGN.md "Canonical GL semantics").  Compile with -ffp-contract=off:

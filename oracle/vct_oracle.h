@@ -11,7 +11,7 @@
  *     tables) -> _ref/{warp_rig,warpmap_cpu}; fixtures tests/golden/warp_rig_ref.json, warpmap_cpu_ref.npz;
  *     tests/test_oracle_kat.py checks orc_warp_rig / orc_warp_partials / orc_warp_weight_table against them;
  *   - GLSL: transferVoxels.comp, filterRadiance.comp (BOX2/BOX3/CUBE), voxelFillHoles.comp, injectRadiance.comp,
- *     setVoxelOpacity.comp, normalizeVoxels.comp, temporalRadianceFilter.comp, voxelize.frag, phong.frag (+ common.glsl) and
+ *     setVoxelOpacity.comp, normalizeVoxels.comp, temporalRadianceFilter.comp, filter3d.comp, voxelize.frag, phong.frag (+ common.glsl) and
  *     generateWarpmapWeights.frag / generateWarpmap.frag, testTesselation.tesc / .tese
  *     are mapped to C++ SYNTAX by ref_rig/glsl2cpp.py (bodies untouched), compiled against ref_rig/glsl_shim.h into
  *     _ref/libvct_glsl_ref.so and run on the same seeded inputs as the orc_* functions (compute shaders: whole dispatches;
@@ -26,7 +26,7 @@
  *     identical; the camera / light clip transforms differ by association order only (the shaders multiply the matrices first,
  *     the passes here transform the vector step by step): <= 2e-7 relative, bounded by the test, see DESIGN.md section 2.
  * STILL UNPINNED (restated from the source, known-answer tests only, tests/golden/kat.json): dither.frag /
- * reflectiveShadowMap.frag (one alpha test each) and filter3d.comp (dead; uses textureLodOffset).
+ * reflectiveShadowMap.frag (one alpha test each).
  *
  * POD parameter structs are shared with the product's public header (the boundary spec); no code is.
  */

@@ -135,6 +135,9 @@ def run_cases(impl):
         vol = voxel_volume(D, 22, fill=0.6, counts=False)
         f("temporal_radiance_filter")(D, 0.8, ptr(vol))
         out[f"temporal_filter_{D}"] = vol
+        src = voxel_volume(2 * D, 24, fill=0.5, counts=False); dst = np.zeros(D ** 3, np.uint32)      # filter3d.comp: 2x2x2 mean through the sampler
+        f("filter3d")(2 * D, ptr(src), ptr(dst))
+        out[f"filter3d_{2 * D}"] = dst
         rng = np.random.default_rng(23)
         cnt = np.where(rng.random(D ** 3) < 0.3, rng.integers(1, 30, D ** 3), 0).astype(np.float32)
         c16 = (rng.random((D ** 3, 4), dtype=np.float32) * cnt[:, None]).astype(np.float16); c16[:, 3] = cnt.astype(np.float16)
