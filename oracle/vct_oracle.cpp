@@ -253,6 +253,30 @@ Prepared prepare(const orc_scene* sc, bool tbn) {
     return P;
 }
 
+// ---- clip transforms of the camera / light passes.  Default ("stepwise"): P * (V * world), ls * world — one world-space
+// position shared by every pass (what the CUDA passes do).  Literal mode (orc_set_literal_vertex_transforms, tests only): the
+// shaders' own association, simple.vert:21 / phong.vert:41,45: ((projection * view) * model) * vec4(position, 1) and
+// (ls * model) * vec4(position, 1).  Same real-number result, different fp32 rounding.
+static int g_literal_vertex_transforms = 0;
+inline void matmul44(const float* a, const float* b, float* r) {            // r = a * b, column by column
+    for (int j = 0; j < 4; ++j) { V4 c = mul(a, {b[4 * j], b[4 * j + 1], b[4 * j + 2], b[4 * j + 3]}); r[4 * j] = c.x; r[4 * j + 1] = c.y; r[4 * j + 2] = c.z; r[4 * j + 3] = c.w; }
+}
+struct ClipMats {                                                            // per actor: (A * B) * model
+    std::vector<float> m; bool literal;
+    ClipMats(const orc_scene* sc, const float* A, const float* B) : literal(g_literal_vertex_transforms != 0) {
+        if (!literal) return;
+        float ab[16];
+        if (B) matmul44(A, B, ab); else std::memcpy(ab, A, sizeof ab);
+        m.resize((size_t)sc->n_actors * 16);
+        for (int a = 0; a < sc->n_actors; ++a) matmul44(ab, sc->actor_model + 16 * (size_t)a, &m[16 * (size_t)a]);
+    }
+    V4 apply(const orc_scene* sc, const float* A, const float* B, unsigned vi, V3 w) const {
+        if (!literal) return B ? mul(A, mul(B, {w.x, w.y, w.z, 1.0f})) : mul(A, {w.x, w.y, w.z, 1.0f});
+        const float* v = sc->vertices + 14 * (size_t)vi;
+        return mul(&m[16 * (size_t)sc->vertex_actor[vi]], {v[0], v[1], v[2], 1.0f});
+    }
+};
+
 // ------------------------------------------------------------------------------------------ rasteriser
 // Canonical coverage: window = (ndc*0.5+0.5)*size, snapped to 8 sub-pixel bits with
 // floor(x*256+0.5); 64-bit integer edge functions; sample at pixel centres; top-left rule in y-up window
@@ -362,8 +386,10 @@ inline bool has_alpha(const orc_scene* sc, int m) { return sc->materials[m].alph
 // Application.cpp:212-233; simple.vert:15-22 (gl_Position = projection*view*model*pos, evaluated right to
 // left as three mat*vec); reflectiveShadowMap.frag:34-38 (alpha discard); GL state: depth test LESS, back-face
 // culling on (steady state after Application.cpp:285), depth = ndc.z*0.5+0.5 stored as float32, clear 1.
+extern "C" void orc_set_literal_vertex_transforms(int on) { g_literal_vertex_transforms = on; }
 extern "C" void orc_shadowmap(const orc_scene* sc, const vct_frame_params* fp, int S, float* depth) {
     Prepared P = prepare(sc, false);
+    const ClipMats light_clip(sc, fp->lp, fp->lv);
     for (size_t i = 0; i < (size_t)S * S; ++i) depth[i] = 1.0f;
     int nb = 1;
 #ifdef _OPENMP
@@ -378,7 +404,7 @@ extern "C" void orc_shadowmap(const orc_scene* sc, const vct_frame_params* fp, i
             for (int k = 0; k < 3; ++k) {
                 const unsigned vi = sc->indices[3 * t + k];
                 V3 w = P.wpos[vi];
-                V4 c = mul(fp->lp, mul(fp->lv, {w.x, w.y, w.z, 1.0f}));
+                V4 c = light_clip.apply(sc, fp->lp, fp->lv, vi, w);
                 cv[k] = {c.x, c.y, c.z, c.w};
                 uv[k][0] = sc->vertices[14 * (size_t)vi + 6]; uv[k][1] = sc->vertices[14 * (size_t)vi + 7];
             }
@@ -703,6 +729,7 @@ extern "C" void orc_world_vertices(const orc_scene* sc, float* wpos, float* wnrm
 //   phong  n_vertices x 16 : fragPosition 3, fragNormal 3, lightFragPos 4, TBN columns T 3 and B 3   phong.vert:36-58
 extern "C" void orc_vertex_stage(const orc_scene* sc, const vct_frame_params* fp, float* voxel, float* light, float* cam, float* phong) {
     Prepared P = prepare(sc, true);
+    const ClipMats light_clip(sc, fp->lp, fp->lv), cam_clip(sc, fp->projection, fp->view), ls_clip(sc, fp->ls, nullptr);
     if (voxel)
         for (int t = 0; t < sc->n_tris; ++t) {
             const unsigned* ix = sc->indices + 3 * (size_t)t;
@@ -713,10 +740,10 @@ extern "C" void orc_vertex_stage(const orc_scene* sc, const vct_frame_params* fp
         }
     for (int i = 0; i < sc->n_vertices; ++i) {
         const V3 w = P.wpos[i];
-        if (light) { V4 c = mul(fp->lp, mul(fp->lv, {w.x, w.y, w.z, 1.0f})); float* o = light + 4 * (size_t)i; o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w; }
-        if (cam) { V4 c = mul(fp->projection, mul(fp->view, {w.x, w.y, w.z, 1.0f})); float* o = cam + 4 * (size_t)i; o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w; }
+        if (light) { V4 c = light_clip.apply(sc, fp->lp, fp->lv, (unsigned)i, w); float* o = light + 4 * (size_t)i; o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w; }
+        if (cam) { V4 c = cam_clip.apply(sc, fp->projection, fp->view, (unsigned)i, w); float* o = cam + 4 * (size_t)i; o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w; }
         if (phong) {
-            V4 l = mul(fp->ls, {w.x, w.y, w.z, 1.0f});
+            V4 l = ls_clip.apply(sc, fp->ls, nullptr, (unsigned)i, w);
             const float v[16] = {w.x, w.y, w.z, P.wnrm[i].x, P.wnrm[i].y, P.wnrm[i].z, l.x, l.y, l.z, l.w, P.T[i].x, P.T[i].y, P.T[i].z, P.B[i].x, P.B[i].y, P.B[i].z};
             std::memcpy(phong + 16 * (size_t)i, v, sizeof v);
         }
@@ -1076,6 +1103,7 @@ inline float pixel_rho2(const Homog& h, const float uv[3][2], float nx, float ny
 
 extern "C" void orc_visibility(const orc_scene* sc, const vct_frame_params* fp, int W, int H, unsigned long long* vis) {
     Prepared P = prepare(sc, false);
+    const ClipMats cam_clip(sc, fp->projection, fp->view);
     for (size_t i = 0; i < (size_t)W * H; ++i) vis[i] = ~0ull;
     int nb = 1;
 #ifdef _OPENMP
@@ -1090,7 +1118,7 @@ extern "C" void orc_visibility(const orc_scene* sc, const vct_frame_params* fp, 
             for (int k = 0; k < 3; ++k) {
                 const unsigned vi = sc->indices[3 * t + k];
                 V3 w = P.wpos[vi];
-                V4 c = mul(fp->projection, mul(fp->view, {w.x, w.y, w.z, 1.0f}));
+                V4 c = cam_clip.apply(sc, fp->projection, fp->view, vi, w);
                 cv[k] = {c.x, c.y, c.z, c.w};
                 uv[k][0] = sc->vertices[14 * (size_t)vi + 6]; uv[k][1] = sc->vertices[14 * (size_t)vi + 7];
             }
@@ -1231,6 +1259,7 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
                        const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
                        const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec) {
     Prepared P = prepare(sc, true);
+    const ClipMats cam_clip(sc, fp->projection, fp->view), ls_clip(sc, fp->ls, nullptr);
     Vol rad, colv; rad.D = colv.D = D; rad.L = colv.L = L;
     { size_t off = 0; for (int l = 0; l < L; ++l) { rad.lv[l] = radiance_pyr + off; colv.lv[l] = color_pyr ? color_pyr + off : nullptr; const size_t d = std::max(1, D >> l); off += d * d * d; } }
     const Vol& vol = (fp->draw_radiance || !color_pyr) ? rad : colv;      // radiance ? voxelRadiance : voxelColor
@@ -1248,8 +1277,8 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
             RV cv[3]; float uv[3][2]; V4 lfp[3];
             for (int k = 0; k < 3; ++k) {
                 V3 w = P.wpos[ix[k]];
-                V4 c = mul(fp->projection, mul(fp->view, {w.x, w.y, w.z, 1.0f})); cv[k] = {c.x, c.y, c.z, c.w};
-                lfp[k] = mul(fp->ls, {w.x, w.y, w.z, 1.0f});                  // phong.vert:45
+                V4 c = cam_clip.apply(sc, fp->projection, fp->view, ix[k], w); cv[k] = {c.x, c.y, c.z, c.w};
+                lfp[k] = ls_clip.apply(sc, fp->ls, nullptr, ix[k], w);         // phong.vert:45
                 uv[k][0] = sc->vertices[14 * (size_t)ix[k] + 6]; uv[k][1] = sc->vertices[14 * (size_t)ix[k] + 7];
             }
             const vct_material& mat = sc->materials[sc->tri_material[t]];

@@ -66,6 +66,8 @@ void orc_voxelize_tess(const orc_scene*, const vct_frame_params*, int D, unsigne
 void orc_voxelize_tess_trace(const orc_scene*, const vct_frame_params*, int D, unsigned* color, unsigned* normal, vct_voxelize_info* info,
                              float* rec, long long rec_cap, long long* rec_count);
 void orc_world_vertices(const orc_scene*, float* wpos3, float* wnrm3);
+/* tests only: evaluate the camera / light clip transforms with the shaders' own association ((P*V)*M)*v instead of P*(V*(M*v)) */
+void orc_set_literal_vertex_transforms(int on);
 void orc_vertex_stage(const orc_scene*, const vct_frame_params*, float* voxel13, float* light4, float* cam4, float* phong16);
 long long orc_tess_patch(const float* wpos9, const vct_frame_params*, int D, float* levels4, float* uvw, long long cap);
 /* a9(1) occupancy voxelise at 32^3 — voxelize.frag:187-193 */

@@ -535,3 +535,40 @@ def test_vertex_and_geometry_stages_against_the_reference_glsl():
         report[name] = (int((d != 0).sum()), int(d.size), float(rel.max()))
         assert rel.max() < 4e-7, (name, report[name])                                                              # a few units of 2^-24 relative to the vector
     print("association-order differences (values differing, of, max relative):", report)
+    # with the shaders' own association switched on in the oracle (tests only) nothing differs any more
+    O.lib().orc_set_literal_vertex_transforms(1)
+    try:
+        O.lib().orc_vertex_stage(C.byref(o.s.c), C.byref(p), None, ptr(light), ptr(cam), ptr(ph))
+    finally:
+        O.lib().orc_set_literal_vertex_transforms(0)
+    assert np.array_equal(light.view(np.uint32), gl4.view(np.uint32)) and np.array_equal(cam.view(np.uint32), gc4.view(np.uint32))
+    assert np.array_equal(ph.reshape(nv, 16)[:, 6:10].view(np.uint32), b[:, 6:10].view(np.uint32))
+
+
+def test_association_order_of_the_clip_transforms_changes_no_pixel_class():
+    """End-to-end effect of the one known deviation: the same frame with the oracle's stepwise transforms and
+    with the shaders' literal ones.  Shadow-map depths move by ulps, coverage does not change, the image stays far above the gate."""
+    from vct_b200 import scene as S
+    D, Lv, SS, W, H = 32, 5, 256, 96, 64
+    sc = vertex_stage_scene()
+    p = S.room_params(W, H)
+    a, b = O.Oracle(sc, D, Lv, SS, W, H), O.Oracle(sc, D, Lv, SS, W, H)
+    a.frame(p)
+    O.lib().orc_set_literal_vertex_transforms(1)
+    try:
+        b.frame(p)
+    finally:
+        O.lib().orc_set_literal_vertex_transforms(0)
+    covered_a, covered_b = a.shadow < 1.0, b.shadow < 1.0
+    assert np.array_equal(covered_a, covered_b), "shadow-map coverage changed"
+    d = _ulp_distance(a.shadow[covered_a], b.shadow[covered_b])
+    assert d.max() <= 16, d.max()                                          # depths agree to a few ulp
+    assert np.array_equal(a.color[0], b.color[0])                         # the voxelisation path does not depend on it
+    same_tri = (a.vis & np.uint64(0xFFFFFFFF)) == (b.vis & np.uint64(0xFFFFFFFF))
+    assert same_tri.mean() > 0.999, same_tri.mean()                       # the visible triangle of (almost) every pixel is the same
+    x = a.image.view(np.uint8).reshape(-1, 4)[:, :3].astype(np.float64); y = b.image.view(np.uint8).reshape(-1, 4)[:, :3].astype(np.float64)
+    mse = ((x - y) ** 2).mean()
+    psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+    print(f"literal vs stepwise transforms: shadow texels differing {(d != 0).mean():.3f} (max {d.max()} ulp), visibility pixels differing {(~same_tri).sum()}, "
+          f"radiance words differing {(a.radiance[0] != b.radiance[0]).sum()}, image PSNR {psnr:.1f} dB")
+    assert psnr >= 60.0
