@@ -380,6 +380,24 @@ inline void homog_eval(const Homog& h, float nx, float ny, float l[3]) {
 
 inline bool has_alpha(const orc_scene* sc, int m) { return sc->materials[m].alpha_tex >= 0; }
 
+// tests only (orc_alpha_trace): every alpha-tested fragment of the shadow-map and depth-prepass passes with what its fragment
+// stage sees — 6 floats: pass (0 = reflectiveShadowMap.frag, 1 = dither.frag), material, u, v, rho^2 of the alpha map, kept (1)
+// or discarded (0).  tests/test_glsl_ref.py replays the reference's two shaders on these records.  Each record carries its own
+// decision, so the order in which the raster bands append does not matter.
+struct AlphaTrace { float* rec = nullptr; long long cap = 0, n = 0; };
+AlphaTrace g_alpha_trace;
+inline void alpha_record(int pass, int material, float u, float v, float rho2, bool kept) {
+    if (!g_alpha_trace.rec) return;
+#pragma omp critical(orc_alpha_trace)
+    {
+        const long long i = g_alpha_trace.n++;
+        if (i < g_alpha_trace.cap) {
+            float* r = g_alpha_trace.rec + 6 * i;
+            r[0] = (float)pass; r[1] = (float)material; r[2] = u; r[3] = v; r[4] = rho2; r[5] = kept ? 1.0f : 0.0f;
+        }
+    }
+}
+
 }  // namespace
 
 // =================================================================================================== a0
@@ -387,6 +405,8 @@ inline bool has_alpha(const orc_scene* sc, int m) { return sc->materials[m].alph
 // left as three mat*vec); reflectiveShadowMap.frag:34-38 (alpha discard); GL state: depth test LESS, back-face
 // culling on (steady state after Application.cpp:285), depth = ndc.z*0.5+0.5 stored as float32, clear 1.
 extern "C" void orc_set_literal_vertex_transforms(int on) { g_literal_vertex_transforms = on; }
+extern "C" void orc_alpha_trace(float* rec, long long cap) { g_alpha_trace.rec = rec; g_alpha_trace.cap = cap; if (rec) g_alpha_trace.n = 0; }
+extern "C" long long orc_alpha_trace_count(void) { return g_alpha_trace.n; }
 extern "C" void orc_shadowmap(const orc_scene* sc, const vct_frame_params* fp, int S, float* depth) {
     Prepared P = prepare(sc, false);
     const ClipMats light_clip(sc, fp->lp, fp->lv);
@@ -420,7 +440,9 @@ extern "C" void orc_shadowmap(const orc_scene* sc, const vct_frame_params* fp, i
                 if (z < -1.0f || z > 1.0f) return;                        // near/far clip
                 if (alpha) {
                     const float u = interp(l, uv[0][0], uv[1][0], uv[2][0]), v = interp(l, uv[0][1], uv[1][1], uv[2][1]);
-                    if (sample2d(*at, u, v, rho2).x < 0.1f) return;
+                    const bool kept = !(sample2d(*at, u, v, rho2).x < 0.1f);
+                    alpha_record(0, m, u, v, rho2, kept);
+                    if (!kept) return;
                 }
                 const float d = z * 0.5f + 0.5f;
                 float& dst = depth[(size_t)py * S + px];
@@ -1140,7 +1162,9 @@ extern "C" void orc_visibility(const orc_scene* sc, const vct_frame_params* fp, 
                         float lb[3];
                         const float rho2 = pixel_rho2(hg, uv, nx, ny, 2.0f / (float)W, 2.0f / (float)H, *at, lb);
                         const float u = interp(lb, uv[0][0], uv[1][0], uv[2][0]), v = interp(lb, uv[0][1], uv[1][1], uv[2][1]);
-                        if (sample2d(*at, u, v, rho2).x < 0.1f) return;
+                        const bool kept = !(sample2d(*at, u, v, rho2).x < 0.1f);
+                        alpha_record(1, m, u, v, rho2, kept);
+                        if (!kept) return;
                     }
                     const float d = z * 0.5f + 0.5f;
                     uint32_t db; std::memcpy(&db, &d, 4);

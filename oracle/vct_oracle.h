@@ -68,6 +68,10 @@ void orc_voxelize_tess_trace(const orc_scene*, const vct_frame_params*, int D, u
 void orc_world_vertices(const orc_scene*, float* wpos3, float* wnrm3);
 /* tests only: evaluate the camera / light clip transforms with the shaders' own association ((P*V)*M)*v instead of P*(V*(M*v)) */
 void orc_set_literal_vertex_transforms(int on);
+/* tests only: record the alpha-tested fragments of orc_shadowmap (pass 0) / orc_visibility (pass 1): 6 floats each — pass, material,
+   u, v, rho^2 of the alpha map, kept; rec = NULL stops recording; the count keeps running past cap */
+void orc_alpha_trace(float* rec6, long long cap);
+long long orc_alpha_trace_count(void);
 void orc_vertex_stage(const orc_scene*, const vct_frame_params*, float* voxel13, float* light4, float* cam4, float* phong16);
 long long orc_tess_patch(const float* wpos9, const vct_frame_params*, int D, float* levels4, float* uvw, long long cap);
 /* a9(1) occupancy voxelise at 32^3 — voxelize.frag:187-193 */

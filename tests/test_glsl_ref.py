@@ -572,3 +572,77 @@ def test_association_order_of_the_clip_transforms_changes_no_pixel_class():
     print(f"literal vs stepwise transforms: shadow texels differing {(d != 0).mean():.3f} (max {d.max()} ulp), visibility pixels differing {(~same_tri).sum()}, "
           f"radiance words differing {(a.radiance[0] != b.radiance[0]).sum()}, image PSNR {psnr:.1f} dB")
     assert psnr >= 60.0
+
+
+# ===================================================== a0 / a0': the alpha tests of reflectiveShadowMap.frag and dither.frag
+def alpha_scenes():
+    """(name, scene, params, S, W, H): the room's alpha-masked quad with its binary hole mask, and the same quad with a smooth noise
+    alpha map whose values cross the 0.1 threshold everywhere (many fragments land within a few 1/255 of it); near and far cameras
+    so that magnified (bilinear) and minified (mip-mapped) lookups both occur."""
+    from vct_b200 import scene as S
+    out = []
+    for name, noise in (("holes", False), ("noise", True)):
+        sc = S.room_scene()
+        if noise:
+            rng = np.random.default_rng(5)
+            a = rng.random((8, 8)).astype(np.float32)
+            a = np.kron(a, np.ones((8, 8), np.float32))
+            for _ in range(6):                                   # smooth: a field that hovers around the threshold
+                a = (a + np.roll(a, 1, 0) + np.roll(a, -1, 0) + np.roll(a, 1, 1) + np.roll(a, -1, 1)) / 5
+            a = np.clip((a - a.mean()) * 120 + 26, 0, 255).astype(np.uint8)
+            t = sc.add_texture(a)
+            for m in sc.materials:
+                if m.alpha_tex >= 0:
+                    m.alpha_tex = t
+        for cam_name, pos, W, H, SS in (("near", (0.9, 0.0, 1.6), 96, 64, 256), ("far", (1.4, 1.2, 1.45), 48, 32, 64)):
+            p = S.room_params(W, H)
+            cam = P.Camera(position=pos, front=(0.45 - pos[0], -0.15 - pos[1], 0.7 - pos[2]))
+            q = P.default_params(W, H, cam, P.make_light(position=(1.2, 4.0, 0.7), direction=(-0.28, -0.9, -0.2), shadow_caster=True, type_=1),
+                                 voxel_min=-1.5, voxel_max=1.5)
+            p.projection, p.view, p.pv, p.eye = q.projection, q.view, q.pv, q.eye
+            out.append((f"{name}_{cam_name}", sc, p, SS, W, H))
+    return out
+
+
+def run_alpha_cases(impl):
+    out = {}
+    for name, sc, p, SS, W, H in alpha_scenes():
+        o = O.Oracle(sc, 32, 5, SS, W, H)
+        cap = 1 << 17
+        rec = np.zeros(cap * 6, np.float32)
+        O.lib().orc_alpha_trace(ptr(rec), C.c_longlong(cap))
+        try:
+            o.shadowmap(p); o.visibility(p)
+            n = O.lib().orc_alpha_trace_count()
+        finally:
+            O.lib().orc_alpha_trace(None, C.c_longlong(0))
+        assert 0 < n <= cap, n
+        r = rec[:6 * n].reshape(n, 6)
+        r = np.ascontiguousarray(r[np.lexsort(r.view(np.uint32).T[::-1])])       # raster bands append in any order: canonical order
+        for ps, fn in ((0, "glsl_rsm_fragments"), (1, "glsl_dither_fragments")):
+            q = np.ascontiguousarray(r[r[:, 0] == ps])
+            assert len(q) > 50, (name, ps, len(q))
+            if impl == "glsl":
+                kept = np.zeros(len(q), np.uint8)
+                getattr(glsl(), fn)(C.byref(o.s.c), ptr(q), C.c_longlong(len(q)), ptr(kept))
+            else:
+                kept = q[:, 5].astype(np.uint8)
+            out[f"alpha_{name}_pass{ps}_kept"] = kept
+            out[f"alpha_{name}_pass{ps}_uv_rho2"] = np.ascontiguousarray(q[:, 2:5]).view(np.uint32).reshape(-1)
+    return out
+
+
+GOLD_ALPHA = os.path.join(ROOT, "tests", "golden", "glsl_ref_alpha.npz")
+
+
+@live
+def test_oracle_alpha_tests_equal_the_reference_glsl_compiled_as_cpp():
+    a, b = run_alpha_cases("oracle"), run_alpha_cases("glsl")
+    compare(a, b, "oracle vs compiled reflectiveShadowMap.frag / dither.frag")
+    kept = np.concatenate([v for k, v in a.items() if k.endswith("_kept")])
+    assert 0.05 < kept.mean() < 0.95, kept.mean()                      # both outcomes occur
+    print(f"{kept.size} alpha-tested fragments, {kept.mean():.3f} kept")
+
+
+def test_oracle_alpha_tests_equal_the_committed_outputs_of_the_reference_glsl():
+    compare(run_alpha_cases("oracle"), dict(np.load(GOLD_ALPHA)), "oracle vs tests/golden/glsl_ref_alpha.npz")
