@@ -322,7 +322,17 @@ def run_b200(args):
                         "timing": f"per-kernel CUDA events on the library stream, mean of {nprof} profiled frames run right after the timed region"}
             roofline["traffic_source"] = "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of one frame"
             if dom["kernel"] == "k_cone_trace":
-                roofline["note"] = "cone trace is bound by L1/texture + L2 throughput (the pyramid is re-read ~100x per frame from cache), see cone_steps_per_s"
+                roofline["note"] = "cone trace is bound by L1/texture + L2 throughput (the pyramid is re-read ~100x per frame from cache), see tex_pipe and cone_steps_per_s"
+                try:                                                   # the honest bound: TEX data-pipe wavefronts (1 per clock per SM), wavefronts per cone step from the committed capture
+                    mt = measured_traffic()
+                    wf = mt["k_cone_trace__tex_wavefronts"] / mt["k_cone_trace__cone_steps"] * steps_cone
+                    mhz = float((clk or {}).get("sm_mhz") or 1965.0)
+                    floor_ms = wf / (148 * mhz * 1e6) * 1e3
+                    roofline["tex_pipe"] = {"wavefronts": int(wf), "peak": "1 TEX wavefront / clock / SM x 148 SMs", "sm_mhz": mhz, "floor_ms": round(floor_ms, 4),
+                                            "frac": round(floor_ms / dom["ms"], 4),
+                                            "source": "l1tex__t_output_wavefronts_pipe_tex_mem_texture.sum per cone step from the committed ncu --set full capture (profiles/traffic.json) x this run's cone steps"}
+                except Exception:
+                    pass
         voxel_bytes = sum(ab[k] for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_chain"))
         voxel_ms = sum(kt.get(k, 0.0) for k in ("k_clear", "voxelize", "k_transfer", "k_inject", "k_mip_chain"))
         cpu = None

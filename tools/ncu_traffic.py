@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
 """profiles/traffic.json from an `ncu --page raw --csv` dump: DRAM bytes per launch of every kernel (first launch of each
-name), keyed by the names bench.py uses.  usage: ncu_traffic.py <raw.csv> <out.json>"""
+name), keyed by the names bench.py uses; for k_cone_trace also the TEX data-pipe wavefronts of the launch (bench.py's
+roofline.tex_pipe; "k_cone_trace__cone_steps" = the cone steps of the captured frame, from the bench line of the same build, is
+kept from the previous file).  usage: ncu_traffic.py <raw.csv> <out.json>"""
 import csv, json, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
@@ -16,5 +18,12 @@ for r in rows[2:]:
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(r[ix[m]]) * scale.get(units[ix[m]], 1)
     out[name] = int(tot)
+    wf = "l1tex__t_output_wavefronts_pipe_tex_mem_texture.sum"
+    if name == "k_cone_trace" and wf in ix:
+        out["k_cone_trace__tex_wavefronts"] = int(float(r[ix[wf]]))
+try:
+    out["k_cone_trace__cone_steps"] = json.load(open(sys.argv[2]))["k_cone_trace__cone_steps"]
+except Exception:
+    pass
 json.dump(out, open(sys.argv[2], "w"), indent=1, sort_keys=True)
 print(out)
