@@ -114,6 +114,12 @@ typedef struct {
      * patches through testTesselation.tesc/.tese instead of voxelize.vert/geom/frag (Application.cpp:585-665).  Unlit albedo,
      * atomicMax (voxelize_atomic_max, bit-reproducible) or the free-running running average (order-dependent like the GLSL). */
     int   voxelize_tesselation;
+    /* Settings::voxelizeTesselationWarp (Application.h:102, default false): the last-but-one entry of common.glsl's mapping
+     * priority (warpVoxels > warpTexture > this > linear, common.glsl:44-60): the voxel grid becomes the camera frustum,
+     * position = (pv * P).xyz / w * 0.5 + 0.5 (common.glsl:37-42).  Used by testTesselation.tese, injectRadiance.comp and
+     * phong.frag (each cone sample goes back to world space and through pv, phong.frag:158-162); voxelize.frag declares the
+     * uniform but never reads it, so the raster voxeliser ignores it — like the reference. */
+    int   voxelize_tesselation_warp;
 } vct_frame_params;
 
 enum { VCT_VIEW_SHADED = 0,

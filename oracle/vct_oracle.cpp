@@ -210,11 +210,24 @@ inline V3 voxel_warp(V3 p, V3 c) {                    // common.glsl:20-27
     return c + o;
 }
 inline V3 eye3(const vct_frame_params* fp) { return {fp->eye[0], fp->eye[1], fp->eye[2]}; }
-// common.glsl:44-60 (voxelizeTesselationWarp is outside the hot-path scope: SURVEY §2b)
+// common.glsl:37-42 (voxelizeTesselationWarp: the voxel grid is the camera frustum — NDC of pv mapped to [0,1]^3)
+inline V3 tess_warp_position(V3 pos, const vct_frame_params* fp) {
+    V4 q = mul(fp->pv, {pos.x, pos.y, pos.z, 1.0f});
+    q.x /= q.w; q.y /= q.w; q.z /= q.w;
+    return {q.x * 0.5f + 0.5f, q.y * 0.5f + 0.5f, q.z * 0.5f + 0.5f};
+}
+// common.glsl:44-60, priority warpVoxels > warpTexture > voxelizeTesselationWarp > linear
 inline V3 get_voxel_position(V3 pos, const vct_frame_params* fp, const uint16_t* warpmap) {
     if (fp->warp_voxels) return voxel_warp(voxel_linear_position(pos, fp), voxel_linear_position(eye3(fp), fp));
     if (fp->warp_texture && warpmap) return warp_sample(warpmap, voxel_linear_position(pos, fp));
+    if (fp->voxelize_tesselation_warp) return tess_warp_position(pos, fp);
     return voxel_linear_position(pos, fp);
+}
+// testTesselation.tese:134: voxelIndex(position.xyz, ..., false) inside the tessellation program — warpVoxels is passed as false
+// and the host never sets that program's warpTexture uniform (Application.cpp:630-640), so only the tessellation warp or the
+// linear mapping can apply, whatever the frame's other warp settings are
+inline V3 tese_voxel_position(V3 pos, const vct_frame_params* fp) {
+    return fp->voxelize_tesselation_warp ? tess_warp_position(pos, fp) : voxel_linear_position(pos, fp);
 }
 
 // --------------------------------------------------------------------------------- scene preprocessing
@@ -717,7 +730,7 @@ static void voxelize_tess_impl(const orc_scene* sc, const vct_frame_params* fp, 
             V4 col = {0, 0, 0, 1};
             if (dt) col = sample2d(*dt, tu, tv, 0.0f);                     // no derivatives in a TES: base level, magnification -> NEAREST
             // (the branch for patches inside one voxel, :128-131, is unreachable: those patches have tessellation level 0)
-            V3 vp = get_voxel_position(pos, fp, nullptr);                  // voxelIndex(position, int(voxelDim), ..., false): warpVoxels off
+            V3 vp = tese_voxel_position(pos, fp);                          // voxelIndex(position, int(voxelDim), ..., false)
             vp = {voxelDim * vp.x, voxelDim * vp.y, voxelDim * vp.z};      // (int(voxelDim) * pos with an integral voxelDim)
             int idx[3];
             if (!to_index(vp, D, idx)) return;
@@ -1228,6 +1241,12 @@ inline V4 trace_cone(const Vol& vol, const vct_frame_params* fp, const uint16_t*
         if (!(sp.x == clampf(sp.x, 0.0f, 1.0f)) || !(sp.y == clampf(sp.y, 0.0f, 1.0f)) || !(sp.z == clampf(sp.z, 0.0f, 1.0f))) break;
         if (fp->warp_texture && warpmap) sp = warp_sample(warpmap, sp);
         else if (fp->warp_voxels) sp = voxel_warp(sp, voxel_linear_position(eye3(fp), fp));
+        else if (fp->voxelize_tesselation_warp) {                          // :158-162: back to world space, then through pv
+            const V3 world = {(sp.x * (fp->voxel_max[0] - fp->voxel_min[0]) + fp->voxel_center[0]) + fp->voxel_min[0],
+                              (sp.y * (fp->voxel_max[1] - fp->voxel_min[1]) + fp->voxel_center[1]) + fp->voxel_min[1],
+                              (sp.z * (fp->voxel_max[2] - fp->voxel_min[2]) + fp->voxel_center[2]) + fp->voxel_min[2]};
+            sp = tess_warp_position(world, fp);                            // getVoxelPosition(world, ..., false): warpTexture is off on this branch
+        }
         V4 sc = vol_sample(vol, sp, lod + lod_offset);
         fetches++;
         const float a = 1.0f - alpha;

@@ -116,7 +116,9 @@ def run_cases(impl):
     # same dispatch write without atomics — order-dependent in the reference, whose own comment says it "doesn't work".)
     S = 96
     for name, kw in (("linear", {}), ("warp_voxels", {"warp_voxels": 1}), ("warp_texture", {"warp_texture": 1}),
-                     ("lighting", {"radiance_lighting": 1})):
+                     ("lighting", {"radiance_lighting": 1}),
+                     # voxelizeTesselationWarp (common.glsl:37-42, 52-54): the camera frustum as voxel grid; below warpTexture in priority
+                     ("tess_warp", {"voxelize_tesselation_warp": 1}), ("tess_warp_below_warp_texture", {"voxelize_tesselation_warp": 1, "warp_texture": 1})):
         D = 24
         p, light = frame_params(D, **kw)
         col, nrm = voxel_volume(D, 11, fill=0.5), voxel_volume(D, 12, fill=1.0, counts=False)
@@ -174,7 +176,9 @@ def test_cases_are_not_vacuous():
     o = run_cases("oracle")
     assert (o["transfer_plain_16_radiance"] >> 24 != 0).sum() > 100 and o["transfer_plain_16_info"][1] > 100
     assert (o["inject_linear"] != voxel_volume(24, 13, fill=0.2, counts=False)).sum() > 50       # texels landed and wrote
-    assert len({o[k].tobytes() for k in o if k.startswith("inject_")}) == 4                        # every mode differs
+    assert len({o[k].tobytes() for k in o if k.startswith("inject_")}) == 5                        # every mode differs ...
+    assert np.array_equal(o["inject_tess_warp_below_warp_texture"], o["inject_warp_texture"])      # ... except where the priority order says so
+    assert (o["inject_tess_warp"] != voxel_volume(24, 13, fill=0.2, counts=False)).sum() > 50
     assert (o["fill_holes_16"] != voxel_volume(16, 9, fill=0.2, counts=False)).sum() > 500
     assert all((o[f"mip_mode{m}_2"] != 0).any() for m in (0, 1, 2))
 
@@ -208,6 +212,12 @@ FRAG_MODES = {
     "no_reflections_no_normal_map": {"enable_reflections": 0, "enable_normal_map": 0, "draw_occlusion": 0},
     "color_volume": {"draw_radiance": 0},
     "fixed_specular_angle": {"specular_cone_angle_from_roughness": 0},
+    # both warps on: the voxeliser and the voxel view take warpVoxels first (voxelize.frag:100-105, common.glsl:44-50), traceCone takes
+    # warpTexture first (phong.frag:150-157)
+    "warp_texture_and_voxels": {"warp_texture": 1, "warp_voxels": 1},
+    "view_voxels_warp_texture_and_voxels": {"debug_view": P.VIEW_VOXELS, "miplevel": 0.7, "warp_texture": 1, "warp_voxels": 1},
+    "tess_warp": {"voxelize_tesselation_warp": 1},                        # phong.frag:158-162: every cone sample through pv
+    "tess_warp_below_warp_voxels": {"voxelize_tesselation_warp": 1, "warp_voxels": 1},
     # debug views of phong.frag
     "view_voxels_point": {"debug_view": P.VIEW_VOXELS, "miplevel": 0.0},
     "view_voxels_lod1_7": {"debug_view": P.VIEW_VOXELS, "miplevel": 1.7},
@@ -222,6 +232,7 @@ FRAG_MODES = {
     "view_occlusion": {"debug_view": P.VIEW_OCCLUSION},
     "view_reflections": {"debug_view": P.VIEW_REFLECTIONS},
     "view_reflections_off": {"debug_view": P.VIEW_REFLECTIONS, "enable_reflections": 0},
+    "view_voxels_tess_warp": {"debug_view": P.VIEW_VOXELS, "miplevel": 0.6, "voxelize_tesselation_warp": 1},
 }
 
 
@@ -400,7 +411,10 @@ def run_tess_cases(impl):
     D, SS, W, H = 32, 64, 32, 32
     sc = pbr_room()
     out = {}
-    for name, kw in (("max", {"voxelize_atomic_max": 1}), ("avg", {"voxelize_atomic_max": 0})):
+    for name, kw in (("max", {"voxelize_atomic_max": 1}), ("avg", {"voxelize_atomic_max": 0}),
+                     ("max_tess_warp", {"voxelize_atomic_max": 1, "voxelize_tesselation_warp": 1}),
+                     # voxelIndex(..., false) in a program whose warpTexture uniform the host never sets: the frame's other warps do not apply
+                     ("max_ignores_other_warps", {"voxelize_atomic_max": 1, "warp_voxels": 1})):
         p = S.room_params(W, H)
         for k, v in kw.items():
             setattr(p, k, v)

@@ -100,6 +100,15 @@ __device__ __forceinline__ V3 voxel_linear_position(V3 p, const vct_frame_params
                (p.y - fp.voxel_center[1] - fp.voxel_min[1]) / (fp.voxel_max[1] - fp.voxel_min[1]),
                (p.z - fp.voxel_center[2] - fp.voxel_min[2]) / (fp.voxel_max[2] - fp.voxel_min[2]));
 }
+// common.glsl:37-42 (voxelizeTesselationWarp): (pv * P).xyz / w * 0.5 + 0.5
+__device__ __forceinline__ V3 tess_warp_position(V3 pos, const vct_frame_params& fp) {
+    const float* m = fp.pv;
+    const float qx = ((m[0] * pos.x + m[4] * pos.y) + m[8] * pos.z) + m[12];
+    const float qy = ((m[1] * pos.x + m[5] * pos.y) + m[9] * pos.z) + m[13];
+    const float qz = ((m[2] * pos.x + m[6] * pos.y) + m[10] * pos.z) + m[14];
+    const float qw = ((m[3] * pos.x + m[7] * pos.y) + m[11] * pos.z) + m[15];
+    return mk3((qx / qw) * 0.5f + 0.5f, (qy / qw) * 0.5f + 0.5f, (qz / qw) * 0.5f + 0.5f);
+}
 __device__ __forceinline__ float voxel_warp_fn1(float x) {
     const float alpha = 0.25f;
     x = alpha * x + (3.0f - 3.0f * alpha) * x * x + (2.0f * alpha - 2.0f) * x * x * x;
@@ -138,11 +147,22 @@ __device__ __forceinline__ V3 warp_sample(const ushort4* __restrict__ wm, V3 tc)
     return lerp3x(lerp3x(c00, c10, fy), lerp3x(c01, c11, fy), fz);
 }
 
-enum { WARP_NONE = 0, WARP_TEXTURE = 1, WARP_VOXELS = 2 };      // common.glsl:44-60 priority: warpVoxels > warpTexture
+// Mapping applied to every cone sample, phong.frag:150-162 (priority INSIDE traceCone: warpTexture > warpVoxels >
+// voxelizeTesselationWarp; common.glsl:44-60, which the voxel view and the other passes use, has warpVoxels first)
+enum { WARP_NONE = 0, WARP_TEXTURE = 1, WARP_VOXELS = 2, WARP_TESS = 3 };
 
 // ---- traceCone, phong.frag:135-180
-struct ConeCtx { cudaTextureObject_t vol, vol_point, vol_last; const ushort4* warp; int D, L; int warp_texture, warp_voxels; V3 eye_tc;
+// (warp map and frame parameters share a slot: WARP_TESS needs pv and the volume extents, never the warp map — the context of
+// the other instantiations keeps its layout)
+struct ConeCtx { cudaTextureObject_t vol, vol_point, vol_last; union { const ushort4* warp; const vct_frame_params* fp; }; int D, L; int warp_texture, warp_voxels; V3 eye_tc;
                  const float4* s_last; float n_last; };
+// phong.frag:158-162 (voxelizeTesselationWarp): the sample goes back to world space and through pv (common.glsl:37-42)
+__device__ __forceinline__ V3 tess_warp_sample(const vct_frame_params& fp, V3 sp) {
+    const V3 world = mk3((sp.x * (fp.voxel_max[0] - fp.voxel_min[0]) + fp.voxel_center[0]) + fp.voxel_min[0],
+                         (sp.y * (fp.voxel_max[1] - fp.voxel_min[1]) + fp.voxel_center[1]) + fp.voxel_min[1],
+                         (sp.z * (fp.voxel_max[2] - fp.voxel_min[2]) + fp.voxel_center[2]) + fp.voxel_min[2]);
+    return tess_warp_position(world, fp);
+}
 
 // ---- last pyramid level from shared memory.  A third of all cone steps have lambda >= L-1 (phong.frag:160: the lod grows
 // with the march) and read only the coarsest level, which is tiny (8^3 texels at 256^3/6 levels).  Every CTA keeps it
@@ -194,6 +214,7 @@ __device__ __noinline__ V4 trace_cone(const ConeCtx& cx, V3 position, V3 normal,
         if (!(sp.x >= 0.0f && sp.x <= 1.0f && sp.y >= 0.0f && sp.y <= 1.0f && sp.z >= 0.0f && sp.z <= 1.0f)) break;   // also NaN
         if (WM == WARP_TEXTURE) sp = warp_sample(cx.warp, sp);
         else if (WM == WARP_VOXELS) sp = voxel_warp(sp, cx.eye_tc);
+        else if (WM == WARP_TESS) sp = tess_warp_sample(*cx.fp, sp);
         const float lambda = lod + lod_offset;
         float4 sc;
         if (!(lambda > 0.5f)) sc = tex3DLod<float4>(cx.vol_point, sp.x, sp.y, sp.z, 0.0f);
@@ -238,6 +259,7 @@ template <int KIND, int WM>
 __device__ __forceinline__ float4 fetch_volume(const ConeCtx& cx, V3 sp, float lambda, float max_lod) {
     if (WM == WARP_TEXTURE) sp = warp_sample(cx.warp, sp);
     else if (WM == WARP_VOXELS) sp = voxel_warp(sp, cx.eye_tc);
+    else if (WM == WARP_TESS) sp = tess_warp_sample(*cx.fp, sp);
     if (KIND == SAMPLE_POINT) return tex3DLod<float4>(cx.vol_point, sp.x, sp.y, sp.z, 0.0f);
     if (KIND == SAMPLE_LAST_SMEM) return sample_last_smem<WM != WARP_NONE>(cx.s_last, cx.n_last, sp);
     if (KIND == SAMPLE_LAST) return tex3DLod<float4>(cx.vol_last, sp.x, sp.y, sp.z, max_lod);
@@ -432,6 +454,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
                 V3 gp = voxel_linear_position(Pw, fp);
                 if (WM == WARP_VOXELS) gp = voxel_warp(gp, voxel_linear_position(mk3(fp.eye[0], fp.eye[1], fp.eye[2]), fp));
                 else if (WM == WARP_TEXTURE) gp = warp_sample(reinterpret_cast<const ushort4*>(a.warp), gp);
+                else if (WM == WARP_TESS) gp = tess_warp_position(Pw, fp);
                 const float Df = (float)fc.D;
                 const V3 vi = mk3(__fdiv_rn(__fmul_rn(Df, gp.x), Df), __fdiv_rn(__fmul_rn(Df, gp.y), Df), __fdiv_rn(__fmul_rn(Df, gp.z), Df));   // voxelIndex(..) / voxelDim
                 const float lambda = fp.miplevel;
@@ -500,7 +523,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
             if (!fp.enable_specular) ssum = mk3(0.f, 0.f, 0.f);
             V3 col;
             if (fp.enable_indirect) {
-                ConeCtx cx; cx.vol = a.vol; cx.vol_point = a.vol_point; cx.vol_last = a.vol_last; cx.warp = a.warp; cx.D = fc.D; cx.L = fc.L;
+                ConeCtx cx; cx.vol = a.vol; cx.vol_point = a.vol_point; cx.vol_last = a.vol_last; if (WM == WARP_TESS) cx.fp = &fp; else cx.warp = a.warp; cx.D = fc.D; cx.L = fc.L;
                 cx.warp_texture = fp.warp_texture; cx.warp_voxels = fp.warp_voxels; cx.eye_tc = voxel_linear_position(eye, fp);
                 cx.s_last = s_last; cx.n_last = (float)a.n_last;
                 const V3 vp = voxel_linear_position(Pw, fp);
@@ -623,15 +646,22 @@ int vctk_cone_trace(vct_ctx* c) {
         else k_cone_trace<WM, SLV, kThreads><<<grid, kThreads, 0, c->stream>>>(a);                             \
     } while (0)
 #define VCT_TRACE(WM) do { if (sl) VCT_TRACE2(WM, true); else VCT_TRACE2(WM, false); } while (0)
+    // Which mapping the kernel applies.  traceCone tests warpTexture first (phong.frag:150-162), common.glsl's getVoxelPosition —
+    // all the voxel view uses (:348) — tests warpVoxels first (common.glsl:44-60); the two differ only when both are switched on.
+    const bool voxel_view = p.debug_view == VCT_VIEW_VOXELS;
+    const int wm = voxel_view ? (p.warp_voxels ? WARP_VOXELS : p.warp_texture ? WARP_TEXTURE : p.voxelize_tesselation_warp ? WARP_TESS : WARP_NONE)
+                              : (p.warp_texture ? WARP_TEXTURE : p.warp_voxels ? WARP_VOXELS : p.voxelize_tesselation_warp ? WARP_TESS : WARP_NONE);
     if (p.debug_view != VCT_VIEW_SHADED) {                      // debug views: own instantiation, default CTA size, no shared-memory last level
         if (p.debug_view < 0 || p.debug_view > VCT_VIEW_REFLECTIONS) { c->error = "vct_cone_trace: unknown debug_view"; return 1; }
         dim3 dgrid((c->W + kThreads / 4 - 1) / (kThreads / 4), (a.y_hi - a.y_lo + 3) / 4);
-        if (p.warp_voxels) k_cone_trace<WARP_VOXELS, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
-        else if (p.warp_texture) k_cone_trace<WARP_TEXTURE, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
+        if (wm == WARP_VOXELS) k_cone_trace<WARP_VOXELS, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
+        else if (wm == WARP_TEXTURE) k_cone_trace<WARP_TEXTURE, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
+        else if (wm == WARP_TESS) k_cone_trace<WARP_TESS, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
         else k_cone_trace<WARP_NONE, false, kThreads, true><<<dgrid, kThreads, 0, c->stream>>>(a);
     }
-    else if (p.warp_voxels) VCT_TRACE(WARP_VOXELS);
-    else if (p.warp_texture) VCT_TRACE(WARP_TEXTURE);
+    else if (wm == WARP_VOXELS) VCT_TRACE(WARP_VOXELS);
+    else if (wm == WARP_TEXTURE) VCT_TRACE(WARP_TEXTURE);
+    else if (wm == WARP_TESS) k_cone_trace<WARP_TESS, false, kThreads><<<dim3((c->W + kThreads / 4 - 1) / (kThreads / 4), (a.y_hi - a.y_lo + 3) / 4), kThreads, 0, c->stream>>>(a);   // default CTA size only
     else VCT_TRACE(WARP_NONE);
 #undef VCT_TRACE
 #undef VCT_TRACE2

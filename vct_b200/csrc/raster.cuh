@@ -344,9 +344,20 @@ __device__ __forceinline__ V3 voxel_warp(V3 p, V3 c) {
     return c + o;
 }
 __device__ __forceinline__ V3 eye_of(const vct_frame_params& fp) { return mk3(fp.eye[0], fp.eye[1], fp.eye[2]); }
+// common.glsl:37-42 (voxelizeTesselationWarp): the camera frustum as voxel grid, (pv * P).xyz / w * 0.5 + 0.5
+__device__ __forceinline__ V3 tess_warp_position(V3 pos, const vct_frame_params& fp) {
+    const float* m = fp.pv;
+    const float qx = ((m[0] * pos.x + m[4] * pos.y) + m[8] * pos.z) + m[12];
+    const float qy = ((m[1] * pos.x + m[5] * pos.y) + m[9] * pos.z) + m[13];
+    const float qz = ((m[2] * pos.x + m[6] * pos.y) + m[10] * pos.z) + m[14];
+    const float qw = ((m[3] * pos.x + m[7] * pos.y) + m[11] * pos.z) + m[15];
+    return mk3((qx / qw) * 0.5f + 0.5f, (qy / qw) * 0.5f + 0.5f, (qz / qw) * 0.5f + 0.5f);
+}
+// common.glsl:44-60, priority warpVoxels > warpTexture > voxelizeTesselationWarp > linear
 __device__ __forceinline__ V3 get_voxel_position(V3 pos, const vct_frame_params& fp, const uint16_t* __restrict__ warpmap) {
     if (fp.warp_voxels) return voxel_warp(voxel_linear_position(pos, fp), voxel_linear_position(eye_of(fp), fp));
     if (fp.warp_texture) return warp_sample(warpmap, voxel_linear_position(pos, fp));
+    if (fp.voxelize_tesselation_warp) return tess_warp_position(pos, fp);
     return voxel_linear_position(pos, fp);
 }
 // ivec3(vec3) truncation + image bounds (out-of-bounds image access is a no-op)

@@ -787,7 +787,7 @@ int vctk_transfer_masked(vct_ctx* c) {
 int vctk_inject(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
     const bool pow2 = (c->S & (c->S - 1)) == 0 && c->S >= 32;
-    if (pow2 && !p.warp_voxels && !p.warp_texture && !p.radiance_lighting && c->D <= 1024) {
+    if (pow2 && !p.warp_voxels && !p.warp_texture && !p.voxelize_tesselation_warp && !p.radiance_lighting && c->D <= 1024) {
         InjectLinear lin; bool sane = true;
         for (int i = 0; i < 3; ++i) {
             volatile float ext = p.voxel_max[i] - p.voxel_min[i];           // one fp32 rounding, like the shader's (max - min)

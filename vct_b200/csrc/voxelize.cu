@@ -459,7 +459,9 @@ __device__ __forceinline__ void tess_eval(const VoxArgs& a, const FrameConst& fc
     const float tu = (u * P.uv[0][0] + v * P.uv[1][0]) + ww * P.uv[2][0], tv = (u * P.uv[0][1] + v * P.uv[1][1]) + ww * P.uv[2][1];
     V4 col = mk4(0.f, 0.f, 0.f, 1.f);
     if (P.dt >= 0) col = sample2d(a.tex[P.dt], tu, tv, 0.0f);
-    const V3 vp = voxel_linear_position(pos, fc.p);
+    // tese:134 voxelIndex(position, ..., false): warpVoxels is passed as false and the host never sets this program's warpTexture
+    // (Application.cpp:630-640), so only the tessellation warp or the linear mapping can apply
+    const V3 vp = fc.p.voxelize_tesselation_warp ? tess_warp_position(pos, fc.p) : voxel_linear_position(pos, fc.p);
     const float Df = (float)a.D;
     int ix, iy, iz;
     if (!to_voxel_index(mk3(Df * vp.x, Df * vp.y, Df * vp.z), a.D, ix, iy, iz)) return;

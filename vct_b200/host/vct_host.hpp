@@ -100,6 +100,7 @@ struct Settings {
     int debugMaterialDiffuse = false, debugMaterialRoughness = false, debugMaterialMetallic = false;
     float miplevel = 0.0f;
     int voxelizeTesselation = false;    // Application.h:85 (reference default true; this host defaults to the north star's raster path)
+    int voxelizeTesselationWarp = false;   // Application.h:102: the camera frustum as voxel grid (common.glsl:37-42)
     int cooktorrance = true, enablePostprocess = true, enableNormalMap = true;
     int enableIndirect = true, enableDiffuse = true, enableSpecular = true, enableReflections = true;
     float ambientScale = 1.0f, reflectScale = 1.0f;
@@ -314,6 +315,7 @@ public:
                      : s.debugIndirect ? VCT_VIEW_INDIRECT : s.debugOcclusion ? VCT_VIEW_OCCLUSION : s.debugReflections ? VCT_VIEW_REFLECTIONS : VCT_VIEW_SHADED;
         p.miplevel = s.miplevel;
         p.voxelize_tesselation = s.voxelizeTesselation;
+        p.voxelize_tesselation_warp = s.voxelizeTesselationWarp;
         return p;
     }
 

@@ -78,7 +78,7 @@ class FrameParams(C.Structure):
         ("enable_reflections", C.c_int), ("ambient_scale", C.c_float), ("reflect_scale", C.c_float),
         ("diffuse_cone", ConeSettings), ("specular_cone", ConeSettings),
         ("specular_cone_angle_from_roughness", C.c_int),
-        ("debug_view", C.c_int), ("miplevel", C.c_float), ("voxelize_tesselation", C.c_int),
+        ("debug_view", C.c_int), ("miplevel", C.c_float), ("voxelize_tesselation", C.c_int), ("voxelize_tesselation_warp", C.c_int),
     ]
 
 
