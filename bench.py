@@ -198,7 +198,8 @@ def run_reference(args):
                 "note": "CPU oracle (C++/OpenMP restatement, bit-identical results), same sample, single run"}
     line = {"impl": "reference", "metric": METRIC, "value": round(ms, 3), "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": data,
-            "config": {"workload": "config 3: PBR Sponza, 256^3 voxels, 6 levels, 1920x1080, 4096^2 shadow map, diffuse+specular cones", "dim": D, "width": W, "height": H},
+            "config": {"workload": "config 3: PBR Sponza, 256^3 voxels, 6 levels, 1920x1080, 4096^2 shadow map, diffuse+specular cones, full per-frame revoxelisation",
+                       "dim": D, "levels": LEVELS, "width": W, "height": H, "shadow": SHADOW, "triangles": sc.n_tris, "mip_chains": 2 if p.mip_color_chain else 1},
             "cpu_baseline": {"value": round(ms, 3), "unit": "ms", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(ms, 3), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "passes_ms": passes, "cpu_port": port, "gpu_launches": 0,
