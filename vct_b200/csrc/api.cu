@@ -203,6 +203,11 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
         VCT_CHECK(c, cudaEventRecord(c->stage_ev[slot], c->stream));
     }
     if (c->tables_dirty) {                      // texture / material tables change only on upload
+        for (int i = 0; i < c->n_materials; ++i) {
+            const DevMaterial& m = c->h_mat[i];
+            for (int t : {m.diffuse_tex, m.specular_tex, m.normal_tex, m.roughness_tex, m.metallic_tex, m.alpha_tex})
+                if (t >= 0 && !c->h_tex[t].level[0]) return fail(c, "a material names a texture that was never uploaded (vct_upload_texture before the first pass)");
+        }
         VCT_CHECK(c, cudaMemcpyAsync(c->d_tex, c->h_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES, cudaMemcpyHostToDevice, c->stream));
         VCT_CHECK(c, cudaMemcpyAsync(c->d_mat, c->h_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS, cudaMemcpyHostToDevice, c->stream));
         c->tables_dirty = false;
@@ -358,7 +363,11 @@ int vct_upload_mesh(vct_ctx* c, int actor, const void* vertices, size_t n_vertic
     if (!c) return 1;
     if (stride < 56 || !vertices || !indices || n_indices % 3 || actor < 0) return fail(c, "vct_upload_mesh: bad arguments (Vertex stride is 56 bytes, src/Graphics/Mesh.h:72-76)");
     for (auto& m : c->meshes) if (m.actor == actor) return fail(c, "vct_upload_mesh: actor already has a mesh");
+    if (actor >= 65536) return fail(c, "vct_upload_mesh: actor ids are 0..65535");
     for (size_t i = 0; i < n_indices; ++i) if (indices[i] >= n_vertices) return fail(c, "vct_upload_mesh: index out of range");
+    if (material_of_triangle)
+        for (size_t t = 0; t < n_indices / 3; ++t)
+            if (material_of_triangle[t] < 0 || material_of_triangle[t] >= VCT_MAX_MATERIALS) return fail(c, "vct_upload_mesh: material id out of range");
     HostMesh m{}; m.actor = actor; m.n_vertices = n_vertices; m.n_tris = n_indices / 3; m.vbase = c->h_vertices.size() / 14; m.tbase = c->h_trimat.size();
     for (int i = 0; i < 16; ++i) m.model.m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
     const size_t v0 = c->h_vertices.size();
@@ -380,7 +389,7 @@ int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels,
     for (int l = 0; l < levels; ++l) total += (size_t)std::max(1, width >> l) * std::max(1, height >> l) * channels;
     uint8_t* d = nullptr;
     VCT_CHECK(c, cudaMalloc(&d, total + 16));
-    VCT_CHECK(c, cudaMemcpy(d, pixels, total, cudaMemcpyHostToDevice));
+    if (cudaError_t r = cudaMemcpy(d, pixels, total, cudaMemcpyHostToDevice); r != cudaSuccess) { cudaFree(d); return fail(c, cudaGetErrorString(r)); }
     c->tex_allocs.push_back(d);
     DevTexture& t = c->h_tex[tex]; t.w = width; t.h = height; t.ch = channels; t.levels = levels;
     size_t off = 0;
@@ -393,6 +402,8 @@ int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels,
 int vct_set_material(vct_ctx* c, int material, const vct_material* m) {
     if (!c) return 1;
     if (material < 0 || material >= VCT_MAX_MATERIALS || !m) return fail(c, "vct_set_material: bad arguments");
+    for (int t : {m->diffuse_tex, m->specular_tex, m->normal_tex, m->roughness_tex, m->metallic_tex, m->alpha_tex})
+        if (t < -1 || t >= VCT_MAX_TEXTURES) return fail(c, "vct_set_material: texture id out of range (-1 = none)");
     DevMaterial& d = c->h_mat[material];
     d.diffuse_tex = m->diffuse_tex; d.specular_tex = m->specular_tex; d.normal_tex = m->normal_tex; d.roughness_tex = m->roughness_tex; d.metallic_tex = m->metallic_tex; d.alpha_tex = m->alpha_tex;
     d.shininess = m->shininess; std::memcpy(d.diffuse, m->diffuse, 12);
@@ -403,6 +414,7 @@ int vct_set_material(vct_ctx* c, int material, const vct_material* m) {
 
 int vct_set_actor_transform(vct_ctx* c, int actor, const float model[16]) {
     if (!c) return 1;
+    if (!model) return fail(c, "vct_set_actor_transform: null matrix");
     for (auto& m : c->meshes) if (m.actor == actor) { std::memcpy(m.model.m, model, 64); return 0; }
     return fail(c, "vct_set_actor_transform: unknown actor");
 }
