@@ -83,3 +83,76 @@ def test_headless_frame_equals_python_mirror(tmp_path, fused):
     assert psnr >= 45.0, psnr
     if fused:
         assert rep["timers_ms"]["total"] > 0
+
+
+FRAME_PARAMS_MAIN = r"""
+#include <cstdio>
+#include "vct_host.hpp"
+using namespace vct_host;
+int main(int argc, char** argv) {
+    Scene sc; sc.addReferenceLights();
+    Application app; app.scene = &sc; app.width = 640; app.height = 360;
+    app.camera.position = {2.5f, 1.5f, -3.0f}; app.camera.hasFront = true; app.camera.frontOverride = {-2.0f, -1.0f, 2.5f};
+    app.vct.min = {-3.f, -3.f, -3.f}; app.vct.max = {3.f, 3.f, 3.f}; app.vct.center = {0.5f, 1.0f, -0.25f};
+    if (argc > 1) {   // every Settings member that reaches the kernels, moved off its default
+        Settings& s = app.settings;
+        s.voxelizeLighting = 0; s.voxelizeAtomicMax = 1; s.axisOverride = 2; s.voxelSetOpacity = 0.25f; s.temporalFilterRadiance = 1; s.temporalDecay = 0.6f;
+        s.radianceLighting = 1; s.voxelFillHoles = 1; s.warpVoxels = 1; s.warpTexture = 1; s.warpTextureLinear = 1; s.warpTextureAxes[1] = 0;
+        s.useWarpmapWeightsTexture = 0; s.warpTextureHighResolution = 3.0f; s.warpTextureLowResolution = 0.25f;
+        s.drawRadiance = 0; s.drawOcclusion = 0; s.cooktorrance = 0; s.enablePostprocess = 0; s.enableNormalMap = 0;
+        s.enableIndirect = 0; s.enableDiffuse = 0; s.enableSpecular = 0; s.enableReflections = 0; s.ambientScale = 0.5f; s.reflectScale = 2.0f;
+        s.diffuseConeSettings.steps = 9; s.specularConeSettings.bias = 2.5f; s.specularConeAngleFromRoughness = 0;
+        s.debugOcclusion = 1; s.drawNormals = 1;          // the shader tests drawNormals first
+        s.miplevel = 1.5f; s.voxelizeTesselation = 1; s.voxelizeTesselationWarp = 1;
+    }
+    const vct_frame_params p = app.frameParams();
+    std::fwrite(&p, sizeof p, 1, stdout);
+    return 0;
+}
+"""
+
+
+def test_cpp_host_frame_parameters_equal_the_python_mirror(tmp_path):
+    """vct_host.hpp::Application::frameParams (the C++ mirror of the uniforms Application::render sets) against
+    vct_b200.params.default_params (the Python mirror the parity tests use): same integers, same scalars, matrices equal to a few
+    ulp of their largest entry (the two hosts use different float libraries).  Runs without a GPU: no context is created."""
+    import ctypes as C
+    from vct_b200 import params as P
+    src = tmp_path / "fp.cpp"; exe = tmp_path / "fp"
+    src.write_text(FRAME_PARAMS_MAIN)
+    lib = os.path.join(ROOT, "vct_b200", "lib")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", f"-I{ROOT}/vct_b200/host", f"-I{ROOT}/include", str(src), "-o", str(exe),
+                           f"-L{lib}", "-lvct_b200", f"-Wl,-rpath,{lib}"])
+    cam = P.Camera(position=(2.5, 1.5, -3.0), front=(-2.0, -1.0, 2.5))
+    light = P.reference_lights()[0]
+    for changed in (False, True):
+        raw = subprocess.run([str(exe)] + (["x"] if changed else []), capture_output=True, check=True).stdout
+        assert len(raw) == C.sizeof(P.FrameParams)
+        got = P.FrameParams.from_buffer_copy(raw)
+        want = P.default_params(640, 360, cam, light, voxel_min=-3.0, voxel_max=3.0, voxel_center=(0.5, 1.0, -0.25))
+        if changed:
+            for k, v in dict(voxelize_lighting=0, voxelize_atomic_max=1, axis_override=2, voxel_set_opacity=0.25, temporal_filter_radiance=1, temporal_decay=0.6,
+                             radiance_lighting=1, voxel_fill_holes=1, warp_voxels=1, warp_texture=1, warp_texture_linear=1, use_warpmap_weights_texture=0,
+                             warp_texture_high_resolution=3.0, warp_texture_low_resolution=0.25, draw_radiance=0, draw_occlusion=0, cooktorrance=0,
+                             enable_postprocess=0, enable_normal_map=0, enable_indirect=0, enable_diffuse=0, enable_specular=0, enable_reflections=0,
+                             ambient_scale=0.5, reflect_scale=2.0, specular_cone_angle_from_roughness=0, debug_view=P.VIEW_NORMALS, miplevel=1.5,
+                             voxelize_tesselation=1, voxelize_tesselation_warp=1).items():
+                setattr(want, k, v)
+            want.warp_texture_axes[1] = 0; want.diffuse_cone.steps = 9; want.specular_cone.bias = 2.5
+        seen = 0
+        for name, ctype in P.FrameParams._fields_:
+            a, b = getattr(got, name), getattr(want, name)
+            if isinstance(a, C.Array) and a._type_ is C.c_float:
+                x, y = np.array(a[:], np.float32), np.array(b[:], np.float32)
+                assert np.all(np.abs(x - y) <= 8 * np.finfo(np.float32).eps * max(1.0, float(np.abs(y).max()))), (name, x, y)
+            elif isinstance(a, C.Array):
+                assert a[:] == b[:], (name, a[:], b[:])
+            elif isinstance(a, C.Structure):
+                for f, _ in a._fields_:
+                    assert getattr(a, f) == pytest.approx(getattr(b, f), rel=1e-6), (name, f)
+            elif ctype is C.c_float:
+                assert a == pytest.approx(b, rel=1e-6), (name, a, b)
+            else:
+                assert a == b, (name, a, b)
+            seen += 1
+        assert seen == len(P.FrameParams._fields_)
