@@ -342,6 +342,10 @@ int vct_destroy(vct_ctx* c) {
     if (c->ev_image_ready) cudaEventDestroy(c->ev_image_ready);
     if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_setup_done) cudaEventDestroy(c->ev_setup_done);
+    cudaFree(c->d_trace_rec);
     for (auto& ev : c->prof_pool) cudaEventDestroy(ev);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -517,6 +521,7 @@ int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
     // sparse frame: vertex transform and masked clear share one launch (kept apart under per-kernel profiling)
     const bool fused_begin = plan_frame(c).sparse && c->profiling < 2 && c->n_vertices > 0;
     if (fused_begin ? vctk_frame_begin_masked(c) : vctk_transform_vertices(c)) return 1;
+    if (vctk_trace_setup_async(c)) return 1;                  // VCT_TRACE_VARIANT bits 6+7 (prototype): shading set-up on a side stream, under the voxel passes
     if (gi_body(c, g, fused_begin)) return 1;
     if (c->cfg.world_size > 1) return 0;                      // caller all-gathers, then vct_exchange + vct_cone_trace
     if (g.rec(EV_GBUF)) return 1;

@@ -579,6 +579,197 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) k_cone_trace(TraceArgs a) {
     if (lane == 0 && fetches) atomicAdd(&a.counters->cone_steps, (unsigned long long)fetches);
 }
 
+
+// ============================================================ split variant (VCT_TRACE_VARIANT bit 6) — PROTOTYPE, not yet run on a GPU
+// nothing in a pixel's shading set-up (visibility decode, attribute interpolation, normal map, direct light + PCF)
+// depends on the voxel pyramid, so it can run under the voxel passes of the same frame on a second stream (bit 7), and the march kernel
+// that follows the mip chain carries the cones only.  k_trace_setup writes 8 float4 planes per pixel of the band (SoA):
+//   0: voxelLinearPosition(P).xyz, specular cone angle (< 0: the frame's schedule)   1: N.xyz, ssum.x   2: T.xyz, ssum.y   3: B.xyz, ssum.z
+//   4: fragNormal.xyz, valid (0: the pixel is finished — background, or no indirect light)   5: reflect(P - eye, N).xyz   6: albedo.xyz   7: dsum.xyz
+// Same arithmetic, in the same order, as k_cone_trace above: the two paths must produce identical images (tools/trace_variants.py).
+constexpr int kSplitPlanes = 8;
+struct SplitRec { float4* plane[kSplitPlanes]; };
+__device__ __forceinline__ float4 f4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+__device__ __forceinline__ uint32_t finish_pixel(const vct_frame_params& fp, V3 col) {
+    if (fp.enable_postprocess) {
+        col = mk3(col.x / (col.x + 1.0f), col.y / (col.y + 1.0f), col.z / (col.z + 1.0f));
+        const float g = 1.0f / 2.2f;
+        col = mk3(powf(col.x, g), powf(col.y, g), powf(col.z, g));
+    }
+    return pack_unorm(mk4(col.x, col.y, col.z, 1.0f));
+}
+__global__ void __launch_bounds__(kThreads) k_trace_setup(TraceArgs a, SplitRec rec) {
+    const FrameConst& fc = *a.fc;
+    const vct_frame_params& fp = fc.p;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int px = blockIdx.x * (kThreads / 4) + w * 8 + (lane & 7);
+    const int py = a.y_lo + blockIdx.y * 4 + (lane >> 3);
+    if (!(px < a.W && py < a.y_hi)) return;
+    const size_t o = (size_t)py * a.W + px, ob = (size_t)(py - a.y_lo) * a.W + px;
+    const unsigned long long key = a.vis[o];
+    if (key == ~0ull) {
+        a.image[o] = pack_unorm(mk4(fp.clear_color[0], fp.clear_color[1], fp.clear_color[2], 1.0f));
+        rec.plane[4][ob] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const uint32_t t = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+    const uint32_t i0 = __ldg(a.indices + 3 * (size_t)t), i1 = __ldg(a.indices + 3 * (size_t)t + 1), i2 = __ldg(a.indices + 3 * (size_t)t + 2);
+    const V3 w0 = f4to3(__ldg(a.wpos + i0)), w1 = f4to3(__ldg(a.wpos + i1)), w2 = f4to3(__ldg(a.wpos + i2));
+    float l[3], lx[3], ly[3];
+    {
+        V4 c[3];
+        c[0] = mul44(fc.projection, mul44(fc.view, mk4(w0.x, w0.y, w0.z, 1.0f)));
+        c[1] = mul44(fc.projection, mul44(fc.view, mk4(w1.x, w1.y, w1.z, 1.0f)));
+        c[2] = mul44(fc.projection, mul44(fc.view, mk4(w2.x, w2.y, w2.z, 1.0f)));
+        float ha[3], hb[3], hc[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const V4 p = c[(i + 1) % 3], q = c[(i + 2) % 3];
+            ha[i] = __fmul_rn(p.y, q.w) - __fmul_rn(q.y, p.w); hb[i] = __fmul_rn(q.x, p.w) - __fmul_rn(p.x, q.w); hc[i] = __fmul_rn(p.x, q.y) - __fmul_rn(q.x, p.y);
+        }
+        const float nx = ((float)px + 0.5f) / (float)a.W * 2.0f - 1.0f, ny = ((float)py + 0.5f) / (float)a.H * 2.0f - 1.0f;
+        auto ev = [&](float x, float y, float out[3]) {
+            const float b0 = ha[0] * x + hb[0] * y + hc[0], b1 = ha[1] * x + hb[1] * y + hc[1], b2 = ha[2] * x + hb[2] * y + hc[2];
+            const float s = b0 + b1 + b2; out[0] = b0 / s; out[1] = b1 / s; out[2] = b2 / s;
+        };
+        ev(nx, ny, l); ev(nx + 2.0f / (float)a.W, ny, lx); ev(nx, ny + 2.0f / (float)a.H, ly);
+    }
+    const float* v0 = a.verts + 14 * (size_t)i0; const float* v1 = a.verts + 14 * (size_t)i1; const float* v2 = a.verts + 14 * (size_t)i2;
+    const float u0 = __ldg(v0 + 6), t0 = __ldg(v0 + 7), u1 = __ldg(v1 + 6), t1 = __ldg(v1 + 7), u2 = __ldg(v2 + 6), t2 = __ldg(v2 + 7);
+    const float u = ip(l, u0, u1, u2), v = ip(l, t0, t1, t2);
+    const float ux = ip(lx, u0, u1, u2) - u, vx = ip(lx, t0, t1, t2) - v, uy = ip(ly, u0, u1, u2) - u, vy = ip(ly, t0, t1, t2) - v;
+    auto fetch = [&](int ti) {
+        const DevTexture& T = a.tex[ti];
+        const float ax = ux * (float)T.w, bx = vx * (float)T.h, ay = uy * (float)T.w, by = vy * (float)T.h;
+        return sample2d(T, u, v, fmaxf(ax * ax + bx * bx, ay * ay + by * by));
+    };
+    const DevMaterial mat = a.mats[__ldg(a.trimat + t)];
+    const V3 Pw = ip3(l, w0, w1, w2);
+    const V3 fn = ip3(l, f4to3(__ldg(a.wnrm + i0)), f4to3(__ldg(a.wnrm + i1)), f4to3(__ldg(a.wnrm + i2)));
+    const V3 Tt = ip3(l, f4to3(__ldg(a.wT + i0)), f4to3(__ldg(a.wT + i1)), f4to3(__ldg(a.wT + i2)));
+    const V3 Bt = ip3(l, f4to3(__ldg(a.wB + i0)), f4to3(__ldg(a.wB + i1)), f4to3(__ldg(a.wB + i2)));
+    const V4 lf0 = mul44(fc.ls, mk4(w0.x, w0.y, w0.z, 1.0f)), lf1 = mul44(fc.ls, mk4(w1.x, w1.y, w1.z, 1.0f)), lf2 = mul44(fc.ls, mk4(w2.x, w2.y, w2.z, 1.0f));
+    const V4 lsp = mk4(ip(l, lf0.x, lf1.x, lf2.x), ip(l, lf0.y, lf1.y, lf2.y), ip(l, lf0.z, lf1.z, lf2.z), ip(l, lf0.w, lf1.w, lf2.w));
+    auto tbn = [&](V3 d) { return (Tt * d.x + Bt * d.y) + fn * d.z; };
+    V3 N;
+    if (fp.enable_normal_map && mat.normal_tex >= 0) {
+        const V4 nm = fetch(mat.normal_tex);
+        N = normalize3(tbn(normalize3(mk3(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f))));
+    } else N = normalize3(fn);
+    const V4 dc4 = mat.diffuse_tex >= 0 ? fetch(mat.diffuse_tex) : mk4(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2], 1.0f);
+    const V3 dc = mk3(dc4.x, dc4.y, dc4.z);
+    const V3 eye = mk3(fp.eye[0], fp.eye[1], fp.eye[2]);
+    const V3 Vv = normalize3(eye - Pw);
+    float rough = 0.5f; if (mat.roughness_tex >= 0) rough = fetch(mat.roughness_tex).x;
+    float metal = 0.0f; if (mat.metallic_tex >= 0) metal = fetch(mat.metallic_tex).x;
+    V3 dsum = mk3(0.f, 0.f, 0.f), ssum = mk3(0.f, 0.f, 0.f);
+    for (int i = 0; i < fc.n_lights; ++i) {
+        const vct_light& Lt = fc.lights[i];
+        if (!Lt.enabled) continue;
+        const V3 lc = mk3(Lt.color[0], Lt.color[1], Lt.color[2]), lpos = mk3(Lt.position[0], Lt.position[1], Lt.position[2]);
+        LR r; r.diffuse = mk3(0.f, 0.f, 0.f); r.specular = mk3(0.f, 0.f, 0.f);
+        if (Lt.type == 0u) {
+            const float dist = length3(lpos - Pw);
+            if (!(dist > Lt.range)) {
+                const float e0 = 0.75f * Lt.range, tt = clampf((dist - e0) / (Lt.range - e0), 0.0f, 1.0f);
+                const float att = 1.0f - tt * tt * (3.0f - 2.0f * tt);
+                const V3 Ld = normalize3(lpos - Pw);
+                if (fp.cooktorrance) { r = cook_torrance(dc, lc, N, Vv, Ld, normalize3(Vv + Ld), rough, metal); r.diffuse = r.diffuse * att; r.specular = r.specular * att; }
+                else {
+                    const float df = fmaxf(dot3(N, Ld), 0.0f), sp = powf(fmaxf(dot3(N, normalize3(Vv + Ld)), 0.0f), mat.shininess);
+                    r.diffuse = ((lc * (df * att)) * Lt.intensity) * dc; r.specular = ((lc * (sp * att)) * Lt.intensity) * dc;
+                }
+            }
+        } else if (Lt.type == 1u) {
+            const V3 Ld = normalize3(mk3(-Lt.direction[0], -Lt.direction[1], -Lt.direction[2]));
+            if (fp.cooktorrance) r = cook_torrance(dc, lc, N, Vv, Ld, normalize3(Vv + Ld), rough, metal);
+            else {
+                const float df = fmaxf(dot3(N, Ld), 0.0f), sp = powf(fmaxf(dot3(N, normalize3(Vv + Ld)), 0.0f), mat.shininess);
+                r.diffuse = ((lc * df) * Lt.intensity) * dc; r.specular = ((lc * sp) * Lt.intensity) * dc;
+            }
+        }
+        if (Lt.shadow_caster) { const float sf = 1.0f - calc_shadow_factor(a.shadow, fc.S, lsp); r.diffuse = r.diffuse * sf; r.specular = r.specular * sf; }
+        dsum = dsum + r.diffuse; ssum = ssum + r.specular;
+    }
+    if (!fp.enable_diffuse) dsum = mk3(0.f, 0.f, 0.f);
+    if (!fp.enable_specular) ssum = mk3(0.f, 0.f, 0.f);
+    if (!fp.enable_indirect) {                                   // nothing left for the march kernel
+        a.image[o] = finish_pixel(fp, (dc * fp.ambient_scale + dsum) + ssum);
+        rec.plane[4][ob] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const V3 I = Pw - eye;
+    const V3 R = I - N * (2.0f * dot3(N, I));
+    const float ang = (fp.specular_cone_angle_from_roughness && mat.roughness_tex >= 0) ? rough * kPI * 0.1f : -1.0f;
+    rec.plane[0][ob] = f4(voxel_linear_position(Pw, fp), ang);
+    rec.plane[1][ob] = f4(N, ssum.x); rec.plane[2][ob] = f4(Tt, ssum.y); rec.plane[3][ob] = f4(Bt, ssum.z);
+    rec.plane[4][ob] = f4(fn, 1.0f); rec.plane[5][ob] = f4(R, 0.0f); rec.plane[6][ob] = f4(dc, 0.0f); rec.plane[7][ob] = f4(dsum, 0.0f);
+}
+// MINB: resident CTAs per SM the register allocation aims at (4: 128 registers like k_cone_trace; 5: 96 registers, no spills; 6: 80
+// registers, 92 bytes of spills — ptxas -v); selected by VCT_TRACE_VARIANT bits 8-9 for the no-warp instantiation, to be measured.
+template <int WM, int MINB = 512 / kThreads>
+__global__ void __launch_bounds__(kThreads, MINB) k_trace_march(TraceArgs a, SplitRec rec) {
+    const FrameConst& fc = *a.fc;
+    const vct_frame_params& fp = fc.p;
+    __shared__ Schedule s_diffuse, s_specular;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&fc.sched_diffuse);          // the two tables are adjacent
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_diffuse);
+        for (int i = threadIdx.x; i < (int)(sizeof(Schedule) / 4); i += kThreads) { dst[i] = __ldg(src + i); reinterpret_cast<uint32_t*>(&s_specular)[i] = __ldg(src + sizeof(Schedule) / 4 + i); }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int px = blockIdx.x * (kThreads / 4) + w * 8 + (lane & 7);
+    const int py = a.y_lo + blockIdx.y * 4 + (lane >> 3);
+    unsigned fetches = 0;
+    if (px < a.W && py < a.y_hi) {
+        const size_t o = (size_t)py * a.W + px, ob = (size_t)(py - a.y_lo) * a.W + px;
+        const float4 r4 = __ldcs(rec.plane[4] + ob);
+        if (r4.w != 0.0f) {
+            const float4 r0 = __ldcs(rec.plane[0] + ob), r1 = __ldcs(rec.plane[1] + ob), r2 = __ldcs(rec.plane[2] + ob), r3 = __ldcs(rec.plane[3] + ob);
+            const float4 r5 = __ldcs(rec.plane[5] + ob), r6 = __ldcs(rec.plane[6] + ob), r7 = __ldcs(rec.plane[7] + ob);
+            const V3 vp = mk3(r0.x, r0.y, r0.z), N = mk3(r1.x, r1.y, r1.z), Tt = mk3(r2.x, r2.y, r2.z), Bt = mk3(r3.x, r3.y, r3.z), fn = mk3(r4.x, r4.y, r4.z);
+            const V3 R = mk3(r5.x, r5.y, r5.z), dc = mk3(r6.x, r6.y, r6.z), dsum = mk3(r7.x, r7.y, r7.z), ssum = mk3(r1.w, r2.w, r3.w);
+            auto tbn = [&](V3 d) { return (Tt * d.x + Bt * d.y) + fn * d.z; };
+            const V3 eye = mk3(fp.eye[0], fp.eye[1], fp.eye[2]);
+            ConeCtx cx; cx.vol = a.vol; cx.vol_point = a.vol_point; cx.vol_last = a.vol_last; if (WM == WARP_TESS) cx.fp = &fp; else cx.warp = a.warp; cx.D = fc.D; cx.L = fc.L;
+            cx.warp_texture = fp.warp_texture; cx.warp_voxels = fp.warp_voxels; cx.eye_tc = voxel_linear_position(eye, fp);
+            cx.s_last = nullptr; cx.n_last = (float)a.n_last;
+            const float scale = 1.0f / (float)fc.D;
+            const float dirs[6][3] = {{0.f, 1.f, 0.f}, {0.f, 0.5f, 0.866025f}, {0.823639f, 0.5f, 0.267617f}, {0.509037f, 0.5f, -0.700629f},
+                                      {-0.5909037f, 0.5f, -0.700629f}, {-0.823639f, 0.5f, 0.267617f}};
+            const float wts[6] = {0.25f, 0.15f, 0.15f, 0.15f, 0.15f, 0.15f};
+            V4 ind = mk4(0.f, 0.f, 0.f, 0.f);
+            {
+                ConeSet<6> cs;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) cs.ds[i] = normalize3(normalize3(tbn(mk3(dirs[i][0], dirs[i][1], dirs[i][2])))) * scale;
+                const V3 start = vp + (N * fp.diffuse_cone.bias) * scale;
+                trace_cones<6, WM, false>(cx, s_diffuse, start, cs, fetches);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) ind = mk4(ind.x + wts[i] * cs.acc[i].x, ind.y + wts[i] * cs.acc[i].y, ind.z + wts[i] * cs.acc[i].z, ind.w + wts[i] * cs.acc[i].w);
+            }
+            const float occl = 1.0f - clampf(ind.w, 0.0f, 1.0f);
+            if (fp.enable_reflections) {
+                V4 rc;
+                if (r0.w >= 0.0f) rc = trace_cone<WM>(cx, vp, N, R, fp.specular_cone.steps, fp.specular_cone.bias, r0.w, fp.specular_cone.cone_initial_height, fp.specular_cone.lod_offset, fetches);
+                else {
+                    const V3 start = vp + (N * fp.specular_cone.bias) * scale;
+                    rc = trace_cone_ahead<4, WM, false>(cx, s_specular, start, normalize3(R) * scale, fetches);
+                }
+                ind.x += rc.x * fp.reflect_scale; ind.y += rc.y * fp.reflect_scale; ind.z += rc.z * fp.reflect_scale;
+            }
+            const V3 indc = mk3(ind.x, ind.y, ind.z) * (dc * fp.ambient_scale);
+            V3 col = (indc + dsum) + ssum;
+            if (fp.draw_occlusion) col = col * occl;
+            a.image[o] = finish_pixel(fp, col);
+        }
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) fetches += __shfl_xor_sync(0xffffffffu, fetches, s);
+    if (lane == 0 && fetches) atomicAdd(&a.counters->cone_steps, (unsigned long long)fetches);
+}
+
 }  // namespace
 
 // The shading preamble of every pixel walks visibility -> indices -> vertex attributes, all evicted from L2 by the voxel
@@ -600,7 +791,7 @@ size_t vctk_image_rows(const vct_ctx* c) {
     return (size_t)((rows8 + ws - 1) / ws) * 8 * ws;
 }
 
-int vctk_cone_trace(vct_ctx* c) {
+static TraceArgs make_trace_args(vct_ctx* c) {
     TraceArgs a{};
     a.fc = c->d_fc; a.W = c->W; a.H = c->H;
     // screen sharding across ranks: world_size equal bands of whole 8-row tiles (the last may be short)
@@ -613,6 +804,56 @@ int vctk_cone_trace(vct_ctx* c) {
     a.vol = rad ? c->radiance_tex : c->color_tex; a.vol_point = rad ? c->radiance_tex_point : c->color_tex_point;
     a.vol_last = rad ? c->radiance_tex_last : c->color_tex_last; a.warp = reinterpret_cast<const ushort4*>(c->d_warpmap);
     a.image = c->d_image; a.counters = c->d_counters;
+    return a;
+}
+// ---- split variant, host side (VCT_TRACE_VARIANT bit 6 = split, bit 7 = set-up on a side stream under the voxel passes)
+static bool split_applies(const vct_ctx* c) { return (c->trace_variant & 64) && c->h_fc.p.debug_view == VCT_VIEW_SHADED; }
+static int split_record(vct_ctx* c, const TraceArgs& a, SplitRec& rec) {
+    const size_t px = (size_t)(a.y_hi - a.y_lo) * c->W, bytes = px * sizeof(float4) * kSplitPlanes;
+    if (bytes > c->trace_rec_bytes) {
+        VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_trace_rec); c->d_trace_rec = nullptr; c->trace_rec_bytes = 0;
+        VCT_CHECK(c, cudaMalloc(&c->d_trace_rec, bytes));
+        c->trace_rec_bytes = bytes;
+    }
+    for (int k = 0; k < kSplitPlanes; ++k) rec.plane[k] = reinterpret_cast<float4*>(c->d_trace_rec) + (size_t)k * px;
+    return 0;
+}
+static int launch_setup(vct_ctx* c, const TraceArgs& a, cudaStream_t st) {
+    SplitRec rec;
+    if (split_record(c, a, rec)) return 1;
+    dim3 grid((c->W + kThreads / 4 - 1) / (kThreads / 4), (a.y_hi - a.y_lo + 3) / 4);
+    k_trace_setup<<<grid, kThreads, 0, st>>>(a, rec);
+    VCT_LAUNCH_CHECK(c, "k_trace_setup");
+    return 0;
+}
+// Called by vct_gi_passes right after the vertex transform (bit 7): fork a side stream, run the set-up there, leave an event for the
+// march.  Needs what the producers left (visibility buffer, shadow map) and this frame's world-space vertices — nothing the voxel
+// passes write.  Works inside a stream capture (fork / join by events).
+int vctk_trace_setup_async(vct_ctx* c) {
+    if (!split_applies(c) || !(c->trace_variant & 128) || c->cfg.world_size > 1 || c->profiling >= 2) return 0;
+    const TraceArgs a = make_trace_args(c);
+    if (a.y_hi <= a.y_lo) return 0;
+    if (!c->side_stream) {
+        VCT_CHECK(c, cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        VCT_CHECK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        VCT_CHECK(c, cudaEventCreateWithFlags(&c->ev_setup_done, cudaEventDisableTiming));
+        SplitRec rec; if (split_record(c, a, rec)) return 1;            // allocate outside any capture
+    }
+    VCT_CHECK(c, cudaEventRecord(c->ev_fork, c->stream));
+    VCT_CHECK(c, cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+    if (c->copy_pending) {                                              // vct_read_image_async: the set-up writes the background pixels of d_image; only the
+        VCT_CHECK(c, cudaStreamWaitEvent(c->side_stream, c->ev_copy_done, 0));   // side stream waits for the copy (the march follows the set-up), the voxel passes do not
+        c->copy_pending = false;
+    }
+    if (launch_setup(c, a, c->side_stream)) return 1;
+    VCT_CHECK(c, cudaEventRecord(c->ev_setup_done, c->side_stream));
+    c->setup_in_flight = true;
+    return 0;
+}
+
+int vctk_cone_trace(vct_ctx* c) {
+    TraceArgs a = make_trace_args(c);
     if (a.y_hi <= a.y_lo) return 0;
     if (c->copy_pending) {                                      // vct_read_image_async: the previous frame's image is still being read back
         VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
@@ -629,11 +870,27 @@ int vctk_cone_trace(vct_ctx* c) {
         VCT_LAUNCH_CHECK(c, "k_l2_prefetch");
     }
     const vct_frame_params& p = c->h_fc.p;
+    if (split_applies(c)) {                                     // VCT_TRACE_VARIANT bit 6 (prototype): set-up + march
+        if (c->setup_in_flight) { VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_setup_done, 0)); c->setup_in_flight = false; }
+        else if (launch_setup(c, a, c->stream)) return 1;
+        SplitRec rec; if (split_record(c, a, rec)) return 1;
+        dim3 grid((c->W + kThreads / 4 - 1) / (kThreads / 4), (a.y_hi - a.y_lo + 3) / 4);
+        const int wm = p.warp_texture ? WARP_TEXTURE : p.warp_voxels ? WARP_VOXELS : p.voxelize_tesselation_warp ? WARP_TESS : WARP_NONE;
+        if (wm == WARP_TEXTURE) k_trace_march<WARP_TEXTURE><<<grid, kThreads, 0, c->stream>>>(a, rec);
+        else if (wm == WARP_VOXELS) k_trace_march<WARP_VOXELS><<<grid, kThreads, 0, c->stream>>>(a, rec);
+        else if (wm == WARP_TESS) k_trace_march<WARP_TESS><<<grid, kThreads, 0, c->stream>>>(a, rec);
+        else if (((c->trace_variant >> 8) & 3) == 1) k_trace_march<WARP_NONE, 5><<<grid, kThreads, 0, c->stream>>>(a, rec);
+        else if (((c->trace_variant >> 8) & 3) == 2) k_trace_march<WARP_NONE, 6><<<grid, kThreads, 0, c->stream>>>(a, rec);
+        else k_trace_march<WARP_NONE><<<grid, kThreads, 0, c->stream>>>(a, rec);
+        VCT_LAUNCH_CHECK(c, "k_trace_march");
+        return 0;
+    }
     // the coarsest level goes to shared memory when it fits (edge <= 8: 256^3 with 6 levels, 128^3 with 5, ...)
     a.n_last = level_dim(c->D, c->L - 1);
-    a.last_level = (rad ? c->d_radiance : c->d_color) + c->level_off[c->L - 1];
+    a.last_level = (p.draw_radiance != 0 ? c->d_radiance : c->d_color) + c->level_off[c->L - 1];
     // tuning knobs (VCT_TRACE_VARIANT): bit 0 = shared-memory last level (measured slower, off), bit 3 = L2 prefetch (off),
-    // bits 4-5 = CTA size 128 / 64 / 32 / 256 threads
+    // bits 4-5 = CTA size 128 / 64 / 32 / 256 threads; bit 6 = split set-up / march kernels, bit 7 = set-up on a side stream, bits 8-9 =
+    // march kernel at 4 / 5 / 6 CTAs per SM (prototype, handled above)
     const int variant = c->trace_variant;
     const bool sl = a.n_last <= kLastMax && (variant & 1) && !p.warp_voxels;
     const int tpb = ((variant >> 4) & 3) == 1 ? 64 : ((variant >> 4) & 3) == 2 ? 32 : ((variant >> 4) & 3) == 3 ? 256 : kThreads;
