@@ -1,4 +1,4 @@
-"""Multi-rank host logic on CPU: world_size 2 with the gloo backend (the N>1 data path of vct_b200/sharded.py).
+"""Multi-rank host logic on CPU: world_size 2 and 4 with the gloo backend (the N>1 data path of vct_b200/sharded.py).
 
 What is checked without a GPU: the z-slab / level-chunk / screen-band partition maths, that BOX2 mips of a slab need
 no halo (the slab of the full-volume mip == the mip computed from a volume holding only that slab), and that the
@@ -72,18 +72,19 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_world2_slab_exchange_reassembles_single_process_pyramid():
+@pytest.mark.parametrize("world", [WORLD, 4])          # 4: the coarsest level (4^3) is exactly one texel per slab
+def test_slab_exchange_reassembles_single_process_pyramid(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, WORLD, port, q)) for r in range(WORLD)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    res = dict(q.get(timeout=5) for _ in range(WORLD))
-    assert res == {0: True, 1: True}
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert res == {r: True for r in range(world)}
 
 
 def test_partition_maths():
