@@ -131,7 +131,8 @@ enum { VCT_VIEW_SHADED = 0,
        VCT_VIEW_DOMINANT_AXIS = 6,     /* `dominant_axis`                                                                 :444-447 */
        VCT_VIEW_INDIRECT = 7,          /* debugIndirect: the six diffuse cones (x occlusion if draw_occlusion)            :489 */
        VCT_VIEW_OCCLUSION = 8,         /* debugOcclusion                                                                  :490 */
-       VCT_VIEW_REFLECTIONS = 9 };     /* debugReflections: the specular cone                                             :505 */
+       VCT_VIEW_REFLECTIONS = 9,       /* debugReflections: the specular cone                                             :505 */
+       VCT_VIEW_LAST = VCT_VIEW_REFLECTIONS };
 
 /* GLBufferedTimer results in ns, same names as reference src/Application.h:192 (+ producers). */
 typedef struct {

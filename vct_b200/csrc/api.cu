@@ -300,7 +300,6 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     vct_ctx* c = new vct_ctx();
     c->cfg = *cfg; c->D = cfg->dim; c->L = clamp_levels(cfg->dim, cfg->levels); c->S = cfg->shadow_size; c->W = cfg->width; c->H = cfg->height;
     auto bail = [&](const char* what) { g_create_error = std::string("vct_create: ") + what + ": " + c->error; vct_destroy(c); return 1; };
-    if (const char* v = getenv("VCT_TRACE_VARIANT")) c->trace_variant = atoi(v);
     if (const char* v = getenv("VCT_SPARSE")) c->sparse_off = atoi(v) == 0;   // VCT_SPARSE=0: dense kernels every frame (A/B and tests)
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
     for (auto& ev : c->ev) if (cudaEventCreate(&ev) != cudaSuccess) return bail("event");
@@ -342,10 +341,6 @@ int vct_destroy(vct_ctx* c) {
     if (c->ev_image_ready) cudaEventDestroy(c->ev_image_ready);
     if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_setup_done) cudaEventDestroy(c->ev_setup_done);
-    cudaFree(c->d_trace_rec);
     for (auto& ev : c->prof_pool) cudaEventDestroy(ev);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -521,7 +516,6 @@ int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
     // sparse frame: vertex transform and masked clear share one launch (kept apart under per-kernel profiling)
     const bool fused_begin = plan_frame(c).sparse && c->profiling < 2 && c->n_vertices > 0;
     if (fused_begin ? vctk_frame_begin_masked(c) : vctk_transform_vertices(c)) return 1;
-    if (vctk_trace_setup_async(c)) return 1;                  // VCT_TRACE_VARIANT bits 6+7 (prototype): shading set-up on a side stream, under the voxel passes
     if (gi_body(c, g, fused_begin)) return 1;
     if (c->cfg.world_size > 1) return 0;                      // caller all-gathers, then vct_exchange + vct_cone_trace
     if (g.rec(EV_GBUF)) return 1;

@@ -164,10 +164,6 @@ struct vct_ctx {
     // asynchronous image read-back (vct_read_image_async): the copy runs on its own stream behind the frame and the next
     // cone trace waits for it before it overwrites d_image
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_image_ready = nullptr, ev_copy_done = nullptr; bool copy_pending = false;
-    int trace_variant = 0;           // VCT_TRACE_VARIANT (tuning knob, see cone_trace.cu)
-    // split cone trace (VCT_TRACE_VARIANT bits 6-7, prototype): per-pixel set-up records, side stream for the set-up kernel
-    void* d_trace_rec = nullptr; size_t trace_rec_bytes = 0;
-    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_setup_done = nullptr; bool setup_in_flight = false;
     std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
 };
@@ -235,7 +231,6 @@ int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);
 int vctk_warpmap(vct_ctx*);
 int vctk_cone_trace(vct_ctx*);
-int vctk_trace_setup_async(vct_ctx*);
 size_t vctk_image_rows(const vct_ctx*);
 int vctk_set_voxel_opacity(vct_ctx*, float);
 int vctk_temporal_radiance_filter(vct_ctx*, float);
