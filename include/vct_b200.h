@@ -171,6 +171,8 @@ int  vct_transfer(vct_ctx*, const vct_frame_params*);      /* :757-785 */
 int  vct_inject(vct_ctx*, const vct_frame_params*);        /* :787-837 */
 int  vct_fill_holes(vct_ctx*, const vct_frame_params*);    /* :839-875 */
 int  vct_mip(vct_ctx*, int which_volume);                  /* :877-921  (VCT_VOL_RADIANCE or VCT_VOL_COLOR) */
+int  vct_mip_kernel(vct_ctx*, int which_volume, int kernel_mode);   /* shaders/filterRadiance.comp:9-60 with its `kernelMode` uniform:
+                                                              0 BOX2 (= vct_mip), 1 BOX3, 2 CUBE; the host never sets it (dead modes) */
 int  vct_exchange(vct_ctx*);                               /* multi-GPU only: publish slab pyramid to the 3D texture
                                                               after the caller's all-gather */
 /* multi-GPU, sparse frames: level 0 of the traced pyramid travels as the flagged x-row segments of each rank's slab, pushed

@@ -106,6 +106,10 @@ class Oracle:
         self.info = P.VoxelizeInfo()
         self.cone_steps = 0
 
+    def set_actor_transform(self, actor, model):
+        """Per-frame actor animation (Scene::update): overwrite the model matrix in place (the orc_scene keeps its pointer)."""
+        self.s.models[actor] = np.asarray(model, np.float32).reshape(16)
+
     def _wm(self, p):
         return ptr(self.warpmap) if p.warp_texture else None
 

@@ -51,7 +51,30 @@ def main():
             lines.append("|".join(f))
         open(os.path.join(dst, "materials.txt"), "w").write("\n".join(lines) + "\n")
     os.remove(tool)
+    for name in SCENES:
+        decode_textures(name)
     print("baked into", OUT)
 
+
+def decode_textures(name):
+    """Decode every texture of a baked scene ONCE, here in the build container, into textures.npz (all mip levels packed, as
+    vct_upload_texture takes them).  The harness (bench.py, tests, both bench arms) then loads texels with numpy alone: the
+    `--impl reference` process never loads libvct_b200.so ("the reference arm loads the repo's .so").  The decoder is
+    the library's own PNG reader, texel-identical to the reference's stb_image on every shipped file (tests/test_ingest.py)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from vct_b200 import ingest
+    d = os.path.join(OUT, name, "textures")
+    out = {}
+    for fn in sorted(os.listdir(d)):
+        t = ingest.load_image(os.path.join(d, fn))
+        out[fn + "|meta"] = np.array([t["width"], t["height"], t["channels"], t["levels"]], np.int32)
+        out[fn + "|px"] = t["pixels"]
+    np.savez_compressed(os.path.join(OUT, name, "textures.npz"), **out)
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--decode-only":
+        for n in SCENES:
+            decode_textures(n)
+    else:
+        main()

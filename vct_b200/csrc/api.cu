@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <exception>
 
 #include <stdlib.h>
 
@@ -170,6 +171,8 @@ void build_schedule(ConeSchedule& t, const vct_cone_settings& cs, int levels) {
 int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     if (!p) return fail(c, "null frame params");
     if (p->diffuse_cone.steps > 64 || p->specular_cone.steps > 64 || p->diffuse_cone.steps < 0 || p->specular_cone.steps < 0) return fail(c, "cone steps must be in [0,64]");
+    if (p->voxel_fill_holes && c->cfg.world_size > 1)
+        return fail(c, "voxelFillHoles reads the 3x3x3 neighbourhood across z-slab borders (voxelFillHoles.comp:8-36): not supported with world_size > 1");
     if (p->radiance_dilate) return fail(c, "radianceDilate is malformed in the reference (injectRadiance.comp:59-64) and is not supported");
     if (finalize_scene(c)) return 1;
     FrameConst& f = c->h_fc;
@@ -317,6 +320,10 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
+    // overflow of a fixed-capacity buffer is also flagged in mapped host memory, so that the next entry point sees it without a sync
+    if (cudaHostAlloc((void**)&c->h_overflow, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) { c->error = "cudaHostAlloc"; return bail("overflow flag"); }
+    *c->h_overflow = 0u;
+    { unsigned* dp = nullptr; if (cudaHostGetDevicePointer((void**)&dp, c->h_overflow, 0) != cudaSuccess || cudaMemcpyAsync(&c->d_counters->overflow_host, &dp, sizeof dp, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->error = "mapped overflow flag"; return bail("overflow flag"); } }
     for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("sync");
     *out = c;
@@ -334,13 +341,14 @@ int vct_destroy(vct_ctx* c) {
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_wpos,
                     (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})
         cudaFree(p);
-    for (void* p : c->tex_allocs) cudaFree(p);
+    for (void* p : c->tex_alloc) cudaFree(p);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->stage_ev) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_image_ready) cudaEventDestroy(c->ev_image_ready);
     if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_overflow) cudaFreeHost(c->h_overflow);
     for (auto& ev : c->prof_pool) cudaEventDestroy(ev);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -351,6 +359,11 @@ int vct_destroy(vct_ctx* c) {
 int vct_remake(vct_ctx* c, int dim, int levels) {
     if (!c) return 1;
     if (dim < 4 || (dim & (dim - 1)) || dim > 1024) return fail(c, "vct_remake: dim must be a power of two in [4,1024]");
+    if (c->cfg.world_size > 1) {
+        if (dim % c->cfg.world_size) return fail(c, "vct_remake: dim must be divisible by world_size");
+        // the staging buffer of the sparse exchange is mapped by the peers (cudaIpc): freeing it here would leave them storing into freed memory
+        if (c->d_xchg) return fail(c, "vct_remake: not supported once the sparse slab exchange is set up (vct_exchange_setup); create new contexts on every rank");
+    }
     VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     free_volumes(c);
     vctk_xchg_free(c);
@@ -367,6 +380,8 @@ int vct_upload_mesh(vct_ctx* c, int actor, const void* vertices, size_t n_vertic
     if (material_of_triangle)
         for (size_t t = 0; t < n_indices / 3; ++t)
             if (material_of_triangle[t] < 0 || material_of_triangle[t] >= VCT_MAX_MATERIALS) return fail(c, "vct_upload_mesh: material id out of range");
+    const size_t nv0 = c->h_vertices.size(), na0 = c->h_vactor.size(), ni0 = c->h_indices.size(), nt0 = c->h_trimat.size();
+    try {
     HostMesh m{}; m.actor = actor; m.n_vertices = n_vertices; m.n_tris = n_indices / 3; m.vbase = c->h_vertices.size() / 14; m.tbase = c->h_trimat.size();
     for (int i = 0; i < 16; ++i) m.model.m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
     const size_t v0 = c->h_vertices.size();
@@ -378,6 +393,10 @@ int vct_upload_mesh(vct_ctx* c, int actor, const void* vertices, size_t n_vertic
     c->meshes.push_back(m);
     c->scene_dirty = true;
     return 0;
+    } catch (const std::exception&) {                           // nothing may cross the C ABI; leave the scene as it was
+        c->h_vertices.resize(nv0); c->h_vactor.resize(na0); c->h_indices.resize(ni0); c->h_trimat.resize(nt0);
+        return fail(c, "vct_upload_mesh: out of host memory");
+    }
 }
 
 int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels, int levels, const void* pixels) {
@@ -389,7 +408,11 @@ int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels,
     uint8_t* d = nullptr;
     VCT_CHECK(c, cudaMalloc(&d, total + 16));
     if (cudaError_t r = cudaMemcpy(d, pixels, total, cudaMemcpyHostToDevice); r != cudaSuccess) { cudaFree(d); return fail(c, cudaGetErrorString(r)); }
-    c->tex_allocs.push_back(d);
+    if (c->tex_alloc[tex]) {                                    // re-upload (streaming / reload): the old block may still be read by queued work
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->tex_alloc[tex]);
+    }
+    c->tex_alloc[tex] = d;
     DevTexture& t = c->h_tex[tex]; t.w = width; t.h = height; t.ch = channels; t.levels = levels;
     size_t off = 0;
     for (int l = 0; l < levels; ++l) { t.level[l] = d + off; off += (size_t)std::max(1, width >> l) * std::max(1, height >> l) * channels; }
@@ -431,10 +454,20 @@ int vct_set_lights(vct_ctx* c, const vct_light* lights, int n) {
 #define PASS_PROLOGUE                                   \
     if (!c) return 1;                                   \
     cudaSetDevice(c->cfg.device);                       \
+    if (overflow_seen(c)) return 1;                     \
     vct_prof_begin(c);                                  \
     if (upload_frame(c, p)) return 1;                   \
     vct_prof_mark(c, "h2d_params");
 
+// A fixed-capacity buffer (fragment records, raster queues, triangle setups) overflowed in an EARLIER call: kernels flag that in
+// mapped host memory, the next pass entry point reports it once (and does nothing else), then the context carries on.
+static int overflow_seen(vct_ctx* c) {
+    if (!c->h_overflow || !*(volatile unsigned*)c->h_overflow) return 0;
+    *(volatile unsigned*)c->h_overflow = 0u;
+    c->error = "a fixed-capacity device buffer overflowed during an earlier call and fragments or tiles were dropped (fragment buffer, raster queues or triangle setups): "
+               "raise vct_config.max_fragments; this call was not executed, the next one will be";
+    return 1;
+}
 int vct_shadowmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_shadowmap(c); }
 int vct_occupancy(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_voxelize(c, true); }
 int vct_warpmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_warpmap(c); }
@@ -457,6 +490,19 @@ int vct_mip(vct_ctx* c, int which) {
     c->seg_valid = false;
     const bool publish = c->cfg.world_size <= 1 && !(which == VCT_VOL_COLOR && !c->color_arr);
     return vctk_mip(c, which, 0, publish);
+}
+// filterRadiance.comp's `kernelMode` uniform (:9-13): 0 = BOX2 (what the host dispatches, = vct_mip), 1 = BOX3 (27 taps x 0.037),
+// 2 = CUBE (7 axial taps x 0.143); the reference declares the uniform and never sets it.  BOX3 / CUBE read across 2x2x2 cell borders,
+// so they need the whole source level: single GPU only.
+int vct_mip_kernel(vct_ctx* c, int which, int kernel_mode) {
+    if (!c) return 1;
+    cudaSetDevice(c->cfg.device);
+    if (which != VCT_VOL_RADIANCE && which != VCT_VOL_COLOR) return fail(c, "vct_mip_kernel: radiance or colour volume only");
+    if (kernel_mode < 0 || kernel_mode > 2) return fail(c, "vct_mip_kernel: kernel_mode is 0 (BOX2), 1 (BOX3) or 2 (CUBE)");
+    if (kernel_mode != 0 && c->cfg.world_size > 1) return fail(c, "vct_mip_kernel: BOX3 / CUBE read across z-slab borders; world_size must be 1");
+    c->seg_valid = false;
+    const bool publish = c->cfg.world_size <= 1 && !(which == VCT_VOL_COLOR && !c->color_arr);
+    return vctk_mip(c, which, kernel_mode, publish);
 }
 int vct_exchange(vct_ctx* c) {
     if (!c) return 1;

@@ -88,10 +88,14 @@ struct Counters {                // device-resident, zeroed per frame
     unsigned expand_count;       // raster work queue (bands of tile rows still to be enumerated)
     unsigned pixel_count;        // raster work queue (single pixels of tiny triangles)
     unsigned setup_count;        // big-triangle setups written by k_raster_bin
-    unsigned overflow;           // set when a fixed-capacity buffer was too small
+    unsigned overflow;           // set when a fixed-capacity buffer was too small (reset with the other per-frame counters)
     unsigned mip_ticket;         // k_mip_chain last-CTA detection (self-resetting)
     unsigned long long cone_steps;
+    unsigned* overflow_host;     // the same flag in mapped pinned host memory: the frame entry points poll it without a device sync
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ void vct_flag_overflow(Counters* c) { c->overflow = 1u; if (c->overflow_host) *c->overflow_host = 1u; }
+#endif
 
 struct HostMesh {
     int actor; size_t n_vertices, n_tris; size_t vbase, tbase;   // offsets into the concatenated device arrays
@@ -119,7 +123,7 @@ struct vct_ctx {
     uint32_t* d_indices = nullptr; int32_t* d_trimat = nullptr;
     Mat4* d_models = nullptr; float* d_nmats = nullptr; int n_actors = 0;
     float4 *d_wpos = nullptr, *d_wnrm = nullptr, *d_wT = nullptr, *d_wB = nullptr;   // per-vertex world-space attributes
-    DevTexture h_tex[VCT_MAX_TEXTURES]{}; DevTexture* d_tex = nullptr; std::vector<void*> tex_allocs; int n_textures = 0;
+    DevTexture h_tex[VCT_MAX_TEXTURES]{}; DevTexture* d_tex = nullptr; void* tex_alloc[VCT_MAX_TEXTURES]{}; int n_textures = 0;
     DevMaterial h_mat[VCT_MAX_MATERIALS]{}; DevMaterial* d_mat = nullptr; int n_materials = 0;
     vct_light h_lights[8]{}; int n_lights = 0;
 
@@ -157,6 +161,7 @@ struct vct_ctx {
     void* d_frame_blob = nullptr; size_t frame_blob_bytes = 0;
     unsigned char* h_stage = nullptr; cudaEvent_t stage_ev[4]{}; unsigned stage_next = 0;
     Counters* d_counters = nullptr; Counters h_counters{};
+    unsigned* h_overflow = nullptr;  // mapped pinned word written by vct_flag_overflow
     // timing
     cudaEvent_t ev[32]{}; vct_timings timings{};
     int profiling = 1;               // 0 none, 1 pass-level events (reference GLTimer semantics), 2 + one event per kernel

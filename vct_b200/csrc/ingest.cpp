@@ -76,6 +76,7 @@ int vct_ingest_get_texture(const vct_ingest* g, int texture, vct_ingest_texture*
 
 int vct_ingest_upload(vct_ctx* c, const vct_ingest* g, int actor, int material_base, int texture_base, const float model[16]) {
     if (!c || !g) return 1;
+    try {
     const vct::IngestScene& s = g->scene;
     for (size_t t = 0; t < s.textures.size(); ++t) {
         const vct::Image& im = s.textures[t];
@@ -94,6 +95,7 @@ int vct_ingest_upload(vct_ctx* c, const vct_ingest* g, int actor, int material_b
     if (vct_upload_mesh(c, actor, s.mesh.vertices.data(), s.mesh.vertices.size() / 14, 56, s.mesh.indices.data(), s.mesh.indices.size(), rebased.data())) return 1;
     static const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     return vct_set_actor_transform(c, actor, model ? model : identity);
+    } catch (const std::exception&) { return 1; }                      // (bad_alloc of the rebased material list: nothing may cross the C ABI)
 }
 
 }  // extern "C"

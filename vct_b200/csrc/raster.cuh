@@ -87,7 +87,7 @@ struct TileQueues {
     uint2* tiles; unsigned tile_cap; unsigned* tile_count;
     uint2* expand; unsigned expand_cap; unsigned* expand_count;
     uint2* pixels; unsigned pixel_cap; unsigned* pixel_count;      // single pixels of tiny triangles: (slot, x | y << 16)
-    unsigned* overflow;
+    Counters* counters;             // vct_flag_overflow
 };
 
 // Is the pixel-centre box [bx0,bx1]x[by0,by1] entirely outside one of the edges?
@@ -115,7 +115,7 @@ __device__ __forceinline__ void enqueue_tiles(bool queued, const TriSetup& s, ui
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(q.tile_count, (unsigned)__popc(sm));
         const uint32_t pos = __shfl_sync(0xffffffffu, base, 0) + __popc(sm & lt_mask);
-        if (single) { if (pos < q.tile_cap) q.tiles[pos] = make_uint2(sslot, (unsigned)s.x0 | (unsigned)s.y0 << 16); else *q.overflow = 1u; }
+        if (single) { if (pos < q.tile_cap) q.tiles[pos] = make_uint2(sslot, (unsigned)s.x0 | (unsigned)s.y0 << 16); else vct_flag_overflow(q.counters); }
     }
     // multi-tile: bands of tile rows, <= max_tiles tiles each (at least one row)
     const bool multi = queued && ntx * nty > 1;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void enqueue_tiles(bool queued, const TriSetup& s, ui
     if (lane == 31) base = atomicAdd(q.expand_count, (unsigned)total);
     uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(inc - nitems);
     for (int r = 0; r < nty && nitems; r += rows, ++pos) {
-        if (pos < q.expand_cap) q.expand[pos] = make_uint2(sslot, (unsigned)r | (unsigned)min(rows, nty - r) << 16); else *q.overflow = 1u;
+        if (pos < q.expand_cap) q.expand[pos] = make_uint2(sslot, (unsigned)r | (unsigned)min(rows, nty - r) << 16); else vct_flag_overflow(q.counters);
     }
 }
 // expand: one warp per item.  `setups` is an array of records of `stride` bytes that begin with a TriSetup.
@@ -160,7 +160,7 @@ __device__ __forceinline__ void expand_items(const unsigned char* __restrict__ s
             base = __shfl_sync(0xffffffffu, base, 0);
             if (keep) {
                 const uint32_t pos = base + __popc(m & lt_mask);
-                if (pos < q.tile_cap) q.tiles[pos] = make_uint2(it.x, (unsigned)ox | (unsigned)oy << 16); else *q.overflow = 1u;
+                if (pos < q.tile_cap) q.tiles[pos] = make_uint2(it.x, (unsigned)ox | (unsigned)oy << 16); else vct_flag_overflow(q.counters);
             }
         }
     }
@@ -170,7 +170,7 @@ static inline TileQueues vctk_tile_queues(vct_ctx* c) {
     q.tiles = reinterpret_cast<uint2*>(c->d_tile_queue); q.tile_cap = (unsigned)c->tile_queue_cap; q.tile_count = &c->d_counters->tile_queue_count;
     q.expand = reinterpret_cast<uint2*>(c->d_expand_queue); q.expand_cap = (unsigned)c->expand_cap; q.expand_count = &c->d_counters->expand_count;
     q.pixels = reinterpret_cast<uint2*>(c->d_pixel_queue); q.pixel_cap = (unsigned)c->pixel_cap; q.pixel_count = &c->d_counters->pixel_count;
-    q.overflow = &c->d_counters->overflow;
+    q.counters = c->d_counters;
     return q;
 }
 // reserve one setup slot per lane with `want` (one atomic per warp); returns the lane's slot

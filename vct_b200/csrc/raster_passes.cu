@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) k_raster_bin(RasterArgs a) {
             bool stored = false;
             if (queued) {
                 if (slot < a.setup_cap) { TileSetup ts; ts.s = S[q]; ts.tri = t; ts.alpha_tex = alpha_tex; ts.pad[0] = ts.pad[1] = 0u; a.setups[slot] = ts; stored = true; }
-                else a.counters->overflow = 1u;
+                else vct_flag_overflow(a.counters);
             }
             enqueue_tiles(stored, S[q], slot, a.q);
         }

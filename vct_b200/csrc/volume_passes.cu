@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4
     if (reset && blockIdx.x == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
         reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
-        reset->cone_steps = 0ull;
+        reset->cone_steps = 0ull; reset->overflow = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
@@ -53,7 +53,7 @@ __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uin
     if (block == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
         reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
-        reset->cone_steps = 0ull;
+        reset->cone_steps = 0ull; reset->overflow = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t t = w_lo + block * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)n_blocks * blockDim.x) {      // [w_lo, n_words): this rank's slab
@@ -743,10 +743,10 @@ int vctk_clear_voxels(vct_ctx* c, bool reset_frame_counters) {
 int vctk_transfer(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
     const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
-    // seg_mark is indexed like the volume: only valid for a whole-volume launch (off == 0, single GPU)
+    // seg_mark is indexed relative to the slab like the volume pointers (off voxels = off / 8 segments)
     k_transfer<<<grid_for(n / 8, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_radiance + off), n / 4,
                                                                     p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters,
-                                                                    (p.temporal_filter_radiance && c->cfg.world_size <= 1 && c->d_seg[c->seg_cur]) ? c->d_seg[c->seg_cur] : nullptr);
+                                                                    (p.temporal_filter_radiance && c->d_seg[c->seg_cur]) ? c->d_seg[c->seg_cur] + off / 8 : nullptr);
     VCT_LAUNCH_CHECK(c, "k_transfer");
     return 0;
 }

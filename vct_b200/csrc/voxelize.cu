@@ -210,7 +210,7 @@ __device__ __forceinline__ void store_fragment(const VoxArgs& a, const VoxHead& 
     const uint32_t o = (uint32_t)(((size_t)iz * D + iy) * D + ix);
     a.seg[o >> 3] = 1;                                                      // every writer stores the same byte
     if (MODE == MODE_SORTED) {
-        if (slot >= a.frag_cap) { a.counters->overflow = 1u; return; }
+        if (slot >= a.frag_cap) { vct_flag_overflow(a.counters); return; }
         Frag f;
         f.key = o; f.tri = S.tri; f.rank = (uint32_t)(py * D + px);
         f.next = atomicExch(a.color + o, slot + 1u);                       // push on the voxel's list
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
         bool stored = false;
         if (need_slot) {
             if (sslot < a.setup_cap) { if (MODE != MODE_OCC) make_shading_setup(a, S); a.setups[sslot] = S; stored = true; }
-            else a.counters->overflow = 1u;
+            else vct_flag_overflow(a.counters);
         }
         {   // pixel items: warp prefix sum -> one atomic per warp
             const int nh = stored ? __popc(hits) : 0;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
                 uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(inc - nh);
                 for (int i = 0; i < bw * bh && nh; ++i) {
                     if (!(hits >> i & 1u)) continue;
-                    if (pos < a.q.pixel_cap) a.q.pixels[pos] = make_uint2(sslot, (unsigned)(S.s.x0 + i % bw) | (unsigned)(S.s.y0 + i / bw) << 16); else a.counters->overflow = 1u;
+                    if (pos < a.q.pixel_cap) a.q.pixels[pos] = make_uint2(sslot, (unsigned)(S.s.x0 + i % bw) | (unsigned)(S.s.y0 + i / bw) << 16); else vct_flag_overflow(a.counters);
                     ++pos;
                 }
             }
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restri
 __global__ void __launch_bounds__(kThreads) k_voxel_expand(const VoxSetup* __restrict__ setups, TileQueues q) {
     expand_items(reinterpret_cast<const unsigned char*>(setups), sizeof(VoxSetup), q);
 }
-__global__ void k_voxel_reset(Counters* c) { c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
+__global__ void k_voxel_reset(Counters* c) { c->overflow = 0; c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
 
 // ================================================================ tessellation voxeliser (reference default)
 // testTesselation.tesc/.tese + the fixed-function tessellator (triangles, equal_spacing, point_mode), Application.cpp:585-665.

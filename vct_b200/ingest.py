@@ -93,15 +93,7 @@ def load_image(path, generate_mips=True):
         g.close()
 
 
-def _texture_from_packed(t):
-    tex = S.Texture.__new__(S.Texture)
-    tex.width, tex.height, tex.channels = t["width"], t["height"], t["channels"]
-    tex.levels, off = [], 0
-    for l in range(t["levels"]):
-        w, h = max(1, t["width"] >> l), max(1, t["height"] >> l)
-        tex.levels.append(t["pixels"][off:off + w * h * t["channels"]].reshape(h, w, t["channels"]))
-        off += w * h * t["channels"]
-    return tex
+_texture_from_packed = S.texture_from_packed
 
 
 def load_obj(scene, path, resource_dir="", model=None):

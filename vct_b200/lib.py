@@ -12,7 +12,7 @@ SO = os.path.join(HERE, "lib", "libvct_b200.so")
 SYMBOLS = [
     "vct_create", "vct_destroy", "vct_remake", "vct_last_error", "vct_upload_mesh", "vct_upload_texture",
     "vct_set_material", "vct_set_actor_transform", "vct_set_lights", "vct_shadowmap", "vct_occupancy", "vct_warpmap",
-    "vct_voxelize", "vct_transfer", "vct_inject", "vct_fill_holes", "vct_mip", "vct_exchange", "vct_gbuffer",
+    "vct_voxelize", "vct_transfer", "vct_inject", "vct_fill_holes", "vct_mip", "vct_mip_kernel", "vct_exchange", "vct_gbuffer",
     "vct_cone_trace", "vct_frame", "vct_gi_passes", "vct_set_voxel_opacity", "vct_temporal_radiance_filter",
     "vct_filter3d", "vct_normalize_voxels_f16", "vct_read_image", "vct_read_volume", "vct_write_volume",
     "vct_read_shadowmap", "vct_write_shadowmap", "vct_read_visibility", "vct_get_counters", "vct_get_timings",
@@ -49,7 +49,7 @@ def load():
         "vct_upload_texture": (ci, [vp, ci, ci, ci, ci, ci, vp]),
         "vct_set_material": (ci, [vp, ci, C.POINTER(P.Material)]), "vct_set_actor_transform": (ci, [vp, ci, C.POINTER(cf)]),
         "vct_set_lights": (ci, [vp, vp, ci]),
-        "vct_mip": (ci, [vp, ci]), "vct_exchange": (ci, [vp]),
+        "vct_mip": (ci, [vp, ci]), "vct_mip_kernel": (ci, [vp, ci, ci]), "vct_exchange": (ci, [vp]),
         "vct_set_voxel_opacity": (ci, [vp, cf]), "vct_temporal_radiance_filter": (ci, [vp, cf]), "vct_filter3d": (ci, [vp, ci, ci]),
         "vct_normalize_voxels_f16": (ci, [vp, vp, vp, cf]),
         "vct_read_image": (ci, [vp, vp]), "vct_read_image_async": (ci, [vp, vp]), "vct_read_image_wait": (ci, [vp, ci]), "vct_read_volume": (ci, [vp, ci, ci, vp]), "vct_write_volume": (ci, [vp, ci, ci, vp]),

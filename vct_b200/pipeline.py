@@ -69,6 +69,7 @@ class Pipeline:
     def inject(self, p): self._ck(self.lib.vct_inject(self.h, C.byref(p)))
     def fill_holes(self, p): self._ck(self.lib.vct_fill_holes(self.h, C.byref(p)))
     def mip(self, which=P.VOL_RADIANCE): self._ck(self.lib.vct_mip(self.h, which))
+    def mip_kernel(self, which, mode): self._ck(self.lib.vct_mip_kernel(self.h, which, mode))
     def exchange(self): self._ck(self.lib.vct_exchange(self.h))
     def frame_was_sparse(self): return bool(self.lib.vct_frame_was_sparse(self.h))
     def mask_parity(self): return int(self.lib.vct_mask_parity(self.h))

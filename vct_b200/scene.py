@@ -43,6 +43,18 @@ class Texture:
         return np.concatenate([l.reshape(-1) for l in self.levels])
 
 
+def texture_from_packed(t):
+    """dict(width, height, channels, levels, pixels = all levels packed) -> Texture"""
+    tex = Texture.__new__(Texture)
+    tex.width, tex.height, tex.channels = t["width"], t["height"], t["channels"]
+    tex.levels, off = [], 0
+    for l in range(t["levels"]):
+        w, h = max(1, t["width"] >> l), max(1, t["height"] >> l)
+        tex.levels.append(t["pixels"][off:off + w * h * t["channels"]].reshape(h, w, t["channels"]))
+        off += w * h * t["channels"]
+    return tex
+
+
 class Mesh:
     """One actor's geometry: vertices (n,14) f32, indices (3T,) u32 in draw order, material id per triangle."""
 
@@ -95,10 +107,13 @@ def baked_available(name):
 
 def load_baked(scene, name, model=None):
     """Append the baked mesh `name` as a new actor (its materials/textures are appended to the scene).
-    Textures are decoded by the library's own PNG reader (vct_ingest_image: the reference's stb_image behaviour,
-    tests/test_ingest.py) and get its generated mips — no image library of the harness is involved."""
-    from . import ingest
+    Texels come from textures.npz, decoded once at bake time (tools/bake_assets.py) by the library's own PNG reader
+    (vct_ingest_image: the reference's stb_image behaviour, tests/test_ingest.py) with its generated mips; loading them
+    here needs numpy only, so a process that must not load libvct_b200.so (bench.py --impl reference) can build the scene.
+    Without the cache the PNG files are decoded through the library."""
     d = os.path.join(BAKED, name)
+    npz = os.path.join(d, "textures.npz")
+    cached = np.load(npz) if os.path.isfile(npz) else None
     verts = np.fromfile(os.path.join(d, "vertices.f32"), np.float32).reshape(-1, 14)
     idx = np.fromfile(os.path.join(d, "indices.u32"), np.uint32)
     tmat = np.fromfile(os.path.join(d, "tri_material.i32"), np.int32)
@@ -108,11 +123,16 @@ def load_baked(scene, name, model=None):
         if not fn:
             return -1
         if fn not in cache:
-            t = ingest.load_image(os.path.join(d, "textures", fn))
+            if cached is not None and fn + "|px" in cached:
+                w, h, ch, lv = (int(x) for x in cached[fn + "|meta"])
+                t = {"width": w, "height": h, "channels": ch, "levels": lv, "pixels": cached[fn + "|px"]}
+            else:
+                from . import ingest
+                t = ingest.load_image(os.path.join(d, "textures", fn))
             if t["channels"] not in (1, 3, 4):                     # grey + alpha: the reference allocates no storage for it (GLHelper.cpp:194-205)
                 cache[fn] = -1
             else:
-                scene.textures.append(ingest._texture_from_packed(t)); cache[fn] = len(scene.textures) - 1
+                scene.textures.append(texture_from_packed(t)); cache[fn] = len(scene.textures) - 1
         return cache[fn]
 
     for line in open(os.path.join(d, "materials.txt")):

@@ -65,9 +65,12 @@ def device_tensor(ptr, nbytes):
 
 # ------------------------------------------------------------------------------------------- the frame
 class ShardedFrame:
-    def __init__(self, pipeline, params, world=1, rank=0):
+    def __init__(self, pipeline, params, world=1, rank=0, workload=None):
         import torch
         self.g, self.p, self.world, self.rank = pipeline, params, world, rank
+        # animated workloads (config 4): per-frame actor transforms, and the whole frame graph (producers included) per step
+        self.workload, self.frame_index = workload, 0
+        self.whole_frame = bool(workload is not None and workload.whole_frame)
         self.torch = torch
         g = pipeline
         if world > 1:
@@ -105,12 +108,13 @@ class ShardedFrame:
                 f"cone trace sharded by {self.band}-row screen band, NCCL all-gather of the image bands")
 
     # producers of the reference frame graph that the GI step consumes (replicated on every rank)
-    def producers(self):
+    def producers(self, gbuffer=True):
         g, p = self.g, self.p
         g.shadowmap(p)
         if p.warp_texture:
             g.occupancy(p); g.warpmap(p)
-        g.gbuffer(p)
+        if gbuffer:
+            g.gbuffer(p)
 
     def _gather_levels(self, first):
         dist, r = self.dist, self.rank
@@ -172,14 +176,25 @@ class ShardedFrame:
                 self.step(); k -= 1
         return replayed
 
+    def _animate(self):
+        if self.workload is not None:
+            for actor, model in self.workload.models(self.frame_index):
+                self.g.set_actor_transform(actor, model)
+        self.frame_index += 1
+
     def step(self):
         g, p = self.g, self.p
+        self._animate()
         if self.world == 1:
-            g.gi_passes(p)
+            (g.frame if self.whole_frame else g.gi_passes)(p)
             return
         with self.torch.cuda.stream(self.stream):
+            if self.whole_frame:
+                self.producers(gbuffer=False)
             g.gi_passes(p)
             self._exchange()
+            if self.whole_frame:
+                g.gbuffer(p)
             g.cone_trace(p)
             r, n = self.rank, self.band_px
             self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
@@ -208,8 +223,9 @@ class ShardedFrame:
     def profiled_step(self):
         """Per-kernel times {name: (ns, launches)} of one step (library profiling level 2)."""
         g, p = self.g, self.p
+        self._animate()
         if self.world == 1:
-            g.gi_passes(p)
+            (g.frame if self.whole_frame else g.gi_passes)(p)
             return g.kernel_times()
         with self.torch.cuda.stream(self.stream):
             g.gi_passes(p)
@@ -222,6 +238,10 @@ class ShardedFrame:
             r, n = self.rank, self.band_px
             self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
         return kt
+
+    def close(self):
+        """Drop the captured graph before the process group goes away (a graph that outlives NCCL's communicator hangs teardown)."""
+        self.graph = None
 
     def pass_times(self):
         """Per-pass ms of one whole reference frame graph (GLTimer semantics; profiling level 1), incl. producers."""
