@@ -42,6 +42,11 @@ typedef struct {
     /* z-slab sharding of the voxel volume across ranks; single GPU: rank 0 of 1. */
     int rank, world_size;
     int max_fragments;  /* capacity of the voxel-fragment buffer (0 = default 8 Mi) */
+    /* Single-process multi-GPU (SURVEY §8b "multi-GPU fan-out is internal"): n_devices > 1 makes vct_create build one context per
+     * listed device (rank i on devices[i]; NULL = devices 0..n-1), enable peer access, attach the slab exchange, and return a handle
+     * that fans every call out; rank / world_size / device above are then ignored.  0 or 1: one context on `device`. */
+    int n_devices;
+    const int* devices;
 } vct_config;
 
 /* 80-byte std140 light record — reference src/Scene.cpp:64-76, shaders/voxelize.frag:31-45. */
@@ -175,16 +180,24 @@ int  vct_mip_kernel(vct_ctx*, int which_volume, int kernel_mode);   /* shaders/f
                                                               0 BOX2 (= vct_mip), 1 BOX3, 2 CUBE; the host never sets it (dead modes) */
 int  vct_exchange(vct_ctx*);                               /* multi-GPU only: publish slab pyramid to the 3D texture
                                                               after the caller's all-gather */
-/* multi-GPU, sparse frames: level 0 of the traced pyramid travels as the flagged x-row segments of each rank's slab, pushed
- * into staging buffers in every peer's memory (NVLink, cudaIpc) instead of a dense all-gather.  Per frame:
- *   vct_gi_passes; if vct_frame_was_sparse: vct_exchange_push, all-gather levels >= 1 (the barrier), vct_exchange_unpack;
- *   else: all-gather every level, vct_exchange.  Then vct_cone_trace.  Setup once: vct_exchange_setup, then hand every
- *   rank's 64-byte handle (vct_exchange_export) to every other rank (vct_exchange_import). */
+/* Multi-GPU (z-slab sharding): once every rank knows its peers' buffers, vct_frame / vct_gi_passes run the WHOLE sharded
+ * frame — voxel passes on the own slab, the slab exchange over NVLink peer memory (exchange.cu: level 0 as the flagged x-row segments
+ * pushed into staging regions in every peer's memory, levels >= 1 stored straight into the peers' pyramids, device-side flags instead of
+ * collectives), the cone trace of the own screen tiles, pixels stored into rank 0's image — with no collective and no host
+ * synchronisation by the caller; rank 0's image is complete when its stream reaches the end of the call.
+ * Setup once, either way:
+ *   one process per GPU   vct_exchange_setup on every rank; hand every rank's VCT_EXCHANGE_HANDLE_BYTES blob (vct_exchange_export:
+ *                         cudaIpc handles) to every other rank (vct_exchange_import)
+ *   one process, N GPUs   vct_config.n_devices > 1 does all of it inside vct_create (peer access + vct_exchange_attach)
+ * Without attached peers a world_size > 1 context stops after its mip chains (the caller all-gathers the levels itself, then
+ * vct_exchange + vct_cone_trace: the round-1 protocol, kept for transports other than peer memory). */
+#define VCT_EXCHANGE_HANDLE_BYTES 256
+typedef struct { void* staging; void* radiance; void* color; void* image; } vct_peer;   /* device pointers valid on THIS rank's device */
 int  vct_exchange_setup(vct_ctx*);
-int  vct_exchange_export(vct_ctx*, void* ipc_handle_64_bytes);
-int  vct_exchange_import(vct_ctx*, int rank, const void* ipc_handle_64_bytes);
-int  vct_exchange_push(vct_ctx*);
-int  vct_exchange_unpack(vct_ctx*);                        /* scatter the records of all ranks + publish levels >= 1 */
+int  vct_exchange_export(vct_ctx*, void* handle /* VCT_EXCHANGE_HANDLE_BYTES */);
+int  vct_exchange_import(vct_ctx*, int rank, const void* handle);
+int  vct_exchange_local(vct_ctx*, vct_peer* out);          /* this rank's own buffers (to attach on peers of the same process) */
+int  vct_exchange_attach(vct_ctx*, int rank, const vct_peer*);
 int  vct_frame_was_sparse(vct_ctx*);                       /* 1: the last vct_frame / vct_gi_passes visited flagged segments only */
 int  vct_mask_parity(vct_ctx*);                            /* which of the two segment masks the NEXT frame writes (0/1): a CUDA graph that
                                                               captured frames must be replayed at the parity it was captured at */

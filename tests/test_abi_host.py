@@ -57,7 +57,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     """Compile the public header with gcc (plain C) and compare sizeof/offsetof with the ctypes mirror."""
     import subprocess
     structs = {"vct_config": P.Config, "vct_light": P.Light, "vct_material": P.Material, "vct_voxelize_info": P.VoxelizeInfo,
-               "vct_cone_settings": P.ConeSettings, "vct_frame_params": P.FrameParams, "vct_timings": P.Timings}
+               "vct_cone_settings": P.ConeSettings, "vct_frame_params": P.FrameParams, "vct_timings": P.Timings, "vct_peer": P.Peer}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "vct_b200.h")}"', "int main(void){"]
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -81,6 +81,7 @@ def test_config2_bunny_128_occupancy_bit_exact():
 
 
 @pytest.mark.skipif(not (S.baked_available("sponza_pbr") and S.baked_available("nanosuit")), reason="baked Sponza / nanosuit missing")
+@pytest.mark.timeout(600)
 def test_config4_animated_warped_temporal_512():
     """Sponza + two animated nanosuits (Application.cpp:97-116), 512^3 grid, warp map regenerated every frame (:235-577),
     temporal radiance filter (transferVoxels.comp:55-62): four frames at 60 Hz, every pyramid level bit for bit; 480x270 frame."""
@@ -108,6 +109,7 @@ def test_config4_animated_warped_temporal_512():
         g.close()
 
 
+@pytest.mark.timeout(400)
 def test_config5_soup_1m_triangles_512():
     """Synthetic soup, 1 Mi triangles (sigma = 1.5 voxels at 512^3), NaN tangents, 1x1 white texture: volumes bit for bit."""
     from vct_b200.pipeline import Pipeline
@@ -124,6 +126,7 @@ def test_config5_soup_1m_triangles_512():
         g.close()
 
 
+@pytest.mark.timeout(600)
 def test_config5_soup_capacity_8m_triangles():
     """Capacity: 8 Mi triangles into 512^3 (queues, setups and the fragment buffer sized from the triangle count), no overflow;
     counters equal to the oracle's voxeliser.  (The 64 Mi-triangle run is tools/soup_capacity.py -> profiles/.)"""

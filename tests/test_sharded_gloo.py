@@ -94,6 +94,13 @@ def test_partition_maths():
         SH.level_chunks(64, 6, 8)                 # coarsest level 2^3 is thinner than 8 slabs
     with pytest.raises(ValueError):
         SH.slab_range(100, 8, 0)
+    # screen tiles of the sharded cone trace (cone_trace.cu ensure_trace_tiles): 64x64 pixels, diagonal stripes, every tile owned once
+    for (w, h, n) in ((1920, 1080, 8), (3840, 2160, 8), (320, 240, 2), (100, 70, 4)):
+        per = [SH.screen_tiles(w, h, n, r) for r in range(n)]
+        allt = sorted(t for p in per for t in p)
+        assert allt == sorted((x, y) for y in range(0, h, 64) for x in range(0, w, 64)), (w, h, n)
+        assert max(len(p) for p in per) - min(len(p) for p in per) <= max(1, -(-h // 64)), (w, h, n)      # balanced to within one tile per row
+    assert SH.tile_owner(3, 2, 4) == 1 and SH.screen_tiles(128, 128, 2, 0) == [(0, 0), (64, 64)]
     band, bands = SH.image_bands(1080, 8)
     assert band == 136 and bands[0] == (0, 136) and bands[7] == (952, 1080) and sum(b - a for a, b in bands) == 1080
     band, bands = SH.image_bands(2160, 8)

@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
-"""Multi-GPU parity (run under torchrun, one rank per GPU): the z-slab sharded frame of vct_b200/sharded.py must give
-exactly the words of the single-GPU frame — every level of the radiance pyramid after the NCCL all-gather, the
-voxelise counters summed over ranks, and the final image after the band all-gather.
+"""Multi-GPU parity (run under torchrun, one rank per GPU): the z-slab sharded frame (exchange inside the library, csrc/exchange.cu)
+must give exactly the words of the single-GPU frame — every level of the traced pyramid on rank 0 after the exchange, the
+voxelise counters summed over ranks, and the final image assembled in rank 0's buffer from every rank's screen tiles.
 
 usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-           tools/sharded_parity.py [room|sponza|sponza512]
+           tools/sharded_parity.py [room|sponza|sponza512|animated]     (animated: config 4 at 256^3 / 960x540, whole frames, moving actors)
 Prints one JSON line on rank 0 and exits non-zero on any mismatch."""
 import json
 import os
@@ -24,14 +24,12 @@ from vct_b200.sharded import ShardedFrame  # noqa: E402
 
 
 def workload(name):
+    """-> (scene, params, D, L, S, W, H, Workload or None)"""
     if name == "room":
-        return S.room_scene(), S.room_params(320, 240), 64, 5, 512, 320, 240
-    import bench
-    if name == "sponza":
-        sc, p, D, W, H, _ = bench.build_workload()
-        return sc, p, D, bench.LEVELS, bench.SHADOW, W, H
-    sc, p, D, W, H, _ = bench.build_workload(3840, 2160, 512)
-    return sc, p, D, bench.LEVELS, bench.SHADOW, W, H
+        return S.room_scene(), S.room_params(320, 240), 64, 5, 512, 320, 240, None
+    from vct_b200.workloads import Workload
+    w = Workload(3) if name == "sponza" else Workload(3, 3840, 2160, 512) if name == "sponza512" else Workload(4, 960, 540, 256)
+    return w.scene, w.params, w.D, w.L, w.S, w.W, w.H, (w if name == "animated" else None)
 
 
 def main():
@@ -39,18 +37,19 @@ def main():
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    sc, p, D, L, SS, W, H = workload(name)
+    sc, p, D, L, SS, W, H, wl = workload(name)
+    frames = 4 if wl else 3
     g = Pipeline(sc, D, L, SS, W, H, device=local, rank=rank, world_size=world)
-    fr = ShardedFrame(g, p, world, rank)
+    fr = ShardedFrame(g, p, world, rank, workload=wl)
     fr.producers()
-    for _ in range(3):                       # later frames: steady state (sparse exchange, publish masks, temporal history) also matches
+    for _ in range(frames):                  # later frames: steady state (sparse exchange, publish masks, temporal history) also matches
         fr.step()
     torch.cuda.synchronize()
     info = g.counters()
     cnt = torch.tensor([info.total_fragments, info.unique_voxels], device="cuda", dtype=torch.int64)
     mx = torch.tensor([info.max_fragments_per_voxel], device="cuda", dtype=torch.int64)
     dist.all_reduce(cnt); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    ok, report = True, {"workload": name, "world": world, "exchange": fr.describe()[:120]}
+    ok, report = True, {"workload": name, "world": world, "exchange": fr.describe()[:100]}
     if rank == 0:
         which = P.VOL_RADIANCE if p.draw_radiance else P.VOL_COLOR
         sharded_levels = [g.read_volume(which, l) for l in range(g.L)]
@@ -61,8 +60,13 @@ def main():
             if p.warp_texture:
                 one.occupancy(p); one.warpmap(p)
             one.gbuffer(p)
-            for _ in range(3):
-                one.gi_passes(p)
+            for k in range(frames):
+                if wl:
+                    for actor, model in wl.models(k):
+                        one.set_actor_transform(actor, model)
+                    one.frame(p)
+                else:
+                    one.gi_passes(p)
             ref_info = one.counters()
             for l in range(one.L):
                 same = np.array_equal(sharded_levels[l], one.read_volume(which, l))

@@ -4,7 +4,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
 #include <exception>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include <stdlib.h>
 
@@ -218,7 +222,7 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     return 0;
 }
 
-enum { EV_START, EV_SHADOW, EV_WARP, EV_CLEAR, EV_VOXEL, EV_TRANSFER, EV_INJECT, EV_MIP, EV_GBUF, EV_TRACE, EV_COUNT };
+enum { EV_START, EV_SHADOW, EV_WARP, EV_CLEAR, EV_VOXEL, EV_TRANSFER, EV_INJECT, EV_MIP, EV_XCHG, EV_GBUF, EV_TRACE, EV_COUNT };
 
 struct Graph { vct_ctx* c; bool timed; int rec(int e) { if (timed && c->profiling >= 1) { cudaError_t r = cudaEventRecord(c->ev[e], c->stream); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } } return 0; } };
 
@@ -265,15 +269,20 @@ int gi_body(vct_ctx* c, Graph& g, bool cleared_by_frame_begin = false) {
         vct_prof_mark(c, "memset");
         if (vctk_clear_voxels(c, true) || g.rec(EV_CLEAR)) return 1;
     }
-    if (vctk_voxelize(c, false, true) || g.rec(EV_VOXEL)) return 1;
-    if ((sparse ? vctk_transfer_masked(c) : vctk_transfer(c)) || g.rec(EV_TRANSFER)) return 1;
+    // sparse frame, temporal filter off, deterministic raster voxeliser: the resolve kernel does transferVoxels for its voxels
+    bool transfer_done = false;
+    if (vctk_voxelize(c, false, true, sparse && !p.temporal_filter_radiance, &transfer_done) || g.rec(EV_VOXEL)) return 1;
+    if (!transfer_done && (sparse ? vctk_transfer_masked(c) : vctk_transfer(c))) return 1;
+    if (g.rec(EV_TRANSFER)) return 1;
     if (vctk_inject(c)) return 1;
     if (p.voxel_fill_holes) { if (ensure_scratch(c) || vctk_fill_holes(c)) return 1; }
     if (g.rec(EV_INJECT)) return 1;
     // single GPU: the chain that the cone tracer samples is written straight into its texture array
-    if (single && !p.draw_radiance && ensure_color_texture(c)) return 1;
+    // (sharded with attached peers: likewise for the own slab; the exchange publishes the remote slabs)
+    const bool direct = single || vctk_xchg_ready(c);
+    if (direct && !p.draw_radiance && ensure_color_texture(c)) return 1;
     const int which[2] = {VCT_VOL_RADIANCE, VCT_VOL_COLOR};
-    const int publish[2] = {single && p.draw_radiance, single && !p.draw_radiance};
+    const int publish[2] = {direct && p.draw_radiance, direct && !p.draw_radiance};
     if (vctk_mip_chains(c, n_chains, which, publish, 0, sparse)) return 1;   // both pyramids, one launch
     // this frame's mask bounds the support of all three level-0 volumes (dense temporal frames: k_transfer flagged the history)
     c->seg_valid = maskable;
@@ -283,15 +292,59 @@ int gi_body(vct_ctx* c, Graph& g, bool cleared_by_frame_begin = false) {
     return g.rec(EV_MIP);
 }
 
+
+// ---- single-process multi-GPU (vct_config.n_devices > 1): the handle the host holds is rank 0's context; `group` lists the other
+// ranks' contexts.  Every call that changes state or enqueues work runs on all of them, each on its own worker thread (a frame is
+// ~20 launches per device: issued one device after the other they would cost more host time than the sharded frame takes on the
+// devices).  Nothing in a frame call blocks the host on a device, which matters: a rank's unpack kernel spins until its peers'
+// push kernels have run, and those are launched by the other workers.
+struct GroupWorker {
+    std::thread th; std::mutex m; std::condition_variable cv;
+    std::function<int()> job; bool has_job = false, quit = false, done = true; int rc = 0;
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            std::function<int()> j = std::move(job); has_job = false;
+            lk.unlock(); const int r = j(); lk.lock();
+            rc = r; done = true; cv.notify_all();
+        }
+    }
+};
+struct Group { std::vector<GroupWorker*> workers; };
+template <class F> int group_run(vct_ctx* leader, F f) {
+    Group* g = reinterpret_cast<Group*>(leader->group_state);
+    leader->in_fan = true;
+    for (size_t i = 0; i < leader->group.size(); ++i) {
+        GroupWorker* w = g->workers[i]; vct_ctx* m = leader->group[i];
+        std::lock_guard<std::mutex> lk(w->m);
+        w->job = [f, m]() { return f(m); }; w->has_job = true; w->done = false; w->cv.notify_all();
+    }
+    int rc = f(leader);
+    for (size_t i = 0; i < leader->group.size(); ++i) {
+        GroupWorker* w = g->workers[i];
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->done; });
+        if (w->rc && !rc) { rc = w->rc; leader->error = "rank " + std::to_string(i + 1) + ": " + leader->group[i]->error; }
+    }
+    leader->in_fan = false;
+    return rc;
+}
+#define VCT_FAN(c, expr) do { if ((c) && !(c)->group.empty() && !(c)->in_fan) return group_run((c), [=](vct_ctx* c) { return (expr); }); } while (0)
+#define VCT_NO_GROUP(c, what) do { if ((c) && !(c)->group.empty()) return fail((c), what ": not available on a multi-device handle (vct_config.n_devices > 1)"); } while (0)
+
 }  // namespace
 
 extern "C" {
 
 const char* vct_last_error(const vct_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
 
+static int create_group(const vct_config* cfg, vct_ctx** out);
 int vct_create(const vct_config* cfg, vct_ctx** out) {
     if (!cfg || !out) { g_create_error = "vct_create: null argument"; return 1; }
     *out = nullptr;
+    if (cfg->n_devices > 1) return create_group(cfg, out);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { g_create_error = std::string("vct_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback"; return 1; }
@@ -315,7 +368,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * 8) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
-        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
+        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, (size_t)(c->S / 4 + 1) * (c->S / 4 + 1) * 8) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
         alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
@@ -330,14 +383,64 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     return 0;
 }
 
+// vct_config.n_devices > 1: one context per device (rank i on devices[i]), peer access both ways, slab exchange attached
+static int create_group(const vct_config* cfg, vct_ctx** out) {
+    const int n = cfg->n_devices;
+    if (n > VCT_MAX_PEERS) { g_create_error = "vct_create: n_devices must be <= 8"; return 1; }
+    std::vector<vct_ctx*> ctx((size_t)n, nullptr);
+    auto undo = [&](const std::string& why) { for (vct_ctx* m : ctx) if (m) vct_destroy(m); g_create_error = why; return 1; };
+    for (int r = 0; r < n; ++r) {
+        vct_config one = *cfg;
+        one.n_devices = 0; one.devices = nullptr; one.device = cfg->devices ? cfg->devices[r] : r; one.rank = r; one.world_size = n;
+        if (vct_create(&one, &ctx[r])) return undo("vct_create: device " + std::to_string(one.device) + ": " + g_create_error);
+    }
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            if (a == b) continue;
+            cudaSetDevice(ctx[a]->cfg.device);
+            int can = 0; cudaDeviceCanAccessPeer(&can, ctx[a]->cfg.device, ctx[b]->cfg.device);
+            if (!can) return undo("vct_create: devices " + std::to_string(ctx[a]->cfg.device) + " and " + std::to_string(ctx[b]->cfg.device) + " have no peer access (NVLink / PCIe P2P)");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctx[b]->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return undo(std::string("vct_create: cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    for (int r = 0; r < n; ++r) if (vct_exchange_setup(ctx[r])) return undo("vct_create: slab exchange: " + ctx[r]->error);
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            if (a == b) continue;
+            vct_peer pb; vct_exchange_local(ctx[b], &pb);
+            if (vct_exchange_attach(ctx[a], b, &pb)) return undo("vct_create: slab exchange: " + ctx[a]->error);
+        }
+    vct_ctx* leader = ctx[0];
+    Group* g = new Group();
+    for (int r = 1; r < n; ++r) {
+        leader->group.push_back(ctx[r]);
+        GroupWorker* w = new GroupWorker();
+        w->th = std::thread([w] { w->loop(); });
+        g->workers.push_back(w);
+    }
+    leader->group_state = g;
+    *out = leader;
+    return 0;
+}
+
 int vct_destroy(vct_ctx* c) {
     if (!c) return 0;
+    if (c->group_state) {
+        Group* g = reinterpret_cast<Group*>(c->group_state);
+        for (GroupWorker* w : g->workers) { { std::lock_guard<std::mutex> lk(w->m); w->quit = true; w->cv.notify_all(); } w->th.join(); delete w; }
+        delete g; c->group_state = nullptr;
+        for (vct_ctx* m : c->group) { cudaSetDevice(m->cfg.device); if (m->stream) cudaStreamSynchronize(m->stream); }
+        cudaSetDevice(c->cfg.device); if (c->stream) cudaStreamSynchronize(c->stream);
+        for (vct_ctx* m : c->group) vct_destroy(m);
+        c->group.clear();
+    }
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
     vctk_xchg_free(c);
-    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, (void*)c->d_warp_scratch,
-                    c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters,
+    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, c->d_shadow_mm, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, (void*)c->d_warp_scratch,
+                    c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters, (void*)c->d_trace_tiles,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_wpos,
                     (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})
         cudaFree(p);
@@ -356,7 +459,7 @@ int vct_destroy(vct_ctx* c) {
 }
 
 // VCT::remake (reference src/Application.h:118-129): destroy + create with clamped level count
-int vct_remake(vct_ctx* c, int dim, int levels) {
+int vct_remake(vct_ctx* c, int dim, int levels) { VCT_NO_GROUP(c, "vct_remake");
     if (!c) return 1;
     if (dim < 4 || (dim & (dim - 1)) || dim > 1024) return fail(c, "vct_remake: dim must be a power of two in [4,1024]");
     if (c->cfg.world_size > 1) {
@@ -371,7 +474,7 @@ int vct_remake(vct_ctx* c, int dim, int levels) {
     return make_volumes(c);
 }
 
-int vct_upload_mesh(vct_ctx* c, int actor, const void* vertices, size_t n_vertices, size_t stride, const uint32_t* indices, size_t n_indices, const int32_t* material_of_triangle) {
+int vct_upload_mesh(vct_ctx* c, int actor, const void* vertices, size_t n_vertices, size_t stride, const uint32_t* indices, size_t n_indices, const int32_t* material_of_triangle) { VCT_FAN(c, vct_upload_mesh(c, actor, vertices, n_vertices, stride, indices, n_indices, material_of_triangle));
     if (!c) return 1;
     if (stride < 56 || !vertices || !indices || n_indices % 3 || actor < 0) return fail(c, "vct_upload_mesh: bad arguments (Vertex stride is 56 bytes, src/Graphics/Mesh.h:72-76)");
     for (auto& m : c->meshes) if (m.actor == actor) return fail(c, "vct_upload_mesh: actor already has a mesh");
@@ -399,7 +502,7 @@ int vct_upload_mesh(vct_ctx* c, int actor, const void* vertices, size_t n_vertic
     }
 }
 
-int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels, int levels, const void* pixels) {
+int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels, int levels, const void* pixels) { VCT_FAN(c, vct_upload_texture(c, tex, width, height, channels, levels, pixels));
     if (!c) return 1;
     if (tex < 0 || tex >= VCT_MAX_TEXTURES || width < 1 || height < 1 || !(channels == 1 || channels == 3 || channels == 4) || levels < 1 || levels > 16 || !pixels)
         return fail(c, "vct_upload_texture: bad arguments");
@@ -421,7 +524,7 @@ int vct_upload_texture(vct_ctx* c, int tex, int width, int height, int channels,
     return 0;
 }
 
-int vct_set_material(vct_ctx* c, int material, const vct_material* m) {
+int vct_set_material(vct_ctx* c, int material, const vct_material* m) { VCT_FAN(c, vct_set_material(c, material, m));
     if (!c) return 1;
     if (material < 0 || material >= VCT_MAX_MATERIALS || !m) return fail(c, "vct_set_material: bad arguments");
     for (int t : {m->diffuse_tex, m->specular_tex, m->normal_tex, m->roughness_tex, m->metallic_tex, m->alpha_tex})
@@ -434,14 +537,14 @@ int vct_set_material(vct_ctx* c, int material, const vct_material* m) {
     return 0;
 }
 
-int vct_set_actor_transform(vct_ctx* c, int actor, const float model[16]) {
+int vct_set_actor_transform(vct_ctx* c, int actor, const float model[16]) { VCT_FAN(c, vct_set_actor_transform(c, actor, model));
     if (!c) return 1;
     if (!model) return fail(c, "vct_set_actor_transform: null matrix");
     for (auto& m : c->meshes) if (m.actor == actor) { std::memcpy(m.model.m, model, 64); return 0; }
     return fail(c, "vct_set_actor_transform: unknown actor");
 }
 
-int vct_set_lights(vct_ctx* c, const vct_light* lights, int n) {
+int vct_set_lights(vct_ctx* c, const vct_light* lights, int n) { VCT_FAN(c, vct_set_lights(c, lights, n));
     if (!c) return 1;
     if (n < 0 || n > 8 || (n && !lights)) return fail(c, "vct_set_lights: 0..8 lights");
     std::memset(c->h_lights, 0, sizeof c->h_lights);
@@ -468,22 +571,22 @@ static int overflow_seen(vct_ctx* c) {
                "raise vct_config.max_fragments; this call was not executed, the next one will be";
     return 1;
 }
-int vct_shadowmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_shadowmap(c); }
-int vct_occupancy(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_voxelize(c, true); }
-int vct_warpmap(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_warpmap(c); }
-int vct_voxelize(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; c->seg_valid = false; return zero_info(c) || vctk_transform_vertices(c) || vctk_clear_voxels(c) || vctk_voxelize(c, false); }
-int vct_transfer(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; c->seg_valid = false; return vctk_transfer(c); }
-int vct_inject(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; c->seg_valid = false; return vctk_inject(c); }
-int vct_fill_holes(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; c->seg_valid = false; return ensure_scratch(c) || vctk_fill_holes(c); }
-int vct_gbuffer(vct_ctx* c, const vct_frame_params* p) { PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_visibility(c); }
-int vct_cone_trace(vct_ctx* c, const vct_frame_params* p) {
+int vct_shadowmap(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_shadowmap(c, p)); PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_shadowmap(c) || vctk_shadow_minmax(c); }
+int vct_occupancy(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_occupancy(c, p)); PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_voxelize(c, true); }
+int vct_warpmap(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_warpmap(c, p)); PASS_PROLOGUE; return vctk_warpmap(c); }
+int vct_voxelize(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_voxelize(c, p)); PASS_PROLOGUE; c->seg_valid = false; return zero_info(c) || vctk_transform_vertices(c) || vctk_clear_voxels(c) || vctk_voxelize(c, false); }
+int vct_transfer(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_transfer(c, p)); PASS_PROLOGUE; c->seg_valid = false; return vctk_transfer(c); }
+int vct_inject(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_inject(c, p)); PASS_PROLOGUE; c->seg_valid = false; return vctk_inject(c); }
+int vct_fill_holes(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_fill_holes(c, p)); PASS_PROLOGUE; c->seg_valid = false; return ensure_scratch(c) || vctk_fill_holes(c); }
+int vct_gbuffer(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_gbuffer(c, p)); PASS_PROLOGUE; return vctk_transform_vertices(c) || vctk_visibility(c); }
+int vct_cone_trace(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_cone_trace(c, p));
     PASS_PROLOGUE;
     if (!p->draw_radiance && !c->color_arr) { if (ensure_color_texture(c) || vctk_publish(c, VCT_VOL_COLOR)) return 1; }
     VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
     vct_prof_mark(c, "memset");
     return vctk_cone_trace(c);
 }
-int vct_mip(vct_ctx* c, int which) {
+int vct_mip(vct_ctx* c, int which) { VCT_FAN(c, vct_mip(c, which));
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);
     if (which != VCT_VOL_RADIANCE && which != VCT_VOL_COLOR) return fail(c, "vct_mip: radiance or colour volume only");
@@ -494,7 +597,7 @@ int vct_mip(vct_ctx* c, int which) {
 // filterRadiance.comp's `kernelMode` uniform (:9-13): 0 = BOX2 (what the host dispatches, = vct_mip), 1 = BOX3 (27 taps x 0.037),
 // 2 = CUBE (7 axial taps x 0.143); the reference declares the uniform and never sets it.  BOX3 / CUBE read across 2x2x2 cell borders,
 // so they need the whole source level: single GPU only.
-int vct_mip_kernel(vct_ctx* c, int which, int kernel_mode) {
+int vct_mip_kernel(vct_ctx* c, int which, int kernel_mode) { VCT_FAN(c, vct_mip_kernel(c, which, kernel_mode));
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);
     if (which != VCT_VOL_RADIANCE && which != VCT_VOL_COLOR) return fail(c, "vct_mip_kernel: radiance or colour volume only");
@@ -504,7 +607,7 @@ int vct_mip_kernel(vct_ctx* c, int which, int kernel_mode) {
     const bool publish = c->cfg.world_size <= 1 && !(which == VCT_VOL_COLOR && !c->color_arr);
     return vctk_mip(c, which, kernel_mode, publish);
 }
-int vct_exchange(vct_ctx* c) {
+int vct_exchange(vct_ctx* c) { VCT_NO_GROUP(c, "vct_exchange");
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);
     vct_prof_begin(c);
@@ -513,49 +616,65 @@ int vct_exchange(vct_ctx* c) {
     return vctk_publish(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR);
 }
 
-// ---- sparse slab exchange over peer memory (exchange.cu); the caller (vct_b200/sharded.py, or the host application's
-// process launcher) only moves the 64-byte cudaIpc handles between the ranks.
-int vct_exchange_setup(vct_ctx* c) { if (!c) return 1; cudaSetDevice(c->cfg.device); return vctk_xchg_setup(c); }
-int vct_exchange_export(vct_ctx* c, void* handle64) {
-    if (!c || !handle64) return 1;
+// ---- slab exchange over peer memory (exchange.cu); the caller only moves the cudaIpc handle blobs between the ranks once
+int vct_exchange_setup(vct_ctx* c) { VCT_NO_GROUP(c, "vct_exchange_setup"); if (!c) return 1; cudaSetDevice(c->cfg.device); return vctk_xchg_setup(c); }
+int vct_exchange_export(vct_ctx* c, void* handle) {
+    if (!c || !handle) return 1;
     cudaSetDevice(c->cfg.device);
     if (!c->d_xchg) return fail(c, "vct_exchange_export: call vct_exchange_setup first");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
-    cudaIpcMemHandle_t h;
-    VCT_CHECK(c, cudaIpcGetMemHandle(&h, c->d_xchg));
-    std::memcpy(handle64, &h, 64);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64 && VCT_EXCHANGE_HANDLE_BYTES >= 4 * 64, "ipc handle size");
+    void* ptrs[4] = {c->d_xchg, c->d_radiance, c->d_color, c->d_image};
+    for (int i = 0; i < 4; ++i) {
+        cudaIpcMemHandle_t h;
+        VCT_CHECK(c, cudaIpcGetMemHandle(&h, ptrs[i]));
+        std::memcpy((char*)handle + 64 * i, &h, 64);
+    }
     return 0;
 }
-int vct_exchange_import(vct_ctx* c, int rank, const void* handle64) {
-    if (!c || !handle64) return 1;
+int vct_exchange_import(vct_ctx* c, int rank, const void* handle) {
+    if (!c || !handle) return 1;
     cudaSetDevice(c->cfg.device);
     if (!c->d_xchg) return fail(c, "vct_exchange_import: call vct_exchange_setup first");
     if (rank < 0 || rank >= c->cfg.world_size) return fail(c, "vct_exchange_import: bad rank");
     if (rank == c->cfg.rank) return 0;
-    cudaIpcMemHandle_t h; std::memcpy(&h, handle64, 64);
-    void* p = nullptr;
-    VCT_CHECK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    c->peer_xchg[rank] = p;
+    if (c->peer[rank].staging) return fail(c, "vct_exchange_import: this rank is already attached");
+    void* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 4; ++i) {
+        cudaIpcMemHandle_t h; std::memcpy(&h, (const char*)handle + 64 * i, 64);
+        VCT_CHECK(c, cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->peer[rank].staging = ptrs[0]; c->peer[rank].radiance = ptrs[1]; c->peer[rank].color = ptrs[2]; c->peer[rank].image = ptrs[3];
+    c->peer_ipc[rank] = true; c->peers_attached++;
+    return 0;
+}
+int vct_exchange_local(vct_ctx* c, vct_peer* out) {
+    if (!c || !out) return 1;
+    if (!c->d_xchg) return fail(c, "vct_exchange_local: call vct_exchange_setup first");
+    *out = c->peer[c->cfg.rank];
+    return 0;
+}
+int vct_exchange_attach(vct_ctx* c, int rank, const vct_peer* peer) {
+    if (!c || !peer) return 1;
+    if (!c->d_xchg) return fail(c, "vct_exchange_attach: call vct_exchange_setup first");
+    if (rank < 0 || rank >= c->cfg.world_size || !peer->staging || !peer->radiance || !peer->color || !peer->image) return fail(c, "vct_exchange_attach: bad arguments");
+    if (rank == c->cfg.rank) return 0;
+    if (c->peer[rank].staging) return fail(c, "vct_exchange_attach: this rank is already attached");
+    c->peer[rank] = *peer; c->peer_ipc[rank] = false; c->peers_attached++;
     return 0;
 }
 int vct_frame_was_sparse(vct_ctx* c) { return c && c->last_frame_sparse ? 1 : 0; }
 int vct_mask_parity(vct_ctx* c) { return c ? c->seg_cur : 0; }
-int vct_exchange_push(vct_ctx* c) {
-    if (!c) return 1;
-    cudaSetDevice(c->cfg.device);
-    vct_prof_begin(c);
-    if (!c->last_frame_sparse) return fail(c, "vct_exchange_push: the last frame was dense; all-gather the levels and call vct_exchange");
-    return vctk_xchg_push(c);
-}
-int vct_exchange_unpack(vct_ctx* c) {
-    if (!c) return 1;
-    cudaSetDevice(c->cfg.device);
-    vct_prof_begin(c);
-    const bool rad = c->h_fc.p.draw_radiance != 0;
-    return vctk_xchg_unpack(c) || vctk_publish_upper(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR);
+
+// tail of a sharded frame with attached peers: exchange, (visibility), cone trace of the own tiles, image hand-over to rank 0
+static int sharded_tail(vct_ctx* c, Graph& g, bool with_visibility) {
+    if (vctk_xchg_frame(c, !c->last_frame_sparse) || g.rec(EV_XCHG)) return 1;
+    if (with_visibility && vctk_visibility(c)) return 1;
+    if (g.rec(EV_GBUF)) return 1;
+    if (vctk_cone_trace(c) || vctk_xchg_image_sync(c)) return 1;
+    return g.rec(EV_TRACE);
 }
 
-int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
+int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_gi_passes(c, p));
     PASS_PROLOGUE;
     Graph g{c, true};
     if (g.rec(EV_START) || g.rec(EV_SHADOW) || g.rec(EV_WARP)) return 1;
@@ -563,32 +682,32 @@ int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) {
     const bool fused_begin = plan_frame(c).sparse && c->profiling < 2 && c->n_vertices > 0;
     if (fused_begin ? vctk_frame_begin_masked(c) : vctk_transform_vertices(c)) return 1;
     if (gi_body(c, g, fused_begin)) return 1;
-    if (c->cfg.world_size > 1) return 0;                      // caller all-gathers, then vct_exchange + vct_cone_trace
-    if (g.rec(EV_GBUF)) return 1;
+    if (c->cfg.world_size > 1) return vctk_xchg_ready(c) ? sharded_tail(c, g, false) : 0;   // no peers: caller all-gathers, then vct_exchange + vct_cone_trace
+    if (g.rec(EV_XCHG) || g.rec(EV_GBUF)) return 1;
     if (vctk_cone_trace(c)) return 1;                         // cone_steps was zeroed by gi_body's clear
     return g.rec(EV_TRACE);
 }
 
 // Application::render in the reference's pass order (src/Application.cpp:196-1085)
-int vct_frame(vct_ctx* c, const vct_frame_params* p) {
+int vct_frame(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_frame(c, p));
     PASS_PROLOGUE;
     Graph g{c, true};
     if (g.rec(EV_START)) return 1;
-    if (vctk_transform_vertices(c) || vctk_shadowmap(c) || g.rec(EV_SHADOW)) return 1;
+    if (vctk_transform_vertices(c) || vctk_shadowmap(c) || vctk_shadow_minmax(c) || g.rec(EV_SHADOW)) return 1;
     if (p->warp_texture) { if (vctk_voxelize(c, true) || vctk_warpmap(c)) return 1; }
     if (g.rec(EV_WARP)) return 1;
     if (gi_body(c, g)) return 1;
-    if (c->cfg.world_size > 1) return 0;
-    if (vctk_visibility(c) || g.rec(EV_GBUF)) return 1;
+    if (c->cfg.world_size > 1) return vctk_xchg_ready(c) ? sharded_tail(c, g, true) : 0;
+    if (g.rec(EV_XCHG) || vctk_visibility(c) || g.rec(EV_GBUF)) return 1;
     if (vctk_cone_trace(c)) return 1;                         // cone_steps was zeroed by gi_body's clear
     return g.rec(EV_TRACE);
 }
 
 // dead-shader equivalents
-int vct_set_voxel_opacity(vct_ctx* c, float o) { if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return zero_info(c) || vctk_set_voxel_opacity(c, o); }
-int vct_temporal_radiance_filter(vct_ctx* c, float d) { if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return vctk_temporal_radiance_filter(c, d); }
-int vct_filter3d(vct_ctx* c, int which, int src_level) { if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return vctk_filter3d(c, which, src_level); }
-int vct_normalize_voxels_f16(vct_ctx* c, void* col, void* nrm, float o) { if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return zero_info(c) || vctk_normalize_voxels_f16(c, col, nrm, o); }
+int vct_set_voxel_opacity(vct_ctx* c, float o) { VCT_FAN(c, vct_set_voxel_opacity(c, o)); if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return zero_info(c) || vctk_set_voxel_opacity(c, o); }
+int vct_temporal_radiance_filter(vct_ctx* c, float d) { VCT_FAN(c, vct_temporal_radiance_filter(c, d)); if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return vctk_temporal_radiance_filter(c, d); }
+int vct_filter3d(vct_ctx* c, int which, int src_level) { VCT_FAN(c, vct_filter3d(c, which, src_level)); if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return vctk_filter3d(c, which, src_level); }
+int vct_normalize_voxels_f16(vct_ctx* c, void* col, void* nrm, float o) { VCT_NO_GROUP(c, "vct_normalize_voxels_f16"); if (!c) return 1; cudaSetDevice(c->cfg.device); c->seg_valid = false; return zero_info(c) || vctk_normalize_voxels_f16(c, col, nrm, o); }
 
 // ------------------------------------------------------------------------------------------ outputs
 static int volume_ptr(vct_ctx* c, int which, int level, void** ptr, size_t* bytes) {
@@ -608,15 +727,30 @@ static int volume_ptr(vct_ctx* c, int which, int level, void** ptr, size_t* byte
     }
     return fail(c, "unknown volume");
 }
-int vct_sync(vct_ctx* c) { if (!c) return 1; cudaSetDevice(c->cfg.device); VCT_CHECK(c, cudaStreamSynchronize(c->stream)); return 0; }
+int vct_sync(vct_ctx* c) { VCT_FAN(c, vct_sync(c)); if (!c) return 1; cudaSetDevice(c->cfg.device); VCT_CHECK(c, cudaStreamSynchronize(c->stream)); return 0; }
 int vct_read_volume(vct_ctx* c, int which, int level, void* out) {
     if (!c || !out) return 1;
+    if (!c->group.empty() && (which == VCT_VOL_COLOR || which == VCT_VOL_NORMAL || which == VCT_VOL_RADIANCE)) {
+        // multi-device handle: every rank holds its z-slab of a volume (the traced pyramid is complete everywhere after a frame, the
+        // others are not): assemble the level from the ranks' slabs
+        void* p0; size_t bytes; if (volume_ptr(c, which, level, &p0, &bytes)) return 1;
+        const int ws = (int)c->group.size() + 1, d = level_dim(c->D, level);
+        if (d % ws) { cudaSetDevice(c->cfg.device); VCT_CHECK(c, cudaMemcpyAsync(out, p0, bytes, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream)); return 0; }
+        const size_t chunk = bytes / ws;
+        for (int r = 0; r < ws; ++r) {
+            vct_ctx* m = r ? c->group[r - 1] : c;
+            void* pm; size_t bm; if (volume_ptr(m, which, level, &pm, &bm)) return fail(c, m->error.c_str());
+            cudaSetDevice(m->cfg.device);
+            VCT_CHECK(c, cudaMemcpyAsync((char*)out + r * chunk, (char*)pm + r * chunk, chunk, cudaMemcpyDeviceToHost, m->stream)); VCT_CHECK(c, cudaStreamSynchronize(m->stream));
+        }
+        return 0;
+    }
     cudaSetDevice(c->cfg.device);
     void* p; size_t b; if (volume_ptr(c, which, level, &p, &b)) return 1;
     VCT_CHECK(c, cudaMemcpyAsync(out, p, b, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
-int vct_write_volume(vct_ctx* c, int which, int level, const void* in) {
+int vct_write_volume(vct_ctx* c, int which, int level, const void* in) { VCT_FAN(c, vct_write_volume(c, which, level, in));
     if (!c || !in) return 1;
     cudaSetDevice(c->cfg.device);
     void* p; size_t b; if (volume_ptr(c, which, level, &p, &b)) return 1;
@@ -632,7 +766,7 @@ int vct_read_image(vct_ctx* c, void* rgba8) {
 }
 // Pipelined read-back: the copy of this frame's image runs on a second stream while the library stream goes on with the next
 // frame's voxel passes; only the next cone trace (the next writer of the image) waits for it.
-int vct_read_image_async(vct_ctx* c, void* pinned_rgba8) {
+int vct_read_image_async(vct_ctx* c, void* pinned_rgba8) { VCT_NO_GROUP(c, "vct_read_image_async");
     if (!c || !pinned_rgba8) return 1;
     cudaSetDevice(c->cfg.device);
     VCT_CHECK(c, cudaEventRecord(c->ev_image_ready, c->stream));
@@ -655,10 +789,12 @@ int vct_read_shadowmap(vct_ctx* c, float* d) {
     VCT_CHECK(c, cudaMemcpyAsync(d, c->d_shadow, (size_t)c->S * c->S * 4, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
-int vct_write_shadowmap(vct_ctx* c, const float* d) {
+int vct_write_shadowmap(vct_ctx* c, const float* d) { VCT_FAN(c, vct_write_shadowmap(c, d));
     if (!c || !d) return 1;
     cudaSetDevice(c->cfg.device);
-    VCT_CHECK(c, cudaMemcpyAsync(c->d_shadow, d, (size_t)c->S * c->S * 4, cudaMemcpyHostToDevice, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    VCT_CHECK(c, cudaMemcpyAsync(c->d_shadow, d, (size_t)c->S * c->S * 4, cudaMemcpyHostToDevice, c->stream));
+    if (vctk_shadow_minmax(c)) return 1;
+    VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 int vct_read_visibility(vct_ctx* c, uint64_t* v) {
@@ -677,6 +813,11 @@ int vct_get_counters(vct_ctx* c, vct_voxelize_info* info) {
     cudaSetDevice(c->cfg.device);
     if (fetch_counters(c)) return 1;
     info->total_fragments = c->h_counters.total_fragments; info->unique_voxels = c->h_counters.unique_voxels; info->max_fragments_per_voxel = c->h_counters.max_fragments_per_voxel;
+    for (vct_ctx* m : c->group) {                              // multi-device handle: a voxel's fragments all land on the rank that owns its slab
+        vct_voxelize_info mi;
+        if (vct_get_counters(m, &mi)) return fail(c, m->error.c_str());
+        info->total_fragments += mi.total_fragments; info->unique_voxels += mi.unique_voxels; info->max_fragments_per_voxel = std::max(info->max_fragments_per_voxel, mi.max_fragments_per_voxel);
+    }
     return 0;
 }
 int vct_get_cone_steps(vct_ctx* c, unsigned long long* steps) {
@@ -684,6 +825,7 @@ int vct_get_cone_steps(vct_ctx* c, unsigned long long* steps) {
     cudaSetDevice(c->cfg.device);
     if (fetch_counters(c)) return 1;
     *steps = c->h_counters.cone_steps;
+    for (vct_ctx* m : c->group) { unsigned long long ms = 0; if (vct_get_cone_steps(m, &ms)) return fail(c, m->error.c_str()); *steps += ms; }
     return 0;
 }
 int vct_get_timings(vct_ctx* c, vct_timings* t) {
@@ -694,7 +836,7 @@ int vct_get_timings(vct_ctx* c, vct_timings* t) {
     std::memset(t, 0, sizeof *t);
     t->shadowmap_ns = ms(EV_START, EV_SHADOW); t->warpmap_ns = ms(EV_SHADOW, EV_WARP); t->clear_ns = ms(EV_WARP, EV_CLEAR);
     t->voxelize_ns = ms(EV_WARP, EV_VOXEL); t->transfer_ns = ms(EV_VOXEL, EV_TRANSFER); t->radiance_ns = ms(EV_TRANSFER, EV_INJECT);
-    t->mipmap_ns = ms(EV_INJECT, EV_MIP); t->gbuffer_ns = ms(EV_MIP, EV_GBUF); t->render_ns = ms(EV_GBUF, EV_TRACE); t->total_ns = ms(EV_START, EV_TRACE);
+    t->mipmap_ns = ms(EV_INJECT, EV_MIP); t->exchange_ns = ms(EV_MIP, EV_XCHG); t->gbuffer_ns = ms(EV_XCHG, EV_GBUF); t->render_ns = ms(EV_GBUF, EV_TRACE); t->total_ns = ms(EV_START, EV_TRACE);
     return 0;
 }
 // A raw pointer lets the caller write the volume at any time: sparse frames are switched off for good (until vct_remake).
@@ -710,7 +852,7 @@ size_t vct_level_bytes(vct_ctx* c, int which, int level) { if (!c) return 0; voi
 void* vct_stream(vct_ctx* c) { return c ? (void*)c->stream : nullptr; }
 // Enqueue on a caller-owned stream (e.g. the stream torch.distributed's NCCL collectives run on) so that the
 // slab exchange needs no host synchronisation.  NULL restores a private stream.
-int vct_set_stream(vct_ctx* c, void* stream) {
+int vct_set_stream(vct_ctx* c, void* stream) { VCT_NO_GROUP(c, "vct_set_stream");
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);
     VCT_CHECK(c, cudaStreamSynchronize(c->stream));
@@ -719,7 +861,7 @@ int vct_set_stream(vct_ctx* c, void* stream) {
     else { VCT_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     return 0;
 }
-int vct_set_profiling(vct_ctx* c, int level) {
+int vct_set_profiling(vct_ctx* c, int level) { VCT_FAN(c, vct_set_profiling(c, level));
     if (!c) return 1;
     if (level < 0 || level > 2) return fail(c, "vct_set_profiling: level 0 (off), 1 (per pass) or 2 (per kernel)");
     c->profiling = level; c->prof_marks.clear(); c->prof_used = 0;
@@ -742,6 +884,11 @@ int vct_get_kernel_times(vct_ctx* c, vct_kernel_time* out, int max_entries) {
     }
     return n;
 }
-unsigned long long vct_launch_count(vct_ctx* c, int reset) { if (!c) return 0; const unsigned long long n = c->launches; if (reset) c->launches = 0; return n; }
+unsigned long long vct_launch_count(vct_ctx* c, int reset) {
+    if (!c) return 0;
+    unsigned long long n = c->launches; if (reset) c->launches = 0;
+    for (vct_ctx* m : c->group) n += vct_launch_count(m, reset);
+    return n;
+}
 
 }  // extern "C"

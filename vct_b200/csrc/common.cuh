@@ -140,13 +140,18 @@ struct vct_ctx {
     // and the mip chain touch only flagged segments (the volume is ~97 % empty).  Anything that writes a volume outside
     // vct_frame / vct_gi_passes invalidates the masks; the next frame then runs the dense kernels once.
     // sparse slab exchange (exchange.cu): local staging, the peers' staging mapped through cudaIpc, record counter
-    void* d_xchg = nullptr; size_t xchg_region_bytes = 0; unsigned xchg_cap = 0; void* peer_xchg[VCT_MAX_PEERS]{}; unsigned* d_xchg_count = nullptr;
+    void* d_xchg = nullptr; size_t xchg_region_bytes = 0; unsigned xchg_cap = 0; unsigned* d_xchg_count = nullptr;
+    vct_peer peer[VCT_MAX_PEERS]{}; bool peer_ipc[VCT_MAX_PEERS]{}; int peers_attached = 0;
+    uint32_t* d_trace_tiles = nullptr; int n_trace_tiles = 0;      // own 64x64 screen tiles (x0 | y0 << 16) of the sharded cone trace
+    std::vector<vct_ctx*> group;                                    // single-process multi-GPU: the other ranks' contexts (this one is rank 0)
+    void* group_state = nullptr; bool in_fan = false;               // worker threads of the group (api.cu); true while a call is being fanned out
     bool last_frame_sparse = false;
     uint8_t* d_seg[2] = {nullptr, nullptr}; int seg_cur = 0, seg_key = -1; bool seg_valid = false, seg_disabled = false, sparse_off = false;
     // warp
     uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
     // shadow map / visibility / image
     float* d_shadow = nullptr; unsigned long long* d_vis = nullptr; uint32_t* d_image = nullptr;
+    void* d_shadow_mm = nullptr; bool shadow_mm_valid = false;   // (S/4)^2 x float2: min / max filtered depth per 4x4 texel block (k_shadow_minmax)
     // voxel fragments (per-voxel linked lists of the deterministic running average)
     size_t frag_cap = 0; void* d_frags = nullptr; uint8_t* d_displaced = nullptr;
     uint32_t* d_warp_scratch = nullptr;
@@ -215,7 +220,8 @@ static inline int level_dim(int D, int l) { int d = D >> l; return d < 1 ? 1 : d
 // pass entry points implemented across the .cu files (all enqueue on ctx->stream)
 int vctk_transform_vertices(vct_ctx*);
 int vctk_clear_voxels(vct_ctx*, bool reset_frame_counters = false);   // true: the same launch zeroes VoxelizeInfo, the raster queues and cone_steps
-int vctk_voxelize(vct_ctx*, bool occupancy, bool counters_already_reset = false);
+// fuse_transfer: the deterministic resolve also does transferVoxels for its voxels (sparse frame, temporal filter off); *transfer_done says whether it did
+int vctk_voxelize(vct_ctx*, bool occupancy, bool counters_already_reset = false, bool fuse_transfer = false, bool* transfer_done = nullptr);
 void vctk_fill_models(vct_ctx*, Mat4* models, float* nmats);
 int vctk_transfer(vct_ctx*);
 int vctk_clear_masked(vct_ctx*);        // sparse frames: clear flagged segments of all three volumes, reset the new mask and the frame counters
@@ -224,14 +230,16 @@ int vctk_frame_begin_masked(vct_ctx*);   // vertex transform + masked clear in o
 bool vctk_sparse_supported(const vct_ctx*);
 int vctk_inject(vct_ctx*);
 int vctk_fill_holes(vct_ctx*);
+int vctk_shadow_minmax(vct_ctx*);
 int vctk_mip(vct_ctx*, int which, int mode, int publish);
 int vctk_mip_chains(vct_ctx*, int n, const int* which, const int* publish, int mode, bool masked = false);
 int vctk_publish(vct_ctx*, int which);
 int vctk_publish_upper(vct_ctx*, int which);   // levels 1..L-1 only
 int vctk_xchg_setup(vct_ctx*);
 void vctk_xchg_free(vct_ctx*);
-int vctk_xchg_push(vct_ctx*);
-int vctk_xchg_unpack(vct_ctx*);
+bool vctk_xchg_ready(const vct_ctx*);          // multi-GPU with every peer attached: the frame entry points run the whole sharded frame
+int vctk_xchg_frame(vct_ctx*, bool dense);
+int vctk_xchg_image_sync(vct_ctx*);
 int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);
 int vctk_warpmap(vct_ctx*);

@@ -17,21 +17,31 @@
 // Device code: cone_trace.cuh (shared with cone_trace_debug.cu, which holds the debug views in an exactly rounded build).
 #include "cone_trace.cuh"
 
-// rows of the image buffer: H rounded up so that it splits into world_size equal bands of whole 8-row tiles
-size_t vctk_image_rows(const vct_ctx* c) {
-    const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, rows8 = (c->H + 7) / 8;
-    return (size_t)((rows8 + ws - 1) / ws) * 8 * ws;
-}
+// rows of the image buffer: whole 64-row screen tiles (the sharded trace addresses pixels by tile)
+size_t vctk_image_rows(const vct_ctx* c) { return (size_t)((c->H + 63) / 64) * 64; }
 
-int vctk_cone_trace_debug(vct_ctx* c, const TraceArgs& a, int wm);          // cone_trace_debug.cu
+int vctk_cone_trace_debug(vct_ctx* c, const TraceArgs& a, int wm, dim3 grid);          // cone_trace_debug.cu
+
+// Screen sharding: 64x64-pixel tiles, tile (tx, ty) belongs to rank (tx + ty) mod N — diagonal stripes, so that every rank
+// gets the same mix of sky, floor and walls.  Mirrored by vct_b200/sharded.py::tile_owner for the host-side tests.
+constexpr int kScreenTile = 64;
+static int ensure_trace_tiles(vct_ctx* c) {
+    if (c->d_trace_tiles) return 0;
+    std::vector<uint32_t> tiles;
+    const int ntx = (c->W + kScreenTile - 1) / kScreenTile, nty = (c->H + kScreenTile - 1) / kScreenTile;
+    for (int ty = 0; ty < nty; ++ty)
+        for (int tx = 0; tx < ntx; ++tx)
+            if ((tx + ty) % c->cfg.world_size == c->cfg.rank) tiles.push_back((uint32_t)(tx * kScreenTile) | (uint32_t)(ty * kScreenTile) << 16);
+    c->n_trace_tiles = (int)tiles.size();
+    VCT_CHECK(c, cudaMalloc(&c->d_trace_tiles, std::max<size_t>(tiles.size(), 1) * 4));
+    if (!tiles.empty()) VCT_CHECK(c, cudaMemcpy(c->d_trace_tiles, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
 
 static TraceArgs make_trace_args(vct_ctx* c) {
     TraceArgs a{};
     a.fc = c->d_fc; a.W = c->W; a.H = c->H;
-    // screen sharding across ranks: world_size equal bands of whole 8-row tiles (the last may be short)
-    const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
-    const int band = (int)(vctk_image_rows(c) / ws);
-    a.y_lo = std::min(c->H, r * band); a.y_hi = std::min(c->H, (r + 1) * band);
+    a.y_lo = 0; a.y_hi = c->H;                               // the whole image, unless this is a sharded frame (vctk_cone_trace)
     a.vis = c->d_vis; a.indices = c->d_indices; a.trimat = c->d_trimat; a.verts = c->d_vertices;
     a.wpos = c->d_wpos; a.wnrm = c->d_wnrm; a.wT = c->d_wT; a.wB = c->d_wB; a.tex = c->d_tex; a.mats = c->d_mat; a.shadow = c->d_shadow;
     const bool rad = c->h_fc.p.draw_radiance != 0;
@@ -44,7 +54,13 @@ static TraceArgs make_trace_args(vct_ctx* c) {
 
 int vctk_cone_trace(vct_ctx* c) {
     TraceArgs a = make_trace_args(c);
-    if (a.y_hi <= a.y_lo) return 0;
+    dim3 grid((c->W + kThreads / 4 - 1) / (kThreads / 4), (c->H + 3) / 4);
+    if (vctk_xchg_ready(c)) {                                   // sharded frame: own tiles only, pixels also into rank 0's image
+        if (ensure_trace_tiles(c)) return 1;
+        if (!c->n_trace_tiles) return 0;
+        a.tiles = c->d_trace_tiles; a.image_remote = c->cfg.rank ? reinterpret_cast<uint32_t*>(c->peer[0].image) : nullptr;
+        grid = dim3((unsigned)c->n_trace_tiles * 32u, 1);
+    }
     if (c->copy_pending) {                                      // vct_read_image_async: the previous frame's image is still being read back
         VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
         c->copy_pending = false;
@@ -57,9 +73,8 @@ int vctk_cone_trace(vct_ctx* c) {
                               : (p.warp_texture ? WARP_TEXTURE : p.warp_voxels ? WARP_VOXELS : p.voxelize_tesselation_warp ? WARP_TESS : WARP_NONE);
     if (p.debug_view != VCT_VIEW_SHADED) {                      // debug views: own instantiations in the exactly rounded unit
         if (p.debug_view < 0 || p.debug_view > VCT_VIEW_LAST) { c->error = "vct_cone_trace: unknown debug_view"; return 1; }
-        return vctk_cone_trace_debug(c, a, wm);
+        return vctk_cone_trace_debug(c, a, wm, grid);
     }
-    const dim3 grid((c->W + kThreads / 4 - 1) / (kThreads / 4), (a.y_hi - a.y_lo + 3) / 4);
     if (wm == WARP_VOXELS) k_cone_trace<WARP_VOXELS><<<grid, kThreads, 0, c->stream>>>(a);
     else if (wm == WARP_TEXTURE) k_cone_trace<WARP_TEXTURE><<<grid, kThreads, 0, c->stream>>>(a);
     else if (wm == WARP_TESS) k_cone_trace<WARP_TESS><<<grid, kThreads, 0, c->stream>>>(a);

@@ -31,6 +31,9 @@ struct TraceArgs {
     cudaTextureObject_t vol, vol_point, vol_last; const ushort4* warp;
     const uint32_t* level0;                      // linear level 0 of the traced pyramid: the voxel view's NEAREST fetch reads it exactly
     uint32_t* image; Counters* counters;
+    // sharded frame (multi-GPU with attached peers): the CTAs walk this rank's 64x64 screen tiles (x0 | y0 << 16; 32 CTAs each) instead of the
+    // whole image, and every pixel is also stored into rank 0's image over NVLink (nullptr on rank 0 and on a single GPU)
+    const uint32_t* tiles; uint32_t* image_remote;
 };
 
 namespace {
@@ -40,6 +43,7 @@ __device__ const float kPI = 3.1415982f;                 // common.glsl:1 [sic]
 
 
 __device__ __forceinline__ V3 f4to3(float4 q) { return mk3(q.x, q.y, q.z); }
+__device__ __forceinline__ void put_pixel(const TraceArgs& a, size_t o, uint32_t word) { a.image[o] = word; if (a.image_remote) a.image_remote[o] = word; }
 __device__ __forceinline__ float ip(const float l[3], float a, float b, float c) { return l[0] * a + l[1] * b + l[2] * c; }
 __device__ __forceinline__ V3 ip3(const float l[3], V3 a, V3 b, V3 c) { return mk3(ip(l, a.x, b.x, c.x), ip(l, a.y, b.y, c.y), ip(l, a.z, b.z, c.z)); }
 
@@ -358,13 +362,19 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int px = blockIdx.x * (kThreads / 4) + w * 8 + (lane & 7);
-    const int py = a.y_lo + blockIdx.y * 4 + (lane >> 3);
+    int px = blockIdx.x * (kThreads / 4) + w * 8 + (lane & 7);
+    int py = a.y_lo + blockIdx.y * 4 + (lane >> 3);
+    if (a.tiles) {                                                        // sharded: CTA b works on 32x4 pixels of own tile b / 32
+        const uint32_t t = __ldg(a.tiles + (blockIdx.x >> 5));
+        const int sub = blockIdx.x & 31;
+        px = (int)(t & 0xFFFFu) + (sub & 1) * 32 + w * 8 + (lane & 7);
+        py = (int)(t >> 16) + (sub >> 1) * 4 + (lane >> 3);
+    }
     unsigned fetches = 0;
     if (px < a.W && py < a.y_hi) {
         const size_t o = (size_t)py * a.W + px;
         const unsigned long long key = a.vis[o];
-        if (key == ~0ull) a.image[o] = pack_unorm(mk4(fp.clear_color[0], fp.clear_color[1], fp.clear_color[2], 1.0f));
+        if (key == ~0ull) put_pixel(a, o, pack_unorm(mk4(fp.clear_color[0], fp.clear_color[1], fp.clear_color[2], 1.0f)));
         else do {                                                         // `break` = the shader's early `return`
             const uint32_t t = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
             const uint32_t i0 = __ldg(a.indices + 3 * (size_t)t), i1 = __ldg(a.indices + 3 * (size_t)t + 1), i2 = __ldg(a.indices + 3 * (size_t)t + 2);
@@ -428,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
                 }
                 else sc = tex3DLod<float4>(a.vol, vi.x, vi.y, vi.z, fminf(lambda, (float)(fc.L - 1)));
                 fetches++;
-                a.image[o] = pack_unorm(mk4(sc.x, sc.y, sc.z, 1.0f));
+                put_pixel(a, o, pack_unorm(mk4(sc.x, sc.y, sc.z, 1.0f)));
                 break;
             }
             if (DBG && (view == VCT_VIEW_MATERIAL_DIFFUSE || view == VCT_VIEW_MATERIAL_ROUGHNESS || view == VCT_VIEW_MATERIAL_METALLIC)) {   // :405-425
@@ -436,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
                 if (view == VCT_VIEW_MATERIAL_DIFFUSE && mat.diffuse_tex >= 0) { const V4 t4 = fetch(mat.diffuse_tex); c = mk3(t4.x, t4.y, t4.z); }
                 if (view == VCT_VIEW_MATERIAL_ROUGHNESS && mat.roughness_tex >= 0) { const float r = fetch(mat.roughness_tex).x; c = mk3(r, r, r); }
                 if (view == VCT_VIEW_MATERIAL_METALLIC && mat.metallic_tex >= 0) { const float r = fetch(mat.metallic_tex).x; c = mk3(r, r, r); }
-                a.image[o] = pack_unorm(mk4(c.x, c.y, c.z, 1.0f));
+                put_pixel(a, o, pack_unorm(mk4(c.x, c.y, c.z, 1.0f)));
                 break;
             }
             V3 N;
@@ -444,10 +454,10 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
                 const V4 nm = fetch(mat.normal_tex);
                 N = normalize3(tbn(normalize3(mk3(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f))));
             } else N = normalize3(fn);
-            if (DBG && view == VCT_VIEW_NORMALS) { a.image[o] = pack_unorm(mk4(N.x, N.y, N.z, 1.0f)); break; }     // :441-443
+            if (DBG && view == VCT_VIEW_NORMALS) { put_pixel(a, o, pack_unorm(mk4(N.x, N.y, N.z, 1.0f))); break; }     // :441-443
             if (DBG && view == VCT_VIEW_DOMINANT_AXIS) {                     // :444-447  step(vec3(max component), |n|)
                 const float ax = fabsf(N.x), ay = fabsf(N.y), az = fabsf(N.z), m = fmaxf(fmaxf(ax, ay), az);
-                a.image[o] = pack_unorm(mk4(ax < m ? 0.0f : 1.0f, ay < m ? 0.0f : 1.0f, az < m ? 0.0f : 1.0f, 1.0f));
+                put_pixel(a, o, pack_unorm(mk4(ax < m ? 0.0f : 1.0f, ay < m ? 0.0f : 1.0f, az < m ? 0.0f : 1.0f, 1.0f)));
                 break;
             }
             const V4 dc4 = mat.diffuse_tex >= 0 ? fetch(mat.diffuse_tex) : mk4(mat.diffuse[0], mat.diffuse[1], mat.diffuse[2], 1.0f);
@@ -509,10 +519,10 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
                 const float occl = 1.0f - clampf(ind.w, 0.0f, 1.0f);
                 if (DBG && view == VCT_VIEW_INDIRECT) {                      // :489 (before reflections and post-processing)
                     const float k = fp.draw_occlusion ? occl : 1.0f;
-                    a.image[o] = pack_unorm(mk4(ind.x * k, ind.y * k, ind.z * k, 1.0f));
+                    put_pixel(a, o, pack_unorm(mk4(ind.x * k, ind.y * k, ind.z * k, 1.0f)));
                     break;
                 }
-                if (DBG && view == VCT_VIEW_OCCLUSION) { a.image[o] = pack_unorm(mk4(occl, occl, occl, 1.0f)); break; }   // :490
+                if (DBG && view == VCT_VIEW_OCCLUSION) { put_pixel(a, o, pack_unorm(mk4(occl, occl, occl, 1.0f))); break; }   // :490
                 if (fp.enable_reflections) {
                     const V3 I = Pw - eye;
                     const V3 R = I - N * (2.0f * dot3(N, I));
@@ -525,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
                         rc = trace_cone_ahead<4, WM>(cx, s_specular, start, normalize3(R) * scale, fetches);
                     }
                     ind.x += rc.x * fp.reflect_scale; ind.y += rc.y * fp.reflect_scale; ind.z += rc.z * fp.reflect_scale;
-                    if (DBG && view == VCT_VIEW_REFLECTIONS) { a.image[o] = pack_unorm(mk4(rc.x, rc.y, rc.z, 1.0f)); break; }   // :505
+                    if (DBG && view == VCT_VIEW_REFLECTIONS) { put_pixel(a, o, pack_unorm(mk4(rc.x, rc.y, rc.z, 1.0f))); break; }   // :505
                 }
                 const V3 indc = mk3(ind.x, ind.y, ind.z) * (dc * fp.ambient_scale);
                 col = (indc + dsum) + ssum;
@@ -536,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
                 const float g = 1.0f / 2.2f;
                 col = mk3(powf(col.x, g), powf(col.y, g), powf(col.z, g));
             }
-            a.image[o] = pack_unorm(mk4(col.x, col.y, col.z, 1.0f));
+            put_pixel(a, o, pack_unorm(mk4(col.x, col.y, col.z, 1.0f)));
         } while (0);
     }
 #pragma unroll

@@ -6,8 +6,7 @@
 // ulp, and the fast-math build of the shaded frame differed from the oracle there (29.4 dB; profiles/r02a_diag_voxel_view.txt).
 #include "cone_trace.cuh"
 
-int vctk_cone_trace_debug(vct_ctx* c, const TraceArgs& a, int wm) {
-    const dim3 grid((c->W + kThreads / 4 - 1) / (kThreads / 4), (a.y_hi - a.y_lo + 3) / 4);
+int vctk_cone_trace_debug(vct_ctx* c, const TraceArgs& a, int wm, dim3 grid) {
     if (wm == WARP_VOXELS) k_cone_trace<WARP_VOXELS, true><<<grid, kThreads, 0, c->stream>>>(a);
     else if (wm == WARP_TEXTURE) k_cone_trace<WARP_TEXTURE, true><<<grid, kThreads, 0, c->stream>>>(a);
     else if (wm == WARP_TESS) k_cone_trace<WARP_TESS, true><<<grid, kThreads, 0, c->stream>>>(a);

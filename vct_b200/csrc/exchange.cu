@@ -1,44 +1,70 @@
-// exchange.cu — sparse slab exchange over NVLink peer memory (multi-GPU, SURVEY §8e "exchange only non-empty bricks").
+// exchange.cu — the one exchange step of the z-slab sharded frame (multi-GPU), entirely in kernels over NVLink peer
+// memory: no NCCL collective and no host synchronisation on the frame's critical path, so the whole N-GPU step can be captured in a
+// CUDA graph like the single-GPU step.
 //
-// The reference is a single-GPU program; this is the one real exchange step of the z-slab sharded frame.  Level 0 of
-// the traced pyramid is 8/9 of its bytes and ~97 % empty, so instead of all-gathering it densely every rank PUSHES the
-// x-row segments of its own slab that hold — or held last frame — a fragment (the segment masks of the sparse frame,
-// common.cuh) straight into a staging buffer in every peer's memory:
-//
-//   k_xchg_push     a warp scans 32 mask words of the own slab, compacts the flagged segments, reserves record slots with
-//                   one atomic, and every lane stores one 16-byte half segment (+ the segment id) to ALL ranks' staging
-//                   (remote stores over NVLink through cudaIpc-mapped pointers; stale segments travel as zeros)
-//   k_xchg_finish   publishes the record count to every rank and re-arms the local counter
-//   (the NCCL all-gather of the small levels >= 1 that follows on the same stream is the cross-GPU barrier)
-//   k_xchg_unpack   every rank scatters the records of all senders into its linear level 0 (remote slabs), into the
-//                   3D texture the cone tracer samples, and into the publish mask — a sparse publish instead of the
-//                   dense linear -> array copy
-//
-// Staging layout on every rank: world_size regions (one per sender): [count | pad to 128 B][ids: cap x u32][data: cap x 32 B],
-// cap = segments of one slab (worst case: every segment flagged).  A region is rewritten only after its owner has passed
-// the image all-gather that ends the frame in which it was unpacked, so one buffer suffices.
+// The reference is a single-GPU program; sharding leaves one real exchange: after its voxel passes every rank owns one z-slab of
+// every level of the traced pyramid and the cone tracer of every rank samples all of it.
+//   level 0      8/9 of the bytes and ~97 % empty: a rank PUSHES the x-row segments (8 voxels, 32 bytes) of its slab that hold — or
+//                held last frame — a fragment (the segment masks of the sparse frame, common.cuh) as (id, data) records into a
+//                staging region in every peer's memory (k_xchg_push: warp-compacted, one atomic per 128 segments, remote 16-byte
+//                stores); on a dense frame (the first, or after the masks were invalidated) every segment of the slab travels
+//   levels >= 1  small and dense per slab: copied straight into the peers' linear levels at the place they have everywhere
+//                (k_xchg_push_upper)
+//   flags        every rank's allocation starts with a control block the PEERS write: ready[s] = the frame number whose records sender s
+//                has completed, consumed[p] = the last frame rank p has unpacked.  k_xchg_finish publishes count + ready after a
+//                system-wide fence; k_xchg_unpack spins on ready[] of all senders before it touches a record; k_xchg_push spins on
+//                consumed[] of all peers before it overwrites the single staging region (a wait that is long satisfied in steady
+//                state: a whole frame lies between).  Frame numbers live in device memory and are advanced by k_xchg_ack, so a
+//                replayed graph counts on correctly.  Every wait is for an event on ANOTHER GPU that depends on nothing here: the
+//                chain push(k) -> unpack(k) -> ack(k) -> push(k+1) cannot deadlock.
+//   unpack       records of the remote slabs are scattered into the linear level 0, the 3D texture the cone tracer samples and the
+//                publish mask (a sparse publish); the own slab was published by the mip chain; levels >= 1 follow by one launch
+//   image        a rank's cone trace stores its pixels into rank 0's image as well (cone_trace.cuh); k_xchg_image_done / _wait order
+//                rank 0's readers behind every rank's pixels.
+// Peer memory is mapped by cudaIpc (one process per GPU: vct_exchange_export / _import) or is plain peer-accessible device memory
+// (one process driving all GPUs: vct_exchange_attach).
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
+constexpr size_t kCtrlBytes = 256;       // XchgControl, padded
 constexpr size_t kHdr = 128;
 
-struct XchgPeers { unsigned char* base[VCT_MAX_PEERS]; int world, rank; size_t region_bytes; unsigned cap; };
-__device__ __forceinline__ unsigned* region_count(unsigned char* base, size_t region_bytes, int sender) { return reinterpret_cast<unsigned*>(base + sender * region_bytes); }
-__device__ __forceinline__ uint32_t* region_ids(unsigned char* base, size_t region_bytes, int sender) { return reinterpret_cast<uint32_t*>(base + sender * region_bytes + kHdr); }
+struct XchgControl {                     // first bytes of every rank's staging allocation; WRITTEN BY THE PEERS
+    unsigned ready[VCT_MAX_PEERS];       // ready[s]: sender s has pushed all its records of frame `ready[s]`
+    unsigned count[VCT_MAX_PEERS];       // count[s]: how many
+    unsigned consumed[VCT_MAX_PEERS];    // consumed[p]: rank p has unpacked frame `consumed[p]` (its staging may be overwritten)
+    unsigned image_done[VCT_MAX_PEERS];  // rank 0: rank p's pixels of frame `image_done[p]` are in this rank's image
+};
+static_assert(sizeof(XchgControl) <= kCtrlBytes, "control block");
+
+struct XchgPeers { unsigned char* base[VCT_MAX_PEERS]; uint32_t* pyramid[VCT_MAX_PEERS]; int world, rank; size_t region_bytes; unsigned cap; };
+__device__ __forceinline__ XchgControl* ctrl(unsigned char* base) { return reinterpret_cast<XchgControl*>(base); }
+__device__ __forceinline__ uint32_t* region_ids(unsigned char* base, size_t region_bytes, int sender) { return reinterpret_cast<uint32_t*>(base + kCtrlBytes + sender * region_bytes + kHdr); }
 __device__ __forceinline__ uint4* region_data(unsigned char* base, size_t region_bytes, int sender, unsigned cap) {
-    return reinterpret_cast<uint4*>(base + sender * region_bytes + kHdr + (((size_t)cap * 4 + 127) & ~(size_t)127));
+    return reinterpret_cast<uint4*>(base + kCtrlBytes + sender * region_bytes + kHdr + (((size_t)cap * 4 + 127) & ~(size_t)127));
+}
+// spin until flags[r] >= want for every r != self (one thread per CTA calls this; the CTA then passes a barrier)
+__device__ __forceinline__ void wait_flags(const unsigned* flags, int world, int self, unsigned want) {
+    for (int r = 0; r < world; ++r) {
+        if (r == self) continue;
+        while ((int)(*(const volatile unsigned*)(flags + r) - want) < 0) __nanosleep(64);
+    }
+    __threadfence_system();
 }
 
-__global__ void __launch_bounds__(kThreads) k_xchg_push(const uint4* __restrict__ level0, const uint32_t* __restrict__ seg_now, const uint32_t* __restrict__ seg_before,
-                                                        size_t word_lo, size_t word_hi, unsigned* __restrict__ counter, const __grid_constant__ XchgPeers peers) {
+__global__ void __launch_bounds__(kThreads) k_xchg_push(const uint4* __restrict__ level0, const uint32_t* __restrict__ seg_now, const uint32_t* __restrict__ seg_before, int dense,
+                                                        size_t word_lo, size_t word_hi, unsigned* __restrict__ counter, const unsigned* __restrict__ seq,
+                                                        const __grid_constant__ XchgPeers peers) {
     __shared__ uint32_t s_list[kThreads / 32][128];
+    if (threadIdx.x == 0) wait_flags(ctrl(peers.base[peers.rank])->consumed, peers.world, peers.rank, *seq);   // the peers are done with last frame's records
+    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t n = word_hi - word_lo, n_round = (n + 31) & ~(size_t)31;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_round; i += (size_t)gridDim.x * blockDim.x) {
         const size_t t = word_lo + i;
-        const uint32_t flags = i < n ? (__ldg(seg_now + t) | __ldg(seg_before + t)) : 0u;
+        const uint32_t flags = i < n ? (dense ? 0x01010101u : (__ldg(seg_now + t) | __ldg(seg_before + t))) : 0u;
         const unsigned nz = (flags & 0xFFu ? 1u : 0u) | (flags & 0xFF00u ? 2u : 0u) | (flags & 0xFF0000u ? 4u : 0u) | (flags & 0xFF000000u ? 8u : 0u);
         int inc = __popc(nz);
         const int mine = inc;
@@ -59,6 +85,7 @@ __global__ void __launch_bounds__(kThreads) k_xchg_push(const uint4* __restrict_
             if (slot >= peers.cap) continue;                                 // cannot happen: cap = segments of the slab
             const uint4 v = __ldcs(level0 + 2 * (size_t)sid + (q & 1));
             for (int r = 0; r < peers.world; ++r) {
+                if (r == peers.rank) continue;                               // the own slab is published by the mip chain
                 unsigned char* b = peers.base[r];
                 region_data(b, peers.region_bytes, peers.rank, peers.cap)[2 * (size_t)slot + (q & 1)] = v;
                 if (!(q & 1)) region_ids(b, peers.region_bytes, peers.rank)[slot] = sid;
@@ -68,32 +95,68 @@ __global__ void __launch_bounds__(kThreads) k_xchg_push(const uint4* __restrict_
     }
     __threadfence_system();
 }
-__global__ void k_xchg_finish(unsigned* __restrict__ counter, const __grid_constant__ XchgPeers peers) {
-    const unsigned n = min(*counter, peers.cap);
-    if ((int)threadIdx.x < peers.world) *region_count(peers.base[threadIdx.x], peers.region_bytes, peers.rank) = n;
+// levels >= 1 of the own slab, dense, straight into every peer's linear pyramid (same offsets on every rank)
+struct UpperLevels { unsigned long long first[VCT_MAX_LEVELS + 1]; unsigned long long off[VCT_MAX_LEVELS]; int n; };   // in 16-byte units / words
+__global__ void __launch_bounds__(kThreads) k_xchg_push_upper(const uint32_t* __restrict__ pyramid, const __grid_constant__ UpperLevels lv, const __grid_constant__ XchgPeers peers) {
+    const unsigned long long total = lv.first[lv.n];
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k + 1 < lv.n && i >= lv.first[k + 1]) ++k;
+        const unsigned long long w = lv.off[k] + (i - lv.first[k]);           // word offset of this rank's chunk element in the pyramid
+        const uint32_t v = __ldcg(pyramid + w);
+        for (int r = 0; r < peers.world; ++r) if (r != peers.rank) peers.pyramid[r][w] = v;
+    }
     __threadfence_system();
+}
+__global__ void k_xchg_finish(unsigned* __restrict__ counter, const unsigned* __restrict__ seq, const __grid_constant__ XchgPeers peers) {
+    const unsigned n = min(*counter, peers.cap), s = *seq + 1u;
+    __threadfence_system();
+    if ((int)threadIdx.x < peers.world && (int)threadIdx.x != peers.rank) {
+        XchgControl* c = ctrl(peers.base[threadIdx.x]);
+        c->count[peers.rank] = n;
+        __threadfence_system();
+        *(volatile unsigned*)&c->ready[peers.rank] = s;
+    }
     __syncthreads();
     if (threadIdx.x == 0) *counter = 0u;
 }
-// grid.y = sender.  Records of the own slab are already in the linear level; remote ones are written there too, so that
-// vct_read_volume and the next dense frame see one consistent volume.
-__global__ void __launch_bounds__(kThreads) k_xchg_unpack(unsigned char* __restrict__ staging, size_t region_bytes, unsigned cap, int rank,
+// grid.y = sender (remote ranks only do work).  Remote records land in the linear level 0 too, so that vct_read_volume and the next
+// dense frame see one consistent volume.
+__global__ void __launch_bounds__(kThreads) k_xchg_unpack(unsigned char* __restrict__ staging, size_t region_bytes, unsigned cap, int rank, int world, const unsigned* __restrict__ seq,
                                                           uint4* __restrict__ level0, cudaSurfaceObject_t surf, uint8_t* __restrict__ pub_mask, int D) {
     const int sender = blockIdx.y;
-    const unsigned n = min(*region_count(staging, region_bytes, sender), cap);
+    if (sender == rank) return;
+    if (threadIdx.x == 0) wait_flags(ctrl(staging)->ready, world, rank, *seq + 1u);
+    __syncthreads();
+    const unsigned n = min(*(const volatile unsigned*)&ctrl(staging)->count[sender], cap);
     const uint32_t* ids = region_ids(staging, region_bytes, sender);
     const uint4* data = region_data(staging, region_bytes, sender, cap);
     const unsigned spr = (unsigned)D >> 3;                                   // segments per x-row
     for (unsigned q = blockIdx.x * kThreads + threadIdx.x; q < 2u * n; q += gridDim.x * kThreads) {
-        const uint32_t sid = ids[q >> 1];
-        const uint4 v = data[q];
-        if (sender != rank) level0[2 * (size_t)sid + (q & 1)] = v;
+        const uint32_t sid = __ldcg(ids + (q >> 1));
+        const uint4 v = __ldcg(data + q);
+        level0[2 * (size_t)sid + (q & 1)] = v;
         const unsigned row = sid / spr, sx = sid - row * spr;
         const int y = (int)(row % (unsigned)D), z = (int)(row / (unsigned)D);
         surf3Dwrite(v, surf, (int)(sx * 32u + (q & 1u) * 16u), y, z);
-        const uint4 o = data[q ^ 1u];
+        const uint4 o = __ldcg(data + (q ^ 1u));
         if (!(q & 1)) pub_mask[sid] = ((v.x | v.y | v.z | v.w | o.x | o.y | o.z | o.w) != 0u) ? 1 : 0;
     }
+}
+__global__ void k_xchg_ack(unsigned* __restrict__ seq, const __grid_constant__ XchgPeers peers) {
+    const unsigned s = *seq + 1u;
+    __threadfence_system();
+    if ((int)threadIdx.x < peers.world && (int)threadIdx.x != peers.rank) *(volatile unsigned*)&ctrl(peers.base[threadIdx.x])->consumed[peers.rank] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) *seq = s;
+}
+// after the cone trace: this rank's pixels of frame *seq are in rank 0's image
+__global__ void k_xchg_image_done(const unsigned* __restrict__ seq, const __grid_constant__ XchgPeers peers) {
+    __threadfence_system();
+    *(volatile unsigned*)&ctrl(peers.base[0])->image_done[peers.rank] = *seq;
+}
+__global__ void k_xchg_image_wait(const unsigned* __restrict__ seq, const __grid_constant__ XchgPeers peers) {
+    wait_flags(ctrl(peers.base[0])->image_done, peers.world, 0, *seq);
 }
 
 }  // namespace
@@ -108,55 +171,88 @@ int vctk_xchg_setup(vct_ctx* c) {
     if (ws < 2 || ws > VCT_MAX_PEERS) { c->error = "sparse exchange: world_size must be in [2, 8]"; return 1; }
     c->xchg_cap = (unsigned)((size_t)c->D * c->D * (c->z_hi - c->z_lo) / 8);
     c->xchg_region_bytes = vctk_xchg_region_bytes(c);
-    VCT_CHECK(c, cudaMalloc(&c->d_xchg, c->xchg_region_bytes * ws));
-    VCT_CHECK(c, cudaMemsetAsync(c->d_xchg, 0, c->xchg_region_bytes * ws, c->stream));
-    VCT_CHECK(c, cudaMalloc(&c->d_xchg_count, 128));
+    const size_t bytes = kCtrlBytes + c->xchg_region_bytes * ws;
+    VCT_CHECK(c, cudaMalloc(&c->d_xchg, bytes));
+    VCT_CHECK(c, cudaMemsetAsync(c->d_xchg, 0, bytes, c->stream));
+    VCT_CHECK(c, cudaMalloc(&c->d_xchg_count, 128));                        // [0] record counter, [16] frame sequence number
     VCT_CHECK(c, cudaMemsetAsync(c->d_xchg_count, 0, 128, c->stream));
     VCT_CHECK(c, cudaStreamSynchronize(c->stream));
-    for (int r = 0; r < VCT_MAX_PEERS; ++r) c->peer_xchg[r] = nullptr;
-    c->peer_xchg[c->cfg.rank] = c->d_xchg;
+    for (int r = 0; r < VCT_MAX_PEERS; ++r) c->peer[r] = vct_peer{};
+    vct_peer& me = c->peer[c->cfg.rank];
+    me.staging = c->d_xchg; me.radiance = c->d_radiance; me.color = c->d_color; me.image = c->d_image;
+    c->peers_attached = 1;
     return 0;
 }
 void vctk_xchg_free(vct_ctx* c) {
     for (int r = 0; r < VCT_MAX_PEERS; ++r) {
-        if (c->peer_xchg[r] && r != c->cfg.rank) cudaIpcCloseMemHandle(c->peer_xchg[r]);
-        c->peer_xchg[r] = nullptr;
+        if (r != c->cfg.rank && c->peer_ipc[r]) {
+            for (void* p : {c->peer[r].staging, c->peer[r].radiance, c->peer[r].color, c->peer[r].image}) if (p) cudaIpcCloseMemHandle(p);
+        }
+        c->peer[r] = vct_peer{}; c->peer_ipc[r] = false;
     }
     cudaFree(c->d_xchg); cudaFree(c->d_xchg_count);
-    c->d_xchg = nullptr; c->d_xchg_count = nullptr;
+    c->d_xchg = nullptr; c->d_xchg_count = nullptr; c->peers_attached = 0;
 }
+bool vctk_xchg_ready(const vct_ctx* c) { return c->cfg.world_size > 1 && c->d_xchg && c->peers_attached == c->cfg.world_size; }
 static int xchg_peers(vct_ctx* c, XchgPeers& p) {
+    const bool rad = c->h_fc.p.draw_radiance != 0;
     p.world = c->cfg.world_size; p.rank = c->cfg.rank; p.region_bytes = c->xchg_region_bytes; p.cap = c->xchg_cap;
     for (int r = 0; r < p.world; ++r) {
-        if (!c->peer_xchg[r]) { c->error = "sparse exchange: a peer's staging buffer was not imported (vct_exchange_import)"; return 1; }
-        p.base[r] = reinterpret_cast<unsigned char*>(c->peer_xchg[r]);
+        if (!c->peer[r].staging) { c->error = "slab exchange: a peer's buffers were not attached (vct_exchange_import / vct_exchange_attach)"; return 1; }
+        p.base[r] = reinterpret_cast<unsigned char*>(c->peer[r].staging);
+        p.pyramid[r] = reinterpret_cast<uint32_t*>(rad ? c->peer[r].radiance : c->peer[r].color);
     }
     return 0;
 }
-int vctk_xchg_push(vct_ctx* c) {
+// the exchange of one frame: every rank ends up with the whole traced pyramid in its 3D texture
+int vctk_xchg_frame(vct_ctx* c, bool dense) {
     XchgPeers p{};
     if (xchg_peers(c, p)) return 1;
     const bool rad = c->h_fc.p.draw_radiance != 0;
-    const uint4* level0 = reinterpret_cast<const uint4*>(rad ? c->d_radiance : c->d_color);
+    uint32_t* pyr = rad ? c->d_radiance : c->d_color;
+    const cudaSurfaceObject_t surf = rad ? c->radiance_surf[0] : c->color_surf[0];
+    uint8_t* mask = rad ? c->d_pub_mask_radiance : c->d_pub_mask_color;
+    if (!surf || !mask) { c->error = "slab exchange: the traced pyramid has no texture array"; return 1; }
+    unsigned* counter = c->d_xchg_count; unsigned* seq = c->d_xchg_count + 16;
+    if (c->copy_pending) {                                   // the previous image is still being read back on rank 0: the peers may not overwrite it yet
+        VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+        c->copy_pending = false;
+    }
     // gi_body swapped the masks at its end: this frame's is seg_cur ^ 1, last frame's is seg_cur
     const size_t words_per_slice = (size_t)c->D * c->D / 32;
     const size_t lo = (size_t)c->z_lo * words_per_slice, hi = (size_t)c->z_hi * words_per_slice;
     const size_t blocks = std::min<size_t>((hi - lo + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
-    k_xchg_push<<<(unsigned)std::max<size_t>(blocks, 1), kThreads, 0, c->stream>>>(level0, reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]),
-                                                                                  reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), lo, hi, c->d_xchg_count, p);
+    k_xchg_push<<<(unsigned)std::max<size_t>(blocks, 1), kThreads, 0, c->stream>>>(reinterpret_cast<const uint4*>(pyr), reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]),
+                                                                                  reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), dense ? 1 : 0, lo, hi, counter, seq, p);
     VCT_LAUNCH_CHECK(c, "k_xchg_push");
-    k_xchg_finish<<<1, 32, 0, c->stream>>>(c->d_xchg_count, p);
+    if (c->L > 1) {
+        UpperLevels lv{};
+        unsigned long long n = 0;
+        for (int l = 1; l < c->L; ++l) {
+            const unsigned long long d = level_dim(c->D, l), chunk = d * d * d / (unsigned long long)c->cfg.world_size;
+            lv.first[lv.n] = n; lv.off[lv.n] = c->level_off[l] + chunk * (unsigned long long)c->cfg.rank; lv.n++; n += chunk;
+        }
+        lv.first[lv.n] = n;
+        k_xchg_push_upper<<<(unsigned)std::min<unsigned long long>((n + kThreads - 1) / kThreads, (unsigned long long)VCT_SM_COUNT * 8), kThreads, 0, c->stream>>>(pyr, lv, p);
+        VCT_LAUNCH_CHECK(c, "k_xchg_push_upper");
+    }
+    k_xchg_finish<<<1, 32, 0, c->stream>>>(counter, seq, p);
     VCT_LAUNCH_CHECK(c, "k_xchg_finish");
+    dim3 grid(VCT_SM_COUNT, c->cfg.world_size);
+    k_xchg_unpack<<<grid, kThreads, 0, c->stream>>>(reinterpret_cast<unsigned char*>(c->d_xchg), c->xchg_region_bytes, c->xchg_cap, c->cfg.rank, c->cfg.world_size, seq,
+                                                    reinterpret_cast<uint4*>(pyr), surf, mask, c->D);
+    VCT_LAUNCH_CHECK(c, "k_xchg_unpack");
+    if (vctk_publish_upper(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR)) return 1;
+    k_xchg_ack<<<1, 32, 0, c->stream>>>(seq, p);
+    VCT_LAUNCH_CHECK(c, "k_xchg_ack");
     return 0;
 }
-int vctk_xchg_unpack(vct_ctx* c) {
-    const bool rad = c->h_fc.p.draw_radiance != 0;
-    uint4* level0 = reinterpret_cast<uint4*>(rad ? c->d_radiance : c->d_color);
-    const cudaSurfaceObject_t surf = rad ? c->radiance_surf[0] : c->color_surf[0];
-    uint8_t* mask = rad ? c->d_pub_mask_radiance : c->d_pub_mask_color;
-    if (!surf || !mask) { c->error = "sparse exchange: the traced pyramid has no texture array yet (run one dense frame first)"; return 1; }
-    dim3 grid(VCT_SM_COUNT * 2, c->cfg.world_size);
-    k_xchg_unpack<<<grid, kThreads, 0, c->stream>>>(reinterpret_cast<unsigned char*>(c->d_xchg), c->xchg_region_bytes, c->xchg_cap, c->cfg.rank, level0, surf, mask, c->D);
-    VCT_LAUNCH_CHECK(c, "k_xchg_unpack");
+// after the cone trace of a sharded frame: rank 0's stream continues only when every rank's pixels are in its image
+int vctk_xchg_image_sync(vct_ctx* c) {
+    XchgPeers p{};
+    if (xchg_peers(c, p)) return 1;
+    const unsigned* seq = c->d_xchg_count + 16;
+    if (c->cfg.rank != 0) { k_xchg_image_done<<<1, 1, 0, c->stream>>>(seq, p); VCT_LAUNCH_CHECK(c, "k_xchg_image_done"); }
+    else { k_xchg_image_wait<<<1, 1, 0, c->stream>>>(seq, p); VCT_LAUNCH_CHECK(c, "k_xchg_image_wait"); }
     return 0;
 }

@@ -33,7 +33,10 @@ __device__ __forceinline__ int fdiv256(long long a) { return (int)((a >= 0) ? a 
 __device__ __forceinline__ bool tri_setup(const RV v[3], int W, int H, bool cull_back, TriSetup& s) {
     int X[3], Y[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { X[i] = snap_coord(v[i].x / v[i].w, W); Y[i] = snap_coord(v[i].y / v[i].w, H); }
+    for (int i = 0; i < 3; ++i) {                                          // x / 1 == x exactly: orthographic views (w == 1) skip the IEEE division
+        const bool unit = v[i].w == 1.0f;
+        X[i] = snap_coord(unit ? v[i].x : v[i].x / v[i].w, W); Y[i] = snap_coord(unit ? v[i].y : v[i].y / v[i].w, H);
+    }
     long long area = (long long)(X[1] - X[0]) * (long long)(Y[2] - Y[0]) - (long long)(Y[1] - Y[0]) * (long long)(X[2] - X[0]);
     if (area == 0) return false;
     s.swapped = 0;
@@ -47,7 +50,7 @@ __device__ __forceinline__ bool tri_setup(const RV v[3], int W, int H, bool cull
         const int a = (k + 1) % 3, b = (k + 2) % 3;
         const int dx = s.X[b] - s.X[a], dy = s.Y[b] - s.Y[a];
         s.bias[k] = (dy < 0 || (dy == 0 && dx < 0)) ? 0 : -1;
-        s.z[k] = v[k].z / v[k].w;
+        s.z[k] = v[k].w == 1.0f ? v[k].z : v[k].z / v[k].w;
     }
     const int minx = min(s.X[0], min(s.X[1], s.X[2])), maxx = max(s.X[0], max(s.X[1], s.X[2]));
     const int miny = min(s.Y[0], min(s.Y[1], s.Y[2])), maxy = max(s.Y[0], max(s.Y[1], s.Y[2]));

@@ -47,12 +47,12 @@ struct __align__(16) VoxSetup : VoxHead {
 };                            // and fetch them (6 x 16 bytes) only when the tile has a fragment
 static_assert(sizeof(VoxHead) == 128 && sizeof(VoxSetup) == 224, "VoxSetup layout");
 
-struct __align__(16) Frag {   // 48 B
+struct __align__(16) Frag {   // 48 B = three 16-byte words; k_voxel_resolve reads only the first for a voxel with one fragment
     uint32_t key;             // voxel index
-    uint32_t tri, rank;       // canonical order: draw index, then py*D+px
     uint32_t next;            // index+1 of the next fragment of the same voxel, 0 = end
-    float cr, cg, cb; uint32_t cw;      // shaded colour      | final packed colour word (head only)
-    float nr, ng, nb; uint32_t nw;      // encoded normal     | final packed normal word (head only)
+    uint32_t cw1, nw1;        // the packed words this fragment yields if it stays alone in its voxel: insert(0, colour / normal)
+    uint32_t tri; float cr, cg, cb;     // canonical order key 1 (draw index) | shaded colour
+    uint32_t rank; float nr, ng, nb;    // canonical order key 2 (py*D+px)    | encoded normal
 };
 static_assert(sizeof(Frag) == 48, "Frag layout");
 
@@ -102,6 +102,19 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
     RV cv[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { const V4 c = mul44(mvp, mk4(w[k].x, w[k].y, w[k].z, 1.0f)); cv[k].x = c.x; cv[k].y = c.y; cv[k].z = c.z; cv[k].w = c.w; }
+    if (cv[0].w == 1.0f && cv[1].w == 1.0f && cv[2].w == 1.0f) {
+        // Early out for the 80-90 % of triangles whose pixel box holds no pixel centre.  The snapped window coordinate differs from
+        // (ndc * 0.5 + 0.5) * D by at most 1/512 pixel, so with a margin of 1/128 pixel an empty float box proves the exact box
+        // [ceil(min - 0.5), floor(max - 0.5)] of tri_setup empty; everything else (and every NaN) takes the exact path.
+        const float fd = (float)a.D, e = 0.0078125f;
+        const float x0 = (cv[0].x * 0.5f + 0.5f) * fd, x1 = (cv[1].x * 0.5f + 0.5f) * fd, x2 = (cv[2].x * 0.5f + 0.5f) * fd;
+        const float y0 = (cv[0].y * 0.5f + 0.5f) * fd, y1 = (cv[1].y * 0.5f + 0.5f) * fd, y2 = (cv[2].y * 0.5f + 0.5f) * fd;
+        const float sum = ((x0 + x1) + x2) + ((y0 + y1) + y2);             // NaN or infinite anywhere: fminf / fmaxf would hide it, take the exact path
+        if (fabsf(sum) < 1e30f) {
+            if (floorf(fmaxf(x0, fmaxf(x1, x2)) - 0.5f + e) < ceilf(fminf(x0, fminf(x1, x2)) - 0.5f - e)) return false;
+            if (floorf(fmaxf(y0, fmaxf(y1, y2)) - 0.5f + e) < ceilf(fminf(y0, fminf(y1, y2)) - 0.5f - e)) return false;
+        }
+    }
     if (!tri_setup(cv, a.D, a.D, false, S.s)) return false;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { S.cvx[k] = cv[k].x; S.cvy[k] = cv[k].y; S.s.z[k] = cv[k].z; }   // the shader interpolates gl_Position.xyz (w == 1)
@@ -148,14 +161,14 @@ __device__ __forceinline__ bool frag_test(const FrameConst& fc, const VoxHead& S
 
 struct Shaded { V3 color, nenc; };
 // voxelize.frag:195-228
-__device__ __forceinline__ Shaded shade_fragment(const FrameConst& fc, const VoxHead& S, const ShadeIn& I, const float l[3], const DevTexture* __restrict__ tex,
+__device__ __forceinline__ Shaded shade_fragment(const FrameConst& fc, int material, float rho2, const ShadeIn& I, const float l[3], const DevTexture* __restrict__ tex,
                                                  const DevMaterial* __restrict__ mats, const float* __restrict__ shadow) {
     const V3 wp = interp3(l, I.w[0], I.w[1], I.w[2]);
     const V3 nn = interp3(l, I.n[0], I.n[1], I.n[2]);
     const float u = interp1(l, I.uv[0][0], I.uv[1][0], I.uv[2][0]), v = interp1(l, I.uv[0][1], I.uv[1][1], I.uv[2][1]);
     V3 col = mk3(0.f, 0.f, 0.f);
-    const int dt = mats[S.material].diffuse_tex;
-    if (dt >= 0) { const V4 a = sample2d(tex[dt], u, v, S.rho2); col = mk3(a.x, a.y, a.z); }
+    const int dt = mats[material].diffuse_tex;
+    if (dt >= 0) { const V4 a = sample2d(tex[dt], u, v, rho2); col = mk3(a.x, a.y, a.z); }
     const V3 N = normalize3(nn);
     Shaded out; out.nenc = mk3((N.x + 1.0f) * 0.5f, (N.y + 1.0f) * 0.5f, (N.z + 1.0f) * 0.5f);
     if (fc.p.voxelize_lighting) {
@@ -206,17 +219,17 @@ __device__ __forceinline__ void rgba8_avg_atomic(uint32_t* addr, float r, float 
 
 // the image atomic of the selected mode; `slot` is the fragment record reserved for MODE_SORTED
 template <int MODE>
-__device__ __forceinline__ void store_fragment(const VoxArgs& a, const VoxHead& S, const Shaded& sh, int D, int px, int py, int ix, int iy, int iz, uint32_t slot) {
+__device__ __forceinline__ void store_fragment(const VoxArgs& a, uint32_t tri, const Shaded& sh, int D, int px, int py, int ix, int iy, int iz, uint32_t slot) {
     const uint32_t o = (uint32_t)(((size_t)iz * D + iy) * D + ix);
     a.seg[o >> 3] = 1;                                                      // every writer stores the same byte
     if (MODE == MODE_SORTED) {
         if (slot >= a.frag_cap) { vct_flag_overflow(a.counters); return; }
         Frag f;
-        f.key = o; f.tri = S.tri; f.rank = (uint32_t)(py * D + px);
+        f.key = o; f.tri = tri; f.rank = (uint32_t)(py * D + px);
         f.next = atomicExch(a.color + o, slot + 1u);                       // push on the voxel's list
         if (f.next) a.displaced[f.next - 1u] = 1;                          // the previous head is no head any more
-        f.cr = sh.color.x; f.cg = sh.color.y; f.cb = sh.color.z; f.cw = 0u;
-        f.nr = sh.nenc.x; f.ng = sh.nenc.y; f.nb = sh.nenc.z; f.nw = 0u;
+        f.cr = sh.color.x; f.cg = sh.color.y; f.cb = sh.color.z; f.cw1 = rgba8_avg_insert(0u, sh.color.x, sh.color.y, sh.color.z);
+        f.nr = sh.nenc.x; f.ng = sh.nenc.y; f.nb = sh.nenc.z; f.nw1 = rgba8_avg_insert(0u, sh.nenc.x, sh.nenc.y, sh.nenc.z);
         {   // streaming store of the 48-byte record (read once by k_voxel_resolve)
             const uint4* src = reinterpret_cast<const uint4*>(&f); uint4* dst = reinterpret_cast<uint4*>(a.frags + slot);
             __stcs(dst, src[0]); __stcs(dst + 1, src[1]); __stcs(dst + 2, src[2]);
@@ -231,58 +244,179 @@ __device__ __forceinline__ void store_fragment(const VoxArgs& a, const VoxHead& 
 }
 
 // ------------------------------------------------------------------------------------------------- bin
+// One thread per triangle: set-up, then the triangle's 8x4 tiles go to the tile queue.  A triangle whose pixel box fits one tile
+// pushes that tile itself (Sponza at 256^3: 50 k of the 56 k triangles that cover a pixel centre).  The others are listed in shared
+// memory and the whole CTA enumerates their tiles together — tile index -> triangle by binary search over a prefix sum, 32 tiles per
+// warp step, trivially rejected tiles dropped — so one large triangle does not serialise in its thread and no separate expand launch
+// (and grid drain) is needed.  Nothing is rasterised here: coverage belongs to k_voxel_tiles.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
     const FrameConst& fc = *a.fc;
-    const int D = a.D, lane = threadIdx.x & 31;
-    const bool occupancy = MODE == MODE_OCC;
-    unsigned counted = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n_round = (a.n_tris + 31u) & ~31u;                       // whole warps stay converged for the votes below
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+    __shared__ uint32_t s_slot[kThreads];                   // multi-tile triangles of this round: setup slot
+    __shared__ uint32_t s_pref[kThreads + 1];               // exclusive prefix sum of their tile counts
+    __shared__ uint32_t s_wsum[kThreads / 32];
+    __shared__ unsigned s_n[2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    if (threadIdx.x < 2) s_n[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * kThreads;
+    const uint32_t n_round = (a.n_tris + kThreads - 1u) / kThreads * kThreads;     // whole CTAs stay converged for the barriers below
+    int round = 0;
+    for (uint32_t t = blockIdx.x * kThreads + threadIdx.x; t < n_round; t += stride, round ^= 1) {
         VoxSetup S;
         const bool valid = t < a.n_tris && make_setup(a, fc, t, S);
-        const int bw = valid ? S.s.x1 - S.s.x0 + 1 : 0, bh = valid ? S.s.y1 - S.s.y0 + 1 : 0;
-        const bool tiny = valid && bw * bh <= kInlineArea;
-        // ---- tiny bounding boxes: coverage here; every fragment becomes one item of the pixel queue, so that the
-        //      (divergent, sparse) hits of many triangles are shaded by full warps in k_voxel_pixels
-        unsigned hits = 0;                                                   // bit i: pixel i of the (<= 4 pixel) box is a fragment
-        if (tiny) {
-            for (int i = 0; i < bw * bh; ++i) {
-                float l[3]; bool oob; int ix, iy, iz;
-                if (frag_test(fc, S, S.s.x0 + i % bw, S.s.y0 + i / bw, D, a.warpmap, occupancy, l, oob, ix, iy, iz)) { counted++; if (!oob) hits |= 1u << i; }
-            }
-        }
-        // ---- publish the setup of every triangle that still has work
-        const bool queued = valid && !tiny;
-        const bool need_slot = queued || hits != 0u;
-        const uint32_t sslot = reserve_slots(need_slot, &a.counters->setup_count);
+        const uint32_t sslot = reserve_slots(valid, &a.counters->setup_count);
         bool stored = false;
-        if (need_slot) {
+        if (valid) {
             if (sslot < a.setup_cap) { if (MODE != MODE_OCC) make_shading_setup(a, S); a.setups[sslot] = S; stored = true; }
             else vct_flag_overflow(a.counters);
         }
-        {   // pixel items: warp prefix sum -> one atomic per warp
-            const int nh = stored ? __popc(hits) : 0;
-            int inc = nh;
+        const int bw = stored ? S.s.x1 - S.s.x0 + 1 : 0, bh = stored ? S.s.y1 - S.s.y0 + 1 : 0;
+        const int ntx = (bw + kTileW - 1) / kTileW, nty = (bh + kTileH - 1) / kTileH;
+        // ---- single-tile triangles: one queue push per warp
+        const bool single = stored && ntx * nty == 1;
+        const unsigned sm = __ballot_sync(0xffffffffu, single);
+        if (sm) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(a.q.tile_count, (unsigned)__popc(sm));
+            const uint32_t pos = __shfl_sync(0xffffffffu, base, 0) + __popc(sm & lt_mask);
+            if (single) { if (pos < a.q.tile_cap) a.q.tiles[pos] = make_uint2(sslot, (unsigned)S.s.x0 | (unsigned)S.s.y0 << 16); else vct_flag_overflow(a.counters); }
+        }
+        // ---- multi-tile triangles: listed, then expanded by the whole CTA
+        const bool multi = stored && ntx * nty > 1;
+        uint32_t li = 0;
+        if (multi) { li = atomicAdd(&s_n[round], 1u); s_slot[li] = sslot; s_pref[li] = (uint32_t)(ntx * nty); }
+        __syncthreads();                                     // list complete; the setups written above are visible to the CTA
+        const unsigned n_multi = s_n[round];
+        if (threadIdx.x == 0) s_n[round ^ 1] = 0u;           // next round's counter (its pushes come after the barrier at the end)
+        if (n_multi) {                                       // uniform over the CTA
+            // exclusive prefix sum of the tile counts (n_multi <= kThreads)
+            const uint32_t mine = threadIdx.x < n_multi ? s_pref[threadIdx.x] : 0u;
+            uint32_t inc = mine;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-            const int total = __shfl_sync(0xffffffffu, inc, 31);
-            if (total) {
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) s_wsum[wid] = inc;
+            __syncthreads();
+            uint32_t woff = 0;
+            for (int k = 0; k < wid; ++k) woff += s_wsum[k];
+            uint32_t total = 0;
+            for (int k = 0; k < kThreads / 32; ++k) total += s_wsum[k];
+            __syncthreads();                                 // every thread has read its own count
+            if (threadIdx.x < n_multi) s_pref[threadIdx.x] = woff + inc - mine;
+            if (threadIdx.x == 0) s_pref[n_multi] = total;
+            __syncthreads();
+            for (uint32_t c0 = wid * 32u; c0 < total; c0 += kThreads) {
+                const uint32_t c = c0 + lane;
+                bool keep = false; int ox = 0, oy = 0; uint32_t slot = 0;
+                if (c < total) {
+                    int lo = 0, hi = (int)n_multi;           // largest j with s_pref[j] <= c
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pref[mid] <= c) lo = mid; else hi = mid; }
+                    slot = s_slot[lo];
+                    const TriSetup ts = a.setups[slot].s;
+                    const int tntx = (ts.x1 - ts.x0 + kTileW) / kTileW;
+                    const int local = (int)(c - s_pref[lo]), ty = local / tntx, tx = local - ty * tntx;
+                    ox = ts.x0 + tx * kTileW; oy = ts.y0 + ty * kTileH;
+                    keep = !tile_rejected(ts, ox, oy, min(ox + kTileW - 1, ts.x1), min(oy + kTileH - 1, ts.y1));
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (!m) continue;
                 uint32_t base = 0;
-                if (lane == 31) base = atomicAdd(a.q.pixel_count, (unsigned)total);
-                uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + (uint32_t)(inc - nh);
-                for (int i = 0; i < bw * bh && nh; ++i) {
-                    if (!(hits >> i & 1u)) continue;
-                    if (pos < a.q.pixel_cap) a.q.pixels[pos] = make_uint2(sslot, (unsigned)(S.s.x0 + i % bw) | (unsigned)(S.s.y0 + i / bw) << 16); else vct_flag_overflow(a.counters);
-                    ++pos;
+                if (lane == 0) base = atomicAdd(a.q.tile_count, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) {
+                    const uint32_t pos = base + __popc(m & lt_mask);
+                    if (pos < a.q.tile_cap) a.q.tiles[pos] = make_uint2(slot, (unsigned)ox | (unsigned)oy << 16); else vct_flag_overflow(a.counters);
                 }
             }
         }
-        // ---- everything else is cut into 8x4 tiles
-        stored = stored && queued;
-        enqueue_tiles(stored, S.s, sslot, a.q);
+        __syncthreads();                                     // list and prefix are free for the next round
     }
+}
+
+// ----------------------------------------------------------------------------------------------- tiles
+// Coverage and shading with every lane busy.  A tile item is (setup slot, origin); its candidate pixels are the part of the 8x4
+// tile inside the triangle's pixel box — 2 on average for the many small triangles, 32 for tiles inside large ones.  A warp takes
+// 32 items, one per lane, and walks the concatenation of their candidates 32 at a time (candidate -> item by a 5-step search over the
+// prefix sum held in the lanes): coverage, near/far clip and the voxel index of voxelize.frag:79-108 run on full warps whatever the
+// triangle sizes.  Fragments are collected in a per-warp ring in shared memory and shaded (voxelize.frag:195-228: albedo fetch,
+// lighting, 5-tap PCF) 32 at a time, so the expensive part runs on full warps too; the image atomic of the selected mode follows.
+struct Hit { uint32_t slot, pxy, vox; float l0, l1, l2; };          // vox = ix | iy << 10 | iz << 20 (dim <= 1024)
+constexpr int kRing = 64;
+template <int MODE>
+__device__ __forceinline__ void shade_batch(const VoxArgs& a, const FrameConst& fc, const Hit* __restrict__ ring, int head, int n) {
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (MODE == MODE_SORTED) {
+        if (lane == 0) base = atomicAdd(&a.counters->n_frag_slots, (unsigned)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+    }
+    if (lane >= n) return;
+    const Hit h = ring[(head + lane) & (kRing - 1)];
+    const VoxSetup* __restrict__ sp = a.setups + h.slot;
+    const uint32_t tri = sp->tri; const int material = sp->material; const float rho2 = sp->rho2;
+    const ShadeIn I = sp->in;
+    const float l[3] = {h.l0, h.l1, h.l2};
+    const Shaded sh = shade_fragment(fc, material, rho2, I, l, a.tex, a.mats, a.shadow);
+    store_fragment<MODE>(a, tri, sh, a.D, (int)(h.pxy & 0xFFFFu), (int)(h.pxy >> 16), (int)(h.vox & 1023u), (int)((h.vox >> 10) & 1023u), (int)(h.vox >> 20), base + (uint32_t)lane);
+}
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a) {
+    const FrameConst& fc = *a.fc;
+    __shared__ Hit s_ring[kThreads / 32][kRing];
+    const int D = a.D, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool occupancy = MODE == MODE_OCC;
+    Hit* ring = s_ring[wid];
+    const unsigned n_items = min(*a.q.tile_count, a.q.tile_cap);
+    const unsigned warps = gridDim.x * (kThreads / 32), gw = blockIdx.x * (kThreads / 32) + wid;
+    unsigned counted = 0; int head = 0, tail = 0;
+    for (unsigned base = gw * 32u; base < n_items; base += warps * 32u) {
+        // ---- one item per lane: origin and candidate box
+        uint32_t slot = 0; int ox = 0, oy = 0, iw = 1, cnt = 0;
+        if (base + lane < n_items) {
+            const uint2 it = __ldg(a.q.tiles + base + lane);
+            slot = it.x; ox = (int)(it.y & 0xFFFFu); oy = (int)(it.y >> 16);
+            const int4 bb = *reinterpret_cast<const int4*>(&a.setups[slot].s.x0);      // x0, x1, y0, y1
+            iw = min(kTileW, bb.y - ox + 1);
+            cnt = iw * min(kTileH, bb.w - oy + 1);
+        }
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        const int total = __shfl_sync(0xffffffffu, inc, 31), excl = inc - cnt;
+        for (int c0 = 0; c0 < total; c0 += 32) {
+            const int c = c0 + lane;
+            const bool cv = c < total;
+            int j = 0;                                       // largest lane whose exclusive prefix is <= c
+#pragma unroll
+            for (int st = 16; st; st >>= 1) { const int e = __shfl_sync(0xffffffffu, excl, j + st); if (e <= c) j += st; }
+            const uint32_t jslot = __shfl_sync(0xffffffffu, slot, j);
+            const int jox = __shfl_sync(0xffffffffu, ox, j), joy = __shfl_sync(0xffffffffu, oy, j), jw = __shfl_sync(0xffffffffu, iw, j);
+            const int local = c - __shfl_sync(0xffffffffu, excl, j);
+            const int ly = local / jw, px = jox + (local - ly * jw), py = joy + ly;
+            float l[3]; bool oob = false; int ix = 0, iy = 0, iz = 0;
+            bool frag = false;
+            if (cv) {
+                const VoxHead S = a.setups[jslot];
+                frag = frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
+            }
+            const bool hit = frag && !oob;
+            if (frag) counted++;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (!m) continue;
+            if (MODE == MODE_OCC) { if (hit) atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); continue; }
+            if (hit) {
+                Hit h; h.slot = jslot; h.pxy = (uint32_t)px | (uint32_t)py << 16; h.vox = (uint32_t)ix | (uint32_t)iy << 10 | (uint32_t)iz << 20;
+                h.l0 = l[0]; h.l1 = l[1]; h.l2 = l[2];
+                ring[(tail + __popc(m & lt_mask)) & (kRing - 1)] = h;
+            }
+            tail += __popc(m);
+            __syncwarp();
+            if (tail - head >= 32) { shade_batch<MODE>(a, fc, ring, head, 32); head += 32; __syncwarp(); }
+        }
+    }
+    if (MODE != MODE_OCC && tail > head) shade_batch<MODE>(a, fc, ring, head, tail - head);
     if (MODE != MODE_OCC) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
@@ -290,120 +424,29 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
     }
 }
 
-// ----------------------------------------------------------------------------------------------- tiles
-// one 8x4 tile of one triangle, one lane per pixel: coverage, voxel index, shading, image atomic
-template <int MODE>
-__device__ __forceinline__ void process_tile(const VoxArgs& a, const FrameConst& fc, unsigned sslot, int ox, int oy, unsigned& counted) {
-    const VoxHead S = a.setups[sslot];                                      // same address in every lane: broadcast
-    const int D = a.D, lane = threadIdx.x & 31;
-    const bool occupancy = MODE == MODE_OCC;
-    const int px = ox + (lane & (kTileW - 1)), py = oy + (lane >> 3);
-    float l[3]; bool oob = false; int ix = 0, iy = 0, iz = 0;
-    const bool frag = px <= S.s.x1 && py <= S.s.y1 && frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
-    const bool hit = frag && !oob;
-    if (frag) counted++;
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (!m) return;
-    if (MODE == MODE_OCC) { if (hit) atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); return; }
-    uint32_t base = 0;
-    if (MODE == MODE_SORTED) {
-        if (lane == 0) base = atomicAdd(&a.counters->n_frag_slots, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-    }
-    if (hit) {
-        const ShadeIn I = a.setups[sslot].in;
-        const Shaded sh = shade_fragment(fc, S, I, l, a.tex, a.mats, a.shadow);
-        store_fragment<MODE>(a, S, sh, D, px, py, ix, iy, iz, base + __popc(m & ((1u << lane) - 1u)));
-    }
-}
-template <int MODE>
-__device__ __forceinline__ void flush_counted(const VoxArgs& a, unsigned counted) {
-    if (MODE == MODE_OCC) return;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
-    if ((threadIdx.x & 31) == 0 && counted) atomicAdd(&a.counters->total_fragments, counted);
-}
-// single-tile triangles: the bin thread queued the tile itself
-template <int MODE>
-__device__ __forceinline__ void voxel_tiles_part(const VoxArgs& a, unsigned block, unsigned n_blocks) {
-    const FrameConst& fc = *a.fc;
-    const unsigned n_items = min(*a.q.tile_count, a.q.tile_cap);
-    const unsigned warps = n_blocks * (kThreads / 32);
-    unsigned counted = 0;
-    for (unsigned item = block * (kThreads / 32) + (threadIdx.x >> 5); item < n_items; item += warps) {
-        const uint2 it = __ldg(a.q.tiles + item);
-        process_tile<MODE>(a, fc, it.x, (int)(it.y & 0xFFFFu), (int)(it.y >> 16), counted);
-    }
-    flush_counted<MODE>(a, counted);
-}
-// ---------------------------------------------------------------------------------------------- pixels
-// One lane per queued pixel of a tiny triangle: every lane works on a different triangle (gathered loads), but the
-// control flow is uniform, so the shading runs at full warp efficiency.
-template <int MODE>
-__device__ __forceinline__ void voxel_pixels_part(const VoxArgs& a, unsigned block, unsigned n_blocks) {
-    const FrameConst& fc = *a.fc;
-    const int D = a.D, lane = threadIdx.x & 31;
-    const bool occupancy = MODE == MODE_OCC;
-    const unsigned n_items = min(*a.q.pixel_count, a.q.pixel_cap);
-    const unsigned stride = n_blocks * kThreads;
-    for (unsigned base = block * kThreads + (threadIdx.x & ~31u); base < n_items; base += stride) {
-        const unsigned item = base + lane;
-        bool hit = false; float l[3]; int ix = 0, iy = 0, iz = 0, px = 0, py = 0;
-        VoxHead S; unsigned sslot = 0;
-        if (item < n_items) {
-            const uint2 it = __ldg(a.q.pixels + item);
-            sslot = it.x;
-            S = a.setups[it.x];
-            px = (int)(it.y & 0xFFFFu); py = (int)(it.y >> 16);
-            bool oob = false;
-            hit = frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz) && !oob;      // true by construction
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (!m) continue;
-        if (MODE == MODE_OCC) { if (hit) atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); continue; }
-        uint32_t slot0 = 0;
-        if (MODE == MODE_SORTED) {
-            if (lane == 0) slot0 = atomicAdd(&a.counters->n_frag_slots, (unsigned)__popc(m));
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        }
-        if (hit) {
-            const ShadeIn I = a.setups[sslot].in;
-            const Shaded sh = shade_fragment(fc, S, I, l, a.tex, a.mats, a.shadow);
-            store_fragment<MODE>(a, S, sh, D, px, py, ix, iy, iz, slot0 + __popc(m & ((1u << lane) - 1u)));
-        }
-    }
-}
-
-// Tile items and single-pixel items are independent work queues: one launch, the first `tile_blocks` CTAs take tiles,
-// the rest take pixels, so the short pixel pass overlaps the tail of the tile pass instead of following it.
-// (Rasterising the bands of multi-tile triangles in here as well, instead of expanding them into the tile queue first,
-// was measured: 88 -> 195 us — a warp that owns a band works through its tiles one dependent chain after the other.)
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a, unsigned tile_blocks) {
-    if (blockIdx.x < tile_blocks) voxel_tiles_part<MODE>(a, blockIdx.x, tile_blocks);
-    else voxel_pixels_part<MODE>(a, blockIdx.x - tile_blocks, gridDim.x - tile_blocks);
-}
-
 // --------------------------------------------------------------------------------------------- resolve
-// One thread per fragment; the thread whose fragment is the head of its voxel's list replays the whole list in
-// canonical order and stores the final words.  Lists are short (Sponza max 10, typical 1); longer ones take the O(n^2)
-// selection path.  A head is a fragment that no later push displaced (`displaced` is set by the pusher and cleared
-// again here, so it needs no per-frame memset); voxelColor is not consulted, so the head can overwrite the list
-// pointer with the final colour in the same kernel.
+// One thread per fragment; the thread whose fragment is the head of its voxel's list (no later push displaced it: `displaced` is set
+// by the pusher and cleared again here, so it needs no per-frame memset) produces the voxel's final words.  One fragment in the
+// voxel — the common case (Sponza: 85 %) — and the words are the ones the fragment precomputed: 16 of the record's 48 bytes are
+// read.  Otherwise the list (Sponza: <= 10 entries) is ordered by (triangle, raster rank) in registers and the truncating average of
+// voxelize.frag:111-139 is replayed in that order; longer lists take the O(n^2) selection path.
+// TRANSFER: on a sparse frame without the temporal filter the head also does transferVoxels.comp:39-62 for its voxel (alpha ->
+// voxelSetOpacity, radiance <- (0,0,0,alpha), VoxelizeInfo counters) — every occupied voxel has exactly one head, the masked clear
+// has zeroed radiance in every flagged segment, and an unoccupied voxel keeps its zeros — so no separate transfer pass runs.
 constexpr int kSortMax = 24;
-__global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restrict__ frags, const Counters* __restrict__ counters, unsigned frag_cap,
-                                                            uint8_t* __restrict__ displaced, uint32_t* __restrict__ color, uint32_t* __restrict__ normal) {
+template <bool TRANSFER>
+__global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restrict__ frags, Counters* __restrict__ counters, unsigned frag_cap,
+                                                            uint8_t* __restrict__ displaced, uint32_t* __restrict__ color, uint32_t* __restrict__ normal,
+                                                            uint32_t* __restrict__ radiance, float opacity) {
     const unsigned n = min(counters->n_frag_slots, frag_cap);
+    unsigned uniq = 0, maxfrag = 0;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint4* rec = reinterpret_cast<const uint4*>(frags + i);      // flag and record loads in flight together
-        const uint4 r0 = __ldcs(rec), r1 = __ldcs(rec + 1), r2 = __ldcs(rec + 2);
+        const uint4 r0 = __ldcs(reinterpret_cast<const uint4*>(frags + i));      // key, next, cw1, nw1 (flag and record loads in flight together)
         if (displaced[i]) { displaced[i] = 0; continue; }
         const uint32_t key = r0.x;
-        uint32_t cw = 0u, nw = 0u;
-        if (r0.w == 0u) {                                                   // next == 0, the common case: a single fragment
-            cw = rgba8_avg_insert(0u, __uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z));
-            nw = rgba8_avg_insert(0u, __uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z));
-        } else {
+        uint32_t cw = r0.z, nw = r0.w;                                          // next == 0: a single fragment
+        if (r0.y != 0u) {
+            cw = 0u; nw = 0u;
             unsigned long long ord[kSortMax]; uint32_t idx[kSortMax];
             int cnt = 0; bool fits = true;
             for (uint32_t j = i + 1u; j; j = frags[j - 1u].next) {
@@ -433,13 +476,27 @@ __global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restri
                 }
             }
         }
+        if (TRANSFER) {                                                     // transferVoxels.comp:39-62, temporal filter off
+            const uint32_t a8 = cw >> 24;
+            if (a8) {
+                uniq++;
+                float aw = (float)a8 / 255.0f;
+                maxfrag = max(maxfrag, f2u_trunc(255.0f * aw));
+                if (opacity > 0.0f) aw = opacity;
+                const uint32_t ab = unorm8(aw) << 24;
+                cw = (cw & 0x00FFFFFFu) | ab;
+                radiance[key] = ab;
+            }
+        }
         color[key] = cw; normal[key] = nw;
+    }
+    if (TRANSFER) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { uniq += __shfl_xor_sync(0xffffffffu, uniq, o); maxfrag = max(maxfrag, __shfl_xor_sync(0xffffffffu, maxfrag, o)); }
+        if ((threadIdx.x & 31) == 0) { if (uniq) atomicAdd(&counters->unique_voxels, uniq); if (maxfrag) atomicMax(&counters->max_fragments_per_voxel, maxfrag); }
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_voxel_expand(const VoxSetup* __restrict__ setups, TileQueues q) {
-    expand_items(reinterpret_cast<const unsigned char*>(setups), sizeof(VoxSetup), q);
-}
 __global__ void k_voxel_reset(Counters* c) { c->overflow = 0; c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
 
 // ================================================================ tessellation voxeliser (reference default)
@@ -540,12 +597,10 @@ __global__ void __launch_bounds__(kThreads) k_voxel_tess(VoxArgs a) {
 }
 
 template <int MODE>
-int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* tiles_name, const char* pixels_name) {
+int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* tiles_name) {
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_voxel_bin<MODE><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, bin_name);
-    k_voxel_expand<<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a.setups, a.q); VCT_LAUNCH_CHECK(c, "k_voxel_expand");
-    (void)pixels_name;
-    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 10, kThreads, 0, c->stream>>>(a, VCT_SM_COUNT * 8); VCT_LAUNCH_CHECK(c, tiles_name);   // tiles + pixels
+    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 6, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, tiles_name);
     return 0;
 }
 
@@ -579,7 +634,8 @@ int vctk_transform_vertices(vct_ctx* c) {
     return 0;
 }
 
-int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset) {
+int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset, bool fuse_transfer, bool* transfer_done) {
+    if (transfer_done) *transfer_done = false;
     if (!c->n_tris) return 0;
     const vct_frame_params& p = c->h_fc.p;
     VoxArgs a{};
@@ -598,7 +654,7 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset) {
     if (occupancy) {
         VCT_CHECK(c, cudaMemsetAsync(c->d_occ, 0, sizeof(uint32_t) * VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM, c->stream));
         vct_prof_mark(c, "memset");
-        return run_mode<MODE_OCC>(c, a, "k_voxel_bin_occ", "k_voxel_tiles_occ", "k_voxel_pixels_occ");
+        return run_mode<MODE_OCC>(c, a, "k_voxel_bin_occ", "k_voxel_tiles_occ");
     }
     if (p.voxelize_tesselation) {                               // the reference's default voxeliser: no rasterisation at all
         const int grid = (int)std::min<size_t>((c->n_tris * 32 + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
@@ -606,10 +662,13 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset) {
         else { k_voxel_tess<MODE_CAS><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, "k_voxel_tess_cas"); }
         return 0;
     }
-    if (p.voxelize_atomic_max) return run_mode<MODE_MAX>(c, a, "k_voxel_bin_max", "k_voxel_tiles_max", "k_voxel_pixels_max");
-    if (!p.deterministic) return run_mode<MODE_CAS>(c, a, "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_pixels_cas");
-    // deterministic running average: per-voxel lists, then ordered sequential replay
-    if (run_mode<MODE_SORTED>(c, a, "k_voxel_bin", "k_voxel_tiles", "k_voxel_pixels")) return 1;
-    k_voxel_resolve<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal); VCT_LAUNCH_CHECK(c, "k_voxel_resolve");
+    if (p.voxelize_atomic_max) return run_mode<MODE_MAX>(c, a, "k_voxel_bin_max", "k_voxel_tiles_max");
+    if (!p.deterministic) return run_mode<MODE_CAS>(c, a, "k_voxel_bin_cas", "k_voxel_tiles_cas");
+    // deterministic running average: per-voxel lists, then ordered sequential replay (fused with transferVoxels when the caller asks)
+    if (run_mode<MODE_SORTED>(c, a, "k_voxel_bin", "k_voxel_tiles")) return 1;
+    if (fuse_transfer) k_voxel_resolve<true><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, p.voxel_set_opacity);
+    else k_voxel_resolve<false><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, 0.0f);
+    VCT_LAUNCH_CHECK(c, "k_voxel_resolve");
+    if (transfer_done) *transfer_done = fuse_transfer;
     return 0;
 }

@@ -6,6 +6,7 @@
 //   vct_headless scene.vcts|mesh.obj [--scale s] [--resources dir] [--dim 256] [--levels 6] [--size 1920x1080] [--shadow 4096] [--frames 3]
 //                [--camera x y z yaw pitch | --eye x y z --front fx fy fz] [--volume min max] [--center x y z]
 //                [--no-reflections] [--atomic-max] [--tesselation] [--tesselation-warp] [--warp-texture] [--warp-voxels] [--temporal] [--fused] [--out frame.ppm]
+//                [--gpus N] (one process driving N devices: z-slab sharded frames, image on device 0) [--track-camera]
 // Exit status: 0 ok, 1 a pass reported an error (message on stderr), 2 usage.  There is no CPU fallback: without a
 // CUDA device vct_create fails and the driver exits 1.
 #include <chrono>
@@ -31,13 +32,14 @@ int main(int argc, char** argv) {
                      "usage: vct_headless scene.vcts|mesh.obj [--scale s] [--resources dir] [--dim D] [--levels L] [--size WxH] [--shadow S] [--frames N]\n"
                      "       [--camera x y z yaw pitch | --eye x y z --front fx fy fz] [--volume min max] [--center x y z]\n"
                      "       [--no-reflections] [--atomic-max] [--tesselation] [--tesselation-warp] [--warp-texture] [--warp-voxels] [--temporal] [--fused] [--out frame.ppm]\n"
+                     "       [--gpus N] [--track-camera]\n"
                      "       [--view voxels|normals|dominant-axis|occlusion|indirect|reflections|material-diffuse|material-roughness|material-metallic] [--miplevel x]\n");
         return argc < 2 ? 2 : 0;
     }
     Application app;
     app.width = 1920; app.height = 1080;
     app.camera.position = {5, 1, 0}; app.camera.yaw = 180.0f;           // reference start pose, Application.cpp:139-141
-    int frames = 3, shadow = Application::SHADOWMAP_WIDTH; bool fused = false; const char* out = nullptr;
+    int frames = 3, shadow = Application::SHADOWMAP_WIDTH, gpus = 0; bool fused = false; const char* out = nullptr;
     float scale = 1.0f; std::string resources;
     auto need = [&](int i, int n) { if (i + n >= argc) { std::fprintf(stderr, "missing value after %s\n", argv[i]); std::exit(2); } };
     for (int i = 2; i < argc; ++i) {
@@ -72,6 +74,8 @@ int main(int argc, char** argv) {
         }
         else if (a == "--miplevel") { need(i, 1); app.settings.miplevel = (float)std::atof(argv[++i]); }
         else if (a == "--fused") fused = true;
+        else if (a == "--gpus") { need(i, 1); gpus = std::atoi(argv[++i]); fused = true; }   // one process, N devices: the sharded frame is vct_frame's
+        else if (a == "--track-camera") app.settings.voxelTrackCamera = true;
         else if (a == "--out") { need(i, 1); out = argv[++i]; }
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -83,7 +87,7 @@ int main(int argc, char** argv) {
         scene.addReferenceLights();
     } else if (!scene.load(argv[1])) return 1;
     if (scene.lights.empty()) { std::fprintf(stderr, "[ERROR] scene has no light (Application.cpp:125-130 needs the shadow-casting main light)\n"); return 1; }
-    if (!app.init(&scene, shadow)) return 1;
+    if (!app.init(&scene, shadow, 0, gpus)) return 1;
     bool ok = true;
     const auto t0 = std::chrono::steady_clock::now();
     for (int f = 0; f < frames; ++f) ok &= fused ? app.renderFused(1.0f / 60.0f) : app.render(1.0f / 60.0f);
@@ -91,11 +95,11 @@ int main(int argc, char** argv) {
     const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (frames > 0 ? frames : 1);
     std::vector<uint8_t> rgba;
     ok &= app.readPixels(rgba);
-    unsigned long long sum = 0; for (uint8_t b : rgba) sum += b;
+    unsigned long long sum = 0, fnv = 1469598103934665603ull; for (uint8_t b : rgba) { sum += b; fnv = (fnv ^ b) * 1099511628211ull; }
     std::printf("{\"frames\": %d, \"wall_ms_per_frame\": %.4f, \"total_fragments\": %u, \"unique_voxels\": %u, \"max_fragments_per_voxel\": %u, "
-                "\"image_byte_sum\": %llu, \"fused\": %s, \"timers_ms\": {\"voxelize\": %.4f, \"shadowmap\": %.4f, \"radiance\": %.4f, \"mipmap\": %.4f, \"render\": %.4f, \"total\": %.4f}, \"ok\": %s}\n",
+                "\"image_byte_sum\": %llu, \"image_fnv1a\": \"%016llx\", \"gpus\": %d, \"fused\": %s, \"timers_ms\": {\"voxelize\": %.4f, \"shadowmap\": %.4f, \"radiance\": %.4f, \"mipmap\": %.4f, \"render\": %.4f, \"total\": %.4f}, \"ok\": %s}\n",
                 frames, wall_ms, app.voxelizeInfo.total_fragments, app.voxelizeInfo.unique_voxels, app.voxelizeInfo.max_fragments_per_voxel,
-                sum, fused ? "true" : "false", app.timers.voxelize, app.timers.shadowmap, app.timers.radiance, app.timers.mipmap, app.timers.render, app.timers.total, ok ? "true" : "false");
+                sum, fnv, gpus > 1 ? gpus : 1, fused ? "true" : "false", app.timers.voxelize, app.timers.shadowmap, app.timers.radiance, app.timers.mipmap, app.timers.render, app.timers.total, ok ? "true" : "false");
     if (out && !write_ppm(out, rgba, app.width, app.height)) { std::fprintf(stderr, "[ERROR] cannot write %s\n", out); ok = false; }
     return ok ? 0 : 1;
 }

@@ -101,6 +101,7 @@ struct Settings {
     float miplevel = 0.0f;
     int voxelizeTesselation = false;    // Application.h:85 (reference default true; this host defaults to the north star's raster path)
     int voxelizeTesselationWarp = false;   // Application.h:102: the camera frustum as voxel grid (common.glsl:37-42)
+    int voxelTrackCamera = false;          // Application.h:86: the volume follows the camera, snapped to the coarsest mip cell (Application.cpp:187-191)
     int cooktorrance = true, enablePostprocess = true, enableNormalMap = true;
     int enableIndirect = true, enableDiffuse = true, enableSpecular = true, enableReflections = true;
     float ambientScale = 1.0f, reflectScale = 1.0f;
@@ -138,10 +139,11 @@ public:
     vec3 center{0, 0, 0}, min{-20, -20, -20}, max{20, 20, 20};
     vct_ctx* ctx = nullptr;
 
-    bool make(int shadow_size, int width, int height, int device = 0, int rank = 0, int world_size = 1) {
+    // n_devices > 1: one handle that shards every frame over devices 0..n-1 of this process (vct_config.n_devices)
+    bool make(int shadow_size, int width, int height, int device = 0, int rank = 0, int world_size = 1, int n_devices = 0) {
         vct_config cfg{};
         cfg.dim = voxelDim; cfg.levels = voxelLevels; cfg.shadow_size = shadow_size; cfg.width = width; cfg.height = height;
-        cfg.device = device; cfg.rank = rank; cfg.world_size = world_size;
+        cfg.device = device; cfg.rank = rank; cfg.world_size = world_size; cfg.n_devices = n_devices;
         if (vct_create(&cfg, &ctx)) { std::fprintf(stderr, "[ERROR] %s\n", vct_last_error(nullptr)); ctx = nullptr; return false; }
         return true;
     }
@@ -251,9 +253,9 @@ public:
     float clearColor[3] = {0.5294f, 0.8078f, 0.9216f}; // Application.cpp:41
 
     // Application::init: create the GPU resources and upload the scene (Mesh VAO/EBO/texture creation)
-    bool init(Scene* s, int shadow_size = SHADOWMAP_WIDTH, int device = 0) {
+    bool init(Scene* s, int shadow_size = SHADOWMAP_WIDTH, int device = 0, int n_devices = 0) {
         scene = s; shadow_size_ = shadow_size;
-        if (!vct.make(shadow_size, width, height, device)) return false;
+        if (!vct.make(shadow_size, width, height, device, 0, 1, n_devices)) return false;
         bool ok = true;
         for (size_t i = 0; i < s->textures.size(); ++i) {
             const Texture& t = s->textures[i];
@@ -319,8 +321,17 @@ public:
         return p;
     }
 
+    // Application::update's voxelTrackCamera block (src/Application.cpp:187-191): the volume centre follows the camera in steps of one
+    // coarsest-level cell, so that the voxelisation does not swim (glm::floor, glm::pow(2.f, levels) component-wise)
+    void trackCamera() {
+        if (!settings.voxelTrackCamera) return;
+        const float k = std::pow(2.0f, (float)vct.voxelLevels);
+        const vec3 cell{k * (vct.max.x - vct.min.x) / (float)vct.voxelDim, k * (vct.max.y - vct.min.y) / (float)vct.voxelDim, k * (vct.max.z - vct.min.z) / (float)vct.voxelDim};
+        vct.center = {std::floor(camera.position.x / cell.x) * cell.x, std::floor(camera.position.y / cell.y) * cell.y, std::floor(camera.position.z / cell.z) * cell.z};
+    }
     bool render(float /*dt*/) {
         if (!vct.ctx || !scene) return false;
+        trackCamera();
         bool ok = true;
         const Settings& s = settings;
         const vct_frame_params p = frameParams();
@@ -348,6 +359,7 @@ public:
     // the whole graph as ONE library call (same passes, pass-level timers filled like GLBufferedTimer::getTime)
     bool renderFused(float /*dt*/) {
         if (!vct.ctx || !scene) return false;
+        trackCamera();
         const vct_frame_params p = frameParams();
         bool ok = true;
         for (size_t a = 0; a < scene->actors.size(); ++a) ok &= ck(vct_set_actor_transform(vct.ctx, (int)a, scene->actors[a].model.m));

@@ -12,9 +12,12 @@ from .lib import VctError, load
 
 class Pipeline:
     def __init__(self, scene, dim=256, levels=6, shadow_size=4096, width=1280, height=720, device=0, rank=0,
-                 world_size=1, max_fragments=0):
+                 world_size=1, max_fragments=0, devices=None):
+        """devices: a list of CUDA ordinals -> ONE handle driving all of them from this process (vct_config.n_devices)."""
         self.lib = load()
-        self.cfg = P.Config(dim, levels, shadow_size, width, height, device, rank, world_size, max_fragments)
+        self._devices = (C.c_int * len(devices))(*devices) if devices else None
+        self.cfg = P.Config(dim, levels, shadow_size, width, height, device, rank, world_size, max_fragments,
+                            len(devices) if devices else 0, self._devices)
         h = C.c_void_p()
         if self.lib.vct_create(C.byref(self.cfg), C.byref(h)):
             raise VctError(self.lib.vct_last_error(None).decode())
@@ -73,18 +76,16 @@ class Pipeline:
     def exchange(self): self._ck(self.lib.vct_exchange(self.h))
     def frame_was_sparse(self): return bool(self.lib.vct_frame_was_sparse(self.h))
     def mask_parity(self): return int(self.lib.vct_mask_parity(self.h))
-    def exchange_push(self): self._ck(self.lib.vct_exchange_push(self.h))
-    def exchange_unpack(self): self._ck(self.lib.vct_exchange_unpack(self.h))
 
     def exchange_setup(self):
-        """Allocate the sparse-exchange staging buffer and return its 64-byte cudaIpc handle."""
+        """Allocate the slab-exchange staging buffer and return this rank's cudaIpc handle blob (one process per GPU)."""
         self._ck(self.lib.vct_exchange_setup(self.h))
-        buf = C.create_string_buffer(64)
+        buf = C.create_string_buffer(P.EXCHANGE_HANDLE_BYTES)
         self._ck(self.lib.vct_exchange_export(self.h, buf))
         return bytes(buf.raw)
 
     def exchange_import(self, rank, handle):
-        self._ck(self.lib.vct_exchange_import(self.h, rank, C.create_string_buffer(handle, 64)))
+        self._ck(self.lib.vct_exchange_import(self.h, rank, C.create_string_buffer(handle, P.EXCHANGE_HANDLE_BYTES)))
     def gbuffer(self, p): self._ck(self.lib.vct_gbuffer(self.h, C.byref(p)))
     def cone_trace(self, p): self._ck(self.lib.vct_cone_trace(self.h, C.byref(p)))
     def frame(self, p): self._ck(self.lib.vct_frame(self.h, C.byref(p)))

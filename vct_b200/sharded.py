@@ -1,15 +1,17 @@
-"""One frame of the GI hot path on 1..N GPUs, one process per GPU.
+"""One frame of the GI hot path on 1..N GPUs, one process per GPU — a THIN caller: the library runs the
+whole sharded frame itself.
 
-world_size == 1   the frame is `vct_gi_passes` on the library's own stream.
-world_size  > 1   z-slab sharding: every rank clears / voxelises / transfers / injects / mip-filters the slab
-                  z in [rank*D/N, (rank+1)*D/N) of every level (BOX2 mips are aligned 2x2x2 reductions, so no
-                  halo is needed while a slab is at least one texel thick at the coarsest level); then ONE exchange
-                  step — an in-place NCCL all-gather per pyramid level, coalesced into a single group launch over
-                  NVLink — gives every rank the whole radiance pyramid; `vct_exchange` publishes it to the 3D
-                  texture; the cone trace is sharded by screen band and the bands are all-gathered into the image.
-                  The library enqueues on torch's current stream, so the collectives need no host synchronisation.
+world_size == 1   the frame is `vct_gi_passes` (or `vct_frame`) on the library's own stream.
+world_size  > 1   once, at start-up, the ranks swap their cudaIpc handle blobs (`vct_exchange_export` / `_import`; the only use of
+                  torch.distributed here, `all_gather_object`).  After that `vct_gi_passes` / `vct_frame` does everything on the
+                  device: voxel passes on the own z-slab [rank*D/N, (rank+1)*D/N), the slab exchange over NVLink peer memory
+                  with device-side flags (csrc/exchange.cu), the cone trace of the own 64x64 screen tiles, pixels stored into
+                  rank 0's image.  No collective, no host synchronisation, and the step is capturable in a CUDA graph.
+                  VCT_SPARSE_EXCHANGE=0 (or a backend other than NCCL) selects the round-1 protocol instead: per-level
+                  all-gather by the caller, `vct_exchange`, full-image trace on every rank.
 
-The partition maths (`slab_range`, `level_chunks`, `image_bands`) is pure Python and is unit-tested on CPU with gloo.
+The partition maths (`slab_range`, `level_chunks`, `tile_owner`, `image_bands`) is pure Python, mirrors the library's, and is
+unit-tested on CPU with gloo.
 """
 import ctypes as C
 import os
@@ -46,6 +48,20 @@ def image_bands(height, world):
     return band, [(min(height, r * band), min(height, (r + 1) * band)) for r in range(world)]
 
 
+SCREEN_TILE = 64
+
+
+def tile_owner(tx, ty, world):
+    """Rank that traces screen tile (tx, ty) of 64x64 pixels — diagonal stripes (cone_trace.cu ensure_trace_tiles)."""
+    return (tx + ty) % world
+
+
+def screen_tiles(width, height, world, rank):
+    """[(x0, y0)] of the tiles `rank` traces, in the order the library walks them."""
+    ntx, nty = (width + SCREEN_TILE - 1) // SCREEN_TILE, (height + SCREEN_TILE - 1) // SCREEN_TILE
+    return [(tx * SCREEN_TILE, ty * SCREEN_TILE) for ty in range(nty) for tx in range(ntx) if tile_owner(tx, ty, world) == rank]
+
+
 def all_gather_levels(dist, level_tensors, chunks, rank):
     """In-place all-gather of every level (rank r's chunk lives at [r*chunk, (r+1)*chunk) of the level tensor).
     Works for any backend (gloo on CPU in the tests, NCCL over NVLink in production)."""
@@ -72,40 +88,39 @@ class ShardedFrame:
         self.workload, self.frame_index = workload, 0
         self.whole_frame = bool(workload is not None and workload.whole_frame)
         self.torch = torch
+        self.graph = None
         g = pipeline
+        self.peer_exchange = False
         if world > 1:
             import torch.distributed as dist
             self.dist = dist
-            # A dedicated (non-default) stream shared by the library and the NCCL collectives: torch's default stream has
-            # handle 0, which vct_set_stream reads as "use a private stream" — the collectives would then not be ordered
-            # after the kernels that produce their input.
+            # a dedicated (non-default) stream: torch's default stream has handle 0, which vct_set_stream reads as "private stream"
             self.stream = torch.cuda.Stream()
             self.stream.wait_stream(torch.cuda.current_stream())
             g.set_stream(self.stream.cuda_stream)
-            which = P.VOL_RADIANCE if params.draw_radiance else P.VOL_COLOR
-            self.levels = [device_tensor(g.device_ptr(which, l), g.level_bytes(which, l)) for l in range(g.L)]
-            self.chunks = level_chunks(g.D, g.L, world)
-            self.band, self.bands = image_bands(g.H, world)
             self.image = device_tensor(g.device_ptr(P.BUF_IMAGE, 0), g.level_bytes(P.BUF_IMAGE, 0))
-            self.band_px = self.band * g.W
-            # sparse exchange of level 0 over peer memory (exchange.cu): every rank maps every other rank's staging buffer
-            self.sparse_exchange = False
             if os.environ.get("VCT_SPARSE_EXCHANGE", "1") != "0" and dist.get_backend() == "nccl":
                 handles = [None] * world
                 dist.all_gather_object(handles, g.exchange_setup())
                 for r, h in enumerate(handles):
                     g.exchange_import(r, h)
-                self.sparse_exchange = True
+                dist.barrier()                                   # every rank has mapped every peer before the first frame stores into them
+                self.peer_exchange = True
+            else:                                                # round-1 protocol: the caller moves the levels
+                which = P.VOL_RADIANCE if params.draw_radiance else P.VOL_COLOR
+                self.levels = [device_tensor(g.device_ptr(which, l), g.level_bytes(which, l)) for l in range(g.L)]
+                self.chunks = level_chunks(g.D, g.L, world)
         else:
             self.stream = torch.cuda.ExternalStream(g.lib.vct_stream(g.h))
 
     def describe(self):
         if self.world == 1:
             return "1 GPU"
-        ex = ("level 0 pushed as flagged x-row segments into every peer's memory over NVLink (cudaIpc), levels >= 1 by coalesced NCCL all-gather"
-              if self.sparse_exchange else "coalesced NCCL all-gather of the radiance pyramid")
-        return (f"{self.world} GPUs: z-slab sharding of clear/voxelise/transfer/inject/mip, {ex}, "
-                f"cone trace sharded by {self.band}-row screen band, NCCL all-gather of the image bands")
+        if self.peer_exchange:
+            return (f"{self.world} GPUs, one process each: z-slab sharding of clear/voxelise/transfer/inject/mip; slab exchange inside the library over NVLink peer memory "
+                    "(level 0 as flagged x-row segments into staging regions, levels >= 1 stored into the peers' pyramids, device-side flags, no collective); "
+                    "cone trace sharded by interleaved 64x64 screen tiles, pixels stored into rank 0's image")
+        return f"{self.world} GPUs: z-slab sharding, per-level NCCL all-gather of the traced pyramid by the caller, full-image cone trace on every rank"
 
     # producers of the reference frame graph that the GI step consumes (replicated on every rank)
     def producers(self, gbuffer=True):
@@ -116,38 +131,15 @@ class ShardedFrame:
         if gbuffer:
             g.gbuffer(p)
 
-    def _gather_levels(self, first):
-        dist, r = self.dist, self.rank
-        levels, chunks = self.levels[first:], self.chunks[first:]
-        try:
-            with dist._coalescing_manager(device=self.levels[0].device):
-                for t, n in zip(levels, chunks):
-                    dist.all_gather_into_tensor(t, t[r * n:(r + 1) * n])
-        except (AttributeError, TypeError, RuntimeError):
-            for t, n in zip(levels, chunks):
-                dist.all_gather_into_tensor(t, t[r * n:(r + 1) * n])
-
-    def _exchange(self):
-        """After vct_gi_passes: give every rank the whole traced pyramid, in its 3D texture.  Sparse frame: level 0 goes
-        as flagged segments through peer memory; the all-gather of the small levels in between is the barrier that
-        orders every rank's pushes before every rank's unpack.  Dense frame (the first, or after an invalidation): all
-        levels by all-gather, dense publish.  All ranks take the same branch (same call history)."""
-        g = self.g
-        if self.sparse_exchange and g.frame_was_sparse():
-            g.exchange_push()
-            self._gather_levels(1)
-            g.exchange_unpack()
-            return {}
-        self._gather_levels(0)
-        g.exchange()
-        return {}
-
-    # ---- CUDA graph: the step is ~25 short launches (+ 2 collectives); replaying a captured pair of steps removes the
-    # host from the loop.  TWO steps per graph because the segment masks swap roles every frame; the graph is only
-    # replayed at the mask parity it was captured at, and only while the frame parameters stay what they were.
+    # ---- CUDA graph: the step is ~15 short launches; replaying a captured pair of steps removes the host from the loop.  TWO steps
+    # per graph because the segment masks swap roles every frame; the graph is only replayed at the mask parity it was captured at,
+    # and only while the frame parameters stay what they were.  N > 1: the sharded step holds kernels only (flags, no collectives).
     def enable_graph(self):
         torch = self.torch
         self.graph, self.graph_error = None, None
+        if self.world > 1 and not self.peer_exchange:
+            self.graph_error = "caller-side all-gather protocol"
+            return False
         try:
             self.g.set_profiling(0)
             torch.cuda.synchronize()
@@ -168,7 +160,7 @@ class ShardedFrame:
         """k steps; pairs go through the captured graph when there is one.  Returns how many steps were replayed."""
         replayed = 0
         while k > 0:
-            if getattr(self, "graph", None) is not None and k >= 2 and self.g.mask_parity() == self.graph_parity:
+            if self.graph is not None and k >= 2 and self.g.mask_parity() == self.graph_parity:
                 with self.torch.cuda.stream(self.stream):
                     self.graph.replay()
                 k -= 2; replayed += 2
@@ -185,24 +177,24 @@ class ShardedFrame:
     def step(self):
         g, p = self.g, self.p
         self._animate()
-        if self.world == 1:
-            (g.frame if self.whole_frame else g.gi_passes)(p)
+        if self.world == 1 or self.peer_exchange:
+            (g.frame if self.whole_frame else g.gi_passes)(p)    # N > 1: the whole sharded frame, exchange and image hand-over included
             return
-        with self.torch.cuda.stream(self.stream):
+        with self.torch.cuda.stream(self.stream):                # round-1 protocol
             if self.whole_frame:
                 self.producers(gbuffer=False)
             g.gi_passes(p)
-            self._exchange()
+            all_gather_levels(self.dist, self.levels, self.chunks, self.rank)
+            g.exchange()
             if self.whole_frame:
                 g.gbuffer(p)
             g.cone_trace(p)
-            r, n = self.rank, self.band_px
-            self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
 
     def step_e2e(self, host_img, pipelined=False):
         """host_img: pinned int32 tensor of W*H pixels.  Frame parameters go host->device inside vct_gi_passes.
         pipelined (one GPU): the read-back is enqueued on the library's copy stream (vct_read_image_async) and overlaps the next
-        step's voxel passes; the caller alternates two host buffers and ends the loop with finish_e2e()."""
+        step's voxel passes; the caller alternates two host buffers and ends the loop with finish_e2e().
+        N > 1: rank 0 owns the finished image and reads it back on the frame's stream."""
         self.step()
         g = self.g
         if self.world == 1:
@@ -223,30 +215,18 @@ class ShardedFrame:
     def profiled_step(self):
         """Per-kernel times {name: (ns, launches)} of one step (library profiling level 2)."""
         g, p = self.g, self.p
-        self._animate()
-        if self.world == 1:
-            (g.frame if self.whole_frame else g.gi_passes)(p)
-            return g.kernel_times()
-        with self.torch.cuda.stream(self.stream):
-            g.gi_passes(p)
-            kt = g.kernel_times()
-            self._exchange(); kt2 = g.kernel_times()          # (kernels of the last library call of the exchange)
-            g.cone_trace(p); kt3 = g.kernel_times()
-            for extra in (kt2, kt3):
-                for k, (ns, n) in extra.items():
-                    a = kt.get(k, (0.0, 0)); kt[k] = (a[0] + ns, a[1] + n)
-            r, n = self.rank, self.band_px
-            self.dist.all_gather_into_tensor(self.image, self.image[r * n:(r + 1) * n])
-        return kt
+        self.step()
+        return g.kernel_times()
 
     def close(self):
-        """Drop the captured graph before the process group goes away (a graph that outlives NCCL's communicator hangs teardown)."""
+        """Drop the captured graph before the context and the process group go away."""
         self.graph = None
 
     def pass_times(self):
-        """Per-pass ms of one whole reference frame graph (GLTimer semantics; profiling level 1), incl. producers."""
+        """Per-pass ms of one step (GLTimer semantics; profiling level 1).  One GPU: of one whole reference frame graph incl. producers."""
         g, p = self.g, self.p
         if self.world > 1:
-            return {}
-        g.frame(p)
+            self.step()
+        else:
+            g.frame(p)
         return {k.replace("_ns", ""): round(v / 1e6, 4) for k, v in g.timings().items() if v > 0}
