@@ -123,7 +123,7 @@ def algorithmic_bytes(D, L, S, W, H, T, F, U, chains):
     }
 
 
-VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_expand", "k_voxel_tiles", "k_voxel_resolve",
+VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_tiles", "k_voxel_resolve", "k_voxel_resolve_long",
                     "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_bin_max", "k_voxel_tiles_max")
 
 
@@ -362,11 +362,16 @@ def run_b200(args):
         ab = {k: v / world for k, v in algorithmic_bytes(D, L, S, W, H, T, job_frag, job_vox, chains).items()}
         kt = {k: v[0] for k, v in kern.items()}
         kt["voxelize"] = sum(kt.get(k, 0.0) for k in VOXELIZE_KERNELS)
+        kt["k_inject"] = kt.get("k_inject", 0.0) + kt.get("k_inject_cull", 0.0)
+        if "k_transfer" not in kt and "k_voxel_resolve" in kt:
+            kt["k_transfer"] = 0.0                                   # sparse frame: transferVoxels runs inside k_voxel_resolve (counted under "voxelize")
         mt = measured_traffic() if (w.config == 3 and world == 1 and (D, W, H) == (256, 1920, 1080)) else {}
         mt["voxelize"] = sum(mt.get(k, 0) for k in ("k_transform_vertices", "k_voxel_bin", "k_voxel_expand", "k_voxel_tiles", "k_voxel_resolve")) or None
         roofs = []
         for name, nbytes in ab.items():
             t_ms = kt.get(name, 0.0)
+            if name == "voxelize" and kt.get("k_transfer") == 0.0:
+                nbytes += ab["k_transfer"]                           # the fused kernel does both jobs
             if t_ms <= 0:
                 continue
             ach = nbytes / (t_ms * 1e-3) / 1e9
@@ -427,16 +432,14 @@ def run_b200(args):
             if kind == "reference":
                 tp = cpu_frame(o, None, w, 2, stride)
                 cpu["port_ms"] = round(1e3 * sum(tp.values()), 1)       # the hand-written C++/OpenMP port of the same passes (bit-identical results)
-        cfg = w.config_dict()
-        cfg.update({"parallelism": fr.describe(),
-                    "sparse_frames": os.environ.get("VCT_SPARSE", "1") != "0",
-                    "cuda_graph": (f"{replayed} of {args.steps} timed steps replayed from a captured pair of steps" if use_graph else
-                                   f"off ({getattr(fr, 'graph_error', None) or ('animated workload: actor matrices change every frame' if w.animated else 'disabled')})"),
-                    "l2": "no explicit flush: the inputs of one step exceed the 126 MB L2 (shadow map 64 MiB + fragment records + visibility + scene geometry + texture pyramid + material textures), "
-                          "so every pass starts L2-cold for its own inputs; k_cone_trace measured standalone with warm L2 is ~60 us faster than inside the step"})
+        cfg = w.config_dict()                                       # identical in both arms (the driver compares them)
+        execution = {"parallelism": fr.describe(),
+                     "sparse_frames": os.environ.get("VCT_SPARSE", "1") != "0",
+                     "cuda_graph": (f"{replayed} of {args.steps} timed steps replayed from a captured pair of steps" if use_graph else
+                                    f"off ({getattr(fr, 'graph_error', None) or ('animated workload: actor matrices change every frame' if w.animated else 'disabled')})")}
         line = {"metric": metric_name(w), "value": round(ms, 4), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": round(ms, 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": w.data,
-                "config": cfg,
+                "config": cfg, "execution": execution,
                 "e2e": {"value": round(e2e_ms, 4), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "readback": "pipelined on a copy stream behind the next step's voxel passes (vct_read_image_async), 2 pinned host buffers" if pipelined
                                     else "synchronous after every step"},

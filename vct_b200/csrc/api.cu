@@ -14,6 +14,8 @@
 
 #include <cstddef>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 thread_local std::string g_create_error;
@@ -25,6 +27,11 @@ size_t vctk_image_rows(const vct_ctx*);
 namespace {
 
 int fail(vct_ctx* c, const char* msg) { c->error = msg; return 1; }
+
+// NVTX ranges around the launches of every pass, named like the reference's GLBufferedTimers (src/Application.h:192: voxelize,
+// shadowmap, radiance, mipmap, render, total) plus this build's extra passes; free when no tool is attached (header-only NVTX 3).
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
+struct NvtxPhases { bool open = false; void next(const char* name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = true; } ~NvtxPhases() { if (open) nvtxRangePop(); } };
 
 void free_volumes(vct_ctx* c) {
     for (int l = 0; l < VCT_MAX_LEVELS; ++l) {
@@ -137,7 +144,7 @@ int finalize_scene(vct_ctx* c) {
     // one setup per queued (sub-)triangle (camera pass: up to two after near clipping); tile queue sized for the
     // scene: every triangle may push one tile, plus headroom for the multi-tile ones
     c->setup_cap = 2 * nt + 64;
-    c->tile_queue_cap = 2 * nt + ((size_t)8 << 20);
+    c->tile_queue_cap = 6 * nt + ((size_t)8 << 20);      // (config 5, 64 Mi triangles: ~3 shadow-map tiles per triangle)
     VCT_CHECK(c, cudaMalloc(&c->d_setup, c->setup_cap * std::max(vctk_tile_setup_bytes(), vctk_vox_setup_bytes())));
     VCT_CHECK(c, cudaMalloc(&c->d_tile_queue, c->tile_queue_cap * 8));
     c->expand_cap = 2 * nt + ((size_t)1 << 20);
@@ -259,6 +266,8 @@ int gi_body(vct_ctx* c, Graph& g, bool cleared_by_frame_begin = false) {
     const FramePlan plan = plan_frame(c);
     const int n_chains = plan.n_chains, key = plan.key;
     const bool maskable = plan.maskable, sparse = plan.sparse;
+    NvtxPhases nv; nv.next("voxelize");                      // clear + voxelise, like the reference's voxelizeTimer (Application.cpp:583-755)
+    auto next_range = [&](const char* name) { nv.next(name); };
     if (cleared_by_frame_begin) {
         if (g.rec(EV_CLEAR)) return 1;
     } else if (sparse) {
@@ -272,11 +281,14 @@ int gi_body(vct_ctx* c, Graph& g, bool cleared_by_frame_begin = false) {
     // sparse frame, temporal filter off, deterministic raster voxeliser: the resolve kernel does transferVoxels for its voxels
     bool transfer_done = false;
     if (vctk_voxelize(c, false, true, sparse && !p.temporal_filter_radiance, &transfer_done) || g.rec(EV_VOXEL)) return 1;
+    next_range("transfer");
     if (!transfer_done && (sparse ? vctk_transfer_masked(c) : vctk_transfer(c))) return 1;
     if (g.rec(EV_TRANSFER)) return 1;
+    next_range("radiance");
     if (vctk_inject(c)) return 1;
     if (p.voxel_fill_holes) { if (ensure_scratch(c) || vctk_fill_holes(c)) return 1; }
     if (g.rec(EV_INJECT)) return 1;
+    next_range("mipmap");
     // single GPU: the chain that the cone tracer samples is written straight into its texture array
     // (sharded with attached peers: likewise for the own slab; the exchange publishes the remote slabs)
     const bool direct = single || vctk_xchg_ready(c);
@@ -368,8 +380,8 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * 8) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
-        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, (size_t)(c->S / 4 + 1) * (c->S / 4 + 1) * 8) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
-        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
+        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, ((size_t)(c->S / 4 + 1) * (c->S / 4 + 1) + (size_t)(c->S / 64 + 1) * (c->S / 16 + 1)) * 8) || alloc((void**)&c->d_inject_list, ((size_t)(c->S / 64 + 1) * (c->S / 16 + 1) + 1) * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
+        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc(&c->d_long_queue, (c->long_cap + 8) * 16) || alloc(&c->d_huge_items, c->frag_cap * 16) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
@@ -439,7 +451,7 @@ int vct_destroy(vct_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
     vctk_xchg_free(c);
-    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, c->d_shadow_mm, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, (void*)c->d_warp_scratch,
+    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, c->d_shadow_mm, (void*)c->d_inject_list, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, c->d_long_queue, c->d_huge_items, (void*)c->d_warp_scratch,
                     c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters, (void*)c->d_trace_tiles,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_wpos,
                     (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})
@@ -667,9 +679,10 @@ int vct_mask_parity(vct_ctx* c) { return c ? c->seg_cur : 0; }
 
 // tail of a sharded frame with attached peers: exchange, (visibility), cone trace of the own tiles, image hand-over to rank 0
 static int sharded_tail(vct_ctx* c, Graph& g, bool with_visibility) {
-    if (vctk_xchg_frame(c, !c->last_frame_sparse) || g.rec(EV_XCHG)) return 1;
-    if (with_visibility && vctk_visibility(c)) return 1;
+    { NvtxRange r("exchange"); if (vctk_xchg_frame(c, !c->last_frame_sparse) || g.rec(EV_XCHG)) return 1; }
+    if (with_visibility) { NvtxRange r("gbuffer"); if (vctk_visibility(c)) return 1; }
     if (g.rec(EV_GBUF)) return 1;
+    NvtxRange r("render");
     if (vctk_cone_trace(c) || vctk_xchg_image_sync(c)) return 1;
     return g.rec(EV_TRACE);
 }
@@ -684,21 +697,24 @@ int vct_gi_passes(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_gi_pas
     if (gi_body(c, g, fused_begin)) return 1;
     if (c->cfg.world_size > 1) return vctk_xchg_ready(c) ? sharded_tail(c, g, false) : 0;   // no peers: caller all-gathers, then vct_exchange + vct_cone_trace
     if (g.rec(EV_XCHG) || g.rec(EV_GBUF)) return 1;
+    NvtxRange r("render");
     if (vctk_cone_trace(c)) return 1;                         // cone_steps was zeroed by gi_body's clear
     return g.rec(EV_TRACE);
 }
 
 // Application::render in the reference's pass order (src/Application.cpp:196-1085)
 int vct_frame(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_frame(c, p));
+    NvtxRange total("total");
     PASS_PROLOGUE;
     Graph g{c, true};
     if (g.rec(EV_START)) return 1;
-    if (vctk_transform_vertices(c) || vctk_shadowmap(c) || vctk_shadow_minmax(c) || g.rec(EV_SHADOW)) return 1;
-    if (p->warp_texture) { if (vctk_voxelize(c, true) || vctk_warpmap(c)) return 1; }
+    { NvtxRange r("shadowmap"); if (vctk_transform_vertices(c) || vctk_shadowmap(c) || vctk_shadow_minmax(c) || g.rec(EV_SHADOW)) return 1; }
+    if (p->warp_texture) { NvtxRange r("warpmap"); if (vctk_voxelize(c, true) || vctk_warpmap(c)) return 1; }
     if (g.rec(EV_WARP)) return 1;
     if (gi_body(c, g)) return 1;
     if (c->cfg.world_size > 1) return vctk_xchg_ready(c) ? sharded_tail(c, g, true) : 0;
-    if (g.rec(EV_XCHG) || vctk_visibility(c) || g.rec(EV_GBUF)) return 1;
+    { NvtxRange r("gbuffer"); if (g.rec(EV_XCHG) || vctk_visibility(c) || g.rec(EV_GBUF)) return 1; }
+    NvtxRange r("render");
     if (vctk_cone_trace(c)) return 1;                         // cone_steps was zeroed by gi_body's clear
     return g.rec(EV_TRACE);
 }

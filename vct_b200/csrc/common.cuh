@@ -90,6 +90,7 @@ struct Counters {                // device-resident, zeroed per frame
     unsigned setup_count;        // big-triangle setups written by k_raster_bin
     unsigned overflow;           // set when a fixed-capacity buffer was too small (reset with the other per-frame counters)
     unsigned mip_ticket;         // k_mip_chain last-CTA detection (self-resetting)
+    unsigned long_count, huge_count, huge_items;   // deterministic voxeliser: queued long per-voxel lists (voxelize.cu)
     unsigned long long cone_steps;
     unsigned* overflow_host;     // the same flag in mapped pinned host memory: the frame entry points poll it without a device sync
 };
@@ -151,9 +152,11 @@ struct vct_ctx {
     uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
     // shadow map / visibility / image
     float* d_shadow = nullptr; unsigned long long* d_vis = nullptr; uint32_t* d_image = nullptr;
+    uint32_t* d_inject_list = nullptr;                              // k_inject_cull: [0] = count, [1..] = active 64x16 shadow-map blocks
     void* d_shadow_mm = nullptr; bool shadow_mm_valid = false;   // (S/4)^2 x float2: min / max filtered depth per 4x4 texel block (k_shadow_minmax)
     // voxel fragments (per-voxel linked lists of the deterministic running average)
     size_t frag_cap = 0; void* d_frags = nullptr; uint8_t* d_displaced = nullptr;
+    void* d_long_queue = nullptr; size_t long_cap = 65536; void* d_huge_items = nullptr;   // long per-voxel lists: queue (+ 8 huge entries behind it), scan buffer
     uint32_t* d_warp_scratch = nullptr;
     // raster work queue: 8-byte tile items + one setup record per queued (sub-)triangle
     void* d_tile_queue = nullptr; size_t tile_queue_cap = 0; void* d_expand_queue = nullptr; size_t expand_cap = 0;

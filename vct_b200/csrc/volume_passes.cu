@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4
     if (reset && blockIdx.x == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
         reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
-        reset->cone_steps = 0ull; reset->overflow = 0;
+        reset->cone_steps = 0ull; reset->overflow = 0; reset->long_count = 0; reset->huge_count = 0; reset->huge_items = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
@@ -53,7 +53,7 @@ __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uin
     if (block == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
         reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
-        reset->cone_steps = 0ull; reset->overflow = 0;
+        reset->cone_steps = 0ull; reset->overflow = 0; reset->long_count = 0; reset->huge_count = 0; reset->huge_items = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t t = w_lo + block * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)n_blocks * blockDim.x) {      // [w_lo, n_words): this rank's slab
@@ -382,13 +382,15 @@ struct InjectLinear {                                 // passed by value: no dep
     float m[16];                                      // ls_inverse, column-major
     int S, log2_qx, D, z_lo, z_hi;
     int skip_far;                                     // the light's far plane (depth 1 = nothing rendered) misses the volume by > 1 voxel
-    // Block skip: voxel coordinates are affine in (ndc x, ndc y, ndc depth): P_k = bx[k]*nx + by[k]*ny + bz[k]*nz + b0[k].  With the
-    // min / max filtered depth of a 4x4 texel block (k_shadow_minmax, written by the shadow pass) interval arithmetic bounds P over the
-    // block; a block that misses the volume — or this rank's z-slab — on one axis by more than the margin is left without loading a
-    // depth.  Sponza: 61 % of the blocks (tools/inject_block_coherence.py: no false verdict over all 1 Mi blocks).
-    const float2* minmax;                             // nullptr: no skip
+    // Block cull: voxel coordinates are affine in (ndc x, ndc y, ndc depth): P_k = bx[k]*nx + by[k]*ny + bz[k]*nz + b0[k].  With the
+    // min / max filtered depth of a 64x16 texel block (k_shadow_minmax*, written by the shadow pass) interval arithmetic bounds P over
+    // the block; k_inject_cull lists the blocks that can reach the volume — and this rank's z-slab — and k_inject_linear runs one CTA
+    // per listed block.  Sponza: 2/3 of the shadow map sees no geometry or lies outside the volume and is never read.
+    const float2* minmax;                             // coarse level (one entry per 64x16 texels); nullptr: every block is listed
+    const uint32_t* list;                             // [0] = number of active blocks, [1..] = block ids (k_inject_cull)
     float bx[3], by[3], bz[3], b0[3];
 };
+constexpr int kInjBlockW = 64, kInjBlockH = 16;      // texels per CTA of k_inject_linear: 16 threads x 4 texels wide, 16 rows
 constexpr float kInjectMargin = 0.02f;               // voxels; the float evaluation of the bound is good to ~1e-4 voxel
 
 // min / max over each 4x4 block of shadow texels of the depth injectRadiance.comp sees at the texel CORNER (LINEAR filter: the mean
@@ -413,6 +415,46 @@ __global__ void __launch_bounds__(256) k_shadow_minmax(const float* __restrict__
         }
     out[b] = make_float2(lo, hi);
 }
+// coarse level: min / max over the 16 x 4 fine entries of a 64x16 texel block
+__global__ void __launch_bounds__(256) k_shadow_minmax_coarse(const float2* __restrict__ fine, int S, float2* __restrict__ out) {
+    const int nbx = S / kInjBlockW, nby = S / kInjBlockH, b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= nbx * nby) return;
+    const int bx = b % nbx, by = b / nbx, nf = S >> 2;
+    float lo = 2.0f, hi = -1.0f;
+    for (int j = 0; j < kInjBlockH / 4; ++j)
+        for (int i = 0; i < kInjBlockW / 4; ++i) { const float2 v = __ldg(fine + (size_t)(by * (kInjBlockH / 4) + j) * nf + bx * (kInjBlockW / 4) + i); lo = fminf(lo, v.x); hi = fmaxf(hi, v.y); }
+    out[b] = make_float2(lo, hi);
+}
+// one CTA: which 64x16 texel blocks of the shadow map can land in the volume (and this rank's slab) this frame
+__global__ void __launch_bounds__(1024) k_inject_cull(const __grid_constant__ InjectLinear lin, uint32_t* __restrict__ list) {
+    __shared__ unsigned s_n;
+    if (threadIdx.x == 0) s_n = 0u;
+    __syncthreads();
+    const int S = lin.S, nbx = S / kInjBlockW, nb = nbx * (S / kInjBlockH);
+    const float inv_s = 1.0f / (float)S, fd = (float)lin.D;
+    for (int b = threadIdx.x; b < nb; b += 1024) {
+        bool active = true;
+        if (lin.minmax) {
+            const float2 mm = __ldg(lin.minmax + b);
+            const int x0 = (b % nbx) * kInjBlockW, y0 = (b / nbx) * kInjBlockH;
+            const float nx0 = ((float)x0 * inv_s) * 2.0f - 1.0f, nx1 = ((float)(x0 + kInjBlockW - 1) * inv_s) * 2.0f - 1.0f;
+            const float ny0 = ((float)y0 * inv_s) * 2.0f - 1.0f, ny1 = ((float)(y0 + kInjBlockH - 1) * inv_s) * 2.0f - 1.0f;
+            const float nz0 = mm.x * 2.0f - 1.0f, nz1 = mm.y * 2.0f - 1.0f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float ax0 = lin.bx[k] * nx0, ax1 = lin.bx[k] * nx1, ay0 = lin.by[k] * ny0, ay1 = lin.by[k] * ny1, az0 = lin.bz[k] * nz0, az1 = lin.bz[k] * nz1;
+                const float lo = ((fminf(ax0, ax1) + fminf(ay0, ay1)) + fminf(az0, az1)) + lin.b0[k];
+                const float hi = ((fmaxf(ax0, ax1) + fmaxf(ay0, ay1)) + fmaxf(az0, az1)) + lin.b0[k];
+                if (hi < -1.0f - kInjectMargin || lo > fd + kInjectMargin) active = false;           // (NaN compares false: stays active)
+                // this rank's z-slab [z_lo, z_hi): (int)P truncates toward zero, so slab 0 also owns P in (-1, 0)
+                if (k == 2 && (hi < (lin.z_lo > 0 ? (float)lin.z_lo : -1.0f) - kInjectMargin || lo > (float)lin.z_hi + kInjectMargin)) active = false;
+            }
+        }
+        if (active) list[1u + atomicAdd(&s_n, 1u)] = (uint32_t)b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) list[0] = s_n;
+}
 __device__ __forceinline__ float div_by_const(float a, float c, float rc) {
     const float q0 = __fmul_rn(a, rc);
     const float q1 = __fmaf_rn(__fmaf_rn(-q0, c, a), rc, q0);
@@ -422,23 +464,9 @@ __global__ void __launch_bounds__(256) k_inject_linear(const float* __restrict__
                                                        const __grid_constant__ InjectLinear lin) {
     const int S = lin.S, D = lin.D;
     const float inv_s = 1.0f / (float)S, fd = (float)D;                     // exact: S is a power of two
-    const int q = blockIdx.x * 256 + threadIdx.x;
-    const int x0 = (q & ((1 << lin.log2_qx) - 1)) * 4, y = q >> lin.log2_qx;
-    if (lin.minmax) {                                                        // the thread's 4 texels lie in one 4x4 block
-        const float2 mm = __ldg(lin.minmax + (size_t)(y >> 2) * (S >> 2) + (x0 >> 2));
-        const float nx0 = ((float)x0 * inv_s) * 2.0f - 1.0f, nx1 = ((float)(x0 + 3) * inv_s) * 2.0f - 1.0f;
-        const float ny0 = ((float)(y & ~3) * inv_s) * 2.0f - 1.0f, ny1 = ((float)((y & ~3) + 3) * inv_s) * 2.0f - 1.0f;
-        const float nz0 = mm.x * 2.0f - 1.0f, nz1 = mm.y * 2.0f - 1.0f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float ax0 = lin.bx[k] * nx0, ax1 = lin.bx[k] * nx1, ay0 = lin.by[k] * ny0, ay1 = lin.by[k] * ny1, az0 = lin.bz[k] * nz0, az1 = lin.bz[k] * nz1;
-            const float lo = ((fminf(ax0, ax1) + fminf(ay0, ay1)) + fminf(az0, az1)) + lin.b0[k];
-            const float hi = ((fmaxf(ax0, ax1) + fmaxf(ay0, ay1)) + fmaxf(az0, az1)) + lin.b0[k];
-            if (hi < -1.0f - kInjectMargin || lo > fd + kInjectMargin) return;                       // (NaN compares false: no skip)
-            // this rank's z-slab [z_lo, z_hi): (int)P truncates toward zero, so slab 0 also owns P in (-1, 0)
-            if (k == 2 && (hi < (lin.z_lo > 0 ? (float)lin.z_lo : -1.0f) - kInjectMargin || lo > (float)lin.z_hi + kInjectMargin)) return;
-        }
-    }
+    if (blockIdx.x >= __ldg(lin.list)) return;                              // CTA i works on the i-th active 64x16 texel block
+    const int blk = (int)__ldg(lin.list + 1 + blockIdx.x), nbx = S / kInjBlockW;
+    const int x0 = (blk % nbx) * kInjBlockW + (threadIdx.x & 15) * 4, y = (blk / nbx) * kInjBlockH + (threadIdx.x >> 4);
     const float* row1 = shadow + (size_t)y * S + x0;
     const float4 b = __ldcs(reinterpret_cast<const float4*>(row1));        // one-touch stream: evict first, keep L2 for the cone tracer's inputs
     const float bm1 = x0 > 0 ? __ldcs(row1 - 1) : 1.0f;                      // CLAMP_TO_BORDER, border 1
@@ -447,7 +475,8 @@ __global__ void __launch_bounds__(256) k_inject_linear(const float* __restrict__
     const float ta[5] = {am1, a.x, a.y, a.z, a.w}, tb[5] = {bm1, b.x, b.y, b.z, b.w};
     // Texels that saw no geometry (all four depths exactly 1) unproject onto the far plane; when the host has shown that
     // plane to lie outside the volume, the bounds test below would reject them anyway.
-    if (lin.skip_far && fminf(fminf(fminf(am1, bm1), fminf(fminf(a.x, a.y), fminf(a.z, a.w))), fminf(fminf(b.x, b.y), fminf(b.z, b.w))) == 1.0f) return;
+    // (a flag, not a return: the lanes of the warp meet again in the shuffle below)
+    const bool far = lin.skip_far && fminf(fminf(fminf(am1, bm1), fminf(fminf(a.x, a.y), fminf(a.z, a.w))), fminf(fminf(b.x, b.y), fminf(b.z, b.w))) == 1.0f;
     const float* m = lin.m;
     const float ny = ((float)y * inv_s) * 2.0f - 1.0f;
     const float my0 = m[4] * ny, my1 = m[5] * ny, my2 = m[6] * ny;
@@ -467,10 +496,10 @@ __global__ void __launch_bounds__(256) k_inject_linear(const float* __restrict__
         const float pz = fd * div_by_const(wz - lin.sub0[2] - lin.sub1[2], lin.c[2], lin.rc[2]);
         int ix, iy, iz;
         o[k] = 0xFFFFFFFFu;
-        if (to_voxel_index(mk3(px, py, pz), D, ix, iy, iz) && iz >= z_lo && iz < z_hi) o[k] = (uint32_t)((iz * D + iy) * D + ix);
+        if (!far && to_voxel_index(mk3(px, py, pz), D, ix, iy, iz) && iz >= z_lo && iz < z_hi) o[k] = (uint32_t)((iz * D + iy) * D + ix);
     }
     uint32_t left = __shfl_up_sync(0xffffffffu, o[3], 1);
-    if ((threadIdx.x & 31) == 0) left = 0xFFFFFFFFu;
+    if ((threadIdx.x & 15) == 0) left = 0xFFFFFFFFu;                        // 16 threads per texel row of the block
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (o[k] != 0xFFFFFFFFu && o[k] != left) radiance[o[k]] = __ldg(color + o[k]);     // packUnorm4x8(unpackUnorm4x8(c)) == c
@@ -832,7 +861,7 @@ int vctk_transfer_masked(vct_ctx* c) {
 int vctk_inject(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
     const bool pow2 = (c->S & (c->S - 1)) == 0 && c->S >= 32;
-    if (pow2 && !p.warp_voxels && !p.warp_texture && !p.voxelize_tesselation_warp && !p.radiance_lighting && c->D <= 1024) {
+    if (pow2 && c->S >= 64 && !p.warp_voxels && !p.warp_texture && !p.voxelize_tesselation_warp && !p.radiance_lighting && c->D <= 1024) {
         InjectLinear lin; bool sane = true;
         for (int i = 0; i < 3; ++i) {
             volatile float ext = p.voxel_max[i] - p.voxel_min[i];           // one fp32 rounding, like the shader's (max - min)
@@ -856,13 +885,17 @@ int vctk_inject(vct_ctx* c) {
                 lin.skip_far = 0;
                 for (int i = 0; i < 3; ++i) if (hi[i] < -2.0 || lo[i] > c->D + 2.0) lin.skip_far = 1;      // (NaN compares false: no skip)
             }
-            lin.minmax = c->shadow_mm_valid ? reinterpret_cast<const float2*>(c->d_shadow_mm) : nullptr;
+            const size_t n_fine = (size_t)(c->S / 4) * (c->S / 4);
+            lin.minmax = c->shadow_mm_valid ? reinterpret_cast<const float2*>(c->d_shadow_mm) + n_fine : nullptr;
+            lin.list = c->d_inject_list;
             for (int i = 0; i < 3; ++i) {                                   // D * ((ls_inverse * ndc)[i] - center - min) / (max - min), in double
                 const double k = (double)c->D / (double)lin.c[i];
                 lin.bx[i] = (float)(k * lin.m[i]); lin.by[i] = (float)(k * lin.m[4 + i]); lin.bz[i] = (float)(k * lin.m[8 + i]);
                 lin.b0[i] = (float)(k * ((double)lin.m[12 + i] - (double)lin.sub0[i] - (double)lin.sub1[i]));
             }
-            k_inject_linear<<<(unsigned)((size_t)c->S * c->S / 4 / 256), 256, 0, c->stream>>>(c->d_shadow, c->d_color, c->d_radiance, lin);
+            k_inject_cull<<<1, 1024, 0, c->stream>>>(lin, c->d_inject_list);
+            VCT_LAUNCH_CHECK(c, "k_inject_cull");
+            k_inject_linear<<<(unsigned)((c->S / kInjBlockW) * (c->S / kInjBlockH)), 256, 0, c->stream>>>(c->d_shadow, c->d_color, c->d_radiance, lin);
             VCT_LAUNCH_CHECK(c, "k_inject");
             return 0;
         }
@@ -882,7 +915,12 @@ int vctk_shadow_minmax(vct_ctx* c) {
     c->shadow_mm_valid = false;
     if (!c->d_shadow_mm || (c->S & (c->S - 1)) || c->S < 32) return 0;
     const int nb = c->S / 4;
-    k_shadow_minmax<<<(nb * nb + 255) / 256, 256, 0, c->stream>>>(c->d_shadow, c->S, reinterpret_cast<float2*>(c->d_shadow_mm));
+    if (c->S < 64) return 0;
+    float2* fine = reinterpret_cast<float2*>(c->d_shadow_mm);
+    k_shadow_minmax<<<(nb * nb + 255) / 256, 256, 0, c->stream>>>(c->d_shadow, c->S, fine);
+    VCT_LAUNCH_CHECK(c, "k_shadow_minmax");
+    const int ncoarse = (c->S / kInjBlockW) * (c->S / kInjBlockH);
+    k_shadow_minmax_coarse<<<(ncoarse + 255) / 256, 256, 0, c->stream>>>(fine, c->S, fine + (size_t)nb * nb);
     VCT_LAUNCH_CHECK(c, "k_shadow_minmax");
     c->shadow_mm_valid = true;
     return 0;

@@ -71,6 +71,21 @@ struct VoxArgs {
     Counters* counters;
 };
 
+// ---- long per-voxel lists (deterministic mode).  Normally a voxel holds 1-10 fragments.  A dense mesh on a coarse grid reaches a few
+// hundred, and a warp mode can pile a large part of the scene into ONE voxel (the reference's warp map is zero outside the 0.8-scaled
+// quad of quad.vert:12, so everything in the outer tenth of the volume is sampled towards voxel 0: 751 k of config 4's 2.0 M fragments).
+// What keeps this cheap and exact: imageAtomicRGBA8Avg forgets its history whenever the 8-bit count wraps to 0 (the next insertion
+// multiplies the stored colour by a weight of 0, voxelize.frag:127-133), so a voxel's final words depend only on the LAST
+// r = ((N - 1) mod 256) + 1 of its N fragments in canonical order.  k_voxel_tiles counts N per voxel in the (still unused) normal
+// volume; the resolve kernel handles N <= kSortMax itself and queues the rest: a warp per voxel up to kMedMax fragments (list walk,
+// bitonic sort in shared memory, replay of the last r), and for the few voxels beyond that a scan of ALL fragment records instead of a
+// walk of a 751 k-entry list: compact the voxel's (order key, slot) pairs, radix-select the r-th largest key, sort and replay those r.
+constexpr int kMedMax = 1024;
+constexpr int kHugeMax = 8;
+struct LongEntry { uint32_t key, head, count, pad; };               // voxel, head slot of its list, fragment count
+struct __align__(16) HugeItem { unsigned long long k; uint32_t slot, h; };   // order key + 1, fragment slot, index into the huge table
+struct LongArgs { LongEntry* queue; unsigned cap; LongEntry* huge; HugeItem* items; unsigned item_cap; };
+
 // voxelize.geom:26-73: axis from the summed vertex normals, projection through that axis' ortho view
 __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& fc, uint32_t t, VoxSetup& S) {
     const uint32_t i0 = __ldg(a.indices + 3 * (size_t)t), i1 = __ldg(a.indices + 3 * (size_t)t + 1), i2 = __ldg(a.indices + 3 * (size_t)t + 2);
@@ -219,15 +234,24 @@ __device__ __forceinline__ void rgba8_avg_atomic(uint32_t* addr, float r, float 
 
 // the image atomic of the selected mode; `slot` is the fragment record reserved for MODE_SORTED
 template <int MODE>
-__device__ __forceinline__ void store_fragment(const VoxArgs& a, uint32_t tri, const Shaded& sh, int D, int px, int py, int ix, int iy, int iz, uint32_t slot) {
+__device__ __forceinline__ void store_fragment(const VoxArgs& a, uint32_t tri, const Shaded& sh, int D, int px, int py, int ix, int iy, int iz, uint32_t slot, unsigned batch_mask) {
     const uint32_t o = (uint32_t)(((size_t)iz * D + iy) * D + ix);
     a.seg[o >> 3] = 1;                                                      // every writer stores the same byte
     if (MODE == MODE_SORTED) {
-        if (slot >= a.frag_cap) { vct_flag_overflow(a.counters); return; }
         Frag f;
         f.key = o; f.tri = tri; f.rank = (uint32_t)(py * D + px);
-        f.next = atomicExch(a.color + o, slot + 1u);                       // push on the voxel's list
-        if (f.next) a.displaced[f.next - 1u] = 1;                          // the previous head is no head any more
+        // Warp-aggregated push: the lanes of this batch that hit the same voxel chain their records among themselves (slots are
+        // consecutive: base + lane) and only the first of them touches the voxel — one atomicExch on the list head and one
+        // atomicAdd on the fragment count (kept in voxelNormal until the resolve overwrites it) per voxel per warp.
+        const unsigned grp = __match_any_sync(batch_mask, o);
+        const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+        const unsigned above = grp & ~((2u << lane) - 1u);                 // group members in higher lanes
+        uint32_t prev = 0u;
+        if (lane == leader) { prev = atomicExch(a.color + o, slot + 1u); atomicAdd(a.normal + o, (unsigned)__popc(grp)); }
+        prev = __shfl_sync(batch_mask, prev, leader);
+        f.next = above ? slot + (uint32_t)(__ffs(above) - 1 - lane) + 1u : prev;
+        if (lane != leader) a.displaced[slot] = 1;                         // only the leader's record can be a list head
+        else if (prev) a.displaced[prev - 1u] = 1;                         // the previous head is no head any more
         f.cr = sh.color.x; f.cg = sh.color.y; f.cb = sh.color.z; f.cw1 = rgba8_avg_insert(0u, sh.color.x, sh.color.y, sh.color.z);
         f.nr = sh.nenc.x; f.ng = sh.nenc.y; f.nb = sh.nenc.z; f.nw1 = rgba8_avg_insert(0u, sh.nenc.x, sh.nenc.y, sh.nenc.z);
         {   // streaming store of the 48-byte record (read once by k_voxel_resolve)
@@ -260,10 +284,15 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
     const unsigned lt_mask = (1u << lane) - 1u;
     if (threadIdx.x < 2) s_n[threadIdx.x] = 0u;
     __syncthreads();
-    const uint32_t stride = gridDim.x * kThreads;
-    const uint32_t n_round = (a.n_tris + kThreads - 1u) / kThreads * kThreads;     // whole CTAs stay converged for the barriers below
+    // Triangle t = (round * kThreads + thread) * gridDim + block: CONSECUTIVE triangles go to consecutive CTAs.  The large triangles of
+    // a scene come in runs (a wall, a floor: neighbours in the index buffer); spread over the grid their tiles are enumerated by many
+    // CTAs at once instead of queueing up in one (measured with block-contiguous triangles: 102 us for Sponza, the CTA that owned the
+    // atrium floor finished last).  The price is uncoalesced index loads (12 bytes per thread, a grid apart), 3 MB in all.
+    const uint32_t per_round = gridDim.x * kThreads;
+    const uint32_t n_rounds = (a.n_tris + per_round - 1u) / per_round;             // the same for every thread: the barriers below stay converged
     int round = 0;
-    for (uint32_t t = blockIdx.x * kThreads + threadIdx.x; t < n_round; t += stride, round ^= 1) {
+    for (uint32_t it = 0; it < n_rounds; ++it, round ^= 1) {
+        const uint32_t t = (it * kThreads + threadIdx.x) * gridDim.x + blockIdx.x;
         VoxSetup S;
         const bool valid = t < a.n_tris && make_setup(a, fc, t, S);
         const uint32_t sslot = reserve_slots(valid, &a.counters->setup_count);
@@ -274,14 +303,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
         }
         const int bw = stored ? S.s.x1 - S.s.x0 + 1 : 0, bh = stored ? S.s.y1 - S.s.y0 + 1 : 0;
         const int ntx = (bw + kTileW - 1) / kTileW, nty = (bh + kTileH - 1) / kTileH;
-        // ---- single-tile triangles: one queue push per warp
+        // ---- single-tile triangles: the small-item queue (a handful of candidate pixels each), one push per warp
         const bool single = stored && ntx * nty == 1;
         const unsigned sm = __ballot_sync(0xffffffffu, single);
         if (sm) {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(a.q.tile_count, (unsigned)__popc(sm));
+            if (lane == 0) base = atomicAdd(a.q.pixel_count, (unsigned)__popc(sm));
             const uint32_t pos = __shfl_sync(0xffffffffu, base, 0) + __popc(sm & lt_mask);
-            if (single) { if (pos < a.q.tile_cap) a.q.tiles[pos] = make_uint2(sslot, (unsigned)S.s.x0 | (unsigned)S.s.y0 << 16); else vct_flag_overflow(a.counters); }
+            if (single) { if (pos < a.q.pixel_cap) a.q.pixels[pos] = make_uint2(sslot, (unsigned)S.s.x0 | (unsigned)S.s.y0 << 16); else vct_flag_overflow(a.counters); }
         }
         // ---- multi-tile triangles: listed, then expanded by the whole CTA
         const bool multi = stored && ntx * nty > 1;
@@ -351,6 +380,7 @@ __device__ __forceinline__ void shade_batch(const VoxArgs& a, const FrameConst& 
         if (lane == 0) base = atomicAdd(&a.counters->n_frag_slots, (unsigned)n);
         base = __shfl_sync(0xffffffffu, base, 0);
     }
+    if (MODE == MODE_SORTED && base + (uint32_t)n > a.frag_cap) { if (lane == 0) vct_flag_overflow(a.counters); return; }   // the fragment buffer is full: drop the batch
     if (lane >= n) return;
     const Hit h = ring[(head + lane) & (kRing - 1)];
     const VoxSetup* __restrict__ sp = a.setups + h.slot;
@@ -358,7 +388,8 @@ __device__ __forceinline__ void shade_batch(const VoxArgs& a, const FrameConst& 
     const ShadeIn I = sp->in;
     const float l[3] = {h.l0, h.l1, h.l2};
     const Shaded sh = shade_fragment(fc, material, rho2, I, l, a.tex, a.mats, a.shadow);
-    store_fragment<MODE>(a, tri, sh, a.D, (int)(h.pxy & 0xFFFFu), (int)(h.pxy >> 16), (int)(h.vox & 1023u), (int)((h.vox >> 10) & 1023u), (int)(h.vox >> 20), base + (uint32_t)lane);
+    store_fragment<MODE>(a, tri, sh, a.D, (int)(h.pxy & 0xFFFFu), (int)(h.pxy >> 16), (int)(h.vox & 1023u), (int)((h.vox >> 10) & 1023u), (int)(h.vox >> 20), base + (uint32_t)lane,
+                         n >= 32 ? 0xffffffffu : (1u << n) - 1u);
 }
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a) {
@@ -368,14 +399,44 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a) {
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool occupancy = MODE == MODE_OCC;
     Hit* ring = s_ring[wid];
-    const unsigned n_items = min(*a.q.tile_count, a.q.tile_cap);
     const unsigned warps = gridDim.x * (kThreads / 32), gw = blockIdx.x * (kThreads / 32) + wid;
     unsigned counted = 0; int head = 0, tail = 0;
+    // one candidate pixel per lane: coverage, clip, voxel index; fragments go to the ring, a full ring batch is shaded
+    auto candidate = [&](bool cv, uint32_t slot, int px, int py) {
+        float l[3]; bool oob = false; int ix = 0, iy = 0, iz = 0;
+        bool frag = false;
+        if (cv) {
+            const VoxHead S = a.setups[slot];
+            frag = px <= S.s.x1 && py <= S.s.y1 && frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
+        }
+        const bool hit = frag && !oob;
+        if (frag) counted++;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (!m) return;
+        if (MODE == MODE_OCC) { if (hit) atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); return; }
+        if (hit) {
+            Hit h; h.slot = slot; h.pxy = (uint32_t)px | (uint32_t)py << 16; h.vox = (uint32_t)ix | (uint32_t)iy << 10 | (uint32_t)iz << 20;
+            h.l0 = l[0]; h.l1 = l[1]; h.l2 = l[2];
+            ring[(tail + __popc(m & lt_mask)) & (kRing - 1)] = h;
+        }
+        tail += __popc(m);
+        __syncwarp();
+        if (tail - head >= 32) { shade_batch<MODE>(a, fc, ring, head, 32); head += 32; __syncwarp(); }
+    };
+    // ---- part 1: the tiles of multi-tile triangles, one 8x4 tile per warp step (one lane per pixel), round-robin over all warps
+    {
+        const unsigned n_tiles = min(*a.q.tile_count, a.q.tile_cap);
+        for (unsigned item = gw; item < n_tiles; item += warps) {
+            const uint2 it = __ldg(a.q.tiles + item);
+            candidate(true, it.x, (int)(it.y & 0xFFFFu) + (lane & (kTileW - 1)), (int)(it.y >> 16) + (lane >> 3));
+        }
+    }
+    // ---- part 2: single-tile triangles, 32 per warp step, their candidate pixels concatenated
+    const unsigned n_items = min(*a.q.pixel_count, a.q.pixel_cap);
     for (unsigned base = gw * 32u; base < n_items; base += warps * 32u) {
-        // ---- one item per lane: origin and candidate box
         uint32_t slot = 0; int ox = 0, oy = 0, iw = 1, cnt = 0;
         if (base + lane < n_items) {
-            const uint2 it = __ldg(a.q.tiles + base + lane);
+            const uint2 it = __ldg(a.q.pixels + base + lane);
             slot = it.x; ox = (int)(it.y & 0xFFFFu); oy = (int)(it.y >> 16);
             const int4 bb = *reinterpret_cast<const int4*>(&a.setups[slot].s.x0);      // x0, x1, y0, y1
             iw = min(kTileW, bb.y - ox + 1);
@@ -387,33 +448,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a) {
         const int total = __shfl_sync(0xffffffffu, inc, 31), excl = inc - cnt;
         for (int c0 = 0; c0 < total; c0 += 32) {
             const int c = c0 + lane;
-            const bool cv = c < total;
             int j = 0;                                       // largest lane whose exclusive prefix is <= c
 #pragma unroll
             for (int st = 16; st; st >>= 1) { const int e = __shfl_sync(0xffffffffu, excl, j + st); if (e <= c) j += st; }
             const uint32_t jslot = __shfl_sync(0xffffffffu, slot, j);
             const int jox = __shfl_sync(0xffffffffu, ox, j), joy = __shfl_sync(0xffffffffu, oy, j), jw = __shfl_sync(0xffffffffu, iw, j);
             const int local = c - __shfl_sync(0xffffffffu, excl, j);
-            const int ly = local / jw, px = jox + (local - ly * jw), py = joy + ly;
-            float l[3]; bool oob = false; int ix = 0, iy = 0, iz = 0;
-            bool frag = false;
-            if (cv) {
-                const VoxHead S = a.setups[jslot];
-                frag = frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
-            }
-            const bool hit = frag && !oob;
-            if (frag) counted++;
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (!m) continue;
-            if (MODE == MODE_OCC) { if (hit) atomicOr(a.occ + ((size_t)iz * D + iy) * D + ix, 1u); continue; }
-            if (hit) {
-                Hit h; h.slot = jslot; h.pxy = (uint32_t)px | (uint32_t)py << 16; h.vox = (uint32_t)ix | (uint32_t)iy << 10 | (uint32_t)iz << 20;
-                h.l0 = l[0]; h.l1 = l[1]; h.l2 = l[2];
-                ring[(tail + __popc(m & lt_mask)) & (kRing - 1)] = h;
-            }
-            tail += __popc(m);
-            __syncwarp();
-            if (tail - head >= 32) { shade_batch<MODE>(a, fc, ring, head, 32); head += 32; __syncwarp(); }
+            const int ly = local / jw;
+            candidate(c < total, jslot, jox + (local - ly * jw), joy + ly);
         }
     }
     if (MODE != MODE_OCC && tail > head) shade_batch<MODE>(a, fc, ring, head, tail - head);
@@ -434,10 +476,29 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a) {
 // voxelSetOpacity, radiance <- (0,0,0,alpha), VoxelizeInfo counters) — every occupied voxel has exactly one head, the masked clear
 // has zeroed radiance in every flagged segment, and an unoccupied voxel keeps its zeros — so no separate transfer pass runs.
 constexpr int kSortMax = 24;
+__device__ __forceinline__ unsigned long long order_key(const Frag& f) { return ((unsigned long long)f.tri << 32 | f.rank) + 1ull; }   // canonical order; 0 = padding
+// final words of one voxel -> volumes; TRANSFER: transferVoxels.comp:39-62 for this voxel (temporal filter off)
+template <bool TRANSFER>
+__device__ __forceinline__ void finish_voxel(uint32_t key, uint32_t cw, uint32_t nw, uint32_t* __restrict__ color, uint32_t* __restrict__ normal, uint32_t* __restrict__ radiance,
+                                             float opacity, unsigned& uniq, unsigned& maxfrag) {
+    if (TRANSFER) {
+        const uint32_t a8 = cw >> 24;
+        if (a8) {
+            uniq++;
+            float aw = (float)a8 / 255.0f;
+            maxfrag = max(maxfrag, f2u_trunc(255.0f * aw));
+            if (opacity > 0.0f) aw = opacity;
+            const uint32_t ab = unorm8(aw) << 24;
+            cw = (cw & 0x00FFFFFFu) | ab;
+            radiance[key] = ab;
+        }
+    }
+    color[key] = cw; normal[key] = nw;
+}
 template <bool TRANSFER>
 __global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restrict__ frags, Counters* __restrict__ counters, unsigned frag_cap,
                                                             uint8_t* __restrict__ displaced, uint32_t* __restrict__ color, uint32_t* __restrict__ normal,
-                                                            uint32_t* __restrict__ radiance, float opacity) {
+                                                            uint32_t* __restrict__ radiance, float opacity, LongArgs lq) {
     const unsigned n = min(counters->n_frag_slots, frag_cap);
     unsigned uniq = 0, maxfrag = 0;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -446,49 +507,28 @@ __global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restri
         const uint32_t key = r0.x;
         uint32_t cw = r0.z, nw = r0.w;                                          // next == 0: a single fragment
         if (r0.y != 0u) {
+            const uint32_t count = normal[key];                                 // fragments of this voxel (counted by k_voxel_tiles)
+            if (count > (uint32_t)kSortMax) {                                   // long list: a warp (or the scan kernels) takes it
+                const unsigned pos = atomicAdd(&counters->long_count, 1u);
+                if (pos < lq.cap) { LongEntry e; e.key = key; e.head = i; e.count = count; e.pad = 0u; lq.queue[pos] = e; }
+                else vct_flag_overflow(counters);
+                continue;
+            }
             cw = 0u; nw = 0u;
             unsigned long long ord[kSortMax]; uint32_t idx[kSortMax];
-            int cnt = 0; bool fits = true;
-            for (uint32_t j = i + 1u; j; j = frags[j - 1u].next) {
-                if (cnt == kSortMax) { fits = false; break; }
-                const unsigned long long k = (unsigned long long)frags[j - 1u].tri << 32 | frags[j - 1u].rank;
+            int cnt = 0;
+            for (uint32_t j = i + 1u; j && cnt < kSortMax; j = frags[j - 1u].next) {
+                const unsigned long long k = order_key(frags[j - 1u]);
                 int p = cnt++;
                 while (p > 0 && ord[p - 1] > k) { ord[p] = ord[p - 1]; idx[p] = idx[p - 1]; --p; }
                 ord[p] = k; idx[p] = j - 1u;
             }
-            if (fits) {
-                for (int q = 0; q < cnt; ++q) {
-                    const Frag& f = frags[idx[q]];
-                    cw = rgba8_avg_insert(cw, f.cr, f.cg, f.cb); nw = rgba8_avg_insert(nw, f.nr, f.ng, f.nb);
-                }
-            } else {                                                        // long list: repeatedly pick the next key in order
-                unsigned long long last = 0; bool first = true;
-                for (;;) {
-                    unsigned long long best = ~0ull; uint32_t bi = 0; bool found = false;
-                    for (uint32_t j = i + 1u; j; j = frags[j - 1u].next) {
-                        const unsigned long long k = (unsigned long long)frags[j - 1u].tri << 32 | frags[j - 1u].rank;
-                        if ((first || k > last) && k <= best) { best = k; bi = j - 1u; found = true; }
-                    }
-                    if (!found) break;
-                    const Frag& f = frags[bi];
-                    cw = rgba8_avg_insert(cw, f.cr, f.cg, f.cb); nw = rgba8_avg_insert(nw, f.nr, f.ng, f.nb);
-                    last = best; first = false;
-                }
+            for (int q = 0; q < cnt; ++q) {
+                const Frag& f = frags[idx[q]];
+                cw = rgba8_avg_insert(cw, f.cr, f.cg, f.cb); nw = rgba8_avg_insert(nw, f.nr, f.ng, f.nb);
             }
         }
-        if (TRANSFER) {                                                     // transferVoxels.comp:39-62, temporal filter off
-            const uint32_t a8 = cw >> 24;
-            if (a8) {
-                uniq++;
-                float aw = (float)a8 / 255.0f;
-                maxfrag = max(maxfrag, f2u_trunc(255.0f * aw));
-                if (opacity > 0.0f) aw = opacity;
-                const uint32_t ab = unorm8(aw) << 24;
-                cw = (cw & 0x00FFFFFFu) | ab;
-                radiance[key] = ab;
-            }
-        }
-        color[key] = cw; normal[key] = nw;
+        finish_voxel<TRANSFER>(key, cw, nw, color, normal, radiance, opacity, uniq, maxfrag);
     }
     if (TRANSFER) {
 #pragma unroll
@@ -496,8 +536,145 @@ __global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restri
         if ((threadIdx.x & 31) == 0) { if (uniq) atomicAdd(&counters->unique_voxels, uniq); if (maxfrag) atomicMax(&counters->max_fragments_per_voxel, maxfrag); }
     }
 }
+// ascending bitonic sort of n2 (power of two) key/slot pairs in shared memory by `nthreads` cooperating threads (tid in [0, nthreads))
+__device__ __forceinline__ void bitonic_sort(unsigned long long* k, uint32_t* v, int n2, int tid, int nthreads, bool whole_block) {
+    for (int size = 2; size <= n2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (whole_block) __syncthreads(); else __syncwarp();
+            for (int t = tid; t < (n2 >> 1); t += nthreads) {
+                const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; const uint32_t x = v[lo]; v[lo] = v[hi]; v[hi] = x; }
+            }
+        }
+    if (whole_block) __syncthreads(); else __syncwarp();
+}
+// replay of the last r entries of an ascending key/slot array (entries [n2 - r, n2)) -> final words
+__device__ __forceinline__ void replay_last(const Frag* __restrict__ frags, const uint32_t* __restrict__ slots, int n2, int r, uint32_t& cw, uint32_t& nw) {
+    cw = 0u; nw = 0u;
+    for (int q = n2 - r; q < n2; ++q) {
+        const Frag& f = frags[slots[q]];
+        cw = rgba8_avg_insert(cw, f.cr, f.cg, f.cb); nw = rgba8_avg_insert(nw, f.nr, f.ng, f.nb);
+    }
+}
+// one warp per queued voxel with kSortMax < N <= kMedMax fragments; longer ones are entered into the huge table
+constexpr int kMedWarps = 2;
+template <bool TRANSFER>
+__global__ void __launch_bounds__(kMedWarps * 32) k_voxel_resolve_medium(const Frag* __restrict__ frags, Counters* __restrict__ counters, uint32_t* __restrict__ color,
+                                                                          uint32_t* __restrict__ normal, uint32_t* __restrict__ radiance, float opacity, LongArgs lq) {
+    __shared__ unsigned long long s_key[kMedWarps][kMedMax];
+    __shared__ uint32_t s_slot[kMedWarps][kMedMax];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned n = min(counters->long_count, lq.cap);
+    unsigned uniq = 0, maxfrag = 0;
+    for (unsigned e = blockIdx.x * kMedWarps + w; e < n; e += gridDim.x * kMedWarps) {
+        const LongEntry le = lq.queue[e];
+        if (le.count > (uint32_t)kMedMax) {
+            if (lane == 0) { const unsigned h = atomicAdd(&counters->huge_count, 1u); if (h < (unsigned)kHugeMax) lq.huge[h] = le; else vct_flag_overflow(counters); }
+            continue;
+        }
+        int cnt = 0;
+        if (lane == 0) for (uint32_t j = le.head + 1u; j && cnt < kMedMax; j = frags[j - 1u].next) s_slot[w][cnt++] = j - 1u;
+        cnt = __shfl_sync(0xffffffffu, cnt, 0);
+        int n2 = 32; while (n2 < cnt) n2 <<= 1;
+        __syncwarp();
+        for (int k = lane; k < n2; k += 32) {
+            if (k < cnt) s_key[w][k] = order_key(frags[s_slot[w][k]]); else { s_key[w][k] = 0ull; s_slot[w][k] = 0u; }
+        }
+        bitonic_sort(s_key[w], s_slot[w], n2, lane, 32, false);
+        if (lane == 0) {
+            uint32_t cw, nw;
+            replay_last(frags, s_slot[w], n2, ((cnt - 1) & 255) + 1, cw, nw);
+            finish_voxel<TRANSFER>(le.key, cw, nw, color, normal, radiance, opacity, uniq, maxfrag);
+        }
+        __syncwarp();
+    }
+    if (TRANSFER && lane == 0) { if (uniq) atomicAdd(&counters->unique_voxels, uniq); if (maxfrag) atomicMax(&counters->max_fragments_per_voxel, maxfrag); }
+}
+// huge voxels, step 1: every fragment record of a voxel in the huge table -> (order key, slot, table index)
+__global__ void __launch_bounds__(kThreads) k_voxel_huge_compact(const Frag* __restrict__ frags, Counters* __restrict__ counters, unsigned frag_cap, LongArgs lq) {
+    __shared__ uint32_t s_keys[kHugeMax];
+    const unsigned nh = min(counters->huge_count, (unsigned)kHugeMax);
+    if (!nh) return;
+    if (threadIdx.x < kHugeMax) s_keys[threadIdx.x] = threadIdx.x < nh ? lq.huge[threadIdx.x].key : 0xFFFFFFFFu;
+    __syncthreads();
+    const unsigned n = min(counters->n_frag_slots, frag_cap);
+    const int lane = threadIdx.x & 31;
+    const unsigned n_round = (n + 31u) & ~31u;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        int h = -1;
+        if (i < n) {
+            const uint32_t key = __ldg(&frags[i].key);
+#pragma unroll
+            for (int k = 0; k < kHugeMax; ++k) if (key == s_keys[k]) h = k;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, h >= 0);
+        if (!m) continue;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&counters->huge_items, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (h >= 0) {
+            const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < lq.item_cap) { HugeItem it; it.k = order_key(frags[i]); it.slot = i; it.h = (uint32_t)h; lq.items[pos] = it; }
+            else vct_flag_overflow(counters);
+        }
+    }
+}
+// huge voxels, step 2: one CTA per voxel.  Radix select (12-bit digits, top down) of the r-th largest order key among the voxel's
+// items, then the r items at or above it are sorted and replayed.
+constexpr int kSelThreads = 1024, kSelBins = 4096;
+template <bool TRANSFER>
+__global__ void __launch_bounds__(kSelThreads) k_voxel_huge_select(const Frag* __restrict__ frags, Counters* __restrict__ counters, uint32_t* __restrict__ color,
+                                                                    uint32_t* __restrict__ normal, uint32_t* __restrict__ radiance, float opacity, LongArgs lq) {
+    __shared__ unsigned s_hist[kSelBins];
+    __shared__ unsigned long long s_key[256]; __shared__ uint32_t s_slot[256];
+    __shared__ unsigned s_pick, s_need, s_n;
+    const unsigned nh = min(counters->huge_count, (unsigned)kHugeMax);
+    const unsigned h = blockIdx.x;
+    if (h >= nh) return;
+    const LongEntry le = lq.huge[h];
+    const unsigned n_items = min(counters->huge_items, lq.item_cap);
+    const int r = (int)((le.count - 1u) & 255u) + 1;
+    unsigned long long prefix = 0ull;                         // the digits of the r-th largest key fixed so far (top down)
+    unsigned need = (unsigned)r;                              // its rank (from the top) among the items that share the prefix
+    for (int shift = 60; shift >= 0; shift -= 12) {
+        for (int b = threadIdx.x; b < kSelBins; b += kSelThreads) s_hist[b] = 0u;
+        __syncthreads();
+        const unsigned long long hi_mask = shift + 12 >= 64 ? 0ull : ~0ull << (shift + 12);
+        for (unsigned i = threadIdx.x; i < n_items; i += kSelThreads) {
+            const HugeItem it = lq.items[i];
+            if (it.h == h && (it.k & hi_mask) == prefix) atomicAdd(&s_hist[(unsigned)(it.k >> shift) & (kSelBins - 1)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {                               // largest digit first: find the digit that holds the `need`-th largest
+            unsigned acc = 0; int b = kSelBins - 1;
+            for (; b > 0; --b) { if (acc + s_hist[b] >= need) break; acc += s_hist[b]; }
+            s_pick = (unsigned)b; s_need = need - acc;
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)s_pick << shift; need = s_need;
+        __syncthreads();
+    }
+    // prefix is now the r-th largest key: gather the r items with key >= prefix (keys are unique)
+    if (threadIdx.x == 0) s_n = 0u;
+    if (threadIdx.x < 256) { s_key[threadIdx.x] = 0ull; s_slot[threadIdx.x] = 0u; }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n_items; i += kSelThreads) {
+        const HugeItem it = lq.items[i];
+        if (it.h == h && it.k >= prefix) { const unsigned pos = atomicAdd(&s_n, 1u); if (pos < 256u) { s_key[pos] = it.k; s_slot[pos] = it.slot; } }
+    }
+    __syncthreads();
+    bitonic_sort(s_key, s_slot, 256, threadIdx.x, kSelThreads, true);
+    if (threadIdx.x == 0) {
+        uint32_t cw, nw; unsigned uniq = 0, maxfrag = 0;
+        replay_last(frags, s_slot, 256, min(r, (int)min(s_n, 256u)), cw, nw);
+        finish_voxel<TRANSFER>(le.key, cw, nw, color, normal, radiance, opacity, uniq, maxfrag);
+        if (TRANSFER) { if (uniq) atomicAdd(&counters->unique_voxels, uniq); if (maxfrag) atomicMax(&counters->max_fragments_per_voxel, maxfrag); }
+    }
+}
 
-__global__ void k_voxel_reset(Counters* c) { c->overflow = 0; c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
+__global__ void k_voxel_reset(Counters* c) { c->overflow = 0; c->long_count = 0; c->huge_count = 0; c->huge_items = 0; c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
 
 // ================================================================ tessellation voxeliser (reference default)
 // testTesselation.tesc/.tese + the fixed-function tessellator (triangles, equal_spacing, point_mode), Application.cpp:585-665.
@@ -666,9 +843,24 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset, bool 
     if (!p.deterministic) return run_mode<MODE_CAS>(c, a, "k_voxel_bin_cas", "k_voxel_tiles_cas");
     // deterministic running average: per-voxel lists, then ordered sequential replay (fused with transferVoxels when the caller asks)
     if (run_mode<MODE_SORTED>(c, a, "k_voxel_bin", "k_voxel_tiles")) return 1;
-    if (fuse_transfer) k_voxel_resolve<true><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, p.voxel_set_opacity);
-    else k_voxel_resolve<false><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, 0.0f);
+    // long per-voxel lists: queue + huge table + scan buffer.  The three extra launches leave at once when nothing was queued
+    // (a couple of microseconds per frame); they are what turns a pile-up from minutes into a fraction of a millisecond.
+    LongArgs lq{reinterpret_cast<LongEntry*>(c->d_long_queue), (unsigned)c->long_cap, reinterpret_cast<LongEntry*>(c->d_long_queue) + c->long_cap,
+                reinterpret_cast<HugeItem*>(c->d_huge_items), c->d_huge_items ? (unsigned)c->frag_cap : 0u};
+    const float op = fuse_transfer ? p.voxel_set_opacity : 0.0f;
+    if (fuse_transfer) k_voxel_resolve<true><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, op, lq);
+    else k_voxel_resolve<false><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, op, lq);
     VCT_LAUNCH_CHECK(c, "k_voxel_resolve");
+    if (fuse_transfer) k_voxel_resolve_medium<true><<<VCT_SM_COUNT * 4, kMedWarps * 32, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
+    else k_voxel_resolve_medium<false><<<VCT_SM_COUNT * 4, kMedWarps * 32, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
+    VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+    {
+        k_voxel_huge_compact<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, lq);
+        VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+        if (fuse_transfer) k_voxel_huge_select<true><<<kHugeMax, kSelThreads, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
+        else k_voxel_huge_select<false><<<kHugeMax, kSelThreads, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
+        VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+    }
     if (transfer_done) *transfer_done = fuse_transfer;
     return 0;
 }

@@ -65,4 +65,6 @@ class Workload:
         p = self.params
         return {"workload": self.describe(), "config_index": self.config, "dim": self.D, "levels": self.L, "width": self.W, "height": self.H,
                 "shadow": self.S, "triangles": self.scene.n_tris, "mip_chains": self.chains,
-                "voxelize_mode": "deterministic running average (canonical draw order)" if p.deterministic else "free-running CAS"}
+                "voxelize_mode": "deterministic running average (canonical draw order)" if p.deterministic else "free-running CAS",
+                "l2": "GPU arm: no explicit flush — the inputs of one step (4096^2 shadow map 64 MiB, fragment records, visibility buffer, scene geometry, "
+                      "texture pyramid, material textures) exceed the 126 MB L2, so every pass starts L2-cold for its own inputs"}
