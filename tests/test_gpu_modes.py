@@ -158,3 +158,36 @@ def test_texture_reupload_replaces_the_texels(room):
         g._ck(g.lib.vct_upload_texture(g.h, 0, t.width, t.height, t.channels, min(16, len(t.levels)), px.ctypes.data))
     o.frame(p); g.frame(p)
     assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0])
+
+
+def test_long_per_voxel_lists_without_a_warp_mode():
+    """Deterministic running average with many fragments per voxel (a dense mesh on a coarse grid): 60 and 300 coincident quads.  The
+    8-bit count wraps at 256 and the average forgets its history there (voxelize.frag:127-133), so only the last (N-1)%256+1 fragments
+    in canonical order matter — which is what the long-list paths of voxelize.cu replay.  First frame: the resolve kernel meets the
+    long lists without its helper kernels and resolves them itself; later frames: the warp-per-voxel kernel.  All equal the oracle."""
+    from vct_b200.pipeline import Pipeline
+    rng = np.random.default_rng(3)
+    for stack in (60, 300):
+        sc = S.Scene()
+        texs = [sc.add_texture(S.checker_texture(16, 4, a=tuple(int(x) for x in rng.integers(30, 255, 3)), b=tuple(int(x) for x in rng.integers(30, 255, 3)), seed=k)) for k in range(6)]
+        mats = [sc.add_material(diffuse=t) for t in texs]
+        parts = [S.quad_mesh([(-0.6, -0.2, 0.5), (0.7, -0.2, 0.5), (0.7, -0.2, -0.6), (-0.6, -0.2, -0.6)], (0, 1, 0), mats[k % 6], 1.0 + 0.1 * (k % 7)) for k in range(stack)]
+        parts.append(S.quad_mesh([(-1.4, -1.0, 1.4), (1.4, -1.0, 1.4), (1.4, -1.0, -1.4), (-1.4, -1.0, -1.4)], (0, 1, 0), mats[0], 4.0))
+        sc.add_actor(S.merge_meshes(parts))
+        sc.lights = [P.make_light(position=(1.2, 4.0, 0.7), direction=(-0.28, -0.9, -0.2), shadow_caster=True, type_=1)]
+        d, l, ss, w, h = 32, 5, 256, 96, 64
+        p = S.room_params(w, h)
+        o = Oracle(sc, d, l, ss, w, h)
+        g = Pipeline(sc, d, l, ss, w, h)
+        try:
+            o.frame(p)
+            assert o.info.max_fragments_per_voxel == stack % 256 or o.info.max_fragments_per_voxel >= 200, o.info.max_fragments_per_voxel
+            for k in range(3):
+                g.frame(p)
+                assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0]), (stack, k)
+                assert np.array_equal(g.read_volume(P.VOL_NORMAL), o.normal), (stack, k)
+                assert np.array_equal(g.read_volume(P.VOL_RADIANCE), o.radiance[0]), (stack, k)
+                i = g.counters()
+                assert (i.total_fragments, i.unique_voxels, i.max_fragments_per_voxel) == (o.info.total_fragments, o.info.unique_voxels, o.info.max_fragments_per_voxel), (stack, k)
+        finally:
+            g.close()

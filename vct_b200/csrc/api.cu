@@ -379,15 +379,15 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     const int N = VCT_WARP_DIM;
     auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
-    if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * 8) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
+    if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * (8 + 16)) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
         alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, ((size_t)(c->S / 4 + 1) * (c->S / 4 + 1) + (size_t)(c->S / 64 + 1) * (c->S / 16 + 1)) * 8) || alloc((void**)&c->d_inject_list, ((size_t)(c->S / 64 + 1) * (c->S / 16 + 1) + 1) * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
         alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc(&c->d_long_queue, (c->long_cap + 8) * 16) || alloc(&c->d_huge_items, c->frag_cap * 16) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
     // overflow of a fixed-capacity buffer is also flagged in mapped host memory, so that the next entry point sees it without a sync
-    if (cudaHostAlloc((void**)&c->h_overflow, sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) { c->error = "cudaHostAlloc"; return bail("overflow flag"); }
-    *c->h_overflow = 0u;
+    if (cudaHostAlloc((void**)&c->h_overflow, 2 * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) { c->error = "cudaHostAlloc"; return bail("overflow flag"); }
+    c->h_overflow[0] = 0u; c->h_overflow[1] = 0u;           // [0] overflow, [1] a long per-voxel list was met (voxelize.cu)
     { unsigned* dp = nullptr; if (cudaHostGetDevicePointer((void**)&dp, c->h_overflow, 0) != cudaSuccess || cudaMemcpyAsync(&c->d_counters->overflow_host, &dp, sizeof dp, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->error = "mapped overflow flag"; return bail("overflow flag"); } }
     for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("sync");
@@ -771,7 +771,9 @@ int vct_write_volume(vct_ctx* c, int which, int level, const void* in) { VCT_FAN
     cudaSetDevice(c->cfg.device);
     void* p; size_t b; if (volume_ptr(c, which, level, &p, &b)) return 1;
     c->seg_valid = false;
-    VCT_CHECK(c, cudaMemcpyAsync(p, in, b, cudaMemcpyHostToDevice, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    VCT_CHECK(c, cudaMemcpyAsync(p, in, b, cudaMemcpyHostToDevice, c->stream));
+    if (which == VCT_VOL_WARPMAP && vctk_warpmap_floats(c)) return 1;
+    VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 int vct_read_image(vct_ctx* c, void* rgba8) {

@@ -246,6 +246,7 @@ int vctk_xchg_image_sync(vct_ctx*);
 int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);
 int vctk_warpmap(vct_ctx*);
+int vctk_warpmap_floats(vct_ctx*);       // float4 copy behind the unorm16 warp map (d_warpmap + 4 * 32^3 ushorts)
 int vctk_cone_trace(vct_ctx*);
 size_t vctk_image_rows(const vct_ctx*);
 int vctk_set_voxel_opacity(vct_ctx*, float);

@@ -46,7 +46,7 @@ static TraceArgs make_trace_args(vct_ctx* c) {
     a.wpos = c->d_wpos; a.wnrm = c->d_wnrm; a.wT = c->d_wT; a.wB = c->d_wB; a.tex = c->d_tex; a.mats = c->d_mat; a.shadow = c->d_shadow;
     const bool rad = c->h_fc.p.draw_radiance != 0;
     a.vol = rad ? c->radiance_tex : c->color_tex; a.vol_point = rad ? c->radiance_tex_point : c->color_tex_point;
-    a.vol_last = rad ? c->radiance_tex_last : c->color_tex_last; a.warp = reinterpret_cast<const ushort4*>(c->d_warpmap);
+    a.vol_last = rad ? c->radiance_tex_last : c->color_tex_last; a.warp = reinterpret_cast<const float4*>(c->d_warpmap + 4 * (size_t)VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM);
     a.level0 = rad ? c->d_radiance : c->d_color;
     a.image = c->d_image; a.counters = c->d_counters;
     return a;

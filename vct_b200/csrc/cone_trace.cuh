@@ -28,7 +28,7 @@ struct TraceArgs {
     const uint32_t* indices; const int32_t* trimat; const float* verts;
     const float4 *wpos, *wnrm, *wT, *wB;
     const DevTexture* tex; const DevMaterial* mats; const float* shadow;
-    cudaTextureObject_t vol, vol_point, vol_last; const ushort4* warp;
+    cudaTextureObject_t vol, vol_point, vol_last; const float4* warp;     // warp map as floats (k_warpmap_floats)
     const uint32_t* level0;                      // linear level 0 of the traced pyramid: the voxel view's NEAREST fetch reads it exactly
     uint32_t* image; Counters* counters;
     // sharded frame (multi-GPU with attached peers): the CTAs walk this rank's 64x64 screen tiles (x0 | y0 << 16; 32 CTAs each) instead of the
@@ -134,17 +134,17 @@ __device__ __forceinline__ V3 voxel_warp(V3 p, V3 c) {
 // interpolation weights move the warped sample position by up to 1/256 of a warp cell, which is enough to
 // flip the NEAREST (lambda <= 0.5) fetches of the specular cone onto a neighbouring voxel (measured: final
 // image PSNR 41 dB with the hardware filter vs the fp32 definition of the oracle).
-__device__ __forceinline__ V3 warp_texel(const ushort4* __restrict__ wm, int x, int y, int z) {
+__device__ __forceinline__ V3 warp_texel(const float4* __restrict__ wm, int x, int y, int z) {
     const int n = VCT_WARP_DIM;
     x = min(max(x, 0), n - 1); y = min(max(y, 0), n - 1); z = min(max(z, 0), n - 1);
-    const ushort4 q = __ldg(wm + (z * n + y) * n + x);
-    return mk3(__fdiv_rn((float)q.x, 65535.0f), __fdiv_rn((float)q.y, 65535.0f), __fdiv_rn((float)q.z, 65535.0f));
+    const float4 q = __ldg(wm + (z * n + y) * n + x);                        // q / 65535 per channel, divided once by k_warpmap_floats
+    return mk3(q.x, q.y, q.z);
 }
 __device__ __forceinline__ V3 lerp3x(V3 a, V3 b, float t) {
     const float s = 1.0f - t;
     return mk3(__fadd_rn(__fmul_rn(a.x, s), __fmul_rn(b.x, t)), __fadd_rn(__fmul_rn(a.y, s), __fmul_rn(b.y, t)), __fadd_rn(__fmul_rn(a.z, s), __fmul_rn(b.z, t)));
 }
-__device__ __forceinline__ V3 warp_sample(const ushort4* __restrict__ wm, V3 tc) {
+__device__ __forceinline__ V3 warp_sample(const float4* __restrict__ wm, V3 tc) {
     const float n = (float)VCT_WARP_DIM;
     const float x = __fmul_rn(tc.x, n) - 0.5f, y = __fmul_rn(tc.y, n) - 0.5f, z = __fmul_rn(tc.z, n) - 0.5f;
     const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
@@ -163,7 +163,7 @@ enum { WARP_NONE = 0, WARP_TEXTURE = 1, WARP_VOXELS = 2, WARP_TESS = 3 };
 // ---- traceCone, phong.frag:135-180
 // (warp map and frame parameters share a slot: WARP_TESS needs pv and the volume extents, never the warp map — the context of
 // the other instantiations keeps its layout)
-struct ConeCtx { cudaTextureObject_t vol, vol_point, vol_last; union { const ushort4* warp; const vct_frame_params* fp; }; int D, L; int warp_texture, warp_voxels; V3 eye_tc; };
+struct ConeCtx { cudaTextureObject_t vol, vol_point, vol_last; union { const float4* warp; const vct_frame_params* fp; }; int D, L; int warp_texture, warp_voxels; V3 eye_tc; };
 // phong.frag:158-162 (voxelizeTesselationWarp): the sample goes back to world space and through pv (common.glsl:37-42)
 __device__ __forceinline__ V3 tess_warp_sample(const vct_frame_params& fp, V3 sp) {
     const V3 world = mk3((sp.x * (fp.voxel_max[0] - fp.voxel_min[0]) + fp.voxel_center[0]) + fp.voxel_min[0],
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
             if (DBG && view == VCT_VIEW_VOXELS) {                            // phong.frag:347-404: the traced volume at this fragment's voxel
                 V3 gp = voxel_linear_position(Pw, fp);
                 if (WM == WARP_VOXELS) gp = voxel_warp(gp, voxel_linear_position(mk3(fp.eye[0], fp.eye[1], fp.eye[2]), fp));
-                else if (WM == WARP_TEXTURE) gp = warp_sample(reinterpret_cast<const ushort4*>(a.warp), gp);
+                else if (WM == WARP_TEXTURE) gp = warp_sample(a.warp, gp);
                 else if (WM == WARP_TESS) gp = tess_warp_position(Pw, fp);
                 const float Df = (float)fc.D;
                 const V3 vi = mk3(__fdiv_rn(__fmul_rn(Df, gp.x), Df), __fdiv_rn(__fmul_rn(Df, gp.y), Df), __fdiv_rn(__fmul_rn(Df, gp.z), Df));   // voxelIndex(..) / voxelDim

@@ -84,7 +84,7 @@ constexpr int kMedMax = 1024;
 constexpr int kHugeMax = 8;
 struct LongEntry { uint32_t key, head, count, pad; };               // voxel, head slot of its list, fragment count
 struct __align__(16) HugeItem { unsigned long long k; uint32_t slot, h; };   // order key + 1, fragment slot, index into the huge table
-struct LongArgs { LongEntry* queue; unsigned cap; LongEntry* huge; HugeItem* items; unsigned item_cap; };
+struct LongArgs { LongEntry* queue; unsigned cap; LongEntry* huge; HugeItem* items; unsigned item_cap; int inline_long; };   // inline_long: the long-list kernels do not run this frame
 
 // voxelize.geom:26-73: axis from the summed vertex normals, projection through that axis' ortho view
 __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& fc, uint32_t t, VoxSetup& S) {
@@ -508,10 +508,35 @@ __global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restri
         uint32_t cw = r0.z, nw = r0.w;                                          // next == 0: a single fragment
         if (r0.y != 0u) {
             const uint32_t count = normal[key];                                 // fragments of this voxel (counted by k_voxel_tiles)
-            if (count > (uint32_t)kSortMax) {                                   // long list: a warp (or the scan kernels) takes it
+            if (count > (uint32_t)kSortMax && !lq.inline_long) {                // long list: a warp (or the scan kernels) takes it
                 const unsigned pos = atomicAdd(&counters->long_count, 1u);
                 if (pos < lq.cap) { LongEntry e; e.key = key; e.head = i; e.count = count; e.pad = 0u; lq.queue[pos] = e; }
                 else vct_flag_overflow(counters);
+                continue;
+            }
+            if (count > (uint32_t)kSortMax) {
+                // The long-list kernels were not launched (no warp mode, and no long list seen so far in this context): tell the host —
+                // it launches them from the next frame on — and resolve this one here by selection: find the r-th largest key top
+                // down, then replay upwards from it.  2 r walks of the list: fine for the dense-mesh case this is for (N ~ 50-400, once).
+                if (counters->overflow_host) counters->overflow_host[1] = 1u;
+                if (count > (uint32_t)kMedMax) { vct_flag_overflow(counters); continue; }     // a pile-up without the scan kernels: reported, not resolved
+                const int r = (int)((count - 1u) & 255u) + 1;
+                unsigned long long bound = ~0ull;                               // descend r times: bound = r-th largest key
+                for (int q = 0; q < r; ++q) {
+                    unsigned long long best = 0ull;
+                    for (uint32_t j = i + 1u; j; j = frags[j - 1u].next) { const unsigned long long k = order_key(frags[j - 1u]); if (k < bound && k > best) best = k; }
+                    bound = best;
+                }
+                cw = 0u; nw = 0u;
+                unsigned long long last = bound - 1ull;                         // ascend from it
+                for (int q = 0; q < r; ++q) {
+                    unsigned long long best = ~0ull; uint32_t bi = 0u;
+                    for (uint32_t j = i + 1u; j; j = frags[j - 1u].next) { const unsigned long long k = order_key(frags[j - 1u]); if (k > last && k < best) { best = k; bi = j - 1u; } }
+                    const Frag& f = frags[bi];
+                    cw = rgba8_avg_insert(cw, f.cr, f.cg, f.cb); nw = rgba8_avg_insert(nw, f.nr, f.ng, f.nb);
+                    last = best;
+                }
+                finish_voxel<TRANSFER>(key, cw, nw, color, normal, radiance, opacity, uniq, maxfrag);
                 continue;
             }
             cw = 0u; nw = 0u;
@@ -777,7 +802,7 @@ template <int MODE>
 int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* tiles_name) {
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_voxel_bin<MODE><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, bin_name);
-    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 6, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, tiles_name);
+    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 3, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, tiles_name);   // one resident wave (3 CTAs per SM): the warps share the queues round-robin
     return 0;
 }
 
@@ -843,14 +868,17 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset, bool 
     if (!p.deterministic) return run_mode<MODE_CAS>(c, a, "k_voxel_bin_cas", "k_voxel_tiles_cas");
     // deterministic running average: per-voxel lists, then ordered sequential replay (fused with transferVoxels when the caller asks)
     if (run_mode<MODE_SORTED>(c, a, "k_voxel_bin", "k_voxel_tiles")) return 1;
-    // long per-voxel lists: queue + huge table + scan buffer.  The three extra launches leave at once when nothing was queued
-    // (a couple of microseconds per frame); they are what turns a pile-up from minutes into a fraction of a millisecond.
+    // long per-voxel lists: queue + huge table + scan buffer.  The three extra launches run when a warp mode is on (pile-ups) or once
+    // the resolve kernel has met a long list in this context (it tells the host through the mapped flag word and resolves that frame's
+    // lists itself); otherwise they are skipped: ~15 us of launches per frame that the common case does not need.
+    const bool long_path = p.warp_voxels || p.warp_texture || (c->h_overflow && ((volatile unsigned*)c->h_overflow)[1]);
     LongArgs lq{reinterpret_cast<LongEntry*>(c->d_long_queue), (unsigned)c->long_cap, reinterpret_cast<LongEntry*>(c->d_long_queue) + c->long_cap,
-                reinterpret_cast<HugeItem*>(c->d_huge_items), c->d_huge_items ? (unsigned)c->frag_cap : 0u};
+                reinterpret_cast<HugeItem*>(c->d_huge_items), c->d_huge_items ? (unsigned)c->frag_cap : 0u, long_path ? 0 : 1};
     const float op = fuse_transfer ? p.voxel_set_opacity : 0.0f;
     if (fuse_transfer) k_voxel_resolve<true><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, op, lq);
     else k_voxel_resolve<false><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, op, lq);
     VCT_LAUNCH_CHECK(c, "k_voxel_resolve");
+    if (!long_path) { if (transfer_done) *transfer_done = fuse_transfer; return 0; }
     if (fuse_transfer) k_voxel_resolve_medium<true><<<VCT_SM_COUNT * 4, kMedWarps * 32, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
     else k_voxel_resolve_medium<false><<<VCT_SM_COUNT * 4, kMedWarps * 32, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
     VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");

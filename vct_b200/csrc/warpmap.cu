@@ -115,11 +115,27 @@ __global__ void __launch_bounds__(1024) k_warpmap(const uint32_t* __restrict__ o
         warpmap[i] = make_ushort4(q[0], q[1], q[2], q[3]);
     }
 }
+// float copy of the warp map for the cone tracer: the unorm16 -> float conversion (q / 65535, one IEEE division per channel) done once
+// per texel here instead of 24 times per cone step there (config 4 at 4K: 68 ms -> see DESIGN.md); same values, bit for bit
+__global__ void __launch_bounds__(256) k_warpmap_floats(const ushort4* __restrict__ warpmap, float4* __restrict__ wf) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM) return;
+    const ushort4 q = warpmap[i];
+    wf[i] = make_float4((float)q.x / 65535.0f, (float)q.y / 65535.0f, (float)q.z / 65535.0f, (float)q.w / 65535.0f);
+}
 }  // namespace
+
+int vctk_warpmap_floats(vct_ctx* c) {
+    const int n = VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM;
+    k_warpmap_floats<<<(n + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const ushort4*>(c->d_warpmap), reinterpret_cast<float4*>(c->d_warpmap + 4 * (size_t)n));
+    VCT_LAUNCH_CHECK(c, "k_warpmap_floats");
+    return 0;
+}
 
 int vctk_warpmap(vct_ctx* c) {
     k_warpmap<<<1, 1024, 0, c->stream>>>(c->d_occ, c->d_fc, reinterpret_cast<ushort4*>(c->d_warpmap), reinterpret_cast<ushort4*>(c->d_wlo),
                                          reinterpret_cast<ushort4*>(c->d_whi), reinterpret_cast<uint8_t*>(c->d_warp_scratch));
     VCT_LAUNCH_CHECK(c, "k_warpmap");
+    if (vctk_warpmap_floats(c)) return 1;
     return 0;
 }
