@@ -384,11 +384,13 @@ struct InjectLinear {                                 // passed by value: no dep
     int skip_far;                                     // the light's far plane (depth 1 = nothing rendered) misses the volume by > 1 voxel
     // Block cull: voxel coordinates are affine in (ndc x, ndc y, ndc depth): P_k = bx[k]*nx + by[k]*ny + bz[k]*nz + b0[k].  With the
     // min / max filtered depth of a 64x16 texel block (k_shadow_minmax*, written by the shadow pass) interval arithmetic bounds P over
-    // the block; k_inject_linear runs one CTA per block and a CTA whose block cannot reach the volume — or this rank's z-slab — leaves
-    // before it loads a depth (CTA-uniform: one 8-byte load).  Sponza: 2/3 of the shadow map sees no geometry or lies outside the volume
-    // and is never read.  (Measured and dropped: the same test per thread on 4x4 blocks, 40 -> 49 us — a dependent load in front of every
-    // thread's depths; a separate one-CTA cull pass writing a block list, 22 us for itself.)
-    const float2* minmax;                             // coarse level (one entry per 64x16 texels); nullptr: no cull
+    // the block; k_inject_cull lists the blocks that can reach the volume — and this rank's z-slab —, k_inject_linear runs one CTA per
+    // listed block.  The list is a function of the shadow map and of (ls_inverse, volume, grid, slab): it is rebuilt when one of them
+    // changes (a new shadow map, a moved volume), not every frame.  Sponza: 2/3 of the shadow map sees no geometry or lies outside the
+    // volume and is never read.  (Measured and dropped: the test per thread on 4x4 blocks, 40 -> 49 us, and per CTA inside the inject
+    // kernel, 55 us — a dependent load in front of the depth loads either way.)
+    const float2* minmax;                             // coarse level (one entry per 64x16 texels); nullptr: every block is listed
+    const uint32_t* list;                             // [0] = number of active blocks, [1..] = their ids (k_inject_cull)
     float bx[3], by[3], bz[3], b0[3];
 };
 constexpr int kInjBlockW = 64, kInjBlockH = 16;      // texels per CTA of k_inject_linear: 16 threads x 4 texels wide, 16 rows
@@ -448,6 +450,17 @@ __device__ __forceinline__ bool inject_block_active(const InjectLinear& lin, int
     }
     return active;
 }
+// which 64x16 texel blocks of the shadow map can land in the volume (and this rank's slab); list[0] was zeroed by the host
+__global__ void __launch_bounds__(256) k_inject_cull(const __grid_constant__ InjectLinear lin, uint32_t* __restrict__ list) {
+    const int nb = (lin.S / kInjBlockW) * (lin.S / kInjBlockH), b = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
+    const bool active = b < nb && inject_block_active(lin, b);
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if (!m) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(list, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (active) list[1u + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)b;
+}
 __device__ __forceinline__ float div_by_const(float a, float c, float rc) {
     const float q0 = __fmul_rn(a, rc);
     const float q1 = __fmaf_rn(__fmaf_rn(-q0, c, a), rc, q0);
@@ -457,8 +470,8 @@ __global__ void __launch_bounds__(256) k_inject_linear(const float* __restrict__
                                                        const __grid_constant__ InjectLinear lin) {
     const int S = lin.S, D = lin.D;
     const float inv_s = 1.0f / (float)S, fd = (float)D;                     // exact: S is a power of two
-    const int blk = (int)blockIdx.x, nbx = S / kInjBlockW;                   // one CTA per 64x16 texel block; 2/3 of them leave here
-    if (!inject_block_active(lin, blk)) return;
+    if (blockIdx.x >= __ldg(lin.list)) return;                              // CTA i works on the i-th active 64x16 texel block
+    const int blk = (int)__ldg(lin.list + 1 + blockIdx.x), nbx = S / kInjBlockW;
     const int x0 = (blk % nbx) * kInjBlockW + (threadIdx.x & 15) * 4, y = (blk / nbx) * kInjBlockH + (threadIdx.x >> 4);
     const float* row1 = shadow + (size_t)y * S + x0;
     const float4 b = __ldcs(reinterpret_cast<const float4*>(row1));        // one-touch stream: evict first, keep L2 for the cone tracer's inputs
@@ -855,7 +868,7 @@ int vctk_inject(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
     const bool pow2 = (c->S & (c->S - 1)) == 0 && c->S >= 32;
     if (pow2 && c->S >= 64 && !p.warp_voxels && !p.warp_texture && !p.voxelize_tesselation_warp && !p.radiance_lighting && c->D <= 1024) {
-        InjectLinear lin; bool sane = true;
+        InjectLinear lin; memset(&lin, 0, sizeof lin); bool sane = true;   // (zeroed padding: the struct is compared bytewise below)
         for (int i = 0; i < 3; ++i) {
             volatile float ext = p.voxel_max[i] - p.voxel_min[i];           // one fp32 rounding, like the shader's (max - min)
             lin.c[i] = ext; lin.rc[i] = (float)(1.0 / (double)lin.c[i]); lin.sub0[i] = p.voxel_center[i]; lin.sub1[i] = p.voxel_min[i];
@@ -885,6 +898,18 @@ int vctk_inject(vct_ctx* c) {
                 lin.bx[i] = (float)(k * lin.m[i]); lin.by[i] = (float)(k * lin.m[4 + i]); lin.bz[i] = (float)(k * lin.m[8 + i]);
                 lin.b0[i] = (float)(k * ((double)lin.m[12 + i] - (double)lin.sub0[i] - (double)lin.sub1[i]));
             }
+            lin.list = c->d_inject_list;
+            // (re)build the active-block list when the shadow map or anything the test reads has changed
+            InjectLinear key = lin; key.minmax = nullptr; key.list = nullptr; key.skip_far = (int)c->shadow_gen;
+            static_assert(sizeof(InjectLinear) <= sizeof(c->inject_key), "inject_key");
+            if (!c->inject_list_valid || memcmp(&key, c->inject_key, sizeof key) != 0) {
+                const int nb = (c->S / kInjBlockW) * (c->S / kInjBlockH);
+                VCT_CHECK(c, cudaMemsetAsync(c->d_inject_list, 0, 4, c->stream));
+                vct_prof_mark(c, "memset");
+                k_inject_cull<<<(nb + 255) / 256, 256, 0, c->stream>>>(lin, c->d_inject_list);
+                VCT_LAUNCH_CHECK(c, "k_inject_cull");
+                memcpy(c->inject_key, &key, sizeof key); c->inject_list_valid = true;
+            }
             k_inject_linear<<<(unsigned)((c->S / kInjBlockW) * (c->S / kInjBlockH)), 256, 0, c->stream>>>(c->d_shadow, c->d_color, c->d_radiance, lin);
             VCT_LAUNCH_CHECK(c, "k_inject");
             return 0;
@@ -902,7 +927,7 @@ int vctk_inject(vct_ctx* c) {
 }
 // after every write of the shadow map (vct_shadowmap, vct_write_shadowmap): block depth bounds for the inject pass
 int vctk_shadow_minmax(vct_ctx* c) {
-    c->shadow_mm_valid = false;
+    c->shadow_mm_valid = false; c->shadow_gen++;             // a new shadow map: the inject pass rebuilds its block list
     if (!c->d_shadow_mm || (c->S & (c->S - 1)) || c->S < 32) return 0;
     const int nb = c->S / 4;
     if (c->S < 64) return 0;

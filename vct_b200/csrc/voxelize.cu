@@ -372,8 +372,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
 // lighting, 5-tap PCF) 32 at a time, so the expensive part runs on full warps too; the image atomic of the selected mode follows.
 struct Hit { uint32_t slot, pxy, vox; float l0, l1, l2; };          // vox = ix | iy << 10 | iz << 20 (dim <= 1024)
 constexpr int kRing = 64;
+// (not inlined: one copy of the shading code per kernel — with three inlined copies the tile kernel stalled on instruction fetch,
+// `no_instruction` 6.1 warps per issue in profiles/r02g)
 template <int MODE>
-__device__ __forceinline__ void shade_batch(const VoxArgs& a, const FrameConst& fc, const Hit* __restrict__ ring, int head, int n) {
+__device__ __noinline__ void shade_batch(const VoxArgs& a, const FrameConst& fc, const Hit* __restrict__ ring, int head, int n) {
     const int lane = threadIdx.x & 31;
     uint32_t base = 0;
     if (MODE == MODE_SORTED) {
@@ -423,40 +425,47 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a) {
         __syncwarp();
         if (tail - head >= 32) { shade_batch<MODE>(a, fc, ring, head, 32); head += 32; __syncwarp(); }
     };
-    // ---- part 1: the tiles of multi-tile triangles, one 8x4 tile per warp step (one lane per pixel), round-robin over all warps
-    {
-        const unsigned n_tiles = min(*a.q.tile_count, a.q.tile_cap);
-        for (unsigned item = gw; item < n_tiles; item += warps) {
+    // One loop, one call site of candidate() (code size).  A warp first takes the tiles of multi-tile triangles, one 8x4 tile per step
+    // (one lane per pixel), round-robin over all warps; then the single-tile triangles, 32 per chunk, their candidate pixels concatenated.
+    const unsigned n_tiles = min(*a.q.tile_count, a.q.tile_cap), n_items = min(*a.q.pixel_count, a.q.pixel_cap);
+    unsigned item = gw, base = gw * 32u;
+    uint32_t cslot = 0; int cox = 0, coy = 0, ciw = 1, cexcl = 0, total = 0, c0 = 0;        // the current chunk of small items (one per lane)
+    for (;;) {
+        bool cv; uint32_t slot; int px, py;
+        if (item < n_tiles) {
             const uint2 it = __ldg(a.q.tiles + item);
-            candidate(true, it.x, (int)(it.y & 0xFFFFu) + (lane & (kTileW - 1)), (int)(it.y >> 16) + (lane >> 3));
-        }
-    }
-    // ---- part 2: single-tile triangles, 32 per warp step, their candidate pixels concatenated
-    const unsigned n_items = min(*a.q.pixel_count, a.q.pixel_cap);
-    for (unsigned base = gw * 32u; base < n_items; base += warps * 32u) {
-        uint32_t slot = 0; int ox = 0, oy = 0, iw = 1, cnt = 0;
-        if (base + lane < n_items) {
-            const uint2 it = __ldg(a.q.pixels + base + lane);
-            slot = it.x; ox = (int)(it.y & 0xFFFFu); oy = (int)(it.y >> 16);
-            const int4 bb = *reinterpret_cast<const int4*>(&a.setups[slot].s.x0);      // x0, x1, y0, y1
-            iw = min(kTileW, bb.y - ox + 1);
-            cnt = iw * min(kTileH, bb.w - oy + 1);
-        }
-        int inc = cnt;
+            item += warps;
+            cv = true; slot = it.x; px = (int)(it.y & 0xFFFFu) + (lane & (kTileW - 1)); py = (int)(it.y >> 16) + (lane >> 3);
+        } else {
+            if (c0 >= total) {                               // next chunk: one item per lane, prefix sum of the candidate counts
+                if (base >= n_items) break;
+                int cnt = 0; cslot = 0; cox = 0; coy = 0; ciw = 1;
+                if (base + lane < n_items) {
+                    const uint2 it = __ldg(a.q.pixels + base + lane);
+                    cslot = it.x; cox = (int)(it.y & 0xFFFFu); coy = (int)(it.y >> 16);
+                    const int4 bb = *reinterpret_cast<const int4*>(&a.setups[cslot].s.x0);      // x0, x1, y0, y1
+                    ciw = min(kTileW, bb.y - cox + 1);
+                    cnt = ciw * min(kTileH, bb.w - coy + 1);
+                }
+                base += warps * 32u;
+                int inc = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-        const int total = __shfl_sync(0xffffffffu, inc, 31), excl = inc - cnt;
-        for (int c0 = 0; c0 < total; c0 += 32) {
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                total = __shfl_sync(0xffffffffu, inc, 31); cexcl = inc - cnt; c0 = 0;
+                if (total == 0) continue;
+            }
             const int c = c0 + lane;
+            c0 += 32;
             int j = 0;                                       // largest lane whose exclusive prefix is <= c
 #pragma unroll
-            for (int st = 16; st; st >>= 1) { const int e = __shfl_sync(0xffffffffu, excl, j + st); if (e <= c) j += st; }
-            const uint32_t jslot = __shfl_sync(0xffffffffu, slot, j);
-            const int jox = __shfl_sync(0xffffffffu, ox, j), joy = __shfl_sync(0xffffffffu, oy, j), jw = __shfl_sync(0xffffffffu, iw, j);
-            const int local = c - __shfl_sync(0xffffffffu, excl, j);
+            for (int st = 16; st; st >>= 1) { const int e = __shfl_sync(0xffffffffu, cexcl, j + st); if (e <= c) j += st; }
+            slot = __shfl_sync(0xffffffffu, cslot, j);
+            const int jox = __shfl_sync(0xffffffffu, cox, j), joy = __shfl_sync(0xffffffffu, coy, j), jw = __shfl_sync(0xffffffffu, ciw, j);
+            const int local = c - __shfl_sync(0xffffffffu, cexcl, j);
             const int ly = local / jw;
-            candidate(c < total, jslot, jox + (local - ly * jw), joy + ly);
+            cv = c < total; px = jox + (local - ly * jw); py = joy + ly;
         }
+        candidate(cv, slot, px, py);
     }
     if (MODE != MODE_OCC && tail > head) shade_batch<MODE>(a, fc, ring, head, tail - head);
     if (MODE != MODE_OCC) {
