@@ -386,8 +386,8 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
     // overflow of a fixed-capacity buffer is also flagged in mapped host memory, so that the next entry point sees it without a sync
-    if (cudaHostAlloc((void**)&c->h_overflow, 2 * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) { c->error = "cudaHostAlloc"; return bail("overflow flag"); }
-    c->h_overflow[0] = 0u; c->h_overflow[1] = 0u;           // [0] overflow, [1] a long per-voxel list was met (voxelize.cu)
+    if (cudaHostAlloc((void**)&c->h_overflow, 4 * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) { c->error = "cudaHostAlloc"; return bail("overflow flag"); }
+    for (int i = 0; i < 4; ++i) c->h_overflow[i] = 0u;       // [0] overflow, [1] a long per-voxel list was met (voxelize.cu), [2] [3] inject block count + generation
     { unsigned* dp = nullptr; if (cudaHostGetDevicePointer((void**)&dp, c->h_overflow, 0) != cudaSuccess || cudaMemcpyAsync(&c->d_counters->overflow_host, &dp, sizeof dp, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->error = "mapped overflow flag"; return bail("overflow flag"); } }
     for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("sync");

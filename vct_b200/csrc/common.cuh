@@ -153,7 +153,7 @@ struct vct_ctx {
     // shadow map / visibility / image
     float* d_shadow = nullptr; unsigned long long* d_vis = nullptr; uint32_t* d_image = nullptr;
     uint32_t* d_inject_list = nullptr;                              // k_inject_cull: [0] = count, [1..] = active 64x16 shadow-map blocks
-    unsigned char inject_key[256]{}; bool inject_list_valid = false; unsigned shadow_gen = 0;   // what the list was built from
+    unsigned char inject_key[256]{}; bool inject_list_valid = false; unsigned shadow_gen = 0, inject_gen = 0;   // what the list was built from
     void* d_shadow_mm = nullptr; bool shadow_mm_valid = false;   // (S/4)^2 x float2: min / max filtered depth per 4x4 texel block (k_shadow_minmax)
     // voxel fragments (per-voxel linked lists of the deterministic running average)
     size_t frag_cap = 0; void* d_frags = nullptr; uint8_t* d_displaced = nullptr;

@@ -461,6 +461,10 @@ __global__ void __launch_bounds__(256) k_inject_cull(const __grid_constant__ Inj
     base = __shfl_sync(0xffffffffu, base, 0);
     if (active) list[1u + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)b;
 }
+// the finished count also goes to mapped host memory, tagged with the list's generation: later frames size their grid with it
+__global__ void k_inject_publish(const uint32_t* __restrict__ list, unsigned* __restrict__ host_words, unsigned gen) {
+    host_words[2] = list[0]; __threadfence_system(); host_words[3] = gen;
+}
 __device__ __forceinline__ float div_by_const(float a, float c, float rc) {
     const float q0 = __fmul_rn(a, rc);
     const float q1 = __fmaf_rn(__fmaf_rn(-q0, c, a), rc, q0);
@@ -909,8 +913,19 @@ int vctk_inject(vct_ctx* c) {
                 k_inject_cull<<<(nb + 255) / 256, 256, 0, c->stream>>>(lin, c->d_inject_list);
                 VCT_LAUNCH_CHECK(c, "k_inject_cull");
                 memcpy(c->inject_key, &key, sizeof key); c->inject_list_valid = true;
+                c->inject_gen++;
+                if (c->h_overflow) {
+                    unsigned* dp = nullptr;
+                    if (cudaHostGetDevicePointer((void**)&dp, c->h_overflow, 0) == cudaSuccess) { k_inject_publish<<<1, 1, 0, c->stream>>>(c->d_inject_list, dp, c->inject_gen); VCT_LAUNCH_CHECK(c, "k_inject_cull"); }
+                }
             }
-            k_inject_linear<<<(unsigned)((c->S / kInjBlockW) * (c->S / kInjBlockH)), 256, 0, c->stream>>>(c->d_shadow, c->d_color, c->d_radiance, lin);
+            // one CTA per LISTED block once the host has seen the count of this list (mapped words [2], [3]); until then one per block
+            unsigned grid = (unsigned)((c->S / kInjBlockW) * (c->S / kInjBlockH));
+            if (c->h_overflow) {
+                const volatile unsigned* hw = (const volatile unsigned*)c->h_overflow;
+                if (hw[3] == c->inject_gen) { const unsigned n = hw[2]; if (n < grid) grid = n; }
+            }
+            if (grid) k_inject_linear<<<grid, 256, 0, c->stream>>>(c->d_shadow, c->d_color, c->d_radiance, lin);
             VCT_LAUNCH_CHECK(c, "k_inject");
             return 0;
         }

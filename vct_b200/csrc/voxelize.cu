@@ -394,7 +394,7 @@ __device__ __noinline__ void shade_batch(const VoxArgs& a, const FrameConst& fc,
                          n >= 32 ? 0xffffffffu : (1u << n) - 1u);
 }
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3) k_voxel_tiles(VoxArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_voxel_tiles(VoxArgs a) {
     const FrameConst& fc = *a.fc;
     __shared__ Hit s_ring[kThreads / 32][kRing];
     const int D = a.D, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -811,7 +811,7 @@ template <int MODE>
 int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* tiles_name) {
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_voxel_bin<MODE><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, bin_name);
-    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 3, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, tiles_name);   // one resident wave (3 CTAs per SM): the warps share the queues round-robin
+    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, tiles_name);   // one resident wave (4 CTAs per SM at 64 registers): the warps share the queues round-robin
     return 0;
 }
 
