@@ -317,7 +317,7 @@ def run_b200(args):
     # One GPU: the read-back of frame i is pipelined behind frame i+1's voxel passes (vct_read_image_async, two pinned host
     # buffers in turn; every step still copies its parameters in and its whole image out, and the timed region ends only
     # after the last image has landed).  --e2e-blocking reads every image back synchronously instead.
-    pipelined = world == 1 and not args.e2e_blocking
+    pipelined = (world == 1 or fr.peer_exchange) and not args.e2e_blocking
     host_imgs = [torch.empty(W * H, dtype=torch.int32).pin_memory() for _ in range(2)]
     h2d = C.sizeof(P.FrameParams) + 80 * len(sc.lights) + (64 + 36) * len(sc.meshes)
     d2h = W * H * 4
@@ -441,7 +441,7 @@ def run_b200(args):
                 "ms_per_step": round(ms, 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8", "data": w.data,
                 "config": cfg, "execution": execution,
                 "e2e": {"value": round(e2e_ms, 4), "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "readback": "pipelined on a copy stream behind the next step's voxel passes (vct_read_image_async), 2 pinned host buffers" if pipelined
+                        "readback": "rank 0, pipelined on a copy stream behind the next step's voxel passes (vct_read_image_async), 2 pinned host buffers" if pipelined
                                     else "synchronous after every step"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_passes": roofs,
                 "kernels_ms": {k: round(v[0], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])},

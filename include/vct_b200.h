@@ -149,7 +149,8 @@ typedef struct { char name[40]; double ns; unsigned launches; unsigned _pad; } v
 
 enum { VCT_VOL_COLOR = 0, VCT_VOL_NORMAL = 1, VCT_VOL_RADIANCE = 2, VCT_VOL_OCCUPANCY = 3, VCT_VOL_WARPMAP = 4,
        VCT_VOL_WARP_WEIGHTS_LOW = 5, VCT_VOL_WARP_WEIGHTS_HIGH = 6,
-       VCT_BUF_IMAGE = 7 /* device pointer only: RGBA8 rows, padded to world_size equal bands of 8-row tiles */ };
+       VCT_BUF_IMAGE = 7 /* device pointer only: RGBA8 rows of the LAST rendered image (the library keeps two images and alternates,
+                            so that a read-back may overlap the next frame); rows padded to whole 64-row screen tiles */ };
 
 /* ---- lifetime: VCT ctor/dtor/remake, Application::init --------------------------- Application.h:109-156 */
 int  vct_create(const vct_config* cfg, vct_ctx** out);

@@ -53,7 +53,7 @@ def main():
     if rank == 0:
         which = P.VOL_RADIANCE if p.draw_radiance else P.VOL_COLOR
         sharded_levels = [g.read_volume(which, l) for l in range(g.L)]
-        sharded_img = fr.image[: W * H].cpu().numpy().view(np.uint32)
+        sharded_img = g.read_image()
         one = Pipeline(sc, D, L, SS, W, H, device=local)
         try:
             one.shadowmap(p)

@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 thread_local std::string g_create_error;
+uint32_t* vct_ctx::image_of(int parity) const { return d_image + (size_t)parity * vctk_image_rows(this) * (size_t)W; }
 size_t vctk_tile_setup_bytes();
 size_t vctk_vox_setup_bytes();
 size_t vctk_frag_bytes();
@@ -373,14 +374,14 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     for (auto& ev : c->ev) if (cudaEventCreate(&ev) != cudaSuccess) return bail("event");
     for (auto& ev : c->stage_ev) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail("copy stream");
-    if (cudaEventCreateWithFlags(&c->ev_image_ready, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+    if (cudaEventCreateWithFlags(&c->ev_image_ready, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_copy_done[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_copy_done[1], cudaEventDisableTiming) != cudaSuccess) return bail("event");
     if (make_frame_blob(c)) return bail("frame constants");
     if (make_volumes(c)) return bail("volumes");
     const int N = VCT_WARP_DIM;
     auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * (8 + 16)) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
-        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, ((size_t)(c->S / 4 + 1) * (c->S / 4 + 1) + (size_t)(c->S / 64 + 1) * (c->S / 16 + 1)) * 8) || alloc((void**)&c->d_inject_list, ((size_t)(c->S / 64 + 1) * (c->S / 16 + 1) + 1) * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, vctk_image_rows(c) * (size_t)c->W * 4) ||
+        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, ((size_t)(c->S / 4 + 1) * (c->S / 4 + 1) + (size_t)(c->S / 64 + 1) * (c->S / 16 + 1)) * 8) || alloc((void**)&c->d_inject_list, ((size_t)(c->S / 64 + 1) * (c->S / 16 + 1) + 1) * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, 2 * vctk_image_rows(c) * (size_t)c->W * 4) ||
         alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc(&c->d_long_queue, (c->long_cap + 8) * 16) || alloc(&c->d_huge_items, c->frag_cap * 16) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
@@ -461,7 +462,7 @@ int vct_destroy(vct_ctx* c) {
     for (auto& ev : c->stage_ev) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_image_ready) cudaEventDestroy(c->ev_image_ready);
-    if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
+    for (auto& ev : c->ev_copy_done) if (ev) cudaEventDestroy(ev);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_overflow) cudaFreeHost(c->h_overflow);
     for (auto& ev : c->prof_pool) cudaEventDestroy(ev);
@@ -739,7 +740,7 @@ static int volume_ptr(vct_ctx* c, int which, int level, void** ptr, size_t* byte
         case VCT_VOL_WARPMAP: *ptr = c->d_warpmap; *bytes = N * N * N * 8; return 0;
         case VCT_VOL_WARP_WEIGHTS_LOW: *ptr = c->d_wlo; *bytes = N * N * N * 8; return 0;
         case VCT_VOL_WARP_WEIGHTS_HIGH: *ptr = c->d_whi; *bytes = N * N * N * 8; return 0;
-        case VCT_BUF_IMAGE: *ptr = c->d_image; *bytes = vctk_image_rows(c) * (size_t)c->W * 4; return 0;
+        case VCT_BUF_IMAGE: *ptr = c->image_of(c->image_parity); *bytes = vctk_image_rows(c) * (size_t)c->W * 4; return 0;   // the image of the last trace
     }
     return fail(c, "unknown volume");
 }
@@ -779,7 +780,7 @@ int vct_write_volume(vct_ctx* c, int which, int level, const void* in) { VCT_FAN
 int vct_read_image(vct_ctx* c, void* rgba8) {
     if (!c || !rgba8) return 1;
     cudaSetDevice(c->cfg.device);
-    VCT_CHECK(c, cudaMemcpyAsync(rgba8, c->d_image, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
+    VCT_CHECK(c, cudaMemcpyAsync(rgba8, c->image_of(c->image_parity), (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 // Pipelined read-back: the copy of this frame's image runs on a second stream while the library stream goes on with the next
@@ -789,15 +790,16 @@ int vct_read_image_async(vct_ctx* c, void* pinned_rgba8) { VCT_NO_GROUP(c, "vct_
     cudaSetDevice(c->cfg.device);
     VCT_CHECK(c, cudaEventRecord(c->ev_image_ready, c->stream));
     VCT_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_image_ready, 0));
-    VCT_CHECK(c, cudaMemcpyAsync(pinned_rgba8, c->d_image, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->copy_stream));
-    VCT_CHECK(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
-    c->copy_pending = true;
+    const int par = c->image_parity;
+    VCT_CHECK(c, cudaMemcpyAsync(pinned_rgba8, c->image_of(par), (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    VCT_CHECK(c, cudaEventRecord(c->ev_copy_done[par], c->copy_stream));
+    c->copy_pending[par] = true;
     return 0;
 }
 int vct_read_image_wait(vct_ctx* c, int block_host) {
     if (!c) return 1;
     cudaSetDevice(c->cfg.device);
-    if (c->copy_pending) { VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0)); c->copy_pending = false; }
+    for (int par = 0; par < 2; ++par) if (c->copy_pending[par]) { VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done[par], 0)); c->copy_pending[par] = false; }
     if (block_host) VCT_CHECK(c, cudaStreamSynchronize(c->copy_stream));
     return 0;
 }

@@ -175,9 +175,13 @@ struct vct_ctx {
     cudaEvent_t ev[32]{}; vct_timings timings{};
     int profiling = 1;               // 0 none, 1 pass-level events (reference GLTimer semantics), 2 + one event per kernel
     bool own_stream = true;
-    // asynchronous image read-back (vct_read_image_async): the copy runs on its own stream behind the frame and the next
-    // cone trace waits for it before it overwrites d_image
-    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_image_ready = nullptr, ev_copy_done = nullptr; bool copy_pending = false;
+    // The image is double-buffered: d_image holds two images and consecutive cone traces alternate between them (image_parity = the
+    // half the LAST trace wrote; all ranks of a sharded frame flip together).  An asynchronous read-back (vct_read_image_async) of
+    // frame k runs on its own stream while frame k + 1 is rendered into the other half; only the trace — and, sharded, the exchange
+    // that lets the peers store pixels into rank 0 — of frame k + 2 waits for it, i.e. practically never.
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_image_ready = nullptr, ev_copy_done[2] = {nullptr, nullptr}; bool copy_pending[2] = {false, false};
+    int image_parity = 0;
+    uint32_t* image_of(int parity) const;
     std::vector<cudaEvent_t> prof_pool; size_t prof_used = 0;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_marks;
 };

@@ -48,22 +48,24 @@ static TraceArgs make_trace_args(vct_ctx* c) {
     a.vol = rad ? c->radiance_tex : c->color_tex; a.vol_point = rad ? c->radiance_tex_point : c->color_tex_point;
     a.vol_last = rad ? c->radiance_tex_last : c->color_tex_last; a.warp = reinterpret_cast<const float4*>(c->d_warpmap + 4 * (size_t)VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM);
     a.level0 = rad ? c->d_radiance : c->d_color;
-    a.image = c->d_image; a.counters = c->d_counters;
+    a.image = c->image_of(c->image_parity ^ 1); a.counters = c->d_counters;       // the half the last trace did not write
     return a;
 }
 
 int vctk_cone_trace(vct_ctx* c) {
     TraceArgs a = make_trace_args(c);
     dim3 grid((c->W + kThreads / 4 - 1) / (kThreads / 4), (c->H + 3) / 4);
+    const int par = c->image_parity ^ 1;
     if (vctk_xchg_ready(c)) {                                   // sharded frame: own tiles only, pixels also into rank 0's image
         if (ensure_trace_tiles(c)) return 1;
-        if (!c->n_trace_tiles) return 0;
-        a.tiles = c->d_trace_tiles; a.image_remote = c->cfg.rank ? reinterpret_cast<uint32_t*>(c->peer[0].image) : nullptr;
+        if (!c->n_trace_tiles) { c->image_parity = par; return 0; }      // (more ranks than tiles: stay in step with the others)
+        a.tiles = c->d_trace_tiles;
+        a.image_remote = c->cfg.rank ? reinterpret_cast<uint32_t*>(c->peer[0].image) + (size_t)par * vctk_image_rows(c) * (size_t)c->W : nullptr;
         grid = dim3((unsigned)c->n_trace_tiles * 32u, 1);
     }
-    if (c->copy_pending) {                                      // vct_read_image_async: the previous frame's image is still being read back
-        VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
-        c->copy_pending = false;
+    if (c->copy_pending[par]) {                                 // vct_read_image_async: this half is still being read back (the frame before the last)
+        VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done[par], 0));
+        c->copy_pending[par] = false;
     }
     const vct_frame_params& p = c->h_fc.p;
     // Which mapping the kernel applies.  traceCone tests warpTexture first (phong.frag:150-162), common.glsl's getVoxelPosition —
@@ -73,12 +75,15 @@ int vctk_cone_trace(vct_ctx* c) {
                               : (p.warp_texture ? WARP_TEXTURE : p.warp_voxels ? WARP_VOXELS : p.voxelize_tesselation_warp ? WARP_TESS : WARP_NONE);
     if (p.debug_view != VCT_VIEW_SHADED) {                      // debug views: own instantiations in the exactly rounded unit
         if (p.debug_view < 0 || p.debug_view > VCT_VIEW_LAST) { c->error = "vct_cone_trace: unknown debug_view"; return 1; }
-        return vctk_cone_trace_debug(c, a, wm, grid);
+        if (vctk_cone_trace_debug(c, a, wm, grid)) return 1;
+        c->image_parity = par;
+        return 0;
     }
     if (wm == WARP_VOXELS) k_cone_trace<WARP_VOXELS><<<grid, kThreads, 0, c->stream>>>(a);
     else if (wm == WARP_TEXTURE) k_cone_trace<WARP_TEXTURE><<<grid, kThreads, 0, c->stream>>>(a);
     else if (wm == WARP_TESS) k_cone_trace<WARP_TESS><<<grid, kThreads, 0, c->stream>>>(a);
     else k_cone_trace<WARP_NONE><<<grid, kThreads, 0, c->stream>>>(a);
     VCT_LAUNCH_CHECK(c, "k_cone_trace");
+    c->image_parity = par;
     return 0;
 }

@@ -214,9 +214,10 @@ int vctk_xchg_frame(vct_ctx* c, bool dense) {
     uint8_t* mask = rad ? c->d_pub_mask_radiance : c->d_pub_mask_color;
     if (!surf || !mask) { c->error = "slab exchange: the traced pyramid has no texture array"; return 1; }
     unsigned* counter = c->d_xchg_count; unsigned* seq = c->d_xchg_count + 16;
-    if (c->copy_pending) {                                   // the previous image is still being read back on rank 0: the peers may not overwrite it yet
-        VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
-        c->copy_pending = false;
+    const int par = c->image_parity ^ 1;                     // the image half this frame's traces write (on every rank)
+    if (c->copy_pending[par]) {                              // still being read back on rank 0 (two frames old): the peers may not store into it yet
+        VCT_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done[par], 0));
+        c->copy_pending[par] = false;
     }
     // gi_body swapped the masks at its end: this frame's is seg_cur ^ 1, last frame's is seg_cur
     const size_t words_per_slice = (size_t)c->D * c->D / 32;

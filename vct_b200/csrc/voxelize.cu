@@ -170,6 +170,7 @@ __device__ __forceinline__ bool frag_test(const FrameConst& fc, const VoxHead& S
     const float z = interp1(l, S.s.z[0], S.s.z[1], S.s.z[2]);
     if (z < -1.0f || z > 1.0f) return false;
     oob = !frag_voxel(fc, S, l, D, warpmap, occupancy, ix, iy, iz);
+    if (occupancy) return true;                                           // the 32^3 occupancy grid is not sharded: every rank builds all of it
     if (oob) return fc.z_lo == 0;                                         // counted once, by the rank owning z = 0
     return iz >= fc.z_lo && iz < fc.z_hi;
 }

@@ -98,7 +98,6 @@ class ShardedFrame:
             self.stream = torch.cuda.Stream()
             self.stream.wait_stream(torch.cuda.current_stream())
             g.set_stream(self.stream.cuda_stream)
-            self.image = device_tensor(g.device_ptr(P.BUF_IMAGE, 0), g.level_bytes(P.BUF_IMAGE, 0))
             if os.environ.get("VCT_SPARSE_EXCHANGE", "1") != "0" and dist.get_backend() == "nccl":
                 handles = [None] * world
                 dist.all_gather_object(handles, g.exchange_setup())
@@ -203,13 +202,14 @@ class ShardedFrame:
             else:
                 g._ck(g.lib.vct_read_image(g.h, host_img.data_ptr()))
         elif self.rank == 0:
-            with self.torch.cuda.stream(self.stream):
-                host_img.copy_(self.image[: g.W * g.H], non_blocking=True)
-            self.stream.synchronize()
+            if pipelined and self.peer_exchange:                 # same pipelining on rank 0: the next frame's exchange and trace wait for the copy
+                g.read_image_async(host_img.data_ptr())
+            else:
+                g._ck(g.lib.vct_read_image(g.h, host_img.data_ptr()))
 
     def finish_e2e(self):
         """Order the library stream behind the last pipelined read-back (so that an event recorded next covers it)."""
-        if self.world == 1:
+        if self.world == 1 or (self.rank == 0 and self.peer_exchange):
             self.g.read_image_wait(block_host=False)
 
     def profiled_step(self):
