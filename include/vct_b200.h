@@ -192,8 +192,8 @@ int  vct_exchange(vct_ctx*);                               /* multi-GPU only: pu
  *   one process, N GPUs   vct_config.n_devices > 1 does all of it inside vct_create (peer access + vct_exchange_attach)
  * Without attached peers a world_size > 1 context stops after its mip chains (the caller all-gathers the levels itself, then
  * vct_exchange + vct_cone_trace: the round-1 protocol, kept for transports other than peer memory). */
-#define VCT_EXCHANGE_HANDLE_BYTES 256
-typedef struct { void* staging; void* radiance; void* color; void* image; } vct_peer;   /* device pointers valid on THIS rank's device */
+#define VCT_EXCHANGE_HANDLE_BYTES 384
+typedef struct { void* staging; void* radiance; void* color; void* image; void* shadow; } vct_peer;   /* device pointers valid on THIS rank's device */
 int  vct_exchange_setup(vct_ctx*);
 int  vct_exchange_export(vct_ctx*, void* handle /* VCT_EXCHANGE_HANDLE_BYTES */);
 int  vct_exchange_import(vct_ctx*, int rank, const void* handle);

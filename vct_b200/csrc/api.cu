@@ -23,6 +23,7 @@ uint32_t* vct_ctx::image_of(int parity) const { return d_image + (size_t)parity 
 size_t vctk_tile_setup_bytes();
 size_t vctk_vox_setup_bytes();
 size_t vctk_frag_bytes();
+size_t vctk_huge_aux_bytes();
 size_t vctk_image_rows(const vct_ctx*);
 
 namespace {
@@ -381,8 +382,8 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * (8 + 16)) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
-        alloc((void**)&c->d_shadow, (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, ((size_t)(c->S / 4 + 1) * (c->S / 4 + 1) + (size_t)(c->S / 64 + 1) * (c->S / 16 + 1)) * 8) || alloc((void**)&c->d_inject_list, ((size_t)(c->S / 64 + 1) * (c->S / 16 + 1) + 1) * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, 2 * vctk_image_rows(c) * (size_t)c->W * 4) ||
-        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc(&c->d_long_queue, (c->long_cap + 8) * 16) || alloc(&c->d_huge_items, c->frag_cap * 16) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
+        alloc((void**)&c->d_shadow_base, 2 * (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, ((size_t)(c->S / 4 + 1) * (c->S / 4 + 1) + (size_t)(c->S / 64 + 1) * (c->S / 16 + 1)) * 8) || alloc((void**)&c->d_inject_list, ((size_t)(c->S / 64 + 1) * (c->S / 16 + 1) + 1) * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, 2 * vctk_image_rows(c) * (size_t)c->W * 4) ||
+        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc(&c->d_long_queue, (c->long_cap + 8) * 16) || alloc(&c->d_huge_items, c->frag_cap * 16) || alloc(&c->d_huge_aux, vctk_huge_aux_bytes()) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");
@@ -391,6 +392,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     for (int i = 0; i < 4; ++i) c->h_overflow[i] = 0u;       // [0] overflow, [1] a long per-voxel list was met (voxelize.cu), [2] [3] inject block count + generation
     { unsigned* dp = nullptr; if (cudaHostGetDevicePointer((void**)&dp, c->h_overflow, 0) != cudaSuccess || cudaMemcpyAsync(&c->d_counters->overflow_host, &dp, sizeof dp, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->error = "mapped overflow flag"; return bail("overflow flag"); } }
     for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }
+    c->d_shadow = c->d_shadow_base;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("sync");
     *out = c;
     return 0;
@@ -452,7 +454,7 @@ int vct_destroy(vct_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_volumes(c);
     vctk_xchg_free(c);
-    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow, c->d_shadow_mm, (void*)c->d_inject_list, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, c->d_long_queue, c->d_huge_items, (void*)c->d_warp_scratch,
+    for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow_base, c->d_shadow_mm, (void*)c->d_inject_list, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, c->d_long_queue, c->d_huge_items, c->d_huge_aux, (void*)c->d_warp_scratch,
                     c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters, (void*)c->d_trace_tiles,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_wpos,
                     (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})
@@ -635,9 +637,9 @@ int vct_exchange_export(vct_ctx* c, void* handle) {
     if (!c || !handle) return 1;
     cudaSetDevice(c->cfg.device);
     if (!c->d_xchg) return fail(c, "vct_exchange_export: call vct_exchange_setup first");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64 && VCT_EXCHANGE_HANDLE_BYTES >= 4 * 64, "ipc handle size");
-    void* ptrs[4] = {c->d_xchg, c->d_radiance, c->d_color, c->d_image};
-    for (int i = 0; i < 4; ++i) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64 && VCT_EXCHANGE_HANDLE_BYTES >= 5 * 64, "ipc handle size");
+    void* ptrs[5] = {c->d_xchg, c->d_radiance, c->d_color, c->d_image, c->d_shadow_base};
+    for (int i = 0; i < 5; ++i) {
         cudaIpcMemHandle_t h;
         VCT_CHECK(c, cudaIpcGetMemHandle(&h, ptrs[i]));
         std::memcpy((char*)handle + 64 * i, &h, 64);
@@ -651,12 +653,12 @@ int vct_exchange_import(vct_ctx* c, int rank, const void* handle) {
     if (rank < 0 || rank >= c->cfg.world_size) return fail(c, "vct_exchange_import: bad rank");
     if (rank == c->cfg.rank) return 0;
     if (c->peer[rank].staging) return fail(c, "vct_exchange_import: this rank is already attached");
-    void* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < 4; ++i) {
+    void* ptrs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 5; ++i) {
         cudaIpcMemHandle_t h; std::memcpy(&h, (const char*)handle + 64 * i, 64);
         VCT_CHECK(c, cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess));
     }
-    c->peer[rank].staging = ptrs[0]; c->peer[rank].radiance = ptrs[1]; c->peer[rank].color = ptrs[2]; c->peer[rank].image = ptrs[3];
+    c->peer[rank].staging = ptrs[0]; c->peer[rank].radiance = ptrs[1]; c->peer[rank].color = ptrs[2]; c->peer[rank].image = ptrs[3]; c->peer[rank].shadow = ptrs[4];
     c->peer_ipc[rank] = true; c->peers_attached++;
     return 0;
 }
@@ -669,7 +671,7 @@ int vct_exchange_local(vct_ctx* c, vct_peer* out) {
 int vct_exchange_attach(vct_ctx* c, int rank, const vct_peer* peer) {
     if (!c || !peer) return 1;
     if (!c->d_xchg) return fail(c, "vct_exchange_attach: call vct_exchange_setup first");
-    if (rank < 0 || rank >= c->cfg.world_size || !peer->staging || !peer->radiance || !peer->color || !peer->image) return fail(c, "vct_exchange_attach: bad arguments");
+    if (rank < 0 || rank >= c->cfg.world_size || !peer->staging || !peer->radiance || !peer->color || !peer->image || !peer->shadow) return fail(c, "vct_exchange_attach: bad arguments");
     if (rank == c->cfg.rank) return 0;
     if (c->peer[rank].staging) return fail(c, "vct_exchange_attach: this rank is already attached");
     c->peer[rank] = *peer; c->peer_ipc[rank] = false; c->peers_attached++;

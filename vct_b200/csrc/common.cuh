@@ -142,7 +142,7 @@ struct vct_ctx {
     // vct_frame / vct_gi_passes invalidates the masks; the next frame then runs the dense kernels once.
     // sparse slab exchange (exchange.cu): local staging, the peers' staging mapped through cudaIpc, record counter
     void* d_xchg = nullptr; size_t xchg_region_bytes = 0; unsigned xchg_cap = 0; unsigned* d_xchg_count = nullptr;
-    vct_peer peer[VCT_MAX_PEERS]{}; bool peer_ipc[VCT_MAX_PEERS]{}; int peers_attached = 0;
+    vct_peer peer[VCT_MAX_PEERS]{}; bool peer_ipc[VCT_MAX_PEERS]{}; int peers_attached = 0; void* d_xchg_dst = nullptr;
     uint32_t* d_trace_tiles = nullptr; int n_trace_tiles = 0;      // own 64x64 screen tiles (x0 | y0 << 16) of the sharded cone trace
     std::vector<vct_ctx*> group;                                    // single-process multi-GPU: the other ranks' contexts (this one is rank 0)
     void* group_state = nullptr; bool in_fan = false;               // worker threads of the group (api.cu); true while a call is being fanned out
@@ -152,12 +152,15 @@ struct vct_ctx {
     uint32_t* d_occ = nullptr; uint16_t *d_warpmap = nullptr, *d_wlo = nullptr, *d_whi = nullptr;
     // shadow map / visibility / image
     float* d_shadow = nullptr; unsigned long long* d_vis = nullptr; uint32_t* d_image = nullptr;
+    // two shadow maps: sharded frames rasterise a band of shadow rows per rank and store it into every peer's map; alternating maps
+    // keep a peer that is already on the next frame from overwriting the one this rank still reads (d_shadow = the current one)
+    float* d_shadow_base = nullptr; int shadow_parity = 0;
     uint32_t* d_inject_list = nullptr;                              // k_inject_cull: [0] = count, [1..] = active 64x16 shadow-map blocks
     unsigned char inject_key[256]{}; bool inject_list_valid = false; unsigned shadow_gen = 0, inject_gen = 0;   // what the list was built from
     void* d_shadow_mm = nullptr; bool shadow_mm_valid = false;   // (S/4)^2 x float2: min / max filtered depth per 4x4 texel block (k_shadow_minmax)
     // voxel fragments (per-voxel linked lists of the deterministic running average)
     size_t frag_cap = 0; void* d_frags = nullptr; uint8_t* d_displaced = nullptr;
-    void* d_long_queue = nullptr; size_t long_cap = 65536; void* d_huge_items = nullptr;   // long per-voxel lists: queue (+ 8 huge entries behind it), scan buffer
+    void* d_long_queue = nullptr; size_t long_cap = 65536; void* d_huge_items = nullptr; void* d_huge_aux = nullptr;   // long per-voxel lists: queue (+ 8 huge entries behind it), scan buffer
     uint32_t* d_warp_scratch = nullptr;
     // raster work queue: 8-byte tile items + one setup record per queued (sub-)triangle
     void* d_tile_queue = nullptr; size_t tile_queue_cap = 0; void* d_expand_queue = nullptr; size_t expand_cap = 0;
@@ -248,6 +251,7 @@ void vctk_xchg_free(vct_ctx*);
 bool vctk_xchg_ready(const vct_ctx*);          // multi-GPU with every peer attached: the frame entry points run the whole sharded frame
 int vctk_xchg_frame(vct_ctx*, bool dense);
 int vctk_xchg_image_sync(vct_ctx*);
+int vctk_xchg_shadow(vct_ctx*, int row_lo, int row_hi);   // sharded shadow pass: own rows -> every peer's map, then wait for everybody's
 int vctk_shadowmap(vct_ctx*);
 int vctk_visibility(vct_ctx*);
 int vctk_warpmap(vct_ctx*);

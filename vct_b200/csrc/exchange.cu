@@ -36,6 +36,7 @@ struct XchgControl {                     // first bytes of every rank's staging 
     unsigned count[VCT_MAX_PEERS];       // count[s]: how many
     unsigned consumed[VCT_MAX_PEERS];    // consumed[p]: rank p has unpacked frame `consumed[p]` (its staging may be overwritten)
     unsigned image_done[VCT_MAX_PEERS];  // rank 0: rank p's pixels of frame `image_done[p]` are in this rank's image
+    unsigned shadow_ready[VCT_MAX_PEERS];// shadow_ready[s]: rank s has stored its band of shadow map number `shadow_ready[s]` here
 };
 static_assert(sizeof(XchgControl) <= kCtrlBytes, "control block");
 
@@ -159,6 +160,24 @@ __global__ void k_xchg_image_wait(const unsigned* __restrict__ seq, const __grid
     wait_flags(ctrl(peers.base[0])->image_done, peers.world, 0, *seq);
 }
 
+// sharded shadow pass: this rank's band of rows -> the same rows of every peer's map; then the flag; then wait for all bands
+__global__ void __launch_bounds__(kThreads) k_xchg_push_shadow(const uint4* __restrict__ src, size_t n16, size_t off16, const __grid_constant__ XchgPeers peers, uint4* const* __restrict__ dst) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(src + off16 + i);
+        for (int r = 0; r < peers.world; ++r) if (r != peers.rank) dst[r][off16 + i] = v;
+    }
+    __threadfence_system();
+}
+__global__ void k_xchg_shadow_sync(unsigned* __restrict__ sseq, const __grid_constant__ XchgPeers peers) {
+    __shared__ unsigned s_seq;
+    if (threadIdx.x == 0) s_seq = *sseq + 1u;
+    __syncthreads();
+    __threadfence_system();
+    if ((int)threadIdx.x < peers.world && (int)threadIdx.x != peers.rank) *(volatile unsigned*)&ctrl(peers.base[threadIdx.x])->shadow_ready[peers.rank] = s_seq;
+    __syncthreads();
+    if (threadIdx.x == 0) { wait_flags(ctrl(peers.base[peers.rank])->shadow_ready, peers.world, peers.rank, s_seq); *sseq = s_seq; }
+}
+
 }  // namespace
 
 size_t vctk_xchg_region_bytes(const vct_ctx* c) {
@@ -179,19 +198,19 @@ int vctk_xchg_setup(vct_ctx* c) {
     VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     for (int r = 0; r < VCT_MAX_PEERS; ++r) c->peer[r] = vct_peer{};
     vct_peer& me = c->peer[c->cfg.rank];
-    me.staging = c->d_xchg; me.radiance = c->d_radiance; me.color = c->d_color; me.image = c->d_image;
+    me.staging = c->d_xchg; me.radiance = c->d_radiance; me.color = c->d_color; me.image = c->d_image; me.shadow = c->d_shadow_base;
     c->peers_attached = 1;
     return 0;
 }
 void vctk_xchg_free(vct_ctx* c) {
     for (int r = 0; r < VCT_MAX_PEERS; ++r) {
         if (r != c->cfg.rank && c->peer_ipc[r]) {
-            for (void* p : {c->peer[r].staging, c->peer[r].radiance, c->peer[r].color, c->peer[r].image}) if (p) cudaIpcCloseMemHandle(p);
+            for (void* p : {c->peer[r].staging, c->peer[r].radiance, c->peer[r].color, c->peer[r].image, c->peer[r].shadow}) if (p) cudaIpcCloseMemHandle(p);
         }
         c->peer[r] = vct_peer{}; c->peer_ipc[r] = false;
     }
-    cudaFree(c->d_xchg); cudaFree(c->d_xchg_count);
-    c->d_xchg = nullptr; c->d_xchg_count = nullptr; c->peers_attached = 0;
+    cudaFree(c->d_xchg); cudaFree(c->d_xchg_count); cudaFree(c->d_xchg_dst);
+    c->d_xchg = nullptr; c->d_xchg_count = nullptr; c->d_xchg_dst = nullptr; c->peers_attached = 0;
 }
 bool vctk_xchg_ready(const vct_ctx* c) { return c->cfg.world_size > 1 && c->d_xchg && c->peers_attached == c->cfg.world_size; }
 static int xchg_peers(vct_ctx* c, XchgPeers& p) {
@@ -246,6 +265,29 @@ int vctk_xchg_frame(vct_ctx* c, bool dense) {
     if (vctk_publish_upper(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR)) return 1;
     k_xchg_ack<<<1, 32, 0, c->stream>>>(seq, p);
     VCT_LAUNCH_CHECK(c, "k_xchg_ack");
+    return 0;
+}
+// Sharded shadow pass (raster_passes.cu): the caller has rasterised rows [row_lo, row_hi) of the CURRENT shadow map (c->d_shadow, the
+// half selected by shadow_parity); store them into the same half of every peer's map and wait until every peer's band has arrived.
+int vctk_xchg_shadow(vct_ctx* c, int row_lo, int row_hi) {
+    XchgPeers p{};
+    if (xchg_peers(c, p)) return 1;
+    const size_t half = (size_t)c->S * c->S;                // floats per map
+    if (!c->d_xchg_dst) {                                    // device table of the peers' map bases (both halves follow each other)
+        VCT_CHECK(c, cudaMalloc(&c->d_xchg_dst, sizeof(void*) * VCT_MAX_PEERS));
+        void* h[VCT_MAX_PEERS] = {};
+        for (int r = 0; r < p.world; ++r) h[r] = c->peer[r].shadow;
+        VCT_CHECK(c, cudaMemcpyAsync(c->d_xchg_dst, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    }
+    unsigned* sseq = c->d_xchg_count + 24;
+    const size_t off16 = ((size_t)c->shadow_parity * half + (size_t)row_lo * c->S) / 4, n16 = (size_t)(row_hi - row_lo) * c->S / 4;
+    if (n16) {
+        k_xchg_push_shadow<<<(unsigned)std::min<size_t>((n16 + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 8), kThreads, 0, c->stream>>>(
+            reinterpret_cast<const uint4*>(c->d_shadow_base), n16, off16, p, reinterpret_cast<uint4* const*>(c->d_xchg_dst));
+        VCT_LAUNCH_CHECK(c, "k_xchg_push_shadow");
+    }
+    k_xchg_shadow_sync<<<1, 32, 0, c->stream>>>(sseq, p);
+    VCT_LAUNCH_CHECK(c, "k_xchg_shadow_sync");
     return 0;
 }
 // after the cone trace of a sharded frame: rank 0's stream continues only when every rank's pixels are in its image

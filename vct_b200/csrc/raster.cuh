@@ -91,7 +91,21 @@ struct TileQueues {
     uint2* expand; unsigned expand_cap; unsigned* expand_count;
     uint2* pixels; unsigned pixel_cap; unsigned* pixel_count;      // single pixels of tiny triangles: (slot, x | y << 16)
     Counters* counters;             // vct_flag_overflow
+    // sharded frame: which pixels this rank rasterises.  Camera pass (own_band == 0): its 64x64 screen tiles (tile (tx, ty) belongs to rank
+    // (tx + ty) mod N, like the cone trace).  Shadow pass (own_band > 0): its band of own_band rows.  own_world <= 1: no filter.
+    int own_world, own_rank, own_band;
 };
+__device__ __forceinline__ bool pixel_owned(const TileQueues& q, int px, int py) {
+    if (q.own_world <= 1) return true;
+    if (q.own_band) return py / q.own_band == q.own_rank;
+    return ((px >> 6) + (py >> 6)) % q.own_world == q.own_rank;
+}
+// may the 8x4 raster tile at (ox, oy), clipped to (x1, y1), hold a pixel this rank owns?  (it touches at most 2x2 screen tiles)
+__device__ __forceinline__ bool tile_owned(const TileQueues& q, int ox, int oy, int x1, int y1) {
+    if (q.own_world <= 1) return true;
+    const int ex = min(ox + 7, x1), ey = min(oy + 3, y1);
+    return pixel_owned(q, ox, oy) || pixel_owned(q, ex, oy) || pixel_owned(q, ox, ey) || pixel_owned(q, ex, ey);
+}
 
 // Is the pixel-centre box [bx0,bx1]x[by0,by1] entirely outside one of the edges?
 __device__ __forceinline__ bool tile_rejected(const TriSetup& s, int bx0, int by0, int bx1, int by1) {
@@ -112,7 +126,7 @@ __device__ __forceinline__ void enqueue_tiles(bool queued, const TriSetup& s, ui
     const unsigned lt_mask = (1u << lane) - 1u;
     const int bw = queued ? s.x1 - s.x0 + 1 : 0, bh = queued ? s.y1 - s.y0 + 1 : 0;
     const int ntx = (bw + kTileW - 1) / kTileW, nty = (bh + kTileH - 1) / kTileH;
-    const bool single = queued && ntx * nty == 1;
+    const bool single = queued && ntx * nty == 1 && tile_owned(q, s.x0, s.y0, s.x1, s.y1);
     const unsigned sm = __ballot_sync(0xffffffffu, single);
     if (sm) {
         uint32_t base = 0;
@@ -153,7 +167,7 @@ __device__ __forceinline__ void expand_items(const unsigned char* __restrict__ s
             bool keep = false; int ox = 0, oy = 0;
             if (tb + lane < nt) {
                 ox = s.x0 + tx * kTileW; oy = s.y0 + (r0 + ty) * kTileH;
-                keep = !tile_rejected(s, ox, oy, min(ox + kTileW - 1, s.x1), min(oy + kTileH - 1, s.y1));
+                keep = tile_owned(q, ox, oy, s.x1, s.y1) && !tile_rejected(s, ox, oy, min(ox + kTileW - 1, s.x1), min(oy + kTileH - 1, s.y1));
             }
             tx += 32; while (tx >= ntx) { tx -= ntx; ty++; }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -174,6 +188,7 @@ static inline TileQueues vctk_tile_queues(vct_ctx* c) {
     q.expand = reinterpret_cast<uint2*>(c->d_expand_queue); q.expand_cap = (unsigned)c->expand_cap; q.expand_count = &c->d_counters->expand_count;
     q.pixels = reinterpret_cast<uint2*>(c->d_pixel_queue); q.pixel_cap = (unsigned)c->pixel_cap; q.pixel_count = &c->d_counters->pixel_count;
     q.counters = c->d_counters;
+    q.own_world = 0; q.own_rank = 0; q.own_band = 0;
     return q;
 }
 // reserve one setup slot per lane with `want` (one atomic per warp); returns the lane's slot

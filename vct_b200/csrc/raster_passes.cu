@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) k_raster_bin(RasterArgs a) {
                 for (int py = s.y0; py <= s.y1; ++py)
                     for (int px = s.x0; px <= s.x1; ++px) {
                         float l[3];
-                        if (!tri_cover(s, px, py, l)) continue;
+                        if (!pixel_owned(a.q, px, py) || !tri_cover(s, px, py, l)) continue;
                         const float z = interp1(l, s.z[0], s.z[1], s.z[2]);
                         if (z < -1.0f || z > 1.0f) continue;
                         if (!alpha_pass<CAMERA>(a, ac, px, py, l)) continue;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kThreads) k_raster_tiles(RasterArgs a) {
         const TriSetup& s = ts.s;
         const int px = (int)(it.y & 0xFFFFu) + (lane & (kTileW - 1)), py = (int)(it.y >> 16) + (lane >> 3);
         float l[3];
-        if (px > s.x1 || py > s.y1 || !tri_cover(s, px, py, l)) continue;
+        if (px > s.x1 || py > s.y1 || !pixel_owned(a.q, px, py) || !tri_cover(s, px, py, l)) continue;
         const float z = interp1(l, s.z[0], s.z[1], s.z[2]);
         if (z < -1.0f || z > 1.0f) continue;
         if (ts.alpha_tex >= 0 && !alpha_test_slow<CAMERA>(a, ts.tri, ts.alpha_tex, px, py, l)) continue;   // rare: masked materials only
@@ -233,17 +233,31 @@ int run_raster(vct_ctx* c) {
     a.setups = reinterpret_cast<TileSetup*>(c->d_setup); a.q = vctk_tile_queues(c);
     a.setup_cap = (unsigned)c->setup_cap; a.counters = c->d_counters;
     a.setup_count = &c->d_counters->setup_count;
-    const size_t npx = (size_t)a.W * a.H;
+    // sharded frame (peers attached): a rank's cone trace reads the visibility of its own screen tiles only; the shadow map is
+    // rasterised in bands of rows, one per rank, into the map the last frame did not use, and the bands are exchanged (exchange.cu)
+    const bool sharded = vctk_xchg_ready(c);
+    int row_lo = 0, row_hi = c->S;
+    if (sharded) {
+        a.q.own_world = c->cfg.world_size; a.q.own_rank = c->cfg.rank;
+        if (!CAMERA) {
+            c->shadow_parity ^= 1; c->d_shadow = c->d_shadow_base + (size_t)c->shadow_parity * c->S * c->S;
+            a.depth_bits = reinterpret_cast<unsigned*>(c->d_shadow);
+            a.q.own_band = (c->S + c->cfg.world_size - 1) / c->cfg.world_size;
+            row_lo = std::min(c->S, c->cfg.rank * a.q.own_band); row_hi = std::min(c->S, row_lo + a.q.own_band);
+        }
+    }
+    const size_t npx = CAMERA ? (size_t)a.W * a.H : (size_t)(row_hi - row_lo) * c->S;
     const int fill_grid = (int)std::min<size_t>((npx + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 32);
     if (CAMERA) k_fill_u64<<<fill_grid, kThreads, 0, c->stream>>>(c->d_vis, npx, ~0ull);
-    else k_fill_u32<<<fill_grid, kThreads, 0, c->stream>>>(a.depth_bits, npx, 0x3F800000u);
+    else k_fill_u32<<<std::max(fill_grid, 1), kThreads, 0, c->stream>>>(a.depth_bits + (size_t)row_lo * c->S, npx, 0x3F800000u);
     VCT_LAUNCH_CHECK(c, CAMERA ? "k_fill_u64" : "k_fill_u32");
     k_reset_queue<<<1, 1, 0, c->stream>>>(c->d_counters); VCT_LAUNCH_CHECK(c, "k_reset_queue");
-    if (!c->n_tris) return 0;
+    if (!c->n_tris) return (!CAMERA && sharded) ? vctk_xchg_shadow(c, row_lo, row_hi) : 0;
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_raster_bin<CAMERA><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, CAMERA ? "k_raster_bin_camera" : "k_raster_bin_light");
     k_raster_expand<<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a.setups, a.q); VCT_LAUNCH_CHECK(c, CAMERA ? "k_raster_expand_camera" : "k_raster_expand_light");
     k_raster_tiles<CAMERA><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, CAMERA ? "k_raster_tiles_camera" : "k_raster_tiles_light");
+    if (!CAMERA && sharded) return vctk_xchg_shadow(c, row_lo, row_hi);
     return 0;
 }
 

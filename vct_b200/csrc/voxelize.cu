@@ -84,7 +84,9 @@ constexpr int kMedMax = 1024;
 constexpr int kHugeMax = 8;
 struct LongEntry { uint32_t key, head, count, pad; };               // voxel, head slot of its list, fragment count
 struct __align__(16) HugeItem { unsigned long long k; uint32_t slot, h; };   // order key + 1, fragment slot, index into the huge table
-struct LongArgs { LongEntry* queue; unsigned cap; LongEntry* huge; HugeItem* items; unsigned item_cap; int inline_long; };   // inline_long: the long-list kernels do not run this frame
+constexpr int kHugeBins = 4096, kHugeSmall = 16384;                 // coarse histogram over the triangle index; per-voxel short list of the gather pass
+struct HugeAux { unsigned hist[kHugeMax][kHugeBins]; unsigned long long thresh[kHugeMax]; unsigned small_n[kHugeMax]; unsigned pad[8]; };
+struct LongArgs { LongEntry* queue; unsigned cap; LongEntry* huge; HugeItem* items; unsigned item_cap; int inline_long; HugeAux* aux; HugeItem* small; int tri_shift; };   // inline_long: the long-list kernels do not run this frame
 
 // voxelize.geom:26-73: axis from the summed vertex normals, projection through that axis' ortho view
 __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& fc, uint32_t t, VoxSetup& S) {
@@ -653,10 +655,49 @@ __global__ void __launch_bounds__(kThreads) k_voxel_huge_compact(const Frag* __r
             const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
             if (pos < lq.item_cap) { HugeItem it; it.k = order_key(frags[i]); it.slot = i; it.h = (uint32_t)h; lq.items[pos] = it; }
             else vct_flag_overflow(counters);
+            atomicAdd(&lq.aux->hist[h][min((unsigned)(frags[i].tri >> lq.tri_shift), (unsigned)kHugeBins - 1u)], 1u);      // coarse histogram over the triangle index
         }
     }
 }
-// huge voxels, step 2: one CTA per voxel.  Radix select (12-bit digits, top down) of the r-th largest order key among the voxel's
+// huge voxels, step 2: the r fragments that matter are those of the LAST triangles.  From the coarse histogram one CTA per voxel finds
+// the bin that holds the r-th largest key; everything at or above that bin goes to a short list (step 3), a few hundred to a few
+// thousand items instead of hundreds of thousands.  The histogram is left zeroed for the next frame.
+__global__ void __launch_bounds__(256) k_voxel_huge_pick(Counters* __restrict__ counters, LongArgs lq) {
+    __shared__ unsigned s_sum[256];
+    const unsigned nh = min(counters->huge_count, (unsigned)kHugeMax), h = blockIdx.x;
+    if (h >= nh) return;
+    const int r = (int)((lq.huge[h].count - 1u) & 255u) + 1;
+    unsigned* hist = lq.aux->hist[h];
+    // thread t owns bins [16 t, 16 t + 16); suffix sums over the 256 chunk totals, then inside the chunk
+    unsigned mine = 0;
+    for (int b = 0; b < 16; ++b) mine += hist[16 * threadIdx.x + b];
+    s_sum[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned acc = 0; int t = 255;
+        for (; t > 0; --t) { if (acc + s_sum[t] >= (unsigned)r) break; acc += s_sum[t]; }
+        int b = 16 * t + 15;
+        for (; b > 16 * t; --b) { if (acc + hist[b] >= (unsigned)r) break; acc += hist[b]; }
+        lq.aux->thresh[h] = ((unsigned long long)((unsigned)b << lq.tri_shift) << 32) + 1ull;       // every key of a triangle >= b << shift
+        lq.aux->small_n[h] = 0u;
+    }
+    __syncthreads();
+    for (int b = 0; b < 16; ++b) hist[16 * threadIdx.x + b] = 0u;
+}
+// huge voxels, step 3: items at or above the voxel's threshold -> its short list
+__global__ void __launch_bounds__(kThreads) k_voxel_huge_gather(Counters* __restrict__ counters, LongArgs lq) {
+    const unsigned nh = min(counters->huge_count, (unsigned)kHugeMax);
+    if (!nh) return;
+    const unsigned n_items = min(counters->huge_items, lq.item_cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+        const HugeItem it = lq.items[i];
+        if (it.k >= lq.aux->thresh[it.h]) {
+            const unsigned pos = atomicAdd(&lq.aux->small_n[it.h], 1u);
+            if (pos < (unsigned)kHugeSmall) lq.small[(size_t)it.h * kHugeSmall + pos] = it;
+        }
+    }
+}
+// huge voxels, step 4: one CTA per voxel.  Radix select (12-bit digits, top down) of the r-th largest order key among the voxel's
 // items, then the r items at or above it are sorted and replayed.
 constexpr int kSelThreads = 1024, kSelBins = 4096;
 template <bool TRANSFER>
@@ -669,7 +710,10 @@ __global__ void __launch_bounds__(kSelThreads) k_voxel_huge_select(const Frag* _
     const unsigned h = blockIdx.x;
     if (h >= nh) return;
     const LongEntry le = lq.huge[h];
-    const unsigned n_items = min(counters->huge_items, lq.item_cap);
+    // the voxel's short list when it fits (the usual case), else every item of every huge voxel (one huge triangle range: slow, still exact)
+    const bool use_small = lq.aux->small_n[h] <= (unsigned)kHugeSmall;
+    const HugeItem* __restrict__ items = use_small ? lq.small + (size_t)h * kHugeSmall : lq.items;
+    const unsigned n_items = use_small ? lq.aux->small_n[h] : min(counters->huge_items, lq.item_cap);
     const int r = (int)((le.count - 1u) & 255u) + 1;
     unsigned long long prefix = 0ull;                         // the digits of the r-th largest key fixed so far (top down)
     unsigned need = (unsigned)r;                              // its rank (from the top) among the items that share the prefix
@@ -678,7 +722,7 @@ __global__ void __launch_bounds__(kSelThreads) k_voxel_huge_select(const Frag* _
         __syncthreads();
         const unsigned long long hi_mask = shift + 12 >= 64 ? 0ull : ~0ull << (shift + 12);
         for (unsigned i = threadIdx.x; i < n_items; i += kSelThreads) {
-            const HugeItem it = lq.items[i];
+            const HugeItem it = items[i];
             if (it.h == h && (it.k & hi_mask) == prefix) atomicAdd(&s_hist[(unsigned)(it.k >> shift) & (kSelBins - 1)], 1u);
         }
         __syncthreads();
@@ -696,7 +740,7 @@ __global__ void __launch_bounds__(kSelThreads) k_voxel_huge_select(const Frag* _
     if (threadIdx.x < 256) { s_key[threadIdx.x] = 0ull; s_slot[threadIdx.x] = 0u; }
     __syncthreads();
     for (unsigned i = threadIdx.x; i < n_items; i += kSelThreads) {
-        const HugeItem it = lq.items[i];
+        const HugeItem it = items[i];
         if (it.h == h && it.k >= prefix) { const unsigned pos = atomicAdd(&s_n, 1u); if (pos < 256u) { s_key[pos] = it.k; s_slot[pos] = it.slot; } }
     }
     __syncthreads();
@@ -820,6 +864,7 @@ int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* til
 
 size_t vctk_vox_setup_bytes() { return sizeof(VoxSetup); }
 size_t vctk_frag_bytes() { return sizeof(Frag); }
+size_t vctk_huge_aux_bytes() { return sizeof(HugeAux) + (size_t)kHugeMax * kHugeSmall * sizeof(HugeItem); }
 
 static void normal_matrix_host(const float* m, float n[9]) {
     // mat3(transpose(inverse(M))) = cofactor(M3)/det — same operation order as the oracle
@@ -883,7 +928,9 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset, bool 
     // lists itself); otherwise they are skipped: ~15 us of launches per frame that the common case does not need.
     const bool long_path = p.warp_voxels || p.warp_texture || (c->h_overflow && ((volatile unsigned*)c->h_overflow)[1]);
     LongArgs lq{reinterpret_cast<LongEntry*>(c->d_long_queue), (unsigned)c->long_cap, reinterpret_cast<LongEntry*>(c->d_long_queue) + c->long_cap,
-                reinterpret_cast<HugeItem*>(c->d_huge_items), c->d_huge_items ? (unsigned)c->frag_cap : 0u, long_path ? 0 : 1};
+                reinterpret_cast<HugeItem*>(c->d_huge_items), c->d_huge_items ? (unsigned)c->frag_cap : 0u, long_path ? 0 : 1,
+                reinterpret_cast<HugeAux*>(c->d_huge_aux), reinterpret_cast<HugeItem*>((char*)c->d_huge_aux + sizeof(HugeAux)), 0};
+    while (((size_t)c->n_tris >> lq.tri_shift) > (size_t)kHugeBins) lq.tri_shift++;
     const float op = fuse_transfer ? p.voxel_set_opacity : 0.0f;
     if (fuse_transfer) k_voxel_resolve<true><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, op, lq);
     else k_voxel_resolve<false><<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, a.displaced, c->d_color, c->d_normal, c->d_radiance, op, lq);
@@ -894,6 +941,10 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset, bool 
     VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
     {
         k_voxel_huge_compact<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, lq);
+        VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+        k_voxel_huge_pick<<<kHugeMax, 256, 0, c->stream>>>(c->d_counters, lq);
+        VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+        k_voxel_huge_gather<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(c->d_counters, lq);
         VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
         if (fuse_transfer) k_voxel_huge_select<true><<<kHugeMax, kSelThreads, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
         else k_voxel_huge_select<false><<<kHugeMax, kSelThreads, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);

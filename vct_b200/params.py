@@ -24,11 +24,11 @@ class Config(C.Structure):
                 ("max_fragments", C.c_int), ("n_devices", C.c_int), ("devices", C.POINTER(C.c_int))]
 
 
-EXCHANGE_HANDLE_BYTES = 256
+EXCHANGE_HANDLE_BYTES = 384
 
 
 class Peer(C.Structure):          # vct_peer
-    _fields_ = [("staging", C.c_void_p), ("radiance", C.c_void_p), ("color", C.c_void_p), ("image", C.c_void_p)]
+    _fields_ = [("staging", C.c_void_p), ("radiance", C.c_void_p), ("color", C.c_void_p), ("image", C.c_void_p), ("shadow", C.c_void_p)]
 
 
 class Light(C.Structure):
