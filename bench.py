@@ -123,7 +123,7 @@ def algorithmic_bytes(D, L, S, W, H, T, F, U, chains):
     }
 
 
-VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_tiles", "k_voxel_resolve", "k_voxel_resolve_long",
+VOXELIZE_KERNELS = ("k_transform_vertices", "k_voxel_reset", "k_voxel_bin", "k_voxel_tiles", "k_voxel_resolve", "k_voxel_resolve_medium", "k_voxel_huge_compact", "k_voxel_huge_pick", "k_voxel_huge_gather", "k_voxel_huge_select",
                     "k_voxel_bin_cas", "k_voxel_tiles_cas", "k_voxel_bin_max", "k_voxel_tiles_max")
 
 

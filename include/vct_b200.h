@@ -47,6 +47,10 @@ typedef struct {
      * that fans every call out; rank / world_size / device above are then ignored.  0 or 1: one context on `device`. */
     int n_devices;
     const int* devices;
+    /* How z is dealt to the ranks: rank of voxel layer z = (z / slab_stripe) mod world_size.  0 = dim / world_size (one contiguous slab per
+     * rank); 16 (a multiple of 16 that divides dim / world_size) interleaves stripes, which balances scenes that fill only part of the
+     * volume (Sponza occupies the middle half of z: with contiguous slabs half of 8 ranks have nothing to voxelise). */
+    int slab_stripe;
 } vct_config;
 
 /* 80-byte std140 light record — reference src/Scene.cpp:64-76, shaders/voxelize.frag:31-45. */

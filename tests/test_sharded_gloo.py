@@ -87,7 +87,69 @@ def test_slab_exchange_reassembles_single_process_pyramid(world):
     assert res == {r: True for r in range(world)}
 
 
+def _stripe_worker(rank, world, port, q, stripe, levels):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import oracle_lib as ol
+        rng = np.random.default_rng(9)
+        full = [np.where(rng.random(D ** 3) < 0.2, rng.integers(0, 2 ** 32, D ** 3, dtype=np.uint64), 0).astype(np.uint32)]
+        for l in range(levels - 1):
+            dst = np.zeros(((D >> l) // 2) ** 3, np.uint32)
+            ol.lib().orc_mip(D >> l, ol.ptr(full[-1]), ol.ptr(dst), 0)
+            full.append(dst)
+        own = SH.stripes(D, stripe, world, rank)
+        top = SH.top_sharded_level(stripe, levels)
+        mine = [np.zeros_like(v) for v in full]
+        for lo, hi in own:
+            mine[0][lo * D * D:hi * D * D] = full[0][lo * D * D:hi * D * D]
+        for l in range(top):                                 # own stripes only: BOX2 needs no halo while texel layers stay inside a stripe
+            d = D >> l
+            dst = np.zeros((d // 2) ** 3, np.uint32)
+            ol.lib().orc_mip(d, ol.ptr(mine[l]), ol.ptr(dst), 0)
+            dd = d // 2
+            for lo, hi in own:
+                a, b = (lo >> (l + 1)) * dd * dd, (hi >> (l + 1)) * dd * dd
+                assert b > a
+                mine[l + 1][a:b] = dst[a:b]
+                assert np.array_equal(dst[a:b], full[l + 1][a:b])
+        tens = [torch.from_numpy(v.view(np.int32)) for v in mine[:top + 1]]
+        for t in tens:                                       # the exchange: every layer has exactly one owner, the others hold zeros
+            dist.all_reduce(t)
+        got = [t.numpy().view(np.uint32) for t in tens]
+        for l in range(top, levels - 1):                     # the tail: every rank, from the complete level below
+            dst = np.zeros(((D >> l) // 2) ** 3, np.uint32)
+            ol.lib().orc_mip(D >> l, ol.ptr(got[l]), ol.ptr(dst), 0)
+            got.append(dst)
+        q.put((rank, len(got) == levels and all(np.array_equal(a, b) for a, b in zip(got, full))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,stripe,levels", [(2, 4, 5), (2, 8, 5), (4, 2, 4)])
+def test_interleaved_stripes_reassemble_single_process_pyramid(world, stripe, levels):
+    """Layers dealt out in stripes (vct_config.slab_stripe): levels up to log2(stripe) from the own stripes, the rest after the exchange."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stripe_worker, args=(r, world, port, q, stripe, levels)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert res == {r: True for r in range(world)}
+
+
 def test_partition_maths():
+    assert SH.stripes(256, 32, 8, 3) == [(96, 128)] == [SH.slab_range(256, 8, 3)]
+    assert SH.stripes(256, 16, 8, 3) == [(48, 64), (176, 192)] and SH.stripes(512, 16, 2, 1)[:2] == [(16, 32), (48, 64)]
+    assert all(sum(SH.stripe_owner(z, 16, 8) == r for z in range(256)) == 32 for r in range(8))
+    assert all(SH.stripe_owner(z, 16, 8) == 3 for lo, hi in SH.stripes(256, 16, 8, 3) for z in range(lo, hi))
+    assert SH.top_sharded_level(16, 6) == 4 and SH.top_sharded_level(32, 6) == 5 and SH.top_sharded_level(128, 6) == 5 and SH.top_sharded_level(16, 3) == 2
+    with pytest.raises(ValueError):
+        SH.stripes(256, 24, 8, 0)
     assert [SH.slab_range(256, 8, r) for r in (0, 7)] == [(0, 32), (224, 256)]
     assert SH.level_chunks(256, 6, 8) == [256 ** 3 // 8, 128 ** 3 // 8, 64 ** 3 // 8, 32 ** 3 // 8, 16 ** 3 // 8, 8 ** 3 // 8]
     with pytest.raises(ValueError):

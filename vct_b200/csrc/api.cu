@@ -91,7 +91,13 @@ int make_volumes(vct_ctx* c) {
     c->seg_valid = false; c->seg_cur = 0;
     if (make_pyramid_texture(c, &c->radiance_arr, &c->radiance_tex, &c->radiance_tex_point, &c->radiance_tex_last, c->radiance_surf, &c->d_pub_mask_radiance)) return 1;
     const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
-    c->z_lo = (int)((long long)c->D * r / ws); c->z_hi = (int)((long long)c->D * (r + 1) / ws);
+    int stripe = c->cfg.slab_stripe;
+    if (stripe == 0 && ws > 1) { const char* e = getenv("VCT_SLAB_STRIPE"); if (e && *e) stripe = atoi(e); }        // tuning override for hosts that leave the field 0
+    if (stripe > 0 && ws > 1 && (c->D / ws) % stripe) stripe = 0;                                                   // does not fit this volume: contiguous slabs
+    const int T = stripe > 0 && ws > 1 ? stripe : c->D / ws;
+    if (T < 1 || c->D % ws) { c->error = "dim must be divisible by world_size"; return 1; }
+    if (ws > 1 && stripe > 0 && (T % 16 || (T & (T - 1)))) { c->error = "slab_stripe must be a power of two >= 16"; return 1; }
+    c->st.T = T; c->st.N = ws; c->st.rank = r; c->st.count = c->D / (T * ws);
     return 0;
 }
 
@@ -194,7 +200,7 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     cp(f.mvp_x, p->mvp_x); cp(f.mvp_y, p->mvp_y); cp(f.mvp_z, p->mvp_z);
     f.p = *p; f.D = c->D; f.L = c->L; f.S = c->S; f.W = c->W; f.H = c->H;
     f.n_lights = c->n_lights; std::memcpy(f.lights, c->h_lights, sizeof f.lights);
-    f.z_lo = c->z_lo; f.z_hi = c->z_hi;
+    f.st = c->st;
     build_schedule(f.sched_diffuse, p->diffuse_cone, c->L); build_schedule(f.sched_specular, p->specular_cone, c->L);
     if (c->n_actors <= kBlobActors) {                    // by value through the launch: no copy engine on the frame's critical path
         static_assert(offsetof(FrameBlob, models) == sizeof(FrameConst), "blob layout");
@@ -628,6 +634,8 @@ int vct_exchange(vct_ctx* c) { VCT_NO_GROUP(c, "vct_exchange");
     vct_prof_begin(c);
     const bool rad = c->h_fc.p.draw_radiance != 0;
     if (!rad && ensure_color_texture(c)) return 1;
+    // the levels whose texel layers straddle the ranks' stripes are filtered here, on every rank, from the gathered level below them
+    if (c->cfg.world_size > 1 && vctk_mip_top_sharded_level(c) + 1 < c->L && vctk_mip_tail(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR)) return 1;
     return vctk_publish(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR);
 }
 
@@ -754,13 +762,18 @@ int vct_read_volume(vct_ctx* c, int which, int level, void* out) {
         // others are not): assemble the level from the ranks' slabs
         void* p0; size_t bytes; if (volume_ptr(c, which, level, &p0, &bytes)) return 1;
         const int ws = (int)c->group.size() + 1, d = level_dim(c->D, level);
-        if (d % ws) { cudaSetDevice(c->cfg.device); VCT_CHECK(c, cudaMemcpyAsync(out, p0, bytes, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream)); return 0; }
-        const size_t chunk = bytes / ws;
+        // levels above the ranks' stripes exist (whole) only in the traced pyramid, computed on every rank after the exchange: rank 0's copy
+        if (level > vctk_mip_top_sharded_level(c)) { cudaSetDevice(c->cfg.device); VCT_CHECK(c, cudaMemcpyAsync(out, p0, bytes, cudaMemcpyDeviceToHost, c->stream)); VCT_CHECK(c, cudaStreamSynchronize(c->stream)); return 0; }
+        const size_t run = (size_t)d * d * (c->st.T >> level) * 4;          // bytes of one stripe at this level
         for (int r = 0; r < ws; ++r) {
             vct_ctx* m = r ? c->group[r - 1] : c;
             void* pm; size_t bm; if (volume_ptr(m, which, level, &pm, &bm)) return fail(c, m->error.c_str());
             cudaSetDevice(m->cfg.device);
-            VCT_CHECK(c, cudaMemcpyAsync((char*)out + r * chunk, (char*)pm + r * chunk, chunk, cudaMemcpyDeviceToHost, m->stream)); VCT_CHECK(c, cudaStreamSynchronize(m->stream));
+            for (int k = 0; k < m->st.count; ++k) {
+                const size_t off = (size_t)d * d * (stripe_z(m->st, k) >> level) * 4;
+                VCT_CHECK(c, cudaMemcpyAsync((char*)out + off, (char*)pm + off, run, cudaMemcpyDeviceToHost, m->stream));
+            }
+            VCT_CHECK(c, cudaStreamSynchronize(m->stream));
         }
         return 0;
     }

@@ -71,13 +71,29 @@ struct DevMaterial { int diffuse_tex, specular_tex, normal_tex, roughness_tex, m
 #define VCT_MAX_CONE_STEPS 64
 struct ConeSchedule { float h[VCT_MAX_CONE_STEPS]; float lambda[VCT_MAX_CONE_STEPS]; int n_point, n_last, steps, pad; };
 
+// How the z layers of the volume are dealt to the ranks (multi-GPU): layer z belongs to rank (z / T) mod N.  T = D / N gives one contiguous slab
+// per rank, T = 16 interleaves stripes.  A rank owns `count` = D / (T N) stripes; its k-th stripe starts at z = (k N + rank) T.  One GPU: N = 1, T = D.
+struct Stripes { int T, N, rank, count; };
+__host__ __device__ __forceinline__ bool owns_z(const Stripes& s, int z) { return s.N <= 1 || (z / s.T) % s.N == s.rank; }
+__host__ __device__ __forceinline__ int stripe_z(const Stripes& s, int k) { return (k * s.N + s.rank) * s.T; }
+// does this rank own a layer of [zlo, zhi] (inclusive, already clamped to the volume)?
+__host__ __device__ __forceinline__ bool owns_any_z(const Stripes& s, int zlo, int zhi) {
+    if (s.N <= 1) return true;
+    const int a = zlo / s.T, b = zhi / s.T;
+    if (b - a + 1 >= s.N) return true;
+    for (int k = a; k <= b; ++k) if (k % s.N == s.rank) return true;
+    return false;
+}
+// index i of an array laid out over this rank's stripes back to back (`per` items per stripe) -> index in the whole volume's array
+__host__ __device__ __forceinline__ size_t stripe_index(const Stripes& s, size_t i, size_t per) { const size_t k = i / per; return (k * s.N + s.rank) * per + (i - k * per); }
+
 struct FrameConst {
     Mat4 projection, view, lp, lv, ls, ls_inverse, mvp_x, mvp_y, mvp_z;
     vct_frame_params p;          // scalar settings (matrices inside are unused on the device)
     int D, L, S, W, H;
     int n_lights;
     vct_light lights[8];
-    int z_lo, z_hi;              // z-slab [z_lo, z_hi) owned by this rank
+    Stripes st;                  // which z layers this rank owns
     ConeSchedule sched_diffuse, sched_specular;
 };
 
@@ -109,7 +125,7 @@ struct HostMesh {
 struct vct_ctx {
     vct_config cfg{};
     int D = 0, L = 0, S = 0, W = 0, H = 0;
-    int z_lo = 0, z_hi = 0;
+    Stripes st{0, 1, 0, 1};          // z layers owned by this rank (make_volumes)
     cudaStream_t stream = nullptr;
     std::string error;
     unsigned long long launches = 0;
@@ -246,6 +262,8 @@ int vctk_mip(vct_ctx*, int which, int mode, int publish);
 int vctk_mip_chains(vct_ctx*, int n, const int* which, const int* publish, int mode, bool masked = false);
 int vctk_publish(vct_ctx*, int which);
 int vctk_publish_upper(vct_ctx*, int which);   // levels 1..L-1 only
+int vctk_mip_top_sharded_level(const vct_ctx*);  // sharded frames: last level filtered from a rank's own stripes
+int vctk_mip_tail(vct_ctx*, int which);          // sharded frames: the levels above it, from the exchanged level, on every rank
 int vctk_xchg_setup(vct_ctx*);
 void vctk_xchg_free(vct_ctx*);
 bool vctk_xchg_ready(const vct_ctx*);          // multi-GPU with every peer attached: the frame entry points run the whole sharded frame

@@ -56,15 +56,15 @@ __device__ __forceinline__ void wait_flags(const unsigned* flags, int world, int
 }
 
 __global__ void __launch_bounds__(kThreads) k_xchg_push(const uint4* __restrict__ level0, const uint32_t* __restrict__ seg_now, const uint32_t* __restrict__ seg_before, int dense,
-                                                        size_t word_lo, size_t word_hi, unsigned* __restrict__ counter, const unsigned* __restrict__ seq,
+                                                        Stripes st, size_t w_stripe, size_t n, unsigned* __restrict__ counter, const unsigned* __restrict__ seq,
                                                         const __grid_constant__ XchgPeers peers) {
     __shared__ uint32_t s_list[kThreads / 32][128];
     if (threadIdx.x == 0) wait_flags(ctrl(peers.base[peers.rank])->consumed, peers.world, peers.rank, *seq);   // the peers are done with last frame's records
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t n = word_hi - word_lo, n_round = (n + 31) & ~(size_t)31;
+    const size_t n_round = (n + 31) & ~(size_t)31;                          // n mask words over this rank's stripes, back to back
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_round; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t t = word_lo + i;
+        const size_t t = i < n ? stripe_index(st, i, w_stripe) : 0;
         const uint32_t flags = i < n ? (dense ? 0x01010101u : (__ldg(seg_now + t) | __ldg(seg_before + t))) : 0u;
         const unsigned nz = (flags & 0xFFu ? 1u : 0u) | (flags & 0xFF00u ? 2u : 0u) | (flags & 0xFF0000u ? 4u : 0u) | (flags & 0xFF000000u ? 8u : 0u);
         int inc = __popc(nz);
@@ -97,12 +97,14 @@ __global__ void __launch_bounds__(kThreads) k_xchg_push(const uint4* __restrict_
     __threadfence_system();
 }
 // levels >= 1 of the own slab, dense, straight into every peer's linear pyramid (same offsets on every rank)
-struct UpperLevels { unsigned long long first[VCT_MAX_LEVELS + 1]; unsigned long long off[VCT_MAX_LEVELS]; int n; };   // in 16-byte units / words
+// one run per (level, stripe): `first` = running element count, `off` = word offset in the pyramid; runs of one level have one length
+constexpr int kMaxRuns = 160;
+struct UpperLevels { unsigned first[kMaxRuns + 1]; unsigned off[kMaxRuns]; int n; };
 __global__ void __launch_bounds__(kThreads) k_xchg_push_upper(const uint32_t* __restrict__ pyramid, const __grid_constant__ UpperLevels lv, const __grid_constant__ XchgPeers peers) {
     const unsigned long long total = lv.first[lv.n];
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
-        int k = 0;
-        while (k + 1 < lv.n && i >= lv.first[k + 1]) ++k;
+        int k = 0, hi = lv.n;                                                 // binary search: first[k] <= i < first[k + 1]
+        while (hi - k > 1) { const int m = (k + hi) >> 1; if (i >= lv.first[m]) k = m; else hi = m; }
         const unsigned long long w = lv.off[k] + (i - lv.first[k]);           // word offset of this rank's chunk element in the pyramid
         const uint32_t v = __ldcg(pyramid + w);
         for (int r = 0; r < peers.world; ++r) if (r != peers.rank) peers.pyramid[r][w] = v;
@@ -181,14 +183,14 @@ __global__ void k_xchg_shadow_sync(unsigned* __restrict__ sseq, const __grid_con
 }  // namespace
 
 size_t vctk_xchg_region_bytes(const vct_ctx* c) {
-    const size_t cap = (size_t)c->D * c->D * (c->z_hi - c->z_lo) / 8;
+    const size_t cap = (size_t)c->D * c->D * c->st.T * c->st.count / 8;
     return kHdr + ((cap * 4 + 127) & ~(size_t)127) + cap * 32;
 }
 int vctk_xchg_setup(vct_ctx* c) {
     if (c->d_xchg) return 0;
     const int ws = c->cfg.world_size;
     if (ws < 2 || ws > VCT_MAX_PEERS) { c->error = "sparse exchange: world_size must be in [2, 8]"; return 1; }
-    c->xchg_cap = (unsigned)((size_t)c->D * c->D * (c->z_hi - c->z_lo) / 8);
+    c->xchg_cap = (unsigned)((size_t)c->D * c->D * c->st.T * c->st.count / 8);
     c->xchg_region_bytes = vctk_xchg_region_bytes(c);
     const size_t bytes = kCtrlBytes + c->xchg_region_bytes * ws;
     VCT_CHECK(c, cudaMalloc(&c->d_xchg, bytes));
@@ -239,20 +241,23 @@ int vctk_xchg_frame(vct_ctx* c, bool dense) {
         c->copy_pending[par] = false;
     }
     // gi_body swapped the masks at its end: this frame's is seg_cur ^ 1, last frame's is seg_cur
-    const size_t words_per_slice = (size_t)c->D * c->D / 32;
-    const size_t lo = (size_t)c->z_lo * words_per_slice, hi = (size_t)c->z_hi * words_per_slice;
-    const size_t blocks = std::min<size_t>((hi - lo + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
+    const size_t w_stripe = (size_t)c->D * c->D / 32 * c->st.T, n_words = w_stripe * c->st.count;
+    const size_t blocks = std::min<size_t>((n_words + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_xchg_push<<<(unsigned)std::max<size_t>(blocks, 1), kThreads, 0, c->stream>>>(reinterpret_cast<const uint4*>(pyr), reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]),
-                                                                                  reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), dense ? 1 : 0, lo, hi, counter, seq, p);
+                                                                                  reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), dense ? 1 : 0, c->st, w_stripe, n_words, counter, seq, p);
     VCT_LAUNCH_CHECK(c, "k_xchg_push");
-    if (c->L > 1) {
+    const int top = vctk_mip_top_sharded_level(c);          // levels 1..top: this rank's stripes, dense; the levels above follow from level `top` on every rank
+    if (top >= 1) {
         UpperLevels lv{};
         unsigned long long n = 0;
-        for (int l = 1; l < c->L; ++l) {
-            const unsigned long long d = level_dim(c->D, l), chunk = d * d * d / (unsigned long long)c->cfg.world_size;
-            lv.first[lv.n] = n; lv.off[lv.n] = c->level_off[l] + chunk * (unsigned long long)c->cfg.rank; lv.n++; n += chunk;
+        for (int l = 1; l <= top; ++l) {
+            const unsigned long long d = level_dim(c->D, l), run = d * d * (unsigned long long)(c->st.T >> l);
+            for (int k = 0; k < c->st.count; ++k) {
+                if (lv.n >= kMaxRuns || c->level_off[l] + d * d * d > 0xFFFFFFFFull) { c->error = "slab exchange: too many (level, stripe) runs — use a larger slab_stripe"; return 1; }
+                lv.first[lv.n] = (unsigned)n; lv.off[lv.n] = (unsigned)(c->level_off[l] + d * d * (unsigned long long)(stripe_z(c->st, k) >> l)); lv.n++; n += run;
+            }
         }
-        lv.first[lv.n] = n;
+        lv.first[lv.n] = (unsigned)n;
         k_xchg_push_upper<<<(unsigned)std::min<unsigned long long>((n + kThreads - 1) / kThreads, (unsigned long long)VCT_SM_COUNT * 8), kThreads, 0, c->stream>>>(pyr, lv, p);
         VCT_LAUNCH_CHECK(c, "k_xchg_push_upper");
     }
@@ -262,6 +267,7 @@ int vctk_xchg_frame(vct_ctx* c, bool dense) {
     k_xchg_unpack<<<grid, kThreads, 0, c->stream>>>(reinterpret_cast<unsigned char*>(c->d_xchg), c->xchg_region_bytes, c->xchg_cap, c->cfg.rank, c->cfg.world_size, seq,
                                                     reinterpret_cast<uint4*>(pyr), surf, mask, c->D);
     VCT_LAUNCH_CHECK(c, "k_xchg_unpack");
+    if (top + 1 < c->L && vctk_mip_tail(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR)) return 1;
     if (vctk_publish_upper(c, rad ? VCT_VOL_RADIANCE : VCT_VOL_COLOR)) return 1;
     k_xchg_ack<<<1, 32, 0, c->stream>>>(seq, p);
     VCT_LAUNCH_CHECK(c, "k_xchg_ack");

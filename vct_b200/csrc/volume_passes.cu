@@ -47,8 +47,9 @@ __global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4
 // Sparse frame: one thread = 4 consecutive segments (32 voxels, 128 bytes per volume).  Segments flagged in last frame's
 // mask are zeroed in voxelColor, voxelNormal and (unless the temporal filter keeps it) voxelRadiance; this frame's mask
 // starts empty (temporal: inherits, because the decaying radiance keeps its support).  Also resets the frame counters.
+// (w_stripe mask words per owned stripe, n_words in all of them: the loop index runs over this rank's stripes back to back)
 __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
-                                                  const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t w_lo, size_t n_words, int temporal,
+                                                  const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, Stripes st, size_t w_stripe, size_t n_words, int temporal,
                                                   Counters* __restrict__ reset, unsigned block, unsigned n_blocks) {
     if (block == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
@@ -56,7 +57,8 @@ __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uin
         reset->cone_steps = 0ull; reset->overflow = 0; reset->long_count = 0; reset->huge_count = 0; reset->huge_items = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (size_t t = w_lo + block * (size_t)blockDim.x + threadIdx.x; t < n_words; t += (size_t)n_blocks * blockDim.x) {      // [w_lo, n_words): this rank's slab
+    for (size_t tl = block * (size_t)blockDim.x + threadIdx.x; tl < n_words; tl += (size_t)n_blocks * blockDim.x) {
+        const size_t t = stripe_index(st, tl, w_stripe);
         const uint32_t flags = __ldg(seg_prev + t);
         seg_cur[t] = temporal ? flags : 0u;
         if (!flags) continue;
@@ -69,18 +71,18 @@ __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uin
     }
 }
 __global__ void __launch_bounds__(kThreads) k_clear_masked(uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
-                                                           const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t w_lo, size_t n_words, int temporal,
+                                                           const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, Stripes st, size_t w_stripe, size_t n_words, int temporal,
                                                            Counters* __restrict__ reset) {
-    clear_masked_part(color, normal, radiance, seg_prev, seg_cur, w_lo, n_words, temporal, reset, blockIdx.x, gridDim.x);
+    clear_masked_part(color, normal, radiance, seg_prev, seg_cur, st, w_stripe, n_words, temporal, reset, blockIdx.x, gridDim.x);
 }
 // Frame begin of vct_gi_passes on a sparse frame: the vertex transform and the masked clear are independent, both are
 // short and neither fills the GPU, so they share one launch (the first `t_blocks` CTAs transform, the rest clear).
 struct TransformArgs { const float* verts; const int32_t* vactor; const Mat4* models; const float* nmats; size_t n; float4 *wpos, *wnrm, *wT, *wB; };
 __global__ void __launch_bounds__(kThreads) k_frame_begin(TransformArgs t, unsigned t_blocks, uint4* __restrict__ color, uint4* __restrict__ normal, uint4* __restrict__ radiance,
-                                                          const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, size_t w_lo, size_t n_words, int temporal,
+                                                          const uint32_t* __restrict__ seg_prev, uint32_t* __restrict__ seg_cur, Stripes st, size_t w_stripe, size_t n_words, int temporal,
                                                           Counters* __restrict__ reset) {
     if (blockIdx.x < t_blocks) transform_vertices_part(t.verts, t.vactor, t.models, t.nmats, t.n, t.wpos, t.wnrm, t.wT, t.wB, blockIdx.x, t_blocks);
-    else clear_masked_part(color, normal, radiance, seg_prev, seg_cur, w_lo, n_words, temporal, reset, blockIdx.x - t_blocks, gridDim.x - t_blocks);
+    else clear_masked_part(color, normal, radiance, seg_prev, seg_cur, st, w_stripe, n_words, temporal, reset, blockIdx.x - t_blocks, gridDim.x - t_blocks);
 }
 
 // --------------------------------------------------------------------------------------------- transfer
@@ -163,14 +165,15 @@ __global__ void __launch_bounds__(kThreads) k_transfer(uint4* __restrict__ color
 // works through their 16-byte quads with all lanes (about one segment in ten is flagged: without the compaction most
 // lanes would idle behind the few that found work).  Only flagged segments can hold a fragment; their radiance was
 // zeroed by k_clear_masked (non-temporal) or holds last frame's value (temporal).
-__global__ void __launch_bounds__(kThreads) k_transfer_masked(uint4* __restrict__ color, uint4* __restrict__ radiance, const uint32_t* __restrict__ seg, size_t w_lo, size_t n_words,
+__global__ void __launch_bounds__(kThreads) k_transfer_masked(uint4* __restrict__ color, uint4* __restrict__ radiance, const uint32_t* __restrict__ seg, Stripes st, size_t w_stripe, size_t n_words,
                                                               float opacity, int temporal, float decay, Counters* __restrict__ counters) {
     __shared__ uint32_t s_list[kThreads / 32][128];
     unsigned uniq = 0, maxfrag = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t n_round = w_lo + ((n_words - w_lo + 31) & ~(size_t)31);                     // [w_lo, n_words): this rank's slab
-    for (size_t t = w_lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_round; t += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t flags = t < n_words ? __ldg(seg + t) : 0u;
+    const size_t n_round = (n_words + 31) & ~(size_t)31;                                     // n_words: over this rank's stripes, back to back
+    for (size_t tl = blockIdx.x * (size_t)blockDim.x + threadIdx.x; tl < n_round; tl += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = tl < n_words ? stripe_index(st, tl, w_stripe) : 0;
+        const uint32_t flags = tl < n_words ? __ldg(seg + t) : 0u;
         const unsigned nz = (flags & 0xFFu ? 1u : 0u) | (flags & 0xFF00u ? 2u : 0u) | (flags & 0xFF0000u ? 4u : 0u) | (flags & 0xFF000000u ? 8u : 0u);
         int inc = __popc(nz);
         const int mine = inc;
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(256) k_inject_generic(const FrameConst* __rest
         const V4 w = mul44(fc.ls_inverse, mk4(nx, ny, nz, 1.0f));
         V3 vp = get_voxel_position(mk3(w.x, w.y, w.z), fc.p, warpmap);
         vp = mk3((float)D * vp.x, (float)D * vp.y, (float)D * vp.z);
-        valid = to_voxel_index(vp, D, ix, iy, iz) && iz >= fc.z_lo && iz < fc.z_hi;      // z-slab ownership (multi-GPU)
+        valid = to_voxel_index(vp, D, ix, iy, iz) && owns_z(fc.st, iz);                  // z ownership (multi-GPU)
         if (valid) o = (uint32_t)(((size_t)iz * D + iy) * D + ix);
     }
     // Neighbouring texels of a row mostly land in the same voxel (4096^2 texels onto ~4e5 voxels) and every writer
@@ -324,7 +327,7 @@ __device__ __forceinline__ uint32_t inject_target(const FrameConst& fc, const ui
     const V4 w = mul44(fc.ls_inverse, mk4(nx, ny, nz, 1.0f));
     V3 vp = get_voxel_position(mk3(w.x, w.y, w.z), fc.p, warpmap);
     vp = mk3((float)D * vp.x, (float)D * vp.y, (float)D * vp.z);
-    if (!to_voxel_index(vp, D, ix, iy, iz) || iz < fc.z_lo || iz >= fc.z_hi) return 0xFFFFFFFFu;   // z-slab ownership (multi-GPU)
+    if (!to_voxel_index(vp, D, ix, iy, iz) || !owns_z(fc.st, iz)) return 0xFFFFFFFFu;              // z ownership (multi-GPU)
     return (uint32_t)(((size_t)iz * D + iy) * D + ix);
 }
 __device__ __forceinline__ void inject_store(const FrameConst& fc, const uint16_t* __restrict__ warpmap, const uint32_t* __restrict__ color,
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(256) k_inject(const FrameConst* __restrict__ f
 struct InjectLinear {                                 // passed by value: no dependent loads of the frame constants
     float rc[3], c[3], sub0[3], sub1[3];              // per axis: 1/(max-min), max-min, center, min
     float m[16];                                      // ls_inverse, column-major
-    int S, log2_qx, D, z_lo, z_hi;
+    int S, log2_qx, D; Stripes st;
     int skip_far;                                     // the light's far plane (depth 1 = nothing rendered) misses the volume by > 1 voxel
     // Block cull: voxel coordinates are affine in (ndc x, ndc y, ndc depth): P_k = bx[k]*nx + by[k]*ny + bz[k]*nz + b0[k].  With the
     // min / max filtered depth of a 64x16 texel block (k_shadow_minmax*, written by the shadow pass) interval arithmetic bounds P over
@@ -445,8 +448,8 @@ __device__ __forceinline__ bool inject_block_active(const InjectLinear& lin, int
         const float lo = ((fminf(ax0, ax1) + fminf(ay0, ay1)) + fminf(az0, az1)) + lin.b0[k];
         const float hi = ((fmaxf(ax0, ax1) + fmaxf(ay0, ay1)) + fmaxf(az0, az1)) + lin.b0[k];
         if (hi < -1.0f - kInjectMargin || lo > fd + kInjectMargin) active = false;           // (NaN compares false: stays active)
-        // this rank's z-slab [z_lo, z_hi): (int)P truncates toward zero, so slab 0 also owns P in (-1, 0)
-        if (k == 2 && (hi < (lin.z_lo > 0 ? (float)lin.z_lo : -1.0f) - kInjectMargin || lo > (float)lin.z_hi + kInjectMargin)) active = false;
+        // this rank's z layers: (int)P truncates toward zero (P in (-1, 0) is layer 0); the interval widened by the margin, clamped to the volume
+        if (k == 2 && active && !owns_any_z(lin.st, max((int)floorf(lo - kInjectMargin), 0), min((int)floorf(hi + kInjectMargin), lin.D - 1))) active = false;
     }
     return active;
 }
@@ -490,7 +493,6 @@ __global__ void __launch_bounds__(256) k_inject_linear(const float* __restrict__
     const float* m = lin.m;
     const float ny = ((float)y * inv_s) * 2.0f - 1.0f;
     const float my0 = m[4] * ny, my1 = m[5] * ny, my2 = m[6] * ny;
-    const int z_lo = lin.z_lo, z_hi = lin.z_hi;
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(256) k_inject_linear(const float* __restrict__
         const float pz = fd * div_by_const(wz - lin.sub0[2] - lin.sub1[2], lin.c[2], lin.rc[2]);
         int ix, iy, iz;
         o[k] = 0xFFFFFFFFu;
-        if (!far && to_voxel_index(mk3(px, py, pz), D, ix, iy, iz) && iz >= z_lo && iz < z_hi) o[k] = (uint32_t)((iz * D + iy) * D + ix);
+        if (!far && to_voxel_index(mk3(px, py, pz), D, ix, iy, iz) && owns_z(lin.st, iz)) o[k] = (uint32_t)((iz * D + iy) * D + ix);
     }
     uint32_t left = __shfl_up_sync(0xffffffffu, o[3], 1);
     if ((threadIdx.x & 15) == 0) left = 0xFFFFFFFFu;                        // 16 threads per texel row of the block
@@ -595,7 +597,8 @@ struct MipChain {
 struct MipChainArgs {
     MipChain chain[2]; int n_chains;              // radiance and colour pyramids filtered by one launch
     unsigned* ticket;                             // last-CTA detection for the tail levels
-    int D, R, L, z0, nbz, tail;                   // tail: reduce levels R..L-2 -> R+1..L-1 in the last CTA
+    int D, R, L, tail;                            // tail: reduce levels R..L-2 -> R+1..L-1 in the last CTA
+    Stripes st;                                   // blockIdx.z counts the bricks of this rank's stripes, back to back
     const uint8_t *seg_a, *seg_b;                 // sparse frames: this and last frame's segment masks (nullptr: dense)
 };
 __device__ __forceinline__ uint32_t box2_words(const uint32_t w[8], const float* __restrict__ lut) {
@@ -610,10 +613,11 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
     __shared__ uint32_t s1[8 * 8 * 8], s2[4 * 4 * 4], s3[2 * 2 * 2];
     __shared__ unsigned s_last;
     lut[threadIdx.x] = (float)threadIdx.x / 255.0f; lut[threadIdx.x + 128] = (float)(threadIdx.x + 128) / 255.0f;   // visible after the first barrier below
-    const int which = blockIdx.z / args.nbz;
-    const MipChain& a = args.chain[which];
+    // one CTA = one 16^3 brick of BOTH pyramids (radiance, then colour): the segment masks are scanned once, and half as many CTAs pay
+    // the fixed cost of a launch slot, the table set-up and the barriers (8192 -> 4096 CTAs at 256^3: 48 -> see DESIGN.md)
     const int B = 1 << args.R, H = B >> 1, D = args.D;
-    const int bx = blockIdx.x * B, by = blockIdx.y * B, bz = args.z0 + (blockIdx.z - which * args.nbz) * B;
+    const int bps = args.st.T >> args.R;          // bricks per stripe along z
+    const int bx = blockIdx.x * B, by = blockIdx.y * B, bz = stripe_z(args.st, blockIdx.z / bps) + (blockIdx.z % bps) * B;
     // ---- level 0 -> 1: one thread = 4 consecutive level-1 texels (8 x 16-byte loads, 1 x 16-byte store)
     const int qx = H >> 2, nquads = qx * H * H, D1 = D >> 1;
     const bool masked = args.seg_a != nullptr;
@@ -634,7 +638,10 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
         }
         block_active = __syncthreads_or(any) != 0;
     } else __syncthreads();
-    if (block_active) {
+    if (block_active)
+    for (int which = 0; which < args.n_chains; ++which) {
+    const MipChain& a = args.chain[which];
+    if (which) __syncthreads();                                           // the shared levels of the previous chain have been read
     for (int q = threadIdx.x; q < nquads; q += kMipThreads) {
         const int lx = (q % qx) * 4, ly = (q / qx) % H, lz = q / (qx * H);
         const int x0 = bx + 2 * lx, y0 = by + 2 * ly, z0 = bz + 2 * lz;
@@ -817,53 +824,57 @@ __global__ void __launch_bounds__(kThreads) k_publish_upper(const __grid_constan
 
 // ============================================================================================ host side
 int vctk_clear_voxels(vct_ctx* c, bool reset_frame_counters) {
-    // only this rank's z-slab of level 0 is cleared (single GPU: the whole volume)
-    const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
-    k_clear<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_normal + off), n / 4,
-                                                                  reset_frame_counters ? c->d_counters : nullptr);
-    VCT_LAUNCH_CHECK(c, "k_clear");
+    // only this rank's z layers of level 0 are cleared (single GPU: the whole volume); dense frames are rare: one launch per stripe
+    for (int k = 0; k < c->st.count; ++k) {
+        const size_t off = (size_t)stripe_z(c->st, k) * c->D * c->D, n = (size_t)c->st.T * c->D * c->D;
+        k_clear<<<grid_for(n / 4, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_normal + off), n / 4,
+                                                                      reset_frame_counters && k == 0 ? c->d_counters : nullptr);
+        VCT_LAUNCH_CHECK(c, "k_clear");
+    }
     return 0;
 }
 int vctk_transfer(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
-    const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
-    // seg_mark is indexed relative to the slab like the volume pointers (off voxels = off / 8 segments)
-    k_transfer<<<grid_for(n / 8, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_radiance + off), n / 4,
-                                                                    p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters,
-                                                                    (p.temporal_filter_radiance && c->d_seg[c->seg_cur]) ? c->d_seg[c->seg_cur] + off / 8 : nullptr);
-    VCT_LAUNCH_CHECK(c, "k_transfer");
+    for (int k = 0; k < c->st.count; ++k) {
+        const size_t off = (size_t)stripe_z(c->st, k) * c->D * c->D, n = (size_t)c->st.T * c->D * c->D;
+        // seg_mark is indexed relative to the stripe like the volume pointers (off voxels = off / 8 segments)
+        k_transfer<<<grid_for(n / 8, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color + off), reinterpret_cast<uint4*>(c->d_radiance + off), n / 4,
+                                                                        p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters,
+                                                                        (p.temporal_filter_radiance && c->d_seg[c->seg_cur]) ? c->d_seg[c->seg_cur] + off / 8 : nullptr);
+        VCT_LAUNCH_CHECK(c, "k_transfer");
+    }
     return 0;
 }
 // Sparse frames need whole segments per x-row and the fused mip-chain kernel with 16^3 blocks (multi-GPU: inside the slab).
 bool vctk_sparse_supported(const vct_ctx* c) {
-    if (c->cfg.world_size > 1 && (c->z_lo % 16 || (c->z_hi - c->z_lo) % 16 || c->z_hi <= c->z_lo)) return false;   // whole 16^3 blocks per slab
+    if (c->cfg.world_size > 1 && (c->st.T % 16 || c->st.count < 1)) return false;   // whole 16^3 blocks per stripe
     return !c->seg_disabled && c->D >= 16 && c->D % 16 == 0 && c->L >= 5 && c->d_seg[0] && c->d_seg[1];
 }
 int vctk_clear_masked(vct_ctx* c) {
-    const size_t wps = (size_t)c->D * c->D / 32, w_lo = c->z_lo * wps, n_words = c->z_hi * wps;   // mask words of this rank's slab
+    const size_t w_stripe = (size_t)c->D * c->D / 32 * c->st.T, n_words = w_stripe * c->st.count;   // mask words of this rank's stripes
     const int temporal = c->h_fc.p.temporal_filter_radiance;
-    k_clear_masked<<<grid_for(n_words - w_lo, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_normal), reinterpret_cast<uint4*>(c->d_radiance),
-                                                                            reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), w_lo, n_words,
+    k_clear_masked<<<grid_for(n_words, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_normal), reinterpret_cast<uint4*>(c->d_radiance),
+                                                                            reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), c->st, w_stripe, n_words,
                                                                             temporal, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_clear");
     return 0;
 }
 int vctk_frame_begin_masked(vct_ctx* c) {
-    const size_t wps = (size_t)c->D * c->D / 32, w_lo = c->z_lo * wps, n_words = c->z_hi * wps;
+    const size_t w_stripe = (size_t)c->D * c->D / 32 * c->st.T, n_words = w_stripe * c->st.count;
     TransformArgs t{c->d_vertices, c->d_vactor, c->d_models, c->d_nmats, c->n_vertices, c->d_wpos, c->d_wnrm, c->d_wT, c->d_wB};
     const unsigned tb = (unsigned)std::min<size_t>((c->n_vertices + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
-    const unsigned cb = (unsigned)grid_for(n_words - w_lo, kThreads);
+    const unsigned cb = (unsigned)grid_for(n_words, kThreads);
     k_frame_begin<<<tb + cb, kThreads, 0, c->stream>>>(t, tb, reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_normal), reinterpret_cast<uint4*>(c->d_radiance),
-                                                       reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), w_lo, n_words,
+                                                       reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur ^ 1]), reinterpret_cast<uint32_t*>(c->d_seg[c->seg_cur]), c->st, w_stripe, n_words,
                                                        c->h_fc.p.temporal_filter_radiance, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_frame_begin");
     return 0;
 }
 int vctk_transfer_masked(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
-    const size_t wps = (size_t)c->D * c->D / 32, w_lo = c->z_lo * wps, n_words = c->z_hi * wps;
-    k_transfer_masked<<<grid_for(n_words - w_lo, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_radiance),
-                                                                               reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), w_lo, n_words,
+    const size_t w_stripe = (size_t)c->D * c->D / 32 * c->st.T, n_words = w_stripe * c->st.count;
+    k_transfer_masked<<<grid_for(n_words, kThreads), kThreads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_color), reinterpret_cast<uint4*>(c->d_radiance),
+                                                                               reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), c->st, w_stripe, n_words,
                                                                                p.voxel_set_opacity, p.temporal_filter_radiance, p.temporal_decay, c->d_counters);
     VCT_LAUNCH_CHECK(c, "k_transfer");
     return 0;
@@ -880,7 +891,7 @@ int vctk_inject(vct_ctx* c) {
         }
         if (sane) {
             memcpy(lin.m, c->h_fc.ls_inverse.m, 64);
-            lin.S = c->S; lin.D = c->D; lin.z_lo = c->z_lo; lin.z_hi = c->z_hi;
+            lin.S = c->S; lin.D = c->D; lin.st = c->st;
             lin.log2_qx = 0; while ((4 << lin.log2_qx) < c->S) lin.log2_qx++;
             {   // far plane (ndc z = 1) of the light frustum in voxel coordinates: affine image of a quad, extremes at the corners
                 double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -956,10 +967,10 @@ int vctk_shadow_minmax(vct_ctx* c) {
     return 0;
 }
 int vctk_fill_holes(vct_ctx* c) {
-    dim3 grid((c->D + 31) / 32, (c->D + 7) / 8, c->z_hi - c->z_lo);
-    k_fill_holes<<<grid, kThreads, 0, c->stream>>>(c->d_radiance, c->d_scratch, c->D, c->z_lo, c->z_hi);
+    dim3 grid((c->D + 31) / 32, (c->D + 7) / 8, c->D);     // (single GPU only: upload_frame refuses voxel_fill_holes with world_size > 1)
+    k_fill_holes<<<grid, kThreads, 0, c->stream>>>(c->d_radiance, c->d_scratch, c->D, 0, c->D);
     VCT_LAUNCH_CHECK(c, "k_fill_holes");
-    const size_t off = (size_t)c->z_lo * c->D * c->D, n = (size_t)(c->z_hi - c->z_lo) * c->D * c->D;
+    const size_t off = 0, n = (size_t)c->D * c->D * c->D;
     VCT_CHECK(c, cudaMemcpyAsync(c->d_radiance + off, c->d_scratch + off, n * 4, cudaMemcpyDeviceToDevice, c->stream));
     vct_prof_mark(c, "memcpy_d2d");
     return 0;
@@ -992,9 +1003,11 @@ int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, 
     }
     int first = 0;                                  // first source level still to be filtered
     int published_upto = 0;                         // levels [0, published_upto) are already in the array
-    // fused chain: R reductions per CTA, block edge 2^R; needs whole blocks inside this rank's slab
+    // fused chain: R reductions per CTA, block edge 2^R; needs whole blocks inside this rank's stripes
+    const Stripes& st = c->st;
+    const bool multi = c->cfg.world_size > 1;
     int R = c->L - 1 < 4 ? c->L - 1 : 4;
-    while (R >= 3 && ((c->z_hi - c->z_lo) % (1 << R) || c->z_lo % (1 << R) || c->D % (1 << R))) R--;
+    while (R >= 3 && (st.T % (1 << R) || c->D % (1 << R))) R--;
     if (mode == 0 && R >= 3) {
         MipChainArgs a{};
         for (int i = 0; i < n; ++i) {
@@ -1006,38 +1019,58 @@ int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, 
             ch.pub_mask = which[i] == VCT_VOL_COLOR ? c->d_pub_mask_color : c->d_pub_mask_radiance;
             if (publish[i] && !ch.pub_mask) { c->error = "vct_mip: publish mask missing"; return 1; }
         }
-        a.n_chains = n; a.D = c->D; a.R = R; a.L = c->L; a.z0 = c->z_lo;
-        a.tail = c->cfg.world_size <= 1 && c->L - 1 > R;        // slabs keep one launch per remaining level (below)
+        a.n_chains = n; a.D = c->D; a.R = R; a.L = c->L; a.st = st;
+        a.tail = !multi && c->L - 1 > R;                        // sharded: the levels above the stripes follow the exchange (vctk_mip_tail)
         a.ticket = &c->d_counters->mip_ticket;
         a.seg_a = masked && R == 4 ? c->d_seg[c->seg_cur] : nullptr; a.seg_b = masked && R == 4 ? c->d_seg[c->seg_cur ^ 1] : nullptr;
         const int B = 1 << R;
-        a.nbz = (c->z_hi - c->z_lo) / B;
-        dim3 grid(c->D / B, c->D / B, a.nbz * n);
+        dim3 grid(c->D / B, c->D / B, st.T / B * st.count);
         k_mip_chain<<<grid, kMipThreads, 0, c->stream>>>(a);
         VCT_LAUNCH_CHECK(c, "k_mip_chain");
         first = a.tail ? c->L - 1 : R;
         published_upto = first + 1;
     }
+    const int top = multi ? vctk_mip_top_sharded_level(c) : c->L - 1;     // sharded: the last level whose z layers lie inside one stripe
     for (int i = 0; i < n; ++i) {
-        for (int l = first; l + 1 < c->L; ++l) {
+        for (int l = first; l + 1 <= top; ++l) {
             const int Ds = level_dim(c->D, l), Dd = Ds >> 1;
             if (Dd < 1) break;
-            // z-slab of the destination level owned by this rank
-            int zd_lo = c->z_lo >> (l + 1), zd_hi = c->z_hi >> (l + 1);
-            if (c->cfg.world_size <= 1) { zd_lo = 0; zd_hi = Dd; }
-            else if (zd_hi <= zd_lo) { c->error = "vct_mip: a mip level is thinner than one z-slab per rank (levels > log2(dim/world_size)+1 need a coarse-level exchange)"; return 1; }
             const uint32_t* src = base[i] + c->level_off[l]; uint32_t* dst = base[i] + c->level_off[l + 1];
-            if (mode == 0 && Dd % 4 == 0) {
-                const size_t items = (size_t)(Dd / 4) * Dd * (zd_hi - zd_lo);
-                k_mip_box2<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, zd_lo, zd_hi);
-                VCT_LAUNCH_CHECK(c, "k_mip_box2");
-            } else {
-                const size_t items = (size_t)Dd * Dd * (zd_hi - zd_lo);
-                k_mip_generic<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, mode, zd_lo, zd_hi);
-                VCT_LAUNCH_CHECK(c, "k_mip_generic");
+            for (int k = 0; k < (multi ? st.count : 1); ++k) {
+                // z layers of the destination level owned by this rank: one run per stripe
+                const int zd_lo = multi ? stripe_z(st, k) >> (l + 1) : 0, zd_hi = multi ? (stripe_z(st, k) + st.T) >> (l + 1) : Dd;
+                if (mode == 0 && Dd % 4 == 0) {
+                    const size_t items = (size_t)(Dd / 4) * Dd * (zd_hi - zd_lo);
+                    k_mip_box2<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, zd_lo, zd_hi);
+                    VCT_LAUNCH_CHECK(c, "k_mip_box2");
+                } else {
+                    const size_t items = (size_t)Dd * Dd * (zd_hi - zd_lo);
+                    k_mip_generic<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(src, dst, Ds, mode, zd_lo, zd_hi);
+                    VCT_LAUNCH_CHECK(c, "k_mip_generic");
+                }
             }
         }
-        if (publish[i] && published_upto < c->L && publish_levels(c, which[i], published_upto, c->L)) return 1;
+        const int pub_end = top + 1;
+        if (publish[i] && published_upto < pub_end && publish_levels(c, which[i], published_upto, pub_end)) return 1;
+    }
+    return 0;
+}
+// Sharded frames: the highest level a rank can filter from its own stripes (texel layers do not straddle a stripe boundary).
+int vctk_mip_top_sharded_level(const vct_ctx* c) {
+    int l = 0;
+    while (l + 1 < c->L && c->st.T % (1 << (l + 1)) == 0) ++l;
+    return l;
+}
+// Sharded frames, after the exchange has completed level `top` on every rank: the few small levels above it, redundantly on every rank
+// (16^3 texels and fewer at the default stripe of 16 layers) — cheaper than another exchange round.
+int vctk_mip_tail(vct_ctx* c, int which) {
+    uint32_t* base = which == VCT_VOL_COLOR ? c->d_color : c->d_radiance;
+    for (int l = vctk_mip_top_sharded_level(c); l + 1 < c->L; ++l) {
+        const int Ds = level_dim(c->D, l), Dd = Ds >> 1;
+        if (Dd < 1) break;
+        const size_t items = (size_t)Dd * Dd * Dd;
+        k_mip_generic<<<grid_for(items, kThreads), kThreads, 0, c->stream>>>(base + c->level_off[l], base + c->level_off[l + 1], Ds, 0, 0, Dd);
+        VCT_LAUNCH_CHECK(c, "k_mip_generic");
     }
     return 0;
 }

@@ -107,7 +107,7 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
             lo[k] = fminf(v0, fminf(v1, v2)) - 1.5f; hi[k] = fmaxf(v0, fmaxf(v1, v2)) + 1.5f;
         }
         const bool inside = lo[0] >= 0.0f && lo[1] >= 0.0f && lo[2] >= 0.0f && hi[0] <= fd && hi[1] <= fd && hi[2] <= fd;   // false for NaN
-        if (inside && (hi[2] < (float)fc.z_lo || lo[2] > (float)fc.z_hi)) return false;
+        if (inside && !owns_any_z(fc.st, max((int)lo[2], 0), min((int)hi[2], a.D - 1))) return false;
     }
     S.in.w[0] = w[0]; S.in.w[1] = w[1]; S.in.w[2] = w[2]; S.in.n[0] = n0; S.in.n[1] = n1; S.in.n[2] = n2;
     const V3 f = normalize3((n0 + n1) + n2);
@@ -173,8 +173,8 @@ __device__ __forceinline__ bool frag_test(const FrameConst& fc, const VoxHead& S
     if (z < -1.0f || z > 1.0f) return false;
     oob = !frag_voxel(fc, S, l, D, warpmap, occupancy, ix, iy, iz);
     if (occupancy) return true;                                           // the 32^3 occupancy grid is not sharded: every rank builds all of it
-    if (oob) return fc.z_lo == 0;                                         // counted once, by the rank owning z = 0
-    return iz >= fc.z_lo && iz < fc.z_hi;
+    if (oob) return fc.st.rank == 0;                                      // counted once, by the rank owning z = 0
+    return owns_z(fc.st, iz);
 }
 
 struct Shaded { V3 color, nenc; };
@@ -655,7 +655,10 @@ __global__ void __launch_bounds__(kThreads) k_voxel_huge_compact(const Frag* __r
             const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
             if (pos < lq.item_cap) { HugeItem it; it.k = order_key(frags[i]); it.slot = i; it.h = (uint32_t)h; lq.items[pos] = it; }
             else vct_flag_overflow(counters);
-            atomicAdd(&lq.aux->hist[h][min((unsigned)(frags[i].tri >> lq.tri_shift), (unsigned)kHugeBins - 1u)], 1u);      // coarse histogram over the triangle index
+            // coarse histogram over the triangle index; neighbouring records mostly belong to the same triangles: one atomic per bin per warp
+            const unsigned bin = min((unsigned)(frags[i].tri >> lq.tri_shift), (unsigned)kHugeBins - 1u);
+            const unsigned grp = __match_any_sync(m, (unsigned)h << 16 | bin);
+            if (lane == __ffs(grp) - 1) atomicAdd(&lq.aux->hist[h][bin], (unsigned)__popc(grp));
         }
     }
 }
@@ -778,7 +781,7 @@ __device__ __forceinline__ void tess_eval(const VoxArgs& a, const FrameConst& fc
     const float Df = (float)a.D;
     int ix, iy, iz;
     if (!to_voxel_index(mk3(Df * vp.x, Df * vp.y, Df * vp.z), a.D, ix, iy, iz)) return;
-    if (iz < fc.z_lo || iz >= fc.z_hi) return;                                   // another rank's slab
+    if (!owns_z(fc.st, iz)) return;                                              // another rank's layers
     const uint32_t o = (uint32_t)(((size_t)iz * a.D + iy) * a.D + ix);
     a.seg[o >> 3] = 1;
     const V3 N = normalize3(nn);
@@ -938,17 +941,17 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset, bool 
     if (!long_path) { if (transfer_done) *transfer_done = fuse_transfer; return 0; }
     if (fuse_transfer) k_voxel_resolve_medium<true><<<VCT_SM_COUNT * 4, kMedWarps * 32, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
     else k_voxel_resolve_medium<false><<<VCT_SM_COUNT * 4, kMedWarps * 32, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
-    VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+    VCT_LAUNCH_CHECK(c, "k_voxel_resolve_medium");
     {
         k_voxel_huge_compact<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(a.frags, c->d_counters, a.frag_cap, lq);
-        VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+        VCT_LAUNCH_CHECK(c, "k_voxel_huge_compact");
         k_voxel_huge_pick<<<kHugeMax, 256, 0, c->stream>>>(c->d_counters, lq);
-        VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+        VCT_LAUNCH_CHECK(c, "k_voxel_huge_pick");
         k_voxel_huge_gather<<<VCT_SM_COUNT * 8, kThreads, 0, c->stream>>>(c->d_counters, lq);
-        VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+        VCT_LAUNCH_CHECK(c, "k_voxel_huge_gather");
         if (fuse_transfer) k_voxel_huge_select<true><<<kHugeMax, kSelThreads, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
         else k_voxel_huge_select<false><<<kHugeMax, kSelThreads, 0, c->stream>>>(a.frags, c->d_counters, c->d_color, c->d_normal, c->d_radiance, op, lq);
-        VCT_LAUNCH_CHECK(c, "k_voxel_resolve_long");
+        VCT_LAUNCH_CHECK(c, "k_voxel_huge_select");
     }
     if (transfer_done) *transfer_done = fuse_transfer;
     return 0;

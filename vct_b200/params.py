@@ -21,7 +21,7 @@ VOL_COLOR, VOL_NORMAL, VOL_RADIANCE, VOL_OCCUPANCY, VOL_WARPMAP, VOL_WARP_WEIGHT
 class Config(C.Structure):
     _fields_ = [("dim", C.c_int), ("levels", C.c_int), ("shadow_size", C.c_int), ("width", C.c_int),
                 ("height", C.c_int), ("device", C.c_int), ("rank", C.c_int), ("world_size", C.c_int),
-                ("max_fragments", C.c_int), ("n_devices", C.c_int), ("devices", C.POINTER(C.c_int))]
+                ("max_fragments", C.c_int), ("n_devices", C.c_int), ("devices", C.POINTER(C.c_int)), ("slab_stripe", C.c_int)]
 
 
 EXCHANGE_HANDLE_BYTES = 384

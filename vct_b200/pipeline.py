@@ -12,12 +12,12 @@ from .lib import VctError, load
 
 class Pipeline:
     def __init__(self, scene, dim=256, levels=6, shadow_size=4096, width=1280, height=720, device=0, rank=0,
-                 world_size=1, max_fragments=0, devices=None):
+                 world_size=1, max_fragments=0, devices=None, slab_stripe=0):
         """devices: a list of CUDA ordinals -> ONE handle driving all of them from this process (vct_config.n_devices)."""
         self.lib = load()
         self._devices = (C.c_int * len(devices))(*devices) if devices else None
         self.cfg = P.Config(dim, levels, shadow_size, width, height, device, rank, world_size, max_fragments,
-                            len(devices) if devices else 0, self._devices)
+                            len(devices) if devices else 0, self._devices, slab_stripe)
         h = C.c_void_p()
         if self.lib.vct_create(C.byref(self.cfg), C.byref(h)):
             raise VctError(self.lib.vct_last_error(None).decode())

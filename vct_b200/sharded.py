@@ -4,13 +4,14 @@ whole sharded frame itself.
 world_size == 1   the frame is `vct_gi_passes` (or `vct_frame`) on the library's own stream.
 world_size  > 1   once, at start-up, the ranks swap their cudaIpc handle blobs (`vct_exchange_export` / `_import`; the only use of
                   torch.distributed here, `all_gather_object`).  After that `vct_gi_passes` / `vct_frame` does everything on the
-                  device: voxel passes on the own z-slab [rank*D/N, (rank+1)*D/N), the slab exchange over NVLink peer memory
+                  device: voxel passes on the own z layers (stripes of `slab_stripe` layers dealt round-robin to the ranks; default:
+                  one contiguous slab [rank*D/N, (rank+1)*D/N)), the slab exchange over NVLink peer memory
                   with device-side flags (csrc/exchange.cu), the cone trace of the own 64x64 screen tiles, pixels stored into
                   rank 0's image.  No collective, no host synchronisation, and the step is capturable in a CUDA graph.
                   VCT_SPARSE_EXCHANGE=0 (or a backend other than NCCL) selects the round-1 protocol instead: per-level
                   all-gather by the caller, `vct_exchange`, full-image trace on every rank.
 
-The partition maths (`slab_range`, `level_chunks`, `tile_owner`, `image_bands`) is pure Python, mirrors the library's, and is
+The partition maths (`slab_range`, `stripes`, `top_sharded_level`, `level_chunks`, `tile_owner`, `image_bands`) is pure Python, mirrors the library's, and is
 unit-tested on CPU with gloo.
 """
 import ctypes as C
@@ -39,6 +40,27 @@ def level_chunks(dim, levels, world):
             raise ValueError(f"level {l} ({d}^3) is thinner than one slab per rank: use levels <= log2(dim/world)+1")
         out.append(d * d * d // world)
     return out
+
+
+def stripe_owner(z, stripe, world):
+    """Rank that owns voxel layer z when the layers are dealt out in stripes of `stripe` layers (common.cuh `owns_z`)."""
+    return (z // stripe) % world
+
+
+def stripes(dim, stripe, world, rank):
+    """[(z_lo, z_hi)] of the stripes `rank` owns; stripe = dim // world is the contiguous slab of `slab_range`."""
+    if stripe < 1 or dim % (stripe * world):
+        raise ValueError("stripe * world_size must divide dim")
+    return [((k * world + rank) * stripe, (k * world + rank + 1) * stripe) for k in range(dim // (stripe * world))]
+
+
+def top_sharded_level(stripe, levels):
+    """Last mip level a rank can filter from its own stripes (texel layers do not straddle a stripe border); the levels above it
+    are filtered on every rank from the exchanged level (volume_passes.cu vctk_mip_top_sharded_level / vctk_mip_tail)."""
+    l = 0
+    while l + 1 < levels and stripe % (1 << (l + 1)) == 0:
+        l += 1
+    return l
 
 
 def image_bands(height, world):
@@ -106,6 +128,8 @@ class ShardedFrame:
                 dist.barrier()                                   # every rank has mapped every peer before the first frame stores into them
                 self.peer_exchange = True
             else:                                                # round-1 protocol: the caller moves the levels
+                if g.cfg.slab_stripe:
+                    raise ValueError("the caller-side all-gather protocol needs contiguous slabs (slab_stripe = 0)")
                 which = P.VOL_RADIANCE if params.draw_radiance else P.VOL_COLOR
                 self.levels = [device_tensor(g.device_ptr(which, l), g.level_bytes(which, l)) for l in range(g.L)]
                 self.chunks = level_chunks(g.D, g.L, world)
@@ -116,7 +140,8 @@ class ShardedFrame:
         if self.world == 1:
             return "1 GPU"
         if self.peer_exchange:
-            return (f"{self.world} GPUs, one process each: z-slab sharding of clear/voxelise/transfer/inject/mip; slab exchange inside the library over NVLink peer memory "
+            T = self.g.cfg.slab_stripe or self.g.D // self.world
+            return (f"{self.world} GPUs, one process each: z sharding of clear/voxelise/transfer/inject/mip in stripes of {T} layers; slab exchange inside the library over NVLink peer memory "
                     "(level 0 as flagged x-row segments into staging regions, levels >= 1 stored into the peers' pyramids, device-side flags, no collective); "
                     "cone trace sharded by interleaved 64x64 screen tiles, pixels stored into rank 0's image")
         return f"{self.world} GPUs: z-slab sharding, per-level NCCL all-gather of the traced pyramid by the caller, full-image cone trace on every rank"
