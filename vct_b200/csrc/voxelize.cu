@@ -595,6 +595,19 @@ __device__ __forceinline__ void replay_last(const Frag* __restrict__ frags, cons
         cw = rgba8_avg_insert(cw, f.cr, f.cg, f.cb); nw = rgba8_avg_insert(nw, f.nr, f.ng, f.nb);
     }
 }
+// the same in two steps for a warp / a CTA: the r records are fetched by all threads into shared memory (6 floats each), then one thread
+// replays them without a global load on its dependent chain
+__device__ __forceinline__ void stage_last(const Frag* __restrict__ frags, const uint32_t* __restrict__ slots, int n2, int r, float* __restrict__ stage, int tid, int nthreads) {
+    for (int q = tid; q < r; q += nthreads) {
+        const Frag& f = frags[slots[n2 - r + q]];
+        float* o = stage + 6 * q;
+        o[0] = f.cr; o[1] = f.cg; o[2] = f.cb; o[3] = f.nr; o[4] = f.ng; o[5] = f.nb;
+    }
+}
+__device__ __forceinline__ void replay_staged(const float* __restrict__ stage, int r, uint32_t& cw, uint32_t& nw) {
+    cw = 0u; nw = 0u;
+    for (int q = 0; q < r; ++q) { const float* o = stage + 6 * q; cw = rgba8_avg_insert(cw, o[0], o[1], o[2]); nw = rgba8_avg_insert(nw, o[3], o[4], o[5]); }
+}
 // one warp per queued voxel with kSortMax < N <= kMedMax fragments; longer ones are entered into the huge table
 constexpr int kMedWarps = 2;
 template <bool TRANSFER>
@@ -620,9 +633,14 @@ __global__ void __launch_bounds__(kMedWarps * 32) k_voxel_resolve_medium(const F
             if (k < cnt) s_key[w][k] = order_key(frags[s_slot[w][k]]); else { s_key[w][k] = 0ull; s_slot[w][k] = 0u; }
         }
         bitonic_sort(s_key[w], s_slot[w], n2, lane, 32, false);
+        const int r = ((cnt - 1) & 255) + 1;
+        float* stage = reinterpret_cast<float*>(s_key[w]);                   // the keys are done with: 256 x 24 bytes fit in their 8 KB
+        __syncwarp();
+        stage_last(frags, s_slot[w], n2, r, stage, lane, 32);
+        __syncwarp();
         if (lane == 0) {
             uint32_t cw, nw;
-            replay_last(frags, s_slot[w], n2, ((cnt - 1) & 255) + 1, cw, nw);
+            replay_staged(stage, r, cw, nw);
             finish_voxel<TRANSFER>(le.key, cw, nw, color, normal, radiance, opacity, uniq, maxfrag);
         }
         __syncwarp();
@@ -708,6 +726,8 @@ __global__ void __launch_bounds__(kSelThreads) k_voxel_huge_select(const Frag* _
                                                                     uint32_t* __restrict__ normal, uint32_t* __restrict__ radiance, float opacity, LongArgs lq) {
     __shared__ unsigned s_hist[kSelBins];
     __shared__ unsigned long long s_key[256]; __shared__ uint32_t s_slot[256];
+    __shared__ float s_stage[256 * 6];
+    __shared__ unsigned s_warp[kSelThreads / 32];
     __shared__ unsigned s_pick, s_need, s_n;
     const unsigned nh = min(counters->huge_count, (unsigned)kHugeMax);
     const unsigned h = blockIdx.x;
@@ -729,10 +749,27 @@ __global__ void __launch_bounds__(kSelThreads) k_voxel_huge_select(const Frag* _
             if (it.h == h && (it.k & hi_mask) == prefix) atomicAdd(&s_hist[(unsigned)(it.k >> shift) & (kSelBins - 1)], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {                               // largest digit first: find the digit that holds the `need`-th largest
-            unsigned acc = 0; int b = kSelBins - 1;
-            for (; b > 0; --b) { if (acc + s_hist[b] >= need) break; acc += s_hist[b]; }
-            s_pick = (unsigned)b; s_need = need - acc;
+        {   // largest digit first: the digit that holds the `need`-th largest.  Thread t owns the 4 bins 4095-4t .. 4092-4t; a CTA-wide
+            // inclusive scan of the threads' sums (from the top digit down) finds the one thread whose bins straddle `need`
+            static_assert(kSelBins == 4 * kSelThreads, "4 bins per thread");
+            const int top = kSelBins - 1 - 4 * (int)threadIdx.x;
+            const unsigned h0 = s_hist[top], h1 = s_hist[top - 1], h2 = s_hist[top - 2], h3 = s_hist[top - 3];
+            const unsigned mine = h0 + h1 + h2 + h3;
+            unsigned inc = mine;
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) s_warp[w] = inc;
+            if (threadIdx.x == 0) { s_pick = 0u; s_need = 1u; }                  // (unreachable default: the voxel holds at least `need` items)
+            __syncthreads();
+            unsigned before = 0;
+            for (int k = 0; k < w; ++k) before += s_warp[k];
+            const unsigned lo = before + inc - mine;                              // items in the digits above this thread's bins
+            if (lo < need && need <= lo + mine) {
+                unsigned acc = lo; int b = top;
+                if (acc + h0 >= need) b = top; else { acc += h0; if (acc + h1 >= need) b = top - 1; else { acc += h1; if (acc + h2 >= need) b = top - 2; else { acc += h2; b = top - 3; } } }
+                s_pick = (unsigned)b; s_need = need - acc;
+            }
         }
         __syncthreads();
         prefix |= (unsigned long long)s_pick << shift; need = s_need;
@@ -748,9 +785,12 @@ __global__ void __launch_bounds__(kSelThreads) k_voxel_huge_select(const Frag* _
     }
     __syncthreads();
     bitonic_sort(s_key, s_slot, 256, threadIdx.x, kSelThreads, true);
+    const int rr = min(r, (int)min(s_n, 256u));
+    stage_last(frags, s_slot, 256, rr, s_stage, threadIdx.x, kSelThreads);
+    __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t cw, nw; unsigned uniq = 0, maxfrag = 0;
-        replay_last(frags, s_slot, 256, min(r, (int)min(s_n, 256u)), cw, nw);
+        replay_staged(s_stage, rr, cw, nw);
         finish_voxel<TRANSFER>(le.key, cw, nw, color, normal, radiance, opacity, uniq, maxfrag);
         if (TRANSFER) { if (uniq) atomicAdd(&counters->unique_voxels, uniq); if (maxfrag) atomicMax(&counters->max_fragments_per_voxel, maxfrag); }
     }
