@@ -387,7 +387,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     const int N = VCT_WARP_DIM;
     auto alloc = [&](void** p, size_t bytes) { cudaError_t r = cudaMalloc(p, bytes); if (r != cudaSuccess) { c->error = cudaGetErrorString(r); return 1; } cudaMemsetAsync(*p, 0, bytes, c->stream); return 0; };
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
-    if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * (8 + 16)) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
+    if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * (8 + 32)) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
         alloc((void**)&c->d_shadow_base, 2 * (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, ((size_t)(c->S / 4 + 1) * (c->S / 4 + 1) + (size_t)(c->S / 64 + 1) * (c->S / 16 + 1)) * 8) || alloc((void**)&c->d_inject_list, ((size_t)(c->S / 64 + 1) * (c->S / 16 + 1) + 1) * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, 2 * vctk_image_rows(c) * (size_t)c->W * 4) ||
         alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc(&c->d_long_queue, (c->long_cap + 8) * 16) || alloc(&c->d_huge_items, c->frag_cap * 16) || alloc(&c->d_huge_aux, vctk_huge_aux_bytes()) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
@@ -395,6 +395,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
         return bail("cudaMalloc");
     // overflow of a fixed-capacity buffer is also flagged in mapped host memory, so that the next entry point sees it without a sync
     if (cudaHostAlloc((void**)&c->h_overflow, 4 * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) { c->error = "cudaHostAlloc"; return bail("overflow flag"); }
+    cudaMemsetAsync(c->d_vis, 0xFF, (size_t)c->W * c->H * 8, c->stream);   // "no geometry" everywhere: a cone trace before the first visibility pass shades background
     for (int i = 0; i < 4; ++i) c->h_overflow[i] = 0u;       // [0] overflow, [1] a long per-voxel list was met (voxelize.cu), [2] [3] inject block count + generation
     { unsigned* dp = nullptr; if (cudaHostGetDevicePointer((void**)&dp, c->h_overflow, 0) != cudaSuccess || cudaMemcpyAsync(&c->d_counters->overflow_host, &dp, sizeof dp, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { c->error = "mapped overflow flag"; return bail("overflow flag"); } }
     for (int i = 0; i < VCT_MAX_MATERIALS; ++i) { DevMaterial& m = c->h_mat[i]; m.diffuse_tex = m.specular_tex = m.normal_tex = m.roughness_tex = m.metallic_tex = m.alpha_tex = -1; m.shininess = 32.0f; }

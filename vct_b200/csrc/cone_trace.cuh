@@ -134,25 +134,30 @@ __device__ __forceinline__ V3 voxel_warp(V3 p, V3 c) {
 // interpolation weights move the warped sample position by up to 1/256 of a warp cell, which is enough to
 // flip the NEAREST (lambda <= 0.5) fetches of the specular cone onto a neighbouring voxel (measured: final
 // image PSNR 41 dB with the hardware filter vs the fp32 definition of the oracle).
-__device__ __forceinline__ V3 warp_texel(const float4* __restrict__ wm, int x, int y, int z) {
+// One 256-bit load (LDG.E.256, sm_100) fetches texel (x, y, z) and its +x neighbour: the table holds them side by side (k_warpmap_floats), q / 65535
+// per channel divided once there.  x, y, z already clamped.
+__device__ __forceinline__ void warp_texel_pair(const float4* __restrict__ wm, int x, int y, int z, V3& a, V3& b) {
     const int n = VCT_WARP_DIM;
-    x = min(max(x, 0), n - 1); y = min(max(y, 0), n - 1); z = min(max(z, 0), n - 1);
-    const float4 q = __ldg(wm + (z * n + y) * n + x);                        // q / 65535 per channel, divided once by k_warpmap_floats
-    return mk3(q.x, q.y, q.z);
+    float ax, ay, az, aw, bx, by, bz, bw;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(ax), "=f"(ay), "=f"(az), "=f"(aw), "=f"(bx), "=f"(by), "=f"(bz), "=f"(bw) : "l"(wm + 2 * ((z * n + y) * n + x)));
+    a = mk3(ax, ay, az); b = mk3(bx, by, bz);
 }
 __device__ __forceinline__ V3 lerp3x(V3 a, V3 b, float t) {
     const float s = 1.0f - t;
     return mk3(__fadd_rn(__fmul_rn(a.x, s), __fmul_rn(b.x, t)), __fadd_rn(__fmul_rn(a.y, s), __fmul_rn(b.y, t)), __fadd_rn(__fmul_rn(a.z, s), __fmul_rn(b.z, t)));
 }
-__device__ __forceinline__ V3 warp_sample(const float4* __restrict__ wm, V3 tc) {
+__device__ __noinline__ V3 warp_sample(const float4* __restrict__ wm, V3 tc) {
     const float n = (float)VCT_WARP_DIM;
     const float x = __fmul_rn(tc.x, n) - 0.5f, y = __fmul_rn(tc.y, n) - 0.5f, z = __fmul_rn(tc.z, n) - 0.5f;
     const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
     const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0; const float fx = x - fx0, fy = y - fy0, fz = z - fz0;
-    const V3 c00 = lerp3x(warp_texel(wm, x0, y0, z0), warp_texel(wm, x0 + 1, y0, z0), fx);
-    const V3 c10 = lerp3x(warp_texel(wm, x0, y0 + 1, z0), warp_texel(wm, x0 + 1, y0 + 1, z0), fx);
-    const V3 c01 = lerp3x(warp_texel(wm, x0, y0, z0 + 1), warp_texel(wm, x0 + 1, y0, z0 + 1), fx);
-    const V3 c11 = lerp3x(warp_texel(wm, x0, y0 + 1, z0 + 1), warp_texel(wm, x0 + 1, y0 + 1, z0 + 1), fx);
+    const int n1 = VCT_WARP_DIM - 1;
+    const int xc = min(max(x0, 0), n1), ya = min(max(y0, 0), n1), yb = min(max(y0 + 1, 0), n1), za = min(max(z0, 0), n1), zb = min(max(z0 + 1, 0), n1);
+    V3 a00, b00, a10, b10, a01, b01, a11, b11;
+    warp_texel_pair(wm, xc, ya, za, a00, b00); warp_texel_pair(wm, xc, yb, za, a10, b10);
+    warp_texel_pair(wm, xc, ya, zb, a01, b01); warp_texel_pair(wm, xc, yb, zb, a11, b11);
+    if (x0 < 0) { b00 = a00; b10 = a10; b01 = a01; b11 = a11; }                // x0 = -1: both corners clamp to texel 0
+    const V3 c00 = lerp3x(a00, b00, fx), c10 = lerp3x(a10, b10, fx), c01 = lerp3x(a01, b01, fx), c11 = lerp3x(a11, b11, fx);
     return lerp3x(lerp3x(c00, c10, fy), lerp3x(c01, c11, fy), fz);
 }
 

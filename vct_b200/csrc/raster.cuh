@@ -326,8 +326,9 @@ __device__ __forceinline__ float calc_shadow_factor(const float* __restrict__ sm
 __device__ __forceinline__ V3 warp_texel(const uint16_t* __restrict__ wm, int x, int y, int z) {
     const int n = VCT_WARP_DIM;
     x = min(max(x, 0), n - 1); y = min(max(y, 0), n - 1); z = min(max(z, 0), n - 1);
-    // the float copy behind the unorm16 texels (k_warpmap_floats): q / 65535 per channel, the IEEE division done once per texel
-    const float4 q = __ldg(reinterpret_cast<const float4*>(wm + 4 * (size_t)n * n * n) + ((size_t)z * n + y) * n + x);
+    // the float copy behind the unorm16 texels (k_warpmap_floats): q / 65535 per channel, the IEEE division done once per texel; one entry =
+    // the texel and its +x neighbour (32 bytes, for the cone tracer's 256-bit loads) — this reader takes the first half
+    const float4 q = __ldg(reinterpret_cast<const float4*>(wm + 4 * (size_t)n * n * n) + 2 * (((size_t)z * n + y) * n + x));
     return mk3(q.x, q.y, q.z);
 }
 __device__ __forceinline__ V3 lerp3(V3 a, V3 b, float t) { const float s = 1.0f - t; return mk3(a.x * s + b.x * t, a.y * s + b.y * t, a.z * s + b.z * t); }

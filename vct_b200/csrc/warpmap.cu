@@ -29,7 +29,7 @@ __device__ __forceinline__ int tot_z(const OccBits& b, int x, int y) { return __
 // grid = 32 CTAs, one z-slice of the warp map each; thread = one texel (warp = y, lane = x).  Every CTA builds the bit tables from the
 // whole occupancy grid (128 KiB from L2, 32 independent loads per thread), so nothing is exchanged between CTAs.
 __global__ void __launch_bounds__(1024) k_warpmap(const uint32_t* __restrict__ occ, const FrameConst* __restrict__ fcp, ushort4* __restrict__ warpmap,
-                                                  ushort4* __restrict__ wlo, ushort4* __restrict__ whi, float4* __restrict__ wf) {
+                                                  ushort4* __restrict__ wlo, ushort4* __restrict__ whi) {
     const vct_frame_params& p = fcp->p;
     __shared__ float wl[N + 1], wh[N + 1];
     __shared__ OccBits B;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(1024) k_warpmap(const uint32_t* __restrict__ o
     const int x = lane, y = w, z = blockIdx.x, i = (z * N + y) * N + x;
     // the quad is drawn at 0.8 scale: texels outside it keep the cleared value 0 in all three targets
     if (!quad_covered(x) || !quad_covered(y)) {
-        warpmap[i] = make_ushort4(0, 0, 0, 0); wlo[i] = make_ushort4(0, 0, 0, 0); whi[i] = make_ushort4(0, 0, 0, 0); wf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        warpmap[i] = make_ushort4(0, 0, 0, 0); wlo[i] = make_ushort4(0, 0, 0, 0); whi[i] = make_ushort4(0, 0, 0, 0);
         return;
     }
     const float tc[3] = {quad_tc(x), quad_tc(y), ((float)z + 0.5f) / (float)N};
@@ -120,16 +120,18 @@ __global__ void __launch_bounds__(1024) k_warpmap(const uint32_t* __restrict__ o
 #pragma unroll
     for (int k = 0; k < 4; ++k) { float v = out[k]; if (!(v > 0.0f)) v = 0.0f; if (v > 1.0f) v = 1.0f; q[k] = (unsigned short)__float2uint_rn(v * 65535.0f); }
     warpmap[i] = make_ushort4(q[0], q[1], q[2], q[3]);
-    // float copy for the cone tracer: the unorm16 -> float conversion (q / 65535, one IEEE division per channel) once per texel here instead of
-    // 24 times per cone step there (config 4 at 4K: 68 ms -> 9 ms); same values, bit for bit
-    wf[i] = make_float4((float)q[0] / 65535.0f, (float)q[1] / 65535.0f, (float)q[2] / 65535.0f, (float)q[3] / 65535.0f);
 }
-// the float copy alone, for a warp map written by the host (vct_write_volume)
+// Float copy of the warp map for the cone tracer and the voxeliser: the unorm16 -> float conversion (q / 65535, one IEEE division per channel) once
+// per texel here instead of 24 times per cone step there (config 4 at 4K: 68 ms -> 9 ms); same values, bit for bit.  Also run after the host
+// writes a warp map (vct_write_volume).
 __global__ void __launch_bounds__(256) k_warpmap_floats(const ushort4* __restrict__ warpmap, float4* __restrict__ wf) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM) return;
     const ushort4 q = warpmap[i];
-    wf[i] = make_float4((float)q.x / 65535.0f, (float)q.y / 65535.0f, (float)q.z / 65535.0f, (float)q.w / 65535.0f);
+    // entry i = texel i and its +x neighbour (CLAMP_TO_EDGE): the tracer fetches both x corners of a trilinear cell with one 256-bit load
+    const ushort4 r = warpmap[(i % VCT_WARP_DIM) == VCT_WARP_DIM - 1 ? i : i + 1];
+    wf[2 * i] = make_float4((float)q.x / 65535.0f, (float)q.y / 65535.0f, (float)q.z / 65535.0f, (float)q.w / 65535.0f);
+    wf[2 * i + 1] = make_float4((float)r.x / 65535.0f, (float)r.y / 65535.0f, (float)r.z / 65535.0f, (float)r.w / 65535.0f);
 }
 }  // namespace
 
@@ -142,7 +144,7 @@ int vctk_warpmap_floats(vct_ctx* c) {
 
 int vctk_warpmap(vct_ctx* c) {
     k_warpmap<<<N, 1024, 0, c->stream>>>(c->d_occ, c->d_fc, reinterpret_cast<ushort4*>(c->d_warpmap), reinterpret_cast<ushort4*>(c->d_wlo),
-                                         reinterpret_cast<ushort4*>(c->d_whi), reinterpret_cast<float4*>(c->d_warpmap + 4 * (size_t)N * N * N));
+                                         reinterpret_cast<ushort4*>(c->d_whi));
     VCT_LAUNCH_CHECK(c, "k_warpmap");
-    return 0;
+    return vctk_warpmap_floats(c);
 }
