@@ -274,7 +274,8 @@ def run_b200(args):
     sc, p, D, W, H, L, S = w.scene, w.params, w.D, w.W, w.H, w.L, w.S
     chains = w.chains
     max_frag = max(8 << 20, 3 * sc.n_tris) if w.config == 5 else 0
-    g = Pipeline(sc, D, L, S, W, H, device=local, rank=rank, world_size=world, max_fragments=max_frag)
+    g = Pipeline(sc, D, L, S, W, H, device=local, rank=rank, world_size=world, max_fragments=max_frag,
+                 slab_stripe=-1 if os.environ.get("VCT_SPARSE_EXCHANGE", "1") == "0" else 0)   # the caller-side all-gather protocol needs contiguous slabs
     from vct_b200.sharded import ShardedFrame
     fr = ShardedFrame(g, p, world, rank, workload=w)              # world == 1: plain vct_gi_passes / vct_frame on the library stream
     stream = fr.stream

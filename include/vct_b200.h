@@ -47,9 +47,11 @@ typedef struct {
      * that fans every call out; rank / world_size / device above are then ignored.  0 or 1: one context on `device`. */
     int n_devices;
     const int* devices;
-    /* How z is dealt to the ranks: rank of voxel layer z = (z / slab_stripe) mod world_size.  0 = dim / world_size (one contiguous slab per
-     * rank); 16 (a multiple of 16 that divides dim / world_size) interleaves stripes, which balances scenes that fill only part of the
-     * volume (Sponza occupies the middle half of z: with contiguous slabs half of 8 ranks have nothing to voxelise). */
+    /* How z is dealt to the ranks: rank of voxel layer z = (z / slab_stripe) mod world_size.  A power of two >= 16 that divides
+     * dim / world_size interleaves stripes, which balances scenes that fill only part of the volume (Sponza occupies the middle half of z: with
+     * contiguous slabs half of 8 ranks have nothing to voxelise).  -1 = one contiguous slab of dim / world_size layers per rank.  0 = the
+     * library chooses: environment variable VCT_SLAB_STRIPE if set, else 16 from 4 ranks on, else contiguous.  A stripe that does not fit the
+     * volume falls back to contiguous slabs; vct_slab_stripe() reports what is in effect. */
     int slab_stripe;
 } vct_config;
 
@@ -204,6 +206,7 @@ int  vct_exchange_import(vct_ctx*, int rank, const void* handle);
 int  vct_exchange_local(vct_ctx*, vct_peer* out);          /* this rank's own buffers (to attach on peers of the same process) */
 int  vct_exchange_attach(vct_ctx*, int rank, const vct_peer*);
 int  vct_frame_was_sparse(vct_ctx*);                       /* 1: the last vct_frame / vct_gi_passes visited flagged segments only */
+int  vct_slab_stripe(vct_ctx*);                            /* layers per stripe in effect (dim for one GPU) */
 int  vct_mask_parity(vct_ctx*);                            /* which of the two segment masks the NEXT frame writes (0/1): a CUDA graph that
                                                               captured frames must be replayed at the parity it was captured at */
 int  vct_gbuffer(vct_ctx*, const vct_frame_params*);       /* :936-965  depth prepass -> visibility buffer */

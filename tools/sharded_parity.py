@@ -39,7 +39,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sc, p, D, L, SS, W, H, wl = workload(name)
     frames = 4 if wl else 3
-    g = Pipeline(sc, D, L, SS, W, H, device=local, rank=rank, world_size=world)
+    g = Pipeline(sc, D, L, SS, W, H, device=local, rank=rank, world_size=world, slab_stripe=-1 if os.environ.get("VCT_SPARSE_EXCHANGE", "1") == "0" else 0)
     fr = ShardedFrame(g, p, world, rank, workload=wl)
     fr.producers()
     for _ in range(frames):                  # later frames: steady state (sparse exchange, publish masks, temporal history) also matches

@@ -93,7 +93,10 @@ int make_volumes(vct_ctx* c) {
     const int ws = c->cfg.world_size > 1 ? c->cfg.world_size : 1, r = c->cfg.world_size > 1 ? c->cfg.rank : 0;
     int stripe = c->cfg.slab_stripe;
     if (stripe == 0 && ws > 1) { const char* e = getenv("VCT_SLAB_STRIPE"); if (e && *e) stripe = atoi(e); }        // tuning override for hosts that leave the field 0
-    if (stripe > 0 && ws > 1 && (c->D / ws) % stripe) stripe = 0;                                                   // does not fit this volume: contiguous slabs
+    // default: stripes of 16 layers from 4 ranks on (measured on 8 B200s, Sponza 256^3: 0.336 ms against 0.361 ms with contiguous slabs — the scene
+    // fills the middle half of z; at 2 ranks the contiguous halves are balanced already and the stripes' shared triangles cost 3 %)
+    if (stripe == 0 && ws >= 4) stripe = 16;
+    if (stripe < 0 || (stripe > 0 && ws > 1 && (c->D / ws) % stripe)) stripe = 0;                                    // -1, or does not fit this volume: contiguous slabs
     const int T = stripe > 0 && ws > 1 ? stripe : c->D / ws;
     if (T < 1 || c->D % ws) { c->error = "dim must be divisible by world_size"; return 1; }
     if (ws > 1 && stripe > 0 && (T % 16 || (T & (T - 1)))) { c->error = "slab_stripe must be a power of two >= 16"; return 1; }
@@ -688,6 +691,7 @@ int vct_exchange_attach(vct_ctx* c, int rank, const vct_peer* peer) {
 }
 int vct_frame_was_sparse(vct_ctx* c) { return c && c->last_frame_sparse ? 1 : 0; }
 int vct_mask_parity(vct_ctx* c) { return c ? c->seg_cur : 0; }
+int vct_slab_stripe(vct_ctx* c) { return c ? c->st.T : 0; }
 
 // tail of a sharded frame with attached peers: exchange, (visibility), cone trace of the own tiles, image hand-over to rank 0
 static int sharded_tail(vct_ctx* c, Graph& g, bool with_visibility) {

@@ -19,7 +19,7 @@ SYMBOLS = [
     "vct_get_cone_steps", "vct_sync", "vct_device_ptr", "vct_level_bytes", "vct_stream", "vct_launch_count",
     "vct_set_stream", "vct_set_profiling", "vct_get_kernel_times",
     "vct_exchange_setup", "vct_exchange_export", "vct_exchange_import", "vct_exchange_local", "vct_exchange_attach",
-    "vct_frame_was_sparse", "vct_mask_parity",
+    "vct_frame_was_sparse", "vct_mask_parity", "vct_slab_stripe",
     "vct_read_image_async", "vct_read_image_wait",
     "vct_ingest_obj", "vct_ingest_image", "vct_ingest_free", "vct_ingest_log", "vct_ingest_get_mesh",
     "vct_ingest_get_material", "vct_ingest_get_texture", "vct_ingest_upload",
@@ -68,7 +68,7 @@ def load():
         "vct_ingest_get_texture": (ci, [vp, ci, C.POINTER(P.IngestTexture)]),
         "vct_ingest_upload": (ci, [vp, vp, ci, ci, ci, C.POINTER(cf)]),
         "vct_exchange_local": (ci, [vp, C.POINTER(P.Peer)]), "vct_exchange_attach": (ci, [vp, ci, C.POINTER(P.Peer)]),
-        "vct_frame_was_sparse": (ci, [vp]), "vct_mask_parity": (ci, [vp]),
+        "vct_frame_was_sparse": (ci, [vp]), "vct_mask_parity": (ci, [vp]), "vct_slab_stripe": (ci, [vp]),
     }
     for name in ("vct_shadowmap", "vct_occupancy", "vct_warpmap", "vct_voxelize", "vct_transfer", "vct_inject", "vct_fill_holes",
                  "vct_gbuffer", "vct_cone_trace", "vct_frame", "vct_gi_passes"):

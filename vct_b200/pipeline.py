@@ -77,6 +77,8 @@ class Pipeline:
     def frame_was_sparse(self): return bool(self.lib.vct_frame_was_sparse(self.h))
     def mask_parity(self): return int(self.lib.vct_mask_parity(self.h))
 
+    def slab_stripe(self): return int(self.lib.vct_slab_stripe(self.h))
+
     def exchange_setup(self):
         """Allocate the slab-exchange staging buffer and return this rank's cudaIpc handle blob (one process per GPU)."""
         self._ck(self.lib.vct_exchange_setup(self.h))

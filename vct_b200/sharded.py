@@ -128,8 +128,8 @@ class ShardedFrame:
                 dist.barrier()                                   # every rank has mapped every peer before the first frame stores into them
                 self.peer_exchange = True
             else:                                                # round-1 protocol: the caller moves the levels
-                if g.cfg.slab_stripe:
-                    raise ValueError("the caller-side all-gather protocol needs contiguous slabs (slab_stripe = 0)")
+                if g.slab_stripe() != g.D // world:
+                    raise ValueError("the caller-side all-gather protocol needs contiguous slabs (Pipeline(..., slab_stripe=-1))")
                 which = P.VOL_RADIANCE if params.draw_radiance else P.VOL_COLOR
                 self.levels = [device_tensor(g.device_ptr(which, l), g.level_bytes(which, l)) for l in range(g.L)]
                 self.chunks = level_chunks(g.D, g.L, world)
@@ -140,7 +140,7 @@ class ShardedFrame:
         if self.world == 1:
             return "1 GPU"
         if self.peer_exchange:
-            T = self.g.cfg.slab_stripe or self.g.D // self.world
+            T = self.g.slab_stripe()
             return (f"{self.world} GPUs, one process each: z sharding of clear/voxelise/transfer/inject/mip in stripes of {T} layers; slab exchange inside the library over NVLink peer memory "
                     "(level 0 as flagged x-row segments into staging regions, levels >= 1 stored into the peers' pyramids, device-side flags, no collective); "
                     "cone trace sharded by interleaved 64x64 screen tiles, pixels stored into rank 0's image")
