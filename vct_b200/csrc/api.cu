@@ -306,7 +306,8 @@ int gi_body(vct_ctx* c, Graph& g, bool cleared_by_frame_begin = false) {
     if (direct && !p.draw_radiance && ensure_color_texture(c)) return 1;
     const int which[2] = {VCT_VOL_RADIANCE, VCT_VOL_COLOR};
     const int publish[2] = {direct && p.draw_radiance, direct && !p.draw_radiance};
-    if (vctk_mip_chains(c, n_chains, which, publish, 0, sparse)) return 1;   // both pyramids, one launch
+    // (sharded with attached peers: the chain also stores its levels >= 1 into the peers' pyramids — compute and exchange in one kernel)
+    if (vctk_mip_chains(c, n_chains, which, publish, 0, sparse, !single && vctk_xchg_ready(c))) return 1;   // both pyramids, one launch
     // this frame's mask bounds the support of all three level-0 volumes (dense temporal frames: k_transfer flagged the history)
     c->seg_valid = maskable;
     c->last_frame_sparse = sparse;

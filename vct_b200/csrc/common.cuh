@@ -159,6 +159,7 @@ struct vct_ctx {
     // sparse slab exchange (exchange.cu): local staging, the peers' staging mapped through cudaIpc, record counter
     void* d_xchg = nullptr; size_t xchg_region_bytes = 0; unsigned xchg_cap = 0; unsigned* d_xchg_count = nullptr;
     vct_peer peer[VCT_MAX_PEERS]{}; bool peer_ipc[VCT_MAX_PEERS]{}; int peers_attached = 0; void* d_xchg_dst = nullptr;
+    int mip_pushed_upto = 0;     // sharded frame: the mip chain of this frame stored levels 1..mip_pushed_upto into the peers' pyramids itself
     uint32_t* d_trace_tiles = nullptr; int n_trace_tiles = 0;      // own 64x64 screen tiles (x0 | y0 << 16) of the sharded cone trace
     std::vector<vct_ctx*> group;                                    // single-process multi-GPU: the other ranks' contexts (this one is rank 0)
     void* group_state = nullptr; bool in_fan = false;               // worker threads of the group (api.cu); true while a call is being fanned out
@@ -259,7 +260,8 @@ int vctk_inject(vct_ctx*);
 int vctk_fill_holes(vct_ctx*);
 int vctk_shadow_minmax(vct_ctx*);
 int vctk_mip(vct_ctx*, int which, int mode, int publish);
-int vctk_mip_chains(vct_ctx*, int n, const int* which, const int* publish, int mode, bool masked = false);
+int vctk_mip_chains(vct_ctx*, int n, const int* which, const int* publish, int mode, bool masked = false, bool push_to_peers = false);
+int vctk_xchg_mip_peers(vct_ctx*, uint32_t** peer_pyramid);   // sharded frame: wait until the peers are done with last frame's pyramid, then their bases (nullptr for this rank)
 int vctk_publish(vct_ctx*, int which);
 int vctk_publish_upper(vct_ctx*, int which);   // levels 1..L-1 only
 int vctk_mip_top_sharded_level(const vct_ctx*);  // sharded frames: last level filtered from a rank's own stripes

@@ -153,6 +153,11 @@ __global__ void k_xchg_ack(unsigned* __restrict__ seq, const __grid_constant__ X
     __syncthreads();
     if (threadIdx.x == 0) *seq = s;
 }
+// before a kernel that stores into the peers' pyramids directly (the mip chain): every peer has acknowledged last frame, i.e. is done
+// reading its pyramid (publish of the upper levels, tail levels)
+__global__ void k_xchg_wait_consumed(const unsigned* __restrict__ seq, const __grid_constant__ XchgPeers peers) {
+    wait_flags(ctrl(peers.base[peers.rank])->consumed, peers.world, peers.rank, *seq);
+}
 // after the cone trace: this rank's pixels of frame *seq are in rank 0's image
 __global__ void k_xchg_image_done(const unsigned* __restrict__ seq, const __grid_constant__ XchgPeers peers) {
     __threadfence_system();
@@ -225,6 +230,14 @@ static int xchg_peers(vct_ctx* c, XchgPeers& p) {
     }
     return 0;
 }
+int vctk_xchg_mip_peers(vct_ctx* c, uint32_t** peer_pyramid) {
+    XchgPeers p{};
+    if (xchg_peers(c, p)) return 1;
+    k_xchg_wait_consumed<<<1, 1, 0, c->stream>>>(c->d_xchg_count + 16, p);
+    VCT_LAUNCH_CHECK(c, "k_xchg_wait_consumed");
+    for (int r = 0; r < VCT_MAX_PEERS; ++r) peer_pyramid[r] = r < p.world && r != p.rank ? p.pyramid[r] : nullptr;
+    return 0;
+}
 // the exchange of one frame: every rank ends up with the whole traced pyramid in its 3D texture
 int vctk_xchg_frame(vct_ctx* c, bool dense) {
     XchgPeers p{};
@@ -247,10 +260,12 @@ int vctk_xchg_frame(vct_ctx* c, bool dense) {
                                                                                   reinterpret_cast<const uint32_t*>(c->d_seg[c->seg_cur]), dense ? 1 : 0, c->st, w_stripe, n_words, counter, seq, p);
     VCT_LAUNCH_CHECK(c, "k_xchg_push");
     const int top = vctk_mip_top_sharded_level(c);          // levels 1..top: this rank's stripes, dense; the levels above follow from level `top` on every rank
-    if (top >= 1) {
+    const int first_upper = c->mip_pushed_upto + 1;         // levels below it went to the peers from inside the mip chain
+    c->mip_pushed_upto = 0;
+    if (top >= first_upper) {
         UpperLevels lv{};
         unsigned long long n = 0;
-        for (int l = 1; l <= top; ++l) {
+        for (int l = first_upper; l <= top; ++l) {
             const unsigned long long d = level_dim(c->D, l), run = d * d * (unsigned long long)(c->st.T >> l);
             for (int k = 0; k < c->st.count; ++k) {
                 if (lv.n >= kMaxRuns || c->level_off[l] + d * d * d > 0xFFFFFFFFull) { c->error = "slab exchange: too many (level, stripe) runs — use a larger slab_stripe"; return 1; }

@@ -598,6 +598,9 @@ struct MipChainArgs {
     MipChain chain[2]; int n_chains;              // radiance and colour pyramids filtered by one launch
     unsigned* ticket;                             // last-CTA detection for the tail levels
     int D, R, L, tail;                            // tail: reduce levels R..L-2 -> R+1..L-1 in the last CTA
+    // sharded frames: the levels >= 1 that chain `push_chain` writes also go to the same place of every peer's pyramid (NVLink stores;
+    // only bricks that hold or held something are written at all, so the exchange of the upper levels is as sparse as the scene)
+    uint32_t* peer[VCT_MAX_PEERS]; unsigned long long lvl_off[VCT_MAX_LEVELS]; int n_peers, push_chain;
     Stripes st;                                   // blockIdx.z counts the bricks of this rank's stripes, back to back
     const uint8_t *seg_a, *seg_b;                 // sparse frames: this and last frame's segment masks (nullptr: dense)
 };
@@ -641,6 +644,7 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
     if (block_active)
     for (int which = 0; which < args.n_chains; ++which) {
     const MipChain& a = args.chain[which];
+    const bool push = which == args.push_chain;
     if (which) __syncthreads();                                           // the shared levels of the previous chain have been read
     for (int q = threadIdx.x; q < nquads; q += kMipThreads) {
         const int lx = (q % qx) * 4, ly = (q / qx) % H, lz = q / (qx * H);
@@ -690,8 +694,10 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
         const uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
         const int gx = (bx >> 1) + lx, gy = (by >> 1) + ly, gz = (bz >> 1) + lz;
         if (f[0] || f[1] || f[2] || f[3]) {                                  // otherwise level 1 is, and stays, zero here
-            *reinterpret_cast<uint4*>(a.lvl[1] + ((size_t)gz * D1 + gy) * D1 + gx) = o;
+            const size_t at = ((size_t)gz * D1 + gy) * D1 + gx;
+            *reinterpret_cast<uint4*>(a.lvl[1] + at) = o;
             if (a.publish) surf3Dwrite(o, a.surf[1], gx * 4, gy, gz);
+            if (push) for (int r = 0; r < args.n_peers; ++r) if (args.peer[r]) *reinterpret_cast<uint4*>(args.peer[r] + args.lvl_off[1] + at) = o;
         }
         *reinterpret_cast<uint4*>(s1 + (lz * H + ly) * H + lx) = o;
     }
@@ -710,8 +716,10 @@ __global__ void __launch_bounds__(kMipThreads) k_mip_chain(const __grid_constant
             for (int j = 0; j < 8; ++j) w[j] = src[((2 * lz + (j & 1)) * Hs + 2 * ly + ((j >> 1) & 1)) * Hs + 2 * lx + (j >> 2)];
             const uint32_t o = box2_words(w, lut);
             const int gx = (bx >> (k + 1)) + lx, gy = (by >> (k + 1)) + ly, gz = (bz >> (k + 1)) + lz;
-            gl[((size_t)gz * Dd + gy) * Dd + gx] = o;
+            const size_t at = ((size_t)gz * Dd + gy) * Dd + gx;
+            gl[at] = o;
             if (a.publish) surf3Dwrite(o, gs, gx * 4, gy, gz);
+            if (push) for (int r = 0; r < args.n_peers; ++r) if (args.peer[r]) args.peer[r][args.lvl_off[k + 1] + at] = o;
             if (dsts) dsts[(lz * Hd + ly) * Hd + lx] = o;
         }
     }
@@ -993,7 +1001,8 @@ static int publish_levels(vct_ctx* c, int which, int l_begin, int l_end) {
 }
 // levels 1..L-1 (the reference's last loop iteration targets a non-existent level: Application.cpp:889-902) of up to
 // two pyramids.  publish[i] != 0 (single GPU): that pyramid also lands in the mipmapped array the cone tracer samples.
-int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, int mode, bool masked) {
+int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, int mode, bool masked, bool push_to_peers) {
+    c->mip_pushed_upto = 0;
     int publish[2] = {0, 0};
     uint32_t* base[2]; cudaSurfaceObject_t* surf[2];
     for (int i = 0; i < n; ++i) {
@@ -1020,6 +1029,17 @@ int vctk_mip_chains(vct_ctx* c, int n, const int* which, const int* publish_in, 
             if (publish[i] && !ch.pub_mask) { c->error = "vct_mip: publish mask missing"; return 1; }
         }
         a.n_chains = n; a.D = c->D; a.R = R; a.L = c->L; a.st = st;
+        a.push_chain = -1; a.n_peers = 0;
+        if (push_to_peers && multi) {
+            const int traced = c->h_fc.p.draw_radiance ? VCT_VOL_RADIANCE : VCT_VOL_COLOR;
+            for (int i = 0; i < n; ++i) if (which[i] == traced) a.push_chain = i;
+            if (a.push_chain >= 0) {
+                if (vctk_xchg_mip_peers(c, a.peer)) return 1;
+                a.n_peers = c->cfg.world_size;
+                for (int k = 0; k < c->L; ++k) a.lvl_off[k] = c->level_off[k];
+                c->mip_pushed_upto = R;
+            }
+        }
         a.tail = !multi && c->L - 1 > R;                        // sharded: the levels above the stripes follow the exchange (vctk_mip_tail)
         a.ticket = &c->d_counters->mip_ticket;
         a.seg_a = masked && R == 4 ? c->d_seg[c->seg_cur] : nullptr; a.seg_b = masked && R == 4 ? c->d_seg[c->seg_cur ^ 1] : nullptr;

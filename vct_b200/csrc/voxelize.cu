@@ -92,7 +92,6 @@ struct LongArgs { LongEntry* queue; unsigned cap; LongEntry* huge; HugeItem* ite
 __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& fc, uint32_t t, VoxSetup& S) {
     const uint32_t i0 = __ldg(a.indices + 3 * (size_t)t), i1 = __ldg(a.indices + 3 * (size_t)t + 1), i2 = __ldg(a.indices + 3 * (size_t)t + 2);
     const V3 w[3] = {ld3(a.wpos, i0), ld3(a.wpos, i1), ld3(a.wpos, i2)};
-    const V3 n0 = ld3(a.wnrm, i0), n1 = ld3(a.wnrm, i1), n2 = ld3(a.wnrm, i2);
     if (a.slab_cull) {
         // Multi-GPU: a triangle whose voxel-space box (1.5 voxels of slack) lies inside the volume but misses this rank's
         // z-slab can produce no fragment here — neither an owned one nor one outside the volume (those are counted by the
@@ -109,6 +108,7 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
         const bool inside = lo[0] >= 0.0f && lo[1] >= 0.0f && lo[2] >= 0.0f && hi[0] <= fd && hi[1] <= fd && hi[2] <= fd;   // false for NaN
         if (inside && !owns_any_z(fc.st, max((int)lo[2], 0), min((int)hi[2], a.D - 1))) return false;
     }
+    const V3 n0 = ld3(a.wnrm, i0), n1 = ld3(a.wnrm, i1), n2 = ld3(a.wnrm, i2);
     S.in.w[0] = w[0]; S.in.w[1] = w[1]; S.in.w[2] = w[2]; S.in.n[0] = n0; S.in.n[1] = n1; S.in.n[2] = n2;
     const V3 f = normalize3((n0 + n1) + n2);
     const float ax = fabsf(f.x), ay = fabsf(f.y), az = fabsf(f.z);
@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
     // Triangle t = (round * kThreads + thread) * gridDim + block: CONSECUTIVE triangles go to consecutive CTAs.  The large triangles of
     // a scene come in runs (a wall, a floor: neighbours in the index buffer); spread over the grid their tiles are enumerated by many
     // CTAs at once instead of queueing up in one (measured with block-contiguous triangles: 102 us for Sponza, the CTA that owned the
-    // atrium floor finished last).  The price is uncoalesced index loads (12 bytes per thread, a grid apart), 3 MB in all.
+    // atrium floor finished last; with warp-contiguous groups of 32: 85 us, config 4 256 us against 66 us).  The price is uncoalesced
+    // index loads (12 bytes per thread, a grid apart), 3 MB in all.
     const uint32_t per_round = gridDim.x * kThreads;
     const uint32_t n_rounds = (a.n_tris + per_round - 1u) / per_round;             // the same for every thread: the barriers below stay converged
     int round = 0;
