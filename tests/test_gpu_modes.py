@@ -191,3 +191,34 @@ def test_long_per_voxel_lists_without_a_warp_mode():
                 assert (i.total_fragments, i.unique_voxels, i.max_fragments_per_voxel) == (o.info.total_fragments, o.info.unique_voxels, o.info.max_fragments_per_voxel), (stack, k)
         finally:
             g.close()
+
+
+def test_pile_up_beyond_1024_fragments_outside_the_warp_modes():
+    """1300 coincident quads: the first frame runs without the long-list kernels, leaves the > 1024-fragment voxels unresolved and says so at the
+    next entry point (once, with its own message); from then on the k_voxel_huge_* kernels run and the frame equals the oracle."""
+    from vct_b200.lib import VctError
+    from vct_b200.pipeline import Pipeline
+    sc = S.Scene()
+    mat = sc.add_material(diffuse=sc.add_texture(S.checker_texture(16, 4, a=(200, 60, 40), b=(40, 90, 220), seed=1)))
+    parts = [S.quad_mesh([(-0.6, -0.2, 0.5), (0.7, -0.2, 0.5), (0.7, -0.2, -0.6), (-0.6, -0.2, -0.6)], (0, 1, 0), mat, 1.0 + 0.1 * (k % 7)) for k in range(1300)]
+    parts.append(S.quad_mesh([(-1.4, -1.0, 1.4), (1.4, -1.0, 1.4), (1.4, -1.0, -1.4), (-1.4, -1.0, -1.4)], (0, 1, 0), mat, 4.0))
+    sc.add_actor(S.merge_meshes(parts))
+    sc.lights = [P.make_light(position=(1.2, 4.0, 0.7), direction=(-0.28, -0.9, -0.2), shadow_caster=True, type_=1)]
+    d, l, ss, w, h = 32, 5, 256, 96, 64
+    p = S.room_params(w, h)
+    o = Oracle(sc, d, l, ss, w, h); o.frame(p)
+    assert o.info.total_fragments > 150000 and o.info.max_fragments_per_voxel == 1300 % 256   # the counter is the word's 8-bit running count
+    g = Pipeline(sc, d, l, ss, w, h)
+    try:
+        g.frame(p); g.sync()
+        with pytest.raises(VctError, match="1024 fragments"):
+            g.frame(p)
+        for k in range(2):
+            g.frame(p)
+            assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0]), k
+            assert np.array_equal(g.read_volume(P.VOL_NORMAL), o.normal), k
+            assert np.array_equal(g.read_volume(P.VOL_RADIANCE), o.radiance[0]), k
+            i = g.counters()
+            assert (i.total_fragments, i.unique_voxels, i.max_fragments_per_voxel) == (o.info.total_fragments, o.info.unique_voxels, o.info.max_fragments_per_voxel), k
+    finally:
+        g.close()

@@ -5,8 +5,8 @@
 TAG=${1:-r02}
 OUT=gpurun_out/${TAG}_sanitizer.txt
 mkdir -p gpurun_out; : > $OUT
-for mode in det cas warp; do
-  for tool in memcheck racecheck; do
+for mode in ${MODES:-det cas warp}; do
+  for tool in ${TOOLS:-memcheck racecheck}; do
     echo "==== compute-sanitizer --tool $tool : sanitize_frame.py $mode" >> $OUT
     timeout 600 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 9 python tools/sanitize_frame.py $mode 2 2>&1 | grep -v "^=========  *$" | tail -25 >> $OUT
     echo "exit code ${PIPESTATUS[0]}" >> $OUT

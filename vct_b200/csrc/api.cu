@@ -592,7 +592,14 @@ int vct_set_lights(vct_ctx* c, const vct_light* lights, int n) { VCT_FAN(c, vct_
 // mapped host memory, the next pass entry point reports it once (and does nothing else), then the context carries on.
 static int overflow_seen(vct_ctx* c) {
     if (!c->h_overflow || !*(volatile unsigned*)c->h_overflow) return 0;
+    const unsigned what = *(volatile unsigned*)c->h_overflow;
     *(volatile unsigned*)c->h_overflow = 0u;
+    if (what == 2u) {
+        c->error = "a voxel received more than 1024 fragments in a frame that ran without the long-list kernels (they start with the first frame that meets a long "
+                   "per-voxel list, or at once in the warp modes): that voxel was left unresolved in the previous frame; this call was not executed, the next one "
+                   "runs them and is exact";
+        return 1;
+    }
     c->error = "a fixed-capacity device buffer overflowed during an earlier call and fragments or tiles were dropped (fragment buffer, raster queues or triangle setups): "
                "raise vct_config.max_fragments; this call was not executed, the next one will be";
     return 1;

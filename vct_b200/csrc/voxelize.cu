@@ -532,7 +532,10 @@ __global__ void __launch_bounds__(kThreads) k_voxel_resolve(const Frag* __restri
                 // it launches them from the next frame on — and resolve this one here by selection: find the r-th largest key top
                 // down, then replay upwards from it.  2 r walks of the list: fine for the dense-mesh case this is for (N ~ 50-400, once).
                 if (counters->overflow_host) counters->overflow_host[1] = 1u;
-                if (count > (uint32_t)kMedMax) { vct_flag_overflow(counters); continue; }     // a pile-up without the scan kernels: reported, not resolved
+                if (count > (uint32_t)kMedMax) {                                // a pile-up without the scan kernels: reported (value 2), not resolved
+                    counters->overflow = 1u; if (counters->overflow_host) *counters->overflow_host = 2u;
+                    continue;
+                }
                 const int r = (int)((count - 1u) & 255u) + 1;
                 unsigned long long bound = ~0ull;                               // descend r times: bound = r-th largest key
                 for (int q = 0; q < r; ++q) {
