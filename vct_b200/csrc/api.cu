@@ -393,7 +393,7 @@ int vct_create(const vct_config* cfg, vct_ctx** out) {
     c->frag_cap = cfg->max_fragments > 0 ? (size_t)cfg->max_fragments : ((size_t)8 << 20);
     if (alloc((void**)&c->d_occ, N * N * N * 4) || alloc((void**)&c->d_warpmap, N * N * N * (8 + 32)) || alloc((void**)&c->d_wlo, N * N * N * 8) || alloc((void**)&c->d_whi, N * N * N * 8) ||
         alloc((void**)&c->d_shadow_base, 2 * (size_t)c->S * c->S * 4) || alloc(&c->d_shadow_mm, ((size_t)(c->S / 4 + 1) * (c->S / 4 + 1) + (size_t)(c->S / 64 + 1) * (c->S / 16 + 1)) * 8) || alloc((void**)&c->d_inject_list, ((size_t)(c->S / 64 + 1) * (c->S / 16 + 1) + 1) * 4) || alloc((void**)&c->d_vis, (size_t)c->W * c->H * 8) || alloc((void**)&c->d_image, 2 * vctk_image_rows(c) * (size_t)c->W * 4) ||
-        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc(&c->d_long_queue, (c->long_cap + 8) * 16) || alloc(&c->d_huge_items, c->frag_cap * 16) || alloc(&c->d_huge_aux, vctk_huge_aux_bytes()) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
+        alloc((void**)&c->d_frags, c->frag_cap * vctk_frag_bytes()) || alloc((void**)&c->d_displaced, c->frag_cap) || alloc(&c->d_long_queue, (c->long_cap + 16) * 16) || alloc(&c->d_huge_items, c->frag_cap * 16) || alloc(&c->d_huge_aux, vctk_huge_aux_bytes()) || alloc((void**)&c->d_warp_scratch, N * N * N * 4) ||
         alloc((void**)&c->d_counters, sizeof(Counters)) ||
         alloc((void**)&c->d_tex, sizeof(DevTexture) * VCT_MAX_TEXTURES) || alloc((void**)&c->d_mat, sizeof(DevMaterial) * VCT_MAX_MATERIALS))
         return bail("cudaMalloc");

@@ -106,7 +106,7 @@ struct Counters {                // device-resident, zeroed per frame
     unsigned setup_count;        // big-triangle setups written by k_raster_bin
     unsigned overflow;           // set when a fixed-capacity buffer was too small (reset with the other per-frame counters)
     unsigned mip_ticket;         // k_mip_chain last-CTA detection (self-resetting)
-    unsigned long_count, huge_count, huge_items;   // deterministic voxeliser: queued long per-voxel lists (voxelize.cu)
+    unsigned long_count, huge_count, huge_items, huge_tickets;   // deterministic voxeliser: queued long per-voxel lists (voxelize.cu)
     unsigned long long cone_steps;
     unsigned* overflow_host;     // the same flag in mapped pinned host memory: the frame entry points poll it without a device sync
 };

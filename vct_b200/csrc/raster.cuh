@@ -323,13 +323,15 @@ __device__ __forceinline__ float calc_shadow_factor(const float* __restrict__ sm
 
 // ------------------------------------------------------------------------------ warpmap (exact software path)
 // 32^3 RGBA16 unorm, LINEAR, CLAMP_TO_EDGE (reference src/Application.cpp:383-389)
-__device__ __forceinline__ V3 warp_texel(const uint16_t* __restrict__ wm, int x, int y, int z) {
+// The float copy behind the unorm16 texels (k_warpmap_floats): q / 65535 per channel, the IEEE division done once per texel.  One entry = texel
+// (x, y, z) and its +x neighbour (CLAMP_TO_EDGE), 32 bytes: one 256-bit load (LDG.E.256, sm_100) fetches both x corners of a trilinear cell.
+// x, y, z already clamped.
+__device__ __forceinline__ void warp_texel_pair(const uint16_t* __restrict__ wm, int x, int y, int z, V3& a, V3& b) {
     const int n = VCT_WARP_DIM;
-    x = min(max(x, 0), n - 1); y = min(max(y, 0), n - 1); z = min(max(z, 0), n - 1);
-    // the float copy behind the unorm16 texels (k_warpmap_floats): q / 65535 per channel, the IEEE division done once per texel; one entry =
-    // the texel and its +x neighbour (32 bytes, for the cone tracer's 256-bit loads) — this reader takes the first half
-    const float4 q = __ldg(reinterpret_cast<const float4*>(wm + 4 * (size_t)n * n * n) + 2 * (((size_t)z * n + y) * n + x));
-    return mk3(q.x, q.y, q.z);
+    const float4* p = reinterpret_cast<const float4*>(wm + 4 * (size_t)n * n * n) + 2 * (((size_t)z * n + y) * n + x);
+    float ax, ay, az, aw, bx, by, bz, bw;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(ax), "=f"(ay), "=f"(az), "=f"(aw), "=f"(bx), "=f"(by), "=f"(bz), "=f"(bw) : "l"(p));
+    a = mk3(ax, ay, az); b = mk3(bx, by, bz);
 }
 __device__ __forceinline__ V3 lerp3(V3 a, V3 b, float t) { const float s = 1.0f - t; return mk3(a.x * s + b.x * t, a.y * s + b.y * t, a.z * s + b.z * t); }
 __device__ __forceinline__ V3 warp_sample(const uint16_t* __restrict__ wm, V3 tc) {
@@ -338,10 +340,14 @@ __device__ __forceinline__ V3 warp_sample(const uint16_t* __restrict__ wm, V3 tc
     const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
     if (!(fabsf(fx0) < 1e9f) || !(fabsf(fy0) < 1e9f) || !(fabsf(fz0) < 1e9f)) return mk3(0.f, 0.f, 0.f);
     const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0; const float fx = x - fx0, fy = y - fy0, fz = z - fz0;
-    V3 c00 = lerp3(warp_texel(wm, x0, y0, z0), warp_texel(wm, x0 + 1, y0, z0), fx);
-    V3 c10 = lerp3(warp_texel(wm, x0, y0 + 1, z0), warp_texel(wm, x0 + 1, y0 + 1, z0), fx);
-    V3 c01 = lerp3(warp_texel(wm, x0, y0, z0 + 1), warp_texel(wm, x0 + 1, y0, z0 + 1), fx);
-    V3 c11 = lerp3(warp_texel(wm, x0, y0 + 1, z0 + 1), warp_texel(wm, x0 + 1, y0 + 1, z0 + 1), fx);
+    const int n1 = VCT_WARP_DIM - 1;
+    const int xc = min(max(x0, 0), n1), ya = min(max(y0, 0), n1), yb = min(max(y0 + 1, 0), n1), za = min(max(z0, 0), n1), zb = min(max(z0 + 1, 0), n1);
+    V3 a00, b00, a10, b10, a01, b01, a11, b11;
+    warp_texel_pair(wm, xc, ya, za, a00, b00); warp_texel_pair(wm, xc, yb, za, a10, b10);
+    warp_texel_pair(wm, xc, ya, zb, a01, b01); warp_texel_pair(wm, xc, yb, zb, a11, b11);
+    if (x0 < 0) { b00 = a00; b10 = a10; b01 = a01; b11 = a11; }                // both x corners clamp to texel 0
+    else if (x0 > n1) { a00 = b00; a10 = b10; a01 = b01; a11 = b11; }          // (x0 >= n: both clamp to the last texel, whose entry holds it twice)
+    V3 c00 = lerp3(a00, b00, fx), c10 = lerp3(a10, b10, fx), c01 = lerp3(a01, b01, fx), c11 = lerp3(a11, b11, fx);
     return lerp3(lerp3(c00, c10, fy), lerp3(c01, c11, fy), fz);
 }
 

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads) k_clear(uint4* __restrict__ a, uint4
     if (reset && blockIdx.x == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
         reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
-        reset->cone_steps = 0ull; reset->overflow = 0; reset->long_count = 0; reset->huge_count = 0; reset->huge_items = 0;
+        reset->cone_steps = 0ull; reset->overflow = 0; reset->long_count = 0; reset->huge_count = 0; reset->huge_items = 0; reset->huge_tickets = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
@@ -54,7 +54,7 @@ __device__ __forceinline__ void clear_masked_part(uint4* __restrict__ color, uin
     if (block == 0 && threadIdx.x == 0) {
         reset->total_fragments = 0; reset->unique_voxels = 0; reset->max_fragments_per_voxel = 0;
         reset->n_frag_slots = 0; reset->tile_queue_count = 0; reset->setup_count = 0; reset->expand_count = 0; reset->pixel_count = 0;
-        reset->cone_steps = 0ull; reset->overflow = 0; reset->long_count = 0; reset->huge_count = 0; reset->huge_items = 0;
+        reset->cone_steps = 0ull; reset->overflow = 0; reset->long_count = 0; reset->huge_count = 0; reset->huge_items = 0; reset->huge_tickets = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (size_t tl = block * (size_t)blockDim.x + threadIdx.x; tl < n_words; tl += (size_t)n_blocks * blockDim.x) {

@@ -81,7 +81,8 @@ struct VoxArgs {
 // bitonic sort in shared memory, replay of the last r), and for the few voxels beyond that a scan of ALL fragment records instead of a
 // walk of a 751 k-entry list: compact the voxel's (order key, slot) pairs, radix-select the r-th largest key, sort and replay those r.
 constexpr int kMedMax = 1024;
-constexpr int kHugeMax = 8;
+constexpr int kHugeMax = 16;                                         // (api.cu reserves 16 entries behind the long queue)
+constexpr uint32_t kWalkMax = 1u << 16;                             // longest list a warp still walks when the huge table has no room for it
 struct LongEntry { uint32_t key, head, count, pad; };               // voxel, head slot of its list, fragment count
 struct __align__(16) HugeItem { unsigned long long k; uint32_t slot, h; };   // order key + 1, fragment slot, index into the huge table
 constexpr int kHugeBins = 4096, kHugeSmall = 16384;                 // coarse histogram over the triangle index; per-voxel short list of the gather pass
@@ -612,7 +613,10 @@ __device__ __forceinline__ void replay_staged(const float* __restrict__ stage, i
     cw = 0u; nw = 0u;
     for (int q = 0; q < r; ++q) { const float* o = stage + 6 * q; cw = rgba8_avg_insert(cw, o[0], o[1], o[2]); nw = rgba8_avg_insert(nw, o[3], o[4], o[5]); }
 }
-// one warp per queued voxel with kSortMax < N <= kMedMax fragments; longer ones are entered into the huge table
+// One warp per queued voxel with N > kSortMax fragments.  N <= kMedMax: list walk, sort, replay.  Longer lists go to the huge table (no walk:
+// the scan kernels below) — the giant ones (N > kWalkMax) always, the others while fewer than kHugeMax / 2 of them have asked; a list that gets
+// no slot is walked here in chunks of kMedMax, keeping the r largest keys met so far between chunks (exact; 0.3 us per node, for scenes
+// with MANY voxels beyond 1024 fragments: a dense mesh on a coarse grid).
 constexpr int kMedWarps = 2;
 template <bool TRANSFER>
 __global__ void __launch_bounds__(kMedWarps * 32) k_voxel_resolve_medium(const Frag* __restrict__ frags, Counters* __restrict__ counters, uint32_t* __restrict__ color,
@@ -625,26 +629,51 @@ __global__ void __launch_bounds__(kMedWarps * 32) k_voxel_resolve_medium(const F
     for (unsigned e = blockIdx.x * kMedWarps + w; e < n; e += gridDim.x * kMedWarps) {
         const LongEntry le = lq.queue[e];
         if (le.count > (uint32_t)kMedMax) {
-            if (lane == 0) { const unsigned h = atomicAdd(&counters->huge_count, 1u); if (h < (unsigned)kHugeMax) lq.huge[h] = le; else vct_flag_overflow(counters); }
-            continue;
+            int placed = 0;
+            if (lane == 0) {
+                const bool giant = le.count > kWalkMax;
+                if (giant || atomicAdd(&counters->huge_tickets, 1u) < (unsigned)(kHugeMax / 2)) {
+                    const unsigned h = atomicAdd(&counters->huge_count, 1u);
+                    if (h < (unsigned)kHugeMax) { lq.huge[h] = le; placed = 1; }
+                }
+                if (giant && !placed) { vct_flag_overflow(counters); placed = 1; }      // more than kHugeMax pile-ups beyond 65536 fragments: reported
+            }
+            if (__shfl_sync(0xffffffffu, placed, 0)) continue;
         }
-        int cnt = 0;
-        if (lane == 0) for (uint32_t j = le.head + 1u; j && cnt < kMedMax; j = frags[j - 1u].next) s_slot[w][cnt++] = j - 1u;
-        cnt = __shfl_sync(0xffffffffu, cnt, 0);
-        int n2 = 32; while (n2 < cnt) n2 <<= 1;
-        __syncwarp();
-        for (int k = lane; k < n2; k += 32) {
-            if (k < cnt) s_key[w][k] = order_key(frags[s_slot[w][k]]); else { s_key[w][k] = 0ull; s_slot[w][k] = 0u; }
+        const int r = (int)((le.count - 1u) & 255u) + 1;                     // only the last r in canonical order matter (voxelize.frag:127-133)
+        uint32_t j = le.head + 1u;                                           // (lane 0's copy walks)
+        int kept = 0, cnt = 0, n2 = 32;
+        for (;;) {
+            int m = kept;
+            if (lane == 0) for (; j && m < kMedMax; j = frags[j - 1u].next) s_slot[w][m++] = j - 1u;
+            cnt = __shfl_sync(0xffffffffu, m, 0);
+            const bool more = __shfl_sync(0xffffffffu, (int)(j != 0u), 0) != 0;
+            n2 = 32; while (n2 < cnt) n2 <<= 1;
+            __syncwarp();
+            for (int k = kept + lane; k < n2; k += 32) {                     // entries [0, kept) carry their keys over from the last chunk
+                if (k < cnt) s_key[w][k] = order_key(frags[s_slot[w][k]]); else { s_key[w][k] = 0ull; s_slot[w][k] = 0u; }
+            }
+            bitonic_sort(s_key[w], s_slot[w], n2, lane, 32, false);
+            if (!more) break;
+            // the list goes on: the r largest keys so far move to the front (through registers: the ranges may overlap), the rest is dropped
+            const int keep = min(r, cnt);
+            unsigned long long kk[8]; uint32_t ss[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const int i = lane + 32 * q; if (i < keep) { kk[q] = s_key[w][n2 - keep + i]; ss[q] = s_slot[w][n2 - keep + i]; } }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const int i = lane + 32 * q; if (i < keep) { s_key[w][i] = kk[q]; s_slot[w][i] = ss[q]; } }
+            __syncwarp();
+            kept = keep;
         }
-        bitonic_sort(s_key[w], s_slot[w], n2, lane, 32, false);
-        const int r = ((cnt - 1) & 255) + 1;
         float* stage = reinterpret_cast<float*>(s_key[w]);                   // the keys are done with: 256 x 24 bytes fit in their 8 KB
         __syncwarp();
-        stage_last(frags, s_slot[w], n2, r, stage, lane, 32);
+        const int rr = min(r, cnt);
+        stage_last(frags, s_slot[w], n2, rr, stage, lane, 32);
         __syncwarp();
         if (lane == 0) {
             uint32_t cw, nw;
-            replay_staged(stage, r, cw, nw);
+            replay_staged(stage, rr, cw, nw);
             finish_voxel<TRANSFER>(le.key, cw, nw, color, normal, radiance, opacity, uniq, maxfrag);
         }
         __syncwarp();
@@ -800,7 +829,7 @@ __global__ void __launch_bounds__(kSelThreads) k_voxel_huge_select(const Frag* _
     }
 }
 
-__global__ void k_voxel_reset(Counters* c) { c->overflow = 0; c->long_count = 0; c->huge_count = 0; c->huge_items = 0; c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
+__global__ void k_voxel_reset(Counters* c) { c->overflow = 0; c->long_count = 0; c->huge_count = 0; c->huge_items = 0; c->huge_tickets = 0; c->n_frag_slots = 0; c->tile_queue_count = 0; c->setup_count = 0; c->expand_count = 0; c->pixel_count = 0; }
 
 // ================================================================ tessellation voxeliser (reference default)
 // testTesselation.tesc/.tese + the fixed-function tessellator (triangles, equal_spacing, point_mode), Application.cpp:585-665.
