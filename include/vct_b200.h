@@ -131,7 +131,18 @@ typedef struct {
      * phong.frag (each cone sample goes back to world space and through pv, phong.frag:158-162); voxelize.frag declares the
      * uniform but never reads it, so the raster voxeliser ignores it — like the reference. */
     int   voxelize_tesselation_warp;
+    /* Settings::conservativeRasterization (Application.h:61-62; reference default MSAA, parity mode OFF): how the two voxelisation
+     * passes (occupancy :244-249, voxelise :673-678) decide coverage.  VCT_RASTER_CENTER = OFF: a fragment where the pixel centre is
+     * covered.  VCT_RASTER_MSAA: GL_MULTISAMPLE on the 4-sample window framebuffer (main.cpp:256) — a fragment where ANY sample is
+     * covered by the near/far-clipped triangle (OpenGL 4.5 section 14.6.6), its inputs interpolated at the pixel centre (no `centroid`
+     * in voxelize.geom/.frag: extrapolated when the centre itself is outside).  GL leaves the sample positions to the driver
+     * (glGetMultisamplefv); msaa_samples holds them as (x, y) pairs in pixels, y up, multiples of 1/256 — all zero selects the
+     * standard 4x pattern of NVIDIA's GL and D3D: (0.375, 0.125) (0.875, 0.375) (0.125, 0.625) (0.625, 0.875).  The NV mode
+     * (GL_CONSERVATIVE_RASTERIZATION_NV) is not built. */
+    int   conservative_raster;
+    float msaa_samples[8];
 } vct_frame_params;
+enum { VCT_RASTER_CENTER = 0, VCT_RASTER_MSAA = 1 };
 
 enum { VCT_VIEW_SHADED = 0,
        VCT_VIEW_VOXELS = 1,            /* `voxelize`: the traced volume sampled at the fragment's voxel, lod = miplevel   phong.frag:347-404 */

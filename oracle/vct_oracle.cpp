@@ -308,7 +308,27 @@ struct Setup {
     float zndc[3];
     int x0, x1, y0, y1; bool valid;
 };
-inline Setup tri_setup(const RV v[3], int W, int H, bool cull_back) {
+// Sample positions in 1/256 pixel from the pixel's lower-left corner.  Settings::conservativeRasterization == MSAA (reference default,
+// Application.cpp:244-249, 673-678): GL_MULTISAMPLE on the 4-sample window framebuffer (main.cpp:256).  OpenGL 4.5 section 14.6.6: a fragment is
+// produced for a pixel if ANY sample is covered (same point-sampling rule per sample, applied to the near/far-clipped triangle); without a
+// `centroid` qualifier the fragment's inputs may be evaluated anywhere in the pixel — canonical choice: the pixel centre (what NVIDIA and AMD
+// hardware do), extrapolated when the centre is outside.  The positions are the driver's (glGetMultisamplefv): a parameter, default the
+// standard 4x pattern.
+struct Samples { int n; int64_t x[4], y[4]; int64_t x_min, x_max, y_min, y_max; };
+inline bool msaa_samples(const vct_frame_params* fp, Samples& ms) {
+    if (fp->conservative_raster != VCT_RASTER_MSAA) return false;
+    static const float standard4x[8] = {0.375f, 0.125f, 0.875f, 0.375f, 0.125f, 0.625f, 0.625f, 0.875f};
+    bool given = false;
+    for (int i = 0; i < 8; ++i) given = given || fp->msaa_samples[i] != 0.0f;
+    const float* sp = given ? fp->msaa_samples : standard4x;
+    ms.n = 4; ms.x_min = ms.y_min = 256; ms.x_max = ms.y_max = 0;
+    for (int i = 0; i < 4; ++i) {
+        ms.x[i] = std::min<int64_t>(255, std::max<int64_t>(0, std::lrint(sp[2 * i] * 256.0f))); ms.y[i] = std::min<int64_t>(255, std::max<int64_t>(0, std::lrint(sp[2 * i + 1] * 256.0f)));
+        ms.x_min = std::min(ms.x_min, ms.x[i]); ms.x_max = std::max(ms.x_max, ms.x[i]); ms.y_min = std::min(ms.y_min, ms.y[i]); ms.y_max = std::max(ms.y_max, ms.y[i]);
+    }
+    return true;
+}
+inline Setup tri_setup(const RV v[3], int W, int H, bool cull_back, const Samples* ms = nullptr) {
     Setup s; s.valid = false;
     int64_t X[3], Y[3];
     for (int i = 0; i < 3; ++i) { X[i] = snap(v[i].x / v[i].w, W); Y[i] = snap(v[i].y / v[i].w, H); }
@@ -328,8 +348,10 @@ inline Setup tri_setup(const RV v[3], int W, int H, bool cull_back) {
     // pixel i has centre 256 i + 128
     auto cdiv = [](int64_t a) { return (a >= 0) ? (a + 255) / 256 : -((-a) / 256); };      // ceil(a/256)
     auto fdiv = [](int64_t a) { return (a >= 0) ? a / 256 : -((-a + 255) / 256); };        // floor(a/256)
-    s.x0 = (int)std::max<int64_t>(0, cdiv(minx - 128)); s.x1 = (int)std::min<int64_t>(W - 1, fdiv(maxx - 128));
-    s.y0 = (int)std::max<int64_t>(0, cdiv(miny - 128)); s.y1 = (int)std::min<int64_t>(H - 1, fdiv(maxy - 128));
+    // (multisampling: pixel i has samples at 256 i + offset; it can hold a covered one iff some offset lands inside [min, max])
+    const int64_t ox_hi = ms ? ms->x_max : 128, ox_lo = ms ? ms->x_min : 128, oy_hi = ms ? ms->y_max : 128, oy_lo = ms ? ms->y_min : 128;
+    s.x0 = (int)std::max<int64_t>(0, cdiv(minx - ox_hi)); s.x1 = (int)std::min<int64_t>(W - 1, fdiv(maxx - ox_lo));
+    s.y0 = (int)std::max<int64_t>(0, cdiv(miny - oy_hi)); s.y1 = (int)std::min<int64_t>(H - 1, fdiv(maxy - oy_lo));
     s.valid = s.x0 <= s.x1 && s.y0 <= s.y1;
     return s;
 }
@@ -355,6 +377,38 @@ inline void raster(const Setup& s, int ylo, int yhi, F&& emit) {
     }
 }
 inline float interp(const float l[3], float a0, float a1, float a2) { return (l[0] * a0 + l[1] * a1) + l[2] * a2; }
+// Multisample variant: emit(px, py, l at the PIXEL CENTRE) for every pixel with at least one sample that is inside the triangle and inside
+// -1 <= z <= 1 at that sample (z[] = ndc z per source vertex); raster-scan order.  The caller does not repeat the near/far test.
+template <class F>
+inline void raster_any_sample(const Setup& s, const Samples& ms, const float z[3], F&& emit) {
+    const float fa = (float)s.area;
+    auto edges = [&](int64_t Px, int64_t Py, int64_t E[3]) {
+        bool in = true;
+        for (int k = 0; k < 3; ++k) {
+            const int a = (k + 1) % 3, b = (k + 2) % 3;
+            E[k] = (s.X[b] - s.X[a]) * (Py - s.Y[a]) - (s.Y[b] - s.Y[a]) * (Px - s.X[a]);
+            in = in && E[k] + s.bias[k] >= 0;
+        }
+        return in;
+    };
+    for (int py = s.y0; py <= s.y1; ++py)
+        for (int px = s.x0; px <= s.x1; ++px) {
+            bool any = false;
+            for (int i = 0; i < ms.n && !any; ++i) {
+                int64_t E[3];
+                if (!edges(256 * (int64_t)px + ms.x[i], 256 * (int64_t)py + ms.y[i], E)) continue;
+                float l[3];
+                for (int k = 0; k < 3; ++k) l[s.order[k]] = (float)E[k] / fa;
+                const float zs = interp(l, z[0], z[1], z[2]);
+                any = !(zs < -1.0f || zs > 1.0f);
+            }
+            if (!any) continue;
+            int64_t E[3]; float l[3];
+            edges(256 * (int64_t)px + 128, 256 * (int64_t)py + 128, E);
+            for (int k = 0; k < 3; ++k) l[s.order[k]] = (float)E[k] / fa;
+            emit(px, py, l);
+        }
+}
 inline V3 interp3(const float l[3], V3 a, V3 b, V3 c) {
     return {interp(l, a.x, b.x, c.x), interp(l, a.y, b.y, c.y), interp(l, a.z, b.z, c.z)};
 }
@@ -516,20 +570,23 @@ extern "C" void orc_occupancy(const orc_scene* sc, const vct_frame_params* fp, u
     const int D = VCT_WARP_DIM;
     Prepared P = prepare(sc, false);
     std::memset(occ, 0, sizeof(unsigned) * D * D * D);
+    Samples ms; const bool msaa = msaa_samples(fp, ms);
     for (int t = 0; t < sc->n_tris; ++t) {
         const unsigned* ix = sc->indices + 3 * (size_t)t;
         VoxAxis va = pick_axis(fp, P.wnrm[ix[0]], P.wnrm[ix[1]], P.wnrm[ix[2]]);
         RV cv[3];
         for (int k = 0; k < 3; ++k) { V3 w = P.wpos[ix[k]]; V4 c = mul(va.mvp, {w.x, w.y, w.z, 1.0f}); cv[k] = {c.x, c.y, c.z, c.w}; }
-        Setup s = tri_setup(cv, D, D, false);
+        Setup s = tri_setup(cv, D, D, false, msaa ? &ms : nullptr);
         if (!s.valid) continue;
-        raster(s, 0, D - 1, [&](int, int, const float l[3]) {
+        auto frag = [&](int, int, const float l[3]) {
             V3 ndc = {interp(l, cv[0].x, cv[1].x, cv[2].x), interp(l, cv[0].y, cv[1].y, cv[2].y), interp(l, cv[0].z, cv[1].z, cv[2].z)};
-            if (ndc.z < -1.0f || ndc.z > 1.0f) return;
+            if (!msaa && (ndc.z < -1.0f || ndc.z > 1.0f)) return;
             int idx[3];
             if (!to_index(frag_voxel_position(ndc, va.axis, D, fp, nullptr, true), D, idx)) return;
             occ[((size_t)idx[2] * D + idx[1]) * D + idx[0]] |= 1u;
-        });
+        };
+        const float zs[3] = {cv[0].z, cv[1].z, cv[2].z};
+        if (msaa) raster_any_sample(s, ms, zs, frag); else raster(s, 0, D - 1, frag);
     }
 }
 
@@ -543,6 +600,7 @@ static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D
         std::memset(normal, 0, sizeof(unsigned) * (size_t)D * D * D);
     }
     unsigned total = 0;
+    Samples ms; const bool msaa = msaa_samples(fp, ms);
     for (int t = 0; t < sc->n_tris; ++t) {
         const unsigned* ix = sc->indices + 3 * (size_t)t;
         V3 n[3] = {P.wnrm[ix[0]], P.wnrm[ix[1]], P.wnrm[ix[2]]}, w[3] = {P.wpos[ix[0]], P.wpos[ix[1]], P.wpos[ix[2]]};
@@ -552,14 +610,14 @@ static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D
             V4 c = mul(va.mvp, {w[k].x, w[k].y, w[k].z, 1.0f}); cv[k] = {c.x, c.y, c.z, c.w};
             uv[k][0] = sc->vertices[14 * (size_t)ix[k] + 6]; uv[k][1] = sc->vertices[14 * (size_t)ix[k] + 7];
         }
-        Setup s = tri_setup(cv, D, D, false);
+        Setup s = tri_setup(cv, D, D, false, msaa ? &ms : nullptr);
         if (!s.valid) continue;
         const vct_material& mat = sc->materials[sc->tri_material[t]];
         const Tex* dt = mat.diffuse_tex >= 0 ? &P.tex[mat.diffuse_tex] : nullptr;
         const float rho2 = dt ? tri_rho2_affine(cv, uv, D, D, *dt) : 0.0f;
-        raster(s, 0, D - 1, [&](int, int, const float l[3]) {
+        auto frag = [&](int, int, const float l[3]) {
             V3 ndc = {interp(l, cv[0].x, cv[1].x, cv[2].x), interp(l, cv[0].y, cv[1].y, cv[2].y), interp(l, cv[0].z, cv[1].z, cv[2].z)};
-            if (ndc.z < -1.0f || ndc.z > 1.0f) return;                  // near/far clip of the ortho volume
+            if (!msaa && (ndc.z < -1.0f || ndc.z > 1.0f)) return;       // near/far clip of the ortho volume (multisampling: per sample, in the rasteriser)
             total++;                                                      // voxelize.frag:195
             V3 wp = interp3(l, w[0], w[1], w[2]);
             V3 nn = interp3(l, n[0], n[1], n[2]);
@@ -610,7 +668,9 @@ static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D
                 color[o] = rgba8_avg_insert(color[o], col.x, col.y, col.z);
                 normal[o] = rgba8_avg_insert(normal[o], nenc.x, nenc.y, nenc.z);
             }
-        });
+        };
+        const float zs[3] = {cv[0].z, cv[1].z, cv[2].z};
+        if (msaa) raster_any_sample(s, ms, zs, frag); else raster(s, 0, D - 1, frag);
     }
     if (info) { info->total_fragments = total; info->unique_voxels = 0; info->max_fragments_per_voxel = 0; }
     if (frag_count) *frag_count = total;

@@ -204,6 +204,8 @@ def pbr_room():
 FRAG_MODES = {
     "default": {},
     "atomic_max": {"voxelize_atomic_max": 1},
+    # Settings::conservativeRasterization == MSAA: fragments wherever any of the 4 samples is covered, inputs extrapolated to the pixel centre
+    "msaa": {"conservative_raster": 1},
     "no_voxel_lighting": {"voxelize_lighting": 0},
     "warp_voxels": {"warp_voxels": 1},
     "warp_texture": {"warp_texture": 1},

@@ -222,3 +222,39 @@ def test_pile_up_beyond_1024_fragments_outside_the_warp_modes():
             assert (i.total_fragments, i.unique_voxels, i.max_fragments_per_voxel) == (o.info.total_fragments, o.info.unique_voxels, o.info.max_fragments_per_voxel), k
     finally:
         g.close()
+
+
+def test_msaa_voxelisation_bit_exact(room):
+    """Settings::conservativeRasterization == MSAA (the reference's default raster mode, Application.cpp:244-249, 673-678): any-sample coverage
+    of the 4x pattern, inputs at the pixel centre.  Occupancy grid, volumes, every pyramid level and the counters equal the oracle's, in the
+    deterministic and the atomic-max mode, with the warp map on top, on a dense and on a sparse frame; a pattern with every sample at the
+    pixel centre reproduces centre sampling."""
+    sc, p, o, g = room
+    o.frame(p); g.frame(p)
+    off = g.read_volume(P.VOL_COLOR).copy(); off_frags = g.counters().total_fragments
+    for mods in ({}, {"voxelize_atomic_max": 1}, {"warp_texture": 1, "temporal_filter_radiance": 1}):
+        q = type(p).from_buffer_copy(p); q.conservative_raster = P.RASTER_MSAA
+        for k, v in mods.items():
+            setattr(q, k, v)
+        for frame in range(2):                                  # second frame: sparse
+            o.frame(q); g.frame(q)
+            if q.warp_texture:
+                assert np.array_equal(g.read_volume(P.VOL_OCCUPANCY), o.occ), (mods, frame)
+            assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0]), (mods, frame)
+            assert np.array_equal(g.read_volume(P.VOL_NORMAL), o.normal), (mods, frame)
+            for l in range(L):
+                assert np.array_equal(g.read_volume(P.VOL_RADIANCE, l), o.radiance[l]), (mods, frame, l)
+            i = g.counters()
+            assert (i.total_fragments, i.unique_voxels, i.max_fragments_per_voxel) == (o.info.total_fragments, o.info.unique_voxels, o.info.max_fragments_per_voxel), (mods, frame)
+            assert psnr(g.read_image(), o.image) >= 45.0
+        if not mods:
+            assert g.counters().total_fragments > off_frags * 1.05
+    q = type(p).from_buffer_copy(p); q.conservative_raster = P.RASTER_MSAA
+    q.msaa_samples = (C.c_float * 8)(*([0.5] * 8))
+    g.frame(q)
+    assert g.counters().total_fragments == off_frags and np.array_equal(g.read_volume(P.VOL_COLOR), off)
+    from vct_b200.lib import VctError
+    q.conservative_raster = 2                                   # GL_CONSERVATIVE_RASTERIZATION_NV: not built, refused
+    with pytest.raises(VctError):
+        g.frame(q)
+    g.frame(p)

@@ -271,3 +271,69 @@ def test_diffuse_march_schedule():
     assert np.allclose(hs, GOLD["diffuse_schedule"]["h"], rtol=2e-3)
     assert np.allclose(lam, GOLD["diffuse_schedule"]["lambda"], atol=6e-3)
     assert lam[7] > 5.0                          # clamped to the coarsest level (L-1 = 5) from step 7 on
+
+
+# ------------------------------------------------------------------ multisample coverage (Settings::conservativeRasterization == MSAA)
+def _one_triangle_scene(cx, cy, r, z=0.3):
+    """A small +z-facing triangle around (cx, cy) in the z-dominant view of a +-1 volume (window = (ndc * 0.5 + 0.5) * D, y up)."""
+    from vct_b200 import scene as S
+    sc = S.Scene()
+    mat = sc.add_material(diffuse=sc.add_texture(np.full((1, 1, 3), 200, np.uint8)))
+    verts = [[cx - r, cy - r, z, 0, 0, 1, 0, 0] + [0] * 6, [cx + r, cy - r, z, 0, 0, 1, 1, 0] + [0] * 6, [cx, cy + r, z, 0, 0, 1, 0, 1] + [0] * 6]
+    sc.add_actor(S.Mesh(np.array(verts, np.float32), [0, 1, 2], np.array([mat], np.int32)))
+    sc.lights = [P.make_light(position=(0.0, 0.0, 3.0), direction=(0.0, 0.0, -1.0), shadow_caster=False, type_=1)]
+    return sc
+
+
+def test_msaa_fragment_where_only_a_sample_is_covered():
+    """OpenGL 4.5 section 14.6.6 with the standard 4x pattern: a triangle 0.3 pixels across around sample 0 of pixel (5, 7) — (5.375, 7.125) —
+    covers neither that pixel's centre nor any other sample: no fragment with centre sampling, exactly one with multisampling, and its voxel
+    is the one of the pixel CENTRE (inputs are interpolated there, extrapolated beyond the triangle)."""
+    D = 16
+    to_world = lambda w: w / D * 2.0 - 1.0
+    sc = _one_triangle_scene(to_world(5.375), to_world(7.125), 0.02)
+    cam = P.Camera(position=(0.0, 0.0, 2.5), front=(0.0, 0.0, -1.0))
+    p = P.default_params(64, 64, cam, sc.lights[0], voxel_min=-1.0, voxel_max=1.0)
+    p.voxelize_lighting = 0
+    o = ol.Oracle(sc, D, 3, 64, 64, 64)
+    o.voxelize(p)
+    assert o.info.total_fragments == 0 and not o.color[0].any()
+    p.conservative_raster = P.RASTER_MSAA
+    o.voxelize(p)
+    assert o.info.total_fragments == 1
+    (idx,) = np.nonzero(o.color[0])
+    assert len(idx) == 1
+    x, y, zc = int(idx[0]) % D, (int(idx[0]) // D) % D, int(idx[0]) // (D * D)
+    assert (x, y, zc) == (5, 7, 10)                            # z = 0.3 in a +-1 volume: (0.3 + 1) / 2 * 16 = 10.4
+    assert o.color[0][idx[0]] >> 24 == 1                       # one insertion into the running average
+    # every sample at the pixel centre: the centre-sampling result, whatever the scene
+    p.msaa_samples = (C.c_float * 8)(*([0.5] * 8))
+    o.voxelize(p)
+    assert o.info.total_fragments == 0
+    # a sample pattern is a parameter: move sample 0 away and the triangle is missed again
+    p.msaa_samples = (C.c_float * 8)(0.125, 0.875, 0.875, 0.375, 0.125, 0.625, 0.625, 0.875)
+    o.voxelize(p)
+    assert o.info.total_fragments == 0
+
+
+def test_msaa_is_a_superset_of_its_samples_and_centre_pattern_equals_off():
+    from vct_b200 import scene as S
+    sc = S.room_scene()
+    D, Lv, SS, W, H = 32, 4, 128, 64, 48
+    p = S.room_params(W, H)
+    o = ol.Oracle(sc, D, Lv, SS, W, H)
+    o.shadowmap(p); o.voxelize(p)
+    off_color, off_frags = o.color[0].copy(), o.info.total_fragments
+    q = type(p).from_buffer_copy(p); q.conservative_raster = P.RASTER_MSAA
+    o.voxelize(q)
+    assert o.info.total_fragments > off_frags * 1.05            # thin and grazing triangles gain fragments
+    assert ((off_color != 0) & (o.color[0] == 0)).sum() <= off_frags * 0.02   # nearly every centre-covered voxel is still hit
+    q.msaa_samples = (C.c_float * 8)(*([0.5] * 8))
+    o.voxelize(q)
+    assert o.info.total_fragments == off_frags and np.array_equal(o.color[0], off_color)
+    q.conservative_raster = P.RASTER_MSAA; q.warp_texture = 1; q.msaa_samples = (C.c_float * 8)(*([0.0] * 8))
+    o.occupancy(q)
+    occ_ms = o.occ.copy()
+    q.conservative_raster = P.RASTER_CENTER
+    o.occupancy(q)
+    assert (occ_ms != 0).sum() > (o.occ != 0).sum()             # the occupancy pass is multisampled too (Application.cpp:244-249)

@@ -195,6 +195,9 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     if (p->diffuse_cone.steps > 64 || p->specular_cone.steps > 64 || p->diffuse_cone.steps < 0 || p->specular_cone.steps < 0) return fail(c, "cone steps must be in [0,64]");
     if (p->voxel_fill_holes && c->cfg.world_size > 1)
         return fail(c, "voxelFillHoles reads the 3x3x3 neighbourhood across z-slab borders (voxelFillHoles.comp:8-36): not supported with world_size > 1");
+    if (p->conservative_raster != VCT_RASTER_CENTER && p->conservative_raster != VCT_RASTER_MSAA)
+        return fail(c, "conservative_raster: VCT_RASTER_CENTER or VCT_RASTER_MSAA (GL_CONSERVATIVE_RASTERIZATION_NV is not built)");
+    for (int i = 0; i < 8; ++i) if (!(p->msaa_samples[i] >= 0.0f && p->msaa_samples[i] < 1.0f)) return fail(c, "msaa_samples: positions are pixel fractions in [0, 1)");
     if (p->radiance_dilate) return fail(c, "radianceDilate is malformed in the reference (injectRadiance.comp:59-64) and is not supported");
     if (finalize_scene(c)) return 1;
     FrameConst& f = c->h_fc;

@@ -30,7 +30,12 @@ __device__ __forceinline__ int snap_coord(float ndc, int size) {
 __device__ __forceinline__ int cdiv256(long long a) { return (int)((a >= 0) ? (a + 255) / 256 : -((-a) / 256)); }
 __device__ __forceinline__ int fdiv256(long long a) { return (int)((a >= 0) ? a / 256 : -((-a + 255) / 256)); }
 
-__device__ __forceinline__ bool tri_setup(const RV v[3], int W, int H, bool cull_back, TriSetup& s) {
+// Sample positions of a raster pass in 1/256 pixel from the pixel's lower-left corner.  Pixel centres: n = 1 at (128, 128).  With
+// GL_MULTISAMPLE (the reference's default "conservative" voxelisation, Application.cpp:673-678) a fragment exists where ANY sample is
+// covered; x_min .. y_max bound the offsets for the pixel boxes.
+struct SampleSet { int n; int x[4], y[4]; int x_min, x_max, y_min, y_max; };
+
+__device__ __forceinline__ bool tri_setup(const RV v[3], int W, int H, bool cull_back, TriSetup& s, const SampleSet* ss = nullptr) {
     int X[3], Y[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {                                          // x / 1 == x exactly: orthographic views (w == 1) skip the IEEE division
@@ -54,8 +59,10 @@ __device__ __forceinline__ bool tri_setup(const RV v[3], int W, int H, bool cull
     }
     const int minx = min(s.X[0], min(s.X[1], s.X[2])), maxx = max(s.X[0], max(s.X[1], s.X[2]));
     const int miny = min(s.Y[0], min(s.Y[1], s.Y[2])), maxy = max(s.Y[0], max(s.Y[1], s.Y[2]));
-    s.x0 = max(0, cdiv256((long long)minx - 128)); s.x1 = min(W - 1, fdiv256((long long)maxx - 128));
-    s.y0 = max(0, cdiv256((long long)miny - 128)); s.y1 = min(H - 1, fdiv256((long long)maxy - 128));
+    // pixel p holds a sample inside [min, max] iff 256 p + offset does for some sample: lower bound from the largest offset, upper from the smallest
+    const int ox_hi = ss ? ss->x_max : 128, ox_lo = ss ? ss->x_min : 128, oy_hi = ss ? ss->y_max : 128, oy_lo = ss ? ss->y_min : 128;
+    s.x0 = max(0, cdiv256((long long)minx - ox_hi)); s.x1 = min(W - 1, fdiv256((long long)maxx - ox_lo));
+    s.y0 = max(0, cdiv256((long long)miny - oy_hi)); s.y1 = min(H - 1, fdiv256((long long)maxy - oy_lo));
     return s.x0 <= s.x1 && s.y0 <= s.y1;
 }
 
@@ -72,6 +79,38 @@ __device__ __forceinline__ bool tri_cover(const TriSetup& s, int px, int py, flo
     const float fa = (float)s.area;
     const float e0 = (float)E[0] / fa, e1 = (float)E[1] / fa, e2 = (float)E[2] / fa;
     l[0] = e0; l[1] = s.swapped ? e2 : e1; l[2] = s.swapped ? e1 : e2;
+    return true;
+}
+// Multisample coverage (OpenGL 4.5 section 14.6.6): true if any sample of pixel (px, py) is covered by the triangle clipped to -1 <= z <= 1
+// (the same top-left rule and the same barycentric formula per sample; z(sample) = sum l_i z_i like the centre's clip test).  l = the
+// barycentrics AT THE PIXEL CENTRE, where the fragment's inputs are interpolated — extrapolated if the centre itself is outside.
+__device__ __forceinline__ bool tri_cover_any(const TriSetup& s, int px, int py, const SampleSet& ss, float l[3]) {
+    const float fa = (float)s.area;
+    bool any = false;
+    for (int i = 0; i < ss.n; ++i) {
+        const long long Px = 256ll * px + ss.x[i], Py = 256ll * py + ss.y[i];
+        long long E[3]; bool in = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int a = (k + 1) % 3, b = (k + 2) % 3;
+            E[k] = (long long)(s.X[b] - s.X[a]) * (Py - s.Y[a]) - (long long)(s.Y[b] - s.Y[a]) * (Px - s.X[a]);
+            in = in && E[k] + s.bias[k] >= 0;
+        }
+        if (!in) continue;
+        const float e0 = (float)E[0] / fa, e1 = (float)E[1] / fa, e2 = (float)E[2] / fa;
+        const float z = (e0 * s.z[0] + (s.swapped ? e2 : e1) * s.z[1]) + (s.swapped ? e1 : e2) * s.z[2];
+        if (z < -1.0f || z > 1.0f) continue;
+        any = true;
+    }
+    if (!any) return false;
+    const long long Px = 256ll * px + 128, Py = 256ll * py + 128;
+    float e[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+        e[k] = (float)((long long)(s.X[b] - s.X[a]) * (Py - s.Y[a]) - (long long)(s.Y[b] - s.Y[a]) * (Px - s.X[a])) / fa;
+    }
+    l[0] = e[0]; l[1] = s.swapped ? e[2] : e[1]; l[2] = s.swapped ? e[1] : e[2];
     return true;
 }
 // ---------------------------------------------------------------------------------------- tile work queue
@@ -107,14 +146,15 @@ __device__ __forceinline__ bool tile_owned(const TileQueues& q, int ox, int oy, 
     return pixel_owned(q, ox, oy) || pixel_owned(q, ex, oy) || pixel_owned(q, ox, ey) || pixel_owned(q, ex, ey);
 }
 
-// Is the pixel-centre box [bx0,bx1]x[by0,by1] entirely outside one of the edges?
-__device__ __forceinline__ bool tile_rejected(const TriSetup& s, int bx0, int by0, int bx1, int by1) {
+// Is the box of sample points of pixels [bx0,bx1]x[by0,by1] (pixel centres without a sample set) entirely outside one of the edges?
+__device__ __forceinline__ bool tile_rejected(const TriSetup& s, int bx0, int by0, int bx1, int by1, const SampleSet* ss = nullptr) {
+    const int ox_hi = ss ? ss->x_max : 128, ox_lo = ss ? ss->x_min : 128, oy_hi = ss ? ss->y_max : 128, oy_lo = ss ? ss->y_min : 128;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int a = (k + 1) % 3, b = (k + 2) % 3;
         const long long ex = s.X[b] - s.X[a], ey = s.Y[b] - s.Y[a];
         // E = ex*(Py - Ya) - ey*(Px - Xa) is maximised at Py = (ex>0 ? top : bottom), Px = (ey>0 ? left : right)
-        const long long Py = 256ll * (ex > 0 ? by1 : by0) + 128, Px = 256ll * (ey > 0 ? bx0 : bx1) + 128;
+        const long long Py = ex > 0 ? 256ll * by1 + oy_hi : 256ll * by0 + oy_lo, Px = ey > 0 ? 256ll * bx0 + ox_lo : 256ll * bx1 + ox_hi;
         if (ex * (Py - s.Y[a]) - ey * (Px - s.X[a]) + s.bias[k] < 0) return true;
     }
     return false;

@@ -67,6 +67,7 @@ struct VoxArgs {
     Frag* frags; unsigned frag_cap; uint8_t* displaced;       // displaced[slot] = 1: a later fragment took over the head of that voxel's list
     uint32_t *color, *normal, *occ;
     uint8_t* seg;             // segment mask of this frame (common.cuh): one byte per 8 voxels of an x-row
+    int msaa; SampleSet ms;   // Settings::conservativeRasterization == MSAA: any-sample coverage (raster.cuh tri_cover_any)
     int slab_cull;            // multi-GPU, linear mapping: triangles that cannot touch this rank's z-slab stop at the bin kernel
     Counters* counters;
 };
@@ -124,16 +125,19 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
         // Early out for the 80-90 % of triangles whose pixel box holds no pixel centre.  The snapped window coordinate differs from
         // (ndc * 0.5 + 0.5) * D by at most 1/512 pixel, so with a margin of 1/128 pixel an empty float box proves the exact box
         // [ceil(min - 0.5), floor(max - 0.5)] of tri_setup empty; everything else (and every NaN) takes the exact path.
+        // (multisampling: the box of sample points instead — smallest offset at the upper end, largest at the lower)
         const float fd = (float)a.D, e = 0.0078125f;
+        const float ox_lo = a.msaa ? (float)a.ms.x_min * 0.00390625f : 0.5f, ox_hi = a.msaa ? (float)a.ms.x_max * 0.00390625f : 0.5f;
+        const float oy_lo = a.msaa ? (float)a.ms.y_min * 0.00390625f : 0.5f, oy_hi = a.msaa ? (float)a.ms.y_max * 0.00390625f : 0.5f;
         const float x0 = (cv[0].x * 0.5f + 0.5f) * fd, x1 = (cv[1].x * 0.5f + 0.5f) * fd, x2 = (cv[2].x * 0.5f + 0.5f) * fd;
         const float y0 = (cv[0].y * 0.5f + 0.5f) * fd, y1 = (cv[1].y * 0.5f + 0.5f) * fd, y2 = (cv[2].y * 0.5f + 0.5f) * fd;
         const float sum = ((x0 + x1) + x2) + ((y0 + y1) + y2);             // NaN or infinite anywhere: fminf / fmaxf would hide it, take the exact path
         if (fabsf(sum) < 1e30f) {
-            if (floorf(fmaxf(x0, fmaxf(x1, x2)) - 0.5f + e) < ceilf(fminf(x0, fminf(x1, x2)) - 0.5f - e)) return false;
-            if (floorf(fmaxf(y0, fmaxf(y1, y2)) - 0.5f + e) < ceilf(fminf(y0, fminf(y1, y2)) - 0.5f - e)) return false;
+            if (floorf(fmaxf(x0, fmaxf(x1, x2)) - ox_lo + e) < ceilf(fminf(x0, fminf(x1, x2)) - ox_hi - e)) return false;
+            if (floorf(fmaxf(y0, fmaxf(y1, y2)) - oy_lo + e) < ceilf(fminf(y0, fminf(y1, y2)) - oy_hi - e)) return false;
         }
     }
-    if (!tri_setup(cv, a.D, a.D, false, S.s)) return false;
+    if (!tri_setup(cv, a.D, a.D, false, S.s, a.msaa ? &a.ms : nullptr)) return false;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { S.cvx[k] = cv[k].x; S.cvy[k] = cv[k].y; S.s.z[k] = cv[k].z; }   // the shader interpolates gl_Position.xyz (w == 1)
     S.tri = t; S.axis = axis; S.material = 0; S.rho2 = 0.0f;
@@ -166,12 +170,16 @@ __device__ __forceinline__ bool frag_voxel(const FrameConst& fc, const VoxHead& 
     else if (fc.p.warp_texture && !occupancy) u = warp_sample(warpmap, u);
     return to_voxel_index(mk3((float)D * u.x, (float)D * u.y, (float)D * u.z), D, ix, iy, iz);
 }
-// fragment exists (coverage + near/far clip) and belongs to this rank's slab
+// fragment exists (coverage + near/far clip) and belongs to this rank's slab.  MS: any-sample coverage, near/far clip per sample
+template <bool MS>
 __device__ __forceinline__ bool frag_test(const FrameConst& fc, const VoxHead& S, int px, int py, int D, const uint16_t* __restrict__ warpmap, bool occupancy,
-                                          float l[3], bool& oob, int& ix, int& iy, int& iz) {
-    if (!tri_cover(S.s, px, py, l)) return false;
-    const float z = interp1(l, S.s.z[0], S.s.z[1], S.s.z[2]);
-    if (z < -1.0f || z > 1.0f) return false;
+                                          const SampleSet& ms, float l[3], bool& oob, int& ix, int& iy, int& iz) {
+    if (MS) { if (!tri_cover_any(S.s, px, py, ms, l)) return false; }
+    else {
+        if (!tri_cover(S.s, px, py, l)) return false;
+        const float z = interp1(l, S.s.z[0], S.s.z[1], S.s.z[2]);
+        if (z < -1.0f || z > 1.0f) return false;
+    }
     oob = !frag_voxel(fc, S, l, D, warpmap, occupancy, ix, iy, iz);
     if (occupancy) return true;                                           // the 32^3 occupancy grid is not sharded: every rank builds all of it
     if (oob) return fc.st.rank == 0;                                      // counted once, by the rank owning z = 0
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_voxel_bin(VoxArgs a) {
                     const int tntx = (ts.x1 - ts.x0 + kTileW) / kTileW;
                     const int local = (int)(c - s_pref[lo]), ty = local / tntx, tx = local - ty * tntx;
                     ox = ts.x0 + tx * kTileW; oy = ts.y0 + ty * kTileH;
-                    keep = !tile_rejected(ts, ox, oy, min(ox + kTileW - 1, ts.x1), min(oy + kTileH - 1, ts.y1));
+                    keep = !tile_rejected(ts, ox, oy, min(ox + kTileW - 1, ts.x1), min(oy + kTileH - 1, ts.y1), a.msaa ? &a.ms : nullptr);
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 if (!m) continue;
@@ -398,7 +406,7 @@ __device__ __noinline__ void shade_batch(const VoxArgs& a, const FrameConst& fc,
     store_fragment<MODE>(a, tri, sh, a.D, (int)(h.pxy & 0xFFFFu), (int)(h.pxy >> 16), (int)(h.vox & 1023u), (int)((h.vox >> 10) & 1023u), (int)(h.vox >> 20), base + (uint32_t)lane,
                          n >= 32 ? 0xffffffffu : (1u << n) - 1u);
 }
-template <int MODE>
+template <int MODE, bool MS>
 __global__ void __launch_bounds__(kThreads, 4) k_voxel_tiles(VoxArgs a) {
     const FrameConst& fc = *a.fc;
     __shared__ Hit s_ring[kThreads / 32][kRing];
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_voxel_tiles(VoxArgs a) {
         bool frag = false;
         if (cv) {
             const VoxHead S = a.setups[slot];
-            frag = px <= S.s.x1 && py <= S.s.y1 && frag_test(fc, S, px, py, D, a.warpmap, occupancy, l, oob, ix, iy, iz);
+            frag = px <= S.s.x1 && py <= S.s.y1 && frag_test<MS>(fc, S, px, py, D, a.warpmap, occupancy, a.ms, l, oob, ix, iy, iz);
         }
         const bool hit = frag && !oob;
         if (frag) counted++;
@@ -932,7 +940,10 @@ template <int MODE>
 int run_mode(vct_ctx* c, const VoxArgs& a, const char* bin_name, const char* tiles_name) {
     const int grid = (int)std::min<size_t>((c->n_tris + kThreads - 1) / kThreads, (size_t)VCT_SM_COUNT * 16);
     k_voxel_bin<MODE><<<grid, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, bin_name);
-    k_voxel_tiles<MODE><<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a); VCT_LAUNCH_CHECK(c, tiles_name);   // one resident wave (4 CTAs per SM at 64 registers): the warps share the queues round-robin
+    // one resident wave (4 CTAs per SM at 64 registers): the warps share the queues round-robin
+    if (a.msaa) k_voxel_tiles<MODE, true><<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a);
+    else k_voxel_tiles<MODE, false><<<VCT_SM_COUNT * 4, kThreads, 0, c->stream>>>(a);
+    VCT_LAUNCH_CHECK(c, tiles_name);
     return 0;
 }
 
@@ -982,7 +993,23 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset, bool 
     // the three ortho views reproduce the linear mapping only for a symmetric cube: cull only then
     const bool cube = p.voxel_min[0] == -p.voxel_max[0] && p.voxel_min[1] == -p.voxel_max[1] && p.voxel_min[2] == -p.voxel_max[2] &&
                       p.voxel_max[0] == p.voxel_max[1] && p.voxel_max[1] == p.voxel_max[2] && p.voxel_max[0] > 0.0f;
-    a.slab_cull = !occupancy && c->cfg.world_size > 1 && !p.warp_voxels && !p.warp_texture && cube && p.axis_override < 0;
+    // Settings::conservativeRasterization == MSAA (both voxelisation passes, Application.cpp:244-249, 673-678): sample offsets in 1/256 pixel
+    a.msaa = p.conservative_raster == VCT_RASTER_MSAA;
+    a.ms = SampleSet{};
+    if (a.msaa) {
+        static const float standard4x[8] = {0.375f, 0.125f, 0.875f, 0.375f, 0.125f, 0.625f, 0.625f, 0.875f};
+        bool given = false;
+        for (int i = 0; i < 8; ++i) given = given || p.msaa_samples[i] != 0.0f;
+        const float* sp = given ? p.msaa_samples : standard4x;
+        a.ms.n = 4; a.ms.x_min = a.ms.y_min = 256; a.ms.x_max = a.ms.y_max = 0;
+        for (int i = 0; i < 4; ++i) {
+            a.ms.x[i] = std::min(255, std::max(0, (int)lrintf(sp[2 * i] * 256.0f))); a.ms.y[i] = std::min(255, std::max(0, (int)lrintf(sp[2 * i + 1] * 256.0f)));
+            a.ms.x_min = std::min(a.ms.x_min, a.ms.x[i]); a.ms.x_max = std::max(a.ms.x_max, a.ms.x[i]);
+            a.ms.y_min = std::min(a.ms.y_min, a.ms.y[i]); a.ms.y_max = std::max(a.ms.y_max, a.ms.y[i]);
+        }
+    }
+    // (a multisampled fragment's inputs are extrapolated to the pixel centre: its voxel can lie outside the triangle's padded box, so no slab cull then)
+    a.slab_cull = !occupancy && c->cfg.world_size > 1 && !p.warp_voxels && !p.warp_texture && cube && p.axis_override < 0 && !a.msaa;
     if (!counters_already_reset) { k_voxel_reset<<<1, 1, 0, c->stream>>>(c->d_counters); VCT_LAUNCH_CHECK(c, "k_voxel_reset"); }
     if (occupancy) {
         VCT_CHECK(c, cudaMemsetAsync(c->d_occ, 0, sizeof(uint32_t) * VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM, c->stream));

@@ -101,6 +101,9 @@ struct Settings {
     float miplevel = 0.0f;
     int voxelizeTesselation = false;    // Application.h:85 (reference default true; this host defaults to the north star's raster path)
     int voxelizeTesselationWarp = false;   // Application.h:102: the camera frustum as voxel grid (common.glsl:37-42)
+    // Application.h:61-62 (reference default MSAA; this host defaults to OFF = the north star's parity mode); NV is not built
+    enum ConservativeRasterizeMode { OFF, MSAA, NV };
+    int conservativeRasterization = OFF;
     int voxelTrackCamera = false;          // Application.h:86: the volume follows the camera, snapped to the coarsest mip cell (Application.cpp:187-191)
     int cooktorrance = true, enablePostprocess = true, enableNormalMap = true;
     int enableIndirect = true, enableDiffuse = true, enableSpecular = true, enableReflections = true;
@@ -318,6 +321,7 @@ public:
         p.miplevel = s.miplevel;
         p.voxelize_tesselation = s.voxelizeTesselation;
         p.voxelize_tesselation_warp = s.voxelizeTesselationWarp;
+        p.conservative_raster = s.conservativeRasterization == Settings::MSAA ? VCT_RASTER_MSAA : VCT_RASTER_CENTER;   // msaa_samples all zero: standard 4x pattern
         return p;
     }
 

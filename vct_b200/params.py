@@ -86,7 +86,12 @@ class FrameParams(C.Structure):
         ("diffuse_cone", ConeSettings), ("specular_cone", ConeSettings),
         ("specular_cone_angle_from_roughness", C.c_int),
         ("debug_view", C.c_int), ("miplevel", C.c_float), ("voxelize_tesselation", C.c_int), ("voxelize_tesselation_warp", C.c_int),
+        ("conservative_raster", C.c_int), ("msaa_samples", C.c_float * 8),
     ]
+
+
+RASTER_CENTER, RASTER_MSAA = 0, 1
+MSAA_STANDARD_4X = (0.375, 0.125, 0.875, 0.375, 0.125, 0.625, 0.625, 0.875)   # glGetMultisamplefv on NVIDIA GL / the D3D standard pattern
 
 
 class Timings(C.Structure):
