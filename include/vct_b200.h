@@ -141,6 +141,11 @@ typedef struct {
      * (GL_CONSERVATIVE_RASTERIZATION_NV) is not built. */
     int   conservative_raster;
     float msaa_samples[8];
+    /* Settings::voxelizeMultiplier (Application.h:87, default 1; the overlay's slider goes from 0.5 to 4): the voxelise pass rasterises into a
+     * viewport of (int)(m * dim) pixels squared (Application.cpp:668) while the voxel index still comes from the interpolated position times
+     * dim — m = 2 gives every voxel four times the fragments.  0 reads as 1.  (The occupancy pass keeps its 32^2 viewport, :239.  Not
+     * replicated: the reference draws into the WINDOW's framebuffer, which cuts a viewport taller than the window.) */
+    float voxelize_multiplier;
 } vct_frame_params;
 enum { VCT_RASTER_CENTER = 0, VCT_RASTER_MSAA = 1 };
 

@@ -601,6 +601,9 @@ static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D
     }
     unsigned total = 0;
     Samples ms; const bool msaa = msaa_samples(fp, ms);
+    // Settings::voxelizeMultiplier: glViewport(0, 0, m * voxelDim, m * voxelDim) (Application.cpp:668; float -> GLsizei truncates); the voxel
+    // index still comes from the interpolated position times imageSize (voxelize.frag:79-108)
+    const int V = fp->voxelize_multiplier > 0.0f ? (int)(fp->voxelize_multiplier * (float)D) : D;
     for (int t = 0; t < sc->n_tris; ++t) {
         const unsigned* ix = sc->indices + 3 * (size_t)t;
         V3 n[3] = {P.wnrm[ix[0]], P.wnrm[ix[1]], P.wnrm[ix[2]]}, w[3] = {P.wpos[ix[0]], P.wpos[ix[1]], P.wpos[ix[2]]};
@@ -610,11 +613,11 @@ static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D
             V4 c = mul(va.mvp, {w[k].x, w[k].y, w[k].z, 1.0f}); cv[k] = {c.x, c.y, c.z, c.w};
             uv[k][0] = sc->vertices[14 * (size_t)ix[k] + 6]; uv[k][1] = sc->vertices[14 * (size_t)ix[k] + 7];
         }
-        Setup s = tri_setup(cv, D, D, false, msaa ? &ms : nullptr);
+        Setup s = tri_setup(cv, V, V, false, msaa ? &ms : nullptr);
         if (!s.valid) continue;
         const vct_material& mat = sc->materials[sc->tri_material[t]];
         const Tex* dt = mat.diffuse_tex >= 0 ? &P.tex[mat.diffuse_tex] : nullptr;
-        const float rho2 = dt ? tri_rho2_affine(cv, uv, D, D, *dt) : 0.0f;
+        const float rho2 = dt ? tri_rho2_affine(cv, uv, V, V, *dt) : 0.0f;
         auto frag = [&](int, int, const float l[3]) {
             V3 ndc = {interp(l, cv[0].x, cv[1].x, cv[2].x), interp(l, cv[0].y, cv[1].y, cv[2].y), interp(l, cv[0].z, cv[1].z, cv[2].z)};
             if (!msaa && (ndc.z < -1.0f || ndc.z > 1.0f)) return;       // near/far clip of the ortho volume (multisampling: per sample, in the rasteriser)
@@ -670,7 +673,7 @@ static void voxelize_impl(const orc_scene* sc, const vct_frame_params* fp, int D
             }
         };
         const float zs[3] = {cv[0].z, cv[1].z, cv[2].z};
-        if (msaa) raster_any_sample(s, ms, zs, frag); else raster(s, 0, D - 1, frag);
+        if (msaa) raster_any_sample(s, ms, zs, frag); else raster(s, 0, V - 1, frag);
     }
     if (info) { info->total_fragments = total; info->unique_voxels = 0; info->max_fragments_per_voxel = 0; }
     if (frag_count) *frag_count = total;

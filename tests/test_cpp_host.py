@@ -103,7 +103,7 @@ int main(int argc, char** argv) {
         s.enableIndirect = 0; s.enableDiffuse = 0; s.enableSpecular = 0; s.enableReflections = 0; s.ambientScale = 0.5f; s.reflectScale = 2.0f;
         s.diffuseConeSettings.steps = 9; s.specularConeSettings.bias = 2.5f; s.specularConeAngleFromRoughness = 0;
         s.debugOcclusion = 1; s.drawNormals = 1;          // the shader tests drawNormals first
-        s.miplevel = 1.5f; s.voxelizeTesselation = 1; s.voxelizeTesselationWarp = 1;
+        s.miplevel = 1.5f; s.voxelizeTesselation = 1; s.voxelizeTesselationWarp = 1; s.voxelizeMultiplier = 2.0f; s.conservativeRasterization = Settings::MSAA;
     }
     const vct_frame_params p = app.frameParams();
     std::fwrite(&p, sizeof p, 1, stdout);
@@ -136,7 +136,7 @@ def test_cpp_host_frame_parameters_equal_the_python_mirror(tmp_path):
                              warp_texture_high_resolution=3.0, warp_texture_low_resolution=0.25, draw_radiance=0, draw_occlusion=0, cooktorrance=0,
                              enable_postprocess=0, enable_normal_map=0, enable_indirect=0, enable_diffuse=0, enable_specular=0, enable_reflections=0,
                              ambient_scale=0.5, reflect_scale=2.0, specular_cone_angle_from_roughness=0, debug_view=P.VIEW_NORMALS, miplevel=1.5,
-                             voxelize_tesselation=1, voxelize_tesselation_warp=1).items():
+                             voxelize_tesselation=1, voxelize_tesselation_warp=1, voxelize_multiplier=2.0, conservative_raster=P.RASTER_MSAA).items():
                 setattr(want, k, v)
             want.warp_texture_axes[1] = 0; want.diffuse_cone.steps = 9; want.specular_cone.bias = 2.5
         seen = 0

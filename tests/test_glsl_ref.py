@@ -206,6 +206,8 @@ FRAG_MODES = {
     "atomic_max": {"voxelize_atomic_max": 1},
     # Settings::conservativeRasterization == MSAA: fragments wherever any of the 4 samples is covered, inputs extrapolated to the pixel centre
     "msaa": {"conservative_raster": 1},
+    # Settings::voxelizeMultiplier: a 1.5 x dim viewport (texture LOD and fragment count follow the viewport, the voxel index does not)
+    "multiplier_1p5": {"voxelize_multiplier": 1.5},
     "no_voxel_lighting": {"voxelize_lighting": 0},
     "warp_voxels": {"warp_voxels": 1},
     "warp_texture": {"warp_texture": 1},

@@ -258,3 +258,25 @@ def test_msaa_voxelisation_bit_exact(room):
     with pytest.raises(VctError):
         g.frame(q)
     g.frame(p)
+
+
+def test_voxelize_multiplier_bit_exact(room):
+    """Settings::voxelizeMultiplier (Application.cpp:668): the voxelise pass in a viewport of (int)(m * dim) pixels squared — more (or fewer)
+    fragments per voxel, canonical order by (triangle, raster rank in THAT viewport), texture LOD from that viewport's derivatives.  Volumes,
+    pyramid and counters equal the oracle's for m = 2, 1.5 and 0.5, with and without multisampling, dense and sparse frame."""
+    sc, p, o, g = room
+    for m, msaa in ((2.0, 0), (1.5, 1), (0.5, 0)):
+        q = type(p).from_buffer_copy(p); q.voxelize_multiplier = m; q.conservative_raster = msaa
+        for frame in range(2):
+            o.frame(q); g.frame(q)
+            assert np.array_equal(g.read_volume(P.VOL_COLOR), o.color[0]), (m, frame)
+            assert np.array_equal(g.read_volume(P.VOL_NORMAL), o.normal), (m, frame)
+            for l in range(L):
+                assert np.array_equal(g.read_volume(P.VOL_RADIANCE, l), o.radiance[l]), (m, frame, l)
+            i = g.counters()
+            assert (i.total_fragments, i.unique_voxels, i.max_fragments_per_voxel) == (o.info.total_fragments, o.info.unique_voxels, o.info.max_fragments_per_voxel), (m, frame)
+    from vct_b200.lib import VctError
+    q = type(p).from_buffer_copy(p); q.voxelize_multiplier = -1.0
+    with pytest.raises(VctError):
+        g.frame(q)
+    g.frame(p)

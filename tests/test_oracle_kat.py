@@ -337,3 +337,26 @@ def test_msaa_is_a_superset_of_its_samples_and_centre_pattern_equals_off():
     q.conservative_raster = P.RASTER_CENTER
     o.occupancy(q)
     assert (occ_ms != 0).sum() > (o.occ != 0).sum()             # the occupancy pass is multisampled too (Application.cpp:244-249)
+
+
+def test_voxelize_multiplier_scales_the_viewport_not_the_grid():
+    """Settings::voxelizeMultiplier (Application.cpp:668): m * dim pixels per side, voxel index from the interpolated position: m = 2 gives about
+    four times the fragments in (nearly) the same voxels; 0 reads as 1."""
+    from vct_b200 import scene as S
+    sc = S.room_scene()
+    D, Lv, SS, W, H = 32, 4, 128, 64, 48
+    p = S.room_params(W, H); p.voxelize_atomic_max = 1
+    o = ol.Oracle(sc, D, Lv, SS, W, H)
+    o.shadowmap(p); o.voxelize(p)
+    base, n1 = o.color[0].copy(), o.info.total_fragments
+    p.voxelize_multiplier = 1.0
+    o.voxelize(p)
+    assert o.info.total_fragments == n1 and np.array_equal(o.color[0], base)
+    p.voxelize_multiplier = 2.0
+    o.voxelize(p)
+    assert 3.6 * n1 < o.info.total_fragments < 4.4 * n1
+    assert ((base != 0) & (o.color[0] == 0)).sum() == 0          # on this scene every voxel of the coarse pass is hit again (no theorem: slivers can slip between samples)
+    assert (o.color[0] != 0).sum() >= (base != 0).sum()
+    p.voxelize_multiplier = 0.5
+    o.voxelize(p)
+    assert 0.2 * n1 < o.info.total_fragments < 0.3 * n1

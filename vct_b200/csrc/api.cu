@@ -195,6 +195,8 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     if (p->diffuse_cone.steps > 64 || p->specular_cone.steps > 64 || p->diffuse_cone.steps < 0 || p->specular_cone.steps < 0) return fail(c, "cone steps must be in [0,64]");
     if (p->voxel_fill_holes && c->cfg.world_size > 1)
         return fail(c, "voxelFillHoles reads the 3x3x3 neighbourhood across z-slab borders (voxelFillHoles.comp:8-36): not supported with world_size > 1");
+    if (!(p->voxelize_multiplier >= 0.0f && p->voxelize_multiplier <= 8.0f) || (p->voxelize_multiplier > 0.0f && (int)(p->voxelize_multiplier * (float)c->D) < 1))
+        return fail(c, "voxelize_multiplier: 0 (= 1) or a factor up to 8 that leaves a viewport of at least one pixel");
     if (p->conservative_raster != VCT_RASTER_CENTER && p->conservative_raster != VCT_RASTER_MSAA)
         return fail(c, "conservative_raster: VCT_RASTER_CENTER or VCT_RASTER_MSAA (GL_CONSERVATIVE_RASTERIZATION_NV is not built)");
     for (int i = 0; i < 8; ++i) if (!(p->msaa_samples[i] >= 0.0f && p->msaa_samples[i] < 1.0f)) return fail(c, "msaa_samples: positions are pixel fractions in [0, 1)");

@@ -60,6 +60,7 @@ __device__ __forceinline__ V3 ld3(const float4* __restrict__ p, uint32_t i) { co
 
 struct VoxArgs {
     const FrameConst* fc; int D;
+    int V;                    // viewport of the raster pass in pixels: (int)(voxelizeMultiplier * D) for the voxelise pass (Application.cpp:668), D otherwise
     const uint32_t* indices; const int32_t* trimat; const float* verts; uint32_t n_tris;
     const float4 *wpos, *wnrm;
     const DevTexture* tex; const DevMaterial* mats; const float* shadow; const uint16_t* warpmap;
@@ -126,7 +127,7 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
         // (ndc * 0.5 + 0.5) * D by at most 1/512 pixel, so with a margin of 1/128 pixel an empty float box proves the exact box
         // [ceil(min - 0.5), floor(max - 0.5)] of tri_setup empty; everything else (and every NaN) takes the exact path.
         // (multisampling: the box of sample points instead — smallest offset at the upper end, largest at the lower)
-        const float fd = (float)a.D, e = 0.0078125f;
+        const float fd = (float)a.V, e = 0.0078125f;
         const float ox_lo = a.msaa ? (float)a.ms.x_min * 0.00390625f : 0.5f, ox_hi = a.msaa ? (float)a.ms.x_max * 0.00390625f : 0.5f;
         const float oy_lo = a.msaa ? (float)a.ms.y_min * 0.00390625f : 0.5f, oy_hi = a.msaa ? (float)a.ms.y_max * 0.00390625f : 0.5f;
         const float x0 = (cv[0].x * 0.5f + 0.5f) * fd, x1 = (cv[1].x * 0.5f + 0.5f) * fd, x2 = (cv[2].x * 0.5f + 0.5f) * fd;
@@ -137,7 +138,7 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
             if (floorf(fmaxf(y0, fmaxf(y1, y2)) - oy_lo + e) < ceilf(fminf(y0, fminf(y1, y2)) - oy_hi - e)) return false;
         }
     }
-    if (!tri_setup(cv, a.D, a.D, false, S.s, a.msaa ? &a.ms : nullptr)) return false;
+    if (!tri_setup(cv, a.V, a.V, false, S.s, a.msaa ? &a.ms : nullptr)) return false;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { S.cvx[k] = cv[k].x; S.cvy[k] = cv[k].y; S.s.z[k] = cv[k].z; }   // the shader interpolates gl_Position.xyz (w == 1)
     S.tri = t; S.axis = axis; S.material = 0; S.rho2 = 0.0f;
@@ -155,7 +156,7 @@ __device__ __forceinline__ void make_shading_setup(const VoxArgs& a, VoxSetup& S
     }
     const int dt = a.mats[S.material].diffuse_tex;
     if (dt < 0) return;
-    S.rho2 = tri_rho2_affine(cv, S.in.uv, a.D, a.D, a.tex[dt]);
+    S.rho2 = tri_rho2_affine(cv, S.in.uv, a.V, a.V, a.tex[dt]);
 }
 
 // voxelize.frag:79-108
@@ -251,7 +252,7 @@ __device__ __forceinline__ void store_fragment(const VoxArgs& a, uint32_t tri, c
     a.seg[o >> 3] = 1;                                                      // every writer stores the same byte
     if (MODE == MODE_SORTED) {
         Frag f;
-        f.key = o; f.tri = tri; f.rank = (uint32_t)(py * D + px);
+        f.key = o; f.tri = tri; f.rank = (uint32_t)(py * a.V + px);
         // Warp-aggregated push: the lanes of this batch that hit the same voxel chain their records among themselves (slots are
         // consecutive: base + lane) and only the first of them touches the voxel — one atomicExch on the list head and one
         // atomicAdd on the fragment count (kept in voxelNormal until the resolve overwrites it) per voxel per warp.
@@ -984,6 +985,7 @@ int vctk_voxelize(vct_ctx* c, bool occupancy, bool counters_already_reset, bool 
     const vct_frame_params& p = c->h_fc.p;
     VoxArgs a{};
     a.fc = c->d_fc; a.D = occupancy ? VCT_WARP_DIM : c->D;
+    a.V = occupancy || !(p.voxelize_multiplier > 0.0f) ? a.D : (int)(p.voxelize_multiplier * (float)a.D);
     a.indices = c->d_indices; a.trimat = c->d_trimat; a.verts = c->d_vertices; a.n_tris = (uint32_t)c->n_tris;
     a.wpos = c->d_wpos; a.wnrm = c->d_wnrm; a.tex = c->d_tex; a.mats = c->d_mat; a.shadow = c->d_shadow; a.warpmap = c->d_warpmap;
     a.setups = reinterpret_cast<VoxSetup*>(c->d_setup); a.setup_cap = (unsigned)c->setup_cap;

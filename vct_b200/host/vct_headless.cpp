@@ -5,7 +5,7 @@
 //
 //   vct_headless scene.vcts|mesh.obj [--scale s] [--resources dir] [--dim 256] [--levels 6] [--size 1920x1080] [--shadow 4096] [--frames 3]
 //                [--camera x y z yaw pitch | --eye x y z --front fx fy fz] [--volume min max] [--center x y z]
-//                [--no-reflections] [--atomic-max] [--msaa] [--tesselation] [--tesselation-warp] [--warp-texture] [--warp-voxels] [--temporal] [--fused] [--out frame.ppm]
+//                [--no-reflections] [--atomic-max] [--msaa] [--voxelize-multiplier M] [--tesselation] [--tesselation-warp] [--warp-texture] [--warp-voxels] [--temporal] [--fused] [--out frame.ppm]
 //                [--gpus N] (one process driving N devices: z-slab sharded frames, image on device 0) [--track-camera]
 // Exit status: 0 ok, 1 a pass reported an error (message on stderr), 2 usage.  There is no CPU fallback: without a
 // CUDA device vct_create fails and the driver exits 1.
@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
         std::fprintf(argc < 2 ? stderr : stdout,
                      "usage: vct_headless scene.vcts|mesh.obj [--scale s] [--resources dir] [--dim D] [--levels L] [--size WxH] [--shadow S] [--frames N]\n"
                      "       [--camera x y z yaw pitch | --eye x y z --front fx fy fz] [--volume min max] [--center x y z]\n"
-                     "       [--no-reflections] [--atomic-max] [--msaa] [--tesselation] [--tesselation-warp] [--warp-texture] [--warp-voxels] [--temporal] [--fused] [--out frame.ppm]\n"
+                     "       [--no-reflections] [--atomic-max] [--msaa] [--voxelize-multiplier M] [--tesselation] [--tesselation-warp] [--warp-texture] [--warp-voxels] [--temporal] [--fused] [--out frame.ppm]\n"
                      "       [--gpus N] [--track-camera]\n"
                      "       [--view voxels|normals|dominant-axis|occlusion|indirect|reflections|material-diffuse|material-roughness|material-metallic] [--miplevel x]\n");
         return argc < 2 ? 2 : 0;
@@ -58,6 +58,7 @@ int main(int argc, char** argv) {
         else if (a == "--center") { need(i, 3); app.vct.center = {(float)std::atof(argv[i + 1]), (float)std::atof(argv[i + 2]), (float)std::atof(argv[i + 3])}; i += 3; }
         else if (a == "--no-reflections") app.settings.enableReflections = false;
         else if (a == "--atomic-max") app.settings.voxelizeAtomicMax = true;
+        else if (a == "--voxelize-multiplier") { need(i, 1); app.settings.voxelizeMultiplier = (float)std::atof(argv[++i]); }   // Settings::voxelizeMultiplier
         else if (a == "--msaa") app.settings.conservativeRasterization = Settings::MSAA;   // Settings::conservativeRasterization = MSAA (the reference's default)
         else if (a == "--tesselation") app.settings.voxelizeTesselation = true;   // the reference's default voxeliser (with --atomic-max: its default frame)
         else if (a == "--tesselation-warp") app.settings.voxelizeTesselationWarp = true;   // Settings::voxelizeTesselationWarp (with --tesselation: the frustum-aligned grid)

@@ -104,6 +104,7 @@ struct Settings {
     // Application.h:61-62 (reference default MSAA; this host defaults to OFF = the north star's parity mode); NV is not built
     enum ConservativeRasterizeMode { OFF, MSAA, NV };
     int conservativeRasterization = OFF;
+    float voxelizeMultiplier = 1.0f;       // Application.h:87: viewport of the voxelise pass = multiplier * voxelDim (Application.cpp:668)
     int voxelTrackCamera = false;          // Application.h:86: the volume follows the camera, snapped to the coarsest mip cell (Application.cpp:187-191)
     int cooktorrance = true, enablePostprocess = true, enableNormalMap = true;
     int enableIndirect = true, enableDiffuse = true, enableSpecular = true, enableReflections = true;
@@ -321,6 +322,7 @@ public:
         p.miplevel = s.miplevel;
         p.voxelize_tesselation = s.voxelizeTesselation;
         p.voxelize_tesselation_warp = s.voxelizeTesselationWarp;
+        p.voxelize_multiplier = s.voxelizeMultiplier;
         p.conservative_raster = s.conservativeRasterization == Settings::MSAA ? VCT_RASTER_MSAA : VCT_RASTER_CENTER;   // msaa_samples all zero: standard 4x pattern
         return p;
     }

@@ -86,7 +86,7 @@ class FrameParams(C.Structure):
         ("diffuse_cone", ConeSettings), ("specular_cone", ConeSettings),
         ("specular_cone_angle_from_roughness", C.c_int),
         ("debug_view", C.c_int), ("miplevel", C.c_float), ("voxelize_tesselation", C.c_int), ("voxelize_tesselation_warp", C.c_int),
-        ("conservative_raster", C.c_int), ("msaa_samples", C.c_float * 8),
+        ("conservative_raster", C.c_int), ("msaa_samples", C.c_float * 8), ("voxelize_multiplier", C.c_float),
     ]
 
 
@@ -264,4 +264,6 @@ def default_params(width, height, camera, light, voxel_min=-20.0, voxel_max=20.0
     p.diffuse_cone = ConeSettings(16, math.radians(60.0), 1.0, 1.0, 0.5)       # Application.h:96
     p.specular_cone = ConeSettings(32, math.radians(30.0), 1.7, 0.5, 0.1)     # Application.h:97
     p.specular_cone_angle_from_roughness = 1
+    p.voxelize_multiplier = 1.0                                               # Application.h:87
+    p.conservative_raster = RASTER_CENTER if parity else RASTER_MSAA          # Application.h:62 (reference default MSAA)
     return p
