@@ -159,7 +159,13 @@ enum { VCT_VIEW_SHADED = 0,
        VCT_VIEW_INDIRECT = 7,          /* debugIndirect: the six diffuse cones (x occlusion if draw_occlusion)            :489 */
        VCT_VIEW_OCCLUSION = 8,         /* debugOcclusion                                                                  :490 */
        VCT_VIEW_REFLECTIONS = 9,       /* debugReflections: the specular cone                                             :505 */
-       VCT_VIEW_LAST = VCT_VIEW_REFLECTIONS };
+       /* sub-views of `voxelize` (phong.frag:350-356), tested by the shader before the radiance / colour lookup of VCT_VIEW_VOXELS */
+       VCT_VIEW_VOXEL_NORMALS = 10,    /* voxelize && normals: voxelNormal (one level, NEAREST) at the fragment's voxel          :350-353 */
+       VCT_VIEW_WARP_TEXTURE = 11,     /* voxelize && debugWarpTexture: texture(warpmap, linear position).xyz                    :354-357 */
+       VCT_VIEW_WARP_TEXTURE_TC = 12,  /* ... with `toggle`: the linear position itself                                          :357 */
+       /* (drawWarpSlope, :360-389, is not built: its colour lookup indexes colors[min(ceil(slope), colors.length())] — out of bounds
+        * whenever the slope reaches the table's length, undefined in GLSL) */
+       VCT_VIEW_LAST = VCT_VIEW_WARP_TEXTURE_TC };
 
 /* GLBufferedTimer results in ns, same names as reference src/Application.h:192 (+ producers). */
 typedef struct {

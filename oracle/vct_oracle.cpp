@@ -1355,6 +1355,9 @@ inline V3 postprocess(V3 c) {                            // phong.frag:210-218
 extern "C" void orc_shade_rows(const orc_scene* sc, const vct_frame_params* fp, int W, int H, int y_lo, int y_hi, int y_stride,
                                const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
                                const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps);
+// voxelNormal for VCT_VIEW_VOXEL_NORMALS (phong.frag:350-353; texture unit 1, Application.cpp:1046): set before a shade call, D^3 words
+static const unsigned* g_normal_volume = nullptr;
+extern "C" void orc_set_normal_volume(const unsigned* normal) { g_normal_volume = normal; }
 extern "C" void orc_shade(const orc_scene* sc, const vct_frame_params* fp, int W, int H, const unsigned long long* vis, int D, int L,
                           const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
                           const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps) {
@@ -1413,10 +1416,24 @@ static void shade_impl(const orc_scene* sc, const vct_frame_params* fp, int W, i
             }
             auto tbn = [&](V3 d) -> V3 { return (Tt * d.x + Bt * d.y) + fn * d.z; };   // mat3(T,B,N) * d
             const int view = fp->debug_view;
-            if (view == VCT_VIEW_VOXELS) {                                    // phong.frag:347-404 (`voxelize`; normals/warp-slope sub-views not built)
+            if (view == VCT_VIEW_WARP_TEXTURE || view == VCT_VIEW_WARP_TEXTURE_TC) {   // :354-357 (voxelize && debugWarpTexture; `toggle` shows the linear position)
+                const V3 tc = voxel_linear_position(Pw, fp);
+                const V3 wv = view == VCT_VIEW_WARP_TEXTURE_TC ? tc : (warpmap ? warp_sample(warpmap, tc) : V3{0.0f, 0.0f, 0.0f});   // no warp map generated yet: an empty texture
+                out = pack_unorm({wv.x, wv.y, wv.z, 1.0f});
+                continue;
+            }
+            if (view == VCT_VIEW_VOXELS || view == VCT_VIEW_VOXEL_NORMALS) {   // phong.frag:347-404 (`voxelize`; the warp-slope sub-views index out of bounds: not built)
                 V3 gp = get_voxel_position(Pw, fp, warpmap);
                 const float Df = (float)D;
                 V3 vi = {(Df * gp.x) / Df, (Df * gp.y) / Df, (Df * gp.z) / Df};   // voxelIndex(...) / voxelDim
+                if (view == VCT_VIEW_VOXEL_NORMALS) {                         // :350-353: one level, NEAREST min and mag, CLAMP_TO_BORDER 0
+                    const float c3[3] = {std::floor(vi.x * Df), std::floor(vi.y * Df), std::floor(vi.z * Df)};
+                    V4 t4 = {0, 0, 0, 0};
+                    if (g_normal_volume && c3[0] >= 0 && c3[1] >= 0 && c3[2] >= 0 && c3[0] < Df && c3[1] < Df && c3[2] < Df)
+                        t4 = unpack_unorm(g_normal_volume[((size_t)(int)c3[2] * D + (int)c3[1]) * D + (int)c3[0]]);
+                    out = pack_unorm({t4.x, t4.y, t4.z, 1.0f});
+                    continue;
+                }
                 V4 c = vol_sample(vol, vi, fp->miplevel);
                 fetch_total += 1;                                             // a volume fetch like any cone step
                 out = pack_unorm({c.x, c.y, c.z, 1.0f});

@@ -102,6 +102,7 @@ void orc_shade(const orc_scene*, const vct_frame_params*, int W, int H, const un
                int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr, const float* shadow, int S,
                const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps);
 
+void orc_set_normal_volume(const unsigned* normal);   /* voxelNormal for VCT_VIEW_VOXEL_NORMALS; D^3 words, must outlive the shade call */
 void orc_shade_rows(const orc_scene*, const vct_frame_params*, int W, int H, int y_lo, int y_hi, int y_stride,
                     const unsigned long long* vis, int D, int L, const unsigned* radiance_pyr, const unsigned* color_pyr,
                     const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps);

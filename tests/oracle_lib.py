@@ -152,6 +152,7 @@ class Oracle:
     def shade(self, p, y_lo=0, y_hi=None, y_stride=1):
         steps = C.c_ulonglong(0)
         rad = np.concatenate(self.radiance); col = np.concatenate(self.color)
+        lib().orc_set_normal_volume(ptr(self.normal))            # VIEW_VOXEL_NORMALS samples voxelNormal (texture unit 1)
         lib().orc_shade_rows(C.byref(self.s.c), C.byref(p), self.W, self.H, y_lo, self.H if y_hi is None else y_hi, y_stride,
                              ptr(self.vis), self.D, self.L, ptr(rad), ptr(col),
                              ptr(self.shadow), self.S, self._wm(p), ptr(self.image), C.byref(steps))

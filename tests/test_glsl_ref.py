@@ -237,6 +237,11 @@ FRAG_MODES = {
     "view_reflections": {"debug_view": P.VIEW_REFLECTIONS},
     "view_reflections_off": {"debug_view": P.VIEW_REFLECTIONS, "enable_reflections": 0},
     "view_voxels_tess_warp": {"debug_view": P.VIEW_VOXELS, "miplevel": 0.6, "voxelize_tesselation_warp": 1},
+    # sub-views of `voxelize` (phong.frag:350-357): voxelNormal at the fragment's voxel; the warp map at the linear position; `toggle`
+    "view_voxel_normals": {"debug_view": P.VIEW_VOXEL_NORMALS, "miplevel": 0.0},
+    "view_voxel_normals_warp_voxels_lod": {"debug_view": P.VIEW_VOXEL_NORMALS, "miplevel": 2.3, "warp_voxels": 1},
+    "view_warp_texture": {"debug_view": P.VIEW_WARP_TEXTURE, "warp_texture": 1},
+    "view_warp_texture_tc": {"debug_view": P.VIEW_WARP_TEXTURE_TC, "warp_texture": 1},
 }
 
 
@@ -271,9 +276,11 @@ def run_fragment_cases(impl, modes=None):
         o.transfer(p); o.inject(p); o.mip("radiance"); o.mip("color"); o.visibility(p)
         rad, colp = np.concatenate(o.radiance), np.concatenate(o.color)
         prec = np.zeros(W * H * 28, np.float32); steps = C.c_ulonglong(0)
+        O.lib().orc_set_normal_volume(ptr(o.normal))
         O.lib().orc_shade_trace(C.byref(o.s.c), C.byref(p), W, H, ptr(o.vis), D, Lv, ptr(rad), ptr(colp), ptr(o.shadow), SS, wm, ptr(o.image), C.byref(steps), ptr(prec))
         if impl == "glsl":
             img = np.zeros(W * H, np.uint32); gsteps = C.c_ulonglong(0)
+            glsl().glsl_set_normal_volume(ptr(o.normal))
             glsl().glsl_shade_pixels(C.byref(o.s.c), C.byref(p), W, H, ptr(prec), D, Lv, ptr(rad), ptr(colp), ptr(o.shadow), SS, wm, ptr(img), C.byref(gsteps))
             out[f"shade_{name}_image"], out[f"shade_{name}_cone_steps"] = img, np.array([gsteps.value], np.uint64)
         else:

@@ -32,6 +32,10 @@ VIEWS = [
     ("reflections", {"debug_view": P.VIEW_REFLECTIONS}),
     ("voxels_warp_voxels", {"debug_view": P.VIEW_VOXELS, "miplevel": 1.2, "warp_voxels": 1}),
     ("indirect_warp_texture", {"debug_view": P.VIEW_INDIRECT, "warp_texture": 1}),
+    ("voxel_normals", {"debug_view": P.VIEW_VOXEL_NORMALS}),
+    ("voxel_normals_warp_voxels", {"debug_view": P.VIEW_VOXEL_NORMALS, "miplevel": 2.3, "warp_voxels": 1}),
+    ("warp_texture", {"debug_view": P.VIEW_WARP_TEXTURE, "warp_texture": 1}),
+    ("warp_texture_tc", {"debug_view": P.VIEW_WARP_TEXTURE_TC, "warp_texture": 1}),
 ]
 
 

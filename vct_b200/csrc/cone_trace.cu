@@ -47,7 +47,7 @@ static TraceArgs make_trace_args(vct_ctx* c) {
     const bool rad = c->h_fc.p.draw_radiance != 0;
     a.vol = rad ? c->radiance_tex : c->color_tex; a.vol_point = rad ? c->radiance_tex_point : c->color_tex_point;
     a.vol_last = rad ? c->radiance_tex_last : c->color_tex_last; a.warp = reinterpret_cast<const float4*>(c->d_warpmap + 4 * (size_t)VCT_WARP_DIM * VCT_WARP_DIM * VCT_WARP_DIM);
-    a.level0 = rad ? c->d_radiance : c->d_color;
+    a.level0 = rad ? c->d_radiance : c->d_color; a.normal0 = c->d_normal;
     a.image = c->image_of(c->image_parity ^ 1); a.counters = c->d_counters;       // the half the last trace did not write
     return a;
 }
@@ -70,11 +70,12 @@ int vctk_cone_trace(vct_ctx* c) {
     const vct_frame_params& p = c->h_fc.p;
     // Which mapping the kernel applies.  traceCone tests warpTexture first (phong.frag:150-162), common.glsl's getVoxelPosition —
     // all the voxel view uses (:348) — tests warpVoxels first (common.glsl:44-60); the two differ only when both are switched on.
-    const bool voxel_view = p.debug_view == VCT_VIEW_VOXELS;
+    const bool voxel_view = p.debug_view == VCT_VIEW_VOXELS || p.debug_view == VCT_VIEW_VOXEL_NORMALS;
     const int wm = voxel_view ? (p.warp_voxels ? WARP_VOXELS : p.warp_texture ? WARP_TEXTURE : p.voxelize_tesselation_warp ? WARP_TESS : WARP_NONE)
                               : (p.warp_texture ? WARP_TEXTURE : p.warp_voxels ? WARP_VOXELS : p.voxelize_tesselation_warp ? WARP_TESS : WARP_NONE);
     if (p.debug_view != VCT_VIEW_SHADED) {                      // debug views: own instantiations in the exactly rounded unit
         if (p.debug_view < 0 || p.debug_view > VCT_VIEW_LAST) { c->error = "vct_cone_trace: unknown debug_view"; return 1; }
+        if (p.debug_view == VCT_VIEW_VOXEL_NORMALS && c->cfg.world_size > 1) { c->error = "VCT_VIEW_VOXEL_NORMALS: voxelNormal is not exchanged between the ranks (world_size must be 1)"; return 1; }
         if (vctk_cone_trace_debug(c, a, wm, grid)) return 1;
         c->image_parity = par;
         return 0;

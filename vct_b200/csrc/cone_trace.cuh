@@ -30,6 +30,7 @@ struct TraceArgs {
     const DevTexture* tex; const DevMaterial* mats; const float* shadow;
     cudaTextureObject_t vol, vol_point, vol_last; const float4* warp;     // warp map as floats (k_warpmap_floats)
     const uint32_t* level0;                      // linear level 0 of the traced pyramid: the voxel view's NEAREST fetch reads it exactly
+    const uint32_t* normal0;                     // voxelNormal (VCT_VIEW_VOXEL_NORMALS)
     uint32_t* image; Counters* counters;
     // sharded frame (multi-GPU with attached peers): the CTAs walk this rank's 64x64 screen tiles (x0 | y0 << 16; 32 CTAs each) instead of the
     // whole image, and every pixel is also stored into rank 0's image over NVLink (nullptr on rank 0 and on a single GPU)
@@ -422,7 +423,13 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
             const V4 lsp = mk4(ip(l, lf0.x, lf1.x, lf2.x), ip(l, lf0.y, lf1.y, lf2.y), ip(l, lf0.z, lf1.z, lf2.z), ip(l, lf0.w, lf1.w, lf2.w));
             auto tbn = [&](V3 d) { return (Tt * d.x + Bt * d.y) + fn * d.z; };
             const int view = DBG ? fp.debug_view : 0;
-            if (DBG && view == VCT_VIEW_VOXELS) {                            // phong.frag:347-404: the traced volume at this fragment's voxel
+            if (DBG && (view == VCT_VIEW_WARP_TEXTURE || view == VCT_VIEW_WARP_TEXTURE_TC)) {   // phong.frag:354-357 (voxelize && debugWarpTexture)
+                const V3 tc = voxel_linear_position(Pw, fp);
+                const V3 wv = view == VCT_VIEW_WARP_TEXTURE_TC ? tc : warp_sample(a.warp, tc);
+                put_pixel(a, o, pack_unorm(mk4(wv.x, wv.y, wv.z, 1.0f)));
+                break;
+            }
+            if (DBG && (view == VCT_VIEW_VOXELS || view == VCT_VIEW_VOXEL_NORMALS)) {   // phong.frag:347-404: a volume at this fragment's voxel
                 V3 gp = voxel_linear_position(Pw, fp);
                 if (WM == WARP_VOXELS) gp = voxel_warp(gp, voxel_linear_position(mk3(fp.eye[0], fp.eye[1], fp.eye[2]), fp));
                 else if (WM == WARP_TEXTURE) gp = warp_sample(a.warp, gp);
@@ -431,6 +438,13 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
                 const V3 vi = mk3(__fdiv_rn(__fmul_rn(Df, gp.x), Df), __fdiv_rn(__fmul_rn(Df, gp.y), Df), __fdiv_rn(__fmul_rn(Df, gp.z), Df));   // voxelIndex(..) / voxelDim
                 const float lambda = fp.miplevel;
                 float4 sc;
+                if (view == VCT_VIEW_VOXEL_NORMALS) {                        // :350-353: voxelNormal has one level and NEAREST filters: texel floor(s * D), border 0
+                    const float fx = floorf(vi.x * Df), fy = floorf(vi.y * Df), fz = floorf(vi.z * Df);
+                    V4 t4 = mk4(0.f, 0.f, 0.f, 0.f);
+                    if (fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < Df && fy < Df && fz < Df) t4 = unpack_unorm(__ldg(a.normal0 + ((size_t)(int)fz * fc.D + (int)fy) * fc.D + (int)fx));
+                    put_pixel(a, o, pack_unorm(mk4(t4.x, t4.y, t4.z, 1.0f)));
+                    break;
+                }
                 if (!(lambda > 0.5f)) {
                     // magnification -> NEAREST on level 0 (GL 4.5 §8.14): texel floor(s * D), border 0.  Read from the linear level: the
                     // texture unit converts coordinates to fixed point before it floors, which flips texels that sit on a voxel boundary.

@@ -98,6 +98,7 @@ struct Settings {
     // debug views, Application.h:40-60 (all false by default); frameParams() folds them into vct_frame_params::debug_view
     int drawVoxels = false, drawNormals = false, drawDominantAxis = false, debugOcclusion = false, debugIndirect = false, debugReflections = false;
     int debugMaterialDiffuse = false, debugMaterialRoughness = false, debugMaterialMetallic = false;
+    int debugWarpTexture = false, toggle = false;   // Application.h:54, :180: sub-views of drawVoxels (phong.frag:354-357)
     float miplevel = 0.0f;
     int voxelizeTesselation = false;    // Application.h:85 (reference default true; this host defaults to the north star's raster path)
     int voxelizeTesselationWarp = false;   // Application.h:102: the camera frustum as voxel grid (common.glsl:37-42)
@@ -316,7 +317,8 @@ public:
         p.diffuse_cone = cone(s.diffuseConeSettings); p.specular_cone = cone(s.specularConeSettings);
         p.specular_cone_angle_from_roughness = s.specularConeAngleFromRoughness;
         // phong.frag tests its debug uniforms in this order (:346-447, 489-505)
-        p.debug_view = s.drawVoxels ? VCT_VIEW_VOXELS : s.debugMaterialDiffuse ? VCT_VIEW_MATERIAL_DIFFUSE : s.debugMaterialRoughness ? VCT_VIEW_MATERIAL_ROUGHNESS
+        p.debug_view = s.drawVoxels ? (s.drawNormals ? VCT_VIEW_VOXEL_NORMALS : s.debugWarpTexture ? (s.toggle ? VCT_VIEW_WARP_TEXTURE_TC : VCT_VIEW_WARP_TEXTURE) : VCT_VIEW_VOXELS)
+                     : s.debugMaterialDiffuse ? VCT_VIEW_MATERIAL_DIFFUSE : s.debugMaterialRoughness ? VCT_VIEW_MATERIAL_ROUGHNESS
                      : s.debugMaterialMetallic ? VCT_VIEW_MATERIAL_METALLIC : s.drawNormals ? VCT_VIEW_NORMALS : s.drawDominantAxis ? VCT_VIEW_DOMINANT_AXIS
                      : s.debugIndirect ? VCT_VIEW_INDIRECT : s.debugOcclusion ? VCT_VIEW_OCCLUSION : s.debugReflections ? VCT_VIEW_REFLECTIONS : VCT_VIEW_SHADED;
         p.miplevel = s.miplevel;

@@ -15,6 +15,7 @@ F3 = C.c_float * 3
 
 VIEW_SHADED, VIEW_VOXELS, VIEW_MATERIAL_DIFFUSE, VIEW_MATERIAL_ROUGHNESS, VIEW_MATERIAL_METALLIC = 0, 1, 2, 3, 4
 VIEW_NORMALS, VIEW_DOMINANT_AXIS, VIEW_INDIRECT, VIEW_OCCLUSION, VIEW_REFLECTIONS = 5, 6, 7, 8, 9
+VIEW_VOXEL_NORMALS, VIEW_WARP_TEXTURE, VIEW_WARP_TEXTURE_TC = 10, 11, 12
 VOL_COLOR, VOL_NORMAL, VOL_RADIANCE, VOL_OCCUPANCY, VOL_WARPMAP, VOL_WARP_WEIGHTS_LOW, VOL_WARP_WEIGHTS_HIGH, BUF_IMAGE = range(8)
 
 
