@@ -162,6 +162,23 @@ __device__ __noinline__ V3 warp_sample(const float4* __restrict__ wm, V3 tc) {
     return lerp3x(lerp3x(c00, c10, fy), lerp3x(c01, c11, fy), fz);
 }
 
+// The same filter with eight plain 16-byte loads (the first half of each pair entry), for the debug view that shows the warp map itself (nvcc 12.9
+// crashes when the out-of-line function above gets a second call site in the debug instantiations)
+__device__ __forceinline__ V3 warp_sample_plain(const float4* __restrict__ wm, V3 tc) {
+    const int n = VCT_WARP_DIM;
+    const float x = __fmul_rn(tc.x, (float)n) - 0.5f, y = __fmul_rn(tc.y, (float)n) - 0.5f, z = __fmul_rn(tc.z, (float)n) - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y), fz0 = floorf(z);
+    if (!(fabsf(fx0) < 1e9f) || !(fabsf(fy0) < 1e9f) || !(fabsf(fz0) < 1e9f)) return mk3(0.f, 0.f, 0.f);
+    const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0; const float fx = x - fx0, fy = y - fy0, fz = z - fz0;
+    auto texel = [&](int xx, int yy, int zz) {
+        xx = min(max(xx, 0), n - 1); yy = min(max(yy, 0), n - 1); zz = min(max(zz, 0), n - 1);
+        const float4 q = __ldg(wm + 2 * ((zz * n + yy) * n + xx));
+        return mk3(q.x, q.y, q.z);
+    };
+    const V3 c00 = lerp3x(texel(x0, y0, z0), texel(x0 + 1, y0, z0), fx), c10 = lerp3x(texel(x0, y0 + 1, z0), texel(x0 + 1, y0 + 1, z0), fx);
+    const V3 c01 = lerp3x(texel(x0, y0, z0 + 1), texel(x0 + 1, y0, z0 + 1), fx), c11 = lerp3x(texel(x0, y0 + 1, z0 + 1), texel(x0 + 1, y0 + 1, z0 + 1), fx);
+    return lerp3x(lerp3x(c00, c10, fy), lerp3x(c01, c11, fy), fz);
+}
 // Mapping applied to every cone sample, phong.frag:150-162 (priority INSIDE traceCone: warpTexture > warpVoxels >
 // voxelizeTesselationWarp; common.glsl:44-60, which the voxel view and the other passes use, has warpVoxels first)
 enum { WARP_NONE = 0, WARP_TEXTURE = 1, WARP_VOXELS = 2, WARP_TESS = 3 };
@@ -425,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_cone_trace(TraceAr
             const int view = DBG ? fp.debug_view : 0;
             if (DBG && (view == VCT_VIEW_WARP_TEXTURE || view == VCT_VIEW_WARP_TEXTURE_TC)) {   // phong.frag:354-357 (voxelize && debugWarpTexture)
                 const V3 tc = voxel_linear_position(Pw, fp);
-                const V3 wv = view == VCT_VIEW_WARP_TEXTURE_TC ? tc : warp_sample(a.warp, tc);
+                const V3 wv = view == VCT_VIEW_WARP_TEXTURE_TC ? tc : warp_sample_plain(a.warp, tc);
                 put_pixel(a, o, pack_unorm(mk4(wv.x, wv.y, wv.z, 1.0f)));
                 break;
             }
