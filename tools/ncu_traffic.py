@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""profiles/traffic.json from an `ncu --page raw --csv` dump: DRAM bytes per launch of every kernel (first launch of each
-name), keyed by the names bench.py uses; for k_cone_trace also the TEX data-pipe wavefronts of the launch (bench.py's
+"""profiles/traffic.json from an `ncu --page raw --csv` dump: DRAM bytes per launch of every kernel (LAST launch of each
+name: the capture runs three frames and the last one is a steady-state sparse frame), keyed by the names bench.py uses; for k_cone_trace also the TEX data-pipe wavefronts of the launch (bench.py's
 roofline.tex_pipe; "k_cone_trace__cone_steps" = the cone steps of the captured frame, from the bench line of the same build, is
 kept from the previous file).  usage: ncu_traffic.py <raw.csv> <out.json>"""
 import csv, json, re, sys
@@ -11,9 +11,7 @@ scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
 for r in rows[2:]:
     name = re.sub(r"<.*", "", r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("<unnamed>::", "")).strip()
-    name = {"k_inject_linear": "k_inject", "k_clear_masked": "k_clear", "k_transfer_masked": "k_transfer"}.get(name, name)
-    if name in out:
-        continue
+    name = {"k_inject_linear": "k_inject", "k_clear_masked": "k_clear", "k_frame_begin": "k_clear", "k_transfer_masked": "k_transfer"}.get(name, name)
     tot = 0.0
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(r[ix[m]]) * scale.get(units[ix[m]], 1)
