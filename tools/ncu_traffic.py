@@ -9,7 +9,11 @@ hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
-for r in rows[2:]:
+body = rows[2:]
+starts = [i for i, r in enumerate(body) if "k_upload_frame" in r[ix["Kernel Name"]]]
+if starts:                                      # only the last frame of the capture (a frame starts with its parameter upload)
+    body = body[starts[-1]:]
+for r in body:
     name = re.sub(r"<.*", "", r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("<unnamed>::", "")).strip()
     name = {"k_inject_linear": "k_inject", "k_clear_masked": "k_clear", "k_frame_begin": "k_clear", "k_transfer_masked": "k_transfer"}.get(name, name)
     tot = 0.0
