@@ -23,7 +23,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close(); return port
 
 
-@pytest.mark.parametrize("workload", ["room", "sponza", "animated"])
+@pytest.mark.parametrize("workload", ["room", "room_msaa", "sponza", "animated"])
 def test_sharded_frame_equals_single_gpu(workload):
     n = _gpus()
     if n < 2:

@@ -4,7 +4,7 @@ must give exactly the words of the single-GPU frame — every level of the trace
 voxelise counters summed over ranks, and the final image assembled in rank 0's buffer from every rank's screen tiles.
 
 usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-           tools/sharded_parity.py [room|sponza|sponza512|animated]     (animated: config 4 at 256^3 / 960x540, whole frames, moving actors)
+           tools/sharded_parity.py [room|room_msaa|sponza|sponza512|animated]     (animated: config 4 at 256^3 / 960x540, whole frames, moving actors)
 Prints one JSON line on rank 0 and exits non-zero on any mismatch."""
 import json
 import os
@@ -25,8 +25,11 @@ from vct_b200.sharded import ShardedFrame  # noqa: E402
 
 def workload(name):
     """-> (scene, params, D, L, S, W, H, Workload or None)"""
-    if name == "room":
-        return S.room_scene(), S.room_params(320, 240), 64, 5, 512, 320, 240, None
+    if name in ("room", "room_msaa"):
+        p = S.room_params(320, 240)
+        if name == "room_msaa":                  # multisample voxelisation at twice the viewport: extrapolated fragments, no triangle cull per rank
+            p.conservative_raster = P.RASTER_MSAA; p.voxelize_multiplier = 2.0
+        return S.room_scene(), p, 64, 5, 512, 320, 240, None
     from vct_b200.workloads import Workload
     w = Workload(3) if name == "sponza" else Workload(3, 3840, 2160, 512) if name == "sponza512" else Workload(4, 960, 540, 256)
     return w.scene, w.params, w.D, w.L, w.S, w.W, w.H, (w if name == "animated" else None)
