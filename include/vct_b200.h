@@ -39,7 +39,7 @@ typedef struct {
     int shadow_size;    /* SHADOWMAP_WIDTH/HEIGHT (4096)                   Application.cpp:30-31 */
     int width, height;  /* frame size                                      common.h:9-10 */
     int device;         /* CUDA device ordinal */
-    /* z-slab sharding of the voxel volume across ranks; single GPU: rank 0 of 1. */
+    /* z sharding of the voxel volume across ranks (slab or stripes: slab_stripe below); single GPU: rank 0 of 1. */
     int rank, world_size;
     int max_fragments;  /* capacity of the voxel-fragment buffer (0 = default 8 Mi) */
     /* Single-process multi-GPU (SURVEY §8b "multi-GPU fan-out is internal"): n_devices > 1 makes vct_create build one context per
@@ -209,7 +209,7 @@ int  vct_mip_kernel(vct_ctx*, int which_volume, int kernel_mode);   /* shaders/f
                                                               0 BOX2 (= vct_mip), 1 BOX3, 2 CUBE; the host never sets it (dead modes) */
 int  vct_exchange(vct_ctx*);                               /* multi-GPU only: publish slab pyramid to the 3D texture
                                                               after the caller's all-gather */
-/* Multi-GPU (z-slab sharding): once every rank knows its peers' buffers, vct_frame / vct_gi_passes run the WHOLE sharded
+/* Multi-GPU (z sharding): once every rank knows its peers' buffers, vct_frame / vct_gi_passes run the WHOLE sharded
  * frame — voxel passes on the own slab, the slab exchange over NVLink peer memory (exchange.cu: level 0 as the flagged x-row segments
  * pushed into staging regions in every peer's memory, levels >= 1 stored straight into the peers' pyramids, device-side flags instead of
  * collectives), the cone trace of the own screen tiles, pixels stored into rank 0's image — with no collective and no host

@@ -194,7 +194,7 @@ int upload_frame(vct_ctx* c, const vct_frame_params* p) {
     if (!p) return fail(c, "null frame params");
     if (p->diffuse_cone.steps > 64 || p->specular_cone.steps > 64 || p->diffuse_cone.steps < 0 || p->specular_cone.steps < 0) return fail(c, "cone steps must be in [0,64]");
     if (p->voxel_fill_holes && c->cfg.world_size > 1)
-        return fail(c, "voxelFillHoles reads the 3x3x3 neighbourhood across z-slab borders (voxelFillHoles.comp:8-36): not supported with world_size > 1");
+        return fail(c, "voxelFillHoles reads the 3x3x3 neighbourhood across the borders of a rank's z layers (voxelFillHoles.comp:8-36): not supported with world_size > 1");
     if (!(p->voxelize_multiplier >= 0.0f && p->voxelize_multiplier <= 8.0f) || (p->voxelize_multiplier > 0.0f && (int)(p->voxelize_multiplier * (float)c->D) < 1))
         return fail(c, "voxelize_multiplier: 0 (= 1) or a factor up to 8 that leaves a viewport of at least one pixel");
     if (p->conservative_raster != VCT_RASTER_CENTER && p->conservative_raster != VCT_RASTER_MSAA)
@@ -640,7 +640,7 @@ int vct_mip_kernel(vct_ctx* c, int which, int kernel_mode) { VCT_FAN(c, vct_mip_
     cudaSetDevice(c->cfg.device);
     if (which != VCT_VOL_RADIANCE && which != VCT_VOL_COLOR) return fail(c, "vct_mip_kernel: radiance or colour volume only");
     if (kernel_mode < 0 || kernel_mode > 2) return fail(c, "vct_mip_kernel: kernel_mode is 0 (BOX2), 1 (BOX3) or 2 (CUBE)");
-    if (kernel_mode != 0 && c->cfg.world_size > 1) return fail(c, "vct_mip_kernel: BOX3 / CUBE read across z-slab borders; world_size must be 1");
+    if (kernel_mode != 0 && c->cfg.world_size > 1) return fail(c, "vct_mip_kernel: BOX3 / CUBE read across the borders of a rank's z layers; world_size must be 1");
     c->seg_valid = false;
     const bool publish = c->cfg.world_size <= 1 && !(which == VCT_VOL_COLOR && !c->color_arr);
     return vctk_mip(c, which, kernel_mode, publish);
@@ -776,7 +776,7 @@ int vct_sync(vct_ctx* c) { VCT_FAN(c, vct_sync(c)); if (!c) return 1; cudaSetDev
 int vct_read_volume(vct_ctx* c, int which, int level, void* out) {
     if (!c || !out) return 1;
     if (!c->group.empty() && (which == VCT_VOL_COLOR || which == VCT_VOL_NORMAL || which == VCT_VOL_RADIANCE)) {
-        // multi-device handle: every rank holds its z-slab of a volume (the traced pyramid is complete everywhere after a frame, the
+        // multi-device handle: every rank holds its z layers (slab or stripes) of a volume (the traced pyramid is complete everywhere after a frame, the
         // others are not): assemble the level from the ranks' slabs
         void* p0; size_t bytes; if (volume_ptr(c, which, level, &p0, &bytes)) return 1;
         const int ws = (int)c->group.size() + 1, d = level_dim(c->D, level);

@@ -1,8 +1,8 @@
-// exchange.cu — the one exchange step of the z-slab sharded frame (multi-GPU), entirely in kernels over NVLink peer
+// exchange.cu — the one exchange step of the z-sharded frame (a rank owns a slab or interleaved stripes of z layers: Stripes, common.cuh) (multi-GPU), entirely in kernels over NVLink peer
 // memory: no NCCL collective and no host synchronisation on the frame's critical path, so the whole N-GPU step can be captured in a
 // CUDA graph like the single-GPU step.
 //
-// The reference is a single-GPU program; sharding leaves one real exchange: after its voxel passes every rank owns one z-slab of
+// The reference is a single-GPU program; sharding leaves one real exchange: after its voxel passes every rank owns its z layers of
 // every level of the traced pyramid and the cone tracer of every rank samples all of it.
 //   level 0      8/9 of the bytes and ~97 % empty: a rank PUSHES the x-row segments (8 voxels, 32 bytes) of its slab that hold — or
 //                held last frame — a fragment (the segment masks of the sparse frame, common.cuh) as (id, data) records into a

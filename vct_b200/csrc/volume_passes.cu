@@ -387,7 +387,7 @@ struct InjectLinear {                                 // passed by value: no dep
     int skip_far;                                     // the light's far plane (depth 1 = nothing rendered) misses the volume by > 1 voxel
     // Block cull: voxel coordinates are affine in (ndc x, ndc y, ndc depth): P_k = bx[k]*nx + by[k]*ny + bz[k]*nz + b0[k].  With the
     // min / max filtered depth of a 64x16 texel block (k_shadow_minmax*, written by the shadow pass) interval arithmetic bounds P over
-    // the block; k_inject_cull lists the blocks that can reach the volume — and this rank's z-slab —, k_inject_linear runs one CTA per
+    // the block; k_inject_cull lists the blocks that can reach the volume — and this rank's z layers —, k_inject_linear runs one CTA per
     // listed block.  The list is a function of the shadow map and of (ls_inverse, volume, grid, slab): it is rebuilt when one of them
     // changes (a new shadow map, a moved volume), not every frame.  Sponza: 2/3 of the shadow map sees no geometry or lies outside the
     // volume and is never read.  (Measured and dropped: the test per thread on 4x4 blocks, 40 -> 49 us, and per CTA inside the inject
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256) k_shadow_minmax_coarse(const float2* __re
         for (int i = 0; i < kInjBlockW / 4; ++i) { const float2 v = __ldg(fine + (size_t)(by * (kInjBlockH / 4) + j) * nf + bx * (kInjBlockW / 4) + i); lo = fminf(lo, v.x); hi = fmaxf(hi, v.y); }
     out[b] = make_float2(lo, hi);
 }
-// can the 64x16 texel block `b` of the shadow map land in the volume (and this rank's z-slab) this frame?  CTA-uniform.
+// can the 64x16 texel block `b` of the shadow map land in the volume (and this rank's z layers) this frame?  CTA-uniform.
 __device__ __forceinline__ bool inject_block_active(const InjectLinear& lin, int b) {
     if (!lin.minmax) return true;
     const int S = lin.S, nbx = S / kInjBlockW;

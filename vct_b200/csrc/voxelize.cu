@@ -69,7 +69,7 @@ struct VoxArgs {
     uint32_t *color, *normal, *occ;
     uint8_t* seg;             // segment mask of this frame (common.cuh): one byte per 8 voxels of an x-row
     int msaa; SampleSet ms;   // Settings::conservativeRasterization == MSAA: any-sample coverage (raster.cuh tri_cover_any)
-    int slab_cull;            // multi-GPU, linear mapping: triangles that cannot touch this rank's z-slab stop at the bin kernel
+    int slab_cull;            // multi-GPU, linear mapping: triangles that cannot touch this rank's z layers stop at the bin kernel
     Counters* counters;
 };
 
@@ -97,7 +97,7 @@ __device__ __forceinline__ bool make_setup(const VoxArgs& a, const FrameConst& f
     const V3 w[3] = {ld3(a.wpos, i0), ld3(a.wpos, i1), ld3(a.wpos, i2)};
     if (a.slab_cull) {
         // Multi-GPU: a triangle whose voxel-space box (1.5 voxels of slack) lies inside the volume but misses this rank's
-        // z-slab can produce no fragment here — neither an owned one nor one outside the volume (those are counted by the
+        // z layers can produce no fragment here — neither an owned one nor one outside the volume (those are counted by the
         // rank that owns z = 0) — so it skips setup, binning and tiles.  Linear mapping only (no warp mode).
         const float fd = (float)a.D;
         float lo[3], hi[3];
