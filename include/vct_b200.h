@@ -246,6 +246,12 @@ int  vct_normalize_voxels_f16(vct_ctx*, void* color_rgba16f, void* normal_rgba16
                                                               DEVICE buffers of dim^3 half4 (USE_RGBA16F build) */
 
 /* ---- outputs ------------------------------------------------------------------------------------------- */
+/* Application::debugVoxels (src/Application.cpp:1222-1275, shaders/debugVoxels.vert/.geom/.frag; Settings::debugVoxels replaces the frame's
+ * render passes, :923-928): every voxel of the base grid whose colour — the traced pyramid sampled at its centre with lod = miplevel — has
+ * alpha > 0 is drawn as a cube of one voxel's size with depth test and back-face culling, in that colour, over the clear colour; uses
+ * projection, view, miplevel, draw_radiance, clear_color and the volume extents of `p`.  The result is the current image (vct_read_image).
+ * One GPU, dim <= 512.  The vertex shader's float(gl_InstanceID) arithmetic is reproduced (ids collapse beyond 2^24 instances, i.e. at 512^3). */
+int  vct_debug_voxels(vct_ctx*, const vct_frame_params*);
 int  vct_read_image(vct_ctx*, void* rgba8 /* width*height*4, row 0 = bottom like glReadPixels */);
 /* Pipelined read-back for render loops (the reference's glfwSwapBuffers never blocks on the frame either, main.cpp:229-240):
  * enqueue the copy of the current image into PINNED host memory on the library's copy stream and return at once; the library

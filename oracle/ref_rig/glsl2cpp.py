@@ -149,7 +149,7 @@ def main():
                 "static thread_local ivec3 gl_GlobalInvocationID;   // uvec3 in GLSL; ids stay far below 2^31\n"
                 "static thread_local vec4 gl_FragCoord; static thread_local int gl_Layer;\n"
                 "static thread_local int gl_InvocationID; static thread_local float gl_TessLevelInner[2], gl_TessLevelOuter[4];\n"
-                "static thread_local vec3 gl_TessCoord; static thread_local vec4 gl_Position;\n"
+                "static thread_local vec3 gl_TessCoord; static thread_local vec4 gl_Position; static thread_local int gl_InstanceID;\n"
                 "struct gl_PerVertex { vec4 gl_Position; }; static thread_local gl_PerVertex gl_in[3];\n"
                 "static void EmitVertex(); static void EndPrimitive();   // geometry stage: defined by the driver\n")
         f.write(body)

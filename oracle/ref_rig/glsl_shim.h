@@ -238,6 +238,7 @@ inline float exp2(float x) { return std::exp2(x); }
 inline float floor(float x) { return std::floor(x); }
 inline float ceil(float x) { return std::ceil(x); }
 inline float fract(float x) { return x - std::floor(x); }
+inline float modf(float x, float& ip) { ip = std::trunc(x); return x - ip; }          // GLSL modf: fractional part, integer part through the out parameter
 inline float abs(float x) { return std::fabs(x); }
 inline int abs(int x) { return x < 0 ? -x : x; }
 inline float sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }

@@ -1576,3 +1576,91 @@ extern "C" int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+// ============================================================================= N3: Application::debugVoxels (src/Application.cpp:1222-1275)
+// glDrawArraysInstanced(GL_POINTS, 0, 1, D^3) through debugVoxels.vert / .geom / .frag: every instance is a voxel of the base grid (its colour the
+// pyramid sampled at the voxel's centre with lod = Settings::miplevel); a voxel with alpha > 0 becomes a cube of one voxel's size — a 21-vertex
+// triangle strip, i.e. 19 triangles, the repeated indices making degenerate stitches — drawn with depth test (GL_LESS), back-face culling (CCW front) and the
+// voxel's colour.  Canonical fixed function as everywhere else in this file: the same fixed-point rasteriser, near-plane clipping in clip space,
+// far plane per fragment, z_ndc interpolated with screen-space barycentrics, window depth z_ndc * 0.5 + 0.5 compared as fp32; among equal depths
+// the FIRST drawn fragment stays (GL_LESS), instances in order, triangles of a strip in order (odd strip triangles have their winding reversed,
+// OpenGL 4.5 section 10.1.8).  quirk kept: debugVoxels.vert derives the voxel from float(gl_InstanceID) with two modf calls — beyond 2^24 instances
+// (512^3) consecutive ids collapse onto even multiples, so some voxels are drawn twice and others never.
+namespace {
+struct DbgVoxel { V3 tc; V3 world; };
+inline DbgVoxel debug_voxel_instance(unsigned id, int D, const vct_frame_params* fp) {       // debugVoxels.vert:19-30
+    const float dim = (float)D;
+    float instance = (float)id;
+    float t = instance / dim; instance = std::trunc(t); const float x = t - instance;       // modf(instance / voxelDim, instance)
+    t = instance / dim; instance = std::trunc(t); const float y = t - instance;
+    const float z = instance / dim;
+    const float h = 0.5f / dim;
+    DbgVoxel o; o.tc = {x + h, y + h, z + h};
+    const float tcv[3] = {o.tc.x, o.tc.y, o.tc.z}; float w[3];
+    for (int k = 0; k < 3; ++k)                                                               // position (0,0,0) + voxelCenter + mix(voxelMin, voxelMax, voxelPosition)
+        w[k] = (0.0f + fp->voxel_center[k]) + (fp->voxel_min[k] * (1.0f - tcv[k]) + fp->voxel_max[k] * tcv[k]);
+    o.world = {w[0], w[1], w[2]};
+    return o;
+}
+const float kCubeVertices[8][3] = {{-0.5f, 0.5f, -0.5f}, {0.5f, 0.5f, -0.5f}, {0.5f, 0.5f, 0.5f}, {-0.5f, 0.5f, 0.5f},
+                                   {-0.5f, -0.5f, -0.5f}, {0.5f, -0.5f, -0.5f}, {0.5f, -0.5f, 0.5f}, {-0.5f, -0.5f, 0.5f}};   // debugVoxels.geom:16-26
+const int kCubeStrip[21] = {5, 4, 1, 0, 0, 0, 0, 3, 1, 2, 5, 6, 4, 7, 0, 3, 3, 3, 2, 7, 6};                                  // :27-33
+}  // namespace
+
+extern "C" void orc_debug_voxel_vertices(const vct_frame_params* fp, int D, unsigned id, float* world3, float* clip21x4) {
+    float mvp[16];                                                                            // glm::mat4 mvp = projection * view (Application.cpp:926)
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r)
+            mvp[4 * c + r] = ((fp->projection[r] * fp->view[4 * c] + fp->projection[4 + r] * fp->view[4 * c + 1]) + fp->projection[8 + r] * fp->view[4 * c + 2]) + fp->projection[12 + r] * fp->view[4 * c + 3];
+    const DbgVoxel v = debug_voxel_instance(id, D, fp);
+    world3[0] = v.world.x; world3[1] = v.world.y; world3[2] = v.world.z;
+    const float dim = (float)D;
+    const float size[3] = {(fp->voxel_max[0] - fp->voxel_min[0]) / dim, (fp->voxel_max[1] - fp->voxel_min[1]) / dim, (fp->voxel_max[2] - fp->voxel_min[2]) / dim};
+    for (int i = 0; i < 21; ++i) {
+        const float* cvx = kCubeVertices[kCubeStrip[i]];
+        const V4 p = mul(mvp, {size[0] * cvx[0] + v.world.x, size[1] * cvx[1] + v.world.y, size[2] * cvx[2] + v.world.z, 1.0f});
+        clip21x4[4 * i] = p.x; clip21x4[4 * i + 1] = p.y; clip21x4[4 * i + 2] = p.z; clip21x4[4 * i + 3] = p.w;
+    }
+}
+
+extern "C" void orc_debug_voxel_color(const vct_frame_params* fp, int D, int L, const unsigned* pyr, unsigned id, float* rgba) {   // debugVoxels.vert:25
+    Vol vol; vol.D = D; vol.L = L;
+    { size_t off = 0; for (int l = 0; l < L; ++l) { vol.lv[l] = pyr + off; const size_t d = std::max(1, D >> l); off += d * d * d; } }
+    const V4 c = vol_sample(vol, debug_voxel_instance(id, D, fp).tc, fp->miplevel);
+    rgba[0] = c.x; rgba[1] = c.y; rgba[2] = c.z; rgba[3] = c.w;
+}
+// pyr: the levels of the pyramid the reference binds (settings.drawRadiance ? voxelRadiance : voxelColor, Application.cpp:927), packed back to back
+extern "C" void orc_debug_voxels(const vct_frame_params* fp, int W, int H, int D, int L, const unsigned* pyr, unsigned* image) {
+    Vol vol; vol.D = D; vol.L = L;
+    { size_t off = 0; for (int l = 0; l < L; ++l) { vol.lv[l] = pyr + off; const size_t d = std::max(1, D >> l); off += d * d * d; } }
+    const unsigned clear = pack_unorm({fp->clear_color[0], fp->clear_color[1], fp->clear_color[2], 1.0f});
+    std::vector<float> depth((size_t)W * H, 1.0f);                                            // glClear(GL_COLOR_BUFFER_BIT | GL_DEPTH_BUFFER_BIT)
+    for (size_t i = 0; i < (size_t)W * H; ++i) image[i] = clear;
+    const unsigned n = (unsigned)D * D * D;
+    for (unsigned id = 0; id < n; ++id) {
+        const DbgVoxel v = debug_voxel_instance(id, D, fp);
+        const V4 c = vol_sample(vol, v.tc, fp->miplevel);                                     // debugVoxels.vert:25 textureLod(voxels, tc, level)
+        if (!(c.w > 0.0f)) continue;                                                          // debugVoxels.geom:46
+        const unsigned word = pack_unorm({c.x, c.y, c.z, 1.0f});                              // debugVoxels.frag:10 (alpha 1 like every image of this library)
+        float world[3], clip[21 * 4];
+        orc_debug_voxel_vertices(fp, D, id, world, clip);
+        for (int k = 0; k + 2 < 21; ++k) {
+            RV cv[3];
+            for (int j = 0; j < 3; ++j) { const float* q = clip + 4 * (k + j); cv[j] = {q[0], q[1], q[2], q[3]}; }
+            if (k & 1) std::swap(cv[0], cv[1]);                                               // odd strip triangle: winding reversed
+            ClipTri ct[2]; const int nct = clip_near(cv, ct);
+            for (int q = 0; q < nct; ++q) {
+                Setup s = tri_setup(ct[q].v, W, H, true);
+                if (!s.valid) continue;
+                const float z[3] = {ct[q].v[0].z / ct[q].v[0].w, ct[q].v[1].z / ct[q].v[1].w, ct[q].v[2].z / ct[q].v[2].w};
+                raster(s, 0, H - 1, [&](int px, int py, const float l[3]) {
+                    const float zn = interp(l, z[0], z[1], z[2]);
+                    if (zn > 1.0f) return;                                                    // far plane
+                    const float dw = zn * 0.5f + 0.5f;
+                    float& dref = depth[(size_t)py * W + px];
+                    if (dw < dref) { dref = dw; image[(size_t)py * W + px] = word; }          // GL_LESS
+                });
+            }
+        }
+    }
+}

@@ -121,6 +121,11 @@ void orc_shade_trace_rows(const orc_scene*, const vct_frame_params*, int W, int 
                           const float* shadow, int S, const unsigned short* warpmap, unsigned* image, unsigned long long* cone_steps, float* frag_rec);
 /* In the three *_trace functions the output volume / image may be NULL: only the fixed-function stage runs and records. */
 
+/* N3  Application::debugVoxels (Application.cpp:1222-1275; debugVoxels.vert/.geom/.frag): the non-empty voxels of the base grid as depth-tested cubes */
+void orc_debug_voxels(const vct_frame_params*, int W, int H, int D, int L, const unsigned* pyramid, unsigned* image);
+void orc_debug_voxel_color(const vct_frame_params*, int D, int L, const unsigned* pyramid, unsigned instance, float* rgba);
+void orc_debug_voxel_vertices(const vct_frame_params*, int D, unsigned instance, float* world3, float* clip21x4);   /* vertex + geometry stage of one instance */
+
 /* KAT helpers */
 unsigned orc_rgba8_avg(unsigned stored, float r, float g, float b);     /* voxelize.frag:111-139, one insertion */
 unsigned orc_pack_unorm4x8(float r, float g, float b, float a);

@@ -158,6 +158,11 @@ class Oracle:
                              ptr(self.shadow), self.S, self._wm(p), ptr(self.image), C.byref(steps))
         self.cone_steps = steps.value
 
+    def debug_voxels(self, p):
+        """Application::debugVoxels: cubes of the traced pyramid's non-empty voxels into self.image."""
+        vol = self.radiance if p.draw_radiance else self.color
+        lib().orc_debug_voxels(C.byref(p), self.W, self.H, self.D, self.L, ptr(np.concatenate(vol)), ptr(self.image))
+
     def frame(self, p):
         self.shadowmap(p)
         if p.warp_texture:

@@ -671,3 +671,60 @@ def test_oracle_alpha_tests_equal_the_reference_glsl_compiled_as_cpp():
 
 def test_oracle_alpha_tests_equal_the_committed_outputs_of_the_reference_glsl():
     compare(run_alpha_cases("oracle"), dict(np.load(GOLD_ALPHA)), "oracle vs tests/golden/glsl_ref_alpha.npz")
+
+
+# ============================================================ debugVoxels.vert / .geom (N3: Application::debugVoxels, Application.cpp:1222-1275)
+# Vertex + geometry stage of the instanced cube renderer: per instance id the voxel's texture coordinate, colour (textureLod at Settings::miplevel),
+# world position and the 21 clip-space vertices of its triangle strip.  Rasterisation, depth test and culling are fixed function: the oracle's.
+def run_debug_voxel_cases(impl):
+    from vct_b200 import scene as S
+    out = {}
+    rng = np.random.default_rng(321)
+    for name, D, Lv, lod, ids in (("d64_point", 64, 5, 0.0, rng.integers(0, 64 ** 3, 3000)), ("d64_lod1_6", 64, 5, 1.6, rng.integers(0, 64 ** 3, 3000)),
+                                  # 512^3 instances exceed 2^24: float(gl_InstanceID) rounds and ids collapse onto even multiples (reference quirk)
+                                  ("d512_float_ids", 512, 1, 0.0, np.concatenate([rng.integers(0, 512 ** 3, 2000), np.arange(2 ** 24 - 4, 2 ** 24 + 12), np.arange(2 ** 26 + 1, 2 ** 26 + 19)]))):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        p = S.room_params(320, 240); p.miplevel = lod
+        if D == 512:
+            pyr = np.zeros(D ** 3, np.uint32); pyr[ids[::3]] = 0xFF336699        # virtual zeros; a few texels set
+        else:
+            lv = [voxel_volume(D, 17, fill=0.3, counts=False)]
+            for l in range(Lv - 1):
+                d = D >> l
+                dst = np.zeros((d // 2) ** 3, np.uint32); O.lib().orc_mip(d, ptr(lv[-1]), ptr(dst), 0); lv.append(dst)
+            pyr = np.concatenate(lv)
+        n = len(ids)
+        world, color, clip, emitted = np.zeros((n, 3), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 84), np.float32), np.zeros(n, np.int32)
+        if impl == "glsl":
+            v7 = np.zeros((n, 7), np.float32)
+            glsl().glsl_debug_voxels_vert(C.byref(p), D, Lv, ptr(pyr), ptr(ids), n, ptr(v7))
+            g85 = np.zeros((n, 85), np.float32)
+            glsl().glsl_debug_voxels_geom(C.byref(p), D, ptr(v7), n, ptr(g85))
+            world, color, emitted, clip = v7[:, :3].copy(), v7[:, 3:].copy(), g85[:, 0].astype(np.int32), g85[:, 1:].copy()
+        else:
+            for i, vid in enumerate(ids):
+                O.lib().orc_debug_voxel_vertices(C.byref(p), D, C.c_uint(int(vid)), ptr(world[i]), ptr(clip[i]))
+                O.lib().orc_debug_voxel_color(C.byref(p), D, Lv, ptr(pyr), C.c_uint(int(vid)), ptr(color[i]))
+            emitted = np.where(color[:, 3] > 0, 21, 0).astype(np.int32)              # debugVoxels.geom:46: nothing for an empty voxel
+            clip[emitted == 0] = 0
+        out[f"dbgvox_{name}_world"] = world.view(np.uint32).reshape(-1)
+        out[f"dbgvox_{name}_color"] = color.view(np.uint32).reshape(-1)
+        out[f"dbgvox_{name}_emitted"] = emitted
+        out[f"dbgvox_{name}_clip"] = np.ascontiguousarray(clip).view(np.uint32).reshape(-1)
+    return out
+
+
+GOLD_DBGVOX = os.path.join(ROOT, "tests", "golden", "glsl_ref_debug_voxels.npz")
+
+
+@live
+def test_oracle_debug_voxel_stages_equal_the_reference_glsl_compiled_as_cpp():
+    a, b = run_debug_voxel_cases("oracle"), run_debug_voxel_cases("glsl")
+    compare(a, b, "oracle vs compiled debugVoxels.vert / debugVoxels.geom")
+    assert 0 < (a["dbgvox_d64_point_emitted"] > 0).mean() < 1 and (a["dbgvox_d64_lod1_6_emitted"] > 0).mean() > 0.9
+    w = a["dbgvox_d512_float_ids_world"].reshape(-1, 3)
+    assert len(np.unique(w[2000:2016], axis=0)) < 16, "ids around 2^24 must collapse (float(gl_InstanceID))"
+
+
+def test_oracle_debug_voxel_stages_equal_the_committed_outputs_of_the_reference_glsl():
+    compare(run_debug_voxel_cases("oracle"), dict(np.load(GOLD_DBGVOX)), "oracle vs tests/golden/glsl_ref_debug_voxels.npz")

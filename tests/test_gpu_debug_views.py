@@ -97,3 +97,41 @@ def test_pipelined_image_readback_is_ordered_with_the_next_frame():
     g.read_image_wait(block_host=False)                          # nothing pending: a no-op
     assert np.array_equal(g.read_image(), want_a)                # the blocking call still works (image of the last frame: pa)
     g.close()
+
+
+def test_debug_voxels_cubes_match_the_oracle():
+    """Application::debugVoxels (Application.cpp:1222-1275, debugVoxels.vert/.geom/.frag): the traced pyramid's non-empty voxels as depth-tested,
+    back-face-culled cubes.  At lod <= 0.5 the voxel colours are texel fetches: the image must equal the oracle's to the last bit (same
+    rasteriser, same depth rule, same draw order); at a fractional lod the texture unit filters with 8-bit weights: >= 45 dB."""
+    from vct_b200.pipeline import Pipeline
+    sc = pbr_room()
+    g = Pipeline(sc, D, L, SS, W, H)
+    o = Oracle(sc, D, L, SS, W, H)
+    try:
+        base = S.room_params(W, H)
+        o.frame(base); g.frame(base)
+        shaded = g.read_image().copy()
+        report = {}
+        for name, kw in (("point", {"miplevel": 0.0}), ("color_volume", {"miplevel": 0.3, "draw_radiance": 0}), ("lod1_4", {"miplevel": 1.4}), ("lod3", {"miplevel": 3.0})):
+            p = S.room_params(W, H)
+            for k, v in kw.items():
+                setattr(p, k, v)
+            o.debug_voxels(p); g.debug_voxels(p)
+            img = g.read_image()
+            assert np.unique(o.image).size > 20, name
+            report[name] = (psnr(img, o.image), int((img != o.image).sum()))
+        print(report)
+        assert report["point"][1] == 0 and report["color_volume"][1] == 0, report
+        assert report["lod1_4"][0] >= 45.0 and report["lod3"][0] >= 45.0, report
+        # a camera inside the volume: cubes cut by the near plane and triangles hundreds of pixels wide (the queued path)
+        p = S.room_params(W, H)
+        cam = P.Camera(position=(0.2, -0.3, 0.1), front=(-0.65, -0.25, -0.72))
+        q = P.default_params(W, H, cam, sc.lights[0], voxel_min=-1.5, voxel_max=1.5)
+        p.projection, p.view, p.pv, p.eye = q.projection, q.view, q.pv, q.eye
+        o.debug_voxels(p); g.debug_voxels(p)
+        img = g.read_image()
+        assert int((img != o.image).sum()) == 0 and np.unique(img).size > 20
+        g.frame(base)
+        assert np.array_equal(g.read_image(), shaded)
+    finally:
+        g.close()

@@ -471,7 +471,7 @@ int vct_destroy(vct_ctx* c) {
     free_volumes(c);
     vctk_xchg_free(c);
     for (void* p : {(void*)c->d_occ, (void*)c->d_warpmap, (void*)c->d_wlo, (void*)c->d_whi, (void*)c->d_shadow_base, c->d_shadow_mm, (void*)c->d_inject_list, (void*)c->d_vis, (void*)c->d_image, c->d_frags, (void*)c->d_displaced, c->d_long_queue, c->d_huge_items, c->d_huge_aux, (void*)c->d_warp_scratch,
-                    c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters, (void*)c->d_trace_tiles,
+                    c->d_tile_queue, c->d_expand_queue, c->d_pixel_queue, c->d_frame_blob, (void*)c->d_counters, (void*)c->d_trace_tiles, c->d_dbg,
                     (void*)c->d_tex, (void*)c->d_mat, (void*)c->d_vertices, (void*)c->d_vactor, (void*)c->d_indices, (void*)c->d_trimat, (void*)c->d_wpos,
                     (void*)c->d_wnrm, (void*)c->d_wT, (void*)c->d_wB, c->d_setup})
         cudaFree(p);
@@ -501,6 +501,7 @@ int vct_remake(vct_ctx* c, int dim, int levels) { VCT_NO_GROUP(c, "vct_remake");
     VCT_CHECK(c, cudaStreamSynchronize(c->stream));
     free_volumes(c);
     vctk_xchg_free(c);
+    cudaFree(c->d_dbg); c->d_dbg = nullptr;                      // sized by dim
     c->D = dim; c->L = clamp_levels(dim, levels); c->cfg.dim = dim; c->cfg.levels = c->L;
     return make_volumes(c);
 }
@@ -623,6 +624,12 @@ int vct_cone_trace(vct_ctx* c, const vct_frame_params* p) { VCT_FAN(c, vct_cone_
     VCT_CHECK(c, cudaMemsetAsync(&c->d_counters->cone_steps, 0, sizeof(unsigned long long), c->stream));
     vct_prof_mark(c, "memset");
     return vctk_cone_trace(c);
+}
+// Application::debugVoxels (Application.cpp:1222-1275): the non-empty voxels of the pyramid the frame traces, as cubes, into the image buffer
+int vct_debug_voxels(vct_ctx* c, const vct_frame_params* p) { VCT_NO_GROUP(c, "vct_debug_voxels");
+    PASS_PROLOGUE;
+    if (!p->draw_radiance && !c->color_arr) { if (ensure_color_texture(c) || vctk_publish(c, VCT_VOL_COLOR)) return 1; }
+    return vctk_debug_voxels(c);
 }
 int vct_mip(vct_ctx* c, int which) { VCT_FAN(c, vct_mip(c, which));
     if (!c) return 1;

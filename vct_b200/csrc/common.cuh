@@ -160,6 +160,7 @@ struct vct_ctx {
     void* d_xchg = nullptr; size_t xchg_region_bytes = 0; unsigned xchg_cap = 0; unsigned* d_xchg_count = nullptr;
     vct_peer peer[VCT_MAX_PEERS]{}; bool peer_ipc[VCT_MAX_PEERS]{}; int peers_attached = 0; void* d_xchg_dst = nullptr;
     int mip_pushed_upto = 0;     // sharded frame: the mip chain of this frame stored levels 1..mip_pushed_upto into the peers' pyramids itself
+    void* d_dbg = nullptr;                                         // vct_debug_voxels: depth | order buffer, voxel list, big-triangle queue (allocated on first use)
     uint32_t* d_trace_tiles = nullptr; int n_trace_tiles = 0;      // own 64x64 screen tiles (x0 | y0 << 16) of the sharded cone trace
     std::vector<vct_ctx*> group;                                    // single-process multi-GPU: the other ranks' contexts (this one is rank 0)
     void* group_state = nullptr; bool in_fan = false;               // worker threads of the group (api.cu); true while a call is being fanned out
@@ -277,6 +278,7 @@ int vctk_visibility(vct_ctx*);
 int vctk_warpmap(vct_ctx*);
 int vctk_warpmap_floats(vct_ctx*);       // float4 copy behind the unorm16 warp map (d_warpmap + 4 * 32^3 ushorts)
 int vctk_cone_trace(vct_ctx*);
+int vctk_debug_voxels(vct_ctx*);   // debug_voxels.cu
 size_t vctk_image_rows(const vct_ctx*);
 int vctk_set_voxel_opacity(vct_ctx*, float);
 int vctk_temporal_radiance_filter(vct_ctx*, float);

@@ -81,6 +81,31 @@ __device__ __forceinline__ bool tri_cover(const TriSetup& s, int px, int py, flo
     l[0] = e0; l[1] = s.swapped ? e2 : e1; l[2] = s.swapped ? e1 : e2;
     return true;
 }
+// near-plane clip (z >= -w), intersections computed from the inside vertex (watertight across shared edges)
+__device__ __forceinline__ int clip_near(const RV in[3], RV out[2][3]) {
+    float d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d[i] = in[i].z + in[i].w;
+    RV poly[4]; int n = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int j = (i + 1) % 3;
+        const bool ii = d[i] >= 0.0f, jj = d[j] >= 0.0f;
+        if (ii) poly[n++] = in[i];
+        if (ii != jj) {
+            const RV a = ii ? in[i] : in[j], b = ii ? in[j] : in[i];
+            const float da = ii ? d[i] : d[j], db = ii ? d[j] : d[i];
+            const float t = da / (da - db);
+            RV r; r.x = (b.x - a.x) * t + a.x; r.y = (b.y - a.y) * t + a.y; r.z = (b.z - a.z) * t + a.z; r.w = (b.w - a.w) * t + a.w;
+            poly[n++] = r;
+        }
+    }
+    if (n < 3) return 0;
+    out[0][0] = poly[0]; out[0][1] = poly[1]; out[0][2] = poly[2];
+    if (n == 4) { out[1][0] = poly[0]; out[1][1] = poly[2]; out[1][2] = poly[3]; return 2; }
+    return 1;
+}
+
 // Multisample coverage (OpenGL 4.5 section 14.6.6): true if any sample of pixel (px, py) is covered by the triangle clipped to -1 <= z <= 1
 // (the same top-left rule and the same barycentric formula per sample; z(sample) = sum l_i z_i like the centre's clip test).  l = the
 // barycentrics AT THE PIXEL CENTRE, where the fragment's inputs are interpolated — extrapolated if the centre itself is outside.

@@ -68,7 +68,8 @@ int main(int argc, char** argv) {
         else if (a == "--view") {                                           // one of the reference's debug toggles (Overlay.cpp), by name
             need(i, 1); const std::string v = argv[++i];
             Settings& st = app.settings;
-            if (v == "voxels") st.drawVoxels = true; else if (v == "voxel-normals") st.drawVoxels = st.drawNormals = true;
+            if (v == "debug-voxels") st.debugVoxels = true;                  // Settings::debugVoxels: cubes (pass-by-pass render only)
+            else if (v == "voxels") st.drawVoxels = true; else if (v == "voxel-normals") st.drawVoxels = st.drawNormals = true;
             else if (v == "warp-texture") st.drawVoxels = st.debugWarpTexture = true; else if (v == "warp-texture-tc") st.drawVoxels = st.debugWarpTexture = st.toggle = true; else if (v == "normals") st.drawNormals = true; else if (v == "dominant-axis") st.drawDominantAxis = true;
             else if (v == "occlusion") st.debugOcclusion = true; else if (v == "indirect") st.debugIndirect = true; else if (v == "reflections") st.debugReflections = true;
             else if (v == "material-diffuse") st.debugMaterialDiffuse = true; else if (v == "material-roughness") st.debugMaterialRoughness = true;

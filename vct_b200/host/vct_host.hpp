@@ -98,6 +98,7 @@ struct Settings {
     // debug views, Application.h:40-60 (all false by default); frameParams() folds them into vct_frame_params::debug_view
     int drawVoxels = false, drawNormals = false, drawDominantAxis = false, debugOcclusion = false, debugIndirect = false, debugReflections = false;
     int debugMaterialDiffuse = false, debugMaterialRoughness = false, debugMaterialMetallic = false;
+    int debugVoxels = false;                        // Application.h:50: the voxels as cubes instead of the frame's render passes (Application.cpp:923-928)
     int debugWarpTexture = false, toggle = false;   // Application.h:54, :180: sub-views of drawVoxels (phong.frag:354-357)
     float miplevel = 0.0f;
     int voxelizeTesselation = false;    // Application.h:85 (reference default true; this host defaults to the north star's raster path)
@@ -358,8 +359,11 @@ public:
         if (s.voxelFillHoles) ok &= ck(vct_fill_holes(vct.ctx, &p));   // :839-875
         ok &= ck(vct_mip(vct.ctx, VCT_VOL_RADIANCE));                  // :877-902  mipmapTimer
         if (s.mipColorChain || !s.drawRadiance) ok &= ck(vct_mip(vct.ctx, VCT_VOL_COLOR));   // :903-917
-        ok &= ck(vct_gbuffer(vct.ctx, &p));                            // :936-965  depth prepass
-        ok &= ck(vct_cone_trace(vct.ctx, &p));                         // :967-1067 renderTimer
+        if (s.debugVoxels) ok &= ck(vct_debug_voxels(vct.ctx, &p));     // :923-928  instead of the prepass and the shading pass
+        else {
+            ok &= ck(vct_gbuffer(vct.ctx, &p));                        // :936-965  depth prepass
+            ok &= ck(vct_cone_trace(vct.ctx, &p));                     // :967-1067 renderTimer
+        }
         ok &= ck(vct_get_counters(vct.ctx, &voxelizeInfo));            // Overlay.cpp:104-110
         return ok;
     }

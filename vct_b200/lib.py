@@ -13,7 +13,7 @@ SYMBOLS = [
     "vct_create", "vct_destroy", "vct_remake", "vct_last_error", "vct_upload_mesh", "vct_upload_texture",
     "vct_set_material", "vct_set_actor_transform", "vct_set_lights", "vct_shadowmap", "vct_occupancy", "vct_warpmap",
     "vct_voxelize", "vct_transfer", "vct_inject", "vct_fill_holes", "vct_mip", "vct_mip_kernel", "vct_exchange", "vct_gbuffer",
-    "vct_cone_trace", "vct_frame", "vct_gi_passes", "vct_set_voxel_opacity", "vct_temporal_radiance_filter",
+    "vct_cone_trace", "vct_debug_voxels", "vct_frame", "vct_gi_passes", "vct_set_voxel_opacity", "vct_temporal_radiance_filter",
     "vct_filter3d", "vct_normalize_voxels_f16", "vct_read_image", "vct_read_volume", "vct_write_volume",
     "vct_read_shadowmap", "vct_write_shadowmap", "vct_read_visibility", "vct_get_counters", "vct_get_timings",
     "vct_get_cone_steps", "vct_sync", "vct_device_ptr", "vct_level_bytes", "vct_stream", "vct_launch_count",
@@ -71,7 +71,7 @@ def load():
         "vct_frame_was_sparse": (ci, [vp]), "vct_mask_parity": (ci, [vp]), "vct_slab_stripe": (ci, [vp]),
     }
     for name in ("vct_shadowmap", "vct_occupancy", "vct_warpmap", "vct_voxelize", "vct_transfer", "vct_inject", "vct_fill_holes",
-                 "vct_gbuffer", "vct_cone_trace", "vct_frame", "vct_gi_passes"):
+                 "vct_gbuffer", "vct_cone_trace", "vct_debug_voxels", "vct_frame", "vct_gi_passes"):
         sig[name] = (ci, [vp, pp])
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -90,6 +90,7 @@ class Pipeline:
         self._ck(self.lib.vct_exchange_import(self.h, rank, C.create_string_buffer(handle, P.EXCHANGE_HANDLE_BYTES)))
     def gbuffer(self, p): self._ck(self.lib.vct_gbuffer(self.h, C.byref(p)))
     def cone_trace(self, p): self._ck(self.lib.vct_cone_trace(self.h, C.byref(p)))
+    def debug_voxels(self, p): self._ck(self.lib.vct_debug_voxels(self.h, C.byref(p)))
     def frame(self, p): self._ck(self.lib.vct_frame(self.h, C.byref(p)))
     def gi_passes(self, p): self._ck(self.lib.vct_gi_passes(self.h, C.byref(p)))
     def sync(self): self._ck(self.lib.vct_sync(self.h))
