@@ -114,6 +114,8 @@ def test_debug_voxels_cubes_match_the_oracle():
         report = {}
         for name, kw in (("point", {"miplevel": 0.0}), ("color_volume", {"miplevel": 0.3, "draw_radiance": 0}), ("lod1_4", {"miplevel": 1.4}), ("lod3", {"miplevel": 3.0})):
             p = S.room_params(W, H)
+            out = P.default_params(W, H, P.Camera(position=(3.4, 2.2, 3.9), front=(-0.62, -0.38, -0.69)), sc.lights[0], voxel_min=-1.5, voxel_max=1.5)
+            p.projection, p.view, p.pv, p.eye = out.projection, out.view, out.pv, out.eye       # from outside: the whole volume as cubes
             for k, v in kw.items():
                 setattr(p, k, v)
             o.debug_voxels(p); g.debug_voxels(p)
@@ -123,11 +125,8 @@ def test_debug_voxels_cubes_match_the_oracle():
         print(report)
         assert report["point"][1] == 0 and report["color_volume"][1] == 0, report
         assert report["lod1_4"][0] >= 45.0 and report["lod3"][0] >= 45.0, report
-        # a camera inside the volume: cubes cut by the near plane and triangles hundreds of pixels wide (the queued path)
+        # the frame's own camera, inside the volume: cubes cut by the near plane and triangles hundreds of pixels wide (the queued path)
         p = S.room_params(W, H)
-        cam = P.Camera(position=(0.2, -0.3, 0.1), front=(-0.65, -0.25, -0.72))
-        q = P.default_params(W, H, cam, sc.lights[0], voxel_min=-1.5, voxel_max=1.5)
-        p.projection, p.view, p.pv, p.eye = q.projection, q.view, q.pv, q.eye
         o.debug_voxels(p); g.debug_voxels(p)
         img = g.read_image()
         assert int((img != o.image).sum()) == 0 and np.unique(img).size > 20
