@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """A small whole frame (room scene, 32^3, 128x96, 256^2 shadow map) in one voxeliser mode, for compute-sanitizer:
-usage: sanitize_frame.py det|cas|max|tess|warp|long|huge [frames]   (prints a checksum of the volumes and the image)
+usage: sanitize_frame.py det|cas|max|tess|warp|long|huge|cubes [frames]   (prints a checksum of the volumes and the image)
 long / huge: 300 / 1300 coincident quads on a 32^3 grid -> per-voxel lists for k_voxel_resolve_medium / the k_voxel_huge_* kernels."""
 import os, sys, zlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -36,6 +36,8 @@ for k in range(frames):
             raise
         print("expected once:", str(e)[:90])
         g.frame(p)
+if mode == "cubes":                             # Application::debugVoxels after the frames (vct_debug_voxels)
+    g.debug_voxels(p)
 g.sync()
 crc = zlib.crc32(g.read_volume(P.VOL_COLOR).tobytes()) ^ zlib.crc32(g.read_volume(P.VOL_RADIANCE).tobytes()) ^ zlib.crc32(g.read_image().tobytes())
 i = g.counters()
