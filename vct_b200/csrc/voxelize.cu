@@ -442,7 +442,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_voxel_tiles(VoxArgs a) {
     // One loop, one call site of candidate() (code size).  A warp first takes the tiles of multi-tile triangles, one 8x4 tile per step
     // (one lane per pixel), round-robin over all warps; then the single-tile triangles, 32 per chunk, their candidate pixels concatenated.
     const unsigned n_tiles = min(*a.q.tile_count, a.q.tile_cap), n_items = min(*a.q.pixel_count, a.q.pixel_cap);
-    unsigned item = gw, base = gw * 32u;
+    // small items per chunk: 32 when there is enough work for every warp, fewer otherwise — a warp works through its chunk's candidates 32 at
+    // a time with a dependent fetch chain per step, so spreading a small scene's items over all warps shortens the kernel
+    const unsigned per = min(32u, max(1u, (n_items + warps - 1u) / warps));
+    unsigned item = gw, base = gw * per;
     uint32_t cslot = 0; int cox = 0, coy = 0, ciw = 1, cexcl = 0, total = 0, c0 = 0;        // the current chunk of small items (one per lane)
     for (;;) {
         bool cv; uint32_t slot; int px, py;
@@ -454,14 +457,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_voxel_tiles(VoxArgs a) {
             if (c0 >= total) {                               // next chunk: one item per lane, prefix sum of the candidate counts
                 if (base >= n_items) break;
                 int cnt = 0; cslot = 0; cox = 0; coy = 0; ciw = 1;
-                if (base + lane < n_items) {
+                if ((unsigned)lane < per && base + lane < n_items) {
                     const uint2 it = __ldg(a.q.pixels + base + lane);
                     cslot = it.x; cox = (int)(it.y & 0xFFFFu); coy = (int)(it.y >> 16);
                     const int4 bb = *reinterpret_cast<const int4*>(&a.setups[cslot].s.x0);      // x0, x1, y0, y1
                     ciw = min(kTileW, bb.y - cox + 1);
                     cnt = ciw * min(kTileH, bb.w - coy + 1);
                 }
-                base += warps * 32u;
+                base += warps * per;
                 int inc = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
