@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2 (or N) GPUs: interleaved stripes (VCT_SLAB_STRIPE=16) against contiguous slabs — parity tests, then config 3 / 4 bench lines both ways
-TAG=${1:-r02l}
+TAG=${1:-ab}
 N=$(nvidia-smi -L | wc -l)
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_sharded.py tests/test_gpu_modes.py -m gpu -q -p no:cacheprovider 2>&1 | tail -15 > gpurun_out/${TAG}_pytest_contiguous.txt
