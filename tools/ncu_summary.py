@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an `ncu --page raw --csv` dump: one block per kernel launch with the metrics the roofline needs."""
 import csv, sys
-rows = list(csv.reader(open(sys.argv[1])))
+rows = list(csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')))       # (an ncu --log-file starts with ==PROF== lines)
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 want = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',

@@ -4,7 +4,7 @@ name: the capture runs three frames and the last one is a steady-state sparse fr
 roofline.tex_pipe; "k_cone_trace__cone_steps" = the cone steps of the captured frame, from the bench line of the same build, is
 kept from the previous file).  usage: ncu_traffic.py <raw.csv> <out.json>"""
 import csv, json, re, sys
-rows = list(csv.reader(open(sys.argv[1])))
+rows = list(csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')))       # (an ncu --log-file starts with ==PROF== lines)
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
