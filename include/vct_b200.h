@@ -261,6 +261,8 @@ int  vct_read_image(vct_ctx*, void* rgba8 /* width*height*4, row 0 = bottom like
 int  vct_read_image_async(vct_ctx*, void* pinned_rgba8);
 int  vct_read_image_wait(vct_ctx*, int block_host);
 int  vct_read_volume(vct_ctx*, int which, int level, void* out);   /* RGBA8 words / u32 occupancy / u16x4 warpmap / f16x4 */
+/* (multi-device handle: a level is assembled from the devices' own z layers; the levels above the sharded ones — see vct_slab_stripe — exist whole
+ * only in the TRACED pyramid, computed on every device after the exchange, and are read from device 0) */
 int  vct_write_volume(vct_ctx*, int which, int level, const void* in);   /* test hook: seed a volume */
 int  vct_read_shadowmap(vct_ctx*, float* depth /* S*S */);
 int  vct_write_shadowmap(vct_ctx*, const float* depth);
