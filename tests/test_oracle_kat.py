@@ -360,3 +360,35 @@ def test_voxelize_multiplier_scales_the_viewport_not_the_grid():
     p.voxelize_multiplier = 0.5
     o.voxelize(p)
     assert 0.2 * n1 < o.info.total_fragments < 0.3 * n1
+
+
+# ------------------------------------------------------------------ Application::debugVoxels: one voxel seen head-on
+def test_debug_voxels_single_cube_head_on():
+    """One occupied voxel of an 8^3 grid over +-1, the camera on its axis looking down -z: only the cube's near face is visible (the far one
+    is back-facing and culled, the sides are edge-on), so the image is one axis-aligned rectangle whose pixel set follows from the projection
+    matrix by hand — the face spans [0, 0.25]^2 at z = 0.25, 2.875 in front of the eye."""
+    D, W, H = 8, 200, 120
+    cam = P.Camera(position=(0.125, 0.125, 3.125), front=(0.0, 0.0, -1.0))
+    light = P.make_light(position=(0.0, 3.0, 0.0), direction=(-0.2, -1.0, -0.1), shadow_caster=False, type_=1)
+    p = P.default_params(W, H, cam, light, voxel_min=-1.0, voxel_max=1.0)
+    vol = np.zeros(D ** 3, np.uint32)
+    vol[(4 * D + 4) * D + 4] = 0xFF336699                          # voxel (4, 4, 4): texcoords [0.5, 0.625)^3 -> world [0, 0.25)^3
+    image = np.zeros(W * H, np.uint32)
+    ol.lib().orc_debug_voxels(C.byref(p), W, H, D, 1, ol.ptr(vol), ol.ptr(image))
+    img = image.reshape(H, W)
+    clear = img[0, 0]
+    ys, xs = np.nonzero(img != clear)
+    assert len(xs) > 0 and np.unique(img[img != clear]).tolist() == [0xFF336699]
+    proj = np.array(p.projection[:], np.float64).reshape(4, 4).T   # column-major float[16]
+    fx, fy = proj[0, 0], proj[1, 1]
+    half = 0.125 / 2.875                                           # half extent of the near face over its distance
+    x_lo, x_hi = (0.5 - 0.5 * fx * half) * W, (0.5 + 0.5 * fx * half) * W      # window-space edges of the face (the eye looks at its centre)
+    y_lo, y_hi = (0.5 - 0.5 * fy * half) * H, (0.5 + 0.5 * fy * half) * H
+    want_x = [i for i in range(W) if x_lo < i + 0.5 < x_hi]
+    want_y = [j for j in range(H) if y_lo < j + 0.5 < y_hi]
+    assert sorted(set(xs.tolist())) == want_x and sorted(set(ys.tolist())) == want_y
+    assert len(xs) == len(want_x) * len(want_y)                    # a filled rectangle, nothing else
+    # an empty volume draws nothing; a fully transparent colour (alpha 0) draws nothing either (debugVoxels.geom:46)
+    vol[:] = 0; vol[0] = 0x00FFFFFF
+    ol.lib().orc_debug_voxels(C.byref(p), W, H, D, 1, ol.ptr(vol), ol.ptr(image))
+    assert (image == clear).all()
